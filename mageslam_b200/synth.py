@@ -1,0 +1,196 @@
+"""Seeded synthetic inputs for the two hot paths. numpy only -- usable on the GPU box.
+
+Frames: blurred-noise images (about 1e4 FAST candidates at threshold 10-20) and a structured scene (filled
+rectangles / discs on a gradient with fine texture) viewed through a smooth homography trajectory.
+BA problems: K cameras on an arc looking at P points in a frustum-visible box, d observations per point
+(template: reference Dependencies/g2o/g2o/examples/ba/ba_demo.cpp:114-200).
+"""
+import numpy as np
+
+
+def _gauss_kernel(sigma):
+    r = max(1, int(3 * sigma + 0.5))
+    x = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-0.5 * (x / sigma) ** 2)
+    return k / k.sum()
+
+
+def _sep_filter(img, k):
+    r = len(k) // 2
+    p = np.pad(img, ((0, 0), (r, r)), mode="reflect")
+    out = np.zeros_like(img, dtype=np.float64)
+    for i, kv in enumerate(k):
+        out += kv * p[:, i:i + img.shape[1]]
+    p = np.pad(out, ((r, r), (0, 0)), mode="reflect")
+    out2 = np.zeros_like(out)
+    for i, kv in enumerate(k):
+        out2 += kv * p[i:i + img.shape[0], :]
+    return out2
+
+
+def noise_frame(seed, w=640, h=480, sigma=1.5):
+    """uniform noise -> Gaussian sigma -> min-max normalise to [0,255]."""
+    rng = np.random.default_rng(seed)
+    f = _sep_filter(rng.random((h, w)), _gauss_kernel(sigma))
+    f = (f - f.min()) / (f.max() - f.min())
+    return np.round(f * 255.0).astype(np.uint8)
+
+
+def structured_scene(seed, w=1280, h=960, nshapes=160):
+    """Filled rectangles / discs on a gradient plus low-amplitude texture: strong, repeatable corners."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = 60.0 + 80.0 * xx / w + 40.0 * yy / h
+    for _ in range(nshapes):
+        val = float(rng.integers(10, 246))
+        if rng.random() < 0.6:
+            x0 = int(rng.integers(0, w - 20)); y0 = int(rng.integers(0, h - 20))
+            ww = int(rng.integers(12, 140)); hh = int(rng.integers(12, 140))
+            img[y0:y0 + hh, x0:x0 + ww] = val
+        else:
+            cx = int(rng.integers(0, w)); cy = int(rng.integers(0, h)); rad = int(rng.integers(6, 60))
+            y0, y1 = max(0, cy - rad), min(h, cy + rad + 1)
+            x0, x1 = max(0, cx - rad), min(w, cx + rad + 1)
+            sub = img[y0:y1, x0:x1]
+            m = (yy[y0:y1, x0:x1] - cy) ** 2 + (xx[y0:y1, x0:x1] - cx) ** 2 <= rad * rad
+            sub[m] = val
+    tex = _sep_filter(rng.random((h, w)), _gauss_kernel(1.0))
+    img += 40.0 * (tex - tex.mean()) / (tex.std() + 1e-9) * 0.5
+    return np.clip(np.round(img), 0, 255).astype(np.uint8)
+
+
+def _warp(scene, Hm, w, h):
+    """Sample scene at Hm * (x, y, 1) with bilinear interpolation (numpy)."""
+    ys, xs = np.mgrid[0:h, 0:w].astype(np.float64)
+    X = Hm[0, 0] * xs + Hm[0, 1] * ys + Hm[0, 2]
+    Y = Hm[1, 0] * xs + Hm[1, 1] * ys + Hm[1, 2]
+    Z = Hm[2, 0] * xs + Hm[2, 1] * ys + Hm[2, 2]
+    X /= Z; Y /= Z
+    sh, sw = scene.shape
+    X = np.clip(X, 0, sw - 1.001); Y = np.clip(Y, 0, sh - 1.001)
+    x0 = np.floor(X).astype(np.int64); y0 = np.floor(Y).astype(np.int64)
+    fx = X - x0; fy = Y - y0
+    s = scene.astype(np.float64)
+    v = (s[y0, x0] * (1 - fx) * (1 - fy) + s[y0, x0 + 1] * fx * (1 - fy) +
+         s[y0 + 1, x0] * (1 - fx) * fy + s[y0 + 1, x0 + 1] * fx * fy)
+    return np.clip(np.round(v), 0, 255).astype(np.uint8)
+
+
+def video_frames(n, w=640, h=480, seed=0):
+    """n frames of the structured scene through a smooth (seeded) homography trajectory; uint8 [n, h, w]."""
+    rng = np.random.default_rng(seed + 1000)
+    scene = structured_scene(seed, 2 * w, 2 * h)
+    ph = rng.random(6) * 2 * np.pi
+    out = np.empty((n, h, w), np.uint8)
+    for t in range(n):
+        a = 0.08 * np.sin(0.021 * t + ph[0])
+        s = 1.0 + 0.15 * np.sin(0.013 * t + ph[1])
+        tx = 0.5 * w + 0.35 * w * np.sin(0.017 * t + ph[2])
+        ty = 0.5 * h + 0.35 * h * np.sin(0.011 * t + ph[3])
+        p0 = 1e-5 * np.sin(0.009 * t + ph[4]); p1 = 1e-5 * np.sin(0.007 * t + ph[5])
+        c, sn = np.cos(a) * s, np.sin(a) * s
+        Hm = np.array([[c, -sn, tx], [sn, c, ty], [p0, p1, 1.0]])
+        out[t] = _warp(scene, Hm, w, h)
+    return out
+
+
+def shifted_noisy(img, dx=3, dy=2, amp=2, seed=1):
+    """Same frame shifted by (dx, dy) px with +-amp grey-level noise (SURVEY 8(d) config 1 self-match)."""
+    rng = np.random.default_rng(seed)
+    out = np.roll(np.roll(img, dy, axis=0), dx, axis=1).astype(np.int16)
+    out += rng.integers(-amp, amp + 1, size=img.shape, dtype=np.int16)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def _rot(rx, ry, rz):
+    cx, sx, cy, sy, cz, sz = np.cos(rx), np.sin(rx), np.cos(ry), np.sin(ry), np.cos(rz), np.sin(rz)
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return Rz @ Ry @ Rx
+
+
+def ba_problem(K=10, P=2000, obs_per_point=4, seed=1, n_fixed=2, f=500.0, cx=320.0, cy=240.0,
+               pixel_sigma=0.5, point_sigma=0.02, pose_sigma=0.01, outlier_frac=0.0, loop=False, info_mode="one"):
+    """Synthetic BA window. Returns a dict of float32 arrays in the BundlerLib conventions:
+    cam_pos[K,3] + cam_rot[K,9] (column-major 3x3) = world->camera (view) transform (reference BundlerLib.cpp:261-276),
+    intrinsics[K,4] = (cx, cy, fx, fy), fixed[K], points[P,3], obs_uv[E,2], obs_cam[E], obs_pt[E], obs_info[E]."""
+    rng = np.random.default_rng(seed)
+    cams_R = np.zeros((K, 3, 3)); cams_t = np.zeros((K, 3))
+    centers = np.zeros((K, 3))
+    for k in range(K):
+        if loop:
+            ang = 2 * np.pi * k / K
+            C = np.array([12.0 * np.cos(ang), 0.3 * np.sin(3 * ang), 12.0 * np.sin(ang)])
+            yaw = -ang + np.pi / 2 + np.pi / 2     # look outward-tangent mix
+            Rwc = _rot(0.0, yaw, 0.0)
+        else:
+            C = np.array([0.25 * (k - (K - 1) / 2.0), 0.02 * np.sin(k), 0.05 * np.cos(0.7 * k)])
+            Rwc = _rot(0.01 * np.sin(k), 0.03 * (k - (K - 1) / 2.0) / max(K, 1), 0.01 * np.cos(k))
+        centers[k] = C
+        R = Rwc.T                      # world -> camera
+        cams_R[k] = R
+        cams_t[k] = -R @ C
+    pts = np.zeros((P, 3))
+    obs_cam = np.zeros(P * obs_per_point, np.int32); obs_pt = np.zeros(P * obs_per_point, np.int32)
+    obs_uv = np.zeros((P * obs_per_point, 2))
+    e = 0
+    for i in range(P):
+        for _try in range(200):
+            if loop:
+                k0 = int(rng.integers(0, K))
+                depth = rng.uniform(3.0, 8.0)
+                local = np.array([rng.uniform(-1.5, 1.5), rng.uniform(-1.0, 1.0), depth])
+                X = cams_R[k0].T @ (local - cams_t[k0])
+                cand = [(k0 + j) % K for j in range(-(obs_per_point // 2), obs_per_point - obs_per_point // 2)]
+            else:
+                X = np.array([rng.uniform(-3.0, 3.0), rng.uniform(-2.0, 2.0), rng.uniform(3.0, 8.0)])
+                cand = list(rng.permutation(K))
+            seen = []
+            for k in cand:
+                Xc = cams_R[k] @ X + cams_t[k]
+                if Xc[2] <= 0.5:
+                    continue
+                u = f * Xc[0] / Xc[2] + cx; v = f * Xc[1] / Xc[2] + cy
+                if 0 <= u < 2 * cx and 0 <= v < 2 * cy:
+                    seen.append((int(k), u, v))
+                if len(seen) == obs_per_point:
+                    break
+            if len(seen) == obs_per_point:
+                break
+        else:
+            raise RuntimeError("could not place point %d" % i)
+        pts[i] = X
+        for k, u, v in seen:
+            obs_cam[e] = k; obs_pt[e] = i
+            obs_uv[e] = (u + rng.normal(0, pixel_sigma), v + rng.normal(0, pixel_sigma))
+            e += 1
+    E = e
+    if outlier_frac > 0:
+        bad = rng.random(E) < outlier_frac
+        obs_uv[bad] += rng.uniform(-60, 60, size=(int(bad.sum()), 2))
+    pts_init = pts + rng.normal(0, point_sigma, size=pts.shape)
+    cam_pos = np.zeros((K, 3), np.float32); cam_rot = np.zeros((K, 9), np.float32)
+    fixed = np.zeros(K, np.int32)
+    for k in range(K):
+        R, t = cams_R[k], cams_t[k]
+        if k < n_fixed:
+            fixed[k] = 1
+        else:
+            dR = _rot(*rng.normal(0, pose_sigma * 0.2, 3))
+            R = dR @ R
+            t = t + rng.normal(0, pose_sigma, 3)
+        cam_pos[k] = t
+        cam_rot[k] = R.T.reshape(-1)          # column-major flattening of R
+    if info_mode == "one":
+        info = np.ones(E, np.float32)
+    else:                                      # MapPointRefinementConfidence(0..5), reference Map/MappingMath.h:42-49
+        rc = rng.integers(0, 6, size=P)
+        conf = 1.0 - 1.0 / (1.5 + rc) ** 2
+        info = conf[obs_pt[:E]].astype(np.float32)
+    return dict(cam_pos=cam_pos, cam_rot=cam_rot,
+                intrinsics=np.tile(np.array([cx, cy, f, f], np.float32), (K, 1)), fixed=fixed,
+                points=pts_init.astype(np.float32), obs_uv=obs_uv[:E].astype(np.float32),
+                obs_cam=obs_cam[:E].copy(), obs_pt=obs_pt[:E].copy(), obs_info=info,
+                true_points=pts.astype(np.float32))

@@ -1,0 +1,85 @@
+/*
+ * oracle/orb_oracle.h -- TEST INFRASTRUCTURE ONLY (CPU restatement of the reference ORB front-end + Match).
+ *
+ * Nothing under mageslam_b200/ may include, link or call this. Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs use it, and only as the checker / the CPU arm.
+ *
+ * Parity status: the reference ships no tests or golden vectors for this path and its
+ * OrbDetector cannot be compiled here (needs OpenCV C++ 3.4 headers, not vendored). The restatement is pinned
+ * against stock OpenCV 4.13 primitives through tests/test_oracle_vs_cv2.py (resize, GaussianBlur, fastAtan2,
+ * FAST-9/16+NMS, BFMatcher::radiusMatch) and against golden vectors generated from it (tests/golden/).
+ * => "parity unpinned by the reference; pinned by cv2 cross-checks" (DESIGN.md section 3).
+ */
+#ifndef MAGE_ORB_ORACLE_H
+#define MAGE_ORB_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cv::KeyPoint memory layout (28 bytes) */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orc_keypoint;
+
+typedef struct { int32_t query, train; float distance; } orc_dmatch;
+
+/* The 14 OrbDetector constructor scalars, reference Image/OpenCVModified.h:68-82, same order. */
+typedef struct {
+    uint32_t gaussian_kernel_size;
+    uint32_t nfeatures;
+    float    scale_factor;
+    uint32_t nlevels;
+    uint32_t patch_size;
+    uint32_t fast_threshold;
+    int32_t  use_orientation;
+    float    feature_factor;
+    float    feature_strength;
+    int32_t  strong_response;
+    float    min_robust_factor;
+    float    max_robust_factor;
+    int32_t  num_cells_x;
+    int32_t  num_cells_y;
+} orc_orb_params;
+
+enum { ORC_ORDER_LIBSTDCXX = 0, ORC_ORDER_CANONICAL = 1 };
+
+/* DetectAndCompute. order_mode: 0 = literal std::nth_element (libstdc++) ordering, 1 = canonical ordering
+ * (stable raster order in RetainBestFeatures; full sort (r desc, strength desc, raster asc) in ANMS).
+ * Returns 0 on success, <0 on unsupported configuration. */
+int orc_orb_detect_and_compute(const orc_orb_params* p, const uint8_t* img, int w, int h, int stride,
+                               int order_mode, orc_keypoint* kps, uint8_t* desc, int capacity, int* count);
+
+/* --- stage-level entry points, used by the cv2 cross-check tests and by the stage parity tests --- */
+void  orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
+int   orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int ksize);
+float orc_fast_atan2(float y, float x);
+int   orc_cv_round_f(float v);
+/* FAST-9/16 + score + 3x3 NMS in raster order; returns number found (may exceed capacity; only capacity written) */
+int   orc_fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, orc_keypoint* out, int capacity);
+/* full score map (uint8, 0 for non-corners), no NMS */
+void  orc_fast9_score_map(const uint8_t* img, int w, int h, int stride, int threshold, uint8_t* score, int score_stride);
+/* level geometry: sizes[2*l]=w, sizes[2*l+1]=h, scales[l], nfeat[l]; returns 0 */
+int   orc_level_layout(const orc_orb_params* p, int w, int h, int* sizes, float* scales, int* nfeat);
+/* builds the chained pyramid into separately allocated level images (tightly packed, stride = level width);
+ * level_ptrs[l] must have room for w_l*h_l bytes. */
+int   orc_build_pyramid(const orc_orb_params* p, const uint8_t* img, int w, int h, int stride, uint8_t** level_ptrs);
+/* keypoint selection for ONE level given raster-ordered candidates (x, y, response); returns kept count.
+ * Applies RetainBestFeatures + ANMS exactly as ComputeKeyPoints does when n_in > n_keep. */
+int   orc_select_level(const orc_orb_params* p, orc_keypoint* kps, int n_in, int n_keep, int order_mode);
+/* ANMS suppression radii (r) for every input item, in input order (diagnostics / tie statistics). */
+int   orc_anms_radii(const orc_orb_params* p, const orc_keypoint* kps, int n_in, int n_keep, int* r_out);
+/* 30 x 1024 int8 pre-rotated pattern regenerated from row 0; patch 31 or 15. returns 0 or -1 */
+int   orc_brief_pattern(int patch_size, int8_t* out30x1024);
+int   orc_umax(int half_patch, int* umax /* half_patch+2 */);
+
+/* Match (reference Tracking/FeatureMatcher.cpp:61-190). masks may be NULL (= all true). out capacity >= nA. */
+int   orc_match(const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_t* descB, int nB, const uint8_t* maskB,
+                int max_hamming, int min_diff, orc_dmatch* out, int* count);
+int   orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

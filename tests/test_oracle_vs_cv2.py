@@ -1,0 +1,118 @@
+"""Pins the ORB/Match oracle against stock OpenCV 4.13 primitives (the reference ships no tests for this path).
+
+CPU only. Skipped if cv2 is not importable. The reference calls cv::resize / GaussianBlur / fastAtan2 / BFMatcher and
+its FAST_t<16> shares OpenCV's FAST lineage.
+"""
+import numpy as np
+import pytest
+
+cv2 = pytest.importorskip("cv2")
+
+from mageslam_b200 import synth
+from tests import oracle_orb as orc
+
+
+def test_cv_round_half_even():
+    for v, e in ((0.5, 0), (1.5, 2), (2.5, 2), (-0.5, 0), (-1.5, -2), (3.49, 3), (1e6 + 0.5, 1000000)):
+        assert orc.lib().orc_cv_round_f(v) == e
+
+
+def test_fast_atan2_matches_cv2():
+    rng = np.random.default_rng(0)
+    ys = rng.integers(-200000, 200001, 20000).astype(np.float32)
+    xs = rng.integers(-200000, 200001, 20000).astype(np.float32)
+    ys[:8] = [0, 0, -1, 1, 1, -1, 0, 5]; xs[:8] = [0, -1, 0, 1, 0, -1, 7, 0]
+    # the scalar cv::fastAtan2 is what the reference calls (OpenCVModified.cpp:435); cv2.phase's vectorised
+    # variant rounds differently and is NOT the reference arithmetic
+    ref = np.array([cv2.fastAtan2(float(y), float(x)) for y, x in zip(ys, xs)], np.float32)
+    got = np.array([orc.fast_atan2(y, x) for y, x in zip(ys, xs)], np.float32)
+    assert np.array_equal(ref.view(np.uint32), got.view(np.uint32))
+    assert abs(orc.fast_atan2(1, 1) - 44.990456) < 1e-5
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_resize_matches_cv2(seed):
+    rng = np.random.default_rng(seed)
+    for _ in range(6):
+        sw, sh = int(rng.integers(40, 700)), int(rng.integers(40, 500))
+        sc = float(rng.uniform(1.05, 2.2))
+        dw, dh = max(4, int(round(sw / sc))), max(4, int(round(sh / sc)))
+        src = rng.integers(0, 256, (sh, sw), dtype=np.uint8)
+        ref = cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(ref, orc.resize(src, dw, dh))
+
+
+def test_pyramid_chain_matches_cv2():
+    p = orc.tier_params()
+    img = synth.noise_frame(3)
+    levels = orc.build_pyramid(p, img)
+    sizes, scales, nfeat = orc.level_layout(p, 640, 480)
+    assert int(nfeat.sum()) == 2000 and len(levels) == 8
+    prev = img
+    for l in range(1, 8):
+        prev = cv2.resize(prev, (int(sizes[l][0]), int(sizes[l][1])), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(prev, levels[l]), l
+    # sizes follow cvRound(cols / (float)pow(sf, l))
+    for l in range(8):
+        s = np.float32(np.float64(np.float32(1.2)) ** l)
+        assert sizes[l][0] == int(np.rint(np.float32(640) / s)) and sizes[l][1] == int(np.rint(np.float32(480) / s))
+
+
+@pytest.mark.parametrize("ksize", [3, 5, 7, 9, 11, 13, 15])
+def test_gaussian_blur_matches_cv2(ksize):
+    rng = np.random.default_rng(ksize)
+    for shape in ((480, 640), (37, 53), (134, 179), (16, 9)):
+        src = rng.integers(0, 256, shape, dtype=np.uint8)
+        ref = cv2.GaussianBlur(src, (ksize, ksize), 2, sigmaY=2, borderType=cv2.BORDER_REFLECT_101)
+        assert np.array_equal(ref, orc.blur(src, ksize)), (ksize, shape)
+
+
+@pytest.mark.parametrize("thr,seed", [(10, 0), (20, 1), (4, 2), (40, 3)])
+def test_fast_matches_cv2(thr, seed):
+    img = synth.noise_frame(seed, 320, 240) if seed % 2 == 0 else synth.video_frames(1, 320, 240, seed)[0]
+    det = cv2.FastFeatureDetector_create(thr, True, cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    ref = det.detect(img)
+    got = orc.fast9(img, thr)
+    assert len(ref) == len(got) and len(got) > 50
+    r = np.array([(k.pt[0], k.pt[1], k.response) for k in ref], np.float32)
+    g = np.stack([got["x"], got["y"], got["response"]], 1)
+    assert np.array_equal(r, g)         # same keypoints, same raster order, same score
+
+
+def test_match_matches_cv2_pipeline():
+    rng = np.random.default_rng(5)
+    for n, flips, maxd, mind in ((300, 10, 30, 1), (500, 24, 40, 3), (64, 4, 30, 1), (200, 60, 64, 2)):
+        A = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        B = A.copy()[rng.permutation(n)]
+        # flip a few random bits per descriptor, and duplicate some rows to create ties
+        for i in range(n):
+            for b in rng.integers(0, 256, int(rng.integers(0, flips))):
+                B[i, b // 8] ^= np.uint8(1 << (b % 8))
+        B[: n // 20] = B[n // 20: 2 * (n // 20)]
+        bf = cv2.BFMatcher(cv2.NORM_HAMMING, False)
+        fwd = bf.radiusMatch(A, B, float(maxd), None, False)
+        bwd = bf.radiusMatch(B, A, float(maxd), None, False)
+
+        def best(rows):
+            out = {}
+            for q, row in enumerate(rows):
+                if len(row) == 0:
+                    continue
+                row = sorted(row, key=lambda m: m.distance)
+                if len(row) > 1 and row[1].distance - row[0].distance < mind:
+                    continue
+                out[q] = (row[0].trainIdx, row[0].distance)
+            return out
+        fb, bb = best(fwd), best(bwd)
+        ref = [(a, t, d) for a, (t, d) in sorted(fb.items()) if bb.get(t, (-1, 0))[0] == a]
+        got = orc.match(A, B, maxd, mind)
+        assert [(int(m["query"]), int(m["train"]), float(m["distance"])) for m in got] == ref
+        assert len(ref) > 0
+
+
+def test_descriptor_distance_is_popcount():
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
+        assert orc.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
+        assert orc.descriptor_distance(a, b) == int(cv2.norm(a, b, cv2.NORM_HAMMING))
