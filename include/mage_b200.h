@@ -1,0 +1,177 @@
+/*
+ * mage_b200.h -- C ABI of the B200-native (sm_100a) hot paths of MAGE-SLAM.
+ *
+ * One shared library (libmage_b200.so), plain pointers and sizes, status codes instead of exceptions.
+ * Each entry point names the reference interface it replaces ("ref" = microsoft/mageslam source tree):
+ *
+ *   ORB extract   ref Core/MAGESLAM/Source/Image/OpenCVModified.h:68-88   OrbDetector ctor + DetectAndCompute
+ *                 ref Core/MAGESLAM/Source/Image/OrbFeatureDetector.h:37  OrbFeatureDetector::Process
+ *   Match         ref Core/MAGESLAM/Source/Tracking/FeatureMatcher.h:68-77 Match
+ *                 ref Core/MAGESLAM/Source/Tracking/FeatureMatcher.h:134-136 GetDescriptorDistance
+ *   Bundle adj.   ref Dependencies/BundlerLib/Include/BundlerLib.h:20-66   class mage::BundlerLib
+ *
+ * Threading: a handle owns its device scratch and is used by one thread at a time (same contract as the
+ * reference objects: OrbDetector is re-entrant only with distinct thread_memory; one BundlerLib per thread).
+ * All functions return MAGE_OK (0) or a negative status; mage_last_error() returns a thread-local message.
+ * There is NO CPU fallback: without a CUDA device every compute entry point returns MAGE_ERR_CUDA.
+ */
+#ifndef MAGE_B200_H
+#define MAGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAGE_OK               0
+#define MAGE_ERR_INVALID     -1   /* bad argument (null pointer, size out of range, capacity too small) */
+#define MAGE_ERR_UNSUPPORTED -2   /* configuration the reference itself asserts on, or not built */
+#define MAGE_ERR_CUDA        -3   /* CUDA runtime error / no device */
+#define MAGE_ERR_OVERFLOW    -4   /* an internal candidate list overflowed (cannot happen with default sizing) */
+
+const char* mage_last_error(void);
+/* library / device probe: returns number of CUDA devices visible (>= 0) or MAGE_ERR_CUDA */
+int mage_device_count(void);
+const char* mage_version(void);
+
+/* ------------------------------------------------------------------------------------------------ ORB extract */
+
+/* cv::KeyPoint memory layout, 28 bytes (ref Image/ImageData.h keypoint buffer) */
+typedef struct mage_keypoint {
+    float   x, y;        /* level-0 pixel coordinates (pt) */
+    float   size;        /* patchSize * layerScale[octave] */
+    float   angle;       /* degrees [0,360], 0 when orientation is disabled */
+    float   response;    /* FAST score */
+    int32_t octave;
+    int32_t class_id;    /* always -1 */
+} mage_keypoint;
+
+/* The 14 OrbDetector constructor scalars in ctor order (ref Image/OpenCVModified.h:68-82,
+ * defaults ref MageSettings.h:151-167). */
+typedef struct mage_orb_params {
+    uint32_t gaussian_kernel_size;   /* odd, 1 (= no blur) .. 15; sigma is fixed at 2 as in the reference */
+    uint32_t nfeatures;
+    float    scale_factor;
+    uint32_t nlevels;
+    uint32_t patch_size;             /* 31 or 15 (pre-rotated BRIEF tables) */
+    uint32_t fast_threshold;
+    int32_t  use_orientation;
+    float    feature_factor;         /* featureFactorANMS */
+    float    feature_strength;       /* featureStrengthANMS */
+    int32_t  strong_response;        /* strongResponseANMS, must be > fast_threshold */
+    float    min_robust_factor;
+    float    max_robust_factor;
+    int32_t  num_cells_x;
+    int32_t  num_cells_y;
+} mage_orb_params;
+
+typedef struct mage_orb_s* mage_orb_t;
+
+/* Replaces the OrbDetector constructor. The handle owns device scratch for up to max_batch frames of
+ * width x height pixels (pyramids, candidate lists, tables). */
+int  mage_orb_create(const mage_orb_params* params, int width, int height, int max_batch, mage_orb_t* out);
+void mage_orb_destroy(mage_orb_t h);
+
+/* Replaces OrbDetector::DetectAndCompute for ONE host image (CV_8UC1, row stride in bytes).
+ * kps/desc are host buffers with room for `capacity` features (ImageData::maxFeatures); desc is 32 bytes each
+ * (ref Image/ORBDescriptor.h). Synchronous on return. stream may be NULL. */
+int  mage_orb_detect_and_compute(mage_orb_t h, const uint8_t* image, int width, int height, int stride,
+                                 mage_keypoint* kps, uint8_t* desc, int capacity, int* count, void* cuda_stream);
+
+/* Batched host variant: n frames (n <= max_batch), frame i at images + i*frame_stride. Outputs are
+ * [n][capacity] arrays, counts[n]. Host buffers should be pinned for full copy bandwidth. Synchronous. */
+int  mage_orb_detect_and_compute_batch(mage_orb_t h, const uint8_t* images, int n, int width, int height, int stride,
+                                       size_t frame_stride, mage_keypoint* kps, uint8_t* desc, int capacity,
+                                       int* counts, void* cuda_stream);
+
+/* Device-resident variant: inputs and outputs are device pointers, nothing leaves HBM, asynchronous on
+ * cuda_stream. d_images rows must be 4-byte aligned (stride % 4 == 0, base 16-byte aligned). */
+int  mage_orb_extract_device(mage_orb_t h, const uint8_t* d_images, int n, int width, int height, int stride,
+                             size_t frame_stride, mage_keypoint* d_kps, uint8_t* d_desc, int capacity,
+                             int* d_counts, void* cuda_stream);
+
+/* Level geometry the handle derived (ref OpenCVModified.cpp:795-811, :660-670); arrays of nlevels entries. */
+int  mage_orb_level_info(mage_orb_t h, int* widths, int* heights, float* scales, int* nfeatures_per_level);
+
+/* Debug/inspection taps used by the stage parity tests (device -> host copies of internal buffers of frame f). */
+int  mage_orb_debug_get_level(mage_orb_t h, int frame, int level, int blurred, uint8_t* out /* w*h, tight */);
+/* candidates after FAST+NMS+border cull of one level, sorted in raster order: packed (score<<24 | y*w+x) */
+int  mage_orb_debug_get_candidates(mage_orb_t h, int frame, int level, uint32_t* out, int capacity, int* count);
+
+/* ------------------------------------------------------------------------------------------------------ Match */
+
+/* cv::DMatch {queryIdx, trainIdx, distance}; imgIdx is not carried (always 0 in the reference's use). */
+typedef struct mage_dmatch { int32_t query_idx, train_idx; float distance; } mage_dmatch;
+
+typedef struct mage_matcher_s* mage_matcher_t;
+int  mage_matcher_create(int max_descriptors, int max_pairs, mage_matcher_t* out);
+void mage_matcher_destroy(mage_matcher_t m);
+
+/* Replaces Match(): two-way brute-force Hamming match with max distance, min best/second-best difference
+ * and cross-check; matches are emitted in ascending A index. masks may be NULL (= all true), else one byte
+ * per descriptor. `out` needs room for nA entries. Host buffers, synchronous. */
+int  mage_match_bf(mage_matcher_t m, const uint8_t* descA, int nA, const uint8_t* maskA,
+                   const uint8_t* descB, int nB, const uint8_t* maskB, int max_hamming, int min_hamming_diff,
+                   mage_dmatch* out, int* count, void* cuda_stream);
+
+/* Device-resident batched variant: pair p matches A = d_desc + a_index[p]*slot_stride (d_counts[a_index[p]]
+ * descriptors) against B likewise; a_index/b_index are host arrays of n_pairs entries. Outputs
+ * d_matches[p][capacity], d_match_counts[p]. Asynchronous. */
+int  mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_counts, size_t slot_stride,
+                          const int* a_index, const int* b_index, int n_pairs, int max_hamming, int min_hamming_diff,
+                          mage_dmatch* d_matches, int capacity, int* d_match_counts, void* cuda_stream);
+
+/* GetDescriptorDistance for n pairs of device-resident descriptors (a[i] vs b[i]) -> d_out[i]. */
+int  mage_descriptor_distance_device(const uint8_t* d_a, const uint8_t* d_b, int n, int* d_out, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------ Bundle adjustment */
+
+typedef struct mage_ba_s* mage_ba_t;
+
+/* BundlerLib(const BundlerParameters&) -- ref BundlerLib.cpp:184-196 */
+int  mage_ba_create(int are_points_fixed, mage_ba_t* out);
+void mage_ba_destroy(mage_ba_t h);
+/* AllocateCameras / AllocateMapPoints / AllocateObservations -- ref BundlerLib.cpp:198-230 (allocate once) */
+int  mage_ba_alloc_cameras(mage_ba_t h, int count);
+int  mage_ba_alloc_points(mage_ba_t h, int count);
+int  mage_ba_alloc_observations(mage_ba_t h, int count);
+/* SetCameraPose -- ref BundlerLib.cpp:261-276. position[3], orientation 3x3 column-major (world->camera),
+ * intrinsics (cx, cy, fx, fy); only fx is used as the focal length, exactly like the reference. */
+int  mage_ba_set_camera(mage_ba_t h, int idx, const float position[3], const float orientation_colmajor[9],
+                        const float intrinsics_cxcyfxfy[4], int is_fixed);
+int  mage_ba_fix_camera(mage_ba_t h, int idx, int value);                                   /* ref :278-281 */
+int  mage_ba_set_point(mage_ba_t h, int idx, const float xyz[3]);                           /* ref :283-292 */
+int  mage_ba_set_observation(mage_ba_t h, int idx, const float uv[2], int camera_idx, int point_idx,
+                             float information_scalar);                                     /* ref :294-309 */
+/* bulk SoA uploads (same semantics as calling the setters for idx = 0..n-1 in order) */
+int  mage_ba_set_cameras_bulk(mage_ba_t h, int n, const float* positions /*n*3*/, const float* orientations /*n*9*/,
+                              const float* intrinsics /*n*4*/, const int32_t* is_fixed /*n*/);
+int  mage_ba_set_points_bulk(mage_ba_t h, int n, const float* xyz /*n*3*/);
+int  mage_ba_set_observations_bulk(mage_ba_t h, int n, const float* uv /*n*2*/, const int32_t* camera_idx,
+                                   const int32_t* point_idx, const float* information /*n*/);
+int  mage_ba_set_lambda(mage_ba_t h, float user_lambda);                                    /* ref :352-355 */
+int  mage_ba_get_lambda(mage_ba_t h, float* lambda);                                        /* ref :357-360 */
+/* StepBundleAdjustment -- ref BundlerLib.cpp:364-447. Runs one LM step per Huber width, then classifies every
+ * active observation (behind camera, or squared error > max_error_square) as an outlier, removes it from later
+ * steps and reports its index. *mean_sq_error = sum of inlier squared errors / inlier count (NaN if none). */
+int  mage_ba_step(mage_ba_t h, const float* huber_width_per_iteration, int n_iterations, float max_error_square,
+                  unsigned int* outliers, int outlier_capacity, int* n_outliers, float* mean_sq_error);
+int  mage_ba_get_pose(mage_ba_t h, int idx, float position[3], float orientation_colmajor[9]);   /* ref :457-465 */
+int  mage_ba_get_point(mage_ba_t h, int idx, float xyz[3]);                                      /* ref :467-471 */
+/* bulk read-back + double precision state for parity tests */
+int  mage_ba_get_poses_bulk(mage_ba_t h, float* positions /*n*3*/, float* orientations /*n*9*/);
+int  mage_ba_get_points_bulk(mage_ba_t h, float* xyz /*n*3*/);
+int  mage_ba_get_state_f64(mage_ba_t h, double* cam_qxyzw_t /*K*7*/, double* points /*P*3*/);
+/* counters: [0]=LM iterations run, [1]=lambda trials, [2]=kernel launches, [3]=structure rebuilds */
+int  mage_ba_get_stats(mage_ba_t h, int64_t stats[4]);
+/* Many independent problems stepped concurrently (one CTA group per problem): same result per handle as calling
+ * mage_ba_step on each. means/outlier outputs are per handle. */
+int  mage_ba_step_many(mage_ba_t* handles, int n_handles, const float* huber_width_per_iteration, int n_iterations,
+                       float max_error_square, float* mean_sq_errors);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGE_B200_H */

@@ -1,0 +1,53 @@
+// Shared helpers for the sm_100a kernels and their C-ABI wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mage_b200.h"
+
+namespace mage {
+
+void set_error(const char* fmt, ...);
+
+#define MAGE_CUDA_TRY(expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            ::mage::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));    \
+            return MAGE_ERR_CUDA;                                                                        \
+        }                                                                                                \
+    } while (0)
+
+#define MAGE_REQUIRE(cond, code, ...)                 \
+    do {                                              \
+        if (!(cond)) {                                \
+            ::mage::set_error(__VA_ARGS__);           \
+            return (code);                            \
+        }                                             \
+    } while (0)
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// Simple bump allocator over one cudaMalloc'ed arena (all scratch of a handle lives in one allocation).
+struct DeviceArena {
+    uint8_t* base = nullptr;
+    size_t size = 0, used = 0;
+    size_t reserve(size_t bytes, size_t align = 256) { used = align_up(used, align); size_t o = used; used += bytes; return o; }
+    cudaError_t commit() { size = used; return cudaMalloc(&base, size ? size : 256); }
+    template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
+    void release() { if (base) cudaFree(base); base = nullptr; }
+};
+
+__device__ __forceinline__ int warp_reduce_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+} // namespace mage

@@ -1,0 +1,307 @@
+// Brute-force two-way Hamming matcher for sm_100a.
+//
+// Replaces Match() (ref Core/MAGESLAM/Source/Tracking/FeatureMatcher.cpp:61-190: two cv::BFMatcher::radiusMatch passes,
+// min best/second-best difference, cross-check) and GetDescriptorDistance (ref :453-504). Closed form in SURVEY A.5:
+//   for each query q: C = {t : H(q,t) <= maxHamming}; d1 <= d2 the two smallest; best(q) = argmin iff C != {} and
+//   (|C| == 1 or d2 - d1 >= minDiff); emit (a, best(a), d1) in ascending a iff best_B(best_A(a)) == a.
+// Integer work: xor + popc over 8 x 32-bit words, operands (2 x 64 KB at 2000 descriptors) live in shared memory /
+// L2 -- ALU bound, not HBM bound. One launch computes both directions of every pair of a batch.
+//
+// The reference sizes its backward lookup by the number of non-empty rows but indexes it by query index (:123-137,
+// :158) -- an out-of-range access whenever some B descriptor has no candidate. The lookup is sized nB here (the intent).
+// Ties for best resolve to the lowest index; with minDiff >= 1 (all shipped settings) a tie is rejected anyway.
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace mage {
+
+struct MatchJob {
+    const uint8_t* desc[2];     // [0] = A, [1] = B, 32 bytes per descriptor, 4-byte aligned
+    const uint8_t* mask[2];     // nullable, one byte per descriptor
+    const int* count_ptr[2];    // nullable: device-resident counts (device batched variant)
+    int count[2];
+    int cap;                    // clamp for device counts
+};
+
+constexpr int kChunk = 256;          // train descriptors staged per iteration
+constexpr int kQPerWarp = 4;
+constexpr int kWarps = 8;
+constexpr int kQPerBlock = kQPerWarp * kWarps;
+constexpr unsigned kNoKey = 0xFFFFFFFFu;
+
+__device__ __forceinline__ int job_count(const MatchJob& j, int side)
+{
+    int n = j.count_ptr[side] ? *j.count_ptr[side] : j.count[side];
+    return max(0, min(n, j.cap));
+}
+
+// best[pair][dir][q] = (distance << 16 | train) or kNoKey
+__global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ best, int stride,
+                                                           int max_hamming, int min_diff)
+{
+    __shared__ uint32_t tw[8][kChunk];          // train words, transposed: conflict-free lane-strided reads
+    __shared__ uint8_t tvalid[kChunk];
+    __shared__ uint32_t qw[kQPerBlock][8];
+    const int pair = blockIdx.y >> 1, dir = blockIdx.y & 1;
+    const MatchJob& job = jobs[pair];
+    const int nQ = job_count(job, dir), nT = job_count(job, dir ^ 1);
+    const int q0 = blockIdx.x * kQPerBlock;
+    if (q0 >= nQ) return;
+    const uint32_t* Q = reinterpret_cast<const uint32_t*>(job.desc[dir]);
+    const uint32_t* T = reinterpret_cast<const uint32_t*>(job.desc[dir ^ 1]);
+    const uint8_t* mQ = job.mask[dir];
+    const uint8_t* mT = job.mask[dir ^ 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (int i = threadIdx.x; i < kQPerBlock * 8; i += blockDim.x) {
+        int q = q0 + (i >> 3);
+        qw[i >> 3][i & 7] = (q < nQ) ? Q[(size_t)q * 8 + (i & 7)] : 0u;
+    }
+    unsigned bkey[kQPerWarp], second[kQPerWarp];
+#pragma unroll
+    for (int k = 0; k < kQPerWarp; k++) { bkey[k] = kNoKey; second[k] = 0xFFFFu; }
+
+    for (int c0 = 0; c0 < nT; c0 += kChunk) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kChunk * 8; i += blockDim.x) {
+            int t = c0 + (i >> 3);
+            tw[i & 7][i >> 3] = (t < nT) ? T[(size_t)t * 8 + (i & 7)] : 0u;
+        }
+        for (int i = threadIdx.x; i < kChunk; i += blockDim.x) {
+            int t = c0 + i;
+            tvalid[i] = (t < nT && (!mT || mT[t])) ? 1 : 0;
+        }
+        __syncthreads();
+        uint32_t q[kQPerWarp][8];
+#pragma unroll
+        for (int k = 0; k < kQPerWarp; k++)
+#pragma unroll
+            for (int w = 0; w < 8; w++) q[k][w] = qw[warp * kQPerWarp + k][w];
+#pragma unroll 2
+        for (int i = 0; i < kChunk / 32; i++) {
+            const int ti = lane + 32 * i;
+            if (!tvalid[ti]) continue;
+            uint32_t t[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) t[w] = tw[w][ti];
+            const unsigned tidx = (unsigned)(c0 + ti);
+#pragma unroll
+            for (int k = 0; k < kQPerWarp; k++) {
+                int d = __popc(q[k][0] ^ t[0]) + __popc(q[k][1] ^ t[1]) + __popc(q[k][2] ^ t[2]) + __popc(q[k][3] ^ t[3]);
+                if (d > max_hamming) continue;                       // radiusMatch keeps d <= maxDistance only
+                d += __popc(q[k][4] ^ t[4]) + __popc(q[k][5] ^ t[5]) + __popc(q[k][6] ^ t[6]) + __popc(q[k][7] ^ t[7]);
+                if (d > max_hamming) continue;
+                unsigned key = ((unsigned)d << 16) | tidx;
+                if (key < bkey[k]) { second[k] = bkey[k] >> 16; bkey[k] = key; }
+                else second[k] = min(second[k], (unsigned)d);
+            }
+        }
+    }
+    // merge the 32 per-lane states of each query
+#pragma unroll
+    for (int k = 0; k < kQPerWarp; k++) {
+        unsigned bk = bkey[k], sd = second[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned obk = __shfl_xor_sync(0xffffffffu, bk, o), osd = __shfl_xor_sync(0xffffffffu, sd, o);
+            unsigned loser = max(bk, obk) >> 16;                     // distance of the worse of the two bests (0xFFFF if none)
+            bk = min(bk, obk);
+            sd = min(min(sd, osd), loser);
+        }
+        const int qi = q0 + warp * kQPerWarp + k;
+        if (lane == 0 && qi < nQ) {
+            unsigned res = bk;
+            if (bk == kNoKey || (mQ && !mQ[qi])) res = kNoKey;
+            else if (sd != 0xFFFFu && (int)sd - (int)(bk >> 16) < min_diff) res = kNoKey;     // ref :130-135 / :149-154
+            best[((size_t)pair * 2 + dir) * stride + qi] = res;
+        }
+    }
+}
+
+// ordered emission (ascending A index) with the cross-check of ref :158
+__global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__ jobs, const unsigned* __restrict__ best, int stride,
+                                                    mage_dmatch* __restrict__ out, int out_cap, int* __restrict__ out_count)
+{
+    __shared__ int warp_sum[8];
+    __shared__ int base;
+    const int pair = blockIdx.x;
+    const MatchJob& job = jobs[pair];
+    const int nA = job_count(job, 0), nB = job_count(job, 1);
+    const unsigned* fwd = best + ((size_t)pair * 2 + 0) * stride;
+    const unsigned* bwd = best + ((size_t)pair * 2 + 1) * stride;
+    mage_dmatch* o = out + (size_t)pair * out_cap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int a0 = 0; a0 < nA; a0 += blockDim.x) {
+        const int a = a0 + threadIdx.x;
+        bool ok = false; unsigned key = kNoKey;
+        if (a < nA) {
+            key = fwd[a];
+            if (key != kNoKey) {
+                int t = key & 0xFFFF;
+                if (t < nB) { unsigned bk = bwd[t]; ok = bk != kNoKey && (int)(bk & 0xFFFF) == a; }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) warp_sum[warp] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int w = 0; w < warp; w++) off += warp_sum[w];
+        off += __popc(m & ((1u << lane) - 1));
+        if (ok && off < out_cap) { mage_dmatch dm; dm.query_idx = a; dm.train_idx = (int)(key & 0xFFFF); dm.distance = (float)(key >> 16); o[off] = dm; }
+        __syncthreads();
+        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; w++) tot += warp_sum[w]; base += tot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out_count[pair] = min(base, out_cap);
+}
+
+__global__ void k_desc_distance(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int n, int* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) d += __popc(a[(size_t)i * 8 + w] ^ b[(size_t)i * 8 + w]);
+    out[i] = d;
+}
+
+} // namespace mage
+
+using namespace mage;
+
+struct mage_matcher_s {
+    int max_desc = 0, max_pairs = 0;
+    MatchJob* h_jobs = nullptr;     // pinned
+    MatchJob* d_jobs = nullptr;
+    unsigned* d_best = nullptr;     // [max_pairs][2][max_desc]
+    uint8_t* d_stage = nullptr;     // single-pair host API staging: A, B, masks, matches, count
+    mage_dmatch* h_out = nullptr;   // pinned staging for results
+    int* h_count = nullptr;
+    cudaStream_t own_stream = nullptr;
+    // memo of the last device-batched job table (a video stream re-submits the same slot pairs every batch)
+    const uint8_t* memo_desc = nullptr; const int* memo_counts = nullptr; size_t memo_stride = 0;
+    std::vector<int> memo_a, memo_b;
+};
+
+extern "C" int mage_matcher_create(int max_descriptors, int max_pairs, mage_matcher_t* out)
+{
+    MAGE_REQUIRE(out && max_descriptors >= 1 && max_descriptors <= 65535 && max_pairs >= 1, MAGE_ERR_INVALID,
+                 "mage_matcher_create: max_descriptors must be 1..65535 and max_pairs >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: the matcher has no CPU fallback"); return MAGE_ERR_CUDA; }
+    mage_matcher_s* m = new mage_matcher_s();
+    m->max_desc = max_descriptors; m->max_pairs = max_pairs;
+    size_t stage = (size_t)max_descriptors * (32 + 32 + 1 + 1) + sizeof(mage_dmatch) * (size_t)max_descriptors + 64 + 256;
+    cudaError_t e = cudaMallocHost(&m->h_jobs, sizeof(MatchJob) * max_pairs);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_jobs, sizeof(MatchJob) * max_pairs);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_best, sizeof(unsigned) * 2 * (size_t)max_pairs * max_descriptors);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_stage, stage);
+    if (e == cudaSuccess) e = cudaMallocHost(&m->h_out, sizeof(mage_dmatch) * (size_t)max_descriptors);
+    if (e == cudaSuccess) e = cudaMallocHost(&m->h_count, sizeof(int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("mage_matcher_create: %s", cudaGetErrorString(e)); mage_matcher_destroy(m); return MAGE_ERR_CUDA; }
+    *out = m;
+    return MAGE_OK;
+}
+
+extern "C" void mage_matcher_destroy(mage_matcher_t m)
+{
+    if (!m) return;
+    if (m->h_jobs) cudaFreeHost(m->h_jobs);
+    if (m->d_jobs) cudaFree(m->d_jobs);
+    if (m->d_best) cudaFree(m->d_best);
+    if (m->d_stage) cudaFree(m->d_stage);
+    if (m->h_out) cudaFreeHost(m->h_out);
+    if (m->h_count) cudaFreeHost(m->h_count);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    delete m;
+}
+
+static int match_launch(mage_matcher_t m, int n_pairs, int max_q, int max_hamming, int min_diff, mage_dmatch* d_out, int out_cap,
+                        int* d_counts, cudaStream_t s)
+{
+    MAGE_CUDA_TRY(cudaMemcpyAsync(m->d_jobs, m->h_jobs, sizeof(MatchJob) * n_pairs, cudaMemcpyHostToDevice, s));
+    dim3 grid(div_up(max_q, kQPerBlock), 2 * n_pairs);
+    k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming, min_diff);
+    k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, d_out, out_cap, d_counts);
+    MAGE_CUDA_TRY(cudaGetLastError());
+    return MAGE_OK;
+}
+
+extern "C" int mage_match_bf(mage_matcher_t m, const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_t* descB, int nB,
+                             const uint8_t* maskB, int max_hamming, int min_diff, mage_dmatch* out, int* count, void* stream)
+{
+    MAGE_REQUIRE(m && count && out, MAGE_ERR_INVALID, "mage_match_bf: null argument");
+    MAGE_REQUIRE(nA >= 0 && nB >= 0 && nA <= m->max_desc && nB <= m->max_desc, MAGE_ERR_INVALID, "descriptor count exceeds matcher capacity %d", m->max_desc);
+    *count = 0;
+    // ref :72-77: nothing to match when either (masked) side is empty
+    if (nA == 0 || nB == 0) return MAGE_OK;
+    MAGE_REQUIRE(descA && descB, MAGE_ERR_INVALID, "mage_match_bf: null descriptors");
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->own_stream;
+    const size_t N = (size_t)m->max_desc;
+    uint8_t* dA = m->d_stage; uint8_t* dB = dA + N * 32; uint8_t* dmA = dB + N * 32; uint8_t* dmB = dmA + N;
+    mage_dmatch* dOut = reinterpret_cast<mage_dmatch*>(m->d_stage + align_up(N * 66, 256));
+    int* dCnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(dOut) + sizeof(mage_dmatch) * N);
+    MAGE_CUDA_TRY(cudaMemcpyAsync(dA, descA, (size_t)nA * 32, cudaMemcpyHostToDevice, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(dB, descB, (size_t)nB * 32, cudaMemcpyHostToDevice, s));
+    if (maskA) MAGE_CUDA_TRY(cudaMemcpyAsync(dmA, maskA, nA, cudaMemcpyHostToDevice, s));
+    if (maskB) MAGE_CUDA_TRY(cudaMemcpyAsync(dmB, maskB, nB, cudaMemcpyHostToDevice, s));
+    m->memo_desc = nullptr; m->memo_a.clear(); m->memo_b.clear();
+    MatchJob& j = m->h_jobs[0];
+    j.desc[0] = dA; j.desc[1] = dB; j.mask[0] = maskA ? dmA : nullptr; j.mask[1] = maskB ? dmB : nullptr;
+    j.count_ptr[0] = j.count_ptr[1] = nullptr; j.count[0] = nA; j.count[1] = nB; j.cap = m->max_desc;
+    int rc = match_launch(m, 1, nA > nB ? nA : nB, max_hamming, min_diff, dOut, m->max_desc, dCnt, s);
+    if (rc != MAGE_OK) return rc;
+    MAGE_CUDA_TRY(cudaMemcpyAsync(m->h_count, dCnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(m->h_out, dOut, sizeof(mage_dmatch) * (size_t)nA, cudaMemcpyDeviceToHost, s));
+    MAGE_CUDA_TRY(cudaStreamSynchronize(s));
+    *count = *m->h_count;
+    memcpy(out, m->h_out, sizeof(mage_dmatch) * (size_t)(*count));
+    return MAGE_OK;
+}
+
+extern "C" int mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_counts, size_t slot_stride,
+                                    const int* a_index, const int* b_index, int n_pairs, int max_hamming, int min_diff,
+                                    mage_dmatch* d_matches, int capacity, int* d_match_counts, void* stream)
+{
+    MAGE_REQUIRE(m && d_desc && d_counts && a_index && b_index && d_matches && d_match_counts, MAGE_ERR_INVALID, "mage_match_bf_device: null argument");
+    MAGE_REQUIRE(n_pairs >= 1 && n_pairs <= m->max_pairs, MAGE_ERR_INVALID, "n_pairs %d exceeds matcher capacity %d", n_pairs, m->max_pairs);
+    MAGE_REQUIRE(slot_stride % 4 == 0 && capacity >= 1, MAGE_ERR_INVALID, "slot_stride must be a multiple of 4");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool same = m->memo_desc == d_desc && m->memo_counts == d_counts && m->memo_stride == slot_stride &&
+                      (int)m->memo_a.size() == n_pairs && std::equal(a_index, a_index + n_pairs, m->memo_a.begin()) &&
+                      std::equal(b_index, b_index + n_pairs, m->memo_b.begin());
+    if (same) {     // job table already resident on the device
+        const int cap = (int)std::min<size_t>(m->max_desc, slot_stride / 32);
+        dim3 grid(div_up(cap, kQPerBlock), 2 * n_pairs);
+        k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming, min_diff);
+        k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, d_matches, capacity, d_match_counts);
+        MAGE_CUDA_TRY(cudaGetLastError());
+        return MAGE_OK;
+    }
+    // the pinned job table is rewritten: wait until any previous upload has been consumed
+    MAGE_CUDA_TRY(cudaStreamSynchronize(s));
+    m->memo_desc = d_desc; m->memo_counts = d_counts; m->memo_stride = slot_stride;
+    m->memo_a.assign(a_index, a_index + n_pairs); m->memo_b.assign(b_index, b_index + n_pairs);
+    for (int p = 0; p < n_pairs; p++) {
+        MatchJob& j = m->h_jobs[p];
+        j.desc[0] = d_desc + (size_t)a_index[p] * slot_stride; j.desc[1] = d_desc + (size_t)b_index[p] * slot_stride;
+        j.mask[0] = j.mask[1] = nullptr;
+        j.count_ptr[0] = d_counts + a_index[p]; j.count_ptr[1] = d_counts + b_index[p];
+        j.count[0] = j.count[1] = 0; j.cap = (int)std::min<size_t>(m->max_desc, slot_stride / 32);
+    }
+    return match_launch(m, n_pairs, m->h_jobs[0].cap, max_hamming, min_diff, d_matches, capacity, d_match_counts, s);
+}
+
+extern "C" int mage_descriptor_distance_device(const uint8_t* d_a, const uint8_t* d_b, int n, int* d_out, void* stream)
+{
+    MAGE_REQUIRE(d_a && d_b && d_out && n >= 0, MAGE_ERR_INVALID, "mage_descriptor_distance_device: bad argument");
+    if (n == 0) return MAGE_OK;
+    k_desc_distance<<<div_up(n, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(d_a), reinterpret_cast<const uint32_t*>(d_b), n, d_out);
+    MAGE_CUDA_TRY(cudaGetLastError());
+    return MAGE_OK;
+}

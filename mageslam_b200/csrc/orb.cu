@@ -1,0 +1,891 @@
+// ORB front-end for sm_100a: pyramid -> FAST-9/16 + score + NMS -> retain-best + ANMS -> orientation -> blur -> rBRIEF.
+//
+// Replaces OrbDetector::DetectAndCompute (ref Core/MAGESLAM/Source/Image/OpenCVModified.cpp:771-886) behind
+// include/mage_b200.h. Integer/byte work, HBM/L2 bound: no tensor cores. A batch of frames is processed per launch
+// (grid.y / grid.z = frame) so the 148 SMs are filled; every kernel reads its geometry from one by-value constant block.
+//
+// Data layout in HBM (one arena per handle):
+//   pyr[f]   : levels 0..L-1 of frame f, each with a 64-byte aligned row pitch (unblurred, chained bilinear)
+//   blur[f]  : same geometry, Gaussian-blurred copy (descriptors sample this one; orientation samples pyr)
+//   cand[f]  : per level, packed u32 (score << 24 | y*w + x) appended with atomics by the FAST kernel
+//   sel[f]   : per level, the <= n_l selected keypoints in final order, same packing
+// The selection order is the canonical one of SURVEY.md section 7 (stable raster order in RetainBestFeatures, fully
+// sorted ANMS prefix) -- a conforming execution of the reference's std::nth_element calls.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+namespace mage {
+
+#include "brief_base_patterns.inc"
+
+constexpr int kMaxLevels = 16;
+constexpr int kMaxCells = 2048;
+constexpr int kSelThreads = 512;
+constexpr int kSelSmemItems = 4096;      // keypoints per (frame, level) handled entirely in shared memory
+
+struct LevelGeom {
+    int w, h, pitch, nfeat;
+    float scale;
+    unsigned pyr_off;       // byte offset inside a frame's pyramid slab
+    unsigned cand_off;      // entry offset inside a frame's candidate arrays
+    unsigned cand_cap;
+    unsigned key_off;       // entry offset inside a frame's key array (pow2-padded capacities)
+    unsigned key_cap;
+    unsigned sel_off;       // entry offset inside a frame's selected array
+    unsigned tab_x, tab_y;  // offsets of the resize tables (destination = this level)
+    int fast_tiles_x, fast_tiles_y, fast_tile_base;
+    int blur_tiles_x, blur_tiles_y, blur_tile_base;
+};
+
+struct OrbGeom {
+    int nlevels, width, height;
+    int fast_threshold, border, patch, half_patch, use_orientation, ksize;
+    int strong_response, num_cells_x, num_cells_y;
+    float feature_factor, feature_strength, min_rf, max_rf;
+    int umax[18];
+    int gk[16];
+    LevelGeom lv[kMaxLevels];
+};
+
+struct OrbBuffers {
+    const uint8_t* lvl0;        // level-0 pixels (user device buffer or the handle's staging copy)
+    size_t lvl0_frame_stride;
+    int lvl0_pitch;
+    uint8_t* pyr;               // unblurred pyramid slabs (levels >= 1; level 0 only when it is the staging copy)
+    uint8_t* blur;              // blurred pyramid slabs (all levels)
+    size_t slab;                // bytes per frame slab
+    const int* tab_ofs;         // resize tables
+    const short2* tab_coef;
+    uint32_t* cand;  int* cand_count;  size_t cand_stride;    // [f][cand_total], [f][kMaxLevels]
+    uint32_t* kept;  uint32_t* cxy;  uint8_t* csc;            // selection scratch, same strides as cand
+    unsigned long long* keys; size_t key_stride;
+    uint32_t* sel;   int* sel_count;   size_t sel_stride;     // [f][sel_total], [f][kMaxLevels]
+    int* status;                                                // [f]
+    const int8_t* pattern;                                      // 30 x 1024 pre-rotated BRIEF table
+};
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ const uint8_t* level_ptr(const OrbGeom& g, const OrbBuffers& b, int f, int l, int& pitch)
+{
+    if (l == 0) { pitch = b.lvl0_pitch; return b.lvl0 + (size_t)f * b.lvl0_frame_stride; }
+    pitch = g.lv[l].pitch;
+    return b.pyr + (size_t)f * b.slab + g.lv[l].pyr_off;
+}
+__device__ __forceinline__ uint8_t* blur_ptr(const OrbGeom& g, const OrbBuffers& b, int f, int l)
+{
+    return b.blur + (size_t)f * b.slab + g.lv[l].pyr_off;
+}
+
+// ------------------------------------------------------------------------------------------------ K1: pyramid level
+// ref OpenCVModified.cpp:819-842 -> cv::resize(level l-1, INTER_LINEAR) restated in SURVEY appendix A.2.
+// One thread = 4 horizontally adjacent output pixels (one 32-bit store); tables hold source offsets + 11-bit coefficients.
+__global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbGeom g, const OrbBuffers b, int l)
+{
+    const LevelGeom& D = g.lv[l];
+    const LevelGeom& S = g.lv[l - 1];
+    const int f = blockIdx.z;
+    const int dy = blockIdx.y * 8 + threadIdx.y;
+    const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    if (dy >= D.h || dx0 >= D.w) return;
+    int spitch;
+    const uint8_t* src = level_ptr(g, b, f, l - 1, spitch);
+    uint8_t* dst = b.pyr + (size_t)f * b.slab + D.pyr_off;
+    const int sy = b.tab_ofs[D.tab_y + dy];
+    const short2 cy = b.tab_coef[D.tab_y + dy];
+    const int sy1 = min(sy + 1, S.h - 1);
+    const uint8_t* r0 = src + (size_t)sy * spitch;
+    const uint8_t* r1 = src + (size_t)sy1 * spitch;
+    uint32_t packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int dx = dx0 + i;
+        if (dx < D.w) {
+            int sx = b.tab_ofs[D.tab_x + dx];
+            short2 cx = b.tab_coef[D.tab_x + dx];
+            int sx1 = min(sx + 1, S.w - 1);
+            int h0 = r0[sx] * cx.x + r0[sx1] * cx.y;
+            int h1 = r1[sx] * cx.x + r1[sx1] * cx.y;
+            int v = ((((int)cy.x * (h0 >> 4)) >> 16) + (((int)cy.y * (h1 >> 4)) >> 16) + 2) >> 2;
+            packed |= (uint32_t)(v & 0xff) << (8 * i);
+        }
+    }
+    *reinterpret_cast<uint32_t*>(dst + (size_t)dy * D.pitch + dx0) = packed;      // pitch % 64 == 0: padding is writable
+}
+
+// ------------------------------------------------------------------------------------------------ K2: FAST + score + NMS
+// ref OpenCVModified.cpp:1224-1512 (FAST_t<16>), :926-1071 (cornerScore<16>), :619-639 (RunByImageBorder).
+// Closed form: score = max(max_k min(d[k..k+8]), -min_k max(d[k..k+8])) - 1, corner <=> score >= thr.
+constexpr int kFastPW = 128, kFastPH = 40;      // pixel tile
+constexpr int kFastOW = 120, kFastOH = 32;      // keypoint (output) tile
+constexpr int kFastSW = 122, kFastSH = 34;      // score tile
+
+__device__ __forceinline__ int min3(int a, int b, int c) { return min(min(a, b), c); }
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
+
+__device__ __forceinline__ int fast_score16(const uint8_t* c)      // c = centre pixel inside the smem tile (pitch kFastPW)
+{
+    constexpr int P = kFastPW;
+    const int v = c[0];
+    int d[16];
+    d[0] = v - c[3 * P];      d[1] = v - c[3 * P + 1];   d[2] = v - c[2 * P + 2];   d[3] = v - c[P + 3];
+    d[4] = v - c[3];          d[5] = v - c[-P + 3];      d[6] = v - c[-2 * P + 2];  d[7] = v - c[-3 * P + 1];
+    d[8] = v - c[-3 * P];     d[9] = v - c[-3 * P - 1];  d[10] = v - c[-2 * P - 2]; d[11] = v - c[-P - 3];
+    d[12] = v - c[-3];        d[13] = v - c[P - 3];      d[14] = v - c[2 * P - 2];  d[15] = v - c[3 * P - 1];
+    int lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        lo3[k] = min3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+        hi3[k] = max3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+    }
+    int q0 = -1000, q1 = 1000;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        q0 = max(q0, min3(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]));
+        q1 = min(q1, max3(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]));
+    }
+    return max(q0, -q1) - 1;
+}
+
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    __shared__ __align__(16) uint8_t px[kFastPH * kFastPW];
+    __shared__ uint8_t sc[kFastSH * kFastPW];
+    const int f = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].fast_tile_base) l++;
+    const LevelGeom& L = g.lv[l];
+    const int t = blockIdx.x - L.fast_tile_base;
+    const int tx = t % L.fast_tiles_x, ty = t / L.fast_tiles_x;
+    const int px0 = kFastOW * tx - 4, py0 = kFastOH * ty - 4;
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+
+    // stage the pixel tile: 32-bit loads, zero fill outside the image rows / pitch
+    for (int i = threadIdx.x; i < kFastPH * (kFastPW / 4); i += blockDim.x) {
+        int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
+        int y = py0 + ry, x = px0 + rx;
+        uint32_t v = 0;
+        if (y >= 0 && y < L.h && x >= 0 && x + 4 <= pitch) v = *reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch + x);
+        *reinterpret_cast<uint32_t*>(&px[ry * kFastPW + rx]) = v;
+    }
+    __syncthreads();
+    const int thr = g.fast_threshold;
+    for (int i = threadIdx.x; i < kFastSH * kFastSW; i += blockDim.x) {
+        int sy = i / kFastSW, sx = i % kFastSW;
+        int x = px0 + 3 + sx, y = py0 + 3 + sy;
+        int s = 0;
+        if (x >= 3 && x <= L.w - 4 && y >= 3 && y <= L.h - 4) {
+            s = fast_score16(&px[(sy + 3) * kFastPW + sx + 3]);
+            s = (s >= thr) ? s : 0;                 // stored as uchar in the reference: 0 for non-corners
+        }
+        sc[sy * kFastPW + sx] = (uint8_t)s;
+    }
+    __syncthreads();
+    const int bd = g.border;
+    uint32_t* cand = b.cand + (size_t)f * b.cand_stride + L.cand_off;
+    int* cnt = b.cand_count + f * kMaxLevels + l;
+    for (int i = threadIdx.x; i < kFastOH * kFastOW; i += blockDim.x) {
+        int oy = i / kFastOW, ox = i % kFastOW;
+        int x = px0 + 4 + ox, y = py0 + 4 + oy;
+        const uint8_t* s = &sc[(oy + 1) * kFastPW + ox + 1];
+        int v = s[0];
+        bool keep = v > 0 && x >= bd && x < L.w - bd && y >= bd && y < L.h - bd &&
+                    v > s[-1] && v > s[1] && v > s[-kFastPW - 1] && v > s[-kFastPW] && v > s[-kFastPW + 1] &&
+                    v > s[kFastPW - 1] && v > s[kFastPW] && v > s[kFastPW + 1];
+        if (keep) {
+            int slot = atomicAdd(cnt, 1);
+            if (slot < (int)L.cand_cap) cand[slot] = ((uint32_t)v << 24) | (uint32_t)(y * L.w + x);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K3: selection
+// ref OpenCVModified.cpp:571-617 (RetainBestFeatures) and :144-360 (AdaptiveNonMaximalSuppresion), canonical order.
+// One CTA per (level, frame). Keys are unique 64-bit words, sorted descending:
+//   ANMS   : r << 32 | score << 24 | (0xFFFFFF - raster)     (r desc, strength desc, raster asc)
+//   raster : (0xFFFFFF - raster) << 32 | score << 24 | (0xFFFFFF - raster)
+__device__ void bitonic_sort_desc(unsigned long long* keys, int npow2)
+{
+    for (int k = 2; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    unsigned long long a = keys[i], c = keys[ixj];
+                    bool desc = (i & k) == 0;
+                    if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads) k_select(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ int hist[256];
+    __shared__ int s_vals[16];          // 0:K 1:stop 2:minX 3:maxX 4:minY 5:maxY 6:minScore 7:R 8:mcd2 9:counter
+    __shared__ float s_rf;
+    __shared__ int cellStart[kMaxCells + 1];
+    __shared__ int cellFill[kMaxCells];
+
+    const int l = blockIdx.x, f = blockIdx.y;
+    const LevelGeom& L = g.lv[l];
+    int n = b.cand_count[f * kMaxLevels + l];
+    if (n > (int)L.cand_cap) { if (threadIdx.x == 0) atomicOr(b.status + f, 1); n = (int)L.cand_cap; }
+    const uint32_t* cand = b.cand + (size_t)f * b.cand_stride + L.cand_off;
+    uint32_t* sel = b.sel + (size_t)f * b.sel_stride + L.sel_off;
+    int* selCount = b.sel_count + f * kMaxLevels + l;
+    const int nKeep = L.nfeat;
+    const int tid = threadIdx.x, nt = blockDim.x;
+
+    unsigned long long* keys;
+    uint32_t *kept, *cxy;
+    uint8_t* csc;
+    auto bind = [&](int K) {
+        if (K <= kSelSmemItems) {
+            keys = reinterpret_cast<unsigned long long*>(smem_raw);
+            kept = reinterpret_cast<uint32_t*>(smem_raw + kSelSmemItems * 8);
+            cxy = kept + kSelSmemItems;
+            csc = reinterpret_cast<uint8_t*>(cxy + kSelSmemItems);
+        } else {
+            keys = b.keys + (size_t)f * b.key_stride + L.key_off;
+            kept = b.kept + (size_t)f * b.cand_stride + L.cand_off;
+            cxy = b.cxy + (size_t)f * b.cand_stride + L.cand_off;
+            csc = b.csc + (size_t)f * b.cand_stride + L.cand_off;
+        }
+    };
+
+    if (n <= nKeep) {
+        // no suppression: keep FAST's raster order (ref :721 branch not taken)
+        bind(n);
+        int np2 = 1; while (np2 < n) np2 <<= 1;
+        for (int i = tid; i < np2; i += nt) {
+            unsigned long long key = 0;
+            if (i < n) { uint32_t c = cand[i]; uint32_t inv = 0xFFFFFFu - (c & 0xFFFFFFu); key = ((unsigned long long)inv << 32) | (c & 0xFF000000u) | inv; }
+            keys[i] = key;
+        }
+        __syncthreads();
+        bitonic_sort_desc(keys, np2);
+        for (int i = tid; i < n; i += nt) {
+            uint32_t lo = (uint32_t)keys[i];
+            sel[i] = (lo & 0xFF000000u) | (0xFFFFFFu - (lo & 0xFFFFFFu));
+        }
+        if (tid == 0) *selCount = n;
+        return;
+    }
+
+    // ---- RetainBestFeatures: histogram of scores, whole-bin cut
+    for (int i = tid; i < 256; i += nt) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) atomicAdd(&hist[cand[i] >> 24], 1);
+    __syncthreads();
+    if (tid == 0) {
+        const int minThreshold = g.fast_threshold, minNum = nKeep;
+        const int maxNum = (int)__fmul_rn((float)nKeep, g.feature_factor);
+        int minNumThreshold = minThreshold, num = 0;
+        for (int i = 255; i >= minThreshold; i--) { num += hist[i]; if (num >= minNum) { minNumThreshold = i; break; } }
+        int lo = max((int)__fmul_rn((float)minNumThreshold, g.feature_strength), minThreshold);
+        int stop = lo; num = 0;
+        for (int i = 255; i >= lo; i--) { num += hist[i]; if (num >= maxNum) { stop = i; break; } }
+        int minScore = stop; while (minScore < 255 && hist[minScore] == 0) minScore++;
+        s_vals[0] = num; s_vals[1] = stop; s_vals[6] = minScore;
+        s_vals[2] = INT_MAX; s_vals[3] = INT_MIN; s_vals[4] = INT_MAX; s_vals[5] = INT_MIN; s_vals[9] = 0;
+    }
+    __syncthreads();
+    const int K = s_vals[0], stop = s_vals[1];
+    bind(K);
+    {
+        int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+        for (int i = tid; i < n; i += nt) {
+            uint32_t c = cand[i];
+            if ((int)(c >> 24) >= stop) {
+                int j = atomicAdd(&s_vals[9], 1);
+                kept[j] = c;
+                int pos = c & 0xFFFFFF, y = pos / L.w, x = pos - y * L.w;
+                mnx = min(mnx, x); mxx = max(mxx, x); mny = min(mny, y); mxy = max(mxy, y);
+            }
+        }
+        if (mnx != INT_MAX) { atomicMin(&s_vals[2], mnx); atomicMax(&s_vals[3], mxx); atomicMin(&s_vals[4], mny); atomicMax(&s_vals[5], mxy); }
+    }
+    const int numX = g.num_cells_x, numY = g.num_cells_y, nCells = numX * numY;
+    for (int i = tid; i < nCells; i += nt) { cellStart[i] = 0; cellFill[i] = 0; }
+    __syncthreads();
+    const int minX = s_vals[2], maxX = s_vals[3], minY = s_vals[4], maxY = s_vals[5];
+    if (tid == 0) {
+        // ref :207-214 robustness factor (float32, no contraction), :259 globalMaxR2, :261-266 minCellDelta2
+        const float thrf = (float)g.fast_threshold;
+        float hi = __fsub_rn((float)g.strong_response, thrf);
+        float val = fminf(hi, fmaxf(0.0f, __fsub_rn((float)s_vals[6], thrf)));
+        float range = fmaxf(0.0f, __fsub_rn(g.max_rf, g.min_rf));
+        s_rf = __fsub_rn(g.max_rf, __fmul_rn(__fdiv_rn(val, (float)(g.strong_response - g.fast_threshold)), range));
+        s_vals[7] = (int)(((double)(maxX - minX)) * ((double)(maxY - minY)) / (double)nKeep);
+        int dx = max((maxX - minX) / numX, 1), dy = max((maxY - minY) / numY, 1);
+        s_vals[8] = min(dx, dy) * min(dx, dy);
+    }
+    // cell histogram
+    for (int j = tid; j < K; j += nt) {
+        int pos = kept[j] & 0xFFFFFF, y = pos / L.w, x = pos - y * L.w;
+        int cell = ((y - minY) * numY / (maxY + 1 - minY)) * numX + (x - minX) * numX / (maxX + 1 - minX);
+        atomicAdd(&cellStart[cell], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {          // exclusive scan over <= 2048 cells by one warp (64 cells per lane)
+        int per = (nCells + 31) / 32, beg = tid * per, end = min(beg + per, nCells), sum = 0;
+        for (int i = beg; i < end; i++) sum += cellStart[i];
+        int incl = sum;
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
+        int run = incl - sum;
+        for (int i = beg; i < end; i++) { int c = cellStart[i]; cellStart[i] = run; run += c; }
+        if (tid == 31) cellStart[nCells] = incl;
+    }
+    __syncthreads();
+    for (int j = tid; j < K; j += nt) {
+        uint32_t c = kept[j];
+        int pos = c & 0xFFFFFF, y = pos / L.w, x = pos - y * L.w;
+        int cell = ((y - minY) * numY / (maxY + 1 - minY)) * numX + (x - minX) * numX / (maxX + 1 - minX);
+        int slot = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
+        cxy[slot] = (uint32_t)x | ((uint32_t)y << 16);
+        csc[slot] = (uint8_t)(c >> 24);
+    }
+    __syncthreads();
+    // ---- ANMS radii: literal ring search of ref :268-326, one thread per keypoint
+    const int R = s_vals[7], mcd2 = s_vals[8];
+    const float rf = s_rf;
+    int np2 = 1; while (np2 < K) np2 <<= 1;
+    for (int slot = tid; slot < np2; slot += nt) {
+        unsigned long long key = 0;
+        if (slot < K) {
+            const uint32_t me = cxy[slot];
+            const int x = me & 0xFFFF, y = me >> 16, sc = csc[slot];
+            const int cx = (x - minX) * numX / (maxX + 1 - minX), cy = (y - minY) * numY / (maxY + 1 - minY);
+            const float s = __fadd_rn(__fmul_rn((float)sc, rf), 0.002f);       // strength >= 0 always (FAST scores)
+            int minR2 = R;
+            for (int d = 0; max(0, d - 1) * max(0, d - 1) * mcd2 < minR2; d++) {
+                if (d > numX + numY) break;                                     // no cells out there
+                for (int yy = -d; yy <= d; yy++) {
+                    int cYY = yy + cy;
+                    if (cYY < 0 || cYY >= numY) continue;
+                    int step = (yy == -d || yy == d) ? 1 : 2 * d;               // ring: full rows at +-d, else the two ends
+                    if (step == 0) step = 1;
+                    for (int xx = -d; xx <= d; xx += step) {
+                        int cXX = xx + cx;
+                        if (cXX < 0 || cXX >= numX) continue;
+                        int c0 = cellStart[cYY * numX + cXX], c1 = cellStart[cYY * numX + cXX + 1];
+                        for (int o = c0; o < c1; o++) {
+                            if ((float)csc[o] > s) {
+                                uint32_t ot = cxy[o];
+                                int ddx = x - (int)(ot & 0xFFFF), ddy = y - (int)(ot >> 16);
+                                int r = ddx * ddx + ddy * ddy;
+                                if (r < minR2) minR2 = r;
+                            }
+                        }
+                    }
+                }
+            }
+            uint32_t inv = 0xFFFFFFu - (uint32_t)(y * L.w + x);
+            key = ((unsigned long long)(uint32_t)minR2 << 32) | ((uint32_t)sc << 24) | inv;
+        }
+        keys[slot] = key;
+    }
+    __syncthreads();
+    bitonic_sort_desc(keys, np2);
+    for (int i = tid; i < nKeep; i += nt) {
+        uint32_t lo = (uint32_t)keys[i];
+        sel[i] = (lo & 0xFF000000u) | (0xFFFFFFu - (lo & 0xFFFFFFu));
+    }
+    if (tid == 0) *selCount = nKeep;
+}
+
+// ------------------------------------------------------------------------------------------------ K5: Gaussian blur
+// ref OpenCVModified.cpp:853-865 -> cv::GaussianBlur(k x k, sigma 2, REFLECT_101), bit-exact Q8.8 path.
+constexpr int kBlurOW = 128, kBlurOH = 32, kBlurMaxR = 7;
+constexpr int kBlurIW = kBlurOW + 2 * kBlurMaxR + 2;    // 144
+constexpr int kBlurIH = kBlurOH + 2 * kBlurMaxR;        // 46
+
+__device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = (i < 0) ? -i : 2 * n - 2 - i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    __shared__ uint8_t in[kBlurIH * kBlurIW];
+    __shared__ uint16_t mid[kBlurIH * kBlurOW];
+    const int f = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_base) l++;
+    const LevelGeom& L = g.lv[l];
+    const int t = blockIdx.x - L.blur_tile_base;
+    const int x0 = (t % L.blur_tiles_x) * kBlurOW, y0 = (t / L.blur_tiles_x) * kBlurOH;
+    const int r = g.ksize / 2, ks = g.ksize;
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+    const int iw = kBlurOW + 2 * r, ih = kBlurOH + 2 * r;
+    for (int i = threadIdx.x; i < ih * iw; i += blockDim.x) {
+        int ry = i / iw, rx = i - ry * iw;
+        int y = reflect101(min(y0 + ry - r, L.h + r), L.h), x = reflect101(min(x0 + rx - r, L.w + r), L.w);
+        in[ry * kBlurIW + rx] = img[(size_t)y * pitch + x];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ih * kBlurOW; i += blockDim.x) {
+        int ry = i / kBlurOW, ox = i - ry * kBlurOW;
+        unsigned acc = 0;
+        for (int k = 0; k < ks; k++) acc += (unsigned)g.gk[k] * in[ry * kBlurIW + ox + k];
+        mid[ry * kBlurOW + ox] = (uint16_t)acc;
+    }
+    __syncthreads();
+    uint8_t* out = blur_ptr(g, b, f, l);
+    for (int i = threadIdx.x; i < kBlurOH * (kBlurOW / 4); i += blockDim.x) {
+        int oy = i / (kBlurOW / 4), ox = (i - oy * (kBlurOW / 4)) * 4;
+        int y = y0 + oy, x = x0 + ox;
+        if (y >= L.h || x >= L.w) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            unsigned acc = 0;
+            for (int k = 0; k < ks; k++) acc += (unsigned)g.gk[k] * mid[(oy + k) * kBlurOW + ox + j];
+            packed |= ((acc + 32768u) >> 16) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4+K7: orientation + rBRIEF
+// ref OpenCVModified.cpp:399-437 (ICAngles), :756-760 (rescale), :502-549 (ComputeOrbDescriptorsPrerotated),
+// cv::fastAtan2 restated in SURVEY appendix A.1 (float32, no FMA contraction).
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, scale), p3 = __fmul_rn(-0.3258083974640975f, scale);
+    const float p5 = __fmul_rn(0.1555786518463281f, scale), p7 = __fmul_rn(-0.04432655554792128f, scale);
+    float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, (float)DBL_EPSILON));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+__global__ void __launch_bounds__(256) k_orient_describe(const __grid_constant__ OrbGeom g, const OrbBuffers b,
+                                                         mage_keypoint* __restrict__ out_kps, uint8_t* __restrict__ out_desc,
+                                                         int* __restrict__ out_counts, int capacity)
+{
+    const int f = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // output slot of this warp
+    const int* selCount = b.sel_count + f * kMaxLevels;
+    int total = 0, l = -1, j = 0;
+    for (int k = 0; k < g.nlevels; k++) {
+        int c = selCount[k];
+        if (l < 0 && i < total + c) { l = k; j = i - total; }
+        total += c;
+    }
+    if (i == 0 && lane == 0) out_counts[f] = min(total, capacity);
+    if (l < 0 || i >= capacity) return;
+    const LevelGeom& L = g.lv[l];
+    const uint32_t c = b.sel[(size_t)f * b.sel_stride + L.sel_off + j];
+    const int pos = c & 0xFFFFFF, score = c >> 24;
+    const int y = pos / L.w, x = pos - y * L.w;
+
+    float angle = 0.f;
+    if (g.use_orientation) {
+        int pitch;
+        const uint8_t* img = level_ptr(g, b, f, l, pitch);
+        const uint8_t* center = img + (size_t)y * pitch + x;
+        const int hp = g.half_patch;
+        int m01 = 0, m10 = 0;
+        // lanes span u = -hp..hp (hp <= 15 -> 31 columns), loop over rows v
+        const int u = lane - hp;
+        if (lane <= 2 * hp) {
+            for (int v = -hp; v <= hp; v++) {
+                int av = v < 0 ? -v : v;
+                if ((u < 0 ? -u : u) <= g.umax[av]) {
+                    int val = center[v * pitch + u];
+                    m10 += u * val;
+                    m01 += v * val;
+                }
+            }
+        }
+        m01 = warp_reduce_sum(m01);
+        m10 = warp_reduce_sum(m10);
+        angle = fast_atan2_deg((float)m01, (float)m10);
+    }
+    const float ptx = __fmul_rn((float)x, L.scale), pty = __fmul_rn((float)y, L.scale);
+    if (lane == 0) {
+        mage_keypoint kp;
+        kp.x = ptx; kp.y = pty;
+        kp.size = __fmul_rn((float)g.patch, L.scale);
+        kp.angle = angle; kp.response = (float)score; kp.octave = l; kp.class_id = -1;
+        out_kps[(size_t)f * capacity + i] = kp;
+    }
+    // descriptor: lane = byte index; 8 tests of 4 int8 coordinates each = 32 contiguous pattern bytes per lane
+    const float inv = __fdiv_rn(1.f, L.scale);
+    const int bin = __float2int_rn(__fdiv_rn(angle, 12.f)) % 30;
+    const int cyy = __float2int_rn(__fmul_rn(pty, inv)), cxx = __float2int_rn(__fmul_rn(ptx, inv));
+    const uint8_t* base = (g.ksize > 1) ? blur_ptr(g, b, f, l) : nullptr;
+    int pitch = L.pitch;
+    if (!base) base = level_ptr(g, b, f, l, pitch);
+    const uint8_t* ctr = base + (size_t)cyy * pitch + cxx;
+    const int4* pp = reinterpret_cast<const int4*>(b.pattern + bin * 1024 + lane * 32);
+    const int4 pa = __ldg(pp), pb = __ldg(pp + 1);
+    const int w8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+    int val = 0;
+#pragma unroll
+    for (int bit = 0; bit < 8; bit++) {
+        int w = w8[bit];
+        int x0 = (int)(signed char)(w & 0xff), y0 = (int)(signed char)((w >> 8) & 0xff);
+        int x1 = (int)(signed char)((w >> 16) & 0xff), y1 = (int)(signed char)((w >> 24) & 0xff);
+        int t0 = ctr[y0 * pitch + x0], t1 = ctr[y1 * pitch + x1];
+        val |= (t0 < t1) << bit;
+    }
+    out_desc[((size_t)f * capacity + i) * 32 + lane] = (uint8_t)val;
+}
+
+// raster-order tap used by the stage parity tests
+__global__ void k_sort_candidates(const __grid_constant__ OrbGeom g, const OrbBuffers b, int f, int l, uint32_t* out, int cap, int* count)
+{
+    const LevelGeom& L = g.lv[l];
+    int n = min(b.cand_count[f * kMaxLevels + l], (int)L.cand_cap);
+    const uint32_t* cand = b.cand + (size_t)f * b.cand_stride + L.cand_off;
+    // rank by counting (debug path, O(n^2/threads))
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t me = cand[i] & 0xFFFFFF;
+        int rank = 0;
+        for (int k = 0; k < n; k++) rank += (cand[k] & 0xFFFFFF) < me;
+        if (rank < cap) out[rank] = cand[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *count = n;
+}
+
+} // namespace mage
+
+// ====================================================================================================================
+// Host side: handle, geometry, launches
+// ====================================================================================================================
+using namespace mage;
+
+struct mage_orb_s {
+    mage_orb_params params;
+    OrbGeom g;
+    OrbBuffers b;
+    DeviceArena arena;
+    int max_batch = 0;
+    size_t sel_total = 0, cand_total = 0, key_total = 0;
+    int fast_tiles = 0, blur_tiles = 0;
+    size_t off_stage_kps = 0, off_stage_desc = 0, off_stage_counts = 0, off_lvl0 = 0;
+    int last_n = 0;
+    int stage_cap = 0;          // staging capacity per frame = max(nfeatures, sum of per-level budgets)
+    cudaStream_t own_stream = nullptr;
+};
+
+namespace {
+
+inline int cvRoundF(float v) { return (int)lrintf(v); }
+inline int cvFloorF(float v) { int i = (int)v; return i - (i > v); }
+inline int cvCeilF(float v) { int i = (int)v; return i + (i < v); }
+
+const int* gauss_kernel_q8(int ksize)
+{
+    // Q8.8 kernels of cv::GaussianBlur's bit-exact path for sigma = 2 (OpenCV 4.x), SURVEY appendix A.3
+    static const int k3[] = {82, 92, 82};
+    static const int k5[] = {39, 57, 64, 57, 39};
+    static const int k7[] = {18, 34, 48, 56, 48, 34, 18};
+    static const int k9[] = {7, 17, 32, 46, 52, 46, 32, 17, 7};
+    static const int k11[] = {2, 7, 17, 31, 45, 52, 45, 31, 17, 7, 2};
+    static const int k13[] = {1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1};
+    static const int k15[] = {0, 1, 2, 7, 16, 31, 45, 52, 45, 31, 16, 7, 2, 1, 0};
+    switch (ksize) {
+    case 3: return k3; case 5: return k5; case 7: return k7; case 9: return k9;
+    case 11: return k11; case 13: return k13; case 15: return k15;
+    default: return nullptr;
+    }
+}
+
+// cv::resize INTER_LINEAR coefficient tables for one axis
+void resize_axis(int ssize, int dsize, int* ofs, short2* coef)
+{
+    double scale = (double)ssize / dsize;
+    for (int d = 0; d < dsize; d++) {
+        float fx = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)std::floor(fx);
+        fx -= s;
+        if (s < 0) { s = 0; fx = 0.f; }
+        if (s >= ssize - 1) { s = ssize - 1; fx = 0.f; }
+        ofs[d] = s;
+        coef[d] = make_short2((short)cvRoundF((1.f - fx) * 2048.f), (short)cvRoundF(fx * 2048.f));
+    }
+}
+
+int select_smem_bytes() { return kSelSmemItems * (8 + 4 + 4 + 1); }
+
+} // namespace
+
+extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, int max_batch, mage_orb_t* out)
+{
+    MAGE_REQUIRE(p && out, MAGE_ERR_INVALID, "mage_orb_create: null argument");
+    MAGE_REQUIRE(width >= 16 && height >= 16 && max_batch >= 1, MAGE_ERR_INVALID, "mage_orb_create: bad size %dx%d batch %d", width, height, max_batch);
+    MAGE_REQUIRE((size_t)width * height < (1u << 24), MAGE_ERR_UNSUPPORTED, "image larger than 2^24 pixels");
+    MAGE_REQUIRE(p->patch_size >= 2, MAGE_ERR_INVALID, "patch_size must be >= 2 (CV_Assert in the reference)");
+    MAGE_REQUIRE(p->patch_size == 31 || p->patch_size == 15, MAGE_ERR_UNSUPPORTED,
+                 "patch_size %u: only the pre-rotated tables (31, 15) are built; the generic path needs cv::RNG", p->patch_size);
+    MAGE_REQUIRE(p->nlevels >= 1 && p->nlevels <= (unsigned)kMaxLevels, MAGE_ERR_UNSUPPORTED, "nlevels must be 1..%d", kMaxLevels);
+    MAGE_REQUIRE(p->gaussian_kernel_size <= 1 || gauss_kernel_q8((int)p->gaussian_kernel_size), MAGE_ERR_UNSUPPORTED,
+                 "gaussian_kernel_size %u unsupported (odd 3..15)", p->gaussian_kernel_size);
+    MAGE_REQUIRE(p->num_cells_x >= 1 && p->num_cells_y >= 1 && p->num_cells_x * p->num_cells_y <= kMaxCells, MAGE_ERR_UNSUPPORTED,
+                 "num_cells_x*num_cells_y must be 1..%d", kMaxCells);
+    MAGE_REQUIRE(p->fast_threshold >= 1 && p->fast_threshold <= 255, MAGE_ERR_INVALID, "fast_threshold must be 1..255 (reference asserts > 0)");
+    MAGE_REQUIRE(p->scale_factor > 1.0f || p->nlevels == 1, MAGE_ERR_INVALID, "scale_factor must be > 1");
+    MAGE_REQUIRE(p->nfeatures >= 1, MAGE_ERR_INVALID, "nfeatures must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: the ORB path has no CPU fallback"); return MAGE_ERR_CUDA; }
+
+    mage_orb_s* h = new mage_orb_s();
+    h->params = *p;
+    h->max_batch = max_batch;
+    OrbGeom& g = h->g;
+    memset(&g, 0, sizeof(g));
+    g.nlevels = (int)p->nlevels; g.width = width; g.height = height;
+    g.fast_threshold = (int)p->fast_threshold; g.patch = (int)p->patch_size; g.half_patch = g.patch / 2;
+    g.use_orientation = p->use_orientation ? 1 : 0;
+    g.border = g.use_orientation ? cvCeilF(g.half_patch * std::sqrt(2.0f)) : g.half_patch;        // ref :712
+    g.ksize = p->gaussian_kernel_size > 1 ? (int)p->gaussian_kernel_size : 1;
+    g.strong_response = p->strong_response; g.num_cells_x = p->num_cells_x; g.num_cells_y = p->num_cells_y;
+    g.feature_factor = p->feature_factor; g.feature_strength = p->feature_strength; g.min_rf = p->min_robust_factor; g.max_rf = p->max_robust_factor;
+    if (g.ksize > 1) { const int* k = gauss_kernel_q8(g.ksize); for (int i = 0; i < g.ksize; i++) g.gk[i] = k[i]; }
+    {   // ref :673-689 umax
+        int hp = g.half_patch, v, v0, vmax = cvFloorF(hp * std::sqrt(2.f) / 2 + 1), vmin = cvCeilF(hp * std::sqrt(2.f) / 2);
+        for (v = 0; v <= vmax; ++v) g.umax[v] = (int)lrint(std::sqrt((double)hp * hp - v * v));
+        for (v = hp, v0 = 0; v >= vmin; --v) { while (g.umax[v0] == g.umax[v0 + 1]) ++v0; g.umax[v] = v0; ++v0; }
+    }
+    // level sizes (ref :795-799), per-level budget (ref :660-670)
+    {
+        int nfeatures = (int)p->nfeatures;
+        float factor = 1.0f / p->scale_factor;
+        float ndesired = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)g.nlevels));
+        int sum = 0;
+        for (int l = 0; l < g.nlevels; l++) {
+            float scale = (float)std::pow((double)p->scale_factor, (double)l);
+            g.lv[l].scale = scale;
+            g.lv[l].w = cvRoundF(width / scale);
+            g.lv[l].h = cvRoundF(height / scale);
+            if (l < g.nlevels - 1) { g.lv[l].nfeat = cvRoundF(ndesired); sum += g.lv[l].nfeat; ndesired *= factor; }
+            else g.lv[l].nfeat = std::max(nfeatures - sum, 0);
+            if (g.lv[l].w < 8 || g.lv[l].h < 8) { delete h; set_error("level %d is %dx%d: too small", l, g.lv[l].w, g.lv[l].h); return MAGE_ERR_UNSUPPORTED; }
+        }
+    }
+    // offsets
+    size_t pyr = 0, cand = 0, key = 0, sel = 0, tab = 0;
+    int ftiles = 0, btiles = 0;
+    for (int l = 0; l < g.nlevels; l++) {
+        LevelGeom& L = g.lv[l];
+        L.pitch = (int)align_up((size_t)L.w, 64);
+        L.pyr_off = (unsigned)pyr; pyr += align_up((size_t)L.pitch * L.h, 256);
+        L.cand_cap = (unsigned)(((L.w + 1) / 2) * ((L.h + 1) / 2));          // strict 3x3 NMS: at most one per 2x2 block
+        L.cand_off = (unsigned)cand; cand += align_up(L.cand_cap, 64);
+        unsigned kc = 1; while (kc < L.cand_cap) kc <<= 1;
+        L.key_cap = kc; L.key_off = (unsigned)key; key += kc;
+        L.sel_off = (unsigned)sel; sel += align_up((size_t)std::max(L.nfeat, 1), 32);
+        L.tab_x = (unsigned)tab; tab += L.w; L.tab_y = (unsigned)tab; tab += L.h;
+        L.fast_tiles_x = div_up(L.w, kFastOW); L.fast_tiles_y = div_up(L.h, kFastOH); L.fast_tile_base = ftiles;
+        ftiles += L.fast_tiles_x * L.fast_tiles_y;
+        L.blur_tiles_x = div_up(L.w, kBlurOW); L.blur_tiles_y = div_up(L.h, kBlurOH); L.blur_tile_base = btiles;
+        btiles += L.blur_tiles_x * L.blur_tiles_y;
+    }
+    h->fast_tiles = ftiles; h->blur_tiles = btiles;
+    h->cand_total = cand; h->key_total = key; h->sel_total = sel;
+
+    DeviceArena& A = h->arena;
+    const size_t B = (size_t)max_batch;
+    size_t o_pyr = A.reserve(pyr * B), o_blur = A.reserve(pyr * B);
+    size_t o_tabo = A.reserve(tab * sizeof(int)), o_tabc = A.reserve(tab * sizeof(short2));
+    size_t o_cand = A.reserve(cand * 4 * B), o_kept = A.reserve(cand * 4 * B), o_cxy = A.reserve(cand * 4 * B), o_csc = A.reserve(cand * B);
+    size_t o_keys = A.reserve(key * 8 * B);
+    size_t o_sel = A.reserve(sel * 4 * B);
+    size_t o_cnt = A.reserve(sizeof(int) * kMaxLevels * B * 2 + sizeof(int) * B);     // cand_count, sel_count, status
+    size_t o_pat = A.reserve(30 * 1024);
+    int sum_nl = 0;
+    for (int l = 0; l < g.nlevels; l++) sum_nl += g.lv[l].nfeat;
+    const int cap = std::max((int)p->nfeatures, sum_nl);
+    h->stage_cap = cap;
+    h->off_stage_kps = A.reserve(sizeof(mage_keypoint) * cap * B);
+    h->off_stage_desc = A.reserve((size_t)32 * cap * B);
+    h->off_stage_counts = A.reserve(sizeof(int) * B);
+    if (A.commit() != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", A.used); delete h; return MAGE_ERR_CUDA; }
+    cudaMemset(A.base, 0, A.size);
+
+    OrbBuffers& b = h->b;
+    b.pyr = A.at<uint8_t>(o_pyr); b.blur = A.at<uint8_t>(o_blur); b.slab = pyr;
+    b.lvl0 = b.pyr; b.lvl0_frame_stride = pyr; b.lvl0_pitch = g.lv[0].pitch;
+    b.tab_ofs = A.at<int>(o_tabo); b.tab_coef = A.at<short2>(o_tabc);
+    b.cand = A.at<uint32_t>(o_cand); b.kept = A.at<uint32_t>(o_kept); b.cxy = A.at<uint32_t>(o_cxy); b.csc = A.at<uint8_t>(o_csc);
+    b.cand_stride = cand;
+    b.keys = A.at<unsigned long long>(o_keys); b.key_stride = key;
+    b.sel = A.at<uint32_t>(o_sel); b.sel_stride = sel;
+    b.cand_count = A.at<int>(o_cnt); b.sel_count = b.cand_count + kMaxLevels * B; b.status = b.sel_count + kMaxLevels * B;
+    b.pattern = A.at<int8_t>(o_pat);
+
+    // tables
+    std::vector<int> tofs(tab); std::vector<short2> tcoef(tab);
+    for (int l = 1; l < g.nlevels; l++) {
+        resize_axis(g.lv[l - 1].w, g.lv[l].w, &tofs[g.lv[l].tab_x], &tcoef[g.lv[l].tab_x]);
+        resize_axis(g.lv[l - 1].h, g.lv[l].h, &tofs[g.lv[l].tab_y], &tcoef[g.lv[l].tab_y]);
+    }
+    std::vector<int8_t> pat(30 * 1024);
+    {   // rows 1..29 = row 0 rotated by 12r degrees, float32, round-half-even
+        const signed char* base = g.patch == 31 ? kBriefBase31 : kBriefBase15;
+        for (int r = 0; r < 30; r++) {
+            double ang = (double)(12 * r) * M_PI / 180.0;
+            float c = (float)std::cos(ang), s = (float)std::sin(ang);
+            for (int i = 0; i < 512; i++) {
+                float x = base[2 * i], y = base[2 * i + 1];
+                volatile float xc = x * c, ys = y * s, xs = x * s, yc = y * c;      // products rounded separately (no contraction)
+                pat[r * 1024 + 2 * i] = (int8_t)lrintf(xc - ys);
+                pat[r * 1024 + 2 * i + 1] = (int8_t)lrintf(xs + yc);
+            }
+        }
+    }
+    cudaError_t e = cudaMemcpy((void*)b.tab_ofs, tofs.data(), tab * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((void*)b.tab_coef, tcoef.data(), tab * sizeof(short2), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy((void*)b.pattern, pat.data(), pat.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes());
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { set_error("mage_orb_create: %s", cudaGetErrorString(e)); A.release(); delete h; return MAGE_ERR_CUDA; }
+    *out = h;
+    return MAGE_OK;
+}
+
+extern "C" void mage_orb_destroy(mage_orb_t h)
+{
+    if (!h) return;
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    h->arena.release();
+    delete h;
+}
+
+extern "C" int mage_orb_level_info(mage_orb_t h, int* widths, int* heights, float* scales, int* nfeat)
+{
+    MAGE_REQUIRE(h, MAGE_ERR_INVALID, "null handle");
+    for (int l = 0; l < h->g.nlevels; l++) {
+        if (widths) widths[l] = h->g.lv[l].w;
+        if (heights) heights[l] = h->g.lv[l].h;
+        if (scales) scales[l] = h->g.lv[l].scale;
+        if (nfeat) nfeat[l] = h->g.lv[l].nfeat;
+    }
+    return MAGE_OK;
+}
+
+// The kernel chain for n frames whose level-0 pixels are described by bufs.lvl0*. Asynchronous on s.
+static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint* d_kps, uint8_t* d_desc, int capacity, int* d_counts, cudaStream_t s)
+{
+    const OrbGeom& g = h->g;
+    MAGE_CUDA_TRY(cudaMemsetAsync(bufs.cand_count, 0, sizeof(int) * kMaxLevels * h->max_batch * 2 + sizeof(int) * h->max_batch, s));
+    for (int l = 1; l < g.nlevels; l++) {
+        dim3 grid(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 8), n), block(32, 8);
+        k_resize<<<grid, block, 0, s>>>(g, bufs, l);
+    }
+    if (g.ksize > 1) k_blur<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs);
+    k_fast<<<dim3(h->fast_tiles, n), 256, 0, s>>>(g, bufs);
+    k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs);
+    k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity);
+    MAGE_CUDA_TRY(cudaGetLastError());
+    h->last_n = n;
+    return MAGE_OK;
+}
+
+extern "C" int mage_orb_extract_device(mage_orb_t h, const uint8_t* d_images, int n, int width, int height, int stride,
+                                       size_t frame_stride, mage_keypoint* d_kps, uint8_t* d_desc, int capacity,
+                                       int* d_counts, void* stream)
+{
+    MAGE_REQUIRE(h && d_images && d_kps && d_desc && d_counts, MAGE_ERR_INVALID, "mage_orb_extract_device: null argument");
+    MAGE_REQUIRE(n >= 1 && n <= h->max_batch, MAGE_ERR_INVALID, "batch %d exceeds max_batch %d", n, h->max_batch);
+    MAGE_REQUIRE(width == h->g.width && height == h->g.height, MAGE_ERR_INVALID, "image %dx%d does not match the handle (%dx%d)", width, height, h->g.width, h->g.height);
+    MAGE_REQUIRE(stride >= width && stride % 4 == 0 && ((uintptr_t)d_images % 16) == 0 && frame_stride % 4 == 0, MAGE_ERR_INVALID,
+                 "device images need stride %% 4 == 0 and a 16-byte aligned base");
+    MAGE_REQUIRE(capacity >= 1, MAGE_ERR_INVALID, "capacity must be >= 1");
+    OrbBuffers bufs = h->b;
+    bufs.lvl0 = d_images; bufs.lvl0_frame_stride = frame_stride; bufs.lvl0_pitch = stride;
+    return orb_launch(h, bufs, n, d_kps, d_desc, capacity, d_counts, (cudaStream_t)stream);
+}
+
+extern "C" int mage_orb_detect_and_compute_batch(mage_orb_t h, const uint8_t* images, int n, int width, int height, int stride,
+                                                 size_t frame_stride, mage_keypoint* kps, uint8_t* desc, int capacity,
+                                                 int* counts, void* stream)
+{
+    MAGE_REQUIRE(h && images && kps && desc && counts, MAGE_ERR_INVALID, "mage_orb_detect_and_compute: null argument");
+    MAGE_REQUIRE(n >= 1 && n <= h->max_batch, MAGE_ERR_INVALID, "batch %d exceeds max_batch %d", n, h->max_batch);
+    MAGE_REQUIRE(width == h->g.width && height == h->g.height && stride >= width, MAGE_ERR_INVALID,
+                 "image %dx%d (stride %d) does not match the handle (%dx%d)", width, height, stride, h->g.width, h->g.height);
+    MAGE_REQUIRE(capacity >= 1, MAGE_ERR_INVALID, "capacity must be >= 1");
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->own_stream;
+    const OrbGeom& g = h->g;
+    const int cap = std::min(capacity, h->stage_cap);     // at most sum(n_l) <= stage_cap keypoints exist per frame
+    // level 0 = copy of the source image (ref :838) straight into the pyramid slab
+    for (int f = 0; f < n; f++)
+        MAGE_CUDA_TRY(cudaMemcpy2DAsync(h->b.pyr + (size_t)f * h->b.slab + g.lv[0].pyr_off, g.lv[0].pitch, images + (size_t)f * frame_stride,
+                                        stride, width, height, cudaMemcpyHostToDevice, s));
+    mage_keypoint* d_kps = h->arena.at<mage_keypoint>(h->off_stage_kps);
+    uint8_t* d_desc = h->arena.at<uint8_t>(h->off_stage_desc);
+    int* d_counts = h->arena.at<int>(h->off_stage_counts);
+    int rc = orb_launch(h, h->b, n, d_kps, d_desc, cap, d_counts, s);
+    if (rc != MAGE_OK) return rc;
+    if (cap == capacity) {
+        MAGE_CUDA_TRY(cudaMemcpyAsync(kps, d_kps, sizeof(mage_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, s));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(desc, d_desc, (size_t)32 * cap * n, cudaMemcpyDeviceToHost, s));
+    } else {
+        MAGE_CUDA_TRY(cudaMemcpy2DAsync(kps, sizeof(mage_keypoint) * (size_t)capacity, d_kps, sizeof(mage_keypoint) * (size_t)cap,
+                                        sizeof(mage_keypoint) * (size_t)cap, n, cudaMemcpyDeviceToHost, s));
+        MAGE_CUDA_TRY(cudaMemcpy2DAsync(desc, (size_t)32 * capacity, d_desc, (size_t)32 * cap, (size_t)32 * cap, n, cudaMemcpyDeviceToHost, s));
+    }
+    MAGE_CUDA_TRY(cudaMemcpyAsync(counts, d_counts, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    std::vector<int> status(n);
+    MAGE_CUDA_TRY(cudaMemcpyAsync(status.data(), h->b.status, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    MAGE_CUDA_TRY(cudaStreamSynchronize(s));
+    for (int f = 0; f < n; f++) MAGE_REQUIRE(status[f] == 0, MAGE_ERR_OVERFLOW, "frame %d: candidate list overflow", f);
+    return MAGE_OK;
+}
+
+extern "C" int mage_orb_detect_and_compute(mage_orb_t h, const uint8_t* image, int width, int height, int stride,
+                                           mage_keypoint* kps, uint8_t* desc, int capacity, int* count, void* stream)
+{
+    return mage_orb_detect_and_compute_batch(h, image, 1, width, height, stride, (size_t)stride * height, kps, desc, capacity, count, stream);
+}
+
+extern "C" int mage_orb_debug_get_level(mage_orb_t h, int frame, int level, int blurred, uint8_t* out)
+{
+    MAGE_REQUIRE(h && out && frame >= 0 && frame < h->max_batch && level >= 0 && level < h->g.nlevels, MAGE_ERR_INVALID, "bad debug request");
+    const LevelGeom& L = h->g.lv[level];
+    const uint8_t* src = (blurred ? h->b.blur : h->b.pyr) + (size_t)frame * h->b.slab + L.pyr_off;
+    MAGE_CUDA_TRY(cudaDeviceSynchronize());
+    MAGE_CUDA_TRY(cudaMemcpy2D(out, L.w, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    return MAGE_OK;
+}
+
+extern "C" int mage_orb_debug_get_candidates(mage_orb_t h, int frame, int level, uint32_t* out, int capacity, int* count)
+{
+    MAGE_REQUIRE(h && out && count && frame >= 0 && frame < h->max_batch && level >= 0 && level < h->g.nlevels, MAGE_ERR_INVALID, "bad debug request");
+    uint32_t* d_out = nullptr; int* d_cnt = nullptr;
+    MAGE_CUDA_TRY(cudaDeviceSynchronize());
+    MAGE_CUDA_TRY(cudaMalloc(&d_out, sizeof(uint32_t) * (size_t)capacity + sizeof(int)));
+    d_cnt = reinterpret_cast<int*>(d_out + capacity);
+    k_sort_candidates<<<64, 256>>>(h->g, h->b, frame, level, d_out, capacity, d_cnt);
+    cudaError_t e = cudaMemcpy(out, d_out, sizeof(uint32_t) * (size_t)capacity, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(count, d_cnt, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    MAGE_CUDA_TRY(e);
+    return MAGE_OK;
+}

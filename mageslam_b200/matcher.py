@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference's matcher surface (Tracking/FeatureMatcher.h:68-77, :134-136) over the C ABI."""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import DMATCH_DTYPE, check, lib, ptr, stream_ptr
+
+
+@dataclass
+class OrbMatcherSettings:
+    """Defaults = reference MageSettings.h:36-39."""
+    MaxHammingDistance: int = 30
+    MinHammingDifference: int = 1
+
+
+class Matcher:
+    """Owns the device workspace of mage_matcher_t (capacity in descriptors / batched pairs)."""
+
+    def __init__(self, max_descriptors=4096, max_pairs=1):
+        self._h = C.c_void_p()
+        self.max_descriptors, self.max_pairs = int(max_descriptors), int(max_pairs)
+        check(lib().mage_matcher_create(self.max_descriptors, self.max_pairs, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mage_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def Match(self, descA, descB, maskA=None, maskB=None, maxHammingDist=30, minHammingDifference=1):
+        """Mirror of Match(imageA, imageB, imageAMask, imageBMask, ..., maxHammingDist, minHammingDifference, goodMatches):
+        returns goodMatches as a DMATCH_DTYPE array (queryIdx = index in A, trainIdx = index in B), ascending queryIdx."""
+        descA = np.ascontiguousarray(descA, np.uint8).reshape(-1, 32)
+        descB = np.ascontiguousarray(descB, np.uint8).reshape(-1, 32)
+        nA, nB = len(descA), len(descB)
+        if maskA is not None:
+            maskA = np.ascontiguousarray(maskA, np.uint8)
+            assert len(maskA) == nA
+        if maskB is not None:
+            maskB = np.ascontiguousarray(maskB, np.uint8)
+            assert len(maskB) == nB
+        out = np.zeros(max(nA, 1), DMATCH_DTYPE)
+        cnt = C.c_int(0)
+        check(lib().mage_match_bf(self._h, ptr(descA) if nA else None, nA, ptr(maskA), ptr(descB) if nB else None, nB, ptr(maskB),
+                                  int(maxHammingDist), int(minHammingDifference), ptr(out), C.byref(cnt), None))
+        return out[:cnt.value]
+
+    def MatchDevice(self, d_desc, d_counts, slot_stride, a_index, b_index, d_matches, capacity, d_match_counts,
+                    maxHammingDist=30, minHammingDifference=1, stream=None):
+        a_index = np.ascontiguousarray(a_index, np.int32); b_index = np.ascontiguousarray(b_index, np.int32)
+        check(lib().mage_match_bf_device(self._h, ptr(d_desc), ptr(d_counts), int(slot_stride), ptr(a_index), ptr(b_index), len(a_index),
+                                         int(maxHammingDist), int(minHammingDifference), ptr(d_matches), int(capacity),
+                                         ptr(d_match_counts), stream_ptr(stream)))
+
+
+_default = None
+
+
+def Match(descA, descB, maskA=None, maskB=None, maxHammingDist=30, minHammingDifference=1):
+    """Free-function form, as in the reference (a process-wide workspace is created on first use)."""
+    global _default
+    n = max(len(descA), len(descB), 1)
+    if _default is None or _default.max_descriptors < n:
+        _default = Matcher(max(4096, n), 1)
+    return _default.Match(descA, descB, maskA, maskB, maxHammingDist, minHammingDifference)
+
+
+def GetDescriptorDistance(d0, d1):
+    """Mirror of GetDescriptorDistance (reference FeatureMatcher.cpp:453-504) for arrays of device descriptors (torch)."""
+    import torch
+    n = d0.shape[0]
+    out = torch.empty(n, dtype=torch.int32, device=d0.device)
+    check(lib().mage_descriptor_distance_device(ptr(d0), ptr(d1), n, ptr(out), stream_ptr(torch.cuda.current_stream())))
+    return out

@@ -1,0 +1,191 @@
+"""GPU parity tests of the ORB front-end: CUDA path (through the C ABI) vs the CPU oracle, bit-exact.
+
+Integer/byte work => the bar is exact equality of every intermediate (pyramid levels, blurred levels, FAST candidates)
+and of the final keypoints (all 7 fields, bit patterns of the floats) and descriptors.
+"""
+import numpy as np
+import pytest
+
+from mageslam_b200 import synth
+from mageslam_b200.orb import FeatureExtractorSettings, OrbDetector, OrbFeatureDetector
+from tests import oracle_orb as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def make_detector(p, max_batch=1):
+    return OrbDetector(p.gaussian_kernel_size, p.nfeatures, p.scale_factor, p.nlevels, p.patch_size, p.fast_threshold,
+                       p.use_orientation, p.feature_factor, p.feature_strength, p.strong_response, p.min_robust_factor,
+                       p.max_robust_factor, p.num_cells_x, p.num_cells_y, max_batch=max_batch)
+
+
+def assert_same_features(gk, gd, ok, od, tag=""):
+    assert len(gk) == len(ok), "%s count %d vs oracle %d" % (tag, len(gk), len(ok))
+    for name in ("octave", "class_id"):
+        assert np.array_equal(gk[name], ok[name]), (tag, name)
+    for name in ("x", "y", "size", "angle", "response"):
+        a = np.ascontiguousarray(gk[name]).view(np.uint32); b = np.ascontiguousarray(ok[name]).view(np.uint32)
+        bad = np.nonzero(a != b)[0]
+        assert len(bad) == 0, "%s field %s differs at %s: gpu %s oracle %s" % (tag, name, bad[:5], gk[name][bad[:5]], ok[name][bad[:5]])
+    bad = np.nonzero((gd != od).any(axis=1))[0]
+    assert len(bad) == 0, "%s descriptors differ at %s" % (tag, bad[:8])
+
+
+@pytest.fixture(scope="module")
+def frames():
+    return {"noise": synth.noise_frame(0), "video": synth.video_frames(4, 640, 480, seed=0)}
+
+
+def test_pyramid_and_blur_levels_bit_exact(frames):
+    p = orc.tier_params()
+    det = make_detector(p)
+    img = frames["video"][0]
+    det.DetectAndCompute(img)
+    ref = orc.build_pyramid(p, img)
+    for l in range(p.nlevels):
+        got = det.DebugLevel(0, l, blurred=False)
+        assert np.array_equal(got, ref[l]), "pyramid level %d: %d px differ" % (l, int((got != ref[l]).sum()))
+        gotb = det.DebugLevel(0, l, blurred=True)
+        refb = orc.blur(ref[l], 7)
+        assert np.array_equal(gotb, refb), "blurred level %d: %d px differ" % (l, int((gotb != refb).sum()))
+
+
+@pytest.mark.parametrize("which,thr", [("noise", 10), ("video", 10), ("video", 4), ("noise", 35)])
+def test_fast_candidates_bit_exact(frames, which, thr):
+    p = orc.tier_params(fast_threshold=thr)
+    det = make_detector(p)
+    img = frames[which] if which == "noise" else frames[which][1]
+    det.DetectAndCompute(img)
+    ref_levels = orc.build_pyramid(p, img)
+    border = 22
+    for l in range(p.nlevels):
+        lvl = ref_levels[l]
+        h, w = lvl.shape
+        k = orc.fast9(lvl, thr)
+        keep = (k["x"] >= border) & (k["x"] < w - border) & (k["y"] >= border) & (k["y"] < h - border)
+        k = k[keep]
+        ref = (k["response"].astype(np.uint32) << 24) | (k["y"].astype(np.uint32) * w + k["x"].astype(np.uint32))
+        got = det.DebugCandidates(0, l)
+        assert len(got) == len(ref), "level %d: %d candidates vs oracle %d" % (l, len(got), len(ref))
+        assert np.array_equal(got, ref), "level %d candidates differ" % l
+
+
+@pytest.mark.parametrize("cfg", ["tier", "tier_thr20", "default", "three_level", "no_orient_31", "small_budget", "k5"])
+def test_detect_and_compute_matches_oracle(frames, cfg):
+    if cfg == "tier":
+        p, imgs = orc.tier_params(), [frames["noise"], frames["video"][0], frames["video"][3]]
+    elif cfg == "tier_thr20":
+        p, imgs = orc.tier_params(fast_threshold=19), [frames["noise"], frames["video"][2]]
+    elif cfg == "default":          # reference defaults at the reference's tracking resolution
+        p, imgs = orc.default_params(), [synth.video_frames(2, 320, 180, seed=3)[1], synth.noise_frame(4, 320, 180)]
+    elif cfg == "three_level":
+        p, imgs = orc.tier_params(nfeatures=1000, nlevels=3, scale_factor=1.5), [frames["video"][1]]
+    elif cfg == "no_orient_31":
+        p = orc.tier_params(nfeatures=800, nlevels=4); p.use_orientation = 0
+        imgs = [frames["video"][1]]
+    elif cfg == "small_budget":     # far more candidates than budget: heavy retain-best + ANMS
+        p, imgs = orc.tier_params(nfeatures=120, nlevels=2, fast_threshold=5), [frames["noise"]]
+    else:
+        p = orc.tier_params(nfeatures=1500, nlevels=5); p.gaussian_kernel_size = 5
+        imgs = [frames["video"][2]]
+    det = make_detector(p)
+    for i, img in enumerate(imgs):
+        gk, gd = det.DetectAndCompute(img)
+        ok, od = orc.detect_and_compute(p, img, mode=1)
+        assert len(ok) > 50
+        assert_same_features(gk, gd, ok, od, "%s[%d]" % (cfg, i))
+
+
+def test_few_candidates_keeps_raster_order():
+    # flat image with a handful of corners: n <= n_l on every level => raster order, no suppression
+    img = np.full((480, 640), 90, np.uint8)
+    rng = np.random.default_rng(7)
+    for _ in range(25):
+        x, y = int(rng.integers(40, 600)), int(rng.integers(40, 440))
+        img[y:y + 9, x:x + 9] = 200
+    p = orc.tier_params()
+    gk, gd = make_detector(p).DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert 10 < len(ok) < 400
+    assert_same_features(gk, gd, ok, od, "sparse")
+
+
+def test_empty_image_gives_zero_features():
+    p = orc.tier_params()
+    gk, gd = make_detector(p).DetectAndCompute(np.full((480, 640), 128, np.uint8))
+    assert len(gk) == 0 and len(gd) == 0
+
+
+def test_capacity_truncates_like_image_data_insert(frames):
+    p = orc.tier_params()
+    det = make_detector(p)
+    gk, gd = det.DetectAndCompute(frames["noise"], capacity=777)
+    ok, od = orc.detect_and_compute(p, frames["noise"], 1, capacity=777)
+    assert len(ok) == 777
+    assert_same_features(gk, gd, ok, od, "capacity")
+
+
+def test_batch_equals_single_and_is_deterministic(frames):
+    p = orc.tier_params()
+    vid = frames["video"]
+    det1 = make_detector(p)
+    detb = make_detector(p, max_batch=4)
+    kps, desc, counts = detb.DetectAndComputeBatch(vid)
+    kps2, desc2, counts2 = detb.DetectAndComputeBatch(vid)
+    assert np.array_equal(counts, counts2) and np.array_equal(desc, desc2) and kps.tobytes() == kps2.tobytes()
+    for f in range(4):
+        gk, gd = det1.DetectAndCompute(vid[f])
+        assert counts[f] == len(gk)
+        assert kps[f, :counts[f]].tobytes() == gk.tobytes()
+        assert np.array_equal(desc[f, :counts[f]], gd)
+
+
+def test_device_resident_variant_equals_host_variant(frames):
+    import torch
+    p = orc.tier_params()
+    vid = frames["video"]
+    det = make_detector(p, max_batch=4)
+    kps, desc, counts = det.DetectAndComputeBatch(vid)
+    d_img = torch.from_numpy(vid).cuda()
+    cap = 2000
+    d_kps = torch.zeros((4, cap, 28), dtype=torch.uint8, device="cuda")
+    d_desc = torch.zeros((4, cap, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(4, dtype=torch.int32, device="cuda")
+    det.ExtractDevice(d_img, d_kps, d_desc, d_cnt, cap, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_cnt.cpu().numpy(), counts)
+    for f in range(4):
+        n = int(counts[f])
+        assert d_kps[f, :n].cpu().numpy().tobytes() == kps[f, :n].tobytes()
+        assert np.array_equal(d_desc[f, :n].cpu().numpy(), desc[f, :n])
+
+
+def test_unsupported_configurations_are_rejected():
+    from mageslam_b200._lib import MageError
+    p = orc.tier_params(); p.patch_size = 21            # generic pattern path needs cv::RNG
+    with pytest.raises(MageError):
+        make_detector(p).DetectAndCompute(np.zeros((480, 640), np.uint8))
+    with pytest.raises(TypeError):                       # CV_Assert(type == CV_8UC1)
+        make_detector(orc.tier_params()).DetectAndCompute(np.zeros((480, 640), np.float32))
+
+
+def test_orb_feature_detector_process(frames):
+    s = FeatureExtractorSettings.tier()
+    gk, gd = OrbFeatureDetector(s).Process(frames["video"][0])
+    ok, od = orc.detect_and_compute(orc.tier_params(), frames["video"][0], 1)
+    assert_same_features(gk, gd, ok, od, "process")
+
+
+def test_full_size_properties_1280x720():
+    # BASELINE config 5 geometry: no oracle-size limit here, check domain properties + oracle equality on one frame
+    img = synth.video_frames(1, 1280, 720, seed=10)[0]
+    p = orc.tier_params()
+    gk, gd = make_detector(p).DetectAndCompute(img)
+    assert len(gk) == 2000
+    ws = np.array([1280 / (1.2 ** o) for o in range(8)])
+    assert (gk["x"] >= 0).all() and (gk["x"] < 1280).all() and (gk["y"] >= 0).all() and (gk["y"] < 720).all()
+    assert (np.diff(gk["octave"]) >= 0).all()                      # levels are appended in order
+    assert np.array_equal(np.bincount(gk["octave"], minlength=8), [434, 362, 302, 251, 209, 175, 145, 122])
+    assert len({(float(k["x"]), float(k["y"]), int(k["octave"])) for k in gk}) == 2000   # no duplicates
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert_same_features(gk, gd, ok, od, "720p")
