@@ -1,0 +1,1149 @@
+// Bundle adjustment for sm_100a: Levenberg-Marquardt over SE(3) poses + 3-D points, Huber-weighted reprojection error,
+// Schur complement, dense LDLT on the reduced camera system -- the arithmetic mage::BundlerLib delegates to g2o
+// (ref Dependencies/BundlerLib/Source/BundlerLib.cpp + Dependencies/g2o), behind include/mage_b200.h.
+//
+// Design: FP64 end to end like the reference (no tensor cores: tcgen05 has no FP64 MMA and the
+// reduced system of a local window is 48x48). The whole LM loop of a StepBundleAdjustment call -- every iteration and
+// every lambda trial -- runs inside ONE persistent kernel launch, one CTA per problem, control scalars in shared memory;
+// the host only builds index structure when the edge set changes and reads back a few scalars + outlier flags.
+// Many independent problems are stepped by one launch (grid = problems). All reductions use a fixed order
+// (no floating-point atomics), so a run is bit-reproducible.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <limits>
+#include <map>
+#include <vector>
+
+namespace mage {
+
+struct BaCtl {
+    double lambda, ni, user_lambda_init, err_sum;
+    int iteration, inlier_count, stop_flag, last_ok;
+    long long lm_iters, lm_trials;
+};
+
+struct BaDev {
+    int K, P, Ea, Kf, Pl, n, nblk, cam_parts;
+    double *cam_q, *cam_t;                    // [K][4] (x y z w), [K][3]  world->camera
+    const double *cam_f, *cam_cx, *cam_cy;    // [K]
+    const int* cam_h;                         // [K] Hessian index of the camera or -1
+    double* pt_X;                             // [P][3]
+    const int *e_cam, *e_pt;                  // [Ea] active observations in insertion order
+    const double *e_uv, *e_info;              // [Ea][2], [Ea]
+    const int *l_pt, *l_ptr, *l_edges;        // landmarks (free points, Hessian order): point id, CSR of active edges
+    const int *c_cam, *c_ptr, *c_edges;       // free cameras (Hessian order): camera id, CSR of active edges
+    const int *blk_ij, *blk_ptr;              // upper blocks of the reduced system: (i1, i2), CSR into pairs
+    const int2* pairs;                        // (edge of i1, edge of i2) sharing a landmark
+    const int* e_l;                           // [Ea] landmark index of the edge's point or -1
+    double *err, *W, *WD, *Hll, *bl, *Dinv, *db, *Hpp, *bp, *S, *bs, *x, *cam_bak, *pt_bak, *part;
+    unsigned char* flags;                     // [Ea] 1 = outlier
+    BaCtl* ctl;
+};
+
+// ------------------------------------------------------------------------------------------------ small math
+__device__ __forceinline__ void q_rot(const double* q, const double* p, double* r)    // Eigen _transformVector
+{
+    double ux = q[1] * p[2] - q[2] * p[1], uy = q[2] * p[0] - q[0] * p[2], uz = q[0] * p[1] - q[1] * p[0];
+    ux += ux; uy += uy; uz += uz;
+    r[0] = p[0] + q[3] * ux + (q[1] * uz - q[2] * uy);
+    r[1] = p[1] + q[3] * uy + (q[2] * ux - q[0] * uz);
+    r[2] = p[2] + q[3] * uz + (q[0] * uy - q[1] * ux);
+}
+__device__ __forceinline__ void q_to_R(const double* q, double* R)
+{
+    double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+    double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0], tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1 - (txx + tyy);
+}
+__device__ void R_to_q(const double* m, double* q)
+{
+    double t = m[0] + m[4] + m[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0); q[3] = 0.5 * t; t = 0.5 / t;
+        q[0] = (m[7] - m[5]) * t; q[1] = (m[2] - m[6]) * t; q[2] = (m[3] - m[1]) * t;
+    } else {
+        int i = 0;
+        if (m[4] > m[0]) i = 1;
+        if (m[8] > m[i * 3 + i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+        q[i] = 0.5 * t; t = 0.5 / t;
+        q[3] = (m[k * 3 + j] - m[j * 3 + k]) * t;
+        q[j] = (m[j * 3 + i] + m[i * 3 + j]) * t;
+        q[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+    }
+}
+__device__ __forceinline__ void q_normalize_rotation(double* q)      // ref se3quat.h:280-285
+{
+    if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+    double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+// ref se3quat.h:218-257 (exp) and :99-105 (operator*):  T <- exp(u) * T,  u = (omega, upsilon)
+__device__ void pose_oplus(double* q, double* t, const double* u)
+{
+    const double om0 = u[0], om1 = u[1], om2 = u[2];
+    const double theta = sqrt(om0 * om0 + om1 * om1 + om2 * om2);
+    const double O[9] = {0, -om2, om1, om2, 0, -om0, -om1, om0, 0};
+    double O2[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+    double a, b, c, d;
+    if (theta < 0.00001) { a = 1; b = 0.5; c = 0.5; d = 1. / 6.; }
+    else { a = sin(theta) / theta; b = (1 - cos(theta)) / (theta * theta); c = b; d = (theta - sin(theta)) / (theta * theta * theta); }
+    double R[9], V[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { double I = (i % 4 == 0) ? 1.0 : 0.0; R[i] = I + a * O[i] + b * O2[i]; V[i] = I + c * O[i] + d * O2[i]; }
+    double eq[4], et[3];
+    R_to_q(R, eq);
+#pragma unroll
+    for (int i = 0; i < 3; i++) et[i] = V[i * 3] * u[3] + V[i * 3 + 1] * u[4] + V[i * 3 + 2] * u[5];
+    q_normalize_rotation(eq);
+    double rt[3];
+    q_rot(eq, t, rt);
+    t[0] = et[0] + rt[0]; t[1] = et[1] + rt[1]; t[2] = et[2] + rt[2];
+    double r[4];
+    r[3] = eq[3] * q[3] - eq[0] * q[0] - eq[1] * q[1] - eq[2] * q[2];
+    r[0] = eq[3] * q[0] + eq[0] * q[3] + eq[1] * q[2] - eq[2] * q[1];
+    r[1] = eq[3] * q[1] + eq[1] * q[3] + eq[2] * q[0] - eq[0] * q[2];
+    r[2] = eq[3] * q[2] + eq[2] * q[3] + eq[0] * q[1] - eq[1] * q[0];
+    q_normalize_rotation(r);
+    q[0] = r[0]; q[1] = r[1]; q[2] = r[2]; q[3] = r[3];
+}
+// ref robust_kernel_impl.cpp:65-78: Huber on the squared error
+__device__ __forceinline__ void huber(double e, double delta, double& rho0, double& rho1)
+{
+    double dsqr = delta * delta;
+    if (e <= dsqr) { rho0 = e; rho1 = 1.0; }
+    else { double sq = sqrt(e); rho0 = 2 * sq * delta - dsqr; rho1 = delta / sq; }
+}
+
+// fixed-order block reductions (bit-reproducible): strided partials -> shuffle tree -> warp 0 tree
+__device__ double block_sum(double v, double* sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[32] = v;
+    }
+    __syncthreads();
+    return sh[32];
+}
+__device__ double block_max(double v, double* sh)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < nw ? sh[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+        if (lane == 0) sh[32] = v;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// ------------------------------------------------------------------------------------------------ phases
+// ref types_six_dof_expmap.h:140-147 computeError
+__device__ void phase_errors(const BaDev& p, int tid, int nt)
+{
+    for (int e = tid; e < p.Ea; e += nt) {
+        const int c = p.e_cam[e];
+        double xt[3];
+        q_rot(p.cam_q + 4 * c, p.pt_X + 3 * (size_t)p.e_pt[e], xt);
+        xt[0] += p.cam_t[3 * c]; xt[1] += p.cam_t[3 * c + 1]; xt[2] += p.cam_t[3 * c + 2];
+        const double f = p.cam_f[c];
+        p.err[2 * e] = p.e_uv[2 * e] - (xt[0] / xt[2] * f + p.cam_cx[c]);
+        p.err[2 * e + 1] = p.e_uv[2 * e + 1] - (xt[1] / xt[2] * f + p.cam_cy[c]);
+    }
+}
+// ref sparse_optimizer.cpp:102-117 activeRobustChi2
+__device__ double phase_chi2(const BaDev& p, double delta, double* sh)
+{
+    double acc = 0;
+    for (int e = threadIdx.x; e < p.Ea; e += blockDim.x) {
+        double e0 = p.err[2 * e], e1 = p.err[2 * e + 1], r0, r1;
+        huber(p.e_info[e] * (e0 * e0 + e1 * e1), delta, r0, r1);
+        acc += r0;
+    }
+    return block_sum(acc, sh);
+}
+
+// Jacobians of ref types_six_dof_expmap.cpp:295-331 at the current state
+__device__ __forceinline__ void edge_jacobians(const BaDev& p, int e, double* Ji /*2x3*/, double* Jj /*2x6*/, bool wantPose)
+{
+    const int c = p.e_cam[e];
+    const double* q = p.cam_q + 4 * c;
+    double xt[3];
+    q_rot(q, p.pt_X + 3 * (size_t)p.e_pt[e], xt);
+    const double x = xt[0] + p.cam_t[3 * c], y = xt[1] + p.cam_t[3 * c + 1], z = xt[2] + p.cam_t[3 * c + 2];
+    const double f = p.cam_f[c], z2 = z * z;
+    double R[9];
+    q_to_R(q, R);
+    const double t00 = f, t02 = -x / z * f, t11 = f, t12 = -y / z * f, miz = -1. / z;
+#pragma unroll
+    for (int cc = 0; cc < 3; cc++) {
+        Ji[cc] = (miz * t00) * R[cc] + (miz * t02) * R[6 + cc];
+        Ji[3 + cc] = (miz * t11) * R[3 + cc] + (miz * t12) * R[6 + cc];
+    }
+    if (wantPose) {
+        Jj[0] = x * y / z2 * f; Jj[1] = -(1 + (x * x / z2)) * f; Jj[2] = y / z * f; Jj[3] = -1. / z * f; Jj[4] = 0; Jj[5] = x / z2 * f;
+        Jj[6] = (1 + y * y / z2) * f; Jj[7] = -x * y / z2 * f; Jj[8] = -x / z * f; Jj[9] = 0; Jj[10] = -1. / z * f; Jj[11] = y / z2 * f;
+    }
+}
+
+// ref block_solver.hpp:463-521 + base_binary_edge.hpp:62-134: landmark blocks H_ll, b_l and pose-landmark blocks W
+__device__ void phase_build_points(const BaDev& p, double delta, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+        for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
+            const int e = p.l_edges[k];
+            const int hj = p.cam_h[p.e_cam[e]];
+            double Ji[6], Jj[12];
+            edge_jacobians(p, e, Ji, Jj, hj >= 0);
+            const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1], info = p.e_info[e];
+            double r0, r1;
+            huber(info * (e0 * e0 + e1 * e1), delta, r0, r1);
+            const double w = r1 * info, o0 = -info * e0 * r1, o1 = -info * e1 * r1;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                b[r] += Ji[r] * o0 + Ji[3 + r] * o1;
+#pragma unroll
+                for (int c = 0; c < 3; c++) H[r * 3 + c] += w * (Ji[r] * Ji[c] + Ji[3 + r] * Ji[3 + c]);
+            }
+            if (hj >= 0) {
+                double* W = p.W + 18 * (size_t)e;
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) W[r * 3 + c] = w * (Jj[r] * Ji[c] + Jj[6 + r] * Ji[3 + c]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) p.Hll[9 * (size_t)li + i] = H[i];
+        p.bl[3 * li] = b[0]; p.bl[3 * li + 1] = b[1]; p.bl[3 * li + 2] = b[2];
+    }
+}
+
+// pose blocks H_pp (diagonal 6x6) and b_p: one warp per (camera, part) slice of the camera's edge list, lanes stride the
+// slice, shuffle-tree reduction, partials summed in part order by phase_finish_cams
+__device__ void phase_build_cams(const BaDev& p, double delta, int warp, int nwarps, int lane)
+{
+    const int items = p.Kf * p.cam_parts;
+    for (int it = warp; it < items; it += nwarps) {
+        const int kf = it / p.cam_parts, part = it % p.cam_parts;
+        const int beg = p.c_ptr[kf], end = p.c_ptr[kf + 1], len = end - beg;
+        const int per = (len + p.cam_parts - 1) / p.cam_parts;
+        const int s0 = beg + part * per, s1 = min(s0 + per, end);
+        double A[21], b[6];
+#pragma unroll
+        for (int i = 0; i < 21; i++) A[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) b[i] = 0;
+        for (int k = s0 + lane; k < s1; k += 32) {
+            const int e = p.c_edges[k];
+            double Ji[6], Jj[12];
+            edge_jacobians(p, e, Ji, Jj, true);
+            const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1], info = p.e_info[e];
+            double r0, r1;
+            huber(info * (e0 * e0 + e1 * e1), delta, r0, r1);
+            const double w = r1 * info, o0 = -info * e0 * r1, o1 = -info * e1 * r1;
+            int idx = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                b[r] += Jj[r] * o0 + Jj[6 + r] * o1;
+#pragma unroll
+                for (int c = r; c < 6; c++) A[idx++] += w * (Jj[r] * Jj[c] + Jj[6 + r] * Jj[6 + c]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 21; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) A[i] += __shfl_down_sync(0xffffffffu, A[i], o);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b[i] += __shfl_down_sync(0xffffffffu, b[i], o);
+        if (lane == 0) {
+            double* dst = p.part + (size_t)it * 27;
+#pragma unroll
+            for (int i = 0; i < 21; i++) dst[i] = A[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++) dst[21 + i] = b[i];
+        }
+    }
+}
+__device__ void phase_finish_cams(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < p.Kf * 27; i += nt) {
+        const int kf = i / 27, j = i % 27;
+        double s = 0;
+        for (int part = 0; part < p.cam_parts; part++) s += p.part[((size_t)kf * p.cam_parts + part) * 27 + j];
+        if (j >= 21) p.bp[6 * kf + (j - 21)] = s;
+        else {
+            int r = 0, rem = j;
+            while (rem >= 6 - r) { rem -= 6 - r; r++; }
+            const int c = r + rem;
+            p.Hpp[36 * (size_t)kf + r * 6 + c] = s;
+            p.Hpp[36 * (size_t)kf + c * 6 + r] = s;
+        }
+    }
+}
+
+// ref optimization_algorithm_levenberg.cpp:151-165 computeLambdaInit: tau * max |diag(H)|
+__device__ double phase_max_diag(const BaDev& p, double* sh)
+{
+    double m = 0;
+    for (int i = threadIdx.x; i < p.Kf * 6; i += blockDim.x) m = fmax(m, fabs(p.Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]));
+    for (int i = threadIdx.x; i < p.Pl * 3; i += blockDim.x) m = fmax(m, fabs(p.Hll[9 * (size_t)(i / 3) + (i % 3) * 4]));
+    return block_max(m, sh);
+}
+
+// Schur step 1 (ref block_solver.hpp:337-352): D^-1 = (H_ll + lambda I)^-1 (3x3 cofactor inverse), db = D^-1 b_l, WD = W D^-1
+__device__ void phase_schur_points(const BaDev& p, double lambda, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double A[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) A[i] = p.Hll[9 * (size_t)li + i];
+        A[0] += lambda; A[4] += lambda; A[8] += lambda;
+        const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+        const double id = 1.0 / (A[0] * c00 + A[1] * c01 + A[2] * c02);
+        double D[9];
+        D[0] = c00 * id; D[1] = (A[2] * A[7] - A[1] * A[8]) * id; D[2] = (A[1] * A[5] - A[2] * A[4]) * id;
+        D[3] = c01 * id; D[4] = (A[0] * A[8] - A[2] * A[6]) * id; D[5] = (A[2] * A[3] - A[0] * A[5]) * id;
+        D[6] = c02 * id; D[7] = (A[1] * A[6] - A[0] * A[7]) * id; D[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+#pragma unroll
+        for (int i = 0; i < 9; i++) p.Dinv[9 * (size_t)li + i] = D[i];
+        const double b0 = p.bl[3 * li], b1 = p.bl[3 * li + 1], b2 = p.bl[3 * li + 2];
+        p.db[3 * li] = D[0] * b0 + D[1] * b1 + D[2] * b2;
+        p.db[3 * li + 1] = D[3] * b0 + D[4] * b1 + D[5] * b2;
+        p.db[3 * li + 2] = D[6] * b0 + D[7] * b1 + D[8] * b2;
+        for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
+            const int e = p.l_edges[k];
+            if (p.cam_h[p.e_cam[e]] < 0) continue;
+            const double* W = p.W + 18 * (size_t)e;
+            double* WD = p.WD + 18 * (size_t)e;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) WD[r * 3 + c] = W[r * 3] * D[c] + W[r * 3 + 1] * D[3 + c] + W[r * 3 + 2] * D[6 + c];
+        }
+    }
+    for (int i = tid; i < p.n * p.n; i += nt) p.S[i] = 0.0;
+}
+
+// Schur step 2 (ref block_solver.hpp:354-390): S_ij = Hpp_ij (+lambda) - sum_pairs WD_e1 W_e2^T per upper block (one warp per
+// block, lanes stride the pair list), and the partials of coeff_i = sum_e W_e db per (camera, part)
+__device__ void phase_schur_blocks(const BaDev& p, double lambda, int warp, int nwarps, int lane)
+{
+    for (int bi = warp; bi < p.nblk; bi += nwarps) {
+        const int i1 = p.blk_ij[2 * bi], i2 = p.blk_ij[2 * bi + 1];
+        double acc[36];
+#pragma unroll
+        for (int i = 0; i < 36; i++) acc[i] = 0;
+        for (int k = p.blk_ptr[bi] + lane; k < p.blk_ptr[bi + 1]; k += 32) {
+            const int2 pr = p.pairs[k];
+            const double* A = p.WD + 18 * (size_t)pr.x;
+            const double* B = p.W + 18 * (size_t)pr.y;
+            double a[18], b[18];
+#pragma unroll
+            for (int i = 0; i < 18; i++) { a[i] = A[i]; b[i] = B[i]; }
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[r * 6 + c] += a[r * 3] * b[c * 3] + a[r * 3 + 1] * b[c * 3 + 1] + a[r * 3 + 2] * b[c * 3 + 2];
+        }
+#pragma unroll
+        for (int i = 0; i < 36; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    double v = -acc[r * 6 + c];
+                    if (i1 == i2) v += p.Hpp[36 * (size_t)i1 + r * 6 + c] + ((r == c) ? lambda : 0.0);
+                    p.S[(size_t)(6 * i1 + r) * p.n + 6 * i2 + c] = v;
+                    if (i1 != i2) p.S[(size_t)(6 * i2 + c) * p.n + 6 * i1 + r] = v;
+                }
+        }
+    }
+    const int items = p.Kf * p.cam_parts;
+    for (int it = warp; it < items; it += nwarps) {
+        const int kf = it / p.cam_parts, part = it % p.cam_parts;
+        const int beg = p.c_ptr[kf], end = p.c_ptr[kf + 1], len = end - beg;
+        const int per = (len + p.cam_parts - 1) / p.cam_parts;
+        const int s0 = beg + part * per, s1 = min(s0 + per, end);
+        double c6[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = s0 + lane; k < s1; k += 32) {
+            const int e = p.c_edges[k];
+            const int li = p.e_l[e];
+            if (li < 0) continue;
+            const double* W = p.W + 18 * (size_t)e;
+            const double d0 = p.db[3 * li], d1 = p.db[3 * li + 1], d2 = p.db[3 * li + 2];
+#pragma unroll
+            for (int r = 0; r < 6; r++) c6[r] += W[r * 3] * d0 + W[r * 3 + 1] * d1 + W[r * 3 + 2] * d2;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c6[i] += __shfl_down_sync(0xffffffffu, c6[i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) p.part[(size_t)it * 27 + i] = c6[i];
+        }
+    }
+}
+__device__ void phase_finish_bs(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < p.n; i += nt) {
+        const int kf = i / 6, j = i % 6;
+        double s = 0;
+        for (int part = 0; part < p.cam_parts; part++) s += p.part[((size_t)kf * p.cam_parts + part) * 27 + j];
+        p.bs[i] = p.bp[i] - s;
+    }
+}
+
+// Dense LDL^T of the reduced system by the whole CTA, in place in S (lower part), then the two triangular solves.
+// ref linear_solver_dense.h:65-113 + Eigen LDLT: fails (returns false) when a pivot is negative (isPositive() false);
+// zero pivots are tolerated like Eigen (no scaling, pseudo-inverse in the solve). x is written only on success.
+__device__ bool phase_ldlt_solve(const BaDev& p, double* sh)
+{
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x;
+    if (n == 0) return true;
+    double* S = p.S;
+    __shared__ int s_neg;
+    if (tid == 0) s_neg = 0;
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        const double d = S[(size_t)k * n + k];
+        if (d < 0) { if (tid == 0) s_neg = 1; }
+        const bool valid = fabs(d) > 0;
+        // column k of L below the diagonal is S[i][k] / d; the update uses the unscaled a_ik = l_ik * d
+        const int rs = n - k - 1;
+        const int tri = rs * (rs + 1) / 2;
+        __syncthreads();
+        if (valid) {
+            for (int t = tid; t < tri; t += nt) {
+                // map t -> (i, j) with k < j <= i < n  (row-major over the lower triangle)
+                int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+                while ((r + 1) * (r + 2) / 2 <= t) r++;
+                while (r * (r + 1) / 2 > t) r--;
+                const int c = t - r * (r + 1) / 2;
+                const int i = k + 1 + r, j = k + 1 + c;
+                S[(size_t)i * n + j] -= S[(size_t)i * n + k] * (S[(size_t)j * n + k] / d);
+            }
+        }
+        __syncthreads();
+        if (valid) for (int i = k + 1 + tid; i < n; i += nt) S[(size_t)i * n + k] /= d;
+    }
+    __syncthreads();
+    if (s_neg) return false;
+    // solve L y = b (forward), D, L^T x = y (backward); y lives in sh-independent global bs (overwritten)
+    double* y = p.bs;
+    for (int k = 0; k < n; k++) {
+        __syncthreads();
+        const double yk = y[k];
+        for (int i = k + 1 + tid; i < n; i += nt) y[i] -= S[(size_t)i * n + k] * yk;
+    }
+    __syncthreads();
+    const double tol = 1.0 / DBL_MAX;
+    for (int i = tid; i < n; i += nt) { const double d = S[(size_t)i * n + i]; y[i] = (fabs(d) > tol) ? y[i] / d : 0.0; }
+    for (int k = n - 1; k >= 0; k--) {
+        __syncthreads();
+        const double xk = y[k];
+        for (int i = tid; i < k; i += nt) y[i] -= S[(size_t)k * n + i] * xk;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nt) p.x[i] = y[i];
+    (void)sh;
+    return true;
+}
+
+// ref block_solver.hpp:418-444: x_l = D^-1 (b_l - W^T x_p)
+__device__ void phase_backsub(const BaDev& p, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double c0 = p.bl[3 * li], c1 = p.bl[3 * li + 1], c2 = p.bl[3 * li + 2];
+        for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
+            const int e = p.l_edges[k];
+            const int hj = p.cam_h[p.e_cam[e]];
+            if (hj < 0) continue;
+            const double* W = p.W + 18 * (size_t)e;
+            const double* xp = p.x + 6 * hj;
+#pragma unroll
+            for (int r = 0; r < 6; r++) { c0 -= W[r * 3] * xp[r]; c1 -= W[r * 3 + 1] * xp[r]; c2 -= W[r * 3 + 2] * xp[r]; }
+        }
+        const double* D = p.Dinv + 9 * (size_t)li;
+        p.x[p.n + 3 * li] = D[0] * c0 + D[1] * c1 + D[2] * c2;
+        p.x[p.n + 3 * li + 1] = D[3] * c0 + D[4] * c1 + D[5] * c2;
+        p.x[p.n + 3 * li + 2] = D[6] * c0 + D[7] * c1 + D[8] * c2;
+    }
+}
+// push (ref base_vertex.h:92-94) + update (ref sparse_optimizer.cpp:433-446, oplusImpl)
+__device__ void phase_backup(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < p.Kf; i += nt) {
+        const int c = p.c_cam[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) p.cam_bak[7 * i + j] = p.cam_q[4 * c + j];
+#pragma unroll
+        for (int j = 0; j < 3; j++) p.cam_bak[7 * i + 4 + j] = p.cam_t[3 * c + j];
+    }
+    for (int i = tid; i < p.Pl * 3; i += nt) p.pt_bak[i] = p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3];
+}
+__device__ void phase_restore(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < p.Kf; i += nt) {
+        const int c = p.c_cam[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) p.cam_q[4 * c + j] = p.cam_bak[7 * i + j];
+#pragma unroll
+        for (int j = 0; j < 3; j++) p.cam_t[3 * c + j] = p.cam_bak[7 * i + 4 + j];
+    }
+    for (int i = tid; i < p.Pl * 3; i += nt) p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3] = p.pt_bak[i];
+}
+__device__ void phase_update(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < p.Kf; i += nt) { const int c = p.c_cam[i]; pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i); }
+    for (int i = tid; i < p.Pl * 3; i += nt) p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3] += p.x[p.n + i];
+}
+// ref optimization_algorithm_levenberg.cpp:167-174 computeScale
+__device__ double phase_scale(const BaDev& p, double lambda, double* sh)
+{
+    double acc = 0;
+    const int tot = p.n + 3 * p.Pl;
+    for (int j = threadIdx.x; j < tot; j += blockDim.x) {
+        const double xj = p.x[j], bj = (j < p.n) ? p.bp[j] : p.bl[j - p.n];
+        acc += xj * (lambda * xj + bj);
+    }
+    return block_sum(acc, sh);
+}
+// ref BundlerLib.cpp:385-427: cheirality + squared-error test per active observation, inlier error accumulation
+__device__ void phase_classify(const BaDev& p, double maxErrSq, double* sh, double& errSum, int& inliers)
+{
+    double acc = 0, cnt = 0;
+    for (int e = threadIdx.x; e < p.Ea; e += blockDim.x) {
+        const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1];
+        const double ss = e0 * e0 + e1 * e1;
+        const int c = p.e_cam[e];
+        const double qc[4] = {-p.cam_q[4 * c], -p.cam_q[4 * c + 1], -p.cam_q[4 * c + 2], p.cam_q[4 * c + 3]};
+        const double nt3[3] = {-p.cam_t[3 * c], -p.cam_t[3 * c + 1], -p.cam_t[3 * c + 2]};
+        double wt[3], fw[3];
+        const double z[3] = {0, 0, 1};
+        q_rot(qc, nt3, wt);
+        q_rot(qc, z, fw);
+        const double* X = p.pt_X + 3 * (size_t)p.e_pt[e];
+        const double dot = (X[0] - wt[0]) * fw[0] + (X[1] - wt[1]) * fw[1] + (X[2] - wt[2]) * fw[2];
+        const bool out = (dot <= 0) || (ss > maxErrSq);
+        p.flags[e] = out ? 1 : 0;
+        if (!out) { acc += ss; cnt += 1.0; }
+    }
+    errSum = block_sum(acc, sh);
+    inliers = (int)block_sum(cnt, sh);
+}
+
+// ------------------------------------------------------------------------------------------------ the persistent LM kernel
+// One CTA per problem runs StepBundleAdjustment's whole loop: for each Huber width one g2o LM iteration
+// (ref optimization_algorithm_levenberg.cpp:57-149, up to 10 lambda trials), then the outlier classification.
+constexpr int kBaThreads = 512;
+
+__global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq)
+{
+    __shared__ double sh[33];
+    __shared__ double s_lambda, s_ni, s_rho;
+    __shared__ int s_accept, s_stop;
+    __shared__ BaDev s_p;
+    const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    if (tid == 0) s_p = probs[blockIdx.x];
+    __syncthreads();
+    const BaDev& p = s_p;
+    BaCtl* ctl = p.ctl;
+    if (tid == 0) { s_lambda = ctl->lambda; s_ni = ctl->ni; s_stop = 0; }
+    __syncthreads();
+    int iteration = ctl->iteration;
+    long long trials = 0, iters = 0;
+
+    for (int it = 0; it < nIters; it++) {
+        if (s_stop) break;
+        const double delta = (double)huberW[it];
+        phase_errors(p, tid, nt);
+        __syncthreads();
+        double currentChi = phase_chi2(p, delta, sh);
+        phase_build_points(p, delta, tid, nt);
+        phase_build_cams(p, delta, warp, nw, lane);
+        __syncthreads();
+        phase_finish_cams(p, tid, nt);
+        __syncthreads();
+        if (iteration == 0) {
+            const double md = phase_max_diag(p, sh);
+            if (tid == 0) { s_lambda = ctl->user_lambda_init > 0 ? ctl->user_lambda_init : 1e-5 * md; s_ni = 2; }
+            __syncthreads();
+        }
+        double rho = 0;
+        int qmax = 0;
+        bool lambdaFinite = true;
+        do {
+            const double lambda = s_lambda;
+            phase_backup(p, tid, nt);
+            phase_schur_points(p, lambda, tid, nt);
+            __syncthreads();
+            phase_schur_blocks(p, lambda, warp, nw, lane);
+            __syncthreads();
+            phase_finish_bs(p, tid, nt);
+            __syncthreads();
+            const bool ok2 = phase_ldlt_solve(p, sh);
+            __syncthreads();
+            if (ok2) phase_backsub(p, tid, nt);
+            __syncthreads();
+            phase_update(p, tid, nt);
+            __syncthreads();
+            phase_errors(p, tid, nt);
+            __syncthreads();
+            double tempChi = phase_chi2(p, delta, sh);
+            if (!ok2) tempChi = DBL_MAX;
+            const double scale = phase_scale(p, lambda, sh) + 1e-3;
+            if (tid == 0) {
+                double r = (currentChi - tempChi) / scale;
+                s_rho = r;
+                if (r > 0 && isfinite(tempChi)) {
+                    double alpha = 1. - pow((2 * r - 1), 3.0);
+                    alpha = fmin(alpha, 2. / 3.);
+                    s_lambda = lambda * fmax(1. / 3., alpha);
+                    s_ni = 2;
+                    s_accept = 1;
+                } else {
+                    s_lambda = lambda * s_ni;
+                    s_ni = s_ni * 2;
+                    s_accept = 0;
+                }
+            }
+            __syncthreads();
+            rho = s_rho;
+            if (s_accept) currentChi = tempChi;
+            else {
+                phase_restore(p, tid, nt);
+                __syncthreads();
+                if (!isfinite(s_lambda)) { lambdaFinite = false; trials++; break; }
+            }
+            qmax++;
+            trials++;
+        } while (rho < 0 && qmax < 10);
+        iteration++;
+        iters++;
+        if (qmax == 10 || rho == 0 || !lambdaFinite) { if (tid == 0) s_stop = 1; }     // Terminate => Step() == false => break
+        __syncthreads();
+    }
+    double errSum; int inl;
+    phase_classify(p, (double)maxErrSq, sh, errSum, inl);
+    if (tid == 0) {
+        ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
+        ctl->err_sum = errSum; ctl->inlier_count = inl; ctl->stop_flag = s_stop;
+        ctl->lm_iters += iters; ctl->lm_trials += trials;
+    }
+}
+
+} // namespace mage
+
+// ====================================================================================================================
+// Host side
+// ====================================================================================================================
+using namespace mage;
+
+namespace {
+
+template <class T> void R_to_q_host(const T* m, T* q)          // Eigen quaternion-from-matrix
+{
+    T t = m[0] + m[4] + m[8];
+    if (t > T(0)) {
+        t = std::sqrt(t + T(1)); q[3] = T(0.5) * t; t = T(0.5) / t;
+        q[0] = (m[7] - m[5]) * t; q[1] = (m[2] - m[6]) * t; q[2] = (m[3] - m[1]) * t;
+    } else {
+        int i = 0;
+        if (m[4] > m[0]) i = 1;
+        if (m[8] > m[i * 3 + i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = std::sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + T(1));
+        q[i] = T(0.5) * t; t = T(0.5) / t;
+        q[3] = (m[k * 3 + j] - m[j * 3 + k]) * t;
+        q[j] = (m[j * 3 + i] + m[i * 3 + j]) * t;
+        q[k] = (m[k * 3 + i] + m[i * 3 + k]) * t;
+    }
+}
+
+struct HostObs { double u, v, info; int cam, pt; bool set, removed; long seq; };
+
+} // namespace
+
+struct mage_ba_s {
+    bool points_fixed = false;
+    int K = 0, P = 0, E = 0;
+    // host mirrors of the problem definition (state is authoritative on the device once uploaded)
+    std::vector<double> cam_q, cam_t, cam_f, cam_cx, cam_cy, pt_X;
+    std::vector<char> cam_fixed, cam_set, pt_set;
+    std::vector<HostObs> obs;
+    long next_seq = 0;
+    bool dirty = true, useless = false, state_uploaded = false, host_state_valid = true;
+    double user_lambda_init = 0, lambda = -1;
+    int iteration_reset = 1;           // SetCurrentLambda / InitializeOptimization reset m_iteration to 0
+    std::vector<int> active;           // active observation ids in insertion order
+    // device
+    DeviceArena state, work;
+    BaDev dev{};
+    BaDev* d_dev = nullptr;
+    BaCtl* d_ctl = nullptr;
+    float* d_huber = nullptr; int huber_cap = 0;
+    BaDev* d_table = nullptr; int table_cap = 0;      // descriptor table of mage_ba_step_many (owned by the lead handle)
+    cudaStream_t stream = nullptr;
+    int64_t stats[4] = {0, 0, 0, 0};
+};
+
+static int ba_upload_state(mage_ba_t h)
+{
+    // camera / point state and intrinsics live in one arena sized at first upload (pools are allocated once, ref :198-230)
+    DeviceArena& A = h->state;
+    if (!A.base) {
+        size_t oq = A.reserve(sizeof(double) * 4 * h->K), ot = A.reserve(sizeof(double) * 3 * h->K);
+        size_t of = A.reserve(sizeof(double) * h->K), ox = A.reserve(sizeof(double) * h->K), oy = A.reserve(sizeof(double) * h->K);
+        size_t op = A.reserve(sizeof(double) * 3 * h->P);
+        size_t oc = A.reserve(sizeof(BaCtl)), od = A.reserve(sizeof(BaDev));
+        MAGE_CUDA_TRY(A.commit());
+        h->dev.cam_q = A.at<double>(oq); h->dev.cam_t = A.at<double>(ot);
+        h->dev.cam_f = A.at<double>(of); h->dev.cam_cx = A.at<double>(ox); h->dev.cam_cy = A.at<double>(oy);
+        h->dev.pt_X = A.at<double>(op);
+        h->d_ctl = A.at<BaCtl>(oc); h->d_dev = A.at<BaDev>(od);
+        BaCtl c{}; c.lambda = -1; c.ni = 2;
+        MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+    }
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->dev.cam_q, h->cam_q.data(), sizeof(double) * 4 * h->K, cudaMemcpyHostToDevice, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->dev.cam_t, h->cam_t.data(), sizeof(double) * 3 * h->K, cudaMemcpyHostToDevice, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync((void*)h->dev.cam_f, h->cam_f.data(), sizeof(double) * h->K, cudaMemcpyHostToDevice, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync((void*)h->dev.cam_cx, h->cam_cx.data(), sizeof(double) * h->K, cudaMemcpyHostToDevice, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync((void*)h->dev.cam_cy, h->cam_cy.data(), sizeof(double) * h->K, cudaMemcpyHostToDevice, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->dev.pt_X, h->pt_X.data(), sizeof(double) * 3 * h->P, cudaMemcpyHostToDevice, h->stream));
+    h->state_uploaded = true;
+    return MAGE_OK;
+}
+
+// ref sparse_optimizer.cpp:208-272 initializeOptimization + :168-192 buildIndexMapping + block_solver.hpp:103-256
+// buildStructure, done on the host whenever the edge set changed (BundlerLib.cpp:156-166); uploads the index structure.
+static int ba_build_structure(mage_ba_t h)
+{
+    h->active.clear();
+    std::vector<std::pair<long, int>> order;
+    for (int e = 0; e < h->E; e++) {
+        const HostObs& o = h->obs[e];
+        if (!o.set || o.removed) continue;
+        if (h->points_fixed && h->cam_fixed[o.cam]) continue;               // allVerticesFixed
+        order.push_back({o.seq, e});
+    }
+    std::sort(order.begin(), order.end());                                   // EdgeIDCompare = insertion order
+    for (auto& pr : order) h->active.push_back(pr.second);
+    const int Ea = (int)h->active.size();
+    std::vector<char> camA(h->K, 0), ptA(h->P, 0);
+    for (int e : h->active) { camA[h->obs[e].cam] = 1; ptA[h->obs[e].pt] = 1; }
+    std::vector<int> cam_h(h->K, -1), pt_l(h->P, -1), c_cam, l_pt;
+    for (int k = 0; k < h->K; k++) if (camA[k] && !h->cam_fixed[k]) { cam_h[k] = (int)c_cam.size(); c_cam.push_back(k); }
+    if (!h->points_fixed)       // point vertex ids count down (ref BundlerLib.cpp:210-218): Hessian order = descending index
+        for (int i = h->P - 1; i >= 0; i--) if (ptA[i]) { pt_l[i] = (int)l_pt.size(); l_pt.push_back(i); }
+    const int Kf = (int)c_cam.size(), Pl = (int)l_pt.size(), n = 6 * Kf;
+    h->useless = (Kf + Pl) == 0;
+    h->dirty = false;
+    h->iteration_reset = 1;
+    h->stats[3]++;
+    if (h->useless) { h->dev.Ea = 0; return MAGE_OK; }
+
+    std::vector<int> e_cam(Ea), e_pt(Ea), e_l(Ea);
+    std::vector<double> e_uv(2 * (size_t)Ea), e_info(Ea);
+    std::vector<int> l_ptr(Pl + 1, 0), c_ptr(Kf + 1, 0);
+    for (int a = 0; a < Ea; a++) {
+        const HostObs& o = h->obs[h->active[a]];
+        e_cam[a] = o.cam; e_pt[a] = o.pt; e_l[a] = pt_l[o.pt];
+        e_uv[2 * a] = o.u; e_uv[2 * a + 1] = o.v; e_info[a] = o.info;
+        if (pt_l[o.pt] >= 0) l_ptr[pt_l[o.pt] + 1]++;
+        if (cam_h[o.cam] >= 0) c_ptr[cam_h[o.cam] + 1]++;
+    }
+    for (int i = 0; i < Pl; i++) l_ptr[i + 1] += l_ptr[i];
+    for (int i = 0; i < Kf; i++) c_ptr[i + 1] += c_ptr[i];
+    std::vector<int> l_edges(l_ptr[Pl]), c_edges(c_ptr[Kf]), lf(l_ptr.begin(), l_ptr.end() - 1), cf(c_ptr.begin(), c_ptr.end() - 1);
+    for (int a = 0; a < Ea; a++) {
+        if (e_l[a] >= 0) l_edges[lf[e_l[a]]++] = a;
+        if (cam_h[e_cam[a]] >= 0) c_edges[cf[cam_h[e_cam[a]]]++] = a;
+    }
+    // upper blocks of the reduced system and their (edge, edge) pair lists; every diagonal block exists
+    std::map<std::pair<int, int>, std::vector<int2>> blocks;
+    for (int i = 0; i < Kf; i++) blocks[{i, i}];
+    for (int li = 0; li < Pl; li++)
+        for (int k1 = l_ptr[li]; k1 < l_ptr[li + 1]; k1++) {
+            const int a1 = l_edges[k1], i1 = cam_h[e_cam[a1]];
+            if (i1 < 0) continue;
+            for (int k2 = l_ptr[li]; k2 < l_ptr[li + 1]; k2++) {
+                const int a2 = l_edges[k2], i2 = cam_h[e_cam[a2]];
+                if (i2 < 0 || i2 < i1) continue;
+                blocks[{i1, i2}].push_back(make_int2(a1, a2));
+            }
+        }
+    std::vector<int> blk_ij, blk_ptr(1, 0);
+    std::vector<int2> pairs;
+    for (auto& kv : blocks) {
+        blk_ij.push_back(kv.first.first); blk_ij.push_back(kv.first.second);
+        pairs.insert(pairs.end(), kv.second.begin(), kv.second.end());
+        blk_ptr.push_back((int)pairs.size());
+    }
+    const int nblk = (int)blk_ij.size() / 2;
+    const int cam_parts = std::max(1, std::min(8, (kBaThreads / 32) / std::max(Kf, 1)));
+
+    DeviceArena& W = h->work;
+    W.release(); W = DeviceArena();
+    auto rI = [&](size_t cnt) { return W.reserve(sizeof(int) * std::max<size_t>(cnt, 1)); };
+    auto rD = [&](size_t cnt) { return W.reserve(sizeof(double) * std::max<size_t>(cnt, 1)); };
+    size_t o_camh = rI(h->K), o_ecam = rI(Ea), o_ept = rI(Ea), o_el = rI(Ea), o_euv = rD(2 * (size_t)Ea), o_einfo = rD(Ea);
+    size_t o_lpt = rI(Pl), o_lptr = rI(Pl + 1), o_ledges = rI(l_edges.size());
+    size_t o_ccam = rI(Kf), o_cptr = rI(Kf + 1), o_cedges = rI(c_edges.size());
+    size_t o_bij = rI(blk_ij.size()), o_bptr = rI(blk_ptr.size()), o_pairs = W.reserve(sizeof(int2) * std::max<size_t>(pairs.size(), 1));
+    size_t o_err = rD(2 * (size_t)Ea), o_W = rD(18 * (size_t)Ea), o_WD = rD(18 * (size_t)Ea), o_Hll = rD(9 * (size_t)Pl), o_bl = rD(3 * (size_t)Pl);
+    size_t o_Dinv = rD(9 * (size_t)Pl), o_db = rD(3 * (size_t)Pl), o_Hpp = rD(36 * (size_t)Kf), o_bp = rD(n), o_S = rD((size_t)n * n), o_bs = rD(n);
+    size_t o_x = rD(n + 3 * (size_t)Pl), o_cbak = rD(7 * (size_t)Kf), o_pbak = rD(3 * (size_t)Pl), o_part = rD((size_t)Kf * cam_parts * 27);
+    size_t o_flags = W.reserve(std::max(Ea, 1));
+    MAGE_CUDA_TRY(W.commit());
+    MAGE_CUDA_TRY(cudaMemsetAsync(W.base, 0, W.size, h->stream));
+    auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+        return bytes ? cudaMemcpyAsync(W.base + off, src, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+    };
+    MAGE_CUDA_TRY(up(o_camh, cam_h.data(), sizeof(int) * h->K));
+    MAGE_CUDA_TRY(up(o_ecam, e_cam.data(), sizeof(int) * Ea)); MAGE_CUDA_TRY(up(o_ept, e_pt.data(), sizeof(int) * Ea));
+    MAGE_CUDA_TRY(up(o_el, e_l.data(), sizeof(int) * Ea));
+    MAGE_CUDA_TRY(up(o_euv, e_uv.data(), sizeof(double) * 2 * Ea)); MAGE_CUDA_TRY(up(o_einfo, e_info.data(), sizeof(double) * Ea));
+    MAGE_CUDA_TRY(up(o_lpt, l_pt.data(), sizeof(int) * Pl)); MAGE_CUDA_TRY(up(o_lptr, l_ptr.data(), sizeof(int) * (Pl + 1)));
+    MAGE_CUDA_TRY(up(o_ledges, l_edges.data(), sizeof(int) * l_edges.size()));
+    MAGE_CUDA_TRY(up(o_ccam, c_cam.data(), sizeof(int) * Kf)); MAGE_CUDA_TRY(up(o_cptr, c_ptr.data(), sizeof(int) * (Kf + 1)));
+    MAGE_CUDA_TRY(up(o_cedges, c_edges.data(), sizeof(int) * c_edges.size()));
+    MAGE_CUDA_TRY(up(o_bij, blk_ij.data(), sizeof(int) * blk_ij.size())); MAGE_CUDA_TRY(up(o_bptr, blk_ptr.data(), sizeof(int) * blk_ptr.size()));
+    MAGE_CUDA_TRY(up(o_pairs, pairs.data(), sizeof(int2) * pairs.size()));
+    BaDev& d = h->dev;
+    d.K = h->K; d.P = h->P; d.Ea = Ea; d.Kf = Kf; d.Pl = Pl; d.n = n; d.nblk = nblk; d.cam_parts = cam_parts;
+    d.cam_h = W.at<int>(o_camh); d.e_cam = W.at<int>(o_ecam); d.e_pt = W.at<int>(o_ept); d.e_l = W.at<int>(o_el);
+    d.e_uv = W.at<double>(o_euv); d.e_info = W.at<double>(o_einfo);
+    d.l_pt = W.at<int>(o_lpt); d.l_ptr = W.at<int>(o_lptr); d.l_edges = W.at<int>(o_ledges);
+    d.c_cam = W.at<int>(o_ccam); d.c_ptr = W.at<int>(o_cptr); d.c_edges = W.at<int>(o_cedges);
+    d.blk_ij = W.at<int>(o_bij); d.blk_ptr = W.at<int>(o_bptr); d.pairs = W.at<int2>(o_pairs);
+    d.err = W.at<double>(o_err); d.W = W.at<double>(o_W); d.WD = W.at<double>(o_WD); d.Hll = W.at<double>(o_Hll); d.bl = W.at<double>(o_bl);
+    d.Dinv = W.at<double>(o_Dinv); d.db = W.at<double>(o_db); d.Hpp = W.at<double>(o_Hpp); d.bp = W.at<double>(o_bp); d.S = W.at<double>(o_S);
+    d.bs = W.at<double>(o_bs); d.x = W.at<double>(o_x); d.cam_bak = W.at<double>(o_cbak); d.pt_bak = W.at<double>(o_pbak); d.part = W.at<double>(o_part);
+    d.flags = W.at<unsigned char>(o_flags);
+    d.ctl = h->d_ctl;
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
+    // pageable staging vectors go out of scope on return: make sure the copies have been consumed
+    MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return MAGE_OK;
+}
+
+extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
+{
+    MAGE_REQUIRE(out, MAGE_ERR_INVALID, "mage_ba_create: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: bundle adjustment has no CPU fallback"); return MAGE_ERR_CUDA; }
+    mage_ba_s* h = new mage_ba_s();
+    h->points_fixed = are_points_fixed != 0;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return MAGE_ERR_CUDA; }
+    *out = h;
+    return MAGE_OK;
+}
+
+extern "C" void mage_ba_destroy(mage_ba_t h)
+{
+    if (!h) return;
+    cudaStreamSynchronize(h->stream);
+    h->state.release(); h->work.release();
+    if (h->d_huber) cudaFree(h->d_huber);
+    if (h->d_table) cudaFree(h->d_table);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int mage_ba_alloc_cameras(mage_ba_t h, int count)
+{
+    MAGE_REQUIRE(h && count >= 0, MAGE_ERR_INVALID, "mage_ba_alloc_cameras: bad argument");
+    MAGE_REQUIRE(h->K == 0 && !h->state_uploaded, MAGE_ERR_INVALID, "can only allocate once");      // ref :200 assert
+    h->K = count;
+    h->cam_q.assign(4 * (size_t)count, 0.0); h->cam_t.assign(3 * (size_t)count, 0.0);
+    for (int k = 0; k < count; k++) h->cam_q[4 * k + 3] = 1.0;
+    h->cam_f.assign(count, 1.0); h->cam_cx.assign(count, 0.0); h->cam_cy.assign(count, 0.0);
+    h->cam_fixed.assign(count, 0); h->cam_set.assign(count, 0);
+    return MAGE_OK;
+}
+extern "C" int mage_ba_alloc_points(mage_ba_t h, int count)
+{
+    MAGE_REQUIRE(h && count >= 0, MAGE_ERR_INVALID, "mage_ba_alloc_points: bad argument");
+    MAGE_REQUIRE(h->P == 0 && !h->state_uploaded, MAGE_ERR_INVALID, "can only allocate once");
+    h->P = count; h->pt_X.assign(3 * (size_t)count, 0.0); h->pt_set.assign(count, 0);
+    return MAGE_OK;
+}
+extern "C" int mage_ba_alloc_observations(mage_ba_t h, int count)
+{
+    MAGE_REQUIRE(h && count >= 0, MAGE_ERR_INVALID, "mage_ba_alloc_observations: bad argument");
+    MAGE_REQUIRE(h->E == 0, MAGE_ERR_INVALID, "can only allocate once");
+    h->E = count; h->obs.assign(count, HostObs{0, 0, 0, -1, -1, false, false, -1});
+    return MAGE_OK;
+}
+
+// ref BundlerLib.cpp:261-276: estimate = SE3Quat(Quaternionf(R).normalized() -> double, t -> double); f = intrinsics[2]
+extern "C" int mage_ba_set_camera(mage_ba_t h, int idx, const float* pos, const float* rot, const float* intr, int is_fixed)
+{
+    MAGE_REQUIRE(h && pos && rot && intr && idx >= 0 && idx < h->K, MAGE_ERR_INVALID, "mage_ba_set_camera: bad argument (idx %d of %d)", idx, h ? h->K : 0);
+    MAGE_REQUIRE(!h->state_uploaded, MAGE_ERR_UNSUPPORTED, "cameras cannot be re-set after the first step");
+    float m[9], q[4];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) m[r * 3 + c] = rot[c * 3 + r];
+    R_to_q_host<float>(m, q);
+    float nn = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (nn > 0.f) { float nrm = std::sqrt(nn); for (int i = 0; i < 4; i++) q[i] = q[i] / nrm; }
+    double qd[4] = {q[0], q[1], q[2], q[3]};
+    if (qd[3] < 0) for (int i = 0; i < 4; i++) qd[i] = -qd[i];
+    double n = std::sqrt(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
+    for (int i = 0; i < 4; i++) h->cam_q[4 * idx + i] = qd[i] / n;
+    for (int i = 0; i < 3; i++) h->cam_t[3 * idx + i] = pos[i];
+    h->cam_f[idx] = intr[2]; h->cam_cx[idx] = intr[0]; h->cam_cy[idx] = intr[1];
+    h->cam_fixed[idx] = is_fixed != 0; h->cam_set[idx] = 1;
+    h->dirty = true;
+    return MAGE_OK;
+}
+extern "C" int mage_ba_fix_camera(mage_ba_t h, int idx, int value)
+{
+    MAGE_REQUIRE(h && idx >= 0 && idx < h->K, MAGE_ERR_INVALID, "mage_ba_fix_camera: bad index");
+    if ((h->cam_fixed[idx] != 0) != (value != 0)) { h->cam_fixed[idx] = value != 0; h->dirty = true; }
+    return MAGE_OK;
+}
+extern "C" int mage_ba_set_point(mage_ba_t h, int idx, const float* xyz)
+{
+    MAGE_REQUIRE(h && xyz && idx >= 0 && idx < h->P, MAGE_ERR_INVALID, "mage_ba_set_point: bad argument");
+    MAGE_REQUIRE(!h->state_uploaded, MAGE_ERR_UNSUPPORTED, "points cannot be re-set after the first step");
+    for (int i = 0; i < 3; i++) h->pt_X[3 * (size_t)idx + i] = xyz[i];
+    h->pt_set[idx] = 1; h->dirty = true;
+    return MAGE_OK;
+}
+extern "C" int mage_ba_set_observation(mage_ba_t h, int idx, const float* uv, int cam, int pt, float info)
+{
+    MAGE_REQUIRE(h && uv && idx >= 0 && idx < h->E && cam >= 0 && cam < h->K && pt >= 0 && pt < h->P, MAGE_ERR_INVALID,
+                 "mage_ba_set_observation: bad argument (idx %d cam %d pt %d)", idx, cam, pt);
+    HostObs& o = h->obs[idx];
+    o.u = uv[0]; o.v = uv[1]; o.info = info; o.cam = cam; o.pt = pt; o.set = true; o.removed = false; o.seq = h->next_seq++;
+    h->dirty = true;
+    return MAGE_OK;
+}
+extern "C" int mage_ba_set_cameras_bulk(mage_ba_t h, int n, const float* pos, const float* rot, const float* intr, const int32_t* fixed)
+{
+    MAGE_REQUIRE(h && pos && rot && intr && fixed && n <= h->K, MAGE_ERR_INVALID, "mage_ba_set_cameras_bulk: bad argument");
+    for (int k = 0; k < n; k++) { int rc = mage_ba_set_camera(h, k, pos + 3 * k, rot + 9 * k, intr + 4 * k, fixed[k]); if (rc) return rc; }
+    return MAGE_OK;
+}
+extern "C" int mage_ba_set_points_bulk(mage_ba_t h, int n, const float* xyz)
+{
+    MAGE_REQUIRE(h && xyz && n <= h->P, MAGE_ERR_INVALID, "mage_ba_set_points_bulk: bad argument");
+    for (int i = 0; i < n; i++) { int rc = mage_ba_set_point(h, i, xyz + 3 * (size_t)i); if (rc) return rc; }
+    return MAGE_OK;
+}
+extern "C" int mage_ba_set_observations_bulk(mage_ba_t h, int n, const float* uv, const int32_t* cam, const int32_t* pt, const float* info)
+{
+    MAGE_REQUIRE(h && uv && cam && pt && info && n <= h->E, MAGE_ERR_INVALID, "mage_ba_set_observations_bulk: bad argument");
+    for (int e = 0; e < n; e++) { int rc = mage_ba_set_observation(h, e, uv + 2 * (size_t)e, cam[e], pt[e], info[e]); if (rc) return rc; }
+    return MAGE_OK;
+}
+// ref BundlerLib.cpp:123-130 + :352-355: resets the iteration counter to 0 and sets the user lambda
+extern "C" int mage_ba_set_lambda(mage_ba_t h, float l)
+{
+    MAGE_REQUIRE(h, MAGE_ERR_INVALID, "null handle");
+    h->user_lambda_init = l; h->iteration_reset = 1;
+    return MAGE_OK;
+}
+extern "C" int mage_ba_get_lambda(mage_ba_t h, float* l)
+{
+    MAGE_REQUIRE(h && l, MAGE_ERR_INVALID, "null argument");
+    *l = (float)h->lambda;
+    return MAGE_OK;
+}
+
+static int ba_prepare(mage_ba_t h, const float* huber, int n_iters)
+{
+    if (!h->state_uploaded) { int rc = ba_upload_state(h); if (rc) return rc; }
+    if (h->dirty) { int rc = ba_build_structure(h); if (rc) return rc; }
+    if (h->useless) return MAGE_OK;
+    if (n_iters > h->huber_cap) {
+        if (h->d_huber) cudaFree(h->d_huber);
+        h->huber_cap = std::max(16, n_iters);
+        MAGE_CUDA_TRY(cudaMalloc(&h->d_huber, sizeof(float) * h->huber_cap));
+    }
+    if (n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, h->stream));
+    if (h->iteration_reset) {
+        // m_iteration = 0 (and the user lambda) take effect at the next solve()
+        struct { double user; } u{h->user_lambda_init};
+        MAGE_CUDA_TRY(cudaMemcpyAsync(&h->d_ctl->user_lambda_init, &u.user, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        int zero = 0;
+        MAGE_CUDA_TRY(cudaMemcpyAsync(&h->d_ctl->iteration, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->iteration_reset = 0;
+    }
+    return MAGE_OK;
+}
+
+static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, float* mean)
+{
+    *n_out = 0;
+    if (h->useless) { *mean = std::numeric_limits<float>::quiet_NaN(); return MAGE_OK; }
+    BaCtl c;
+    std::vector<unsigned char> flags(std::max(h->dev.Ea, 1));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(flags.data(), h->dev.flags, h->dev.Ea, cudaMemcpyDeviceToHost, h->stream));
+    MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->lambda = c.lambda;
+    h->stats[0] = c.lm_iters; h->stats[1] = c.lm_trials;
+    h->host_state_valid = false;
+    int m = 0;
+    for (int a = 0; a < h->dev.Ea; a++)
+        if (flags[a]) {
+            const int e = h->active[a];
+            h->obs[e].removed = true; h->dirty = true;                 // removeEdge => m_dirty (ref :112-116, :435-441)
+            if (outliers && m < cap) outliers[m] = (unsigned)e;
+            m++;
+        }
+    *n_out = m;
+    *mean = (float)(c.err_sum / (double)c.inlier_count);               // NaN when no inlier, like the reference's 0/0
+    return MAGE_OK;
+}
+
+extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float max_err_sq, unsigned int* outliers, int cap,
+                            int* n_outliers, float* mean_sq_error)
+{
+    MAGE_REQUIRE(h && n_outliers && mean_sq_error && (huber || n_iters == 0) && n_iters >= 0, MAGE_ERR_INVALID, "mage_ba_step: bad argument");
+    int rc = ba_prepare(h, huber, n_iters);
+    if (rc) return rc;
+    if (!h->useless) {
+        k_ba_step<<<1, kBaThreads, 0, h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq);
+        MAGE_CUDA_TRY(cudaGetLastError());
+        h->stats[2]++;
+    }
+    return ba_finish(h, outliers, cap, n_outliers, mean_sq_error);
+}
+
+extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n_iters, float max_err_sq, float* means)
+{
+    MAGE_REQUIRE(hs && n >= 1 && means && (huber || n_iters == 0), MAGE_ERR_INVALID, "mage_ba_step_many: bad argument");
+    // gather the per-problem descriptors into one table and step every problem with ONE launch (grid = problems)
+    std::vector<BaDev> table;
+    std::vector<int> live;
+    for (int i = 0; i < n; i++) {
+        int rc = ba_prepare(hs[i], huber, n_iters);
+        if (rc) return rc;
+        if (!hs[i]->useless) { table.push_back(hs[i]->dev); live.push_back(i); }
+    }
+    mage_ba_t lead = hs[0];
+    if (!table.empty()) {
+        if ((int)table.size() > lead->table_cap) {
+            if (lead->d_table) cudaFree(lead->d_table);
+            lead->table_cap = (int)table.size();
+            MAGE_CUDA_TRY(cudaMalloc(&lead->d_table, sizeof(BaDev) * table.size()));
+        }
+        BaDev* d_table = lead->d_table;
+        cudaError_t e = cudaMemcpyAsync(d_table, table.data(), sizeof(BaDev) * table.size(), cudaMemcpyHostToDevice, lead->stream);
+        for (int i : live) if (e == cudaSuccess && hs[i] != lead) e = cudaStreamSynchronize(hs[i]->stream);
+        if (e == cudaSuccess) {
+            k_ba_step<<<(unsigned)table.size(), kBaThreads, 0, lead->stream>>>(d_table, hs[live[0]]->d_huber, n_iters, max_err_sq);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(lead->stream);
+        MAGE_CUDA_TRY(e);
+        lead->stats[2]++;
+    }
+    for (int i = 0; i < n; i++) {
+        int nout = 0;
+        int rc = ba_finish(hs[i], nullptr, 0, &nout, &means[i]);
+        if (rc) return rc;
+    }
+    return MAGE_OK;
+}
+
+static int ba_sync_host_state(mage_ba_t h)
+{
+    if (h->host_state_valid || !h->state_uploaded) return MAGE_OK;
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->cam_q.data(), h->dev.cam_q, sizeof(double) * 4 * h->K, cudaMemcpyDeviceToHost, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->cam_t.data(), h->dev.cam_t, sizeof(double) * 3 * h->K, cudaMemcpyDeviceToHost, h->stream));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->pt_X.data(), h->dev.pt_X, sizeof(double) * 3 * h->P, cudaMemcpyDeviceToHost, h->stream));
+    MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->host_state_valid = true;
+    return MAGE_OK;
+}
+
+// ref BundlerLib.cpp:457-465: t -> float, normalized quaternion -> rotation matrix -> float (column-major)
+extern "C" int mage_ba_get_pose(mage_ba_t h, int idx, float* pos, float* rot)
+{
+    MAGE_REQUIRE(h && pos && rot && idx >= 0 && idx < h->K, MAGE_ERR_INVALID, "mage_ba_get_pose: bad argument");
+    int rc = ba_sync_host_state(h);
+    if (rc) return rc;
+    double q[4] = {h->cam_q[4 * idx], h->cam_q[4 * idx + 1], h->cam_q[4 * idx + 2], h->cam_q[4 * idx + 3]};
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) q[i] /= n;
+    double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+    double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0], tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    double R[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+    for (int i = 0; i < 3; i++) pos[i] = (float)h->cam_t[3 * idx + i];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rot[c * 3 + r] = (float)R[r * 3 + c];
+    return MAGE_OK;
+}
+extern "C" int mage_ba_get_point(mage_ba_t h, int idx, float* xyz)
+{
+    MAGE_REQUIRE(h && xyz && idx >= 0 && idx < h->P, MAGE_ERR_INVALID, "mage_ba_get_point: bad argument");
+    int rc = ba_sync_host_state(h);
+    if (rc) return rc;
+    for (int i = 0; i < 3; i++) xyz[i] = (float)h->pt_X[3 * (size_t)idx + i];
+    return MAGE_OK;
+}
+extern "C" int mage_ba_get_poses_bulk(mage_ba_t h, float* pos, float* rot)
+{
+    MAGE_REQUIRE(h && pos && rot, MAGE_ERR_INVALID, "null argument");
+    for (int k = 0; k < h->K; k++) { int rc = mage_ba_get_pose(h, k, pos + 3 * k, rot + 9 * k); if (rc) return rc; }
+    return MAGE_OK;
+}
+extern "C" int mage_ba_get_points_bulk(mage_ba_t h, float* xyz)
+{
+    MAGE_REQUIRE(h && xyz, MAGE_ERR_INVALID, "null argument");
+    for (int i = 0; i < h->P; i++) { int rc = mage_ba_get_point(h, i, xyz + 3 * (size_t)i); if (rc) return rc; }
+    return MAGE_OK;
+}
+extern "C" int mage_ba_get_state_f64(mage_ba_t h, double* cams7, double* pts3)
+{
+    MAGE_REQUIRE(h && cams7 && pts3, MAGE_ERR_INVALID, "null argument");
+    int rc = ba_sync_host_state(h);
+    if (rc) return rc;
+    for (int k = 0; k < h->K; k++) {
+        for (int i = 0; i < 4; i++) cams7[7 * k + i] = h->cam_q[4 * k + i];
+        for (int i = 0; i < 3; i++) cams7[7 * k + 4 + i] = h->cam_t[3 * k + i];
+    }
+    std::copy(h->pt_X.begin(), h->pt_X.end(), pts3);
+    return MAGE_OK;
+}
+extern "C" int mage_ba_get_stats(mage_ba_t h, int64_t stats[4])
+{
+    MAGE_REQUIRE(h && stats, MAGE_ERR_INVALID, "null argument");
+    for (int i = 0; i < 4; i++) stats[i] = h->stats[i];
+    return MAGE_OK;
+}

@@ -1,0 +1,44 @@
+"""Shared BA parity driver: runs a mage::BundlerLib-shaped object side by side with a checker and compares after each call."""
+import numpy as np
+
+from mageslam_b200 import synth
+from tests.oracle_ba import BaOracle, have_ref, rel_frobenius
+
+# north_star tolerance: poses / points within 1e-4 relative Frobenius of the g2o solution at the same iteration count
+TOL = 1e-4
+
+
+def best_checker(points_fixed=False):
+    """The reference's own compiled code when oracle/_ref travelled with the repo, else the pinned restatement."""
+    return BaOracle("ref" if have_ref() else "port", points_fixed)
+
+
+def run_side_by_side(candidate, checker, huber, max_err_sq, calls, tol=TOL, tag=""):
+    """candidate: object with StepBundleAdjustment(huber, max) -> mean and .last_outliers/.poses()/.points()/.GetCurrentLambda().
+    Returns the list of per-call relative errors (for reporting)."""
+    report = []
+    for c in range(calls):
+        mean_c = candidate.StepBundleAdjustment(huber, max_err_sq)
+        out_c = np.asarray(candidate.last_outliers, np.int64)
+        mean_r, out_r = checker.StepBundleAdjustment(huber, max_err_sq)
+        assert np.array_equal(out_c, np.asarray(out_r, np.int64)), "%s call %d: outlier sets differ (%d vs %d)" % (tag, c, len(out_c), len(out_r))
+        pc, rc = candidate.poses(); pr, rr = checker.poses()
+        e_pos, e_rot, e_pts = rel_frobenius(pc, pr), rel_frobenius(rc, rr), rel_frobenius(candidate.points(), checker.points())
+        lam_c, lam_r = candidate.GetCurrentLambda(), checker.GetCurrentLambda()
+        assert e_pos <= tol and e_rot <= tol and e_pts <= tol, "%s call %d: relF pos %.3g rot %.3g pts %.3g" % (tag, c, e_pos, e_rot, e_pts)
+        assert abs(lam_c - lam_r) <= 1e-3 * abs(lam_r) + 1e-12, "%s call %d: lambda %g vs %g" % (tag, c, lam_c, lam_r)
+        if np.isnan(mean_r):
+            assert np.isnan(mean_c)
+        else:
+            assert abs(mean_c - mean_r) <= 1e-4 * abs(mean_r) + 1e-9, "%s call %d: mean error %g vs %g" % (tag, c, mean_c, mean_r)
+        report.append((e_pos, e_rot, e_pts))
+    return report
+
+
+def smoke_ba():
+    from mageslam_b200.bundler import BundlerLib, BundlerParameters
+    prob = synth.ba_problem(K=6, P=300, obs_per_point=3, seed=21)
+    gpu = BundlerLib(BundlerParameters(False)).load(prob)
+    chk = best_checker().load(prob)
+    rep = run_side_by_side(gpu, chk, [1.8], 1e9, 3, tag="smoke")
+    print("smoke: local BA 3 LM steps vs %s oracle -- max relF %.2e" % (chk.kind, max(max(r) for r in rep)))

@@ -1,0 +1,75 @@
+"""CPU tests that PIN the BA oracle: the FP64 restatement (oracle/ba_oracle.cpp) against
+ (1) golden vectors produced by the reference's own BundlerLib + g2o (tests/golden/ba_golden.npz, tools/gen_ba_golden.py), and
+ (2) the compiled reference itself (oracle/_ref/libbundler_ref.so) when it is present, step by step."""
+import os
+
+import numpy as np
+import pytest
+
+from mageslam_b200 import synth
+from tests.ba_checks import run_side_by_side
+from tests.oracle_ba import BaOracle, have_ref, rel_frobenius
+from tools.gen_ba_golden import CASES
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_golden.npz"))
+
+
+class _Adapter:
+    """gives a BaOracle the candidate interface of ba_checks.run_side_by_side"""
+    def __init__(self, o):
+        self.o = o
+    def StepBundleAdjustment(self, hub, mx):
+        mean, self.last_outliers = self.o.StepBundleAdjustment(hub, mx)
+        return mean
+    def __getattr__(self, n):
+        return getattr(self.o, n)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_port_matches_reference_golden(name):
+    kw, pf, hub, mx, calls = CASES[name]
+    prob = synth.ba_problem(**kw)
+    port = BaOracle("port", pf).load(prob)
+    for c in range(calls):
+        mean, outl = port.StepBundleAdjustment(hub, mx)
+        pos, rot = port.poses()
+        assert rel_frobenius(pos, GOLD["%s/%d/pos" % (name, c)]) < 1e-6
+        assert rel_frobenius(rot, GOLD["%s/%d/rot" % (name, c)]) < 1e-6
+        assert rel_frobenius(port.points(), GOLD["%s/%d/pts" % (name, c)]) < 1e-6
+        gmean, glam = GOLD["%s/%d/scalars" % (name, c)]
+        assert abs(mean - gmean) <= 1e-5 * abs(gmean) and abs(port.GetCurrentLambda() - glam) <= 1e-4 * abs(glam)
+        assert np.array_equal(outl.astype(np.int64), GOLD["%s/%d/outliers" % (name, c)])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("variant", ["clean", "outliers", "confidence", "pose_only", "user_lambda"])
+def test_port_matches_compiled_reference_at_tier_size(variant):
+    pf = variant == "pose_only"
+    if variant == "clean":
+        prob, hub, mx, calls = synth.ba_problem(), [1.8], 1e9, 10
+    elif variant == "outliers":
+        prob, hub, mx, calls = synth.ba_problem(outlier_frac=0.05), [1.8], 7.25, 10
+    elif variant == "confidence":
+        prob, hub, mx, calls = synth.ba_problem(info_mode="confidence", seed=3), [1.8, 1.8], 1e9, 5
+    elif variant == "pose_only":
+        prob, hub, mx, calls = synth.ba_problem(K=1, P=300, obs_per_point=1, n_fixed=0, pose_sigma=0.03, seed=5), [2.0, 2.0, 2.0], 25.0, 2
+    else:
+        prob, hub, mx, calls = synth.ba_problem(seed=7), [1.8], 1e9, 4
+    ref = BaOracle("ref", pf).load(prob); port = BaOracle("port", pf).load(prob)
+    if variant == "user_lambda":
+        ref.SetCurrentLambda(5.0); port.SetCurrentLambda(5.0)
+    run_side_by_side(_Adapter(port), ref, hub, mx, calls, tol=1e-6, tag=variant)
+
+
+def test_degenerate_inputs():
+    # no LM iteration requested: nothing active yet => mean is NaN (0/0), no outliers (ref BundlerLib.cpp:385-446)
+    prob = synth.ba_problem(K=4, P=40, obs_per_point=2, seed=1)
+    port = BaOracle("port").load(prob)
+    mean, outl = port.StepBundleAdjustment([], 1e9)
+    assert np.isnan(mean) and len(outl) == 0
+    # every vertex fixed => optimizer is "useless", Step() returns false, state untouched
+    prob["fixed"][:] = 1
+    port = BaOracle("port", True).load(prob)
+    before = port.poses()[0].copy()
+    mean, outl = port.StepBundleAdjustment([1.8, 1.8], 1e9)
+    assert np.isnan(mean) and len(outl) == 0 and np.array_equal(before, port.poses()[0])
