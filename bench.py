@@ -1,0 +1,422 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native MAGE-SLAM hot paths.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): ORB extract+match fps @ 640x480 (config[1]: synthetic video stream, 2000 keypoints/frame, frame t matched
+against frame t-1), with the local-BA LM iterations/sec (10 keyframes / 2000 points / 8000 observations) as the secondary metric
+in the same JSON line ("ba"). One "step" = one pass of the front-end over one batch of frames.
+
+  value     whole-job frames/s with the frames already resident in HBM (device-resident C-ABI entry point)
+  e2e       the same metric through the host-buffer C-ABI call (mage_frontend_process): pinned host frames in, host
+            keypoints/descriptors/matches out, H2D + D2H inside the timed region
+  roofline  dominant kernel of the step: algorithmic bytes per launch / its CUDA-event duration vs the measured HBM peak
+  cpu_baseline  the CPU oracle (port of the reference ORB path; the reference's own BundlerLib+g2o for BA) on host cores
+Multi-GPU: replicas only (one independent sequence per GPU, no data-path collective); NCCL is used for the barrier and
+the max-over-ranks reduction. --impl reference times the CPU implementation of the same path on all host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+NFEAT, NLEVELS, SCALE = 2000, 8, 1.2
+METRIC, UNIT = "orb_extract_match_fps_640x480", "frames/s"
+WORKLOAD = "640x480 synthetic video stream, 2000 keypoints/frame (8 levels x1.2, patch 31, oriented, FAST thr 10), frame t matched vs t-1 (maxHamming 30, minDiff 1)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def frame_ring(n_unique, ring, seed):
+    """ring frames (> L2 in total) from n_unique warped views of the synthetic scene; the rest are flips / brightness shifts."""
+    from mageslam_b200 import synth
+    base = synth.video_frames(n_unique, W, H, seed=seed)
+    out = np.empty((ring, H, W), np.uint8)
+    for i in range(ring):
+        f = base[i % n_unique]
+        k = (i // n_unique) % 4
+        if k == 1:
+            f = f[:, ::-1]
+        elif k == 2:
+            f = f[::-1, :]
+        elif k == 3:
+            f = f[::-1, ::-1]
+        out[i] = f
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.p = gpu, None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def level_areas():
+    areas = []
+    for l in range(NLEVELS):
+        s = np.float32(np.float64(np.float32(SCALE)) ** l)
+        areas.append(int(np.rint(np.float32(W) / s)) * int(np.rint(np.float32(H) / s)))
+    return areas
+
+
+def algorithmic_bytes_per_frame():
+    """compulsory bytes each kernel must move per 640x480 frame (8 levels x1.2, 2000 keypoints)."""
+    a = level_areas()
+    tot = sum(a)
+    return {
+        "k_resize": sum(a[l - 1] + a[l] for l in range(1, NLEVELS)),         # read level l-1, write level l
+        "k_blur": 2 * tot,                                                     # read + write every level
+        "k_fast": tot + 4 * 8000,                                              # read every level once + ~8k packed candidates
+        "k_select": 2 * 4 * 8000 + 4 * NFEAT,                                  # candidates in, kept list, selected out
+        "k_orient_describe": NFEAT * (709 + 512 + 28 + 32 + 4),                # orientation patch + 512 BRIEF samples + outputs
+        "k_match_dir": 2 * 2 * NFEAT * 32 + 2 * 4 * NFEAT,                     # both descriptor sets, both directions + best arrays
+        "k_match_emit": 2 * 4 * NFEAT + 12 * NFEAT,
+    }
+
+
+def cpu_orb_sample(frames, threads=1):
+    """Oracle (port of the reference ORB + Match) on `frames` consecutive frames; returns fps. Checker code, CPU only."""
+    from tests import oracle_orb as orc
+    p = orc.tier_params(NFEAT, NLEVELS, SCALE, 10)
+    t0 = time.perf_counter()
+    prev = None
+    for f in frames:
+        k, d = orc.detect_and_compute(p, f, 1)
+        if prev is not None:
+            orc.match(d, prev, 30, 1)
+        prev = d
+    dt = time.perf_counter() - t0
+    return len(frames) / dt
+
+
+_REF_RING = None      # rendered once in the parent, inherited by the forked workers
+
+
+def _cpu_worker(args):
+    start, n = args
+    fr = [_REF_RING[(start + i) % len(_REF_RING)] for i in range(n)]
+    t0 = time.perf_counter()
+    cpu_orb_sample(fr)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """CPU arm: the reference's ORB path cannot be compiled here (needs OpenCV 3.4 C++ headers), so this times the oracle port
+    of it, frame-parallel over all host cores (the reference itself is single-threaded per frame, MAGESlam.cpp:146)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 4
+    global _REF_RING
+    _REF_RING = frame_ring(min(args.unique, 32), 64, seed=10)
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, [((s * cores + w) * per_worker, per_worker) for w in range(cores)])
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+    frames_per_step = cores * per_worker
+    ms = 1e3 * sum(times) / len(times)
+    value = frames_per_step / (ms / 1e3)
+    sample = "%d frames per step (%d worker processes x %d consecutive frames each, extract + match vs previous)" % (frames_per_step, cores, per_worker)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    # secondary: the reference's own BundlerLib + g2o (compiled unmodified into oracle/_ref) on the local-BA window
+    try:
+        line["ba"] = cpu_ba_baseline(parallel=True)
+    except Exception as e:      # pragma: no cover
+        line["ba"] = {"unavailable": str(e)[:200]}
+    print(json.dumps(line))
+
+
+_BA_PROB = None       # generated once in the parent, inherited by forked workers
+
+
+def _ba_worker(n_windows):
+    """Builds n_windows oracle instances (untimed), then times one 10-iteration StepBundleAdjustment call on each."""
+    from tests.oracle_ba import BaOracle, have_ref
+    global _BA_PROB
+    if _BA_PROB is None:
+        from mageslam_b200 import synth
+        _BA_PROB = synth.ba_problem(seed=1)
+    insts = [BaOracle("ref" if have_ref() else "port").load(_BA_PROB) for _ in range(n_windows)]
+    for o in insts:
+        o.StepBundleAdjustment([1.8], 1e9)       # structure build + first iteration, untimed (same protocol as the GPU arm)
+    t0 = time.perf_counter()
+    for o in insts:
+        o.StepBundleAdjustment([1.8] * 10, 1e9)
+    return time.perf_counter() - t0
+
+
+def cpu_ba_baseline(parallel=False, reps=8):
+    from tests.oracle_ba import have_ref
+    from mageslam_b200 import synth
+    global _BA_PROB
+    _BA_PROB = synth.ba_problem(seed=1)
+    kind = "reference" if have_ref() else "port"
+    if not parallel:
+        t = _ba_worker(reps) / reps
+        return {"metric": "local_ba_lm_iters_per_sec", "value": 10.0 / t, "unit": "LM iterations/s", "cores": 1, "kind": kind,
+                "sample": "%d x StepBundleAdjustment(10 Huber widths) on the 10 KF / 2000 pt / 8000 obs window, 1 thread" % reps}
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per = 6
+    with mp.get_context("fork").Pool(cores) as pool:
+        ts = pool.map(_ba_worker, [per] * cores)
+    value = sum(per * 10 / t for t in ts)          # all workers run concurrently: aggregate = sum of per-worker rates
+    return {"metric": "local_ba_lm_iters_per_sec", "value": value, "unit": "LM iterations/s", "cores": cores, "kind": kind,
+            "sample": "%d processes x %d independent windows x 10 LM iterations" % (cores, per)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mageslam_b200 import _lib
+    from mageslam_b200.frontend import FrontEnd
+    from mageslam_b200.orb import FeatureExtractorSettings
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()      # raises if the CUDA extension is missing: there is no fallback path
+    B, ring_n = args.batch, args.ring
+    ring = frame_ring(args.unique, ring_n, seed=10 + rank)                    # one independent sequence per rank
+    h_ring = torch.from_numpy(ring).pin_memory()
+    d_ring = h_ring.cuda()
+    settings = FeatureExtractorSettings.tier(NFEAT, NLEVELS, SCALE, 10)
+    fe_dev = FrontEnd(settings, W, H, B, chunk=B)
+    fe_host = FrontEnd(settings, W, H, B, chunk=args.chunk)
+    outs = fe_host.alloc_outputs(pinned=True)
+    stream = torch.cuda.current_stream()
+    nb = ring_n // B
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step(i):
+        fe_dev.ProcessDevice(d_ring[(i % nb) * B:(i % nb + 1) * B], stream)
+
+    # ---- device-resident throughput (value)
+    for i in range(args.warmup):
+        dev_step(i)
+    barrier()
+    clk = ClockSampler(local); clk.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = clk.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B / (ms_max / 1e3)
+    kps, desc, cnt, mt, mc = fe_dev.ReadDeviceResults()
+    kp_mean, match_mean = float(cnt.mean()), float(mc[1:].mean())
+
+    # ---- end to end through the host-buffer C ABI (pinned host frames in, host results out)
+    for i in range(args.warmup):
+        fe_host.Process(h_ring[(i % nb) * B:(i % nb + 1) * B], outs)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        j = (args.warmup + i) % nb
+        fe_host.Process(h_ring[j * B:(j + 1) * B], outs)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (float(t.item()) / 1e3)
+    cap = fe_host.capacity
+    h2d = B * W * H
+    d2h = B * (cap * (28 + 32 + 12) + 8)
+
+    # ---- per-kernel CUDA-event timing pass (same inputs, instrumented launches) -> roofline of the dominant kernel
+    L.mage_profile_get.argtypes = [__import__("ctypes").c_int, __import__("ctypes").POINTER(__import__("ctypes").c_double),
+                                   __import__("ctypes").POINTER(__import__("ctypes").c_longlong)]
+    L.mage_profile_name.restype = __import__("ctypes").c_char_p
+    L.mage_profile_reset(); L.mage_profile_enable(1)
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    L.mage_profile_collect(); L.mage_profile_enable(0)
+    import ctypes as C
+    kern = {}
+    for s in range(L.mage_profile_slots()):
+        tot, n = C.c_double(0), C.c_longlong(0)
+        L.mage_profile_get(s, C.byref(tot), C.byref(n))
+        if n.value:
+            kern[L.mage_profile_name(s).decode()] = (tot.value / n.value, n.value)
+    alg = algorithmic_bytes_per_frame()
+    step_kernel_ms = sum(v[0] for k, v in kern.items() if k in alg)
+    dom = max((k for k in kern if k in alg), key=lambda k: kern[k][0])
+    peak, peak_src = peaks()
+    dom_ms = kern[dom][0]
+    achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "launch_ms": dom_ms, "share_of_step": dom_ms / step_kernel_ms,
+                "algorithmic_bytes_per_launch": alg[dom] * B,
+                "kernels": {k: {"ms": round(v[0], 5), "share": round(v[0] / step_kernel_ms, 4),
+                                "GBps": round(alg[k] * B / (v[0] * 1e-3) / 1e9, 2)} for k, v in kern.items() if k in alg}}
+    if dom == "k_match_dir":
+        wordops = 2 * 2 * NFEAT * NFEAT * 8 * B          # xor+popc word operations per launch (both directions)
+        roofline["note"] = "integer-ALU bound (xor+popc), operands live in shared memory/L2; %.2f Tera word-ops/s" % (wordops / (dom_ms * 1e-3) / 1e12)
+    launches_per_step = (NLEVELS - 1) + 1 + 1 + 1 + 1 + 2
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": B, "sequences": world, "parallelism": "replicas (one sequence per GPU)",
+                       "l2": "inputs larger than L2: %d-frame ring = %.0f MB per GPU" % (ring_n, ring_n * W * H / 1e6),
+                       "keypoints_per_frame": kp_mean, "matches_per_frame": match_mean, "e2e_chunk": args.chunk,
+                       "e2e_timer": "host clock around synchronous C-ABI calls, device idle at both ends"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline}
+
+    if rank == 0 and world == 1:
+        sample_n = args.cpu_frames
+        fps = cpu_orb_sample(list(ring[:sample_n]))
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
+                                "sample": "%d consecutive frames of the same ring, extract + match vs previous, 1 thread (host has %d cores)" % (sample_n, os.cpu_count() or 1)}
+    # ---- secondary metric: local BA
+    try:
+        line["ba"] = bench_ba(args, world, rank, dist if world > 1 else None)
+    except Exception as e:      # pragma: no cover
+        line["ba"] = {"error": str(e)[:300]}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_ba(args, world, rank, dist):
+    """local BA (BASELINE config 3): 10 KF / 2000 pts / 8000 obs, 10 LM iterations per StepBundleAdjustment call."""
+    import torch
+    from mageslam_b200 import synth
+    from mageslam_b200.bundler import BundlerLib, StepMany
+    hub = [1.8] * 10
+    nprob = args.ba_problems
+    probs = [synth.ba_problem(seed=1 + 97 * rank + i) for i in range(min(nprob, 8))]
+    # single problem latency path
+    single = []
+    for r in range(3):
+        b = BundlerLib().load(probs[0])
+        b.StepBundleAdjustment([1.8], 1e9)             # structure build + first iteration (not timed)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        b.StepBundleAdjustment(hub, 1e9)
+        torch.cuda.synchronize(); single.append(time.perf_counter() - t0)
+        st = b.stats()
+    # batched: one CTA per problem, one launch for all
+    bs = [BundlerLib().load(probs[i % len(probs)]) for i in range(nprob)]
+    StepMany(bs, [1.8], 1e9)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    StepMany(bs, hub, 1e9)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    iters = sum(b.stats()["lm_iterations"] for b in bs) - nprob      # minus the untimed first iteration of each
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out = {"metric": "local_ba_lm_iters_per_sec", "unit": "LM iterations/s", "value": world * iters / float(t.item()),
+           "config": {"workload": "local BA 10 KF / 2000 pts / 8000 obs, Huber 1.8, 10 LM iterations per call", "problems_per_gpu": nprob,
+                      "mode": "batched: one CTA per problem, one persistent launch per call"},
+           "single_problem": {"value": 10.0 / statistics.median(single), "unit": "LM iterations/s", "ms_per_call": 1e3 * statistics.median(single)},
+           "dtype": "f64"}
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_ba_baseline(parallel=False)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per step")
+    ap.add_argument("--chunk", type=int, default=8, help="pipelining granularity of the host (e2e) path")
+    ap.add_argument("--ring", type=int, default=512, help="frames in the input ring (157 MB at 512 > 126 MB L2)")
+    ap.add_argument("--unique", type=int, default=64, help="distinct warped views rendered for the ring")
+    ap.add_argument("--cpu-frames", type=int, default=40, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--ba-problems", type=int, default=148)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

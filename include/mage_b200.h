@@ -35,6 +35,17 @@ const char* mage_last_error(void);
 /* library / device probe: returns number of CUDA devices visible (>= 0) or MAGE_ERR_CUDA */
 int mage_device_count(void);
 const char* mage_version(void);
+/* synchronous device -> host copy for bindings that hold raw device pointers */
+int mage_memcpy_d2h(void* dst, const void* src, size_t bytes);
+
+/* Optional per-kernel timing with CUDA events on the launching stream (measurement aid for bench.py; off by default).
+ * Slots are kernel names (mage_profile_name); a "group" is one timed launch (or the chained pyramid launches). */
+int         mage_profile_enable(int on);
+int         mage_profile_collect(void);      /* device sync + fold the recorded event pairs into the totals */
+int         mage_profile_reset(void);
+int         mage_profile_slots(void);
+const char* mage_profile_name(int slot);
+int         mage_profile_get(int slot, double* total_ms, long long* groups);
 
 /* ------------------------------------------------------------------------------------------------ ORB extract */
 
@@ -123,8 +134,36 @@ int  mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_
                           const int* a_index, const int* b_index, int n_pairs, int max_hamming, int min_hamming_diff,
                           mage_dmatch* d_matches, int capacity, int* d_match_counts, void* cuda_stream);
 
+/* Same, split in two: register the pair table once, then launch any sub-range of it (no host work per launch). */
+int  mage_matcher_set_jobs_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_counts, size_t slot_stride,
+                                  const int* a_index, const int* b_index, int n_pairs);
+int  mage_match_run_jobs(mage_matcher_t m, int first_pair, int n_pairs, int max_hamming, int min_hamming_diff,
+                         mage_dmatch* d_matches, int capacity, int* d_match_counts, void* cuda_stream);
+
 /* GetDescriptorDistance for n pairs of device-resident descriptors (a[i] vs b[i]) -> d_out[i]. */
 int  mage_descriptor_distance_device(const uint8_t* d_a, const uint8_t* d_b, int n, int* d_out, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------- Front-end for a video stream */
+
+/* ORB extract of a batch of frames + Match of every frame (query) against its predecessor (train): the reference's
+ * per-frame call sequence (ref Tasks/ImageAnalyzer.cpp:119 -> OrbFeatureDetector::Process; Tracking/MapInitialization.cpp:585
+ * -> Match) for `batch` frames per call. The last frame of a call is kept on the device as predecessor of the next call.
+ * chunk (<= batch, 0 = batch) is the pipelining granularity of the host variant: upload of chunk k+1, compute of chunk k
+ * and download of chunk k-1 overlap on three streams. */
+typedef struct mage_frontend_s* mage_frontend_t;
+int  mage_frontend_create(const mage_orb_params* params, int width, int height, int batch, int chunk, int max_hamming,
+                          int min_hamming_diff, mage_frontend_t* out);
+void mage_frontend_destroy(mage_frontend_t f);
+int  mage_frontend_reset(mage_frontend_t f);                 /* start a new sequence (no predecessor) */
+int  mage_frontend_capacity(mage_frontend_t f);              /* features per frame slot in the output arrays */
+/* Host buffers (pinned for overlap), synchronous: kps/desc/matches are [n][capacity] arrays, counts/match_counts [n]. */
+int  mage_frontend_process(mage_frontend_t f, const uint8_t* images, int n, int stride, size_t frame_stride,
+                           mage_keypoint* kps, uint8_t* desc, int* counts, mage_dmatch* matches, int* match_counts);
+/* Device-resident frames, results stay in the handle's device buffers (mage_frontend_device_buffers). Asynchronous. */
+int  mage_frontend_process_device(mage_frontend_t f, const uint8_t* d_images, int n, int stride, size_t frame_stride,
+                                  void* cuda_stream);
+int  mage_frontend_device_buffers(mage_frontend_t f, mage_keypoint** d_kps, uint8_t** d_desc, int** d_counts,
+                                  mage_dmatch** d_matches, int** d_match_counts, int* capacity);
 
 /* ------------------------------------------------------------------------------------------ Bundle adjustment */
 

@@ -1038,7 +1038,7 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
     int rc = ba_prepare(h, huber, n_iters);
     if (rc) return rc;
     if (!h->useless) {
-        k_ba_step<<<1, kBaThreads, 0, h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq);
+        { ProfScope ps(PROF_BA_STEP, h->stream); k_ba_step<<<1, kBaThreads, 0, h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq); }
         MAGE_CUDA_TRY(cudaGetLastError());
         h->stats[2]++;
     }
@@ -1067,7 +1067,7 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
         cudaError_t e = cudaMemcpyAsync(d_table, table.data(), sizeof(BaDev) * table.size(), cudaMemcpyHostToDevice, lead->stream);
         for (int i : live) if (e == cudaSuccess && hs[i] != lead) e = cudaStreamSynchronize(hs[i]->stream);
         if (e == cudaSuccess) {
-            k_ba_step<<<(unsigned)table.size(), kBaThreads, 0, lead->stream>>>(d_table, hs[live[0]]->d_huber, n_iters, max_err_sq);
+            { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step<<<(unsigned)table.size(), kBaThreads, 0, lead->stream>>>(d_table, hs[live[0]]->d_huber, n_iters, max_err_sq); }
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(lead->stream);

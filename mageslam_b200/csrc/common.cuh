@@ -42,6 +42,17 @@ struct DeviceArena {
     void release() { if (base) cudaFree(base); base = nullptr; }
 };
 
+// Optional per-kernel timing (CUDA events on the launching stream), used by bench.py for the live roofline figure.
+enum ProfSlot { PROF_RESIZE = 0, PROF_BLUR, PROF_FAST, PROF_SELECT, PROF_ORIENT_DESCRIBE, PROF_MATCH_DIR, PROF_MATCH_EMIT, PROF_BA_STEP, PROF_SLOTS };
+bool prof_enabled();
+void prof_begin(int slot, cudaStream_t s);
+void prof_end(int slot, cudaStream_t s);
+struct ProfScope {
+    int slot; cudaStream_t s; bool on;
+    ProfScope(int slot_, cudaStream_t s_) : slot(slot_), s(s_), on(prof_enabled()) { if (on) prof_begin(slot, s); }
+    ~ProfScope() { if (on) prof_end(slot, s); }
+};
+
 __device__ __forceinline__ int warp_reduce_sum(int v)
 {
 #pragma unroll

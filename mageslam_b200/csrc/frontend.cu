@@ -1,0 +1,183 @@
+// Per-frame front-end for a video stream: ORB extract of a batch of frames + brute-force match of every frame against its
+// predecessor, the call sequence of the reference's tracking front-end (ref Tasks/ImageAnalyzer.cpp:119 -> Process,
+// Tracking/MapInitialization.cpp:585 -> Match) in batched form. Built only on the C ABI of orb.cu / match.cu.
+//
+// Host variant: frames come from (pinned) host memory in chunks; chunk k+1 is uploaded on a copy stream while chunk k is
+// processed on the compute stream and chunk k-1's results are downloaded on a third stream (events order the hand-offs).
+// Device variant: frames already in HBM, results stay in HBM, fully asynchronous.
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+using namespace mage;
+
+struct mage_frontend_s {
+    mage_orb_t orb = nullptr;
+    mage_matcher_t matcher = nullptr;
+    int width = 0, height = 0, pitch = 0, batch = 0, chunk = 0, cap = 0, max_hamming = 30, min_diff = 1;
+    // device slots: slot 0 = last frame of the previous call, slots 1..batch = frames of this call
+    uint8_t* d_images = nullptr;
+    mage_keypoint* d_kps = nullptr;
+    uint8_t* d_desc = nullptr;
+    int* d_counts = nullptr;
+    mage_dmatch* d_matches = nullptr;
+    int* d_match_counts = nullptr;
+    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_done;
+    cudaEvent_t ev_prev = nullptr;
+    std::vector<int> a_idx, b_idx;
+    bool has_prev = false;
+};
+
+extern "C" void mage_frontend_destroy(mage_frontend_s* f);
+
+extern "C" int mage_frontend_create(const mage_orb_params* p, int width, int height, int batch, int chunk, int max_hamming, int min_diff,
+                                    mage_frontend_s** out)
+{
+    MAGE_REQUIRE(p && out && batch >= 1, MAGE_ERR_INVALID, "mage_frontend_create: bad argument");
+    if (chunk <= 0 || chunk > batch) chunk = batch;
+    mage_frontend_s* f = new mage_frontend_s();
+    f->width = width; f->height = height; f->batch = batch; f->chunk = chunk; f->max_hamming = max_hamming; f->min_diff = min_diff;
+    int rc = mage_orb_create(p, width, height, chunk, &f->orb);
+    if (rc != MAGE_OK) { delete f; return rc; }
+    int nf[16]; int sum = 0;
+    mage_orb_level_info(f->orb, nullptr, nullptr, nullptr, nf);
+    for (unsigned l = 0; l < p->nlevels; l++) sum += nf[l];
+    f->cap = std::max((int)p->nfeatures, sum);
+    rc = mage_matcher_create(std::min(f->cap, 65535), batch, &f->matcher);
+    if (rc != MAGE_OK) { mage_frontend_destroy(f); return rc; }
+    const size_t B1 = (size_t)batch + 1;
+    f->pitch = (int)align_up((size_t)width, 16);          // staging rows: 16-byte aligned so every frame base is too
+    cudaError_t e = cudaMalloc(&f->d_images, (size_t)f->pitch * height * batch);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_kps, sizeof(mage_keypoint) * f->cap * B1);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_desc, (size_t)32 * f->cap * B1);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_counts, sizeof(int) * B1);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_matches, sizeof(mage_dmatch) * f->cap * (size_t)batch);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_match_counts, sizeof(int) * batch);
+    if (e == cudaSuccess) e = cudaMemset(f->d_counts, 0, sizeof(int) * B1);
+    if (e == cudaSuccess) e = cudaMemset(f->d_match_counts, 0, sizeof(int) * batch);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking);
+    const int nchunks = div_up(batch, chunk);
+    f->ev_in.resize(nchunks); f->ev_done.resize(nchunks);
+    for (int i = 0; i < nchunks && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&f->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_prev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { set_error("mage_frontend_create: %s", cudaGetErrorString(e)); mage_frontend_destroy(f); return MAGE_ERR_CUDA; }
+    f->a_idx.resize(batch); f->b_idx.resize(batch);
+    for (int i = 0; i < batch; i++) { f->a_idx[i] = i + 1; f->b_idx[i] = i; }       // frame i (query) vs frame i-1 (train)
+    rc = mage_matcher_set_jobs_device(f->matcher, f->d_desc, f->d_counts, (size_t)32 * f->cap, f->a_idx.data(), f->b_idx.data(), batch);
+    if (rc != MAGE_OK) { mage_frontend_destroy(f); return rc; }
+    *out = f;
+    return MAGE_OK;
+}
+
+extern "C" void mage_frontend_destroy(mage_frontend_s* f)
+{
+    if (!f) return;
+    cudaDeviceSynchronize();
+    if (f->orb) mage_orb_destroy(f->orb);
+    if (f->matcher) mage_matcher_destroy(f->matcher);
+    cudaFree(f->d_images); cudaFree(f->d_kps); cudaFree(f->d_desc); cudaFree(f->d_counts); cudaFree(f->d_matches); cudaFree(f->d_match_counts);
+    for (auto e : f->ev_in) if (e) cudaEventDestroy(e);
+    for (auto e : f->ev_done) if (e) cudaEventDestroy(e);
+    if (f->ev_prev) cudaEventDestroy(f->ev_prev);
+    if (f->s_copy) cudaStreamDestroy(f->s_copy);
+    if (f->s_compute) cudaStreamDestroy(f->s_compute);
+    if (f->s_out) cudaStreamDestroy(f->s_out);
+    delete f;
+}
+
+// new sequence: forget the previous frame (its slot gets an empty descriptor set => no matches for the next first frame)
+extern "C" int mage_frontend_reset(mage_frontend_s* f)
+{
+    MAGE_REQUIRE(f, MAGE_ERR_INVALID, "null handle");
+    MAGE_CUDA_TRY(cudaMemsetAsync(f->d_counts, 0, sizeof(int), f->s_compute));
+    f->has_prev = false;
+    return MAGE_OK;
+}
+
+// extract + match of frames [c0, c1) whose pixels are at d_img (frame stride fs, row stride st), on stream s
+static int frontend_compute(mage_frontend_s* f, const uint8_t* d_img, int st, size_t fs, int c0, int c1, cudaStream_t s)
+{
+    const size_t cap = (size_t)f->cap;
+    int rc = mage_orb_extract_device(f->orb, d_img, c1 - c0, f->width, f->height, st, fs, f->d_kps + cap * (c0 + 1), f->d_desc + 32 * cap * (c0 + 1),
+                                     f->cap, f->d_counts + c0 + 1, s);
+    if (rc != MAGE_OK) return rc;
+    return mage_match_run_jobs(f->matcher, c0, c1 - c0, f->max_hamming, f->min_diff, f->d_matches + cap * c0, f->cap, f->d_match_counts + c0, s);
+}
+
+// keep the last frame of this call as "previous" for the next one
+static int frontend_roll(mage_frontend_s* f, int n, cudaStream_t s)
+{
+    const size_t cap = (size_t)f->cap;
+    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_desc, f->d_desc + 32 * cap * n, 32 * cap, cudaMemcpyDeviceToDevice, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_kps, f->d_kps + cap * n, sizeof(mage_keypoint) * cap, cudaMemcpyDeviceToDevice, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_counts, f->d_counts + n, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    f->has_prev = true;
+    return MAGE_OK;
+}
+
+extern "C" int mage_frontend_process_device(mage_frontend_s* f, const uint8_t* d_images, int n, int stride, size_t frame_stride, void* stream)
+{
+    MAGE_REQUIRE(f && d_images && n >= 1 && n <= f->batch, MAGE_ERR_INVALID, "mage_frontend_process_device: bad argument");
+    cudaStream_t s = stream ? (cudaStream_t)stream : f->s_compute;
+    for (int c0 = 0; c0 < n; c0 += f->chunk) {
+        int c1 = std::min(n, c0 + f->chunk);
+        int rc = frontend_compute(f, d_images + (size_t)c0 * frame_stride, stride, frame_stride, c0, c1, s);
+        if (rc != MAGE_OK) return rc;
+    }
+    return frontend_roll(f, n, s);
+}
+
+extern "C" int mage_frontend_device_buffers(mage_frontend_s* f, mage_keypoint** d_kps, uint8_t** d_desc, int** d_counts, mage_dmatch** d_matches,
+                                            int** d_match_counts, int* capacity)
+{
+    MAGE_REQUIRE(f, MAGE_ERR_INVALID, "null handle");
+    const size_t cap = (size_t)f->cap;
+    if (d_kps) *d_kps = f->d_kps + cap; if (d_desc) *d_desc = f->d_desc + 32 * cap; if (d_counts) *d_counts = f->d_counts + 1;
+    if (d_matches) *d_matches = f->d_matches; if (d_match_counts) *d_match_counts = f->d_match_counts; if (capacity) *capacity = f->cap;
+    return MAGE_OK;
+}
+
+extern "C" int mage_frontend_process(mage_frontend_s* f, const uint8_t* images, int n, int stride, size_t frame_stride, mage_keypoint* kps,
+                                     uint8_t* desc, int* counts, mage_dmatch* matches, int* match_counts)
+{
+    MAGE_REQUIRE(f && images && kps && desc && counts && matches && match_counts && n >= 1 && n <= f->batch, MAGE_ERR_INVALID,
+                 "mage_frontend_process: bad argument");
+    MAGE_REQUIRE(stride >= f->width, MAGE_ERR_INVALID, "stride smaller than width");
+    const size_t cap = (size_t)f->cap, W = (size_t)f->width, H = (size_t)f->height, PT = (size_t)f->pitch;
+    const int nch = div_up(n, f->chunk);
+    // uploads of the next call must not overwrite frames still being read: the previous call ended with a full sync
+    for (int k = 0; k < nch; k++) {
+        const int c0 = k * f->chunk, c1 = std::min(n, c0 + f->chunk);
+        if ((size_t)stride == PT && frame_stride == PT * H)
+            MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_images + PT * H * c0, images + frame_stride * c0, PT * H * (c1 - c0), cudaMemcpyHostToDevice, f->s_copy));
+        else
+            for (int i = c0; i < c1; i++)
+                MAGE_CUDA_TRY(cudaMemcpy2DAsync(f->d_images + PT * H * i, PT, images + frame_stride * i, stride, W, H, cudaMemcpyHostToDevice, f->s_copy));
+        MAGE_CUDA_TRY(cudaEventRecord(f->ev_in[k], f->s_copy));
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, f->ev_in[k], 0));
+        int rc = frontend_compute(f, f->d_images + PT * H * c0, f->pitch, PT * H, c0, c1, f->s_compute);
+        if (rc != MAGE_OK) return rc;
+        MAGE_CUDA_TRY(cudaEventRecord(f->ev_done[k], f->s_compute));
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_out, f->ev_done[k], 0));
+        const int m = c1 - c0;
+        MAGE_CUDA_TRY(cudaMemcpyAsync(kps + cap * c0, f->d_kps + cap * (c0 + 1), sizeof(mage_keypoint) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(desc + 32 * cap * c0, f->d_desc + 32 * cap * (c0 + 1), 32 * cap * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(matches + cap * c0, f->d_matches + cap * c0, sizeof(mage_dmatch) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(counts + c0, f->d_counts + c0 + 1, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(match_counts + c0, f->d_match_counts + c0, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
+    }
+    int rc = frontend_roll(f, n, f->s_compute);
+    if (rc != MAGE_OK) return rc;
+    MAGE_CUDA_TRY(cudaStreamSynchronize(f->s_out));
+    MAGE_CUDA_TRY(cudaStreamSynchronize(f->s_compute));
+    return MAGE_OK;
+}
+
+extern "C" int mage_frontend_capacity(mage_frontend_s* f) { return f ? f->cap : 0; }

@@ -226,8 +226,8 @@ static int match_launch(mage_matcher_t m, int n_pairs, int max_q, int max_hammin
 {
     MAGE_CUDA_TRY(cudaMemcpyAsync(m->d_jobs, m->h_jobs, sizeof(MatchJob) * n_pairs, cudaMemcpyHostToDevice, s));
     dim3 grid(div_up(max_q, kQPerBlock), 2 * n_pairs);
-    k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming, min_diff);
-    k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, d_out, out_cap, d_counts);
+    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming, min_diff); }
+    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, d_out, out_cap, d_counts); }
     MAGE_CUDA_TRY(cudaGetLastError());
     return MAGE_OK;
 }
@@ -264,27 +264,19 @@ extern "C" int mage_match_bf(mage_matcher_t m, const uint8_t* descA, int nA, con
     return MAGE_OK;
 }
 
-extern "C" int mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_counts, size_t slot_stride,
-                                    const int* a_index, const int* b_index, int n_pairs, int max_hamming, int min_diff,
-                                    mage_dmatch* d_matches, int capacity, int* d_match_counts, void* stream)
+// Registers a table of device-resident pairs once (uploaded synchronously); mage_match_run_jobs then launches any
+// sub-range of it without touching the host table again (a video stream re-submits the same slot pairs every batch).
+extern "C" int mage_matcher_set_jobs_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_counts, size_t slot_stride,
+                                            const int* a_index, const int* b_index, int n_pairs)
 {
-    MAGE_REQUIRE(m && d_desc && d_counts && a_index && b_index && d_matches && d_match_counts, MAGE_ERR_INVALID, "mage_match_bf_device: null argument");
+    MAGE_REQUIRE(m && d_desc && d_counts && a_index && b_index, MAGE_ERR_INVALID, "mage_matcher_set_jobs_device: null argument");
     MAGE_REQUIRE(n_pairs >= 1 && n_pairs <= m->max_pairs, MAGE_ERR_INVALID, "n_pairs %d exceeds matcher capacity %d", n_pairs, m->max_pairs);
-    MAGE_REQUIRE(slot_stride % 4 == 0 && capacity >= 1, MAGE_ERR_INVALID, "slot_stride must be a multiple of 4");
-    cudaStream_t s = (cudaStream_t)stream;
+    MAGE_REQUIRE(slot_stride % 4 == 0, MAGE_ERR_INVALID, "slot_stride must be a multiple of 4");
     const bool same = m->memo_desc == d_desc && m->memo_counts == d_counts && m->memo_stride == slot_stride &&
                       (int)m->memo_a.size() == n_pairs && std::equal(a_index, a_index + n_pairs, m->memo_a.begin()) &&
                       std::equal(b_index, b_index + n_pairs, m->memo_b.begin());
-    if (same) {     // job table already resident on the device
-        const int cap = (int)std::min<size_t>(m->max_desc, slot_stride / 32);
-        dim3 grid(div_up(cap, kQPerBlock), 2 * n_pairs);
-        k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming, min_diff);
-        k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, d_matches, capacity, d_match_counts);
-        MAGE_CUDA_TRY(cudaGetLastError());
-        return MAGE_OK;
-    }
-    // the pinned job table is rewritten: wait until any previous upload has been consumed
-    MAGE_CUDA_TRY(cudaStreamSynchronize(s));
+    if (same) return MAGE_OK;
+    MAGE_CUDA_TRY(cudaDeviceSynchronize());          // the table may still be in use by earlier launches
     m->memo_desc = d_desc; m->memo_counts = d_counts; m->memo_stride = slot_stride;
     m->memo_a.assign(a_index, a_index + n_pairs); m->memo_b.assign(b_index, b_index + n_pairs);
     for (int p = 0; p < n_pairs; p++) {
@@ -294,7 +286,33 @@ extern "C" int mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, con
         j.count_ptr[0] = d_counts + a_index[p]; j.count_ptr[1] = d_counts + b_index[p];
         j.count[0] = j.count[1] = 0; j.cap = (int)std::min<size_t>(m->max_desc, slot_stride / 32);
     }
-    return match_launch(m, n_pairs, m->h_jobs[0].cap, max_hamming, min_diff, d_matches, capacity, d_match_counts, s);
+    MAGE_CUDA_TRY(cudaMemcpy(m->d_jobs, m->h_jobs, sizeof(MatchJob) * n_pairs, cudaMemcpyHostToDevice));
+    return MAGE_OK;
+}
+
+extern "C" int mage_match_run_jobs(mage_matcher_t m, int first_pair, int n_pairs, int max_hamming, int min_diff, mage_dmatch* d_matches,
+                                   int capacity, int* d_match_counts, void* stream)
+{
+    MAGE_REQUIRE(m && d_matches && d_match_counts && first_pair >= 0 && n_pairs >= 1 && first_pair + n_pairs <= (int)m->memo_a.size(),
+                 MAGE_ERR_INVALID, "mage_match_run_jobs: pair range outside the registered table");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cap = m->h_jobs[first_pair].cap;
+    dim3 grid(div_up(cap, kQPerBlock), 2 * n_pairs);
+    unsigned* best = m->d_best + (size_t)first_pair * 2 * m->max_desc;
+    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, max_hamming, min_diff); }
+    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, d_matches, capacity, d_match_counts); }
+    MAGE_CUDA_TRY(cudaGetLastError());
+    return MAGE_OK;
+}
+
+extern "C" int mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_counts, size_t slot_stride,
+                                    const int* a_index, const int* b_index, int n_pairs, int max_hamming, int min_diff,
+                                    mage_dmatch* d_matches, int capacity, int* d_match_counts, void* stream)
+{
+    MAGE_REQUIRE(capacity >= 1, MAGE_ERR_INVALID, "capacity must be >= 1");
+    int rc = mage_matcher_set_jobs_device(m, d_desc, d_counts, slot_stride, a_index, b_index, n_pairs);
+    if (rc != MAGE_OK) return rc;
+    return mage_match_run_jobs(m, 0, n_pairs, max_hamming, min_diff, d_matches, capacity, d_match_counts, stream);
 }
 
 extern "C" int mage_descriptor_distance_device(const uint8_t* d_a, const uint8_t* d_b, int n, int* d_out, void* stream)

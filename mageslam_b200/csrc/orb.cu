@@ -794,14 +794,17 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
 {
     const OrbGeom& g = h->g;
     MAGE_CUDA_TRY(cudaMemsetAsync(bufs.cand_count, 0, sizeof(int) * kMaxLevels * h->max_batch * 2 + sizeof(int) * h->max_batch, s));
-    for (int l = 1; l < g.nlevels; l++) {
-        dim3 grid(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 8), n), block(32, 8);
-        k_resize<<<grid, block, 0, s>>>(g, bufs, l);
+    {
+        ProfScope ps(PROF_RESIZE, s);       // the L-1 chained launches are timed as one group
+        for (int l = 1; l < g.nlevels; l++) {
+            dim3 grid(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 8), n), block(32, 8);
+            k_resize<<<grid, block, 0, s>>>(g, bufs, l);
+        }
     }
-    if (g.ksize > 1) k_blur<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs);
-    k_fast<<<dim3(h->fast_tiles, n), 256, 0, s>>>(g, bufs);
-    k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs);
-    k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity);
+    if (g.ksize > 1) { ProfScope ps(PROF_BLUR, s); k_blur<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs); }
+    { ProfScope ps(PROF_FAST, s); k_fast<<<dim3(h->fast_tiles, n), 256, 0, s>>>(g, bufs); }
+    { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }
+    { ProfScope ps(PROF_ORIENT_DESCRIBE, s); k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity); }
     MAGE_CUDA_TRY(cudaGetLastError());
     h->last_n = n;
     return MAGE_OK;

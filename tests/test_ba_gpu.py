@@ -109,8 +109,10 @@ def test_degenerate_inputs():
     before = useless.poses()[0].copy()
     mean = useless.StepBundleAdjustment([1.8, 1.8], 1e9)
     assert np.isnan(mean) and len(useless.last_outliers) == 0 and np.array_equal(before, useless.poses()[0])
-    # all cameras fixed, points free: reduced camera system is empty, landmarks are solved block by block
-    chk = best_checker().load(prob2)
+    # all cameras fixed, points free: reduced camera system is empty, landmarks are solved block by block.
+    # The reference itself segfaults here (LinearSolverDense/Eigen LDLT reads coeff(0,0) of a 0x0 matrix), so the
+    # checker is the restatement, which treats the empty system as solved.
+    chk = BaOracle("port").load(prob2)
     free_pts = BundlerLib().load(prob2)
     run_side_by_side(free_pts, chk, [1.8], 1e9, 3, tag="points_only")
 
