@@ -1,0 +1,59 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/mage_b200.h declares, and fails
+loudly (MAGE_ERR_CUDA, no CPU fallback) when no device is present. No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    src = open(os.path.join(ROOT, "include", "mage_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mage_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mageslam_b200 import _lib
+    L = _lib.lib()
+    names = declared_functions()
+    assert len(names) > 45
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, "declared in include/mage_b200.h but not exported: %s" % missing
+
+
+def test_struct_layouts_match_the_reference_types():
+    from mageslam_b200 import _lib
+    assert _lib.KEYPOINT_DTYPE.itemsize == 28          # cv::KeyPoint
+    assert _lib.DMATCH_DTYPE.itemsize == 12
+    assert C.sizeof(_lib.OrbParams) == 14 * 4          # the 14 OrbDetector ctor scalars
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    import numpy as np
+    from mageslam_b200._lib import MAGE_ERR_CUDA, MageError
+    from mageslam_b200.bundler import BundlerLib
+    from mageslam_b200.matcher import Matcher
+    from mageslam_b200.orb import FeatureExtractorSettings, OrbFeatureDetector
+    for make in (lambda: OrbFeatureDetector(FeatureExtractorSettings.tier()).Process(np.zeros((480, 640), np.uint8)),
+                 lambda: Matcher(100, 1), lambda: BundlerLib()):
+        with pytest.raises(MageError) as ei:
+            make()
+        assert ei.value.code == MAGE_ERR_CUDA
+
+
+def test_product_does_not_import_the_oracle():
+    # the oracle is test infrastructure: nothing under mageslam_b200/ may reference it
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mageslam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                if re.search(r"oracle/|liborb_oracle|libba_oracle|libbundler_ref|tests\.oracle|from tests", txt):
+                    bad.append(f)
+    assert not bad, bad

@@ -1,0 +1,62 @@
+"""GPU tests of the video front-end (mage_frontend_*): batch extract + match-vs-previous equals the single-call APIs and the oracle."""
+import numpy as np
+import pytest
+
+from mageslam_b200 import synth
+from mageslam_b200.frontend import FrontEnd
+from mageslam_b200.matcher import Match
+from mageslam_b200.orb import FeatureExtractorSettings, OrbFeatureDetector
+from tests import oracle_orb as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def tuples(m, q="query_idx", t="train_idx"):
+    return [(int(a), int(b), float(d)) for a, b, d in zip(m[q], m[t], m["distance"])]
+
+
+@pytest.mark.parametrize("chunk", [0, 3])
+def test_host_and_device_variants_match_single_calls(chunk):
+    import torch
+    s = FeatureExtractorSettings.tier()
+    vid = synth.video_frames(10, 640, 480, seed=2)
+    det = OrbFeatureDetector(s)
+    singles = [det.Process(f) for f in vid]
+    fe = FrontEnd(s, 640, 480, batch=5, chunk=chunk)
+    outs = fe.alloc_outputs(pinned=True)
+    h = torch.from_numpy(vid).pin_memory()
+    d = h.cuda()
+    fe_dev = FrontEnd(s, 640, 480, batch=5, chunk=chunk)
+    for call in range(2):                       # second call matches its first frame against the last frame of the first call
+        kps, desc, cnt, mt, mc = fe.Process(h[call * 5:(call + 1) * 5], outs)
+        fe_dev.ProcessDevice(d[call * 5:(call + 1) * 5], torch.cuda.current_stream())
+        dk, dd, dc, dm, dmc = fe_dev.ReadDeviceResults()
+        for i in range(5):
+            g = call * 5 + i
+            sk, sd = singles[g]
+            assert cnt[i] == len(sk) == dc[i]
+            assert kps[i, :cnt[i]].tobytes() == sk.tobytes() == dk[i, :dc[i]].tobytes()
+            assert np.array_equal(desc[i, :cnt[i]], sd) and np.array_equal(dd[i, :dc[i]], sd)
+            if g == 0:
+                assert mc[i] == 0 and dmc[i] == 0          # no predecessor
+            else:
+                ref = Match(sd, singles[g - 1][1], None, None, 30, 1)
+                assert tuples(mt[i, :mc[i]]) == tuples(ref) == tuples(dm[i, :dmc[i]])
+                assert mc[i] > 100
+    # oracle cross-check of one pair end to end
+    o1 = orc.detect_and_compute(orc.tier_params(), vid[7], 1)[1]; o0 = orc.detect_and_compute(orc.tier_params(), vid[6], 1)[1]
+    assert tuples(mt[2, :mc[2]]) == tuples(orc.match(o1, o0, 30, 1), "query", "train")
+
+
+def test_reset_forgets_predecessor():
+    import torch
+    s = FeatureExtractorSettings.tier(num_features=500, num_levels=4)
+    vid = torch.from_numpy(synth.video_frames(4, 640, 480, seed=4)).pin_memory()
+    fe = FrontEnd(s, 640, 480, batch=2)
+    outs = fe.alloc_outputs()
+    fe.Process(vid[:2], outs)
+    _, _, _, _, mc = fe.Process(vid[2:], outs)
+    assert mc[0] > 0
+    fe.Reset()
+    _, _, _, _, mc = fe.Process(vid[2:], outs)
+    assert mc[0] == 0 and mc[1] > 0
