@@ -248,7 +248,7 @@ def run_ours(args):
     fe_dev = FrontEnd(settings, W, H, B, chunk=B)
     fe_host = FrontEnd(settings, W, H, B, chunk=args.chunk)
     outs = fe_host.alloc_outputs(pinned=True)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # the launching stream: kernels AND the timing events are enqueued on it
     nb = ring_n // B
 
     def barrier():

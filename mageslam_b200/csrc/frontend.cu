@@ -96,7 +96,8 @@ extern "C" void mage_frontend_destroy(mage_frontend_s* f)
 extern "C" int mage_frontend_reset(mage_frontend_s* f)
 {
     MAGE_REQUIRE(f, MAGE_ERR_INVALID, "null handle");
-    MAGE_CUDA_TRY(cudaMemsetAsync(f->d_counts, 0, sizeof(int), f->s_compute));
+    MAGE_CUDA_TRY(cudaDeviceSynchronize());
+    MAGE_CUDA_TRY(cudaMemset(f->d_counts, 0, sizeof(int)));
     f->has_prev = false;
     return MAGE_OK;
 }
@@ -125,7 +126,7 @@ static int frontend_roll(mage_frontend_s* f, int n, cudaStream_t s)
 extern "C" int mage_frontend_process_device(mage_frontend_s* f, const uint8_t* d_images, int n, int stride, size_t frame_stride, void* stream)
 {
     MAGE_REQUIRE(f && d_images && n >= 1 && n <= f->batch, MAGE_ERR_INVALID, "mage_frontend_process_device: bad argument");
-    cudaStream_t s = stream ? (cudaStream_t)stream : f->s_compute;
+    cudaStream_t s = (cudaStream_t)stream;       // NULL = the default stream, like any CUDA API
     for (int c0 = 0; c0 < n; c0 += f->chunk) {
         int c1 = std::min(n, c0 + f->chunk);
         int rc = frontend_compute(f, d_images + (size_t)c0 * frame_stride, stride, frame_stride, c0, c1, s);
