@@ -216,7 +216,7 @@ __device__ void phase_build_points(const BaDev& p, double delta, int tid, int nt
     for (int li = tid; li < p.Pl; li += nt) {
         double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
         for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
-            const int e = p.l_edges[k];
+            const int e = k;                              // edges are stored grouped by landmark
             const int hj = p.cam_h[p.e_cam[e]];
             double Ji[6], Jj[12];
             edge_jacobians(p, e, Ji, Jj, hj >= 0);
@@ -339,14 +339,17 @@ __device__ void phase_schur_points(const BaDev& p, double lambda, int tid, int n
         p.db[3 * li + 1] = D[3] * b0 + D[4] * b1 + D[5] * b2;
         p.db[3 * li + 2] = D[6] * b0 + D[7] * b1 + D[8] * b2;
         for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
-            const int e = p.l_edges[k];
+            const int e = k;
             if (p.cam_h[p.e_cam[e]] < 0) continue;
-            const double* W = p.W + 18 * (size_t)e;
-            double* WD = p.WD + 18 * (size_t)e;
+            const double* __restrict__ W = p.W + 18 * (size_t)e;
+            double* __restrict__ WD = p.WD + 18 * (size_t)e;
+            double w[18];
+#pragma unroll
+            for (int i = 0; i < 18; i++) w[i] = W[i];              // all loads in flight before the first store
 #pragma unroll
             for (int r = 0; r < 6; r++)
 #pragma unroll
-                for (int c = 0; c < 3; c++) WD[r * 3 + c] = W[r * 3] * D[c] + W[r * 3 + 1] * D[3 + c] + W[r * 3 + 2] * D[6 + c];
+                for (int c = 0; c < 3; c++) WD[r * 3 + c] = w[r * 3] * D[c] + w[r * 3 + 1] * D[3 + c] + w[r * 3 + 2] * D[6 + c];
         }
     }
     for (int i = tid; i < p.n * p.n; i += nt) p.S[i] = 0.0;
@@ -487,7 +490,7 @@ __device__ void phase_backsub(const BaDev& p, int tid, int nt)
     for (int li = tid; li < p.Pl; li += nt) {
         double c0 = p.bl[3 * li], c1 = p.bl[3 * li + 1], c2 = p.bl[3 * li + 2];
         for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
-            const int e = p.l_edges[k];
+            const int e = k;
             const int hj = p.cam_h[p.e_cam[e]];
             if (hj < 0) continue;
             const double* W = p.W + 18 * (size_t)e;
@@ -569,14 +572,46 @@ __device__ void phase_classify(const BaDev& p, double maxErrSq, double* sh, doub
 // (ref optimization_algorithm_levenberg.cpp:57-149, up to 10 lambda trials), then the outlier classification.
 constexpr int kBaThreads = 512;
 
-__global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq)
+// Shared-memory residency: the reduced system S (n x n) + its right-hand side and the camera state (pose, intrinsics,
+// Hessian index) live in dynamic shared memory whenever they fit -- the dense LDL^T and every per-edge camera lookup then run
+// at shared-memory latency instead of L2 latency. Global memory stays the source of truth across launches.
+constexpr int kBaMaxSmemCams = 128;
+
+__host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) * ((size_t)n * n + n); }
+__host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
+
+__global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq,
+                                                            unsigned dynBytes)
 {
+    extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ double sh[33];
     __shared__ double s_lambda, s_ni, s_rho;
     __shared__ int s_accept, s_stop;
     __shared__ BaDev s_p;
+    __shared__ double *g_cam_q, *g_cam_t;       // global home of the camera state (written back at the end)
     const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-    if (tid == 0) s_p = probs[blockIdx.x];
+    if (tid == 0) {
+        s_p = probs[blockIdx.x];
+        g_cam_q = nullptr; g_cam_t = nullptr;
+        size_t off = 0;
+        if (s_p.n > 0 && ba_smem_need_S(s_p.n) <= dynBytes) {
+            s_p.S = reinterpret_cast<double*>(dyn); s_p.bs = s_p.S + (size_t)s_p.n * s_p.n;
+            off = ba_smem_need_S(s_p.n);
+        }
+        if (s_p.K <= kBaMaxSmemCams && off + ba_smem_need_cams(s_p.K) <= dynBytes) {
+            double* c = reinterpret_cast<double*>(dyn + off);
+            g_cam_q = s_p.cam_q; g_cam_t = s_p.cam_t;
+            const double *gf = s_p.cam_f, *gx = s_p.cam_cx, *gy = s_p.cam_cy; const int* gh = s_p.cam_h;
+            double* sq = c; double* st = c + 4 * s_p.K; double* sf = c + 7 * s_p.K; double* sx = c + 8 * s_p.K; double* sy = c + 9 * s_p.K;
+            int* shh = reinterpret_cast<int*>(c + 10 * s_p.K);
+            for (int k = 0; k < s_p.K; k++) {
+                for (int j = 0; j < 4; j++) sq[4 * k + j] = g_cam_q[4 * k + j];
+                for (int j = 0; j < 3; j++) st[3 * k + j] = g_cam_t[3 * k + j];
+                sf[k] = gf[k]; sx[k] = gx[k]; sy[k] = gy[k]; shh[k] = gh[k];
+            }
+            s_p.cam_q = sq; s_p.cam_t = st; s_p.cam_f = sf; s_p.cam_cx = sx; s_p.cam_cy = sy; s_p.cam_h = shh;
+        }
+    }
     __syncthreads();
     const BaDev& p = s_p;
     BaCtl* ctl = p.ctl;
@@ -657,6 +692,10 @@ __global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restri
     }
     double errSum; int inl;
     phase_classify(p, (double)maxErrSq, sh, errSum, inl);
+    if (g_cam_q) {
+        for (int i = tid; i < 4 * p.K; i += nt) g_cam_q[i] = p.cam_q[i];
+        for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
+    }
     if (tid == 0) {
         ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
         ctl->err_sum = errSum; ctl->inlier_count = inl; ctl->stop_flag = s_stop;
@@ -719,6 +758,16 @@ struct mage_ba_s {
     int64_t stats[4] = {0, 0, 0, 0};
 };
 
+// dynamic shared memory for one problem: reduced system + camera state when they fit in 200 KB, else whatever subset fits
+static size_t ba_dyn_smem(int n, int K)
+{
+    const size_t limit = 200 * 1024;
+    size_t need = 0;
+    if (n > 0 && ba_smem_need_S(n) <= limit) need = ba_smem_need_S(n);
+    if (K <= kBaMaxSmemCams && need + ba_smem_need_cams(K) <= limit) need += ba_smem_need_cams(K);
+    return need;
+}
+
 static int ba_upload_state(mage_ba_t h)
 {
     // camera / point state and intrinsics live in one arena sized at first upload (pools are allocated once, ref :198-230)
@@ -767,6 +816,10 @@ static int ba_build_structure(mage_ba_t h)
     for (int k = 0; k < h->K; k++) if (camA[k] && !h->cam_fixed[k]) { cam_h[k] = (int)c_cam.size(); c_cam.push_back(k); }
     if (!h->points_fixed)       // point vertex ids count down (ref BundlerLib.cpp:210-218): Hessian order = descending index
         for (int i = h->P - 1; i >= 0; i--) if (ptA[i]) { pt_l[i] = (int)l_pt.size(); l_pt.push_back(i); }
+    // device edge order: grouped by landmark (so a landmark's edges are contiguous and l_edges is the identity), insertion
+    // order inside a group; the reference's activeEdges order (insertion) is restored on the host when outliers are reported
+    if (!h->points_fixed)
+        std::stable_sort(h->active.begin(), h->active.end(), [&](int a, int b) { return pt_l[h->obs[a].pt] < pt_l[h->obs[b].pt]; });
     const int Kf = (int)c_cam.size(), Pl = (int)l_pt.size(), n = 6 * Kf;
     h->useless = (Kf + Pl) == 0;
     h->dirty = false;
@@ -867,6 +920,7 @@ extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
     mage_ba_s* h = new mage_ba_s();
     h->points_fixed = are_points_fixed != 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return MAGE_ERR_CUDA; }
+    if (cudaFuncSetAttribute(k_ba_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); cudaStreamDestroy(h->stream); delete h; return MAGE_ERR_CUDA; }
     *out = h;
     return MAGE_OK;
 }
@@ -1018,14 +1072,17 @@ static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, f
     h->lambda = c.lambda;
     h->stats[0] = c.lm_iters; h->stats[1] = c.lm_trials;
     h->host_state_valid = false;
-    int m = 0;
+    std::vector<std::pair<long, int>> flagged;                          // (insertion sequence, observation) of every removed edge
     for (int a = 0; a < h->dev.Ea; a++)
-        if (flags[a]) {
-            const int e = h->active[a];
-            h->obs[e].removed = true; h->dirty = true;                 // removeEdge => m_dirty (ref :112-116, :435-441)
-            if (outliers && m < cap) outliers[m] = (unsigned)e;
-            m++;
-        }
+        if (flags[a]) flagged.push_back({h->obs[h->active[a]].seq, h->active[a]});
+    std::sort(flagged.begin(), flagged.end());                          // the reference walks activeEdges() in insertion order (:387)
+    int m = 0;
+    for (auto& fl : flagged) {
+        const int e = fl.second;
+        h->obs[e].removed = true; h->dirty = true;                     // removeEdge => m_dirty (ref :112-116, :435-441)
+        if (outliers && m < cap) outliers[m] = (unsigned)e;
+        m++;
+    }
     *n_out = m;
     *mean = (float)(c.err_sum / (double)c.inlier_count);               // NaN when no inlier, like the reference's 0/0
     return MAGE_OK;
@@ -1038,7 +1095,7 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
     int rc = ba_prepare(h, huber, n_iters);
     if (rc) return rc;
     if (!h->useless) {
-        { ProfScope ps(PROF_BA_STEP, h->stream); k_ba_step<<<1, kBaThreads, 0, h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq); }
+        { ProfScope ps(PROF_BA_STEP, h->stream); k_ba_step<<<1, kBaThreads, ba_dyn_smem(h->dev.n, h->dev.K), h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, (unsigned)ba_dyn_smem(h->dev.n, h->dev.K)); }
         MAGE_CUDA_TRY(cudaGetLastError());
         h->stats[2]++;
     }
@@ -1057,6 +1114,8 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
         if (!hs[i]->useless) { table.push_back(hs[i]->dev); live.push_back(i); }
     }
     mage_ba_t lead = hs[0];
+    size_t dyn = 0;
+    for (auto& d : table) dyn = std::max(dyn, ba_dyn_smem(d.n, d.K));
     if (!table.empty()) {
         if ((int)table.size() > lead->table_cap) {
             if (lead->d_table) cudaFree(lead->d_table);
@@ -1067,7 +1126,7 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
         cudaError_t e = cudaMemcpyAsync(d_table, table.data(), sizeof(BaDev) * table.size(), cudaMemcpyHostToDevice, lead->stream);
         for (int i : live) if (e == cudaSuccess && hs[i] != lead) e = cudaStreamSynchronize(hs[i]->stream);
         if (e == cudaSuccess) {
-            { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step<<<(unsigned)table.size(), kBaThreads, 0, lead->stream>>>(d_table, hs[live[0]]->d_huber, n_iters, max_err_sq); }
+            { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step<<<(unsigned)table.size(), kBaThreads, dyn, lead->stream>>>(d_table, hs[live[0]]->d_huber, n_iters, max_err_sq, (unsigned)dyn); }
             e = cudaGetLastError();
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(lead->stream);

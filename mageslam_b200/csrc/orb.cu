@@ -38,7 +38,7 @@ struct LevelGeom {
     unsigned sel_off;       // entry offset inside a frame's selected array
     unsigned tab_x, tab_y;  // offsets of the resize tables (destination = this level)
     int fast_tiles_x, fast_tiles_y, fast_tile_base;
-    int blur_tiles_x, blur_tiles_y, blur_tile_base;
+    int blur_tiles_x, blur_tiles_y, blur_tile_base;      // tile rows = kBlurOH (generic kernel) or 8*kBlur7Rows (7x7 fast path)
 };
 
 struct OrbGeom {
@@ -150,10 +150,61 @@ __device__ __forceinline__ int fast_score16(const uint8_t* c)      // c = centre
     return max(q0, -q1) - 1;
 }
 
+// Two horizontally adjacent pixels per thread in packed s16x2 form (VIADD.16x2 / VIMNMX3.S16x2 on sm_100a): e[k] = ring - centre
+// for both pixels, sliding minimum/maximum over 9 consecutive ring positions as two levels of 3-input min/max.
+// The pixel tile is staged as u16 twice -- A[y][x] and As[y][x] = A[y][x+1] -- so that every (pixel, right neighbour) pair
+// is one aligned 32-bit shared-memory load whatever the parity of its column.
+constexpr int kFastP16 = kFastPW;                 // u16 elements per staged row
+
+template <int DX, int DY>
+__device__ __forceinline__ uint32_t ring_pair(const uint16_t* A, const uint16_t* As, int py, int px /* odd */)
+{
+    // column of the first pixel of the pair: c = px + DX; c even -> A[c], c odd -> As[c - 1]
+    const int c = px + DX;
+    const uint16_t* base = ((DX & 1) != 0) ? A : As;           // px is odd: DX odd => c even
+    const int col = ((DX & 1) != 0) ? c : c - 1;
+    return *reinterpret_cast<const uint32_t*>(base + (py + DY) * kFastP16 + col);
+}
+
+__device__ __forceinline__ uint32_t fast_score_pair(const uint16_t* A, const uint16_t* As, int py, int px)
+{
+    const uint32_t vv = ring_pair<0, 0>(A, As, py, px);
+    const uint32_t nv = __vadd2(~vv, 0x00010001u);               // (-v0, -v1)
+    uint32_t e[16];
+    e[0] = __vadd2(ring_pair<0, 3>(A, As, py, px), nv);   e[1] = __vadd2(ring_pair<1, 3>(A, As, py, px), nv);
+    e[2] = __vadd2(ring_pair<2, 2>(A, As, py, px), nv);   e[3] = __vadd2(ring_pair<3, 1>(A, As, py, px), nv);
+    e[4] = __vadd2(ring_pair<3, 0>(A, As, py, px), nv);   e[5] = __vadd2(ring_pair<3, -1>(A, As, py, px), nv);
+    e[6] = __vadd2(ring_pair<2, -2>(A, As, py, px), nv);  e[7] = __vadd2(ring_pair<1, -3>(A, As, py, px), nv);
+    e[8] = __vadd2(ring_pair<0, -3>(A, As, py, px), nv);  e[9] = __vadd2(ring_pair<-1, -3>(A, As, py, px), nv);
+    e[10] = __vadd2(ring_pair<-2, -2>(A, As, py, px), nv); e[11] = __vadd2(ring_pair<-3, -1>(A, As, py, px), nv);
+    e[12] = __vadd2(ring_pair<-3, 0>(A, As, py, px), nv);  e[13] = __vadd2(ring_pair<-3, 1>(A, As, py, px), nv);
+    e[14] = __vadd2(ring_pair<-2, 2>(A, As, py, px), nv);  e[15] = __vadd2(ring_pair<-1, 3>(A, As, py, px), nv);
+    uint32_t lo3[16], hi3[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        lo3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+        hi3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+    }
+    uint32_t m9[16], M9[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        m9[k] = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+        M9[k] = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+    }
+    // with e = -d:  max_k min9(d) = -min_k max9(e),  -min_k max9(d) = max_k min9(e)
+    uint32_t a = __vimax3_s16x2(m9[0], m9[1], m9[2]), bq = __vimin3_s16x2(M9[0], M9[1], M9[2]);
+#pragma unroll
+    for (int k = 3; k < 15; k += 2) { a = __vimax3_s16x2(a, m9[k], m9[k + 1]); bq = __vimin3_s16x2(bq, M9[k], M9[k + 1]); }
+    a = __vmaxs2(a, m9[15]); bq = __vmins2(bq, M9[15]);
+    const uint32_t negb = __vadd2(~bq, 0x00010001u);
+    return __vadd2(__vmaxs2(a, negb), 0xFFFFFFFFu);              // score = max(...) - 1 per half
+}
+
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
-    __shared__ __align__(16) uint8_t px[kFastPH * kFastPW];
-    __shared__ uint8_t sc[kFastSH * kFastPW];
+    __shared__ __align__(16) uint16_t A[kFastPH * kFastP16];
+    __shared__ __align__(16) uint16_t As[kFastPH * kFastP16];
+    __shared__ __align__(4) uint8_t sc[kFastSH * kFastPW];
     const int f = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].fast_tile_base) l++;
@@ -164,25 +215,36 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     int pitch;
     const uint8_t* img = level_ptr(g, b, f, l, pitch);
 
-    // stage the pixel tile: 32-bit loads, zero fill outside the image rows / pitch
+    // stage the pixel tile: 32-bit global loads (zero fill outside the image rows / pitch), widened to u16 twice
     for (int i = threadIdx.x; i < kFastPH * (kFastPW / 4); i += blockDim.x) {
-        int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
-        int y = py0 + ry, x = px0 + rx;
+        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
+        const int y = py0 + ry, x = px0 + rx;
         uint32_t v = 0;
         if (y >= 0 && y < L.h && x >= 0 && x + 4 <= pitch) v = *reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch + x);
-        *reinterpret_cast<uint32_t*>(&px[ry * kFastPW + rx]) = v;
+        const uint32_t p01 = __byte_perm(v, 0, 0x4140), p23 = __byte_perm(v, 0, 0x4342), p12 = __byte_perm(v, 0, 0x4241);
+        uint16_t* a = A + ry * kFastP16 + rx;
+        uint16_t* as = As + ry * kFastP16 + rx;
+        *reinterpret_cast<uint32_t*>(a) = p01;
+        *reinterpret_cast<uint32_t*>(a + 2) = p23;
+        if (rx > 0) as[-1] = (uint16_t)(v & 0xff);               // As[x] = A[x + 1]
+        *reinterpret_cast<uint32_t*>(as) = p12;
+        as[2] = (uint16_t)(v >> 24);
     }
     __syncthreads();
     const int thr = g.fast_threshold;
-    for (int i = threadIdx.x; i < kFastSH * kFastSW; i += blockDim.x) {
-        int sy = i / kFastSW, sx = i % kFastSW;
-        int x = px0 + 3 + sx, y = py0 + 3 + sy;
-        int s = 0;
-        if (x >= 3 && x <= L.w - 4 && y >= 3 && y <= L.h - 4) {
-            s = fast_score16(&px[(sy + 3) * kFastPW + sx + 3]);
-            s = (s >= thr) ? s : 0;                 // stored as uchar in the reference: 0 for non-corners
+    constexpr int kPairs = kFastSW / 2;                          // 61 pairs per score row
+    for (int i = threadIdx.x; i < kFastSH * kPairs; i += blockDim.x) {
+        const int sy = i / kPairs, sx = (i - sy * kPairs) * 2;
+        const int x = px0 + 3 + sx, y = py0 + 3 + sy;
+        uint32_t out = 0;
+        if (y >= 3 && y <= L.h - 4 && x + 1 >= 3 && x <= L.w - 4) {
+            const uint32_t s2 = fast_score_pair(A, As, sy + 3, sx + 3);
+            int s0 = (int)(short)(s2 & 0xffff), s1 = (int)(short)(s2 >> 16);
+            s0 = (s0 >= thr && x >= 3) ? s0 : 0;                 // stored as uchar in the reference: 0 for non-corners
+            s1 = (s1 >= thr && x + 1 <= L.w - 4) ? s1 : 0;
+            out = (uint32_t)s0 | ((uint32_t)s1 << 8);
         }
-        sc[sy * kFastPW + sx] = (uint8_t)s;
+        *reinterpret_cast<uint16_t*>(&sc[sy * kFastPW + sx]) = (uint16_t)out;
     }
     __syncthreads();
     const int bd = g.border;
@@ -458,6 +520,65 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
     }
 }
 
+// 7x7 fast path (the reference default GaussianKernelSize and every BASELINE config). The Q8.8 convolution is exact
+// integer arithmetic (sum of products <= 2^24, one rounding at the end), so the horizontal taps run as two IDP.4A per pixel on
+// funnel-shifted words and the vertical taps as IMADs over a register column; no shared memory, 32-bit coalesced loads/stores.
+constexpr int kBlur7Rows = 16;      // output rows per thread (22 source rows incl. the +-3 halo)
+
+__device__ __forceinline__ uint32_t load_word_reflect(const uint8_t* row, int x, int w)
+{
+    if (x >= 0 && x + 4 <= w) return *reinterpret_cast<const uint32_t*>(row + x);
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) v |= (uint32_t)row[reflect101(x + i, w)] << (8 * i);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    const int f = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_base) l++;
+    const LevelGeom& L = g.lv[l];
+    const int t = blockIdx.x - L.blur_tile_base;
+    const int x = (t % L.blur_tiles_x) * 128 + (threadIdx.x & 31) * 4;
+    const int y0 = (t / L.blur_tiles_x) * (8 * kBlur7Rows) + (threadIdx.x >> 5) * kBlur7Rows;
+    if (x >= L.w || y0 >= L.h) return;
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+    const uint32_t K0 = (uint32_t)g.gk[0] | ((uint32_t)g.gk[1] << 8) | ((uint32_t)g.gk[2] << 16) | ((uint32_t)g.gk[3] << 24);
+    const uint32_t K1 = (uint32_t)g.gk[4] | ((uint32_t)g.gk[5] << 8) | ((uint32_t)g.gk[6] << 16);
+    int T[kBlur7Rows + 6][4];
+#pragma unroll
+    for (int i = 0; i < kBlur7Rows + 6; i++) {
+        const int sy = reflect101(min(y0 + i - 3, L.h + 2), L.h);
+        const uint8_t* row = img + (size_t)sy * pitch;
+        const uint32_t w0 = load_word_reflect(row, x - 4, L.w), w1 = load_word_reflect(row, x, L.w), w2 = load_word_reflect(row, x + 4, L.w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t v0 = (j == 3) ? w1 : __funnelshift_r(w0, w1, 8 * (1 + j));     // bytes x-3+j .. x+j
+            const uint32_t v1 = (j == 3) ? w2 : __funnelshift_r(w1, w2, 8 * (1 + j));     // bytes x+1+j .. x+4+j
+            T[i][j] = (int)__dp4a(v1, K1, __dp4a(v0, K0, 0u));
+        }
+    }
+    uint8_t* out = blur_ptr(g, b, f, l);
+#pragma unroll
+    for (int r = 0; r < kBlur7Rows; r++) {
+        const int y = y0 + r;
+        if (y < L.h) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                unsigned acc = 32768u;
+#pragma unroll
+                for (int k = 0; k < 7; k++) acc += (unsigned)g.gk[k] * (unsigned)T[r + k][j];
+                packed |= (acc >> 16) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K4+K7: orientation + rBRIEF
 // ref OpenCVModified.cpp:399-437 (ICAngles), :756-760 (rescale), :502-549 (ComputeOrbDescriptorsPrerotated),
 // cv::fastAtan2 restated in SURVEY appendix A.1 (float32, no FMA contraction).
@@ -703,7 +824,7 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
         L.tab_x = (unsigned)tab; tab += L.w; L.tab_y = (unsigned)tab; tab += L.h;
         L.fast_tiles_x = div_up(L.w, kFastOW); L.fast_tiles_y = div_up(L.h, kFastOH); L.fast_tile_base = ftiles;
         ftiles += L.fast_tiles_x * L.fast_tiles_y;
-        L.blur_tiles_x = div_up(L.w, kBlurOW); L.blur_tiles_y = div_up(L.h, kBlurOH); L.blur_tile_base = btiles;
+        L.blur_tiles_x = div_up(L.w, kBlurOW); L.blur_tiles_y = div_up(L.h, g.ksize == 7 ? 8 * kBlur7Rows : kBlurOH); L.blur_tile_base = btiles;
         btiles += L.blur_tiles_x * L.blur_tiles_y;
     }
     h->fast_tiles = ftiles; h->blur_tiles = btiles;
@@ -801,7 +922,8 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
             k_resize<<<grid, block, 0, s>>>(g, bufs, l);
         }
     }
-    if (g.ksize > 1) { ProfScope ps(PROF_BLUR, s); k_blur<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs); }
+    if (g.ksize == 7) { ProfScope ps(PROF_BLUR, s); k_blur7<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs); }
+    else if (g.ksize > 1) { ProfScope ps(PROF_BLUR, s); k_blur<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs); }
     { ProfScope ps(PROF_FAST, s); k_fast<<<dim3(h->fast_tiles, n), 256, 0, s>>>(g, bufs); }
     { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }
     { ProfScope ps(PROF_ORIENT_DESCRIBE, s); k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity); }
