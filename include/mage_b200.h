@@ -129,7 +129,7 @@ int  mage_match_bf(mage_matcher_t m, const uint8_t* descA, int nA, const uint8_t
 
 /* Device-resident batched variant: pair p matches A = d_desc + a_index[p]*slot_stride (d_counts[a_index[p]]
  * descriptors) against B likewise; a_index/b_index are host arrays of n_pairs entries. Outputs
- * d_matches[p][capacity], d_match_counts[p]. Asynchronous. */
+ * d_matches[p][capacity], d_match_counts[p]. d_desc and slot_stride must be 16-byte aligned. Asynchronous. */
 int  mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, const int* d_counts, size_t slot_stride,
                           const int* a_index, const int* b_index, int n_pairs, int max_hamming, int min_hamming_diff,
                           mage_dmatch* d_matches, int capacity, int* d_match_counts, void* cuda_stream);

@@ -37,91 +37,101 @@ __device__ __forceinline__ int job_count(const MatchJob& j, int side)
     return max(0, min(n, j.cap));
 }
 
-// best[pair][dir][q] = (distance << 16 | train) or kNoKey
-__global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ best, int stride,
-                                                           int max_hamming, int min_diff)
+// The distance matrix is evaluated ONCE for both directions. Each (a, b) first goes through a 96-bit filter -- the first three
+// words with a carry-save adder (ones = x0^x1^x2, twos = maj(x0,x1,x2); popc(ones) + 2 popc(twos) is the exact 96-bit
+// distance, a lower bound of the full one) -- which rejects all but ~1e-4 of random pairs at maxHamming 30 with 2 POPC.
+// Survivors get the exact 256-bit distance; if it is within maxHamming the pair updates four packed (distance << 16 | index)
+// slots with integer atomics: best/second of row a (A -> B) and best/second of column b (B -> A). "second" receives the
+// loser of every best update, which yields exactly the second smallest key whatever the arrival order, so the result is
+// deterministic. stats layout: [pair][4][stride] = fwd best, fwd second, bwd best, bwd second.
+__global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
 {
     __shared__ uint32_t tw[8][kChunk];          // train words, transposed: conflict-free lane-strided reads
+    __shared__ uint32_t tx[kChunk];             // t0 ^ t1 ^ t2 per train
     __shared__ uint8_t tvalid[kChunk];
     __shared__ uint32_t qw[kQPerBlock][8];
-    const int pair = blockIdx.y >> 1, dir = blockIdx.y & 1;
+    const int pair = blockIdx.y;
     const MatchJob& job = jobs[pair];
-    const int nQ = job_count(job, dir), nT = job_count(job, dir ^ 1);
+    const int nQ = job_count(job, 0), nT = job_count(job, 1);
     const int q0 = blockIdx.x * kQPerBlock;
     if (q0 >= nQ) return;
-    const uint32_t* Q = reinterpret_cast<const uint32_t*>(job.desc[dir]);
-    const uint32_t* T = reinterpret_cast<const uint32_t*>(job.desc[dir ^ 1]);
-    const uint8_t* mQ = job.mask[dir];
-    const uint8_t* mT = job.mask[dir ^ 1];
+    const uint32_t* Q = reinterpret_cast<const uint32_t*>(job.desc[0]);
+    const uint4* T4 = reinterpret_cast<const uint4*>(job.desc[1]);
+    const uint8_t* mQ = job.mask[0];
+    const uint8_t* mT = job.mask[1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned* fbest = stats + ((size_t)pair * 4 + 0) * stride;
+    unsigned* fsecond = stats + ((size_t)pair * 4 + 1) * stride;
+    unsigned* bbest = stats + ((size_t)pair * 4 + 2) * stride;
+    unsigned* bsecond = stats + ((size_t)pair * 4 + 3) * stride;
 
     for (int i = threadIdx.x; i < kQPerBlock * 8; i += blockDim.x) {
         int q = q0 + (i >> 3);
         qw[i >> 3][i & 7] = (q < nQ) ? Q[(size_t)q * 8 + (i & 7)] : 0u;
     }
-    unsigned bkey[kQPerWarp], second[kQPerWarp];
+    __syncthreads();
+    uint32_t q[kQPerWarp][3], qx[kQPerWarp];
+    bool qok[kQPerWarp];
 #pragma unroll
-    for (int k = 0; k < kQPerWarp; k++) { bkey[k] = kNoKey; second[k] = 0xFFFFu; }
-
+    for (int k = 0; k < kQPerWarp; k++) {
+        const int qi = q0 + warp * kQPerWarp + k;
+        q[k][0] = qw[warp * kQPerWarp + k][0]; q[k][1] = qw[warp * kQPerWarp + k][1]; q[k][2] = qw[warp * kQPerWarp + k][2];
+        qx[k] = q[k][0] ^ q[k][1] ^ q[k][2];
+        qok[k] = qi < nQ && (!mQ || mQ[qi]);
+    }
     for (int c0 = 0; c0 < nT; c0 += kChunk) {
         __syncthreads();
-        for (int i = threadIdx.x; i < kChunk * 8; i += blockDim.x) {
-            int t = c0 + (i >> 3);
-            tw[i & 7][i >> 3] = (t < nT) ? T[(size_t)t * 8 + (i & 7)] : 0u;
-        }
-        for (int i = threadIdx.x; i < kChunk; i += blockDim.x) {
-            int t = c0 + i;
-            tvalid[i] = (t < nT && (!mT || mT[t])) ? 1 : 0;
+        // 16-byte coalesced global loads; thread i -> descriptor i/2, half i%2
+        for (int i = threadIdx.x; i < kChunk * 2; i += blockDim.x) {
+            const int tl = i >> 1, half = i & 1, t = c0 + tl;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (t < nT) v = T4[(size_t)t * 2 + half];
+            tw[half * 4 + 0][tl] = v.x; tw[half * 4 + 1][tl] = v.y; tw[half * 4 + 2][tl] = v.z; tw[half * 4 + 3][tl] = v.w;
+            if (half == 0) { tx[tl] = v.x ^ v.y ^ v.z; tvalid[tl] = (t < nT && (!mT || mT[t])) ? 1 : 0; }
         }
         __syncthreads();
-        uint32_t q[kQPerWarp][8];
-#pragma unroll
-        for (int k = 0; k < kQPerWarp; k++)
-#pragma unroll
-            for (int w = 0; w < 8; w++) q[k][w] = qw[warp * kQPerWarp + k][w];
 #pragma unroll 2
         for (int i = 0; i < kChunk / 32; i++) {
             const int ti = lane + 32 * i;
-            if (!tvalid[ti]) continue;
-            uint32_t t[8];
+            const uint32_t t0 = tw[0][ti], t1 = tw[1][ti], t2 = tw[2][ti], txx = tx[ti];
+            unsigned pass = 0;
 #pragma unroll
-            for (int w = 0; w < 8; w++) t[w] = tw[w][ti];
+            for (int k = 0; k < kQPerWarp; k++) {
+                const uint32_t x0 = q[k][0] ^ t0, x1 = q[k][1] ^ t1, x2 = q[k][2] ^ t2;
+                const uint32_t twos = (x0 & x1) | (x2 & (x0 | x1));
+                const int d3 = __popc(qx[k] ^ txx) + 2 * __popc(twos);
+                pass |= (d3 <= max_hamming) ? (1u << k) : 0u;
+            }
+            if (pass == 0 || !tvalid[ti]) continue;
             const unsigned tidx = (unsigned)(c0 + ti);
 #pragma unroll
             for (int k = 0; k < kQPerWarp; k++) {
-                int d = __popc(q[k][0] ^ t[0]) + __popc(q[k][1] ^ t[1]) + __popc(q[k][2] ^ t[2]) + __popc(q[k][3] ^ t[3]);
-                if (d > max_hamming) continue;                       // radiusMatch keeps d <= maxDistance only
-                d += __popc(q[k][4] ^ t[4]) + __popc(q[k][5] ^ t[5]) + __popc(q[k][6] ^ t[6]) + __popc(q[k][7] ^ t[7]);
-                if (d > max_hamming) continue;
-                unsigned key = ((unsigned)d << 16) | tidx;
-                if (key < bkey[k]) { second[k] = bkey[k] >> 16; bkey[k] = key; }
-                else second[k] = min(second[k], (unsigned)d);
+                if (!((pass >> k) & 1) || !qok[k]) continue;
+                const int ql = warp * kQPerWarp + k;
+                int d = 0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) d += __popc(qw[ql][w] ^ tw[w][ti]);
+                if (d > max_hamming) continue;                      // radiusMatch keeps d <= maxDistance only
+                const unsigned qidx = (unsigned)(q0 + ql);
+                const unsigned kf = ((unsigned)d << 16) | tidx, kb = ((unsigned)d << 16) | qidx;
+                unsigned old = atomicMin(&fbest[qidx], kf);
+                atomicMin(&fsecond[qidx], max(old, kf));
+                old = atomicMin(&bbest[tidx], kb);
+                atomicMin(&bsecond[tidx], max(old, kb));
             }
-        }
-    }
-    // merge the 32 per-lane states of each query
-#pragma unroll
-    for (int k = 0; k < kQPerWarp; k++) {
-        unsigned bk = bkey[k], sd = second[k];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            unsigned obk = __shfl_xor_sync(0xffffffffu, bk, o), osd = __shfl_xor_sync(0xffffffffu, sd, o);
-            unsigned loser = max(bk, obk) >> 16;                     // distance of the worse of the two bests (0xFFFF if none)
-            bk = min(bk, obk);
-            sd = min(min(sd, osd), loser);
-        }
-        const int qi = q0 + warp * kQPerWarp + k;
-        if (lane == 0 && qi < nQ) {
-            unsigned res = bk;
-            if (bk == kNoKey || (mQ && !mQ[qi])) res = kNoKey;
-            else if (sd != 0xFFFFu && (int)sd - (int)(bk >> 16) < min_diff) res = kNoKey;     // ref :130-135 / :149-154
-            best[((size_t)pair * 2 + dir) * stride + qi] = res;
         }
     }
 }
 
-// ordered emission (ascending A index) with the cross-check of ref :158
-__global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__ jobs, const unsigned* __restrict__ best, int stride,
+// min-difference test (ref :130-135 / :149-154) on the packed stats, then cross-check (ref :158) and ordered emission
+__device__ __forceinline__ unsigned resolve_best(unsigned best, unsigned second, int min_diff)
+{
+    if (best == kNoKey) return kNoKey;
+    if (second != kNoKey && (int)(second >> 16) - (int)(best >> 16) < min_diff) return kNoKey;
+    return best;
+}
+
+__global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__ jobs, const unsigned* __restrict__ stats, int stride, int min_diff,
                                                     mage_dmatch* __restrict__ out, int out_cap, int* __restrict__ out_count)
 {
     __shared__ int warp_sum[8];
@@ -129,8 +139,10 @@ __global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__
     const int pair = blockIdx.x;
     const MatchJob& job = jobs[pair];
     const int nA = job_count(job, 0), nB = job_count(job, 1);
-    const unsigned* fwd = best + ((size_t)pair * 2 + 0) * stride;
-    const unsigned* bwd = best + ((size_t)pair * 2 + 1) * stride;
+    const unsigned* fbest = stats + ((size_t)pair * 4 + 0) * stride;
+    const unsigned* fsecond = stats + ((size_t)pair * 4 + 1) * stride;
+    const unsigned* bbest = stats + ((size_t)pair * 4 + 2) * stride;
+    const unsigned* bsecond = stats + ((size_t)pair * 4 + 3) * stride;
     mage_dmatch* o = out + (size_t)pair * out_cap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) base = 0;
@@ -139,10 +151,10 @@ __global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__
         const int a = a0 + threadIdx.x;
         bool ok = false; unsigned key = kNoKey;
         if (a < nA) {
-            key = fwd[a];
+            key = resolve_best(fbest[a], fsecond[a], min_diff);
             if (key != kNoKey) {
-                int t = key & 0xFFFF;
-                if (t < nB) { unsigned bk = bwd[t]; ok = bk != kNoKey && (int)(bk & 0xFFFF) == a; }
+                const int t = key & 0xFFFF;
+                if (t < nB) { const unsigned bk = resolve_best(bbest[t], bsecond[t], min_diff); ok = bk != kNoKey && (int)(bk & 0xFFFF) == a; }
             }
         }
         unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -177,7 +189,7 @@ struct mage_matcher_s {
     int max_desc = 0, max_pairs = 0;
     MatchJob* h_jobs = nullptr;     // pinned
     MatchJob* d_jobs = nullptr;
-    unsigned* d_best = nullptr;     // [max_pairs][2][max_desc]
+    unsigned* d_best = nullptr;     // [max_pairs][4][max_desc]: fwd best, fwd second, bwd best, bwd second
     uint8_t* d_stage = nullptr;     // single-pair host API staging: A, B, masks, matches, count
     mage_dmatch* h_out = nullptr;   // pinned staging for results
     int* h_count = nullptr;
@@ -198,7 +210,7 @@ extern "C" int mage_matcher_create(int max_descriptors, int max_pairs, mage_matc
     size_t stage = (size_t)max_descriptors * (32 + 32 + 1 + 1) + sizeof(mage_dmatch) * (size_t)max_descriptors + 64 + 256;
     cudaError_t e = cudaMallocHost(&m->h_jobs, sizeof(MatchJob) * max_pairs);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_jobs, sizeof(MatchJob) * max_pairs);
-    if (e == cudaSuccess) e = cudaMalloc(&m->d_best, sizeof(unsigned) * 2 * (size_t)max_pairs * max_descriptors);
+    if (e == cudaSuccess) e = cudaMalloc(&m->d_best, sizeof(unsigned) * 4 * (size_t)max_pairs * max_descriptors);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_stage, stage);
     if (e == cudaSuccess) e = cudaMallocHost(&m->h_out, sizeof(mage_dmatch) * (size_t)max_descriptors);
     if (e == cudaSuccess) e = cudaMallocHost(&m->h_count, sizeof(int));
@@ -225,9 +237,10 @@ static int match_launch(mage_matcher_t m, int n_pairs, int max_q, int max_hammin
                         int* d_counts, cudaStream_t s)
 {
     MAGE_CUDA_TRY(cudaMemcpyAsync(m->d_jobs, m->h_jobs, sizeof(MatchJob) * n_pairs, cudaMemcpyHostToDevice, s));
-    dim3 grid(div_up(max_q, kQPerBlock), 2 * n_pairs);
-    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming, min_diff); }
-    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, d_out, out_cap, d_counts); }
+    dim3 grid(div_up(max_q, kQPerBlock), n_pairs);
+    MAGE_CUDA_TRY(cudaMemsetAsync(m->d_best, 0xFF, sizeof(unsigned) * 4 * (size_t)n_pairs * m->max_desc, s));
+    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming); }
+    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, min_diff, d_out, out_cap, d_counts); }
     MAGE_CUDA_TRY(cudaGetLastError());
     return MAGE_OK;
 }
@@ -271,7 +284,7 @@ extern "C" int mage_matcher_set_jobs_device(mage_matcher_t m, const uint8_t* d_d
 {
     MAGE_REQUIRE(m && d_desc && d_counts && a_index && b_index, MAGE_ERR_INVALID, "mage_matcher_set_jobs_device: null argument");
     MAGE_REQUIRE(n_pairs >= 1 && n_pairs <= m->max_pairs, MAGE_ERR_INVALID, "n_pairs %d exceeds matcher capacity %d", n_pairs, m->max_pairs);
-    MAGE_REQUIRE(slot_stride % 4 == 0, MAGE_ERR_INVALID, "slot_stride must be a multiple of 4");
+    MAGE_REQUIRE(slot_stride % 16 == 0 && ((uintptr_t)d_desc % 16) == 0, MAGE_ERR_INVALID, "d_desc and slot_stride must be 16-byte aligned");
     const bool same = m->memo_desc == d_desc && m->memo_counts == d_counts && m->memo_stride == slot_stride &&
                       (int)m->memo_a.size() == n_pairs && std::equal(a_index, a_index + n_pairs, m->memo_a.begin()) &&
                       std::equal(b_index, b_index + n_pairs, m->memo_b.begin());
@@ -297,10 +310,11 @@ extern "C" int mage_match_run_jobs(mage_matcher_t m, int first_pair, int n_pairs
                  MAGE_ERR_INVALID, "mage_match_run_jobs: pair range outside the registered table");
     cudaStream_t s = (cudaStream_t)stream;
     const int cap = m->h_jobs[first_pair].cap;
-    dim3 grid(div_up(cap, kQPerBlock), 2 * n_pairs);
-    unsigned* best = m->d_best + (size_t)first_pair * 2 * m->max_desc;
-    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, max_hamming, min_diff); }
-    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, d_matches, capacity, d_match_counts); }
+    dim3 grid(div_up(cap, kQPerBlock), n_pairs);
+    unsigned* best = m->d_best + (size_t)first_pair * 4 * m->max_desc;
+    MAGE_CUDA_TRY(cudaMemsetAsync(best, 0xFF, sizeof(unsigned) * 4 * (size_t)n_pairs * m->max_desc, s));
+    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, max_hamming); }
+    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, min_diff, d_matches, capacity, d_match_counts); }
     MAGE_CUDA_TRY(cudaGetLastError());
     return MAGE_OK;
 }

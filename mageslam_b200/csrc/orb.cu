@@ -248,8 +248,12 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     }
     __syncthreads();
     const int bd = g.border;
-    uint32_t* cand = b.cand + (size_t)f * b.cand_stride + L.cand_off;
-    int* cnt = b.cand_count + f * kMaxLevels + l;
+    // survivors are collected in shared memory (reusing the pixel tile) and appended with ONE global atomic per CTA:
+    // a returning global atomic per warp iteration stalled the whole loop on L2 round trips (ncu: 41 % of samples)
+    uint32_t* list = reinterpret_cast<uint32_t*>(A);            // <= 960 survivors (strict NMS: one per 2x2 block)
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     for (int i = threadIdx.x; i < kFastOH * kFastOW; i += blockDim.x) {
         int oy = i / kFastOW, ox = i % kFastOW;
         int x = px0 + 4 + ox, y = py0 + 4 + oy;
@@ -258,10 +262,17 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
         bool keep = v > 0 && x >= bd && x < L.w - bd && y >= bd && y < L.h - bd &&
                     v > s[-1] && v > s[1] && v > s[-kFastPW - 1] && v > s[-kFastPW] && v > s[-kFastPW + 1] &&
                     v > s[kFastPW - 1] && v > s[kFastPW] && v > s[kFastPW + 1];
-        if (keep) {
-            int slot = atomicAdd(cnt, 1);
-            if (slot < (int)L.cand_cap) cand[slot] = ((uint32_t)v << 24) | (uint32_t)(y * L.w + x);
-        }
+        if (keep) list[atomicAdd(&s_n, 1)] = ((uint32_t)v << 24) | (uint32_t)(y * L.w + x);
+    }
+    __syncthreads();
+    const int n = s_n;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(b.cand_count + f * kMaxLevels + l, n);
+    __syncthreads();
+    uint32_t* cand = b.cand + (size_t)f * b.cand_stride + L.cand_off;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int slot = s_base + i;
+        if (slot < (int)L.cand_cap) cand[slot] = list[i];
     }
 }
 
@@ -525,13 +536,16 @@ __global__ void __launch_bounds__(256) k_blur(const __grid_constant__ OrbGeom g,
 // funnel-shifted words and the vertical taps as IMADs over a register column; no shared memory, 32-bit coalesced loads/stores.
 constexpr int kBlur7Rows = 16;      // output rows per thread (22 source rows incl. the +-3 halo)
 
+__device__ __noinline__ uint32_t load_word_reflect_slow(const uint8_t* row, int x, int w)
+{
+    uint32_t v = 0;
+    for (int i = 0; i < 4; i++) v |= (uint32_t)row[reflect101(x + i, w)] << (8 * i);
+    return v;
+}
 __device__ __forceinline__ uint32_t load_word_reflect(const uint8_t* row, int x, int w)
 {
     if (x >= 0 && x + 4 <= w) return *reinterpret_cast<const uint32_t*>(row + x);
-    uint32_t v = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) v |= (uint32_t)row[reflect101(x + i, w)] << (8 * i);
-    return v;
+    return load_word_reflect_slow(row, x, w);
 }
 
 __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g, const OrbBuffers b)
@@ -548,6 +562,7 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
     const uint8_t* img = level_ptr(g, b, f, l, pitch);
     const uint32_t K0 = (uint32_t)g.gk[0] | ((uint32_t)g.gk[1] << 8) | ((uint32_t)g.gk[2] << 16) | ((uint32_t)g.gk[3] << 24);
     const uint32_t K1 = (uint32_t)g.gk[4] | ((uint32_t)g.gk[5] << 8) | ((uint32_t)g.gk[6] << 16);
+    const unsigned k0 = g.gk[0], k1 = g.gk[1], k2 = g.gk[2], k3 = g.gk[3];      // symmetric kernel: k[6-i] == k[i]
     int T[kBlur7Rows + 6][4];
 #pragma unroll
     for (int i = 0; i < kBlur7Rows + 6; i++) {
@@ -569,9 +584,8 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
             uint32_t packed = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                unsigned acc = 32768u;
-#pragma unroll
-                for (int k = 0; k < 7; k++) acc += (unsigned)g.gk[k] * (unsigned)T[r + k][j];
+                const unsigned acc = 32768u + k0 * (unsigned)(T[r][j] + T[r + 6][j]) + k1 * (unsigned)(T[r + 1][j] + T[r + 5][j]) +
+                                     k2 * (unsigned)(T[r + 2][j] + T[r + 4][j]) + k3 * (unsigned)T[r + 3][j];
                 packed |= (acc >> 16) << (8 * j);
             }
             *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
@@ -602,6 +616,30 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
     return a;
 }
 
+// lanes span u = -hp..hp (hp <= 15 -> at most 31 columns); rows v are unrolled when hp is a compile-time constant
+template <int HP>
+__device__ __forceinline__ void orient_moments(const uint8_t* center, int pitch, int lane, const int* umax, int& m01, int& m10, int hp_rt = 0)
+{
+    const int hp = HP ? HP : hp_rt;
+    const int u = lane - hp, au = u < 0 ? -u : u;
+    if (lane > 2 * hp) return;
+    if (HP) {
+        int val[2 * (HP ? HP : 1) + 1];
+#pragma unroll
+        for (int i = 0; i < 2 * HP + 1; i++) {
+            const int v = i - HP, av = v < 0 ? -v : v;
+            val[i] = (au <= umax[av]) ? (int)center[v * pitch + u] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * HP + 1; i++) { m10 += u * val[i]; m01 += (i - HP) * val[i]; }
+    } else {
+        for (int v = -hp; v <= hp; v++) {
+            const int av = v < 0 ? -v : v;
+            if (au <= umax[av]) { const int x = center[v * pitch + u]; m10 += u * x; m01 += v * x; }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_orient_describe(const __grid_constant__ OrbGeom g, const OrbBuffers b,
                                                          mage_keypoint* __restrict__ out_kps, uint8_t* __restrict__ out_desc,
                                                          int* __restrict__ out_counts, int capacity)
@@ -628,20 +666,10 @@ __global__ void __launch_bounds__(256) k_orient_describe(const __grid_constant__
         int pitch;
         const uint8_t* img = level_ptr(g, b, f, l, pitch);
         const uint8_t* center = img + (size_t)y * pitch + x;
-        const int hp = g.half_patch;
         int m01 = 0, m10 = 0;
-        // lanes span u = -hp..hp (hp <= 15 -> 31 columns), loop over rows v
-        const int u = lane - hp;
-        if (lane <= 2 * hp) {
-            for (int v = -hp; v <= hp; v++) {
-                int av = v < 0 ? -v : v;
-                if ((u < 0 ? -u : u) <= g.umax[av]) {
-                    int val = center[v * pitch + u];
-                    m10 += u * val;
-                    m01 += v * val;
-                }
-            }
-        }
+        if (g.half_patch == 15) orient_moments<15>(center, pitch, lane, g.umax, m01, m10);
+        else if (g.half_patch == 7) orient_moments<7>(center, pitch, lane, g.umax, m01, m10);
+        else orient_moments<0>(center, pitch, lane, g.umax, m01, m10, g.half_patch);
         m01 = warp_reduce_sum(m01);
         m10 = warp_reduce_sum(m10);
         angle = fast_atan2_deg((float)m01, (float)m10);
