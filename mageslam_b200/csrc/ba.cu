@@ -10,6 +10,8 @@
 // (no floating-point atomics), so a run is bit-reproducible.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -41,6 +43,9 @@ struct BaDev {
     double *err, *W, *WD, *Hll, *bl, *Dinv, *db, *Hpp, *bp, *S, *bs, *x, *cam_bak, *pt_bak, *part;
     unsigned char* flags;                     // [Ea] 1 = outlier
     BaCtl* ctl;
+    // cooperative (multi-CTA) variant: per-(block, part) partial sums of the Schur products and the grid reduction slots
+    double *spart, *gred;
+    int schur_parts;
 };
 
 // ------------------------------------------------------------------------------------------------ small math
@@ -703,6 +708,318 @@ __global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------ cooperative variant
+// Same algorithm, ONE problem spread over a cooperative grid (latency path of a single StepBundleAdjustment call): phases are
+// partitioned over all threads of the grid and separated by grid-wide barriers; reductions go through fixed-order per-block
+// partials (bit-reproducible for a given grid size); the camera state is replicated in every block's shared memory and updated
+// redundantly, so no broadcast is needed; block 0 assembles and factorises the reduced system in its shared memory.
+namespace cg = cooperative_groups;
+constexpr int kCoopThreads = 256;
+constexpr int kCoopMaxBlocks = 64;
+constexpr int kCoopRedVals = 2;
+
+template <int NV>
+__device__ void grid_sum(cg::grid_group& grid, double (&v)[NV], const BaDev& p, int& seq, double* sh, double* sh_out)
+{
+    double* slot = p.gred + (size_t)(seq & 1) * kCoopRedVals * kCoopMaxBlocks;
+    seq++;
+#pragma unroll
+    for (int j = 0; j < NV; j++) {
+        const double s = block_sum(v[j], sh);
+        if (threadIdx.x == 0) slot[j * kCoopMaxBlocks + blockIdx.x] = s;
+    }
+    grid.sync();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            double t = 0;
+            for (unsigned bI = 0; bI < gridDim.x; bI++) t += slot[j * kCoopMaxBlocks + bI];
+            sh_out[j] = t;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < NV; j++) v[j] = sh_out[j];
+    __syncthreads();
+}
+
+// per-(block, part) partial products  sum_pairs WD_e1 W_e2^T  (one warp per item)
+__device__ void phase_schur_products_parts(const BaDev& p, int warp, int nwarps, int lane)
+{
+    const int items = p.nblk * p.schur_parts;
+    for (int it = warp; it < items; it += nwarps) {
+        const int bi = it / p.schur_parts, part = it % p.schur_parts;
+        const int beg = p.blk_ptr[bi], end = p.blk_ptr[bi + 1], per = (end - beg + p.schur_parts - 1) / p.schur_parts;
+        const int s0 = beg + part * per, s1 = min(s0 + per, end);
+        double acc[36];
+#pragma unroll
+        for (int i = 0; i < 36; i++) acc[i] = 0;
+        for (int k = s0 + lane; k < s1; k += 32) {
+            const int2 pr = p.pairs[k];
+            const double* __restrict__ A = p.WD + 18 * (size_t)pr.x;
+            const double* __restrict__ B = p.W + 18 * (size_t)pr.y;
+            double a[18], b[18];
+#pragma unroll
+            for (int i = 0; i < 18; i++) { a[i] = A[i]; b[i] = B[i]; }
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[r * 6 + c] += a[r * 3] * b[c * 3] + a[r * 3 + 1] * b[c * 3 + 1] + a[r * 3 + 2] * b[c * 3 + 2];
+        }
+#pragma unroll
+        for (int i = 0; i < 36; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
+        if (lane == 0) {
+            double* dst = p.spart + (size_t)it * 36;
+#pragma unroll
+            for (int i = 0; i < 36; i++) dst[i] = acc[i];
+        }
+    }
+}
+// per-(camera, part) partials of coeff_i = sum_e W_e db (same slots as the single-CTA kernel)
+__device__ void phase_coeff_parts(const BaDev& p, int warp, int nwarps, int lane)
+{
+    const int items = p.Kf * p.cam_parts;
+    for (int it = warp; it < items; it += nwarps) {
+        const int kf = it / p.cam_parts, part = it % p.cam_parts;
+        const int beg = p.c_ptr[kf], end = p.c_ptr[kf + 1], len = end - beg;
+        const int per = (len + p.cam_parts - 1) / p.cam_parts;
+        const int s0 = beg + part * per, s1 = min(s0 + per, end);
+        double c6[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = s0 + lane; k < s1; k += 32) {
+            const int e = p.c_edges[k];
+            const int li = p.e_l[e];
+            if (li < 0) continue;
+            const double* W = p.W + 18 * (size_t)e;
+            const double d0 = p.db[3 * li], d1 = p.db[3 * li + 1], d2 = p.db[3 * li + 2];
+#pragma unroll
+            for (int r = 0; r < 6; r++) c6[r] += W[r * 3] * d0 + W[r * 3 + 1] * d1 + W[r * 3 + 2] * d2;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c6[i] += __shfl_down_sync(0xffffffffu, c6[i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) p.part[(size_t)it * 27 + i] = c6[i];
+        }
+    }
+}
+// block 0: S = Hpp (+lambda) - sum of partial products, mirrored, in shared memory; bs = bp - coeff
+__device__ void phase_assemble_reduced(const BaDev& p, double lambda)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, n = p.n;
+    for (int i = tid; i < n * n; i += nt) p.S[i] = 0.0;
+    __syncthreads();
+    for (int item = tid; item < p.nblk * 36; item += nt) {
+        const int bi = item / 36, rc = item % 36, r = rc / 6, c = rc % 6;
+        const int i1 = p.blk_ij[2 * bi], i2 = p.blk_ij[2 * bi + 1];
+        double acc = 0;
+        for (int part = 0; part < p.schur_parts; part++) acc += p.spart[((size_t)bi * p.schur_parts + part) * 36 + rc];
+        double v = -acc;
+        if (i1 == i2) v += p.Hpp[36 * (size_t)i1 + rc] + ((r == c) ? lambda : 0.0);
+        p.S[(size_t)(6 * i1 + r) * n + 6 * i2 + c] = v;
+        if (i1 != i2) p.S[(size_t)(6 * i2 + c) * n + 6 * i1 + r] = v;
+    }
+    phase_finish_bs(p, tid, nt);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __restrict__ prob, const float* __restrict__ huberW, int nIters, float maxErrSq,
+                                                                unsigned dynBytes)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ double sh[33];
+    __shared__ double sh_out[4];
+    __shared__ double s_lambda, s_ni, s_rho;
+    __shared__ int s_accept, s_stop;
+    __shared__ BaDev s_p;
+    __shared__ double *g_cam_q, *g_cam_t;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt, gwarp = gtid >> 5, gnw = gnt >> 5;
+    if (tid == 0) {
+        s_p = prob[0];
+        s_p.S = reinterpret_cast<double*>(dyn); s_p.bs = s_p.S + (size_t)s_p.n * s_p.n;        // used by block 0 only
+        double* c = reinterpret_cast<double*>(dyn + ba_smem_need_S(s_p.n));
+        g_cam_q = s_p.cam_q; g_cam_t = s_p.cam_t;
+        const double *gf = s_p.cam_f, *gx = s_p.cam_cx, *gy = s_p.cam_cy; const int* gh = s_p.cam_h;
+        double* sq = c; double* st = c + 4 * s_p.K; double* sf = c + 7 * s_p.K; double* sx = c + 8 * s_p.K; double* sy = c + 9 * s_p.K;
+        int* shh = reinterpret_cast<int*>(c + 10 * s_p.K);
+        for (int k = 0; k < s_p.K; k++) {
+            for (int j = 0; j < 4; j++) sq[4 * k + j] = g_cam_q[4 * k + j];
+            for (int j = 0; j < 3; j++) st[3 * k + j] = g_cam_t[3 * k + j];
+            sf[k] = gf[k]; sx[k] = gx[k]; sy[k] = gy[k]; shh[k] = gh[k];
+        }
+        s_p.cam_q = sq; s_p.cam_t = st; s_p.cam_f = sf; s_p.cam_cx = sx; s_p.cam_cy = sy; s_p.cam_h = shh;
+    }
+    __syncthreads();
+    const BaDev& p = s_p;
+    BaCtl* ctl = p.ctl;
+    if (tid == 0) { s_lambda = ctl->lambda; s_ni = ctl->ni; s_stop = 0; }
+    __syncthreads();
+    int iteration = ctl->iteration, seq = 0;
+    long long trials = 0, iters = 0;
+    (void)dynBytes;
+
+    // errors of this thread's edges + robust chi2 partial
+    auto errors_chi2 = [&](double delta) {
+        double acc = 0;
+        for (int e = gtid; e < p.Ea; e += gnt) {
+            const int c = p.e_cam[e];
+            double xt[3];
+            q_rot(p.cam_q + 4 * c, p.pt_X + 3 * (size_t)p.e_pt[e], xt);
+            xt[0] += p.cam_t[3 * c]; xt[1] += p.cam_t[3 * c + 1]; xt[2] += p.cam_t[3 * c + 2];
+            const double f = p.cam_f[c];
+            const double e0 = p.e_uv[2 * e] - (xt[0] / xt[2] * f + p.cam_cx[c]), e1 = p.e_uv[2 * e + 1] - (xt[1] / xt[2] * f + p.cam_cy[c]);
+            p.err[2 * e] = e0; p.err[2 * e + 1] = e1;
+            double r0, r1;
+            huber(p.e_info[e] * (e0 * e0 + e1 * e1), delta, r0, r1);
+            acc += r0;
+        }
+        return acc;
+    };
+
+    for (int it = 0; it < nIters; it++) {
+        if (s_stop) break;
+        const double delta = (double)huberW[it];
+        double red[2];
+        red[0] = errors_chi2(delta); red[1] = 0;
+        grid_sum<1>(grid, reinterpret_cast<double(&)[1]>(red[0]), p, seq, sh, sh_out);
+        double currentChi = red[0];
+        phase_build_points(p, delta, gtid, gnt);
+        phase_build_cams(p, delta, gwarp, gnw, lane);
+        grid.sync();
+        phase_finish_cams(p, gtid, gnt);
+        if (iteration == 0) {
+            grid.sync();
+            double m = 0;
+            for (int i = gtid; i < p.Kf * 6; i += gnt) m = fmax(m, fabs(p.Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]));
+            for (int i = gtid; i < p.Pl * 3; i += gnt) m = fmax(m, fabs(p.Hll[9 * (size_t)(i / 3) + (i % 3) * 4]));
+            const double bm = block_max(m, sh);
+            double* slot = p.gred + (size_t)(seq & 1) * kCoopRedVals * kCoopMaxBlocks; seq++;
+            if (tid == 0) slot[blockIdx.x] = bm;
+            grid.sync();
+            if (tid == 0) {
+                double md = 0;
+                for (unsigned bI = 0; bI < gridDim.x; bI++) md = fmax(md, slot[bI]);
+                s_lambda = ctl->user_lambda_init > 0 ? ctl->user_lambda_init : 1e-5 * md; s_ni = 2;
+            }
+            __syncthreads();
+        }
+        double rho = 0;
+        int qmax = 0;
+        bool lambdaFinite = true;
+        do {
+            const double lambda = s_lambda;
+            // push: points partitioned over the grid, cameras per block (replicated state)
+            for (int i = tid; i < p.Kf; i += nt) {
+                const int c = p.c_cam[i];
+                for (int j = 0; j < 4; j++) p.cam_bak[7 * i + j] = p.cam_q[4 * c + j];      // every block writes the same values
+                for (int j = 0; j < 3; j++) p.cam_bak[7 * i + 4 + j] = p.cam_t[3 * c + j];
+            }
+            for (int i = gtid; i < p.Pl * 3; i += gnt) p.pt_bak[i] = p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3];
+            phase_schur_points(p, lambda, gtid, gnt);          // also zeroes p.S (block-local shared memory)
+            grid.sync();
+            phase_schur_products_parts(p, gwarp, gnw, lane);
+            phase_coeff_parts(p, gwarp, gnw, lane);
+            grid.sync();
+            if (blockIdx.x == 0) {
+                phase_assemble_reduced(p, lambda);
+                const bool ok = phase_ldlt_solve(p, sh);
+                if (tid == 0) ctl->last_ok = ok ? 1 : 0;
+            }
+            grid.sync();
+            const bool ok2 = *reinterpret_cast<volatile int*>(&ctl->last_ok) != 0;
+            if (ok2) phase_backsub(p, gtid, gnt);
+            __syncthreads();
+            // update: a landmark's increment was written by the same thread that applies it; cameras are replicated
+            for (int li = gtid; li < p.Pl; li += gnt)
+                for (int r = 0; r < 3; r++) p.pt_X[3 * (size_t)p.l_pt[li] + r] += p.x[p.n + 3 * li + r];
+            for (int i = tid; i < p.Kf; i += nt) { const int c = p.c_cam[i]; pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i); }
+            grid.sync();
+            red[0] = errors_chi2(delta);
+            red[1] = 0;
+            {
+                const int tot = p.n + 3 * p.Pl;
+                for (int j = gtid; j < tot; j += gnt) {
+                    const double xj = p.x[j], bj = (j < p.n) ? p.bp[j] : p.bl[j - p.n];
+                    red[1] += xj * (lambda * xj + bj);
+                }
+            }
+            grid_sum<2>(grid, red, p, seq, sh, sh_out);
+            double tempChi = red[0];
+            if (!ok2) tempChi = DBL_MAX;
+            const double scale = red[1] + 1e-3;
+            if (tid == 0) {
+                double r = (currentChi - tempChi) / scale;
+                s_rho = r;
+                if (r > 0 && isfinite(tempChi)) {
+                    double alpha = 1. - pow((2 * r - 1), 3.0);
+                    alpha = fmin(alpha, 2. / 3.);
+                    s_lambda = lambda * fmax(1. / 3., alpha);
+                    s_ni = 2;
+                    s_accept = 1;
+                } else {
+                    s_lambda = lambda * s_ni;
+                    s_ni = s_ni * 2;
+                    s_accept = 0;
+                }
+            }
+            __syncthreads();
+            rho = s_rho;
+            if (s_accept) currentChi = tempChi;
+            else {
+                for (int i = tid; i < p.Kf; i += nt) {
+                    const int c = p.c_cam[i];
+                    for (int j = 0; j < 4; j++) p.cam_q[4 * c + j] = p.cam_bak[7 * i + j];
+                    for (int j = 0; j < 3; j++) p.cam_t[3 * c + j] = p.cam_bak[7 * i + 4 + j];
+                }
+                for (int i = gtid; i < p.Pl * 3; i += gnt) p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3] = p.pt_bak[i];
+                grid.sync();
+                if (!isfinite(s_lambda)) { lambdaFinite = false; trials++; break; }
+            }
+            qmax++;
+            trials++;
+        } while (rho < 0 && qmax < 10);
+        iteration++;
+        iters++;
+        if (qmax == 10 || rho == 0 || !lambdaFinite) { if (tid == 0) s_stop = 1; }
+        __syncthreads();
+    }
+    // outlier classification (ref BundlerLib.cpp:385-427), partitioned over the grid
+    {
+        double red[2] = {0, 0};
+        for (int e = gtid; e < p.Ea; e += gnt) {
+            const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1];
+            const double ss = e0 * e0 + e1 * e1;
+            const int c = p.e_cam[e];
+            const double qc[4] = {-p.cam_q[4 * c], -p.cam_q[4 * c + 1], -p.cam_q[4 * c + 2], p.cam_q[4 * c + 3]};
+            const double nt3[3] = {-p.cam_t[3 * c], -p.cam_t[3 * c + 1], -p.cam_t[3 * c + 2]};
+            double wt[3], fw[3];
+            const double z[3] = {0, 0, 1};
+            q_rot(qc, nt3, wt);
+            q_rot(qc, z, fw);
+            const double* X = p.pt_X + 3 * (size_t)p.e_pt[e];
+            const double dot = (X[0] - wt[0]) * fw[0] + (X[1] - wt[1]) * fw[1] + (X[2] - wt[2]) * fw[2];
+            const bool out = (dot <= 0) || (ss > (double)maxErrSq);
+            p.flags[e] = out ? 1 : 0;
+            if (!out) { red[0] += ss; red[1] += 1.0; }
+        }
+        grid_sum<2>(grid, red, p, seq, sh, sh_out);
+        if (blockIdx.x == 0) {
+            for (int i = tid; i < 4 * p.K; i += nt) g_cam_q[i] = p.cam_q[i];
+            for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
+            if (tid == 0) {
+                ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
+                ctl->err_sum = red[0]; ctl->inlier_count = (int)red[1]; ctl->stop_flag = s_stop;
+                ctl->lm_iters += iters; ctl->lm_trials += trials;
+            }
+        }
+    }
+}
+
 } // namespace mage
 
 // ====================================================================================================================
@@ -756,6 +1073,7 @@ struct mage_ba_s {
     BaDev* d_table = nullptr; int table_cap = 0;      // descriptor table of mage_ba_step_many (owned by the lead handle)
     cudaStream_t stream = nullptr;
     int64_t stats[4] = {0, 0, 0, 0};
+    int coop_blocks = 0;               // > 0: cooperative launch available, grid size to use
 };
 
 // dynamic shared memory for one problem: reduced system + camera state when they fit in 200 KB, else whatever subset fits
@@ -865,7 +1183,8 @@ static int ba_build_structure(mage_ba_t h)
         blk_ptr.push_back((int)pairs.size());
     }
     const int nblk = (int)blk_ij.size() / 2;
-    const int cam_parts = std::max(1, std::min(8, (kBaThreads / 32) / std::max(Kf, 1)));
+    const int cam_parts = std::max(1, std::min(16, 256 / std::max(Kf, 1)));     // (camera, part) reduction items
+    const int schur_parts = 8;
 
     DeviceArena& W = h->work;
     W.release(); W = DeviceArena();
@@ -879,6 +1198,7 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_Dinv = rD(9 * (size_t)Pl), o_db = rD(3 * (size_t)Pl), o_Hpp = rD(36 * (size_t)Kf), o_bp = rD(n), o_S = rD((size_t)n * n), o_bs = rD(n);
     size_t o_x = rD(n + 3 * (size_t)Pl), o_cbak = rD(7 * (size_t)Kf), o_pbak = rD(3 * (size_t)Pl), o_part = rD((size_t)Kf * cam_parts * 27);
     size_t o_flags = W.reserve(std::max(Ea, 1));
+    size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     MAGE_CUDA_TRY(W.commit());
     MAGE_CUDA_TRY(cudaMemsetAsync(W.base, 0, W.size, h->stream));
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
@@ -906,6 +1226,7 @@ static int ba_build_structure(mage_ba_t h)
     d.bs = W.at<double>(o_bs); d.x = W.at<double>(o_x); d.cam_bak = W.at<double>(o_cbak); d.pt_bak = W.at<double>(o_pbak); d.part = W.at<double>(o_part);
     d.flags = W.at<unsigned char>(o_flags);
     d.ctl = h->d_ctl;
+    d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
     MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
     // pageable staging vectors go out of scope on return: make sure the copies have been consumed
     MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -921,6 +1242,19 @@ extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
     h->points_fixed = are_points_fixed != 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return MAGE_ERR_CUDA; }
     if (cudaFuncSetAttribute(k_ba_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); cudaStreamDestroy(h->stream); delete h; return MAGE_ERR_CUDA; }
+    // cooperative (multi-CTA) variant for the single-problem latency path
+    {
+        int dev = 0, coop = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char* env = getenv("MAGE_BA_COOP_BLOCKS");
+        int want = env ? atoi(env) : 32;
+        if (coop && want > 0 && cudaFuncSetAttribute(k_ba_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_step_coop, kCoopThreads, 64 * 1024) == cudaSuccess && per_sm > 0)
+            h->coop_blocks = std::min(std::min(want, kCoopMaxBlocks), sms * per_sm);
+        cudaGetLastError();
+    }
     *out = h;
     return MAGE_OK;
 }
@@ -1095,7 +1429,16 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
     int rc = ba_prepare(h, huber, n_iters);
     if (rc) return rc;
     if (!h->useless) {
-        { ProfScope ps(PROF_BA_STEP, h->stream); k_ba_step<<<1, kBaThreads, ba_dyn_smem(h->dev.n, h->dev.K), h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, (unsigned)ba_dyn_smem(h->dev.n, h->dev.K)); }
+        const size_t coop_smem = ba_smem_need_S(h->dev.n) + ba_smem_need_cams(h->dev.K);
+        const bool use_coop = h->coop_blocks > 1 && h->dev.K <= kBaMaxSmemCams && coop_smem <= 64 * 1024 && h->dev.Ea >= 1024;
+        ProfScope ps(PROF_BA_STEP, h->stream);
+        if (use_coop) {
+            const BaDev* d_dev = h->d_dev; const float* d_hub = h->d_huber; unsigned dynb = (unsigned)coop_smem;
+            void* args[] = {(void*)&d_dev, (void*)&d_hub, (void*)&n_iters, (void*)&max_err_sq, (void*)&dynb};
+            MAGE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ba_step_coop, dim3(h->coop_blocks), dim3(kCoopThreads), args, coop_smem, h->stream));
+        } else {
+            k_ba_step<<<1, kBaThreads, ba_dyn_smem(h->dev.n, h->dev.K), h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, (unsigned)ba_dyn_smem(h->dev.n, h->dev.K));
+        }
         MAGE_CUDA_TRY(cudaGetLastError());
         h->stats[2]++;
     }

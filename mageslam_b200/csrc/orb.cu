@@ -119,9 +119,9 @@ __global__ void __launch_bounds__(256) k_resize(const __grid_constant__ OrbGeom 
 // ------------------------------------------------------------------------------------------------ K2: FAST + score + NMS
 // ref OpenCVModified.cpp:1224-1512 (FAST_t<16>), :926-1071 (cornerScore<16>), :619-639 (RunByImageBorder).
 // Closed form: score = max(max_k min(d[k..k+8]), -min_k max(d[k..k+8])) - 1, corner <=> score >= thr.
-constexpr int kFastPW = 128, kFastPH = 40;      // pixel tile
-constexpr int kFastOW = 120, kFastOH = 32;      // keypoint (output) tile
-constexpr int kFastSW = 122, kFastSH = 34;      // score tile
+constexpr int kFastPW = 128, kFastPH = 72;      // pixel tile
+constexpr int kFastOW = 120, kFastOH = 64;      // keypoint (output) tile
+constexpr int kFastSW = 122, kFastSH = 66;      // score tile
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return min(min(a, b), c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     const int bd = g.border;
     // survivors are collected in shared memory (reusing the pixel tile) and appended with ONE global atomic per CTA:
     // a returning global atomic per warp iteration stalled the whole loop on L2 round trips (ncu: 41 % of samples)
-    uint32_t* list = reinterpret_cast<uint32_t*>(A);            // <= 960 survivors (strict NMS: one per 2x2 block)
+    uint32_t* list = reinterpret_cast<uint32_t*>(A);            // <= 1920 survivors (strict NMS: one per 2x2 block)
     __shared__ int s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
@@ -358,17 +358,36 @@ __global__ void __launch_bounds__(kSelThreads) k_select(const __grid_constant__ 
     __syncthreads();
     for (int i = tid; i < n; i += nt) atomicAdd(&hist[cand[i] >> 24], 1);
     __syncthreads();
-    if (tid == 0) {
-        const int minThreshold = g.fast_threshold, minNum = nKeep;
+    // suffix sums cum[i] = sum_{j >= i} hist[j] by the first 256 threads (Hillis-Steele in shared memory), then the two
+    // thresholds of RetainBestFeatures as max-reductions -- replaces two serial 256-bin walks by one thread
+    __shared__ int cum[256];
+    if (tid < 256) cum[tid] = hist[tid];
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        int v = 0;
+        if (tid < 256 && tid + o < 256) v = cum[tid + o];
+        __syncthreads();
+        if (tid < 256) cum[tid] += v;
+        __syncthreads();
+    }
+    if (tid == 0) { s_vals[10] = -1; s_vals[11] = -1; s_vals[12] = 256; }
+    __syncthreads();
+    const int minThreshold = g.fast_threshold;
+    if (tid < 256 && tid >= minThreshold && cum[tid] >= nKeep) atomicMax(&s_vals[10], tid);       // first loop of ref :592-600
+    __syncthreads();
+    {
+        const int minNumThreshold = s_vals[10] >= 0 ? s_vals[10] : minThreshold;
         const int maxNum = (int)__fmul_rn((float)nKeep, g.feature_factor);
-        int minNumThreshold = minThreshold, num = 0;
-        for (int i = 255; i >= minThreshold; i--) { num += hist[i]; if (num >= minNum) { minNumThreshold = i; break; } }
-        int lo = max((int)__fmul_rn((float)minNumThreshold, g.feature_strength), minThreshold);
-        int stop = lo; num = 0;
-        for (int i = 255; i >= lo; i--) { num += hist[i]; if (num >= maxNum) { stop = i; break; } }
-        int minScore = stop; while (minScore < 255 && hist[minScore] == 0) minScore++;
-        s_vals[0] = num; s_vals[1] = stop; s_vals[6] = minScore;
-        s_vals[2] = INT_MAX; s_vals[3] = INT_MIN; s_vals[4] = INT_MAX; s_vals[5] = INT_MIN; s_vals[9] = 0;
+        const int lo = max((int)__fmul_rn((float)minNumThreshold, g.feature_strength), minThreshold);
+        if (tid < 256 && tid >= lo && cum[tid] >= maxNum) atomicMax(&s_vals[11], tid);                // second loop of ref :605-613
+        __syncthreads();
+        const int stop_ = s_vals[11] >= 0 ? s_vals[11] : lo;
+        if (tid < 256 && tid >= stop_ && hist[tid] > 0) atomicMin(&s_vals[12], tid);
+        __syncthreads();
+        if (tid == 0) {
+            s_vals[0] = stop_ < 256 ? cum[stop_] : 0; s_vals[1] = stop_; s_vals[6] = min(s_vals[12], 255);
+            s_vals[2] = INT_MAX; s_vals[3] = INT_MIN; s_vals[4] = INT_MAX; s_vals[5] = INT_MIN; s_vals[9] = 0;
+        }
     }
     __syncthreads();
     const int K = s_vals[0], stop = s_vals[1];
