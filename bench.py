@@ -320,7 +320,15 @@ def run_ours(args):
     peak, peak_src = peaks()
     dom_ms = kern[dom][0]
     achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:        # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at the same batch size, from the committed ncu capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("frames_per_launch") == B and dom in tj["kernels"]:
+            traffic = tj["kernels"][dom]
+    except Exception:
+        traffic = None
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launch_ms": dom_ms, "share_of_step": dom_ms / step_kernel_ms,
                 "algorithmic_bytes_per_launch": alg[dom] * B,
                 "kernels": {k: {"ms": round(v[0], 5), "share": round(v[0] / step_kernel_ms, 4),

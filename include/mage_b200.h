@@ -205,6 +205,8 @@ int  mage_ba_get_points_bulk(mage_ba_t h, float* xyz /*n*3*/);
 int  mage_ba_get_state_f64(mage_ba_t h, double* cam_qxyzw_t /*K*7*/, double* points /*P*3*/);
 /* counters: [0]=LM iterations run, [1]=lambda trials, [2]=kernel launches, [3]=structure rebuilds */
 int  mage_ba_get_stats(mage_ba_t h, int64_t stats[4]);
+/* diagnostics: accumulated nanoseconds per phase of the cooperative kernel as seen by block 0 */
+int  mage_ba_debug_phase_ns(mage_ba_t h, long long phase_ns[16]);
 /* Many independent problems stepped concurrently (one CTA group per problem): same result per handle as calling
  * mage_ba_step on each. means/outlier outputs are per handle. */
 int  mage_ba_step_many(mage_ba_t* handles, int n_handles, const float* huber_width_per_iteration, int n_iterations,

@@ -25,6 +25,7 @@ struct BaCtl {
     double lambda, ni, user_lambda_init, err_sum;
     int iteration, inlier_count, stop_flag, last_ok;
     long long lm_iters, lm_trials;
+    long long phase_ns[16];     // cooperative kernel: time per phase seen by block 0 (diagnostics)
 };
 
 struct BaDev {
@@ -444,27 +445,22 @@ __device__ bool phase_ldlt_solve(const BaDev& p, double* sh)
     __shared__ int s_neg;
     if (tid == 0) s_neg = 0;
     __syncthreads();
+    const int tx = tid & 15, ty = tid >> 4, nty = nt >> 4;
     for (int k = 0; k < n; k++) {
         const double d = S[(size_t)k * n + k];
         if (d < 0) { if (tid == 0) s_neg = 1; }
         const bool valid = fabs(d) > 0;
-        // column k of L below the diagonal is S[i][k] / d; the update uses the unscaled a_ik = l_ik * d
-        const int rs = n - k - 1;
-        const int tri = rs * (rs + 1) / 2;
+        const double inv_d = valid ? 1.0 / d : 0.0;
+        // trailing update with the unscaled column: S_ij -= a_ik * a_jk / d  (lower triangle, k < j <= i)
         __syncthreads();
         if (valid) {
-            for (int t = tid; t < tri; t += nt) {
-                // map t -> (i, j) with k < j <= i < n  (row-major over the lower triangle)
-                int r = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-                while ((r + 1) * (r + 2) / 2 <= t) r++;
-                while (r * (r + 1) / 2 > t) r--;
-                const int c = t - r * (r + 1) / 2;
-                const int i = k + 1 + r, j = k + 1 + c;
-                S[(size_t)i * n + j] -= S[(size_t)i * n + k] * (S[(size_t)j * n + k] / d);
+            for (int i = k + 1 + ty; i < n; i += nty) {
+                const double aik = S[(size_t)i * n + k] * inv_d;
+                for (int j = k + 1 + tx; j <= i; j += 16) S[(size_t)i * n + j] -= aik * S[(size_t)j * n + k];
             }
         }
         __syncthreads();
-        if (valid) for (int i = k + 1 + tid; i < n; i += nt) S[(size_t)i * n + k] /= d;
+        if (valid) for (int i = k + 1 + tid; i < n; i += nt) S[(size_t)i * n + k] *= inv_d;
     }
     __syncthreads();
     if (s_neg) return false;
@@ -714,9 +710,12 @@ __global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restri
 // partials (bit-reproducible for a given grid size); the camera state is replicated in every block's shared memory and updated
 // redundantly, so no broadcast is needed; block 0 assembles and factorises the reduced system in its shared memory.
 namespace cg = cooperative_groups;
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PH(i) do { if (blockIdx.x == 0 && tid == 0) { long long _n = gtimer(); ctl->phase_ns[i] += _n - t_last; t_last = _n; } } while (0)
 constexpr int kCoopThreads = 256;
-constexpr int kCoopMaxBlocks = 64;
+constexpr int kCoopMaxBlocks = 148;
 constexpr int kCoopRedVals = 2;
+constexpr int kSchurParts = 8;              // partial-product slices per reduced-system block (compile time: unrolled sums)
 
 template <int NV>
 __device__ void grid_sum(cg::grid_group& grid, double (&v)[NV], const BaDev& p, int& seq, double* sh, double* sh_out)
@@ -751,30 +750,43 @@ __device__ void phase_schur_products_parts(const BaDev& p, int warp, int nwarps,
         const int bi = it / p.schur_parts, part = it % p.schur_parts;
         const int beg = p.blk_ptr[bi], end = p.blk_ptr[bi + 1], per = (end - beg + p.schur_parts - 1) / p.schur_parts;
         const int s0 = beg + part * per, s1 = min(s0 + per, end);
-        double acc[36];
+        // lane l owns element (r, c) = (l / 6, l % 6) of the block; lanes 0..3 also own elements 32..35
+        const int r0 = lane / 6, c0 = lane % 6, r1 = (32 + lane) / 6, c1 = (32 + lane) % 6;
+        double acc0 = 0, acc1 = 0;
+        const int2* __restrict__ pairs = p.pairs;
+        const double* __restrict__ WDp = p.WD;
+        const double* __restrict__ Wp = p.W;
+        int k = s0;
+        for (; k + 4 <= s1; k += 4) {          // 4 pairs per trip: indices, then 24 operand loads in flight, then the math
+            int2 pr[4];
 #pragma unroll
-        for (int i = 0; i < 36; i++) acc[i] = 0;
-        for (int k = s0 + lane; k < s1; k += 32) {
-            const int2 pr = p.pairs[k];
-            const double* __restrict__ A = p.WD + 18 * (size_t)pr.x;
-            const double* __restrict__ B = p.W + 18 * (size_t)pr.y;
-            double a[18], b[18];
+            for (int u = 0; u < 4; u++) pr[u] = pairs[k + u];
+            double a[4][3], b[4][3], a1[4][3], b1[4][3];
 #pragma unroll
-            for (int i = 0; i < 18; i++) { a[i] = A[i]; b[i] = B[i]; }
+            for (int u = 0; u < 4; u++) {
+                const double* A = WDp + 18 * (size_t)pr[u].x; const double* B = Wp + 18 * (size_t)pr[u].y;
 #pragma unroll
-            for (int r = 0; r < 6; r++)
+                for (int j = 0; j < 3; j++) { a[u][j] = A[r0 * 3 + j]; b[u][j] = B[c0 * 3 + j]; }
+                if (lane < 4) {
 #pragma unroll
-                for (int c = 0; c < 6; c++) acc[r * 6 + c] += a[r * 3] * b[c * 3] + a[r * 3 + 1] * b[c * 3 + 1] + a[r * 3 + 2] * b[c * 3 + 2];
+                    for (int j = 0; j < 3; j++) { a1[u][j] = A[r1 * 3 + j]; b1[u][j] = B[c1 * 3 + j]; }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                acc0 += a[u][0] * b[u][0] + a[u][1] * b[u][1] + a[u][2] * b[u][2];
+                if (lane < 4) acc1 += a1[u][0] * b1[u][0] + a1[u][1] * b1[u][1] + a1[u][2] * b1[u][2];
+            }
         }
-#pragma unroll
-        for (int i = 0; i < 36; i++)
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
-        if (lane == 0) {
-            double* dst = p.spart + (size_t)it * 36;
-#pragma unroll
-            for (int i = 0; i < 36; i++) dst[i] = acc[i];
+        for (; k < s1; k++) {
+            const int2 pr = pairs[k];
+            const double* A = WDp + 18 * (size_t)pr.x; const double* B = Wp + 18 * (size_t)pr.y;
+            acc0 += A[r0 * 3] * B[c0 * 3] + A[r0 * 3 + 1] * B[c0 * 3 + 1] + A[r0 * 3 + 2] * B[c0 * 3 + 2];
+            if (lane < 4) acc1 += A[r1 * 3] * B[c1 * 3] + A[r1 * 3 + 1] * B[c1 * 3 + 1] + A[r1 * 3 + 2] * B[c1 * 3 + 2];
         }
+        double* dst = p.spart + (size_t)it * 36;
+        dst[lane] = acc0;
+        if (lane < 4) dst[32 + lane] = acc1;
     }
 }
 // per-(camera, part) partials of coeff_i = sum_e W_e db (same slots as the single-CTA kernel)
@@ -816,7 +828,9 @@ __device__ void phase_assemble_reduced(const BaDev& p, double lambda)
         const int bi = item / 36, rc = item % 36, r = rc / 6, c = rc % 6;
         const int i1 = p.blk_ij[2 * bi], i2 = p.blk_ij[2 * bi + 1];
         double acc = 0;
-        for (int part = 0; part < p.schur_parts; part++) acc += p.spart[((size_t)bi * p.schur_parts + part) * 36 + rc];
+        const double* __restrict__ sp = p.spart + (size_t)bi * kSchurParts * 36 + rc;
+#pragma unroll
+        for (int part = 0; part < kSchurParts; part++) acc += sp[part * 36];
         double v = -acc;
         if (i1 == i2) v += p.Hpp[36 * (size_t)i1 + rc] + ((r == c) ? lambda : 0.0);
         p.S[(size_t)(6 * i1 + r) * n + 6 * i2 + c] = v;
@@ -862,6 +876,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
     int iteration = ctl->iteration, seq = 0;
     long long trials = 0, iters = 0;
     (void)dynBytes;
+    long long t_last = gtimer();
 
     // errors of this thread's edges + robust chi2 partial
     auto errors_chi2 = [&](double delta) {
@@ -888,9 +903,11 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
         red[0] = errors_chi2(delta); red[1] = 0;
         grid_sum<1>(grid, reinterpret_cast<double(&)[1]>(red[0]), p, seq, sh, sh_out);
         double currentChi = red[0];
+        PH(0);
         phase_build_points(p, delta, gtid, gnt);
         phase_build_cams(p, delta, gwarp, gnw, lane);
         grid.sync();
+        PH(1);
         phase_finish_cams(p, gtid, gnt);
         if (iteration == 0) {
             grid.sync();
@@ -922,15 +939,20 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
             for (int i = gtid; i < p.Pl * 3; i += gnt) p.pt_bak[i] = p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3];
             phase_schur_points(p, lambda, gtid, gnt);          // also zeroes p.S (block-local shared memory)
             grid.sync();
+            PH(2);
             phase_schur_products_parts(p, gwarp, gnw, lane);
             phase_coeff_parts(p, gwarp, gnw, lane);
             grid.sync();
+            PH(3);
             if (blockIdx.x == 0) {
                 phase_assemble_reduced(p, lambda);
+                PH(8);
                 const bool ok = phase_ldlt_solve(p, sh);
                 if (tid == 0) ctl->last_ok = ok ? 1 : 0;
             }
+            PH(4);
             grid.sync();
+            PH(5);
             const bool ok2 = *reinterpret_cast<volatile int*>(&ctl->last_ok) != 0;
             if (ok2) phase_backsub(p, gtid, gnt);
             __syncthreads();
@@ -939,6 +961,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
                 for (int r = 0; r < 3; r++) p.pt_X[3 * (size_t)p.l_pt[li] + r] += p.x[p.n + 3 * li + r];
             for (int i = tid; i < p.Kf; i += nt) { const int c = p.c_cam[i]; pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i); }
             grid.sync();
+            PH(6);
             red[0] = errors_chi2(delta);
             red[1] = 0;
             {
@@ -949,6 +972,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
                 }
             }
             grid_sum<2>(grid, red, p, seq, sh, sh_out);
+            PH(7);
             double tempChi = red[0];
             if (!ok2) tempChi = DBL_MAX;
             const double scale = red[1] + 1e-3;
@@ -1073,6 +1097,8 @@ struct mage_ba_s {
     BaDev* d_table = nullptr; int table_cap = 0;      // descriptor table of mage_ba_step_many (owned by the lead handle)
     cudaStream_t stream = nullptr;
     int64_t stats[4] = {0, 0, 0, 0};
+    BaCtl h_ctl{};                      // host copies of the last call's control block / outlier flags
+    std::vector<unsigned char> h_flags;
     int coop_blocks = 0;               // > 0: cooperative launch available, grid size to use
 };
 
@@ -1184,7 +1210,7 @@ static int ba_build_structure(mage_ba_t h)
     }
     const int nblk = (int)blk_ij.size() / 2;
     const int cam_parts = std::max(1, std::min(16, 256 / std::max(Kf, 1)));     // (camera, part) reduction items
-    const int schur_parts = 8;
+    const int schur_parts = kSchurParts;
 
     DeviceArena& W = h->work;
     W.release(); W = DeviceArena();
@@ -1394,15 +1420,27 @@ static int ba_prepare(mage_ba_t h, const float* huber, int n_iters)
     return MAGE_OK;
 }
 
-static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, float* mean)
+// read-back of one call: enqueue (async on stream s) ...
+static int ba_finish_enqueue(mage_ba_t h, cudaStream_t s)
+{
+    if (h->useless) return MAGE_OK;
+    h->h_flags.resize(std::max(h->dev.Ea, 1));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(&h->h_ctl, h->d_ctl, sizeof(BaCtl), cudaMemcpyDeviceToHost, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(h->h_flags.data(), h->dev.flags, h->dev.Ea, cudaMemcpyDeviceToHost, s));
+    return MAGE_OK;
+}
+// ... and complete (after the stream has been synchronised)
+static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, float* mean, bool enqueued = false)
 {
     *n_out = 0;
     if (h->useless) { *mean = std::numeric_limits<float>::quiet_NaN(); return MAGE_OK; }
-    BaCtl c;
-    std::vector<unsigned char> flags(std::max(h->dev.Ea, 1));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(flags.data(), h->dev.flags, h->dev.Ea, cudaMemcpyDeviceToHost, h->stream));
-    MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!enqueued) {
+        int rc = ba_finish_enqueue(h, h->stream);
+        if (rc) return rc;
+        MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    }
+    const BaCtl& c = h->h_ctl;
+    const std::vector<unsigned char>& flags = h->h_flags;
     h->lambda = c.lambda;
     h->stats[0] = c.lm_iters; h->stats[1] = c.lm_trials;
     h->host_state_valid = false;
@@ -1472,13 +1510,14 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
             { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step<<<(unsigned)table.size(), kBaThreads, dyn, lead->stream>>>(d_table, hs[live[0]]->d_huber, n_iters, max_err_sq, (unsigned)dyn); }
             e = cudaGetLastError();
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(lead->stream);
         MAGE_CUDA_TRY(e);
         lead->stats[2]++;
     }
+    for (int i = 0; i < n; i++) { int rc = ba_finish_enqueue(hs[i], lead->stream); if (rc) return rc; }
+    MAGE_CUDA_TRY(cudaStreamSynchronize(lead->stream));
     for (int i = 0; i < n; i++) {
         int nout = 0;
-        int rc = ba_finish(hs[i], nullptr, 0, &nout, &means[i]);
+        int rc = ba_finish(hs[i], nullptr, 0, &nout, &means[i], true);
         if (rc) return rc;
     }
     return MAGE_OK;
@@ -1543,6 +1582,15 @@ extern "C" int mage_ba_get_state_f64(mage_ba_t h, double* cams7, double* pts3)
     std::copy(h->pt_X.begin(), h->pt_X.end(), pts3);
     return MAGE_OK;
 }
+extern "C" int mage_ba_debug_phase_ns(mage_ba_t h, long long out[16])
+{
+    MAGE_REQUIRE(h && out && h->d_ctl, MAGE_ERR_INVALID, "null argument");
+    BaCtl c;
+    MAGE_CUDA_TRY(cudaMemcpy(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; i++) out[i] = c.phase_ns[i];
+    return MAGE_OK;
+}
+
 extern "C" int mage_ba_get_stats(mage_ba_t h, int64_t stats[4])
 {
     MAGE_REQUIRE(h && stats, MAGE_ERR_INVALID, "null argument");
