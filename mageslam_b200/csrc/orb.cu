@@ -254,15 +254,25 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     __shared__ int s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < kFastOH * kFastOW; i += blockDim.x) {
-        int oy = i / kFastOW, ox = i % kFastOW;
-        int x = px0 + 4 + ox, y = py0 + 4 + oy;
-        const uint8_t* s = &sc[(oy + 1) * kFastPW + ox + 1];
-        int v = s[0];
-        bool keep = v > 0 && x >= bd && x < L.w - bd && y >= bd && y < L.h - bd &&
-                    v > s[-1] && v > s[1] && v > s[-kFastPW - 1] && v > s[-kFastPW] && v > s[-kFastPW + 1] &&
-                    v > s[kFastPW - 1] && v > s[kFastPW] && v > s[kFastPW + 1];
-        if (keep) list[atomicAdd(&s_n, 1)] = ((uint32_t)v << 24) | (uint32_t)(y * L.w + x);
+    // 4 score bytes per iteration (one aligned 32-bit shared load); the vast majority of words are all zero (non-corners)
+    for (int i = threadIdx.x; i < kFastOH * (kFastPW / 4); i += blockDim.x) {
+        const int oy = i / (kFastPW / 4), wx = (i - oy * (kFastPW / 4)) * 4;       // score-tile columns wx .. wx+3 of row oy+1
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(&sc[(oy + 1) * kFastPW + wx]);
+        if (word == 0) continue;
+        const int y = py0 + 4 + oy;
+        if (y < bd || y >= L.h - bd) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int v = (word >> (8 * j)) & 0xff;
+            const int sx = wx + j;                      // score column; keypoint column ox = sx - 1
+            if (v == 0 || sx < 1 || sx > kFastOW) continue;
+            const int x = px0 + 3 + sx;
+            if (x < bd || x >= L.w - bd) continue;
+            const uint8_t* s = &sc[(oy + 1) * kFastPW + sx];
+            const bool keep = v > s[-1] && v > s[1] && v > s[-kFastPW - 1] && v > s[-kFastPW] && v > s[-kFastPW + 1] &&
+                              v > s[kFastPW - 1] && v > s[kFastPW] && v > s[kFastPW + 1];
+            if (keep) list[atomicAdd(&s_n, 1)] = ((uint32_t)v << 24) | (uint32_t)(y * L.w + x);
+        }
     }
     __syncthreads();
     const int n = s_n;
@@ -576,7 +586,7 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
     const int t = blockIdx.x - L.blur_tile_base;
     const int x = (t % L.blur_tiles_x) * 128 + (threadIdx.x & 31) * 4;
     const int y0 = (t / L.blur_tiles_x) * (8 * kBlur7Rows) + (threadIdx.x >> 5) * kBlur7Rows;
-    if (x >= L.w || y0 >= L.h) return;
+    if (x < 4 || x + 8 > L.w || y0 >= L.h) return;       // edge columns (needing REFLECT_101 in x) are done by k_blur7_edges
     int pitch;
     const uint8_t* img = level_ptr(g, b, f, l, pitch);
     const uint32_t K0 = (uint32_t)g.gk[0] | ((uint32_t)g.gk[1] << 8) | ((uint32_t)g.gk[2] << 16) | ((uint32_t)g.gk[3] << 24);
@@ -587,7 +597,8 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
     for (int i = 0; i < kBlur7Rows + 6; i++) {
         const int sy = reflect101(min(y0 + i - 3, L.h + 2), L.h);
         const uint8_t* row = img + (size_t)sy * pitch;
-        const uint32_t w0 = load_word_reflect(row, x - 4, L.w), w1 = load_word_reflect(row, x, L.w), w2 = load_word_reflect(row, x + 4, L.w);
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row + x - 4), w1 = *reinterpret_cast<const uint32_t*>(row + x),
+                       w2 = *reinterpret_cast<const uint32_t*>(row + x + 4);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const uint32_t v0 = (j == 3) ? w1 : __funnelshift_r(w0, w1, 8 * (1 + j));     // bytes x-3+j .. x+j
@@ -610,6 +621,33 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
             *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
         }
     }
+}
+
+// Edge columns of the 7x7 blur: x in [0, 4) and [xr, w) with xr = the first column not covered by an interior thread.
+// One thread per output pixel, plain 49-tap evaluation with REFLECT_101 (about 1.5 % of the pixels).
+__global__ void __launch_bounds__(256) k_blur7_edges(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    const int f = blockIdx.z, l = blockIdx.y;
+    if (l >= g.nlevels) return;
+    const LevelGeom& L = g.lv[l];
+    // interior threads cover x in [4, xr) where xr = 4 * floor((w - 8) / 4) + 4 ... i.e. the largest multiple of 4 with x + 8 <= w, plus 4
+    const int last = ((L.w - 8) / 4) * 4;                       // last interior thread column (>= 4 when w >= 12)
+    const int xr = (L.w >= 12) ? last + 4 : 0;                  // right strip starts here; whole row when the level is tiny
+    const int nleft = (L.w >= 12) ? 4 : 0, nright = L.w - xr, ncols = nleft + nright;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncols * L.h) return;
+    const int y = i / ncols, c = i - y * ncols;
+    const int x = (c < nleft) ? c : xr + (c - nleft);
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+    unsigned acc = 32768u;
+    for (int j = 0; j < 7; j++) {
+        const uint8_t* row = img + (size_t)reflect101(y + j - 3, L.h) * pitch;
+        unsigned t = 0;
+        for (int k = 0; k < 7; k++) t += (unsigned)g.gk[k] * row[reflect101(x + k - 3, L.w)];
+        acc += (unsigned)g.gk[j] * t;
+    }
+    blur_ptr(g, b, f, l)[(size_t)y * L.pitch + x] = (uint8_t)(acc >> 16);
 }
 
 // ------------------------------------------------------------------------------------------------ K4+K7: orientation + rBRIEF
@@ -969,7 +1007,11 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
             k_resize<<<grid, block, 0, s>>>(g, bufs, l);
         }
     }
-    if (g.ksize == 7) { ProfScope ps(PROF_BLUR, s); k_blur7<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs); }
+    if (g.ksize == 7) {
+        ProfScope ps(PROF_BLUR, s);
+        k_blur7<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs);
+        k_blur7_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, s>>>(g, bufs);
+    }
     else if (g.ksize > 1) { ProfScope ps(PROF_BLUR, s); k_blur<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs); }
     { ProfScope ps(PROF_FAST, s); k_fast<<<dim3(h->fast_tiles, n), 256, 0, s>>>(g, bufs); }
     { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }
