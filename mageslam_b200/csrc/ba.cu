@@ -47,6 +47,9 @@ struct BaDev {
     // cooperative (multi-CTA) variant: per-(block, part) partial sums of the Schur products and the grid reduction slots
     double *spart, *gred;
     int schur_parts;
+    // large reduced systems (global BA): S stays in global memory and is factorised by the whole grid
+    int big;
+    double* Wk;                               // [n][kLdltNB] panel workspace (L_ik * D_k)
 };
 
 // ------------------------------------------------------------------------------------------------ small math
@@ -576,7 +579,10 @@ constexpr int kBaThreads = 512;
 // Shared-memory residency: the reduced system S (n x n) + its right-hand side and the camera state (pose, intrinsics,
 // Hessian index) live in dynamic shared memory whenever they fit -- the dense LDL^T and every per-edge camera lookup then run
 // at shared-memory latency instead of L2 latency. Global memory stays the source of truth across launches.
-constexpr int kBaMaxSmemCams = 128;
+constexpr int kBaMaxSmemCams = 1024;
+constexpr int kLdltNB = 32;                 // panel width of the grid-wide blocked LDL^T
+constexpr int kLdltTile = 64;               // trailing-update tile
+constexpr size_t kBigScratchBytes = sizeof(double) * (2 * kLdltTile * (kLdltNB + 1) + kLdltNB * kLdltNB + 64);
 
 __host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) * ((size_t)n * n + n); }
 __host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
@@ -840,6 +846,166 @@ __device__ void phase_assemble_reduced(const BaDev& p, double lambda)
     __syncthreads();
 }
 
+// ---- large reduced systems ------------------------------------------------------------------------------------------
+// S = Hpp (+lambda) - partial products, written (lower part + mirror) into the global n x n matrix zeroed by phase_schur_points
+__device__ void phase_assemble_big(const BaDev& p, double lambda, int gtid, int gnt)
+{
+    const int n = p.n;
+    for (int item = gtid; item < p.nblk * 36; item += gnt) {
+        const int bi = item / 36, rc = item % 36, r = rc / 6, c = rc % 6;
+        const int i1 = p.blk_ij[2 * bi], i2 = p.blk_ij[2 * bi + 1];
+        double acc = 0;
+        const double* __restrict__ sp = p.spart + (size_t)bi * kSchurParts * 36 + rc;
+#pragma unroll
+        for (int part = 0; part < kSchurParts; part++) acc += sp[part * 36];
+        double v = -acc;
+        if (i1 == i2) v += p.Hpp[36 * (size_t)i1 + rc] + ((r == c) ? lambda : 0.0);
+        p.S[(size_t)(6 * i1 + r) * n + 6 * i2 + c] = v;
+        if (i1 != i2) p.S[(size_t)(6 * i2 + c) * n + 6 * i1 + r] = v;
+    }
+}
+
+// Grid-wide right-looking blocked LDL^T without pivoting (the damped reduced system is SPD; a negative pivot => "not positive",
+// ref linear_solver_dense.h:104-112). In place: strict lower part <- L, diagonal <- D. Three grid barriers per panel:
+//   (a) block 0 factors the nb x nb diagonal block in shared memory,
+//   (b) every thread solves one row of the panel:  Y = A_ik L_kk^-T,  L_ik = Y D_k^-1   (Y kept in Wk for the update),
+//   (c) 64 x 64 tiles of the trailing matrix:  A_ij -= Y_i L_j^T  (lower tiles only), one tile per CTA pass.
+__device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scratch, int* okflag)
+{
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x;
+    const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt;
+    double* S = p.S;
+    double* Ys = scratch;                                   // [kLdltTile][kLdltNB + 1]
+    double* Ls = Ys + kLdltTile * (kLdltNB + 1);           // [kLdltTile][kLdltNB + 1]
+    double* Dk = Ls + kLdltTile * (kLdltNB + 1);           // [kLdltNB][kLdltNB] diagonal block (L below the diagonal, D on it)
+    __shared__ int s_bad;
+    if (tid == 0) s_bad = 0;
+    for (int k0 = 0; k0 < n; k0 += kLdltNB) {
+        const int nb = min(kLdltNB, n - k0);
+        // (a)
+        if (blockIdx.x == 0) {
+            for (int i = tid; i < nb * nb; i += nt) Dk[i] = S[(size_t)(k0 + i / nb) * n + k0 + i % nb];
+            __syncthreads();
+            for (int k = 0; k < nb; k++) {
+                const double d = Dk[k * nb + k];
+                if (d < 0 && tid == 0) s_bad = 1;
+                const bool valid = fabs(d) > 0;
+                const double inv_d = valid ? 1.0 / d : 0.0;
+                __syncthreads();
+                if (valid)
+                    for (int t = tid; t < (nb - k - 1) * (nb - k - 1); t += nt) {
+                        const int i = k + 1 + t / (nb - k - 1), j = k + 1 + t % (nb - k - 1);
+                        if (j <= i) Dk[i * nb + j] -= Dk[i * nb + k] * inv_d * Dk[j * nb + k];
+                    }
+                __syncthreads();
+                if (valid) for (int i = k + 1 + tid; i < nb; i += nt) Dk[i * nb + k] *= inv_d;
+                __syncthreads();
+            }
+            for (int i = tid; i < nb * nb; i += nt) if (i % nb <= i / nb) S[(size_t)(k0 + i / nb) * n + k0 + i % nb] = Dk[i];
+            if (tid == 0 && s_bad) *okflag = 0;
+        }
+        grid.sync();
+        const int r0 = k0 + nb;                              // first row below the panel
+        if (r0 >= n) break;
+        // (b) every block keeps a copy of the factored diagonal block
+        for (int i = tid; i < nb * nb; i += nt) Dk[i] = S[(size_t)(k0 + i / nb) * n + k0 + i % nb];
+        __syncthreads();
+        for (int row = r0 + gtid; row < n; row += gnt) {
+            double y[kLdltNB];
+            double* a = S + (size_t)row * n + k0;
+#pragma unroll
+            for (int j = 0; j < kLdltNB; j++) y[j] = (j < nb) ? a[j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < kLdltNB; j++) {
+                if (j < nb) {
+                    double v = y[j];
+#pragma unroll
+                    for (int m = 0; m < kLdltNB; m++) if (m < j) v -= y[m] * Dk[j * nb + m];
+                    y[j] = v;
+                }
+            }
+            double* w = p.Wk + (size_t)row * kLdltNB;
+#pragma unroll
+            for (int j = 0; j < kLdltNB; j++) {
+                if (j < nb) {
+                    const double d = Dk[j * nb + j];
+                    w[j] = y[j];
+                    a[j] = (fabs(d) > 0) ? y[j] / d : 0.0;
+                } else w[j] = 0.0;
+            }
+        }
+        grid.sync();
+        // (c)
+        const int T = (n - r0 + kLdltTile - 1) / kLdltTile, ntiles = T * (T + 1) / 2;
+        const int ty = tid >> 4, tx = tid & 15;              // 16 x 16 threads, 4 x 4 outputs each
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+            while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
+            while (ti * (ti + 1) / 2 > tile) ti--;
+            const int tj = tile - ti * (ti + 1) / 2;
+            const int ri = r0 + ti * kLdltTile, rj = r0 + tj * kLdltTile;
+            __syncthreads();
+            for (int i = tid; i < kLdltTile * kLdltNB; i += nt) {
+                const int rr = i / kLdltNB, m = i % kLdltNB;
+                Ys[rr * (kLdltNB + 1) + m] = (ri + rr < n) ? p.Wk[(size_t)(ri + rr) * kLdltNB + m] : 0.0;
+                Ls[rr * (kLdltNB + 1) + m] = (rj + rr < n && m < nb) ? S[(size_t)(rj + rr) * n + k0 + m] : 0.0;
+            }
+            __syncthreads();
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] = 0;
+#pragma unroll 4
+            for (int m = 0; m < kLdltNB; m++) {
+                double ya[4], lb[4];
+#pragma unroll
+                for (int a = 0; a < 4; a++) { ya[a] = Ys[(ty * 4 + a) * (kLdltNB + 1) + m]; lb[a] = Ls[(tx * 4 + a) * (kLdltNB + 1) + m]; }
+#pragma unroll
+                for (int a = 0; a < 4; a++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) acc[a][b] += ya[a] * lb[b];
+            }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int i = ri + ty * 4 + a, j = rj + tx * 4 + b;
+                    if (i < n && j < n && j <= i) S[(size_t)i * n + j] -= acc[a][b];
+                }
+        }
+        grid.sync();
+    }
+    return true;
+}
+
+// block 0: L y = b (row-oriented dot products), D, L^T x = y (row k of L is column k of L^T); x -> p.x[0..n)
+__device__ void tri_solve_big(const BaDev& p, double* sh)
+{
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x;
+    const double* S = p.S;
+    double* y = p.bs;
+    for (int i = 0; i < n; i++) {
+        double acc = 0;
+        const double* row = S + (size_t)i * n;
+        for (int k = tid; k < i; k += nt) acc += row[k] * y[k];
+        const double s = block_sum(acc, sh);
+        if (tid == 0) y[i] -= s;
+        __syncthreads();
+    }
+    const double tol = 1.0 / DBL_MAX;
+    for (int i = tid; i < n; i += nt) { const double d = S[(size_t)i * n + i]; y[i] = (fabs(d) > tol) ? y[i] / d : 0.0; }
+    __syncthreads();
+    for (int k = n - 1; k >= 0; k--) {
+        const double xk = y[k];
+        const double* row = S + (size_t)k * n;
+        for (int i = tid; i < k; i += nt) y[i] -= row[i] * xk;
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += nt) p.x[i] = y[i];
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __restrict__ prob, const float* __restrict__ huberW, int nIters, float maxErrSq,
                                                                 unsigned dynBytes)
 {
@@ -855,8 +1021,9 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
     const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt, gwarp = gtid >> 5, gnw = gnt >> 5;
     if (tid == 0) {
         s_p = prob[0];
-        s_p.S = reinterpret_cast<double*>(dyn); s_p.bs = s_p.S + (size_t)s_p.n * s_p.n;        // used by block 0 only
-        double* c = reinterpret_cast<double*>(dyn + ba_smem_need_S(s_p.n));
+        size_t cam_off = kBigScratchBytes;                      // big mode: S / bs stay in global memory, the head of dyn is LDL^T scratch
+        if (!s_p.big) { s_p.S = reinterpret_cast<double*>(dyn); s_p.bs = s_p.S + (size_t)s_p.n * s_p.n; cam_off = ba_smem_need_S(s_p.n); }
+        double* c = reinterpret_cast<double*>(dyn + cam_off);
         g_cam_q = s_p.cam_q; g_cam_t = s_p.cam_t;
         const double *gf = s_p.cam_f, *gx = s_p.cam_cx, *gy = s_p.cam_cy; const int* gh = s_p.cam_h;
         double* sq = c; double* st = c + 4 * s_p.K; double* sf = c + 7 * s_p.K; double* sx = c + 8 * s_p.K; double* sy = c + 9 * s_p.K;
@@ -944,11 +1111,20 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
             phase_coeff_parts(p, gwarp, gnw, lane);
             grid.sync();
             PH(3);
-            if (blockIdx.x == 0) {
-                phase_assemble_reduced(p, lambda);
+            if (!p.big) {
+                if (blockIdx.x == 0) {
+                    phase_assemble_reduced(p, lambda);
+                    PH(8);
+                    const bool ok = phase_ldlt_solve(p, sh);
+                    if (tid == 0) ctl->last_ok = ok ? 1 : 0;
+                }
+            } else {
+                phase_assemble_big(p, lambda, gtid, gnt);
+                if (blockIdx.x == 0) { phase_finish_bs(p, tid, nt); if (tid == 0) ctl->last_ok = 1; }
+                grid.sync();
                 PH(8);
-                const bool ok = phase_ldlt_solve(p, sh);
-                if (tid == 0) ctl->last_ok = ok ? 1 : 0;
+                grid_ldlt_big(grid, p, reinterpret_cast<double*>(dyn), &ctl->last_ok);
+                if (blockIdx.x == 0 && *reinterpret_cast<volatile int*>(&ctl->last_ok)) tri_solve_big(p, sh);
             }
             PH(4);
             grid.sync();
@@ -1100,6 +1276,7 @@ struct mage_ba_s {
     BaCtl h_ctl{};                      // host copies of the last call's control block / outlier flags
     std::vector<unsigned char> h_flags;
     int coop_blocks = 0;               // > 0: cooperative launch available, grid size to use
+    int coop_blocks_max = 0;           // co-resident limit (large problems use the whole chip)
 };
 
 // dynamic shared memory for one problem: reduced system + camera state when they fit in 200 KB, else whatever subset fits
@@ -1225,6 +1402,8 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_x = rD(n + 3 * (size_t)Pl), o_cbak = rD(7 * (size_t)Kf), o_pbak = rD(3 * (size_t)Pl), o_part = rD((size_t)Kf * cam_parts * 27);
     size_t o_flags = W.reserve(std::max(Ea, 1));
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
+    const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
+    size_t o_Wk = rD(big ? (size_t)n * kLdltNB : 1);
     MAGE_CUDA_TRY(W.commit());
     MAGE_CUDA_TRY(cudaMemsetAsync(W.base, 0, W.size, h->stream));
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
@@ -1253,6 +1432,7 @@ static int ba_build_structure(mage_ba_t h)
     d.flags = W.at<unsigned char>(o_flags);
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
+    d.big = big; d.Wk = W.at<double>(o_Wk);
     MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
     // pageable staging vectors go out of scope on return: make sure the copies have been consumed
     MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1277,8 +1457,11 @@ extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
         const char* env = getenv("MAGE_BA_COOP_BLOCKS");
         int want = env ? atoi(env) : 32;
         if (coop && want > 0 && cudaFuncSetAttribute(k_ba_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_step_coop, kCoopThreads, 64 * 1024) == cudaSuccess && per_sm > 0)
-            h->coop_blocks = std::min(std::min(want, kCoopMaxBlocks), sms * per_sm);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_step_coop, kCoopThreads, 128 * 1024) == cudaSuccess && per_sm > 0)
+        {
+            h->coop_blocks_max = std::min(kCoopMaxBlocks, sms * per_sm);
+            h->coop_blocks = std::min(want, h->coop_blocks_max);
+        }
         cudaGetLastError();
     }
     *out = h;
@@ -1467,13 +1650,15 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
     int rc = ba_prepare(h, huber, n_iters);
     if (rc) return rc;
     if (!h->useless) {
-        const size_t coop_smem = ba_smem_need_S(h->dev.n) + ba_smem_need_cams(h->dev.K);
-        const bool use_coop = h->coop_blocks > 1 && h->dev.K <= kBaMaxSmemCams && coop_smem <= 64 * 1024 && h->dev.Ea >= 1024;
+        const size_t coop_smem = (h->dev.big ? kBigScratchBytes : ba_smem_need_S(h->dev.n)) + ba_smem_need_cams(h->dev.K);
+        const bool use_coop = h->coop_blocks > 1 && h->dev.K <= kBaMaxSmemCams && coop_smem <= 128 * 1024 && (h->dev.Ea >= 1024 || h->dev.big);
+        MAGE_REQUIRE(use_coop || !h->dev.big, MAGE_ERR_UNSUPPORTED, "reduced camera system of %d unknowns needs the cooperative kernel (not available)", h->dev.n);
+        const int coop_grid = h->dev.big ? h->coop_blocks_max : h->coop_blocks;
         ProfScope ps(PROF_BA_STEP, h->stream);
         if (use_coop) {
             const BaDev* d_dev = h->d_dev; const float* d_hub = h->d_huber; unsigned dynb = (unsigned)coop_smem;
             void* args[] = {(void*)&d_dev, (void*)&d_hub, (void*)&n_iters, (void*)&max_err_sq, (void*)&dynb};
-            MAGE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ba_step_coop, dim3(h->coop_blocks), dim3(kCoopThreads), args, coop_smem, h->stream));
+            MAGE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ba_step_coop, dim3(coop_grid), dim3(kCoopThreads), args, coop_smem, h->stream));
         } else {
             k_ba_step<<<1, kBaThreads, ba_dyn_smem(h->dev.n, h->dev.K), h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, (unsigned)ba_dyn_smem(h->dev.n, h->dev.K));
         }
@@ -1492,7 +1677,10 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
     for (int i = 0; i < n; i++) {
         int rc = ba_prepare(hs[i], huber, n_iters);
         if (rc) return rc;
-        if (!hs[i]->useless) { table.push_back(hs[i]->dev); live.push_back(i); }
+        if (!hs[i]->useless) {
+            MAGE_REQUIRE(!hs[i]->dev.big, MAGE_ERR_UNSUPPORTED, "problem %d has a large reduced system: step it with mage_ba_step (cooperative kernel)", i);
+            table.push_back(hs[i]->dev); live.push_back(i);
+        }
     }
     mage_ba_t lead = hs[0];
     size_t dyn = 0;

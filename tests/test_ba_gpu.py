@@ -133,3 +133,20 @@ def test_convergence_property_full_size():
     assert all(b <= a + 1e-6 for a, b in zip(means, means[1:]))
     assert 0.2 < means[-1] < 0.5
     assert rel_frobenius(gpu.points(), prob["true_points"]) < rel_frobenius(prob["points"], prob["true_points"])
+
+
+def test_global_ba_medium_large_reduced_system():
+    # global-BA shaped window (loop trajectory, banded co-visibility) whose reduced camera system (118 free cameras => 708
+    # unknowns) does not fit one CTA: exercises the grid-wide blocked LDL^T path against the reference's dense Eigen LDLT
+    prob = synth.ba_problem(K=120, P=6000, obs_per_point=8, seed=2, loop=True)
+    gpu = BundlerLib().load(prob)
+    chk = best_checker().load(prob)
+    rep = run_side_by_side(gpu, chk, [1.8], 1e9, 4, tag="global_medium")
+    assert max(max(r) for r in rep) < TOL
+
+
+def test_global_ba_with_outlier_removal_and_reinit():
+    prob = synth.ba_problem(K=60, P=2500, obs_per_point=6, seed=8, loop=True, outlier_frac=0.04)
+    gpu = BundlerLib().load(prob)
+    chk = best_checker().load(prob)
+    run_side_by_side(gpu, chk, [1.8, 1.8], 7.25, 3, tag="global_outliers")
