@@ -24,6 +24,7 @@ namespace mage {
 struct BaCtl {
     double lambda, ni, user_lambda_init, err_sum;
     int iteration, inlier_count, stop_flag, last_ok;
+    int n_flagged, pad_;
     long long lm_iters, lm_trials;
     long long phase_ns[16];     // cooperative kernel: time per phase seen by block 0 (diagnostics)
 };
@@ -548,9 +549,9 @@ __device__ double phase_scale(const BaDev& p, double lambda, double* sh)
     return block_sum(acc, sh);
 }
 // ref BundlerLib.cpp:385-427: cheirality + squared-error test per active observation, inlier error accumulation
-__device__ void phase_classify(const BaDev& p, double maxErrSq, double* sh, double& errSum, int& inliers)
+__device__ void phase_classify(const BaDev& p, double maxErrSq, double* sh, double& errSum, int& inliers, int& flagged)
 {
-    double acc = 0, cnt = 0;
+    double acc = 0, cnt = 0, nfl = 0;
     for (int e = threadIdx.x; e < p.Ea; e += blockDim.x) {
         const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1];
         const double ss = e0 * e0 + e1 * e1;
@@ -565,16 +566,17 @@ __device__ void phase_classify(const BaDev& p, double maxErrSq, double* sh, doub
         const double dot = (X[0] - wt[0]) * fw[0] + (X[1] - wt[1]) * fw[1] + (X[2] - wt[2]) * fw[2];
         const bool out = (dot <= 0) || (ss > maxErrSq);
         p.flags[e] = out ? 1 : 0;
-        if (!out) { acc += ss; cnt += 1.0; }
+        if (!out) { acc += ss; cnt += 1.0; } else nfl += 1.0;
     }
     errSum = block_sum(acc, sh);
     inliers = (int)block_sum(cnt, sh);
+    flagged = (int)block_sum(nfl, sh);
 }
 
 // ------------------------------------------------------------------------------------------------ the persistent LM kernel
 // One CTA per problem runs StepBundleAdjustment's whole loop: for each Huber width one g2o LM iteration
 // (ref optimization_algorithm_levenberg.cpp:57-149, up to 10 lambda trials), then the outlier classification.
-constexpr int kBaThreads = 512;
+constexpr int kBaThreads = 256;
 
 // Shared-memory residency: the reduced system S (n x n) + its right-hand side and the camera state (pose, intrinsics,
 // Hessian index) live in dynamic shared memory whenever they fit -- the dense LDL^T and every per-edge camera lookup then run
@@ -587,7 +589,7 @@ constexpr size_t kBigScratchBytes = sizeof(double) * (2 * kLdltTile * (kLdltNB +
 __host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) * ((size_t)n * n + n); }
 __host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
 
-__global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq,
+__global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq,
                                                             unsigned dynBytes)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
@@ -697,15 +699,15 @@ __global__ void __launch_bounds__(kBaThreads, 1) k_ba_step(const BaDev* __restri
         if (qmax == 10 || rho == 0 || !lambdaFinite) { if (tid == 0) s_stop = 1; }     // Terminate => Step() == false => break
         __syncthreads();
     }
-    double errSum; int inl;
-    phase_classify(p, (double)maxErrSq, sh, errSum, inl);
+    double errSum; int inl, nfl;
+    phase_classify(p, (double)maxErrSq, sh, errSum, inl, nfl);
     if (g_cam_q) {
         for (int i = tid; i < 4 * p.K; i += nt) g_cam_q[i] = p.cam_q[i];
         for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
     }
     if (tid == 0) {
         ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
-        ctl->err_sum = errSum; ctl->inlier_count = inl; ctl->stop_flag = s_stop;
+        ctl->err_sum = errSum; ctl->inlier_count = inl; ctl->stop_flag = s_stop; ctl->n_flagged = nfl;
         ctl->lm_iters += iters; ctl->lm_trials += trials;
     }
 }
@@ -1213,11 +1215,18 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
             for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
             if (tid == 0) {
                 ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
-                ctl->err_sum = red[0]; ctl->inlier_count = (int)red[1]; ctl->stop_flag = s_stop;
+                ctl->err_sum = red[0]; ctl->inlier_count = (int)red[1]; ctl->stop_flag = s_stop; ctl->n_flagged = p.Ea - (int)red[1];
                 ctl->lm_iters += iters; ctl->lm_trials += trials;
             }
         }
     }
+}
+
+// copies every problem's control block into one contiguous table (one D2H copy for a whole batch)
+__global__ void k_ba_gather_ctl(const BaDev* __restrict__ probs, int n, BaCtl* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = *probs[i].ctl;
 }
 
 } // namespace mage
@@ -1271,6 +1280,8 @@ struct mage_ba_s {
     BaCtl* d_ctl = nullptr;
     float* d_huber = nullptr; int huber_cap = 0;
     BaDev* d_table = nullptr; int table_cap = 0;      // descriptor table of mage_ba_step_many (owned by the lead handle)
+    BaCtl* d_ctl_table = nullptr; int ctl_cap = 0;    // gathered control blocks of a batch
+    std::vector<BaCtl> h_ctl_table;
     cudaStream_t stream = nullptr;
     int64_t stats[4] = {0, 0, 0, 0};
     BaCtl h_ctl{};                      // host copies of the last call's control block / outlier flags
@@ -1475,6 +1486,7 @@ extern "C" void mage_ba_destroy(mage_ba_t h)
     h->state.release(); h->work.release();
     if (h->d_huber) cudaFree(h->d_huber);
     if (h->d_table) cudaFree(h->d_table);
+    if (h->d_ctl_table) cudaFree(h->d_ctl_table);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1580,17 +1592,17 @@ extern "C" int mage_ba_get_lambda(mage_ba_t h, float* l)
     return MAGE_OK;
 }
 
-static int ba_prepare(mage_ba_t h, const float* huber, int n_iters)
+static int ba_prepare(mage_ba_t h, const float* huber, int n_iters, bool upload_huber = true)
 {
     if (!h->state_uploaded) { int rc = ba_upload_state(h); if (rc) return rc; }
     if (h->dirty) { int rc = ba_build_structure(h); if (rc) return rc; }
     if (h->useless) return MAGE_OK;
-    if (n_iters > h->huber_cap) {
+    if (upload_huber && n_iters > h->huber_cap) {
         if (h->d_huber) cudaFree(h->d_huber);
         h->huber_cap = std::max(16, n_iters);
         MAGE_CUDA_TRY(cudaMalloc(&h->d_huber, sizeof(float) * h->huber_cap));
     }
-    if (n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, h->stream));
+    if (upload_huber && n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, h->stream));
     if (h->iteration_reset) {
         // m_iteration = 0 (and the user lambda) take effect at the next solve()
         struct { double user; } u{h->user_lambda_init};
@@ -1603,25 +1615,26 @@ static int ba_prepare(mage_ba_t h, const float* huber, int n_iters)
     return MAGE_OK;
 }
 
-// read-back of one call: enqueue (async on stream s) ...
-static int ba_finish_enqueue(mage_ba_t h, cudaStream_t s)
+// read-back of one call: the control block first; the per-edge outlier flags only when the kernel flagged something
+static int ba_fetch_flags(mage_ba_t h, cudaStream_t s)
 {
-    if (h->useless) return MAGE_OK;
-    h->h_flags.resize(std::max(h->dev.Ea, 1));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(&h->h_ctl, h->d_ctl, sizeof(BaCtl), cudaMemcpyDeviceToHost, s));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(h->h_flags.data(), h->dev.flags, h->dev.Ea, cudaMemcpyDeviceToHost, s));
+    h->h_flags.assign(std::max(h->dev.Ea, 1), 0);
+    if (h->h_ctl.n_flagged > 0) {
+        MAGE_CUDA_TRY(cudaMemcpyAsync(h->h_flags.data(), h->dev.flags, h->dev.Ea, cudaMemcpyDeviceToHost, s));
+        MAGE_CUDA_TRY(cudaStreamSynchronize(s));
+    }
     return MAGE_OK;
 }
-// ... and complete (after the stream has been synchronised)
-static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, float* mean, bool enqueued = false)
+static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, float* mean, bool have_ctl = false, cudaStream_t s = nullptr)
 {
     *n_out = 0;
     if (h->useless) { *mean = std::numeric_limits<float>::quiet_NaN(); return MAGE_OK; }
-    if (!enqueued) {
-        int rc = ba_finish_enqueue(h, h->stream);
-        if (rc) return rc;
-        MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (!have_ctl) {
+        s = h->stream;
+        MAGE_CUDA_TRY(cudaMemcpyAsync(&h->h_ctl, h->d_ctl, sizeof(BaCtl), cudaMemcpyDeviceToHost, s));
+        MAGE_CUDA_TRY(cudaStreamSynchronize(s));
     }
+    { int rc = ba_fetch_flags(h, s); if (rc) return rc; }
     const BaCtl& c = h->h_ctl;
     const std::vector<unsigned char>& flags = h->h_flags;
     h->lambda = c.lambda;
@@ -1675,14 +1688,22 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
     std::vector<BaDev> table;
     std::vector<int> live;
     for (int i = 0; i < n; i++) {
-        int rc = ba_prepare(hs[i], huber, n_iters);
+        int rc = ba_prepare(hs[i], huber, n_iters, false);        // the Huber table is uploaded once, on the lead handle
         if (rc) return rc;
         if (!hs[i]->useless) {
             MAGE_REQUIRE(!hs[i]->dev.big, MAGE_ERR_UNSUPPORTED, "problem %d has a large reduced system: step it with mage_ba_step (cooperative kernel)", i);
             table.push_back(hs[i]->dev); live.push_back(i);
         }
     }
-    mage_ba_t lead = hs[0];
+    mage_ba_t lead = live.empty() ? hs[0] : hs[live[0]];
+    if (!live.empty()) {
+        if (n_iters > lead->huber_cap) {
+            if (lead->d_huber) cudaFree(lead->d_huber);
+            lead->huber_cap = std::max(16, n_iters);
+            MAGE_CUDA_TRY(cudaMalloc(&lead->d_huber, sizeof(float) * lead->huber_cap));
+        }
+        if (n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(lead->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, lead->stream));
+    }
     size_t dyn = 0;
     for (auto& d : table) dyn = std::max(dyn, ba_dyn_smem(d.n, d.K));
     if (!table.empty()) {
@@ -1693,19 +1714,29 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
         }
         BaDev* d_table = lead->d_table;
         cudaError_t e = cudaMemcpyAsync(d_table, table.data(), sizeof(BaDev) * table.size(), cudaMemcpyHostToDevice, lead->stream);
-        for (int i : live) if (e == cudaSuccess && hs[i] != lead) e = cudaStreamSynchronize(hs[i]->stream);
         if (e == cudaSuccess) {
-            { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step<<<(unsigned)table.size(), kBaThreads, dyn, lead->stream>>>(d_table, hs[live[0]]->d_huber, n_iters, max_err_sq, (unsigned)dyn); }
+            { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step<<<(unsigned)table.size(), kBaThreads, dyn, lead->stream>>>(d_table, lead->d_huber, n_iters, max_err_sq, (unsigned)dyn); }
             e = cudaGetLastError();
         }
         MAGE_CUDA_TRY(e);
         lead->stats[2]++;
     }
-    for (int i = 0; i < n; i++) { int rc = ba_finish_enqueue(hs[i], lead->stream); if (rc) return rc; }
-    MAGE_CUDA_TRY(cudaStreamSynchronize(lead->stream));
+    if (!table.empty()) {
+        const int nl = (int)table.size();
+        if (nl > lead->ctl_cap) {
+            if (lead->d_ctl_table) cudaFree(lead->d_ctl_table);
+            lead->ctl_cap = nl;
+            MAGE_CUDA_TRY(cudaMalloc(&lead->d_ctl_table, sizeof(BaCtl) * nl));
+        }
+        lead->h_ctl_table.resize(nl);
+        k_ba_gather_ctl<<<div_up(nl, 128), 128, 0, lead->stream>>>(lead->d_table, nl, lead->d_ctl_table);
+        MAGE_CUDA_TRY(cudaMemcpyAsync(lead->h_ctl_table.data(), lead->d_ctl_table, sizeof(BaCtl) * nl, cudaMemcpyDeviceToHost, lead->stream));
+        MAGE_CUDA_TRY(cudaStreamSynchronize(lead->stream));
+        for (int k = 0; k < nl; k++) hs[live[k]]->h_ctl = lead->h_ctl_table[k];
+    }
     for (int i = 0; i < n; i++) {
         int nout = 0;
-        int rc = ba_finish(hs[i], nullptr, 0, &nout, &means[i], true);
+        int rc = ba_finish(hs[i], nullptr, 0, &nout, &means[i], true, lead->stream);
         if (rc) return rc;
     }
     return MAGE_OK;
