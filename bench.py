@@ -417,7 +417,7 @@ def main():
     ap.add_argument("--ring", type=int, default=512, help="frames in the input ring (157 MB at 512 > 126 MB L2)")
     ap.add_argument("--unique", type=int, default=64, help="distinct warped views rendered for the ring")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames of the bounded CPU-baseline sample")
-    ap.add_argument("--ba-problems", type=int, default=148)
+    ap.add_argument("--ba-problems", type=int, default=296)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
