@@ -412,7 +412,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frames per step")
+    ap.add_argument("--batch", type=int, default=128, help="frames per step")
     ap.add_argument("--chunk", type=int, default=32, help="pipelining granularity of the host (e2e) path")
     ap.add_argument("--ring", type=int, default=512, help="frames in the input ring (157 MB at 512 > 126 MB L2)")
     ap.add_argument("--unique", type=int, default=64, help="distinct warped views rendered for the ring")

@@ -43,6 +43,7 @@ struct BaDev {
     const int2* pairs;                        // (edge of i1, edge of i2) sharing a landmark
     const int* e_l;                           // [Ea] landmark index of the edge's point or -1
     double *err, *W, *WD, *Hll, *bl, *Dinv, *db, *Hpp, *bp, *S, *bs, *x, *cam_bak, *pt_bak, *part;
+    double* Hc;                               // [Ea][12] per-edge contribution to (H_ll 3x3, b_l 3)
     unsigned char* flags;                     // [Ea] 1 = outlier
     BaCtl* ctl;
     // cooperative (multi-CTA) variant: per-(block, part) partial sums of the Schur products and the grid reduction slots
@@ -220,37 +221,51 @@ __device__ __forceinline__ void edge_jacobians(const BaDev& p, int e, double* Ji
     }
 }
 
-// ref block_solver.hpp:463-521 + base_binary_edge.hpp:62-134: landmark blocks H_ll, b_l and pose-landmark blocks W
+// ref block_solver.hpp:463-521 + base_binary_edge.hpp:62-134: landmark blocks H_ll, b_l and pose-landmark blocks W.
+// Edge-parallel: every active edge with a free point computes its Jacobians once, stores W (6x3) and its contribution to
+// (H_ll, b_l) into a per-edge slot; phase_sum_points then adds a landmark's (contiguous) slots in edge order.
 __device__ void phase_build_points(const BaDev& p, double delta, int tid, int nt)
 {
+    for (int e = tid; e < p.Ea; e += nt) {
+        if (p.e_l[e] < 0) continue;
+        const int hj = p.cam_h[p.e_cam[e]];
+        double Ji[6], Jj[12];
+        edge_jacobians(p, e, Ji, Jj, hj >= 0);
+        const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1], info = p.e_info[e];
+        double r0, r1;
+        huber(info * (e0 * e0 + e1 * e1), delta, r0, r1);
+        const double w = r1 * info, o0 = -info * e0 * r1, o1 = -info * e1 * r1;
+        double* __restrict__ hc = p.Hc + 12 * (size_t)e;
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            hc[9 + r] = Ji[r] * o0 + Ji[3 + r] * o1;
+#pragma unroll
+            for (int c = 0; c < 3; c++) hc[r * 3 + c] = w * (Ji[r] * Ji[c] + Ji[3 + r] * Ji[3 + c]);
+        }
+        if (hj >= 0) {
+            double* __restrict__ W = p.W + 18 * (size_t)e;
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) W[r * 3 + c] = w * (Jj[r] * Ji[c] + Jj[6 + r] * Ji[3 + c]);
+        }
+    }
+}
+__device__ void phase_sum_points(const BaDev& p, int tid, int nt)
+{
     for (int li = tid; li < p.Pl; li += nt) {
-        double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-        for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
-            const int e = k;                              // edges are stored grouped by landmark
-            const int hj = p.cam_h[p.e_cam[e]];
-            double Ji[6], Jj[12];
-            edge_jacobians(p, e, Ji, Jj, hj >= 0);
-            const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1], info = p.e_info[e];
-            double r0, r1;
-            huber(info * (e0 * e0 + e1 * e1), delta, r0, r1);
-            const double w = r1 * info, o0 = -info * e0 * r1, o1 = -info * e1 * r1;
+        double acc[12];
 #pragma unroll
-            for (int r = 0; r < 3; r++) {
-                b[r] += Ji[r] * o0 + Ji[3 + r] * o1;
+        for (int i = 0; i < 12; i++) acc[i] = 0;
+        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
+        for (int k = k0; k < k1; k++) {
+            const double* __restrict__ hc = p.Hc + 12 * (size_t)k;
 #pragma unroll
-                for (int c = 0; c < 3; c++) H[r * 3 + c] += w * (Ji[r] * Ji[c] + Ji[3 + r] * Ji[3 + c]);
-            }
-            if (hj >= 0) {
-                double* W = p.W + 18 * (size_t)e;
-#pragma unroll
-                for (int r = 0; r < 6; r++)
-#pragma unroll
-                    for (int c = 0; c < 3; c++) W[r * 3 + c] = w * (Jj[r] * Ji[c] + Jj[6 + r] * Ji[3 + c]);
-            }
+            for (int i = 0; i < 12; i++) acc[i] += hc[i];
         }
 #pragma unroll
-        for (int i = 0; i < 9; i++) p.Hll[9 * (size_t)li + i] = H[i];
-        p.bl[3 * li] = b[0]; p.bl[3 * li + 1] = b[1]; p.bl[3 * li + 2] = b[2];
+        for (int i = 0; i < 9; i++) p.Hll[9 * (size_t)li + i] = acc[i];
+        p.bl[3 * li] = acc[9]; p.bl[3 * li + 1] = acc[10]; p.bl[3 * li + 2] = acc[11];
     }
 }
 
@@ -328,13 +343,26 @@ __device__ double phase_max_diag(const BaDev& p, double* sh)
     return block_max(m, sh);
 }
 
-// Schur step 1 (ref block_solver.hpp:337-352): D^-1 = (H_ll + lambda I)^-1 (3x3 cofactor inverse), db = D^-1 b_l, WD = W D^-1
+// Schur step 1 (ref block_solver.hpp:337-352): D^-1 = (H_ll + lambda I)^-1 (3x3 cofactor inverse), db = D^-1 b_l, WD = W D^-1.
+// Edge-parallel: each edge inverts its landmark's block itself (a few dozen flops, cheaper than a dependent round trip) and the
+// first edge of a landmark publishes D^-1 and db.
 __device__ void phase_schur_points(const BaDev& p, double lambda, int tid, int nt)
 {
-    for (int li = tid; li < p.Pl; li += nt) {
-        double A[9];
+    for (int e = tid; e < p.Ea; e += nt) {
+        const int li = p.e_l[e];
+        if (li < 0) continue;
+        const bool hasCam = p.cam_h[p.e_cam[e]] >= 0;
+        const bool first = e == p.l_ptr[li];
+        if (!hasCam && !first) continue;
+        double A[9], w[18];
+        const double* __restrict__ Hl = p.Hll + 9 * (size_t)li;
+        const double* __restrict__ W = p.W + 18 * (size_t)e;
 #pragma unroll
-        for (int i = 0; i < 9; i++) A[i] = p.Hll[9 * (size_t)li + i];
+        for (int i = 0; i < 9; i++) A[i] = Hl[i];
+        if (hasCam) {
+#pragma unroll
+            for (int i = 0; i < 18; i++) w[i] = W[i];
+        }
         A[0] += lambda; A[4] += lambda; A[8] += lambda;
         const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
         const double id = 1.0 / (A[0] * c00 + A[1] * c01 + A[2] * c02);
@@ -342,20 +370,16 @@ __device__ void phase_schur_points(const BaDev& p, double lambda, int tid, int n
         D[0] = c00 * id; D[1] = (A[2] * A[7] - A[1] * A[8]) * id; D[2] = (A[1] * A[5] - A[2] * A[4]) * id;
         D[3] = c01 * id; D[4] = (A[0] * A[8] - A[2] * A[6]) * id; D[5] = (A[2] * A[3] - A[0] * A[5]) * id;
         D[6] = c02 * id; D[7] = (A[1] * A[6] - A[0] * A[7]) * id; D[8] = (A[0] * A[4] - A[1] * A[3]) * id;
+        if (first) {
 #pragma unroll
-        for (int i = 0; i < 9; i++) p.Dinv[9 * (size_t)li + i] = D[i];
-        const double b0 = p.bl[3 * li], b1 = p.bl[3 * li + 1], b2 = p.bl[3 * li + 2];
-        p.db[3 * li] = D[0] * b0 + D[1] * b1 + D[2] * b2;
-        p.db[3 * li + 1] = D[3] * b0 + D[4] * b1 + D[5] * b2;
-        p.db[3 * li + 2] = D[6] * b0 + D[7] * b1 + D[8] * b2;
-        for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
-            const int e = k;
-            if (p.cam_h[p.e_cam[e]] < 0) continue;
-            const double* __restrict__ W = p.W + 18 * (size_t)e;
+            for (int i = 0; i < 9; i++) p.Dinv[9 * (size_t)li + i] = D[i];
+            const double b0 = p.bl[3 * li], b1 = p.bl[3 * li + 1], b2 = p.bl[3 * li + 2];
+            p.db[3 * li] = D[0] * b0 + D[1] * b1 + D[2] * b2;
+            p.db[3 * li + 1] = D[3] * b0 + D[4] * b1 + D[5] * b2;
+            p.db[3 * li + 2] = D[6] * b0 + D[7] * b1 + D[8] * b2;
+        }
+        if (hasCam) {
             double* __restrict__ WD = p.WD + 18 * (size_t)e;
-            double w[18];
-#pragma unroll
-            for (int i = 0; i < 18; i++) w[i] = W[i];              // all loads in flight before the first store
 #pragma unroll
             for (int r = 0; r < 6; r++)
 #pragma unroll
@@ -576,6 +600,8 @@ __device__ void phase_classify(const BaDev& p, double maxErrSq, double* sh, doub
 // ------------------------------------------------------------------------------------------------ the persistent LM kernel
 // One CTA per problem runs StepBundleAdjustment's whole loop: for each Huber width one g2o LM iteration
 // (ref optimization_algorithm_levenberg.cpp:57-149, up to 10 lambda trials), then the outlier classification.
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PH(i) do { if (blockIdx.x == 0 && tid == 0) { long long _n = gtimer(); ctl->phase_ns[i] += _n - t_last; t_last = _n; } } while (0)
 constexpr int kBaThreads = 256;
 
 // Shared-memory residency: the reduced system S (n x n) + its right-hand side and the camera state (pose, intrinsics,
@@ -629,17 +655,21 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
     int iteration = ctl->iteration;
     long long trials = 0, iters = 0;
 
+    long long t_last = gtimer();
     for (int it = 0; it < nIters; it++) {
         if (s_stop) break;
         const double delta = (double)huberW[it];
         phase_errors(p, tid, nt);
         __syncthreads();
         double currentChi = phase_chi2(p, delta, sh);
+        PH(0);
         phase_build_points(p, delta, tid, nt);
         phase_build_cams(p, delta, warp, nw, lane);
         __syncthreads();
+        phase_sum_points(p, tid, nt);
         phase_finish_cams(p, tid, nt);
         __syncthreads();
+        PH(1);
         if (iteration == 0) {
             const double md = phase_max_diag(p, sh);
             if (tid == 0) { s_lambda = ctl->user_lambda_init > 0 ? ctl->user_lambda_init : 1e-5 * md; s_ni = 2; }
@@ -653,21 +683,26 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
             phase_backup(p, tid, nt);
             phase_schur_points(p, lambda, tid, nt);
             __syncthreads();
+            PH(2);
             phase_schur_blocks(p, lambda, warp, nw, lane);
             __syncthreads();
             phase_finish_bs(p, tid, nt);
             __syncthreads();
+            PH(3);
             const bool ok2 = phase_ldlt_solve(p, sh);
             __syncthreads();
+            PH(4);
             if (ok2) phase_backsub(p, tid, nt);
             __syncthreads();
             phase_update(p, tid, nt);
             __syncthreads();
+            PH(6);
             phase_errors(p, tid, nt);
             __syncthreads();
             double tempChi = phase_chi2(p, delta, sh);
             if (!ok2) tempChi = DBL_MAX;
             const double scale = phase_scale(p, lambda, sh) + 1e-3;
+            PH(7);
             if (tid == 0) {
                 double r = (currentChi - tempChi) / scale;
                 s_rho = r;
@@ -718,8 +753,6 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
 // partials (bit-reproducible for a given grid size); the camera state is replicated in every block's shared memory and updated
 // redundantly, so no broadcast is needed; block 0 assembles and factorises the reduced system in its shared memory.
 namespace cg = cooperative_groups;
-__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-#define PH(i) do { if (blockIdx.x == 0 && tid == 0) { long long _n = gtimer(); ctl->phase_ns[i] += _n - t_last; t_last = _n; } } while (0)
 constexpr int kCoopThreads = 256;
 constexpr int kCoopMaxBlocks = 148;
 constexpr int kCoopRedVals = 2;
@@ -1077,9 +1110,10 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
         phase_build_cams(p, delta, gwarp, gnw, lane);
         grid.sync();
         PH(1);
+        phase_sum_points(p, gtid, gnt);
         phase_finish_cams(p, gtid, gnt);
+        grid.sync();
         if (iteration == 0) {
-            grid.sync();
             double m = 0;
             for (int i = gtid; i < p.Kf * 6; i += gnt) m = fmax(m, fabs(p.Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]));
             for (int i = gtid; i < p.Pl * 3; i += gnt) m = fmax(m, fabs(p.Hll[9 * (size_t)(i / 3) + (i % 3) * 4]));
@@ -1412,6 +1446,7 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_Dinv = rD(9 * (size_t)Pl), o_db = rD(3 * (size_t)Pl), o_Hpp = rD(36 * (size_t)Kf), o_bp = rD(n), o_S = rD((size_t)n * n), o_bs = rD(n);
     size_t o_x = rD(n + 3 * (size_t)Pl), o_cbak = rD(7 * (size_t)Kf), o_pbak = rD(3 * (size_t)Pl), o_part = rD((size_t)Kf * cam_parts * 27);
     size_t o_flags = W.reserve(std::max(Ea, 1));
+    size_t o_Hc = rD(12 * (size_t)Ea);
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
     size_t o_Wk = rD(big ? (size_t)n * kLdltNB : 1);
@@ -1441,6 +1476,7 @@ static int ba_build_structure(mage_ba_t h)
     d.Dinv = W.at<double>(o_Dinv); d.db = W.at<double>(o_db); d.Hpp = W.at<double>(o_Hpp); d.bp = W.at<double>(o_bp); d.S = W.at<double>(o_S);
     d.bs = W.at<double>(o_bs); d.x = W.at<double>(o_x); d.cam_bak = W.at<double>(o_cbak); d.pt_bak = W.at<double>(o_pbak); d.part = W.at<double>(o_part);
     d.flags = W.at<unsigned char>(o_flags);
+    d.Hc = W.at<double>(o_Hc);
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
     d.big = big; d.Wk = W.at<double>(o_Wk);

@@ -14,7 +14,7 @@ def kernel_ms(slot=7):
     return t.value, n.value
 prob = synth.ba_problem()
 hub = [1.8] * 10
-for G in (32,):
+for G in (0, 32):
     os.environ["MAGE_BA_COOP_BLOCKS"] = str(G)
     res = []
     for rep in range(3):
@@ -34,7 +34,7 @@ for G in (32,):
         G, min(r[0] for r in res), min(r[1] for r in res), 10 / (min(r[0] for r in res) * 1e-3), 10 / (min(r[1] for r in res) * 1e-3), st["lm_iterations"], st["lambda_trials"], m))
     print("      phase us (errors+chi2, build, schur_pts, schur_prod, assemble+ldlt, sync, backsub+update, errors+scale):", [round(float(x) / 1e3, 1) for x in ph[:9]], '(last = assemble only)')
 os.environ["MAGE_BA_COOP_BLOCKS"] = "32"
-for N in (296, 444, 592):
+for N in (296,):
     bs = [BundlerLib().load(prob) for _ in range(N)]
     StepMany(bs, [1.8], 1e9)
     L.mage_profile_reset(); L.mage_profile_enable(1)
