@@ -107,7 +107,7 @@ def level_areas():
     areas = []
     for l in range(NLEVELS):
         s = np.float32(np.float64(np.float32(SCALE)) ** l)
-        areas.append(int(np.rint(np.float32(W) / s)) * int(np.rint(np.float32(H) / s)))
+        areas.append(int(np.rint(np.float32(W) / s)) * int(np.rint(np.float32(H) / s)))    # W, H are module globals (default 640 x 480)
     return areas
 
 
@@ -417,8 +417,14 @@ def main():
     ap.add_argument("--ring", type=int, default=512, help="frames in the input ring (157 MB at 512 > 126 MB L2)")
     ap.add_argument("--unique", type=int, default=64, help="distinct warped views rendered for the ring")
     ap.add_argument("--cpu-frames", type=int, default=40, help="frames of the bounded CPU-baseline sample")
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--ba-problems", type=int, default=296)
     args = ap.parse_args()
+    global W, H, METRIC, WORKLOAD
+    if (args.width, args.height) != (W, H):
+        WORKLOAD = WORKLOAD.replace("640x480", "%dx%d" % (args.width, args.height)); METRIC = "orb_extract_match_fps_%dx%d" % (args.width, args.height)
+        W, H = args.width, args.height
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

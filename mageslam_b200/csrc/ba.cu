@@ -269,6 +269,40 @@ __device__ void phase_sum_points(const BaDev& p, int tid, int nt)
     }
 }
 
+// landmark-parallel variant (one thread walks a landmark's edges): fewer instructions, used by the one-CTA-per-problem kernel
+__device__ void phase_build_points_lm(const BaDev& p, double delta, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+        for (int k = p.l_ptr[li]; k < p.l_ptr[li + 1]; k++) {
+            const int e = k;                              // edges are stored grouped by landmark
+            const int hj = p.cam_h[p.e_cam[e]];
+            double Ji[6], Jj[12];
+            edge_jacobians(p, e, Ji, Jj, hj >= 0);
+            const double e0 = p.err[2 * e], e1 = p.err[2 * e + 1], info = p.e_info[e];
+            double r0, r1;
+            huber(info * (e0 * e0 + e1 * e1), delta, r0, r1);
+            const double w = r1 * info, o0 = -info * e0 * r1, o1 = -info * e1 * r1;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                b[r] += Ji[r] * o0 + Ji[3 + r] * o1;
+#pragma unroll
+                for (int c = 0; c < 3; c++) H[r * 3 + c] += w * (Ji[r] * Ji[c] + Ji[3 + r] * Ji[3 + c]);
+            }
+            if (hj >= 0) {
+                double* W = p.W + 18 * (size_t)e;
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) W[r * 3 + c] = w * (Jj[r] * Ji[c] + Jj[6 + r] * Ji[3 + c]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 9; i++) p.Hll[9 * (size_t)li + i] = H[i];
+        p.bl[3 * li] = b[0]; p.bl[3 * li + 1] = b[1]; p.bl[3 * li + 2] = b[2];
+    }
+}
+
 // pose blocks H_pp (diagonal 6x6) and b_p: one warp per (camera, part) slice of the camera's edge list, lanes stride the
 // slice, shuffle-tree reduction, partials summed in part order by phase_finish_cams
 __device__ void phase_build_cams(const BaDev& p, double delta, int warp, int nwarps, int lane)
@@ -663,10 +697,9 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
         __syncthreads();
         double currentChi = phase_chi2(p, delta, sh);
         PH(0);
-        phase_build_points(p, delta, tid, nt);
+        phase_build_points_lm(p, delta, tid, nt);
         phase_build_cams(p, delta, warp, nw, lane);
         __syncthreads();
-        phase_sum_points(p, tid, nt);
         phase_finish_cams(p, tid, nt);
         __syncthreads();
         PH(1);
