@@ -90,35 +90,38 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __res
             if (half == 0) { tx[tl] = v.x ^ v.y ^ v.z; tvalid[tl] = (t < nT && (!mT || mT[t])) ? 1 : 0; }
         }
         __syncthreads();
-#pragma unroll 2
+        // filter pass: branch-free over the lane's 8 trains x 4 queries (32 pairs), survivors recorded in a bit mask
+        unsigned hits = 0;
+#pragma unroll
         for (int i = 0; i < kChunk / 32; i++) {
             const int ti = lane + 32 * i;
             const uint32_t t0 = tw[0][ti], t1 = tw[1][ti], t2 = tw[2][ti], txx = tx[ti];
-            unsigned pass = 0;
 #pragma unroll
             for (int k = 0; k < kQPerWarp; k++) {
                 const uint32_t x0 = q[k][0] ^ t0, x1 = q[k][1] ^ t1, x2 = q[k][2] ^ t2;
                 const uint32_t twos = (x0 & x1) | (x2 & (x0 | x1));
                 const int d3 = __popc(qx[k] ^ txx) + 2 * __popc(twos);
-                pass |= (d3 <= max_hamming) ? (1u << k) : 0u;
+                hits |= (d3 <= max_hamming) ? (1u << (i * kQPerWarp + k)) : 0u;
             }
-            if (pass == 0 || !tvalid[ti]) continue;
-            const unsigned tidx = (unsigned)(c0 + ti);
+        }
+        // survivors (about 1e-4 of random pairs, plus the true matches): exact distance, then the four packed updates
+        while (hits) {
+            const int bit = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int i = bit / kQPerWarp, k = bit % kQPerWarp;
+            const int ti = lane + 32 * i;
+            if (!tvalid[ti] || !qok[k]) continue;
+            const int ql = warp * kQPerWarp + k;
+            int d = 0;
 #pragma unroll
-            for (int k = 0; k < kQPerWarp; k++) {
-                if (!((pass >> k) & 1) || !qok[k]) continue;
-                const int ql = warp * kQPerWarp + k;
-                int d = 0;
-#pragma unroll
-                for (int w = 0; w < 8; w++) d += __popc(qw[ql][w] ^ tw[w][ti]);
-                if (d > max_hamming) continue;                      // radiusMatch keeps d <= maxDistance only
-                const unsigned qidx = (unsigned)(q0 + ql);
-                const unsigned kf = ((unsigned)d << 16) | tidx, kb = ((unsigned)d << 16) | qidx;
-                unsigned old = atomicMin(&fbest[qidx], kf);
-                atomicMin(&fsecond[qidx], max(old, kf));
-                old = atomicMin(&bbest[tidx], kb);
-                atomicMin(&bsecond[tidx], max(old, kb));
-            }
+            for (int w = 0; w < 8; w++) d += __popc(qw[ql][w] ^ tw[w][ti]);
+            if (d > max_hamming) continue;                          // radiusMatch keeps d <= maxDistance only
+            const unsigned tidx = (unsigned)(c0 + ti), qidx = (unsigned)(q0 + ql);
+            const unsigned kf = ((unsigned)d << 16) | tidx, kb = ((unsigned)d << 16) | qidx;
+            unsigned old = atomicMin(&fbest[qidx], kf);
+            atomicMin(&fsecond[qidx], max(old, kf));
+            old = atomicMin(&bbest[tidx], kb);
+            atomicMin(&bsecond[tidx], max(old, kb));
         }
     }
 }

@@ -595,7 +595,11 @@ __global__ void __launch_bounds__(256) k_blur7(const __grid_constant__ OrbGeom g
     int T[kBlur7Rows + 6][4];
 #pragma unroll
     for (int i = 0; i < kBlur7Rows + 6; i++) {
-        const int sy = reflect101(min(y0 + i - 3, L.h + 2), L.h);
+        // branch-free REFLECT_101 of the row index (levels are >= 8 rows, the overshoot is at most 3 after the clamp), so that
+        // all 66 loads of the thread can be issued back to back
+        int sy = min(y0 + i - 3, L.h + 2);
+        sy = sy < 0 ? -sy : sy;
+        sy = sy >= L.h ? 2 * L.h - 2 - sy : sy;
         const uint8_t* row = img + (size_t)sy * pitch;
         const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row + x - 4), w1 = *reinterpret_cast<const uint32_t*>(row + x),
                        w2 = *reinterpret_cast<const uint32_t*>(row + x + 4);
