@@ -143,6 +143,24 @@ int  mage_match_run_jobs(mage_matcher_t m, int first_pair, int n_pairs, int max_
 /* GetDescriptorDistance for n pairs of device-resident descriptors (a[i] vs b[i]) -> d_out[i]. */
 int  mage_descriptor_distance_device(const uint8_t* d_a, const uint8_t* d_b, int n, int* d_out, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------------ RadiusMatch */
+
+/* KeypointSpatialIndex (ref Image/KeypointSpatialIndex.h:22-38, .cpp:45-58): built once per analysed image from its
+ * keypoints. Instead of an R*-tree the handle stores every keypoint's rank in the enumeration order of the reference's
+ * packed boost R*-tree, which is all RadiusMatch's result depends on. */
+typedef struct mage_spatial_index_s* mage_spatial_index_t;
+int  mage_spatial_index_create(const mage_keypoint* keypoints, int n, mage_spatial_index_t* out);
+void mage_spatial_index_destroy(mage_spatial_index_t ix);
+int  mage_spatial_index_rank(mage_spatial_index_t ix, int* rank_out /* n */);
+/* RadiusMatch, multi-query overload (ref Tracking/FeatureMatcher.h:92-106, .cpp:294-376); nq = 1 gives the single-query
+ * overload (ref .h:119-132, .cpp:384-446: count is 0 or 1, out[0].query_idx = 0). query_pos_override (2 floats per query),
+ * query_mask and target_mask (one byte per keypoint) may be NULL. Target keypoints are the ones the index was built from;
+ * target_desc holds their 32-byte descriptors. out needs room for nq matches. Host buffers, synchronous. */
+int  mage_radius_match(mage_spatial_index_t ix, const mage_keypoint* query_kps, int nq, const float* query_pos_override,
+                       const uint8_t* query_mask, const uint8_t* query_desc, const uint8_t* target_mask,
+                       const uint8_t* target_desc, float radius, int max_hamming, int min_hamming_diff,
+                       mage_dmatch* out, int* count, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------- Front-end for a video stream */
 
 /* ORB extract of a batch of frames + Match of every frame (query) against its predecessor (train): the reference's

@@ -4,7 +4,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._lib import DMATCH_DTYPE, check, lib, ptr, stream_ptr
+from ._lib import DMATCH_DTYPE, KEYPOINT_DTYPE, check, lib, ptr, stream_ptr
 
 
 @dataclass
@@ -78,3 +78,48 @@ def GetDescriptorDistance(d0, d1):
     out = torch.empty(n, dtype=torch.int32, device=d0.device)
     check(lib().mage_descriptor_distance_device(ptr(d0), ptr(d1), n, ptr(out), stream_ptr(torch.cuda.current_stream())))
     return out
+
+
+class KeypointSpatialIndex:
+    """Mirror of mage::KeypointSpatialIndex (reference Image/KeypointSpatialIndex.h:22-38): built from an image's keypoints."""
+
+    def __init__(self, keypoints):
+        self.keypoints = np.ascontiguousarray(keypoints, KEYPOINT_DTYPE)
+        self._h = C.c_void_p()
+        check(lib().mage_spatial_index_create(ptr(self.keypoints) if len(self.keypoints) else None, len(self.keypoints), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mage_spatial_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def Rank(self):
+        r = np.zeros(len(self.keypoints), np.int32)
+        if len(r):
+            check(lib().mage_spatial_index_rank(self._h, ptr(r)))
+        return r
+
+
+def RadiusMatch(queryKeypoints, queryKeypointPositionOverrides, queryKeypointsMask, queryDescriptors, targetKeypointsIndex,
+                targetKeypointsMask, targetDescriptors, radius, maxHammingDist, minHammingDifference):
+    """Mirror of RadiusMatch (reference Tracking/FeatureMatcher.h:92-106): returns goodMatches (DMATCH_DTYPE, ascending queryIdx).
+    targetKeypoints are the keypoints targetKeypointsIndex was built from."""
+    qk = np.ascontiguousarray(queryKeypoints, KEYPOINT_DTYPE)
+    qd = np.ascontiguousarray(queryDescriptors, np.uint8).reshape(-1, 32)
+    td = np.ascontiguousarray(targetDescriptors, np.uint8).reshape(-1, 32)
+    assert len(qd) == len(qk) and len(td) == len(targetKeypointsIndex.keypoints)
+    qp = None if queryKeypointPositionOverrides is None else np.ascontiguousarray(queryKeypointPositionOverrides, np.float32).reshape(-1, 2)
+    qm = None if queryKeypointsMask is None else np.ascontiguousarray(queryKeypointsMask, np.uint8)
+    tm = None if targetKeypointsMask is None else np.ascontiguousarray(targetKeypointsMask, np.uint8)
+    out = np.zeros(max(len(qk), 1), DMATCH_DTYPE)
+    cnt = C.c_int(0)
+    check(lib().mage_radius_match(targetKeypointsIndex._h, ptr(qk) if len(qk) else None, len(qk), ptr(qp), ptr(qm), ptr(qd) if len(qk) else None,
+                                  ptr(tm), ptr(td) if len(td) else None, float(radius), int(maxHammingDist), int(minHammingDifference),
+                                  ptr(out), C.byref(cnt), None))
+    return out[:cnt.value]

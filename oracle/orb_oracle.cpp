@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -712,3 +713,118 @@ int orc_match(const uint8_t* descA, int nAall, const uint8_t* maskA, const uint8
 }
 
 } // extern "C"
+
+// ---- RadiusMatch ------------------------------------------------------------------------------------------------------
+// The reference gates candidates with a boost::geometry R*-tree (rstar<12>) built by the range constructor, i.e. boost's
+// packing algorithm (boost 1.67 index/detail/rtree/pack_create.hpp, vendored by the reference): top-down, split at an
+// element-count median along the longest edge of the (hint) bounding box with std::nth_element, leaves of <= 12 values.
+// A box query reports values in depth-first order of that tree, so the enumeration order of the candidates -- the only thing
+// RadiusMatch's result depends on beyond the candidate set -- is the order of the packed leaves. The restatement below
+// reproduces that order (rank of every value); it is validated against the real boost R-tree (oracle/radius_ref.cpp).
+namespace {
+struct PackEntry { float c[3]; int idx; };
+struct PackBox { float lo[3], hi[3]; };
+struct PackCounts { size_t maxc, minc; };
+constexpr size_t kRtMax = 12, kRtMin = 3;                          // rstar<12>: min = 0.3 * max
+
+size_t packMedianCount(size_t count, const PackCounts& sc)         // pack_create.hpp calculate_median_count
+{
+    size_t n = count / sc.maxc, r = count % sc.maxc, median = (n / 2) * sc.maxc;
+    if (r != 0) {
+        if (sc.minc <= r) median = ((n + 1) / 2) * sc.maxc;
+        else {
+            size_t cmm = count - sc.minc;
+            n = cmm / sc.maxc; r = cmm % sc.maxc;
+            if (r == 0) median = ((n + 1) / 2) * sc.maxc;
+            else median = (n == 0) ? r : ((n + 2) / 2) * sc.maxc;
+        }
+    }
+    return median;
+}
+void packPerLevel(PackEntry* first, PackEntry* last, const PackBox& hint, size_t count, const PackCounts& sc, std::vector<int>& order);
+void packPackets(PackEntry* first, PackEntry* last, const PackBox& hint, size_t count, const PackCounts& sc, const PackCounts& next, std::vector<int>& order)
+{
+    if (count <= sc.maxc) { packPerLevel(first, last, hint, count, next, order); return; }
+    size_t medianCount = packMedianCount(count, sc);
+    PackEntry* median = first + medianCount;
+    float len = hint.hi[0] - hint.lo[0]; int dim = 0;               // pack_utils::biggest_edge
+    for (int d = 1; d < 3; d++) { float cur = hint.hi[d] - hint.lo[d]; if (len < cur) { dim = d; len = cur; } }
+    std::nth_element(first, median, last, [dim](const PackEntry& a, const PackEntry& b) { return a.c[dim] < b.c[dim]; });
+    PackBox left = hint, right = hint;
+    float mid = hint.lo[dim] + (hint.hi[dim] - hint.lo[dim]) / 2;
+    left.hi[dim] = mid; right.lo[dim] = mid;
+    packPackets(first, median, left, medianCount, sc, next, order);
+    packPackets(median, last, right, count - medianCount, sc, next, order);
+}
+void packPerLevel(PackEntry* first, PackEntry* last, const PackBox& hint, size_t count, const PackCounts& sc, std::vector<int>& order)
+{
+    if (sc.maxc <= 1) { for (PackEntry* e = first; e != last; ++e) order.push_back(e->idx); return; }      // leaf: values in range order
+    PackCounts next{sc.maxc / kRtMax, sc.minc / kRtMax};
+    packPackets(first, last, hint, count, sc, next, order);
+}
+// enumeration (depth-first) order of the packed tree
+void rtreeOrder(const orc_keypoint* kps, int n, std::vector<int>& order)
+{
+    order.clear();
+    if (n <= 0) return;
+    std::vector<PackEntry> e(n);
+    PackBox box;
+    for (int i = 0; i < n; i++) {
+        e[i] = PackEntry{{kps[i].x, kps[i].y, kps[i].octave * 100.f}, i};
+        for (int d = 0; d < 3; d++) {
+            if (i == 0) { box.lo[d] = box.hi[d] = e[i].c[d]; }
+            else { box.lo[d] = std::min(box.lo[d], e[i].c[d]); box.hi[d] = std::max(box.hi[d], e[i].c[d]); }
+        }
+    }
+    PackCounts sc{1, 1};                                              // calculate_subtree_elements_counts
+    for (size_t smax = kRtMax; smax < (size_t)n; smax *= kRtMax) sc.maxc = smax;
+    sc.minc = kRtMin * (sc.maxc / kRtMax);
+    packPerLevel(e.data(), e.data() + n, box, (size_t)n, sc, order);
+}
+} // namespace
+
+extern "C" int orc_rtree_order(const orc_keypoint* kps, int n, int* order_out)
+{
+    std::vector<int> order;
+    rtreeOrder(kps, n, order);
+    std::copy(order.begin(), order.end(), order_out);
+    return (int)order.size();
+}
+
+// ref Tracking/FeatureMatcher.cpp:294-446 + Image/KeypointSpatialIndex.cpp:89-97 (box query: same octave, |dx|,|dy| <= radius)
+extern "C" int orc_radius_match(const orc_keypoint* qk, int nq, const float* qpos_override, const uint8_t* qmask, const uint8_t* qdesc,
+                                const orc_keypoint* tk, int nt, const uint8_t* tmask, const uint8_t* tdesc, float radius, int maxHamming,
+                                int minDiff, orc_dmatch* out)
+{
+    std::vector<int> order;
+    rtreeOrder(tk, nt, order);
+    std::vector<orc_dmatch> almost;
+    for (int q = 0; q < nq; q++) {
+        if (qmask && !qmask[q]) continue;
+        const float px = qpos_override ? qpos_override[2 * q] : qk[q].x, py = qpos_override ? qpos_override[2 * q + 1] : qk[q].y;
+        const float lox = px - radius, hix = px + radius, loy = py - radius, hiy = py + radius;
+        const float loz = qk[q].octave * 100.f - 1.f, hiz = qk[q].octave * 100.f + 1.f;
+        int best = maxHamming + 1, second = INT_MAX;
+        orc_dmatch bm{0, -1, 0.f};
+        for (int t : order) {                                                   // enumeration order of the R-tree
+            const float z = tk[t].octave * 100.f;
+            if (!(lox <= tk[t].x && tk[t].x <= hix && loy <= tk[t].y && tk[t].y <= hiy && loz <= z && z <= hiz)) continue;
+            if (tmask && !tmask[t]) continue;
+            int d = orc_descriptor_distance(qdesc + 32 * (size_t)q, tdesc + 32 * (size_t)t);
+            if (d < best) { bm.train = t; bm.distance = (float)d; second = best; best = d; }
+        }
+        if (bm.train != -1 && (second - best) > minDiff) { bm.query = q; almost.push_back(bm); }
+    }
+    int n = 0;
+    if (almost.size() > 1) {
+        std::vector<float> bestD(nt, FLT_MAX), secondD(nt, FLT_MAX);
+        for (const auto& m : almost) {
+            if (m.distance < bestD[m.train]) { secondD[m.train] = bestD[m.train]; bestD[m.train] = m.distance; }
+            else if (m.distance < secondD[m.train]) secondD[m.train] = m.distance;
+        }
+        for (const auto& m : almost) if (m.distance == bestD[m.train] && bestD[m.train] < secondD[m.train]) out[n++] = m;
+    } else {
+        for (const auto& m : almost) out[n++] = m;
+    }
+    return n;
+}

@@ -79,6 +79,13 @@ int   orc_match(const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_
                 int max_hamming, int min_diff, orc_dmatch* out, int* count);
 int   orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
 
+/* RadiusMatch (reference Tracking/FeatureMatcher.cpp:294-446) over the enumeration order of the packed boost R*-tree
+ * (reference Image/KeypointSpatialIndex.cpp). order_out receives the depth-first value order of the tree built from kps. */
+int   orc_rtree_order(const orc_keypoint* kps, int n, int* order_out);
+int   orc_radius_match(const orc_keypoint* qk, int nq, const float* qpos_override, const uint8_t* qmask, const uint8_t* qdesc,
+                       const orc_keypoint* tk, int nt, const uint8_t* tmask, const uint8_t* tdesc, float radius, int max_hamming,
+                       int min_diff, orc_dmatch* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,3 +161,57 @@ def match(descA, descB, max_hamming=30, min_diff=1, maskA=None, maskB=None):
 def descriptor_distance(a, b):
     a, ap = _u8(a); b, bp = _u8(b)
     return lib().orc_descriptor_distance(ap, bp)
+
+
+def rtree_order(kps):
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    order = np.zeros(len(kps), np.int32)
+    n = lib().orc_rtree_order(kps.ctypes.data_as(C.c_void_p), len(kps), order.ctypes.data_as(C.c_void_p))
+    return order[:n]
+
+
+def radius_match(qk, qdesc, tk, tdesc, radius, max_hamming, min_diff, qpos=None, qmask=None, tmask=None):
+    qk = np.ascontiguousarray(qk, KP_DTYPE); tk = np.ascontiguousarray(tk, KP_DTYPE)
+    qdesc, qdp = _u8(qdesc); tdesc, tdp = _u8(tdesc)
+    out = np.zeros(max(len(qk), 1), DM_DTYPE)
+    vp = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+    qpos, qmask, tmask = vp(qpos, np.float32), vp(qmask, np.uint8), vp(tmask, np.uint8)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    L = lib()
+    L.orc_radius_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_float, C.c_int, C.c_int, C.c_void_p]
+    n = L.orc_radius_match(p(qk), len(qk), p(qpos), p(qmask), qdp, p(tk), len(tk), p(tmask), tdp, float(radius), int(max_hamming), int(min_diff), p(out))
+    return out[:n].copy()
+
+
+_RREF = None
+
+
+def radius_ref():
+    """The RadiusMatch oracle on the REAL boost R*-tree (oracle/_ref/libradius_ref.so); None when it was not built."""
+    global _RREF
+    path = os.path.join(ROOT, "oracle", "_ref", "libradius_ref.so")
+    if _RREF is None and os.path.exists(path):
+        R = C.CDLL(path)
+        R.rmref_index_create.restype = C.c_void_p
+        R.rmref_index_create.argtypes = [C.c_void_p, C.c_int]
+        R.rmref_index_destroy.argtypes = [C.c_void_p]
+        R.rmref_query.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p, C.c_int]
+        R.rmref_radius_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_float, C.c_int, C.c_int, C.c_void_p]
+        _RREF = R
+    return _RREF
+
+
+def radius_match_ref(qk, qdesc, tk, tdesc, radius, max_hamming, min_diff, qpos=None, qmask=None, tmask=None):
+    R = radius_ref()
+    qk = np.ascontiguousarray(qk, KP_DTYPE); tk = np.ascontiguousarray(tk, KP_DTYPE)
+    qdesc, qdp = _u8(qdesc); tdesc, tdp = _u8(tdesc)
+    vp = lambda a, dt: None if a is None else np.ascontiguousarray(a, dt)
+    qpos, qmask, tmask = vp(qpos, np.float32), vp(qmask, np.uint8), vp(tmask, np.uint8)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    idx = R.rmref_index_create(p(tk), len(tk))
+    out = np.zeros(max(len(qk), 1), DM_DTYPE)
+    n = R.rmref_radius_match(idx, p(qk), len(qk), p(qpos), p(qmask), qdp, len(tk), p(tmask), tdp, float(radius), int(max_hamming), int(min_diff), p(out))
+    R.rmref_index_destroy(idx)
+    return out[:n].copy()
