@@ -359,10 +359,42 @@ def run_ours(args):
         line["ba"] = bench_ba(args, world, rank, dist if world > 1 else None)
     except Exception as e:      # pragma: no cover
         line["ba"] = {"error": str(e)[:300]}
+    if rank == 0 and world == 1:
+        try:
+            line["radius_match"] = bench_radius(kps, desc, cnt)
+        except Exception as e:      # pragma: no cover
+            line["radius_match"] = {"error": str(e)[:300]}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_radius(kps, desc, cnt):
+    """RadiusMatch of one frame's keypoints against the next frame's spatial index (radius 24 px), host-buffer C ABI
+    (index build + H2D + kernels + D2H per call) vs the oracle port on one core."""
+    from mageslam_b200.matcher import KeypointSpatialIndex, RadiusMatch
+    from tests import oracle_orb as orc
+    k0, d0, k1, d1 = kps[0, :cnt[0]].copy(), desc[0, :cnt[0]].copy(), kps[1, :cnt[1]].copy(), desc[1, :cnt[1]].copy()
+    ix = KeypointSpatialIndex(k1)
+    RadiusMatch(k0, None, None, d0, ix, None, d1, 24.0, 30, 1)
+    reps = 50
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m = RadiusMatch(k0, None, None, d0, ix, None, d1, 24.0, 30, 1)
+    t_match = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(10):
+        KeypointSpatialIndex(k1).close()
+    t_index = (time.perf_counter() - t0) / 10
+    t0 = time.perf_counter()
+    ref = orc.radius_match(k0.view(orc.KP_DTYPE), d0, k1.view(orc.KP_DTYPE), d1, 24.0, 30, 1)
+    t_cpu = time.perf_counter() - t0
+    same = len(ref) == len(m) and bool(np.array_equal(ref["train"], m["train_idx"]))
+    return {"metric": "radius_match_queries_per_sec", "value": len(k0) / t_match, "unit": "queries/s", "queries": int(len(k0)), "targets": int(len(k1)),
+            "matches": int(len(m)), "ms_per_call": 1e3 * t_match, "index_build_ms": 1e3 * t_index, "matches_equal_oracle": same,
+            "cpu_baseline": {"value": len(k0) / t_cpu, "unit": "queries/s", "cores": 1, "kind": "port",
+                             "sample": "one call, %d queries x %d targets (includes building the packed-tree order)" % (len(k0), len(k1))}}
 
 
 def bench_ba(args, world, rank, dist):
