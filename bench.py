@@ -324,8 +324,8 @@ def run_ours(args):
     try:        # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at the same batch size, from the committed ncu capture
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("frames_per_launch") == B and dom in tj["kernels"]:
-            traffic = tj["kernels"][dom]
+        if dom in tj["kernels"]:      # captured at tj["frames_per_launch"] frames per launch; DRAM traffic scales with the batch
+            traffic = tj["kernels"][dom] / tj["frames_per_launch"] * B
     except Exception:
         traffic = None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

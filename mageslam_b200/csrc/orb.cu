@@ -644,11 +644,19 @@ __global__ void __launch_bounds__(256) k_blur7_edges(const __grid_constant__ Orb
     const int x = (c < nleft) ? c : xr + (c - nleft);
     int pitch;
     const uint8_t* img = level_ptr(g, b, f, l, pitch);
+    int xs[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) xs[k] = reflect101(x + k - 3, L.w);          // column taps once per pixel
     unsigned acc = 32768u;
+#pragma unroll
     for (int j = 0; j < 7; j++) {
-        const uint8_t* row = img + (size_t)reflect101(y + j - 3, L.h) * pitch;
+        int sy = y + j - 3;                                                   // branch-free row reflect (|overshoot| <= 3 < h)
+        sy = sy < 0 ? -sy : sy;
+        sy = sy >= L.h ? 2 * L.h - 2 - sy : sy;
+        const uint8_t* row = img + (size_t)sy * pitch;
         unsigned t = 0;
-        for (int k = 0; k < 7; k++) t += (unsigned)g.gk[k] * row[reflect101(x + k - 3, L.w)];
+#pragma unroll
+        for (int k = 0; k < 7; k++) t += (unsigned)g.gk[k] * row[xs[k]];
         acc += (unsigned)g.gk[j] * t;
     }
     blur_ptr(g, b, f, l)[(size_t)y * L.pitch + x] = (uint8_t)(acc >> 16);

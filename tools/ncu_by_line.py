@@ -27,7 +27,8 @@ def main():
     rep, kernel, obj = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
     sl = sass_lines(obj, kernel)
-    csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kernel], capture_output=True, text=True).stdout
+    kernel_ncu = sys.argv[5] if len(sys.argv) > 5 else kernel
+    csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kernel_ncu], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(csvtxt)))
     hi = [i for i, r in enumerate(rows) if "# Samples" in r][0]
     hdr = rows[hi]; si = hdr.index("# Samples"); ie = hdr.index("Instructions Executed")
