@@ -166,45 +166,59 @@ __device__ __forceinline__ uint32_t ring_pair(const uint16_t* A, const uint16_t*
     return *reinterpret_cast<const uint32_t*>(base + (py + DY) * kFastP16 + col);
 }
 
-__device__ __forceinline__ uint32_t fast_score_pair(const uint16_t* A, const uint16_t* As, int py, int px)
+__device__ __forceinline__ uint32_t fast_score_pair(const uint16_t* A, const uint16_t* As, int py, int px, uint32_t negthr2)
 {
+    // min/max commute with the subtraction of the centre, so the whole network runs on the RAW ring values R[0..15] and the
+    // centre v enters once at the end:  score + 1 = max(v - T, S - v),  S = max_k min(R[k..k+8]),  T = min_k max(R[k..k+8]).
+    // Windows k = 2j and 2j+1 share R[2j+1..2j+8]; max(min(sh, a), min(sh, b)) = min(sh, max(a, b)), hence
+    //   S = max_j min(R[2j+1..2j+8], max(R[2j], R[2j+9])),  T = min_j max(R[2j+1..2j+8], min(R[2j], R[2j+9]))
+    // -> 36 packed min/max per polarity (the ALU pipe issues these at half rate, so their count is what bounds the kernel).
+    uint32_t R[16];
+    R[0] = ring_pair<0, 3>(A, As, py, px);    R[1] = ring_pair<1, 3>(A, As, py, px);
+    R[2] = ring_pair<2, 2>(A, As, py, px);    R[3] = ring_pair<3, 1>(A, As, py, px);
+    R[4] = ring_pair<3, 0>(A, As, py, px);    R[5] = ring_pair<3, -1>(A, As, py, px);
+    R[6] = ring_pair<2, -2>(A, As, py, px);   R[7] = ring_pair<1, -3>(A, As, py, px);
+    R[8] = ring_pair<0, -3>(A, As, py, px);   R[9] = ring_pair<-1, -3>(A, As, py, px);
+    R[10] = ring_pair<-2, -2>(A, As, py, px); R[11] = ring_pair<-3, -1>(A, As, py, px);
+    R[12] = ring_pair<-3, 0>(A, As, py, px);  R[13] = ring_pair<-3, 1>(A, As, py, px);
+    R[14] = ring_pair<-2, 2>(A, As, py, px);  R[15] = ring_pair<-1, 3>(A, As, py, px);
+    uint32_t pmin[8], pmax[8], xmin[8], xmax[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        pmin[j] = __vmins2(R[(2 * j + 1) & 15], R[(2 * j + 2) & 15]);
+        pmax[j] = __vmaxs2(R[(2 * j + 1) & 15], R[(2 * j + 2) & 15]);
+        xmin[j] = __vmins2(R[2 * j], R[(2 * j + 9) & 15]);
+        xmax[j] = __vmaxs2(R[2 * j], R[(2 * j + 9) & 15]);
+    }
+    uint32_t qmin[8], qmax[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { qmin[j] = __vmins2(pmin[j], pmin[(j + 1) & 7]); qmax[j] = __vmaxs2(pmax[j], pmax[(j + 1) & 7]); }
+    uint32_t ymin[8], ymax[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        ymin[j] = __vimin3_s16x2(qmin[j], qmin[(j + 2) & 7], xmax[j]);
+        ymax[j] = __vimax3_s16x2(qmax[j], qmax[(j + 2) & 7], xmin[j]);
+    }
+    uint32_t S = __vimax3_s16x2(ymin[0], ymin[1], ymin[2]), T = __vimin3_s16x2(ymax[0], ymax[1], ymax[2]);
+    S = __vimax3_s16x2(S, ymin[3], ymin[4]); T = __vimin3_s16x2(T, ymax[3], ymax[4]);
+    S = __vimax3_s16x2(S, ymin[5], ymin[6]); T = __vimin3_s16x2(T, ymax[5], ymax[6]);
+    S = __vmaxs2(S, ymin[7]); T = __vmins2(T, ymax[7]);
     const uint32_t vv = ring_pair<0, 0>(A, As, py, px);
-    const uint32_t nv = __vadd2(~vv, 0x00010001u);               // (-v0, -v1)
-    uint32_t e[16];
-    e[0] = __vadd2(ring_pair<0, 3>(A, As, py, px), nv);   e[1] = __vadd2(ring_pair<1, 3>(A, As, py, px), nv);
-    e[2] = __vadd2(ring_pair<2, 2>(A, As, py, px), nv);   e[3] = __vadd2(ring_pair<3, 1>(A, As, py, px), nv);
-    e[4] = __vadd2(ring_pair<3, 0>(A, As, py, px), nv);   e[5] = __vadd2(ring_pair<3, -1>(A, As, py, px), nv);
-    e[6] = __vadd2(ring_pair<2, -2>(A, As, py, px), nv);  e[7] = __vadd2(ring_pair<1, -3>(A, As, py, px), nv);
-    e[8] = __vadd2(ring_pair<0, -3>(A, As, py, px), nv);  e[9] = __vadd2(ring_pair<-1, -3>(A, As, py, px), nv);
-    e[10] = __vadd2(ring_pair<-2, -2>(A, As, py, px), nv); e[11] = __vadd2(ring_pair<-3, -1>(A, As, py, px), nv);
-    e[12] = __vadd2(ring_pair<-3, 0>(A, As, py, px), nv);  e[13] = __vadd2(ring_pair<-3, 1>(A, As, py, px), nv);
-    e[14] = __vadd2(ring_pair<-2, 2>(A, As, py, px), nv);  e[15] = __vadd2(ring_pair<-1, 3>(A, As, py, px), nv);
-    uint32_t lo3[16], hi3[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        lo3[k] = __vimin3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-        hi3[k] = __vimax3_s16x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-    }
-    uint32_t m9[16], M9[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        m9[k] = __vimin3_s16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-        M9[k] = __vimax3_s16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
-    }
-    // with e = -d:  max_k min9(d) = -min_k max9(e),  -min_k max9(d) = max_k min9(e)
-    uint32_t a = __vimax3_s16x2(m9[0], m9[1], m9[2]), bq = __vimin3_s16x2(M9[0], M9[1], M9[2]);
-#pragma unroll
-    for (int k = 3; k < 15; k += 2) { a = __vimax3_s16x2(a, m9[k], m9[k + 1]); bq = __vimin3_s16x2(bq, M9[k], M9[k + 1]); }
-    a = __vmaxs2(a, m9[15]); bq = __vmins2(bq, M9[15]);
-    const uint32_t negb = __vadd2(~bq, 0x00010001u);
-    return __vadd2(__vmaxs2(a, negb), 0xFFFFFFFFu);              // score = max(...) - 1 per half
+    const uint32_t m = __vmaxs2(__vsub2(vv, T), __vsub2(S, vv));            // score + 1 per half
+    // Returned BIASED: max(score - (thr - 1), 0), i.e. 0 for non-corners and an order-preserving positive value for corners
+    // (the NMS only compares; the emitter adds thr - 1 back)
+    return __vmaxs2(__vadd2(m, negthr2), 0u);
 }
+
+constexpr int kFastScP = 64;                      // score row pitch in PAIR words (two u16 scores per word; 61 used + 3 zeroed)
+constexpr size_t kFastSmemBytes = 2 * (size_t)kFastPH * kFastP16 * sizeof(uint16_t) + (size_t)kFastSH * kFastScP * sizeof(uint32_t);
 
 __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
-    __shared__ __align__(16) uint16_t A[kFastPH * kFastP16];
-    __shared__ __align__(16) uint16_t As[kFastPH * kFastP16];
-    __shared__ __align__(4) uint8_t sc[kFastSH * kFastPW];
+    extern __shared__ __align__(16) uint8_t fast_smem[];
+    uint16_t* A = reinterpret_cast<uint16_t*>(fast_smem);
+    uint16_t* As = A + kFastPH * kFastP16;
+    uint32_t* sc = reinterpret_cast<uint32_t*>(As + kFastPH * kFastP16);       // [kFastSH][kFastScP], scores as u16 pairs
     const int f = blockIdx.y;
     int l = 0;
     while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].fast_tile_base) l++;
@@ -215,12 +229,24 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     int pitch;
     const uint8_t* img = level_ptr(g, b, f, l, pitch);
 
-    // stage the pixel tile: 32-bit global loads (zero fill outside the image rows / pitch), widened to u16 twice
-    for (int i = threadIdx.x; i < kFastPH * (kFastPW / 4); i += blockDim.x) {
+    // stage the pixel tile: 32-bit global loads (zero fill outside the image rows / pitch), all issued before the first use,
+    // then widened to u16 twice
+    constexpr int kStageIters = kFastPH * (kFastPW / 4) / 256;
+    static_assert(kStageIters * 256 == kFastPH * (kFastPW / 4), "pixel tile must be a whole number of 256-thread passes");
+    uint32_t pv[kStageIters];
+#pragma unroll
+    for (int it = 0; it < kStageIters; it++) {
+        const int i = it * 256 + threadIdx.x;
         const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
         const int y = py0 + ry, x = px0 + rx;
-        uint32_t v = 0;
-        if (y >= 0 && y < L.h && x >= 0 && x + 4 <= pitch) v = *reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch + x);
+        pv[it] = 0;
+        if (y >= 0 && y < L.h && x >= 0 && x + 4 <= pitch) pv[it] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch + x));
+    }
+#pragma unroll
+    for (int it = 0; it < kStageIters; it++) {
+        const int i = it * 256 + threadIdx.x;
+        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
+        const uint32_t v = pv[it];
         const uint32_t p01 = __byte_perm(v, 0, 0x4140), p23 = __byte_perm(v, 0, 0x4342), p12 = __byte_perm(v, 0, 0x4241);
         uint16_t* a = A + ry * kFastP16 + rx;
         uint16_t* as = As + ry * kFastP16 + rx;
@@ -230,21 +256,25 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
         *reinterpret_cast<uint32_t*>(as) = p12;
         as[2] = (uint16_t)(v >> 24);
     }
-    __syncthreads();
-    const int thr = g.fast_threshold;
     constexpr int kPairs = kFastSW / 2;                          // 61 pairs per score row
-    for (int i = threadIdx.x; i < kFastSH * kPairs; i += blockDim.x) {
-        const int sy = i / kPairs, sx = (i - sy * kPairs) * 2;
-        const int x = px0 + 3 + sx, y = py0 + 3 + sy;
-        uint32_t out = 0;
-        if (y >= 3 && y <= L.h - 4 && x + 1 >= 3 && x <= L.w - 4) {
-            const uint32_t s2 = fast_score_pair(A, As, sy + 3, sx + 3);
-            int s0 = (int)(short)(s2 & 0xffff), s1 = (int)(short)(s2 >> 16);
-            s0 = (s0 >= thr && x >= 3) ? s0 : 0;                 // stored as uchar in the reference: 0 for non-corners
-            s1 = (s1 >= thr && x + 1 <= L.w - 4) ? s1 : 0;
-            out = (uint32_t)s0 | ((uint32_t)s1 << 8);
+    for (int i = threadIdx.x; i < kFastSH * (kFastScP - kPairs); i += blockDim.x)      // the unused tail pairs read as 0
+        sc[(i / (kFastScP - kPairs)) * kFastScP + kPairs + i % (kFastScP - kPairs)] = 0;
+    __syncthreads();
+    // scores: thread = (pair column, row phase); the column bounds become one hoisted mask and the row bounds loop limits
+    const int thr = g.fast_threshold;
+    {
+        const uint32_t thr2 = (uint32_t)thr | ((uint32_t)thr << 16), negthr2 = __vadd2(~thr2, 0x00010001u);
+        const int sp = threadIdx.x & (kFastScP - 1), r0 = threadIdx.x / kFastScP;          // 64 pair columns x 4 row phases
+        const int x = px0 + 3 + 2 * sp;
+        const uint32_t cmask = ((x >= 3 && x <= L.w - 4) ? 0x0000ffffu : 0u) | ((x + 1 >= 3 && x + 1 <= L.w - 4) ? 0xffff0000u : 0u);
+        const int sy_lo = max(0, -py0), sy_hi = min(kFastSH - 1, L.h - 7 - py0);           // rows with 3 <= y <= h - 4
+        if (sp < kPairs) {
+            for (int sy = r0; sy < kFastSH; sy += 256 / kFastScP) {
+                uint32_t out = 0;
+                if (cmask != 0 && sy >= sy_lo && sy <= sy_hi) out = fast_score_pair(A, As, sy + 3, 2 * sp + 3, negthr2) & cmask;
+                sc[sy * kFastScP + sp] = out;
+            }
         }
-        *reinterpret_cast<uint16_t*>(&sc[sy * kFastPW + sx]) = (uint16_t)out;
     }
     __syncthreads();
     const int bd = g.border;
@@ -254,24 +284,54 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     __shared__ int s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
-    // 4 score bytes per iteration (one aligned 32-bit shared load); the vast majority of words are all zero (non-corners)
-    for (int i = threadIdx.x; i < kFastOH * (kFastPW / 4); i += blockDim.x) {
-        const int oy = i / (kFastPW / 4), wx = (i - oy * (kFastPW / 4)) * 4;       // score-tile columns wx .. wx+3 of row oy+1
-        const uint32_t word = *reinterpret_cast<const uint32_t*>(&sc[(oy + 1) * kFastPW + wx]);
-        if (word == 0) continue;
-        const int y = py0 + 4 + oy;
-        if (y < bd || y >= L.h - bd) continue;
+    // strict 3x3 non-maximum suppression, 4 pixels (two pair words) per thread iteration in packed u16x2 arithmetic: the
+    // neighbourhood maximum of a pair is VIMNMX3 over funnel-shifted row words. Thread = (quad column, row phase): the border
+    // cull in x is one hoisted lane mask, in y the loop limits; quads without a corner leave after one 64-bit load. A warp is
+    // one row of quads and runs a uniform trip count, so survivors are appended with one shared atomic per warp iteration.
+    constexpr int kQuads = (kPairs + 1) / 2;                     // 31 quads per row (the last one half inside the zeroed tail)
+    static_assert(kQuads <= 32 && kFastOH % 8 == 0, "one warp per quad row, 8 row phases");
+    const int lane = threadIdx.x & 31, q = lane;
+    const int xq = px0 + 3 + 4 * q;                              // image column of quad pixel 0 (score column sx = 4q)
+    const int xlo = max(bd, px0 + 4), xhi = min(L.w - bd, px0 + 4 + kFastOW);     // keypoint columns of this tile inside the border
+    uint2 xmask;
+    xmask.x = ((xq >= xlo && xq < xhi) ? 0x0000ffffu : 0u) | ((xq + 1 >= xlo && xq + 1 < xhi) ? 0xffff0000u : 0u);
+    xmask.y = ((xq + 2 >= xlo && xq + 2 < xhi) ? 0x0000ffffu : 0u) | ((xq + 3 >= xlo && xq + 3 < xhi) ? 0xffff0000u : 0u);
+    if (q >= kQuads) xmask.x = xmask.y = 0;
+    const int oy_lo = max(0, bd - (py0 + 4)), oy_hi = min(kFastOH - 1, L.h - bd - 1 - (py0 + 4));
+    for (int oy = threadIdx.x >> 5; oy < kFastOH; oy += 8) {
+        if (oy < oy_lo || oy > oy_hi) continue;                  // warp-uniform
+        const uint32_t* row = sc + (oy + 1) * kFastScP + 2 * (q < kQuads ? q : 0);
+        const uint2 c = *reinterpret_cast<const uint2*>(row);
+        uint32_t keep = 0;                                       // bit 0 / 16 / 1 / 17 = pixel 0 / 1 / 2 / 3 of the quad survives
+        if (((c.x & xmask.x) | (c.y & xmask.y)) != 0) {
+            const uint2 u = *reinterpret_cast<const uint2*>(row - kFastScP), d = *reinterpret_cast<const uint2*>(row + kFastScP);
+            const uint32_t cp = row[-1], cn = row[2], up = row[-kFastScP - 1], un = row[-kFastScP + 2];
+            const uint32_t dp = row[kFastScP - 1], dn = row[kFastScP + 2];
+            const uint32_t c01 = __funnelshift_r(c.x, c.y, 16), u01 = __funnelshift_r(u.x, u.y, 16), d01 = __funnelshift_r(d.x, d.y, 16);
+            // pair 0 (pixels 0,1): left = (prev.hi, x.lo), right = (x.hi, y.lo); pair 1 (pixels 2,3): left = (x.hi, y.lo), right = (y.hi, next.lo)
+            uint32_t n0 = __vimax3_u16x2(__funnelshift_r(up, u.x, 16), u.x, u01);
+            n0 = __vimax3_u16x2(n0, __funnelshift_r(cp, c.x, 16), c01);
+            n0 = __vimax3_u16x2(n0, __vimax3_u16x2(__funnelshift_r(dp, d.x, 16), d.x, d01), n0);
+            uint32_t n1 = __vimax3_u16x2(u01, u.y, __funnelshift_r(u.y, un, 16));
+            n1 = __vimax3_u16x2(n1, c01, __funnelshift_r(c.y, cn, 16));
+            n1 = __vimax3_u16x2(n1, __vimax3_u16x2(d01, d.y, __funnelshift_r(d.y, dn, 16)), n1);
+            // v > n  <=>  max(v, n) != n; the differences are < 256 per half, so "+ 0xff >> 8" turns each half into its nonzero flag
+            const uint32_t g0 = __vmaxu2(c.x & xmask.x, n0) ^ n0, g1 = __vmaxu2(c.y & xmask.y, n1) ^ n1;
+            keep = (((g0 + 0x00ff00ffu) >> 8) & 0x00010001u) | (((g1 + 0x00ff00ffu) >> 7) & 0x00020002u);
+        }
+        if (__any_sync(0xffffffffu, keep != 0)) {
+            const int mine = __popc(keep);
+            int incl = mine;                                      // inclusive warp prefix sum of the survivor counts
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int v = (word >> (8 * j)) & 0xff;
-            const int sx = wx + j;                      // score column; keypoint column ox = sx - 1
-            if (v == 0 || sx < 1 || sx > kFastOW) continue;
-            const int x = px0 + 3 + sx;
-            if (x < bd || x >= L.w - bd) continue;
-            const uint8_t* s = &sc[(oy + 1) * kFastPW + sx];
-            const bool keep = v > s[-1] && v > s[1] && v > s[-kFastPW - 1] && v > s[-kFastPW] && v > s[-kFastPW + 1] &&
-                              v > s[kFastPW - 1] && v > s[kFastPW] && v > s[kFastPW + 1];
-            if (keep) list[atomicAdd(&s_n, 1)] = ((uint32_t)v << 24) | (uint32_t)(y * L.w + x);
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&s_n, incl);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+            const uint32_t pos = (uint32_t)((py0 + 4 + oy) * L.w + xq), bias = (uint32_t)(thr - 1);
+            if (keep & 0x00000001u) list[base++] = (((c.x & 0xffffu) + bias) << 24) | pos;
+            if (keep & 0x00010000u) list[base++] = (((c.x >> 16) + bias) << 24) | (pos + 1);
+            if (keep & 0x00000002u) list[base++] = (((c.y & 0xffffu) + bias) << 24) | (pos + 2);
+            if (keep & 0x00020000u) list[base++] = (((c.y >> 16) + bias) << 24) | (pos + 3);
         }
     }
     __syncthreads();
@@ -699,8 +759,10 @@ __device__ __forceinline__ void orient_moments(const uint8_t* center, int pitch,
             const int v = i - HP, av = v < 0 ? -v : v;
             val[i] = (au <= umax[av]) ? (int)center[v * pitch + u] : 0;
         }
+        int rowsum = 0;                                          // m10 = u * (column sum): one multiply per lane instead of one per row
 #pragma unroll
-        for (int i = 0; i < 2 * HP + 1; i++) { m10 += u * val[i]; m01 += (i - HP) * val[i]; }
+        for (int i = 0; i < 2 * HP + 1; i++) { rowsum += val[i]; m01 += (i - HP) * val[i]; }
+        m10 += u * rowsum;
     } else {
         for (int v = -hp; v <= hp; v++) {
             const int av = v < 0 ? -v : v;
@@ -717,12 +779,15 @@ __global__ void __launch_bounds__(256) k_orient_describe(const __grid_constant__
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // output slot of this warp
     const int* selCount = b.sel_count + f * kMaxLevels;
-    int total = 0, l = -1, j = 0;
-    for (int k = 0; k < g.nlevels; k++) {
-        int c = selCount[k];
-        if (l < 0 && i < total + c) { l = k; j = i - total; }
-        total += c;
-    }
+    // level of output slot i: one coalesced load of the per-level counts + a warp prefix sum (kMaxLevels = 16 <= warp)
+    const int cnt = lane < g.nlevels ? selCount[lane] : 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < kMaxLevels; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, kMaxLevels - 1);
+    const uint32_t lm = __ballot_sync(0xffffffffu, lane < g.nlevels && i < incl);
+    const int l = lm ? __ffs(lm) - 1 : -1;
+    const int j = i - __shfl_sync(0xffffffffu, incl - cnt, l < 0 ? 0 : l);
     if (i == 0 && lane == 0) out_counts[f] = min(total, capacity);
     if (l < 0 || i >= capacity) return;
     const LevelGeom& L = g.lv[l];
@@ -809,6 +874,8 @@ struct mage_orb_s {
     int last_n = 0;
     int stage_cap = 0;          // staging capacity per frame = max(nfeatures, sum of per-level budgets)
     cudaStream_t own_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;      // the blur runs here, concurrently with FAST + selection (it only feeds the descriptors)
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
 };
 
 namespace {
@@ -981,7 +1048,11 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     if (e == cudaSuccess) e = cudaMemcpy((void*)b.tab_coef, tcoef.data(), tab * sizeof(short2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((void*)b.pattern, pat.data(), pat.size(), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("mage_orb_create: %s", cudaGetErrorString(e)); A.release(); delete h; return MAGE_ERR_CUDA; }
     *out = h;
     return MAGE_OK;
@@ -991,6 +1062,9 @@ extern "C" void mage_orb_destroy(mage_orb_t h)
 {
     if (!h) return;
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
+    if (h->ev_blur) cudaEventDestroy(h->ev_blur);
     h->arena.release();
     delete h;
 }
@@ -1019,14 +1093,21 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
             k_resize<<<grid, block, 0, s>>>(g, bufs, l);
         }
     }
+    // fork: the blurred pyramid is only read by the descriptor stage, so it is produced on a second stream while FAST and the
+    // selection run on the caller's stream (when per-kernel timing is on, everything stays on one stream to keep the events clean)
+    const bool fork = g.ksize > 1 && !prof_enabled();
+    cudaStream_t sb = fork ? h->aux_stream : s;
+    if (fork) { MAGE_CUDA_TRY(cudaEventRecord(h->ev_pyr, s)); MAGE_CUDA_TRY(cudaStreamWaitEvent(sb, h->ev_pyr, 0)); }
     if (g.ksize == 7) {
-        ProfScope ps(PROF_BLUR, s);
-        k_blur7<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs);
-        k_blur7_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, s>>>(g, bufs);
+        ProfScope ps(PROF_BLUR, sb);
+        k_blur7<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+        k_blur7_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
     }
-    else if (g.ksize > 1) { ProfScope ps(PROF_BLUR, s); k_blur<<<dim3(h->blur_tiles, n), 256, 0, s>>>(g, bufs); }
-    { ProfScope ps(PROF_FAST, s); k_fast<<<dim3(h->fast_tiles, n), 256, 0, s>>>(g, bufs); }
+    else if (g.ksize > 1) { ProfScope ps(PROF_BLUR, sb); k_blur<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs); }
+    if (fork) MAGE_CUDA_TRY(cudaEventRecord(h->ev_blur, sb));
+    { ProfScope ps(PROF_FAST, s); k_fast<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs); }
     { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }
+    if (fork) MAGE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_blur, 0));
     { ProfScope ps(PROF_ORIENT_DESCRIBE, s); k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity); }
     MAGE_CUDA_TRY(cudaGetLastError());
     h->last_n = n;
