@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __res
 {
     __shared__ uint32_t tw[8][kChunk];          // train words, transposed: conflict-free lane-strided reads
     __shared__ uint32_t tx[kChunk];             // t0 ^ t1 ^ t2 per train
+    __shared__ uint32_t t01s[kChunk];           // t0 ^ t1 per train
     __shared__ uint8_t tvalid[kChunk];
     __shared__ uint32_t qw[kQPerBlock][8];
     const int pair = blockIdx.y;
@@ -70,13 +71,14 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __res
         qw[i >> 3][i & 7] = (q < nQ) ? Q[(size_t)q * 8 + (i & 7)] : 0u;
     }
     __syncthreads();
-    uint32_t q[kQPerWarp][3], qx[kQPerWarp];
+    uint32_t q[kQPerWarp][3], qx[kQPerWarp], q01[kQPerWarp];
     bool qok[kQPerWarp];
 #pragma unroll
     for (int k = 0; k < kQPerWarp; k++) {
         const int qi = q0 + warp * kQPerWarp + k;
         q[k][0] = qw[warp * kQPerWarp + k][0]; q[k][1] = qw[warp * kQPerWarp + k][1]; q[k][2] = qw[warp * kQPerWarp + k][2];
         qx[k] = q[k][0] ^ q[k][1] ^ q[k][2];
+        q01[k] = q[k][0] ^ q[k][1];
         qok[k] = qi < nQ && (!mQ || mQ[qi]);
     }
     for (int c0 = 0; c0 < nT; c0 += kChunk) {
@@ -87,28 +89,36 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __res
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (t < nT) v = T4[(size_t)t * 2 + half];
             tw[half * 4 + 0][tl] = v.x; tw[half * 4 + 1][tl] = v.y; tw[half * 4 + 2][tl] = v.z; tw[half * 4 + 3][tl] = v.w;
-            if (half == 0) { tx[tl] = v.x ^ v.y ^ v.z; tvalid[tl] = (t < nT && (!mT || mT[t])) ? 1 : 0; }
+            if (half == 0) { tx[tl] = v.x ^ v.y ^ v.z; t01s[tl] = v.x ^ v.y; tvalid[tl] = (t < nT && (!mT || mT[t])) ? 1 : 0; }
         }
         __syncthreads();
         // filter pass: branch-free over the lane's 8 trains x 4 queries (32 pairs), survivors recorded in a bit mask
+        static_assert(kChunk / 32 * kQPerWarp == 32, "one hit bit per (train, query) evaluation");
         unsigned hits = 0;
 #pragma unroll
         for (int i = 0; i < kChunk / 32; i++) {
             const int ti = lane + 32 * i;
-            const uint32_t t0 = tw[0][ti], t1 = tw[1][ti], t2 = tw[2][ti], txx = tx[ti];
+            const uint32_t t0 = tw[0][ti], t2 = tw[2][ti], t01 = t01s[ti], txx = tx[ti];
 #pragma unroll
             for (int k = 0; k < kQPerWarp; k++) {
-                const uint32_t x0 = q[k][0] ^ t0, x1 = q[k][1] ^ t1, x2 = q[k][2] ^ t2;
-                const uint32_t twos = (x0 & x1) | (x2 & (x0 | x1));
-                const int d3 = __popc(qx[k] ^ txx) + 2 * __popc(twos);
-                hits |= (d3 <= max_hamming) ? (1u << (i * kQPerWarp + k)) : 0u;
+                // maj(x0, x1, x2) = (x0 != x1) ? x2 : x0, with x0 ^ x1 = (q0 ^ q1) ^ (t0 ^ t1) from precomputed halves:
+                // 4 LOP3 for the carry word + 1 for the sum word (xor/popc saturate the half-rate ALU pipe; every LOP3 counts)
+                const uint32_t u = q01[k] ^ t01, x0 = q[k][0] ^ t0, x2 = q[k][2] ^ t2;
+                const uint32_t twos = (u & x2) | (~u & x0);
+                // the sign of (maxHamming - d96) is shifted in with one funnel shift (ALU pipe) and the subtraction is left to
+                // IMADs (FMA pipe): xor/popc saturate the half-rate ALU pipe, so a compare + select there costs real time
+                int slack;
+                asm("mad.lo.s32 %0, %1, -2, %2;" : "=r"(slack) : "r"(__popc(twos)), "r"(max_hamming));
+                asm("mad.lo.s32 %0, %1, -1, %2;" : "=r"(slack) : "r"(__popc(qx[k] ^ txx)), "r"(slack));
+                hits = __funnelshift_l((unsigned)slack, hits, 1);           // reject bit of evaluation n ends up at bit 31 - n
             }
         }
+        hits = ~hits;
         // survivors (about 1e-4 of random pairs, plus the true matches): exact distance, then the four packed updates
         while (hits) {
             const int bit = __ffs(hits) - 1;
             hits &= hits - 1;
-            const int i = bit / kQPerWarp, k = bit % kQPerWarp;
+            const int n = 31 - bit, i = n / kQPerWarp, k = n % kQPerWarp;
             const int ti = lane + 32 * i;
             if (!tvalid[ti] || !qok[k]) continue;
             const int ql = warp * kQPerWarp + k;
