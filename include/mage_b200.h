@@ -161,6 +161,43 @@ int  mage_radius_match(mage_spatial_index_t ix, const mage_keypoint* query_kps, 
                        const uint8_t* target_desc, float radius, int max_hamming, int min_hamming_diff,
                        mage_dmatch* out, int* count, void* cuda_stream);
 
+/* ------------------------------------------------------------------- Map-point projection + candidate culling */
+
+/* One local-map point as TrackLocalMap reads it through its proxy (ref Tracking/TrackLocalMap.cpp:519-554):
+ * GetPosition(), GetMeanViewingDirection() (unit length), GetDMin(), GetDMax(). 32 bytes. */
+typedef struct {
+    float position[3];
+    float mean_view_dir[3];
+    float dmin, dmax;
+} mage_map_point;
+
+typedef struct {
+    float view[12];              /* cv::Matx34f, row-major: Pose::GetViewMatrix() (ref TrackLocalMap.cpp:167) */
+    float fx, fy, cx, cy;        /* calibration(0,0), (1,1), (0,2), (1,2) (ref Tracking/Reprojection.cpp:35-40) */
+    float frame_position[3];     /* Pose::GetWorldSpacePosition() (ref TrackLocalMap.cpp:152) */
+    float frame_forward[3];      /* Pose::GetWorldSpaceForward(), unit length (ref TrackLocalMap.cpp:153) */
+    float min_cos_view_angle;    /* std::cos(mira::deg2rad(MinDegreesBetweenCurrentViewAndMapPointView)) (ref :541) */
+    float image_border;          /* AnalyzedImage::GetImageBorder() */
+    uint32_t width, height;      /* AnalyzedImage::GetWidth()/GetHeight() */
+    float pyramid_scale;         /* AnalyzedImage::GetPyramidScale() */
+    uint32_t num_levels;         /* AnalyzedImage::GetNumLevels() */
+} mage_projection_params;
+
+enum { MAGE_PROJ_GOOD_CANDIDATE = 1,   /* IsGoodCandidate() returned true */
+       MAGE_PROJ_PREDICTED = 2 };      /* ... and the predicted octave is inside [0, num_levels]: `predicted` of ref :360 */
+
+/* For every map point: ProjectUndistorted (ref Tracking/Reprojection.cpp:26-43) -> IsGoodCandidate (ref
+ * Tracking/TrackLocalMap.cpp:519-554) -> ComputeOctave (ref Map/MappingMath.h:13-16), i.e. the part of
+ * TrackLocalMap::ProjectMapPointIntoCurrentFrame (ref :325-388) that precedes the RadiusMatch call. out_kps[i] is the
+ * cv::KeyPoint(projected.Point, -1, 0, 0, octave, -1) the reference passes to RadiusMatch (octave is 0 unless the point is
+ * a good candidate); out_depth[i] (nullable) is Projection::Distance; out_flags[i] is a MAGE_PROJ_* bit set. Also covers
+ * ProjectPoints (ref Reprojection.cpp:16-24): read out_kps[i].x/.y and out_depth[i], ignore the flags.
+ * Host buffers, synchronous; the _device variant takes device pointers and only enqueues on cuda_stream. */
+int  mage_project_map_points(const mage_projection_params* params, const mage_map_point* points, int n, mage_keypoint* out_kps,
+                             float* out_depth, uint8_t* out_flags, void* cuda_stream);
+int  mage_project_map_points_device(const mage_projection_params* params, const mage_map_point* d_points, int n,
+                                    mage_keypoint* d_out_kps, float* d_out_depth, uint8_t* d_out_flags, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------- Front-end for a video stream */
 
 /* ORB extract of a batch of frames + Match of every frame (query) against its predecessor (train): the reference's

@@ -73,6 +73,8 @@ def lib():
     L.mage_spatial_index_destroy.restype = None
     L.mage_spatial_index_rank.argtypes = [vp, vp]
     L.mage_radius_match.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, cf, ci, ci, vp, C.POINTER(ci), vp]
+    L.mage_project_map_points.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    L.mage_project_map_points_device.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     if hasattr(L, "mage_ba_create"):
         L.mage_ba_create.argtypes = [ci, C.POINTER(vp)]
         L.mage_ba_destroy.argtypes = [vp]

@@ -194,3 +194,41 @@ def ba_problem(K=10, P=2000, obs_per_point=4, seed=1, n_fixed=2, f=500.0, cx=320
                 points=pts_init.astype(np.float32), obs_uv=obs_uv[:E].astype(np.float32),
                 obs_cam=obs_cam[:E].copy(), obs_pt=obs_pt[:E].copy(), obs_info=info,
                 true_points=pts.astype(np.float32))
+
+
+def local_map_scene(n=4000, seed=0, width=640, height=480, scale=1.2, levels=8):
+    """A tracking-thread scene for the map-point projection step: a camera pose (view matrix, calibration, position, forward)
+    and n local-map points scattered so that every culling branch of IsGoodCandidate fires (behind the camera, outside the
+    image border, viewing angle, scale-invariance range, octave out of range). Returns a dict of float32 arrays."""
+    rng = np.random.default_rng(seed)
+    ang = rng.normal(0, 0.2, 3)
+    cx, sx, cy, sy, cz, sz = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]]); Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]); Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    R = (Rz @ Ry @ Rx)                       # world -> camera
+    C = rng.normal(0, 0.5, 3)                 # camera centre (world)
+    view = np.concatenate([R, (-R @ C)[:, None]], axis=1).astype(np.float32)
+    K = np.array([[520.0, 0, width / 2 + 3.5], [0, 515.0, height / 2 - 2.25], [0, 0, 1]], np.float32)
+    forward = (R.T @ np.array([0, 0, 1.0])).astype(np.float32)
+    forward /= np.linalg.norm(forward)
+    # points in camera space: mostly in front within the frustum, some behind / outside
+    z = rng.uniform(-2.0, 12.0, n)
+    z[np.abs(z) < 0.05] = 0.5
+    x = rng.uniform(-0.85, 0.85, n) * np.abs(z)
+    y = rng.uniform(-0.65, 0.65, n) * np.abs(z)
+    Pc = np.stack([x, y, z], axis=1)
+    Pw = (R.T @ Pc.T).T + C
+    dist = np.linalg.norm(Pw - C, axis=1)
+    # mean viewing direction: from a previous observer roughly along the current ray, perturbed up to ~90 degrees
+    ray = (Pw - C) / np.maximum(dist[:, None], 1e-6)
+    d = ray + rng.normal(0, 0.6, (n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # scale-invariance range: observed at octave o at distance d0 ~ dist * jitter
+    o = rng.integers(0, levels, n)
+    d0 = dist * rng.uniform(0.4, 2.5, n)
+    dmin = d0 * np.power(scale, -(o + 0.5))
+    dmax = d0 * np.power(scale, levels - (o + 0.5))
+    pts = np.zeros(n, np.dtype([("position", "<f4", 3), ("mean_view_dir", "<f4", 3), ("dmin", "<f4"), ("dmax", "<f4")]))
+    pts["position"] = Pw.astype(np.float32); pts["mean_view_dir"] = d.astype(np.float32)
+    pts["dmin"] = dmin.astype(np.float32); pts["dmax"] = dmax.astype(np.float32)
+    return dict(view=view, K=K, position=C.astype(np.float32), forward=forward, points=pts, width=width, height=height,
+                scale=scale, levels=levels)

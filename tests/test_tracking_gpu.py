@@ -1,0 +1,108 @@
+"""GPU parity of the map-point projection step (mage_project_map_points) against the oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+from mageslam_b200 import synth
+from mageslam_b200.tracking import (MAP_POINT_DTYPE, PROJ_GOOD_CANDIDATE, PROJ_PREDICTED, ProjectMapPoints, ProjectMapPointsDevice,
+                                    ProjectPoints, make_params)
+from mageslam_b200._lib import KEYPOINT_DTYPE
+
+from tests import oracle_tracking as ot
+
+pytestmark = pytest.mark.gpu
+
+
+def scene_params(sc, angle=60.0, border=16.0):
+    return make_params(sc["view"], sc["K"], sc["position"], sc["forward"], angle, border, sc["width"], sc["height"], sc["scale"], sc["levels"])
+
+
+def check_against_oracle(sc, p, kps, depth, flags):
+    okps, odepth, oflags = ot.project_map_points(p, sc["points"])
+    # projection, depth and the IsGoodCandidate verdict are pure IEEE f32 in a fixed order: bit-exact
+    assert np.array_equal(kps["x"].view(np.uint32), okps["x"].view(np.uint32))
+    assert np.array_equal(kps["y"].view(np.uint32), okps["y"].view(np.uint32))
+    assert np.array_equal(depth.view(np.uint32), odepth.view(np.uint32))
+    assert np.array_equal(flags & PROJ_GOOD_CANDIDATE, oflags & PROJ_GOOD_CANDIDATE)
+    for name in ("size", "angle", "response", "class_id"):
+        assert np.array_equal(kps[name], okps[name])
+    # the octave goes through log2f (CUDA's vs the host libm's, both <= 1 ulp): it may only differ when the pre-rounding
+    # value sits within 2e-6 of a rounding boundary (x.5)
+    bad = np.flatnonzero((kps["octave"] != okps["octave"]) | (flags != oflags))
+    for i in bad:
+        m = sc["points"][i]
+        d = np.linalg.norm(m["position"].astype(np.float64) - sc["position"].astype(np.float64))
+        t = ot.octave_real(d, m["dmin"], sc["scale"])
+        assert abs((t - np.floor(t)) - 0.5) < 2e-6, "octave differs away from a rounding boundary at point %d" % i
+    assert len(bad) <= max(1, len(kps) // 10000)
+    return len(bad)
+
+
+@pytest.mark.parametrize("seed,n", [(0, 4000), (7, 257), (11, 1)])
+def test_project_map_points_equals_oracle(seed, n):
+    sc = synth.local_map_scene(n, seed=seed)
+    p = scene_params(sc)
+    kps, depth, flags = ProjectMapPoints(p, sc["points"])
+    check_against_oracle(sc, p, kps, depth, flags)
+    if n > 1000:
+        assert ((flags & PROJ_PREDICTED) != 0).sum() > 100
+
+
+def test_other_settings_and_full_size():
+    # BASELINE-size local map: 200k points in one call, default tracking angle and a 1280x720 frame
+    sc = synth.local_map_scene(200000, seed=21, width=1280, height=720, scale=1.5, levels=4)
+    p = scene_params(sc, angle=45.0, border=31.0)
+    kps, depth, flags = ProjectMapPoints(p, sc["points"])
+    check_against_oracle(sc, p, kps, depth, flags)
+
+
+def test_device_variant_and_empty():
+    import torch
+    sc = synth.local_map_scene(1000, seed=3)
+    p = scene_params(sc)
+    kps0, depth0, flags0 = ProjectMapPoints(p, sc["points"][:0])
+    assert len(kps0) == 0
+    d_pts = torch.from_numpy(sc["points"].view(np.uint8).reshape(-1, 32)).cuda()
+    d_kps = torch.zeros((1000, 28), dtype=torch.uint8, device="cuda")
+    d_depth = torch.zeros(1000, dtype=torch.float32, device="cuda")
+    d_flags = torch.zeros(1000, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    ProjectMapPointsDevice(p, d_pts, d_kps, d_depth, d_flags, 1000, s)
+    s.synchronize()
+    kps = d_kps.cpu().numpy().view(KEYPOINT_DTYPE).reshape(-1)
+    check_against_oracle(sc, p, kps, d_depth.cpu().numpy(), d_flags.cpu().numpy())
+
+
+def test_project_points_mirror():
+    sc = synth.local_map_scene(500, seed=9)
+    pts2d, depth = ProjectPoints(sc["points"]["position"], sc["view"], sc["K"])
+    p = scene_params(sc)
+    okps, odepth, _ = ot.project_map_points(p, sc["points"])
+    assert np.array_equal(pts2d[:, 0], okps["x"]) and np.array_equal(pts2d[:, 1], okps["y"]) and np.array_equal(depth, odepth)
+
+
+def test_feeds_radius_match():
+    """The projected keypoints are valid RadiusMatch queries: end to end against the oracle's RadiusMatch."""
+    from mageslam_b200.matcher import KeypointSpatialIndex, RadiusMatch
+    from tests import oracle_orb as orc
+    rng = np.random.default_rng(2)
+    sc = synth.local_map_scene(1500, seed=13)
+    p = scene_params(sc)
+    kps, depth, flags = ProjectMapPoints(p, sc["points"])
+    pred = ((flags & PROJ_PREDICTED) != 0).astype(np.uint8)
+    # current-frame keypoints scattered around the projections, random octaves / descriptors
+    nt = 1800
+    tk = np.zeros(nt, KEYPOINT_DTYPE)
+    src = rng.integers(0, len(kps), nt)
+    tk["x"] = kps["x"][src] + rng.normal(0, 4, nt).astype(np.float32)
+    tk["y"] = kps["y"][src] + rng.normal(0, 4, nt).astype(np.float32)
+    tk["octave"] = np.clip(kps["octave"][src] + rng.integers(-1, 2, nt), 0, 7)
+    qdesc = rng.integers(0, 256, (len(kps), 32), dtype=np.uint8)
+    tdesc = qdesc[src].copy()
+    flip = rng.integers(0, 256, (nt, 3))
+    for j in range(3):
+        tdesc[np.arange(nt), flip[:, j] // 8] ^= (1 << (flip[:, j] % 8)).astype(np.uint8)
+    ix = KeypointSpatialIndex(tk)
+    got = RadiusMatch(kps, None, pred, qdesc, ix, None, tdesc, 8.0, 50, 2)
+    want = orc.radius_match(kps.astype(orc.KP_DTYPE), qdesc, tk.astype(orc.KP_DTYPE), tdesc, 8.0, 50, 2, qmask=pred)
+    assert len(got) == len(want) and len(got) > 50
+    assert np.array_equal(got["query_idx"], want["query"]) and np.array_equal(got["train_idx"], want["train"])
