@@ -140,6 +140,18 @@ int  mage_matcher_set_jobs_device(mage_matcher_t m, const uint8_t* d_desc, const
 int  mage_match_run_jobs(mage_matcher_t m, int first_pair, int n_pairs, int max_hamming, int min_hamming_diff,
                          mage_dmatch* d_matches, int capacity, int* d_match_counts, void* cuda_stream);
 
+/* IndexedMatch (ref Tracking/FeatureMatcher.h:30-45, .cpp:192-268): the vocabulary-gated two-way match used for new map
+ * point creation and loop closure. The BoW lookups stay with the caller (BaseBow::QueryFeatures(desc, keyframeId, closeMatches)
+ * / BaseFeatureMatcher::QueryFeatures, ref .cpp:222-229, :251-258): their results arrive as CSR candidate lists, in the order
+ * QueryFeatures returned them -- a2b_offsets[nA + 1] / a2b_candidates (indices into B) for every A feature, b2a_offsets[nB + 1] /
+ * b2a_candidates (indices into A) for every B feature (only the lists of B features that end up matched are consulted, as
+ * in the reference). Masks may be NULL (= all true). out needs room for nA matches (ascending query index = ref order).
+ * Host buffers, synchronous. */
+int  mage_indexed_match(mage_matcher_t m, const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_t* descB, int nB,
+                        const uint8_t* maskB, const int* a2b_offsets, const int* a2b_candidates, const int* b2a_offsets,
+                        const int* b2a_candidates, int max_hamming, int min_hamming_diff, mage_dmatch* out, int* count,
+                        void* cuda_stream);
+
 /* GetDescriptorDistance for n pairs of device-resident descriptors (a[i] vs b[i]) -> d_out[i]. */
 int  mage_descriptor_distance_device(const uint8_t* d_a, const uint8_t* d_b, int n, int* d_out, void* cuda_stream);
 

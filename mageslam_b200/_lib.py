@@ -68,6 +68,7 @@ def lib():
     L.mage_match_bf.argtypes = [vp, vp, ci, vp, vp, ci, vp, ci, ci, vp, C.POINTER(ci), vp]
     L.mage_match_bf_device.argtypes = [vp, vp, vp, sz, vp, vp, ci, ci, ci, vp, ci, vp, vp]
     L.mage_descriptor_distance_device.argtypes = [vp, vp, ci, vp, vp]
+    L.mage_indexed_match.argtypes = [vp, vp, ci, vp, vp, ci, vp, vp, vp, vp, vp, ci, ci, vp, C.POINTER(ci), vp]
     L.mage_spatial_index_create.argtypes = [vp, ci, C.POINTER(vp)]
     L.mage_spatial_index_destroy.argtypes = [vp]
     L.mage_spatial_index_destroy.restype = None

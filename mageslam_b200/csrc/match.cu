@@ -184,6 +184,58 @@ __global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__
     if (threadIdx.x == 0) out_count[pair] = min(base, out_cap);
 }
 
+// IndexedMatch (ref Tracking/FeatureMatcher.cpp:192-268): the candidate sets come from the vocabulary (BoW node lists, the
+// caller's business) instead of the whole image, as CSR lists. One warp per query descriptor and direction (blockIdx.y:
+// 0 = A -> B over a2b, 1 = B -> A over b2a); lanes stride over the list with the exact 256-bit distance. TrackMatch
+// (ref :28-56) keeps the true smallest and second smallest distance below maxHamming, the best being the FIRST list entry
+// with the smallest distance: key = distance << 22 | list position. The stats land in the layout k_match_emit resolves
+// (min-difference test, B -> A best must point back to a, ascending-a emission) -- the reference's second loop evaluates
+// B -> A only for matched b's, but its result for a given b does not depend on which a asked.
+__global__ void __launch_bounds__(256) k_indexed_best(const MatchJob* __restrict__ jobs, const int* __restrict__ off0, const int* __restrict__ cand0,
+                                                      const int* __restrict__ off1, const int* __restrict__ cand1, unsigned* __restrict__ stats,
+                                                      int stride, int max_hamming)
+{
+    const MatchJob& job = jobs[0];
+    const int dir = blockIdx.y;
+    const int nQ = job_count(job, dir), nT = job_count(job, 1 - dir);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (q >= nQ) return;
+    const uint8_t* mQ = job.mask[dir];
+    const uint8_t* mT = job.mask[1 - dir];
+    if (mQ && !mQ[q]) return;                                   // stats stay kNoKey
+    const uint4* Q4 = reinterpret_cast<const uint4*>(job.desc[dir]) + (size_t)q * 2;
+    const uint4* T4 = reinterpret_cast<const uint4*>(job.desc[1 - dir]);
+    const uint4 qa = __ldg(Q4), qb = __ldg(Q4 + 1);
+    const int* off = dir == 0 ? off0 : off1;
+    const int* cand = dir == 0 ? cand0 : cand1;
+    const int beg = off[q], end = off[q + 1];
+    const unsigned inf = (unsigned)(max_hamming + 1);
+    unsigned bd = inf, sd = inf, bpos = 0, bidx = 0;
+    for (int j = beg + lane; j < end; j += 32) {
+        const int t = cand[j];
+        if (t < 0 || t >= nT || (mT && !mT[t])) continue;
+        const uint4 ta = __ldg(T4 + (size_t)t * 2), tb = __ldg(T4 + (size_t)t * 2 + 1);
+        const unsigned d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w) +
+                           __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+        if (d < bd) { sd = bd; bd = d; bpos = (unsigned)(j - beg); bidx = (unsigned)t; }
+        else if (d < sd) sd = d;
+    }
+    unsigned key = (bd << 22) | min(bpos, 0x3FFFFFu);          // lists longer than 4M entries are rejected on the host
+    unsigned kmin = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    if ((kmin >> 22) >= inf) return;                            // no candidate below maxHamming
+    const bool winner = key == kmin && bd < inf;
+    unsigned second = winner ? sd : bd;                         // everyone else's best competes for second place
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) second = min(second, __shfl_xor_sync(0xffffffffu, second, o));
+    if (winner) {
+        stats[((size_t)(2 * dir) + 0) * stride + q] = (bd << 16) | bidx;
+        stats[((size_t)(2 * dir) + 1) * stride + q] = second >= inf ? kNoKey : (second << 16);
+    }
+}
+
 __global__ void k_desc_distance(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int n, int* __restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,6 +392,62 @@ extern "C" int mage_match_bf_device(mage_matcher_t m, const uint8_t* d_desc, con
     int rc = mage_matcher_set_jobs_device(m, d_desc, d_counts, slot_stride, a_index, b_index, n_pairs);
     if (rc != MAGE_OK) return rc;
     return mage_match_run_jobs(m, 0, n_pairs, max_hamming, min_diff, d_matches, capacity, d_match_counts, stream);
+}
+
+extern "C" int mage_indexed_match(mage_matcher_t m, const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_t* descB, int nB,
+                                  const uint8_t* maskB, const int* a2b_offsets, const int* a2b_candidates, const int* b2a_offsets,
+                                  const int* b2a_candidates, int max_hamming, int min_diff, mage_dmatch* out, int* count, void* stream)
+{
+    MAGE_REQUIRE(m && count && out, MAGE_ERR_INVALID, "mage_indexed_match: null argument");
+    MAGE_REQUIRE(nA >= 0 && nB >= 0 && nA <= m->max_desc && nB <= m->max_desc, MAGE_ERR_INVALID, "descriptor count exceeds matcher capacity %d", m->max_desc);
+    *count = 0;
+    if (nA == 0 || nB == 0) return MAGE_OK;                     // ref :208: imageAMaskCount == 0 || imageBMaskCount == 0
+    MAGE_REQUIRE(descA && descB && a2b_offsets && b2a_offsets, MAGE_ERR_INVALID, "mage_indexed_match: null descriptors / offsets");
+    MAGE_REQUIRE(max_hamming >= 0 && max_hamming <= 256, MAGE_ERR_INVALID, "mage_indexed_match: max_hamming outside 0..256");
+    const int nab = a2b_offsets[nA], nba = b2a_offsets[nB];
+    MAGE_REQUIRE(a2b_offsets[0] == 0 && b2a_offsets[0] == 0 && nab >= 0 && nba >= 0, MAGE_ERR_INVALID, "mage_indexed_match: malformed CSR offsets");
+    for (int i = 0; i < nA; i++) MAGE_REQUIRE(a2b_offsets[i + 1] >= a2b_offsets[i] && a2b_offsets[i + 1] - a2b_offsets[i] < (1 << 22), MAGE_ERR_INVALID, "mage_indexed_match: a2b offsets must ascend, lists < 4M entries");
+    for (int i = 0; i < nB; i++) MAGE_REQUIRE(b2a_offsets[i + 1] >= b2a_offsets[i] && b2a_offsets[i + 1] - b2a_offsets[i] < (1 << 22), MAGE_ERR_INVALID, "mage_indexed_match: b2a offsets must ascend, lists < 4M entries");
+    MAGE_REQUIRE((nab == 0 || a2b_candidates) && (nba == 0 || b2a_candidates), MAGE_ERR_INVALID, "mage_indexed_match: null candidate list");
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->own_stream;
+    const size_t N = (size_t)m->max_desc;
+    uint8_t* dA = m->d_stage; uint8_t* dB = dA + N * 32; uint8_t* dmA = dB + N * 32; uint8_t* dmB = dmA + N;
+    mage_dmatch* dOut = reinterpret_cast<mage_dmatch*>(m->d_stage + align_up(N * 66, 256));
+    int* dCnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(dOut) + sizeof(mage_dmatch) * N);
+    // candidate lists are per call and of arbitrary size: stream-ordered scratch
+    int* d_csr = nullptr;
+    const size_t n_csr = (size_t)(nA + 1) + (size_t)(nB + 1) + (size_t)nab + (size_t)nba;
+    MAGE_CUDA_TRY(cudaMallocAsync(&d_csr, sizeof(int) * n_csr, s));
+    int* d_off0 = d_csr; int* d_off1 = d_off0 + nA + 1; int* d_c0 = d_off1 + nB + 1; int* d_c1 = d_c0 + nab;
+    cudaError_t e = cudaMemcpyAsync(dA, descA, (size_t)nA * 32, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dB, descB, (size_t)nB * 32, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && maskA) e = cudaMemcpyAsync(dmA, maskA, nA, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && maskB) e = cudaMemcpyAsync(dmB, maskB, nB, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off0, a2b_offsets, sizeof(int) * (nA + 1), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off1, b2a_offsets, sizeof(int) * (nB + 1), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && nab) e = cudaMemcpyAsync(d_c0, a2b_candidates, sizeof(int) * nab, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && nba) e = cudaMemcpyAsync(d_c1, b2a_candidates, sizeof(int) * nba, cudaMemcpyHostToDevice, s);
+    m->memo_desc = nullptr; m->memo_a.clear(); m->memo_b.clear();
+    MatchJob& j = m->h_jobs[0];
+    j.desc[0] = dA; j.desc[1] = dB; j.mask[0] = maskA ? dmA : nullptr; j.mask[1] = maskB ? dmB : nullptr;
+    j.count_ptr[0] = j.count_ptr[1] = nullptr; j.count[0] = nA; j.count[1] = nB; j.cap = m->max_desc;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_jobs, m->h_jobs, sizeof(MatchJob), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->d_best, 0xFF, sizeof(unsigned) * 4 * (size_t)m->max_desc, s);
+    if (e == cudaSuccess) {
+        const int nmax = nA > nB ? nA : nB;
+        k_indexed_best<<<dim3(div_up(nmax, 8), 2), 256, 0, s>>>(m->d_jobs, d_off0, d_c0, d_off1, d_c1, m->d_best, m->max_desc, max_hamming);
+        k_match_emit<<<1, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, min_diff, dOut, m->max_desc, dCnt);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->h_count, dCnt, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(m->h_out, dOut, sizeof(mage_dmatch) * (size_t)nA, cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(d_csr, s);
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = e2;
+    MAGE_CUDA_TRY(e);
+    *count = *m->h_count;
+    memcpy(out, m->h_out, sizeof(mage_dmatch) * (size_t)(*count));
+    return MAGE_OK;
 }
 
 extern "C" int mage_descriptor_distance_device(const uint8_t* d_a, const uint8_t* d_b, int n, int* d_out, void* stream)

@@ -51,12 +51,42 @@ class Matcher:
                                   int(maxHammingDist), int(minHammingDifference), ptr(out), C.byref(cnt), None))
         return out[:cnt.value]
 
+    def IndexedMatch(self, closeMatchesAtoB, closeMatchesBtoA, descA, descB, maskA=None, maskB=None, maxHammingDist=30,
+                     minHammingDifference=1):
+        """Mirror of IndexedMatch (reference Tracking/FeatureMatcher.h:30-45, .cpp:192-268). closeMatchesAtoB[i] is what
+        QueryFeatures(descA[i], idB / matcherB) returned (indices into B, in that order), closeMatchesBtoA[j] likewise for
+        descB[j]; either a list of index lists or a CSR pair (offsets int32[n+1], candidates int32[...])."""
+        descA = np.ascontiguousarray(descA, np.uint8).reshape(-1, 32)
+        descB = np.ascontiguousarray(descB, np.uint8).reshape(-1, 32)
+        nA, nB = len(descA), len(descB)
+        o0, c0 = _as_csr(closeMatchesAtoB, nA)
+        o1, c1 = _as_csr(closeMatchesBtoA, nB)
+        maskA = None if maskA is None else np.ascontiguousarray(maskA, np.uint8)
+        maskB = None if maskB is None else np.ascontiguousarray(maskB, np.uint8)
+        out = np.zeros(max(nA, 1), DMATCH_DTYPE)
+        cnt = C.c_int(0)
+        check(lib().mage_indexed_match(self._h, ptr(descA) if nA else None, nA, ptr(maskA), ptr(descB) if nB else None, nB, ptr(maskB),
+                                       ptr(o0), ptr(c0) if len(c0) else None, ptr(o1), ptr(c1) if len(c1) else None,
+                                       int(maxHammingDist), int(minHammingDifference), ptr(out), C.byref(cnt), None))
+        return out[:cnt.value]
+
     def MatchDevice(self, d_desc, d_counts, slot_stride, a_index, b_index, d_matches, capacity, d_match_counts,
                     maxHammingDist=30, minHammingDifference=1, stream=None):
         a_index = np.ascontiguousarray(a_index, np.int32); b_index = np.ascontiguousarray(b_index, np.int32)
         check(lib().mage_match_bf_device(self._h, ptr(d_desc), ptr(d_counts), int(slot_stride), ptr(a_index), ptr(b_index), len(a_index),
                                          int(maxHammingDist), int(minHammingDifference), ptr(d_matches), int(capacity),
                                          ptr(d_match_counts), stream_ptr(stream)))
+
+
+def _as_csr(lists, n):
+    if isinstance(lists, tuple) and len(lists) == 2:
+        off, cand = (np.ascontiguousarray(a, np.int32) for a in lists)
+    else:
+        off = np.zeros(n + 1, np.int32)
+        off[1:] = np.cumsum([len(l) for l in lists], dtype=np.int64)
+        cand = np.ascontiguousarray(np.concatenate([np.asarray(l, np.int32) for l in lists]) if n and off[-1] else np.zeros(0, np.int32), np.int32)
+    assert len(off) == n + 1
+    return off, cand
 
 
 _default = None
@@ -69,6 +99,15 @@ def Match(descA, descB, maskA=None, maskB=None, maxHammingDist=30, minHammingDif
     if _default is None or _default.max_descriptors < n:
         _default = Matcher(max(4096, n), 1)
     return _default.Match(descA, descB, maskA, maskB, maxHammingDist, minHammingDifference)
+
+
+def IndexedMatch(closeMatchesAtoB, closeMatchesBtoA, descA, descB, maskA=None, maskB=None, maxHammingDist=30, minHammingDifference=1):
+    """Free-function form of Matcher.IndexedMatch."""
+    global _default
+    n = max(len(descA), len(descB), 1)
+    if _default is None or _default.max_descriptors < n:
+        _default = Matcher(max(4096, n), 1)
+    return _default.IndexedMatch(closeMatchesAtoB, closeMatchesBtoA, descA, descB, maskA, maskB, maxHammingDist, minHammingDifference)
 
 
 def GetDescriptorDistance(d0, d1):

@@ -714,6 +714,57 @@ int orc_match(const uint8_t* descA, int nAall, const uint8_t* maskA, const uint8
 
 } // extern "C"
 
+// ---- IndexedMatch -----------------------------------------------------------------------------------------------------
+// ref Tracking/FeatureMatcher.cpp:192-268 (IndexedMatch) with TrackMatch (:22-57). The vocabulary lookups
+// (BaseBow::QueryFeatures / BaseFeatureMatcher::QueryFeatures, BoW subsystem, out of scope) are inputs: CSR candidate lists
+// in the order QueryFeatures returns them, a2b for every A feature and b2a for every B feature.
+namespace {
+struct TrackMatchResult { size_t MatchIdx; int HammingDistance; };
+
+void track_match(const uint8_t* descLeft, const uint8_t* descsRight, size_t idxRight, const uint8_t* rightMask, TrackMatchResult& best,
+                 TrackMatchResult& second, int maxHamming)
+{
+    if (!rightMask || rightMask[idxRight]) {
+        int hamming_dist = orc_descriptor_distance(descLeft, descsRight + 32 * idxRight);
+        if (hamming_dist < maxHamming) {
+            if (hamming_dist < best.HammingDistance) { second = best; best = {idxRight, hamming_dist}; }
+            else if (hamming_dist < second.HammingDistance) { second = {idxRight, hamming_dist}; }
+        }
+    }
+}
+} // namespace
+
+extern "C" int orc_indexed_match(const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_t* descB, int nB, const uint8_t* maskB,
+                                 const int* a2b_off, const int* a2b, const int* b2a_off, const int* b2a, int maxHammingDist,
+                                 int minHammingDifference, orc_dmatch* out)
+{
+    size_t cntA = 0, cntB = 0;
+    for (int i = 0; i < nA; i++) cntA += (!maskA || maskA[i]);
+    for (int i = 0; i < nB; i++) cntB += (!maskB || maskB[i]);
+    if (cntA == 0 || cntB == 0) return 0;
+    const int maxHamming = maxHammingDist + 1;
+    const size_t none = (size_t)-1;
+    std::vector<std::pair<size_t, size_t>> matches;
+    for (size_t idxA = 0; idxA < (size_t)nA; ++idxA) {
+        if (maskA && !maskA[idxA]) continue;
+        TrackMatchResult best{none, maxHamming}, second{none, maxHamming};
+        for (int j = a2b_off[idxA]; j < a2b_off[idxA + 1]; ++j) track_match(descA + 32 * idxA, descB, (size_t)a2b[j], maskB, best, second, maxHamming);
+        if (best.HammingDistance < maxHamming &&
+            (second.HammingDistance >= maxHamming || second.HammingDistance - best.HammingDistance >= minHammingDifference))
+            matches.emplace_back(idxA, best.MatchIdx);
+    }
+    int n = 0;
+    for (const auto& match : matches) {
+        const size_t idxB = match.second;
+        TrackMatchResult best{none, maxHamming}, second{none, maxHamming};
+        for (int j = b2a_off[idxB]; j < b2a_off[idxB + 1]; ++j) track_match(descB + 32 * idxB, descA, (size_t)b2a[j], maskA, best, second, maxHamming);
+        if (best.HammingDistance < maxHamming && best.MatchIdx == match.first &&
+            (second.HammingDistance >= maxHamming || second.HammingDistance - best.HammingDistance >= minHammingDifference))
+            out[n++] = orc_dmatch{(int)best.MatchIdx, (int)idxB, (float)best.HammingDistance};
+    }
+    return n;
+}
+
 // ---- RadiusMatch ------------------------------------------------------------------------------------------------------
 // The reference gates candidates with a boost::geometry R*-tree (rstar<12>) built by the range constructor, i.e. boost's
 // packing algorithm (boost 1.67 index/detail/rtree/pack_create.hpp, vendored by the reference): top-down, split at an

@@ -79,6 +79,11 @@ int   orc_match(const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_
                 int max_hamming, int min_diff, orc_dmatch* out, int* count);
 int   orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
 
+/* IndexedMatch (reference Tracking/FeatureMatcher.cpp:192-268): BoW-gated two-way match; the vocabulary lookups are given as CSR
+ * candidate lists (a2b_off[nA+1]/a2b, b2a_off[nB+1]/b2a) in QueryFeatures order. out capacity >= nA; returns the count. */
+int   orc_indexed_match(const uint8_t* descA, int nA, const uint8_t* maskA, const uint8_t* descB, int nB, const uint8_t* maskB,
+                        const int* a2b_off, const int* a2b, const int* b2a_off, const int* b2a, int max_hamming, int min_diff, orc_dmatch* out);
+
 /* RadiusMatch (reference Tracking/FeatureMatcher.cpp:294-446) over the enumeration order of the packed boost R*-tree
  * (reference Image/KeypointSpatialIndex.cpp). order_out receives the depth-first value order of the tree built from kps. */
 int   orc_rtree_order(const orc_keypoint* kps, int n, int* order_out);

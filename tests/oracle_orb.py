@@ -158,6 +158,23 @@ def match(descA, descB, max_hamming=30, min_diff=1, maskA=None, maskB=None):
     return out[:cnt.value].copy()
 
 
+def indexed_match(descA, descB, a2b, b2a, max_hamming=30, min_diff=1, maskA=None, maskB=None):
+    """a2b / b2a: CSR pairs (offsets int32[n+1], candidates int32[...])."""
+    descA, ap = _u8(descA); descB, bp = _u8(descB)
+    nA, nB = len(descA), len(descB)
+    o0, c0 = (np.ascontiguousarray(x, np.int32) for x in a2b)
+    o1, c1 = (np.ascontiguousarray(x, np.int32) for x in b2a)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    maskA = None if maskA is None else np.ascontiguousarray(maskA, np.uint8)
+    maskB = None if maskB is None else np.ascontiguousarray(maskB, np.uint8)
+    out = np.zeros(max(nA, 1), DM_DTYPE)
+    L = lib()
+    L.orc_indexed_match.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    n = L.orc_indexed_match(ap, nA, p(maskA), bp, nB, p(maskB), p(o0), p(c0), p(o1), p(c1), int(max_hamming), int(min_diff), p(out))
+    return out[:n].copy()
+
+
 def descriptor_distance(a, b):
     a, ap = _u8(a); b, bp = _u8(b)
     return lib().orc_descriptor_distance(ap, bp)
