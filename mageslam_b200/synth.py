@@ -193,7 +193,59 @@ def ba_problem(K=10, P=2000, obs_per_point=4, seed=1, n_fixed=2, f=500.0, cx=320
                 intrinsics=np.tile(np.array([cx, cy, f, f], np.float32), (K, 1)), fixed=fixed,
                 points=pts_init.astype(np.float32), obs_uv=obs_uv[:E].astype(np.float32),
                 obs_cam=obs_cam[:E].copy(), obs_pt=obs_pt[:E].copy(), obs_info=info,
-                true_points=pts.astype(np.float32))
+                true_points=pts.astype(np.float32), true_cam_R=cams_R.copy(), true_cam_t=cams_t.copy())
+
+
+def _quat_xyzw(R):
+    """Rotation matrix -> unit quaternion (x, y, z, w), w >= 0."""
+    t = np.trace(R)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([(R[2, 1] - R[1, 2]) / s, (R[0, 2] - R[2, 0]) / s, (R[1, 0] - R[0, 1]) / s, 0.25 * s])
+    else:
+        i = int(np.argmax(np.diag(R))); j = (i + 1) % 3; k = (j + 1) % 3
+        s = np.sqrt(R[i, i] - R[j, j] - R[k, k] + 1.0) * 2
+        q = np.zeros(4)
+        q[i] = 0.25 * s; q[3] = (R[k, j] - R[j, k]) / s; q[j] = (R[j, i] + R[i, j]) / s; q[k] = (R[k, i] + R[i, k]) / s
+    if q[3] < 0:
+        q = -q
+    return q / np.linalg.norm(q)
+
+
+def ba_add_tethers(prob, seed=0, n_distance=4, n_rotation=4, n_transform=4, noise=1e-3):
+    """Adds tether edges between cameras to a ba_problem dict, in the conventions of BundlerLib's three constraint setters
+    (reference BundlerLib.cpp:311-350): tether_distance = [(cam1, cam2, distance, weight)] on the view-transform translations,
+    tether_rotation = [(cam1, cam2, q_xyzw of T1^-1 T2, weight)], tether_transform = [(cam1, cam2, t, q_xyzw, weight)] with
+    C = T2 T1^-1 (the measurement EdgeSE3Expmap's error log(T2^-1 C T1) vanishes at). Pairs include one with a fixed camera
+    and one with both cameras fixed (an inactive edge) when the window has fixed cameras."""
+    rng = np.random.default_rng(seed)
+    R, t, fixed = prob["true_cam_R"], prob["true_cam_t"], prob["fixed"]
+    K = len(R)
+    def pairs(n, off):
+        out = []
+        for i in range(n):
+            a = (i * 2 + off) % (K - 1)
+            out.append((a, a + 1))
+        if n and fixed[0] and fixed[1]:
+            out[0] = (0, 1)                                # both fixed: never active
+        if n > 1 and K > 2:
+            out[1] = (K - 1, 1)                            # reversed index order, one end fixed when n_fixed >= 2
+        return out
+    dist = [(a, b, float(np.linalg.norm(t[b] - t[a]) * (1 + rng.normal(0, noise))), float(rng.uniform(200.0, 2000.0))) for a, b in pairs(n_distance, 0)]
+    rot = []
+    for a, b in pairs(n_rotation, 1):
+        Rrel = R[a].T @ R[b]
+        q = _quat_xyzw(_rot(*rng.normal(0, noise, 3)) @ Rrel)
+        rot.append((a, b, q.astype(np.float32), float(rng.uniform(500.0, 5000.0))))
+    xf = []
+    for a, b in pairs(n_transform, 0):
+        Rc = R[b] @ R[a].T
+        tc = t[b] - Rc @ t[a]
+        q = _quat_xyzw(_rot(*rng.normal(0, noise, 3)) @ Rc)
+        xf.append((a, b, (tc + rng.normal(0, noise, 3)).astype(np.float32), q.astype(np.float32), float(rng.uniform(1e5, 1e6))))
+    out = dict(prob)
+    out["tether_distance"], out["tether_rotation"], out["tether_transform"] = dist, rot, xf
+    return out
 
 
 def local_map_scene(n=4000, seed=0, width=640, height=480, scale=1.2, levels=8):

@@ -11,7 +11,12 @@
  *
  * Parity status: PINNED -- validated against the reference's own code compiled into oracle/_ref/libbundler_ref.so
  * (tests/test_ba_oracle.py compares poses, points, lambda and outlier sets step by step). Tether edges
- * (BundlerLib.cpp:24-90, 311-350) are outside the restated slice.
+ * (BundlerLib.cpp:24-90 EdgeScaleConstraint / EdgeRotationConstraint with g2o's numeric BaseMultiEdge Jacobians,
+ * core/base_multi_edge.hpp:68-118; g2o EdgeSE3Expmap, types_six_dof_expmap.h:108-127 / .cpp:278-293; setters
+ * BundlerLib.cpp:311-350) are restated too. One documented deviation: the reference's closing loop (BundlerLib.cpp:389-427)
+ * walks ALL active edges and static_casts vertex(0) of a tether edge to VertexSBAPointXYZ -- it reads a camera vertex as if
+ * it were a point, so whether a tether edge's squared error enters the returned mean is undefined behaviour. Here (and in
+ * the product) tether edges never enter the mean or the outlier list ("only remove point if it is a camera/point edge").
  *
  * Nothing under mageslam_b200/ may include, link or call this file.
  */
@@ -115,6 +120,62 @@ inline Pose poseOplus(const Pose& T, const double* u)
     return out;
 }
 
+// ref se3quat.h:120-125 inverse, :99-105 operator*
+inline Pose poseInverse(const Pose& T)
+{
+    Pose r;
+    r.r = T.r; r.r.x = -r.r.x; r.r.y = -r.r.y; r.r.z = -r.r.z;
+    Vec3 nt; for (int i = 0; i < 3; i++) nt[i] = T.t[i] * -1.;
+    r.t = qrot(r.r, nt);
+    return r;
+}
+inline Pose poseMul(const Pose& a, const Pose& b)
+{
+    Pose r = a;
+    Vec3 rt = qrot(a.r, b.t);
+    for (int i = 0; i < 3; i++) r.t[i] += rt[i];
+    r.r = qmul(a.r, b.r);
+    qnormalizeRotation(r.r);
+    return r;
+}
+inline void mat3mul(const double* A, const double* B, double* C)
+{
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { double s = 0; for (int k = 0; k < 3; k++) s += A[i * 3 + k] * B[k * 3 + j]; C[i * 3 + j] = s; }
+}
+// ref se3quat.h:171-210 SE3Quat::log -> (omega, upsilon)
+inline void poseLog(const Pose& T, double res[6])
+{
+    double R[9]; qtoR(T.r, R);
+    double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+    double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};                 // deltaR (se3_ops.hpp)
+    double omega[3], Vinv[9];
+    auto skewOf = [](const double* o, double* O) { O[0] = 0; O[1] = -o[2]; O[2] = o[1]; O[3] = o[2]; O[4] = 0; O[5] = -o[0]; O[6] = -o[1]; O[7] = o[0]; O[8] = 0; };
+    double O[9], O2[9];
+    if (std::abs(d) > 0.99999) {
+        for (int i = 0; i < 3; i++) omega[i] = 0.5 * dR[i];
+        skewOf(omega, O); mat3mul(O, O, O2);
+        for (int i = 0; i < 9; i++) Vinv[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * O[i] + (1. / 12.) * O2[i];
+    } else {
+        double theta = std::acos(d);
+        double k = theta / (2 * std::sqrt(1 - d * d));
+        for (int i = 0; i < 3; i++) omega[i] = k * dR[i];
+        skewOf(omega, O); mat3mul(O, O, O2);
+        double c = (1 - theta / (2 * std::tan(theta / 2))) / (theta * theta);
+        for (int i = 0; i < 9; i++) Vinv[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * O[i] + c * O2[i];
+    }
+    for (int i = 0; i < 3; i++) res[i] = omega[i];
+    for (int i = 0; i < 3; i++) res[3 + i] = Vinv[i * 3] * T.t[0] + Vinv[i * 3 + 1] * T.t[1] + Vinv[i * 3 + 2] * T.t[2];
+}
+// ref se3quat.h:217-226 adj(): [R 0; skew(t) R  R], row-major 6x6
+inline void poseAdj(const Pose& T, double A[36])
+{
+    double R[9]; qtoR(T.r, R);
+    double Sk[9] = {0, -T.t[2], T.t[1], T.t[2], 0, -T.t[0], -T.t[1], T.t[0], 0}, SR[9];
+    mat3mul(Sk, R, SR);
+    for (int i = 0; i < 36; i++) A[i] = 0;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) { A[r * 6 + c] = R[r * 3 + c]; A[(3 + r) * 6 + 3 + c] = R[r * 3 + c]; A[(3 + r) * 6 + c] = SR[r * 3 + c]; }
+}
+
 inline bool inv3(const double* A, double* Ai)           // Eigen 3x3 inverse: cofactors / determinant
 {
     double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
@@ -181,9 +242,22 @@ struct Camera { Pose T; double f = 0, cx = 0, cy = 0; bool fixed = false; bool s
 struct Point { Vec3 X; bool set = false; int hidx = -1; };
 struct Obs { double u = 0, v = 0, info = 0; int cam = -1, pt = -1; bool set = false, removed = false; long seq = -1; double err[2] = {0, 0}; };
 
+// tether edges between two cameras: 0 = EdgeScaleConstraint (BundlerLib.cpp:24-55), 1 = EdgeRotationConstraint (:57-90),
+// 2 = g2o EdgeSE3Expmap (RelativeTransformConstraints)
+struct Tether {
+    int type = -1, c1 = -1, c2 = -1, dim = 0;
+    double dist = 0, w = 0;       // measurement (type 0), weight (types 0/1: multiplies the error; type 2: information = w I)
+    Quat q; Pose C;               // measurement of type 1 / type 2
+    bool set = false; long seq = -1;
+    double err[6] = {0, 0, 0, 0, 0, 0};
+    double J[2][36];              // dim x 6, row-major, per vertex
+};
+
 struct BA {
     bool pointsFixed = false;
     std::vector<Camera> cams; std::vector<Point> pts; std::vector<Obs> obs;
+    std::vector<Tether> teth[3];
+    std::vector<Tether*> activeT;       // active tether edges, insertion order
     long nextSeq = 0;
     // optimizer state (StepOptimizer + OptimizationAlgorithmLevenberg)
     bool dirty = true, useless = false;
@@ -195,6 +269,8 @@ struct BA {
     std::vector<double> x, b;           // full solution / rhs (poses first, then landmarks)
     std::vector<double> Hpp, Hll, W;    // dense (6Kf)^2 row-major; 9 per free point; 18 per active obs (6x3 row-major)
 };
+
+inline void computeTetherErrors(BA& s);
 
 // ref types_six_dof_expmap.h:140-147 computeError (+ cam_map, SE3Quat::map)
 inline void computeErrors(BA& s)
@@ -208,6 +284,34 @@ inline void computeErrors(BA& s)
         o.err[0] = o.u - (pu * c.f + c.cx);
         o.err[1] = o.v - (pv * c.f + c.cy);
     }
+    computeTetherErrors(s);
+}
+inline void tetherError(const BA& s, const Tether& t, double* err)
+{
+    const Pose& T1 = s.cams[t.c1].T; const Pose& T2 = s.cams[t.c2].T;
+    if (t.type == 0) {
+        double dx = T2.t[0] - T1.t[0], dy = T2.t[1] - T1.t[1], dz = T2.t[2] - T1.t[2];
+        err[0] = (t.dist - std::sqrt(dx * dx + dy * dy + dz * dz)) * t.w;
+    } else if (t.type == 1) {
+        Pose rel = poseMul(poseInverse(T1), T2);
+        // Eigen angularDistance: d = this * other.conjugate(); 2 * atan2(d.vec().norm(), |d.w|)
+        Quat mc = t.q; mc.x = -mc.x; mc.y = -mc.y; mc.z = -mc.z;
+        Quat d = qmul(rel.r, mc);
+        err[0] = 2 * std::atan2(std::sqrt(d.x * d.x + d.y * d.y + d.z * d.z), std::abs(d.w)) * t.w;
+    } else {
+        Pose E = poseMul(poseMul(poseInverse(T2), t.C), T1);
+        poseLog(E, err);
+    }
+}
+inline void computeTetherErrors(BA& s)
+{
+    for (Tether* t : s.activeT) tetherError(s, *t, t->err);
+}
+inline double tetherChi2(const Tether& t)
+{
+    double ss = 0;
+    for (int i = 0; i < t.dim; i++) ss += t.err[i] * ((t.type == 2 ? t.w : 1.0) * t.err[i]);       // e^T Omega e
+    return ss;
 }
 // ref robust_kernel_impl.cpp:65-78 (Huber on the squared error) and sparse_optimizer.cpp:102-117
 inline void huberRho(double e, double delta, double rho[3])
@@ -225,6 +329,7 @@ inline double robustChi2(const BA& s)
         huberRho(chi2, s.huber, rho);
         chi += rho[0];
     }
+    for (const Tether* t : s.activeT) chi += tetherChi2(*t);               // no robust kernel on tether edges
     return chi;
 }
 
@@ -243,6 +348,14 @@ void initializeOptimization(BA& s)
     for (auto& pr : order) s.active.push_back(pr.second);
     std::vector<char> camActive(s.cams.size(), 0), ptActive(s.pts.size(), 0);
     for (int e : s.active) { camActive[s.obs[e].cam] = 1; ptActive[s.obs[e].pt] = 1; }
+    s.activeT.clear();
+    for (auto& v : s.teth) for (Tether& t : v) {
+        if (!t.set) continue;
+        if (s.cams[t.c1].fixed && s.cams[t.c2].fixed) continue;          // allVerticesFixed
+        s.activeT.push_back(&t);
+        camActive[t.c1] = 1; camActive[t.c2] = 1;
+    }
+    std::sort(s.activeT.begin(), s.activeT.end(), [](const Tether* a, const Tether* b) { return a->seq < b->seq; });
     for (auto& c : s.cams) c.hidx = -1;
     for (auto& p : s.pts) p.hidx = -1;
     s.camOrder.clear(); s.ptOrder.clear();
@@ -266,6 +379,8 @@ void buildStructure(BA& s)
     s.Hll.assign((size_t)3 * s.sizeLandmarks, 0.0);
     s.W.assign((size_t)18 * s.active.size(), 0.0);
 }
+
+void addTethers(BA& s);
 
 // ref block_solver.hpp:463-521 buildSystem; types_six_dof_expmap.cpp:295-331 linearizeOplus;
 // base_binary_edge.hpp:62-134 constructQuadraticForm (robust branch)
@@ -317,6 +432,73 @@ void buildSystem(BA& s)
         if (hi >= 0 && hj >= 0) {
             double* W = &s.W[18 * a];       // pose (6) x point (3)
             for (int r = 0; r < 6; r++) for (int cc = 0; cc < 3; cc++) W[r * 3 + cc] += wOmega * (Jj[r] * Ji[cc] + Jj[6 + r] * Ji[3 + cc]);
+        }
+    }
+    addTethers(s);
+}
+
+// Tether edges: linearisation (numeric for the BaseMultiEdge types, ref base_multi_edge.hpp:68-118: central differences with
+// delta = 1e-9 through oplus on each free vertex; analytic adjoints for EdgeSE3Expmap, ref types_six_dof_expmap.cpp:278-293)
+// and quadratic form (ref base_multi_edge.hpp:155-197, base_binary_edge.hpp:75-103): H_ii += A^T O A, b_i += A^T (-O e),
+// H_ij += A^T O B.
+void linearizeTether(BA& s, Tether& t)
+{
+    const int cam[2] = {t.c1, t.c2};
+    if (t.type == 2) {
+        const Pose& Ti = s.cams[t.c1].T; const Pose& Tj = s.cams[t.c2].T;
+        Pose invTij = poseInverse(t.C);
+        Pose invTj_Tij = poseMul(poseInverse(Tj), t.C);
+        Pose invTi_invTij = poseMul(poseInverse(Ti), invTij);
+        poseAdj(invTj_Tij, t.J[0]);
+        poseAdj(invTi_invTij, t.J[1]);
+        for (int i = 0; i < 36; i++) t.J[1][i] = -t.J[1][i];
+        return;
+    }
+    const double delta = 1e-9, scalar = 1 / (2 * delta);
+    for (int v = 0; v < 2; v++) {
+        Camera& c = s.cams[cam[v]];
+        if (c.fixed) continue;
+        for (int d = 0; d < 6; d++) {
+            double add[6] = {0, 0, 0, 0, 0, 0}, ep[6], em[6];
+            const Pose keep = c.T;
+            add[d] = delta;  c.T = poseOplus(keep, add); tetherError(s, t, ep); c.T = keep;
+            add[d] = -delta; c.T = poseOplus(keep, add); tetherError(s, t, em); c.T = keep;
+            for (int r = 0; r < t.dim; r++) t.J[v][r * 6 + d] = scalar * (ep[r] - em[r]);
+        }
+    }
+}
+void addTethers(BA& s)
+{
+    const int n = s.sizePoses;
+    for (Tether* tp : s.activeT) {
+        Tether& t = *tp;
+        linearizeTether(s, t);
+        const double om = (t.type == 2) ? t.w : 1.0;                       // information = om * I
+        const int h[2] = {s.cams[t.c1].hidx, s.cams[t.c2].hidx};
+        const bool freeV[2] = {!s.cams[t.c1].fixed, !s.cams[t.c2].fixed};
+        for (int v = 0; v < 2; v++) {
+            if (!freeV[v]) continue;
+            const double* A = t.J[v];
+            for (int r = 0; r < 6; r++) {
+                double bb = 0;
+                for (int k = 0; k < t.dim; k++) bb += A[k * 6 + r] * (-(om * t.err[k]));
+                s.b[6 * h[v] + r] += bb;
+                for (int c = 0; c < 6; c++) {
+                    double hh = 0;
+                    for (int k = 0; k < t.dim; k++) hh += (A[k * 6 + r] * om) * A[k * 6 + c];
+                    s.Hpp[(size_t)(6 * h[v] + r) * n + 6 * h[v] + c] += hh;
+                }
+            }
+        }
+        if (freeV[0] && freeV[1]) {
+            const double* A = t.J[0]; const double* B = t.J[1];
+            if (h[0] == h[1]) continue;                                     // (degenerate: both ends the same camera)
+            for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) {
+                double hh = 0;
+                for (int k = 0; k < t.dim; k++) hh += (A[k * 6 + r] * om) * B[k * 6 + c];
+                s.Hpp[(size_t)(6 * h[0] + r) * n + 6 * h[1] + c] += hh;
+                s.Hpp[(size_t)(6 * h[1] + c) * n + 6 * h[0] + r] += hh;
+            }
         }
     }
 }
@@ -477,6 +659,38 @@ void baorc_set_observation(void* h, int idx, const float* uv, int cam, int pt, f
     BA* s = static_cast<BA*>(h);
     Obs& o = s->obs[idx];
     o.u = uv[0]; o.v = uv[1]; o.cam = cam; o.pt = pt; o.info = info; o.set = true; o.removed = false; o.seq = s->nextSeq++;
+    s->dirty = true;
+}
+// ref BundlerLib.cpp:243-259, :311-350. q = (x, y, z, w). -1 leaves a pool untouched.
+void baorc_alloc_tethers(void* h, int n_distance, int n_rotation, int n_transform)
+{
+    BA* s = static_cast<BA*>(h);
+    const int n[3] = {n_distance, n_rotation, n_transform};
+    for (int k = 0; k < 3; k++) if (n[k] >= 0) { s->teth[k].assign(n[k], Tether()); }
+}
+void baorc_set_fixed_distance(void* h, int idx, int cam1, int cam2, float distance, float weight)
+{
+    BA* s = static_cast<BA*>(h);
+    Tether& t = s->teth[0][idx];
+    t.type = 0; t.dim = 1; t.c1 = cam1; t.c2 = cam2; t.dist = distance; t.w = weight; t.set = true; t.seq = s->nextSeq++;
+    s->dirty = true;
+}
+void baorc_set_relative_rotation(void* h, int idx, int cam1, int cam2, const float* q, float weight)
+{
+    BA* s = static_cast<BA*>(h);
+    Tether& t = s->teth[1][idx];
+    t.type = 1; t.dim = 1; t.c1 = cam1; t.c2 = cam2; t.w = weight; t.set = true; t.seq = s->nextSeq++;
+    t.q.x = q[0]; t.q.y = q[1]; t.q.z = q[2]; t.q.w = q[3];                // Quaternionf::cast<double>(), not normalised
+    s->dirty = true;
+}
+void baorc_set_relative_transform(void* h, int idx, int cam1, int cam2, const float* dpos, const float* q, float weight)
+{
+    BA* s = static_cast<BA*>(h);
+    Tether& t = s->teth[2][idx];
+    t.type = 2; t.dim = 6; t.c1 = cam1; t.c2 = cam2; t.w = weight; t.set = true; t.seq = s->nextSeq++;
+    t.C.r.x = q[0]; t.C.r.y = q[1]; t.C.r.z = q[2]; t.C.r.w = q[3];
+    qnormalizeRotation(t.C.r);                                             // SE3Quat(q, t) ctor
+    for (int i = 0; i < 3; i++) t.C.t[i] = dpos[i];
     s->dirty = true;
 }
 void baorc_set_lambda(void* h, float l) { BA* s = static_cast<BA*>(h); s->iteration = 0; s->userLambdaInit = l; }

@@ -40,6 +40,28 @@ void refba_set_observation(void* h, int idx, const float* uv, int cam, int pt, f
 {
     static_cast<mage::BundlerLib*>(h)->SetObservation((size_t)idx, Eigen::Map<const Eigen::Vector2f>(uv), (size_t)cam, (size_t)pt, info);
 }
+// tether edges (BundlerLib.h:41-48). q = Eigen coefficient order (x, y, z, w)
+void refba_alloc_tethers(void* h, int n_distance, int n_rotation, int n_transform)
+{
+    auto* b = static_cast<mage::BundlerLib*>(h);
+    if (n_distance >= 0) b->AllocateFixedDistanceConstraints((size_t)n_distance);
+    if (n_rotation >= 0) b->AllocateRelativeRotationConstraints((size_t)n_rotation);
+    if (n_transform >= 0) b->AllocateRelativeTransformConstraints((size_t)n_transform);
+}
+void refba_set_fixed_distance(void* h, int idx, int cam1, int cam2, float distance, float weight)
+{
+    static_cast<mage::BundlerLib*>(h)->SetFixedDistanceConstraint((size_t)idx, (size_t)cam1, (size_t)cam2, distance, weight);
+}
+void refba_set_relative_rotation(void* h, int idx, int cam1, int cam2, const float* q_xyzw, float weight)
+{
+    Eigen::Quaternionf q(q_xyzw[3], q_xyzw[0], q_xyzw[1], q_xyzw[2]);
+    static_cast<mage::BundlerLib*>(h)->SetRelativeRotationConstraint((size_t)idx, (size_t)cam1, (size_t)cam2, q, weight);
+}
+void refba_set_relative_transform(void* h, int idx, int cam1, int cam2, const float* dpos, const float* q_xyzw, float weight)
+{
+    Eigen::Quaternionf q(q_xyzw[3], q_xyzw[0], q_xyzw[1], q_xyzw[2]);
+    static_cast<mage::BundlerLib*>(h)->SetRelativeTransformConstraint((size_t)idx, (size_t)cam1, (size_t)cam2, Eigen::Map<const Eigen::Vector3f>(dpos), q, weight);
+}
 void refba_fix_camera(void* h, int idx, int value) { static_cast<mage::BundlerLib*>(h)->FixCameraPose((size_t)idx, value != 0); }
 void refba_set_lambda(void* h, float l) { static_cast<mage::BundlerLib*>(h)->SetCurrentLambda(l); }
 float refba_get_lambda(void* h) { return static_cast<mage::BundlerLib*>(h)->GetCurrentLambda(); }

@@ -13,7 +13,7 @@ def best_checker(points_fixed=False):
     return BaOracle("ref" if have_ref() else "port", points_fixed)
 
 
-def run_side_by_side(candidate, checker, huber, max_err_sq, calls, tol=TOL, tag=""):
+def run_side_by_side(candidate, checker, huber, max_err_sq, calls, tol=TOL, tag="", check_mean=True):
     """candidate: object with StepBundleAdjustment(huber, max) -> mean and .last_outliers/.poses()/.points()/.GetCurrentLambda().
     Returns the list of per-call relative errors (for reporting)."""
     report = []
@@ -27,7 +27,9 @@ def run_side_by_side(candidate, checker, huber, max_err_sq, calls, tol=TOL, tag=
         lam_c, lam_r = candidate.GetCurrentLambda(), checker.GetCurrentLambda()
         assert e_pos <= tol and e_rot <= tol and e_pts <= tol, "%s call %d: relF pos %.3g rot %.3g pts %.3g" % (tag, c, e_pos, e_rot, e_pts)
         assert abs(lam_c - lam_r) <= 1e-3 * abs(lam_r) + 1e-12, "%s call %d: lambda %g vs %g" % (tag, c, lam_c, lam_r)
-        if np.isnan(mean_r):
+        if not check_mean:
+            pass        # tether edges: the reference's returned mean is undefined behaviour (oracle/ba_oracle.cpp header)
+        elif np.isnan(mean_r):
             assert np.isnan(mean_c)
         else:
             assert abs(mean_c - mean_r) <= 1e-4 * abs(mean_r) + 1e-9, "%s call %d: mean error %g vs %g" % (tag, c, mean_c, mean_r)

@@ -38,6 +38,10 @@ def _load(kind):
     fn("get_lambda").restype = C.c_float
     fn("step").argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     fn("step").restype = C.c_float
+    fn("alloc_tethers").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    fn("set_fixed_distance").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float]
+    fn("set_relative_rotation").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float]
+    fn("set_relative_transform").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float]
     fn("get_pose").argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     fn("get_point").argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     _libs[kind] = (L, pre)
@@ -81,7 +85,22 @@ class BaOracle:
         for e in range(E):
             self._f("set_observation")(self.h, e, f32(prob["obs_uv"][e]).ctypes.data, int(prob["obs_cam"][e]), int(prob["obs_pt"][e]),
                                        float(prob["obs_info"][e]))
+        self.load_tethers(prob)
         return self
+
+    def load_tethers(self, prob):
+        """Optional tether edges of a synth.ba_problem(..., tethers=True) dict, in BundlerLib's own call order."""
+        f32 = lambda a: np.ascontiguousarray(a, np.float32)
+        dist, rot, xf = prob.get("tether_distance", []), prob.get("tether_rotation", []), prob.get("tether_transform", [])
+        if not (len(dist) or len(rot) or len(xf)):
+            return
+        self._f("alloc_tethers")(self.h, len(dist), len(rot), len(xf))
+        for i, (c1, c2, d, w) in enumerate(dist):
+            self._f("set_fixed_distance")(self.h, i, int(c1), int(c2), float(d), float(w))
+        for i, (c1, c2, q, w) in enumerate(rot):
+            self._f("set_relative_rotation")(self.h, i, int(c1), int(c2), f32(q).ctypes.data, float(w))
+        for i, (c1, c2, t, q, w) in enumerate(xf):
+            self._f("set_relative_transform")(self.h, i, int(c1), int(c2), f32(t).ctypes.data, f32(q).ctypes.data, float(w))
 
     def SetCurrentLambda(self, l):
         self._f("set_lambda")(self.h, float(l))

@@ -9,7 +9,7 @@ import pytest
 from mageslam_b200 import synth
 from tests.ba_checks import run_side_by_side
 from tests.oracle_ba import BaOracle, have_ref, rel_frobenius
-from tools.gen_ba_golden import CASES
+from tools.gen_ba_golden import CASES, build_problem
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_golden.npz"))
 
@@ -28,7 +28,7 @@ class _Adapter:
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_port_matches_reference_golden(name):
     kw, pf, hub, mx, calls = CASES[name]
-    prob = synth.ba_problem(**kw)
+    prob = build_problem(kw)
     port = BaOracle("port", pf).load(prob)
     for c in range(calls):
         mean, outl = port.StepBundleAdjustment(hub, mx)
@@ -37,12 +37,16 @@ def test_port_matches_reference_golden(name):
         assert rel_frobenius(rot, GOLD["%s/%d/rot" % (name, c)]) < 1e-6
         assert rel_frobenius(port.points(), GOLD["%s/%d/pts" % (name, c)]) < 1e-6
         gmean, glam = GOLD["%s/%d/scalars" % (name, c)]
-        assert abs(mean - gmean) <= 1e-5 * abs(gmean) and abs(port.GetCurrentLambda() - glam) <= 1e-4 * abs(glam)
+        assert abs(port.GetCurrentLambda() - glam) <= 1e-4 * abs(glam)
+        # with tether edges the reference's returned mean is undefined behaviour (it reads camera vertices as points,
+        # BundlerLib.cpp:402-403); the restatement keeps tether edges out of the mean (oracle/ba_oracle.cpp header)
+        if "tethers" not in kw:
+            assert abs(mean - gmean) <= 1e-5 * abs(gmean)
         assert np.array_equal(outl.astype(np.int64), GOLD["%s/%d/outliers" % (name, c)])
 
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("variant", ["clean", "outliers", "confidence", "pose_only", "user_lambda"])
+@pytest.mark.parametrize("variant", ["clean", "outliers", "confidence", "pose_only", "user_lambda", "tethers"])
 def test_port_matches_compiled_reference_at_tier_size(variant):
     pf = variant == "pose_only"
     if variant == "clean":
@@ -53,12 +57,14 @@ def test_port_matches_compiled_reference_at_tier_size(variant):
         prob, hub, mx, calls = synth.ba_problem(info_mode="confidence", seed=3), [1.8, 1.8], 1e9, 5
     elif variant == "pose_only":
         prob, hub, mx, calls = synth.ba_problem(K=1, P=300, obs_per_point=1, n_fixed=0, pose_sigma=0.03, seed=5), [2.0, 2.0, 2.0], 25.0, 2
+    elif variant == "tethers":
+        prob, hub, mx, calls = synth.ba_add_tethers(synth.ba_problem(seed=9), seed=5, noise=1e-2), [1.8, 1.8], 1e9, 3
     else:
         prob, hub, mx, calls = synth.ba_problem(seed=7), [1.8], 1e9, 4
     ref = BaOracle("ref", pf).load(prob); port = BaOracle("port", pf).load(prob)
     if variant == "user_lambda":
         ref.SetCurrentLambda(5.0); port.SetCurrentLambda(5.0)
-    run_side_by_side(_Adapter(port), ref, hub, mx, calls, tol=1e-6, tag=variant)
+    run_side_by_side(_Adapter(port), ref, hub, mx, calls, tol=1e-6, tag=variant, check_mean=variant != "tethers")
 
 
 def test_degenerate_inputs():

@@ -14,12 +14,26 @@ CASES = {
     "local_outliers": (dict(K=6, P=200, obs_per_point=4, seed=12, outlier_frac=0.06), False, [1.8, 1.8], 7.25, 4),
     "pose_only": (dict(K=1, P=120, obs_per_point=1, seed=13, n_fixed=0, pose_sigma=0.03), True, [2.0, 2.0, 2.0], 25.0, 2),
     "info_weights": (dict(K=5, P=120, obs_per_point=3, seed=14, info_mode="confidence"), False, [0.9], 1e9, 5),
+    # tether edges (BundlerLib.cpp:24-90, :311-350): fixed-distance, relative-rotation and relative-transform constraints
+    "tether_distance": (dict(K=6, P=150, obs_per_point=3, seed=15, tethers=dict(seed=1, n_distance=4, n_rotation=0, n_transform=0, noise=1e-2)), False, [1.8, 1.8], 1e9, 3),
+    "tether_rotation": (dict(K=6, P=150, obs_per_point=3, seed=16, tethers=dict(seed=2, n_distance=0, n_rotation=4, n_transform=0, noise=1e-2)), False, [1.8, 1.8], 1e9, 3),
+    "tether_transform": (dict(K=6, P=150, obs_per_point=3, seed=17, tethers=dict(seed=3, n_distance=0, n_rotation=0, n_transform=4, noise=1e-2)), False, [1.8, 1.8], 1e9, 3),
+    "tether_all_outliers": (dict(K=7, P=200, obs_per_point=4, seed=18, outlier_frac=0.05, tethers=dict(seed=4, n_distance=3, n_rotation=3, n_transform=3, noise=1e-2)), False, [1.8, 1.8], 7.25, 3),
 }
+
+
+def build_problem(kw):
+    """CASES kwargs -> synth problem dict (the optional 'tethers' entry goes to synth.ba_add_tethers)."""
+    kw = dict(kw)
+    teth = kw.pop("tethers", None)
+    prob = synth.ba_problem(**kw)
+    return synth.ba_add_tethers(prob, **teth) if teth else prob
+
 
 def main():
     out = {}
     for name, (kw, pf, hub, mx, calls) in CASES.items():
-        prob = synth.ba_problem(**kw)
+        prob = build_problem(kw)
         ref = BaOracle("ref", pf).load(prob)
         for c in range(calls):
             mean, outl = ref.StepBundleAdjustment(hub, mx)
