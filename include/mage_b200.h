@@ -257,6 +257,24 @@ int  mage_ba_set_cameras_bulk(mage_ba_t h, int n, const float* positions /*n*3*/
 int  mage_ba_set_points_bulk(mage_ba_t h, int n, const float* xyz /*n*3*/);
 int  mage_ba_set_observations_bulk(mage_ba_t h, int n, const float* uv /*n*2*/, const int32_t* camera_idx,
                                    const int32_t* point_idx, const float* information /*n*/);
+
+/* Tether edges between two cameras (ref BundlerLib.h:41-48; BundlerLib.cpp:243-259 pools, :311-350 setters; edge types :24-90 and
+ * g2o EdgeSE3Expmap). Each pool is allocated once and filled slot by slot; a setter adds the edge (and dirties the problem).
+ *   fixed distance     : error = (distance - |t2 - t1|) * weight on the translations of the two view transforms
+ *   relative rotation  : error = angularDistance((T1^-1 T2).rotation(), q) * weight; q = (x, y, z, w), used as given
+ *   relative transform : error = log(T2^-1 C T1), C = (q normalised, delta_position), information = weight * I6
+ * The two scalar edges have no analytic Jacobian in the reference (g2o differentiates BaseMultiEdge numerically, central
+ * differences with delta 1e-9); the kernel evaluates the same differences. Tether edges never appear in the outlier list and do
+ * not enter the returned mean error (the reference's closing loop reads their camera vertex as a point: undefined behaviour,
+ * see DESIGN.md). Supported by the single-CTA kernel: MAGE_ERR_UNSUPPORTED on problems whose reduced system exceeds it. */
+int  mage_ba_alloc_fixed_distance_constraints(mage_ba_t h, int count);
+int  mage_ba_set_fixed_distance_constraint(mage_ba_t h, int idx, int cam1, int cam2, float distance, float weight);
+int  mage_ba_alloc_relative_rotation_constraints(mage_ba_t h, int count);
+int  mage_ba_set_relative_rotation_constraint(mage_ba_t h, int idx, int cam1, int cam2, const float* q_xyzw, float weight);
+int  mage_ba_alloc_relative_transform_constraints(mage_ba_t h, int count);
+int  mage_ba_set_relative_transform_constraint(mage_ba_t h, int idx, int cam1, int cam2, const float* delta_position,
+                                               const float* q_xyzw, float weight);
+
 int  mage_ba_set_lambda(mage_ba_t h, float user_lambda);                                    /* ref :352-355 */
 int  mage_ba_get_lambda(mage_ba_t h, float* lambda);                                        /* ref :357-360 */
 /* StepBundleAdjustment -- ref BundlerLib.cpp:364-447. Runs one LM step per Huber width, then classifies every

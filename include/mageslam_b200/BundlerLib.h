@@ -2,8 +2,7 @@
 // Same namespace, class name, method names and signatures; every method forwards to the C ABI of mage_b200.h
 // (libmage_b200.so), so Core/MAGESLAM/Source/BundleAdjustment/BundleAdjust.cpp and Tracking/TrackLocalMap.cpp compile
 // and link against it unchanged (replace the BundlerLib include directory and link libmage_b200 instead of
-// BundlerLib + g2o). Tether constraints (reference BundlerLib.cpp:311-350) are not accelerated yet: the three
-// Allocate*/Set*Constraint pairs throw std::logic_error if a count > 0 is requested.
+// BundlerLib + g2o). The three tether constraint pools (reference BundlerLib.cpp:243-259, :311-350) forward too.
 #pragma once
 
 #include <memory>
@@ -57,12 +56,26 @@ namespace mage
                                           static_cast<int>(mapPointIndex), informationMatrixScalar));
         }
 
-        void AllocateFixedDistanceConstraints(size_t count) { RequireNoTethers(count); }
-        void SetFixedDistanceConstraint(size_t, size_t, size_t, float = 1.0f, float = 1.0f) { RequireNoTethers(1); }
-        void AllocateRelativeRotationConstraints(size_t count) { RequireNoTethers(count); }
-        void SetRelativeRotationConstraint(size_t, size_t, size_t, const Eigen::Quaternionf&, float = 1.0f) { RequireNoTethers(1); }
-        void AllocateRelativeTransformConstraints(size_t count) { RequireNoTethers(count); }
-        void SetRelativeTransformConstraint(size_t, size_t, size_t, Eigen::Map<const Eigen::Vector3f>, const Eigen::Quaternionf&, float) { RequireNoTethers(1); }
+        void AllocateFixedDistanceConstraints(size_t count) { Check(mage_ba_alloc_fixed_distance_constraints(m_handle, static_cast<int>(count))); }
+        void SetFixedDistanceConstraint(size_t idx, size_t cameraIndex1, size_t cameraIndex2, float distance = 1.0f, float weight = 1.0f)
+        {
+            Check(mage_ba_set_fixed_distance_constraint(m_handle, static_cast<int>(idx), static_cast<int>(cameraIndex1), static_cast<int>(cameraIndex2), distance, weight));
+        }
+
+        void AllocateRelativeRotationConstraints(size_t count) { Check(mage_ba_alloc_relative_rotation_constraints(m_handle, static_cast<int>(count))); }
+        void SetRelativeRotationConstraint(size_t idx, size_t cameraIndex1, size_t cameraIndex2, const Eigen::Quaternionf& deltaRotation, float weight = 1.0f)
+        {
+            const float q[4] = { deltaRotation.x(), deltaRotation.y(), deltaRotation.z(), deltaRotation.w() };
+            Check(mage_ba_set_relative_rotation_constraint(m_handle, static_cast<int>(idx), static_cast<int>(cameraIndex1), static_cast<int>(cameraIndex2), q, weight));
+        }
+
+        void AllocateRelativeTransformConstraints(size_t count) { Check(mage_ba_alloc_relative_transform_constraints(m_handle, static_cast<int>(count))); }
+        void SetRelativeTransformConstraint(size_t idx, size_t cameraIndex1, size_t cameraIndex2, Eigen::Map<const Eigen::Vector3f> deltaPosition, const Eigen::Quaternionf& deltaRotation, float weight)
+        {
+            const float q[4] = { deltaRotation.x(), deltaRotation.y(), deltaRotation.z(), deltaRotation.w() };
+            Check(mage_ba_set_relative_transform_constraint(m_handle, static_cast<int>(idx), static_cast<int>(cameraIndex1), static_cast<int>(cameraIndex2),
+                                                            deltaPosition.data(), q, weight));
+        }
 
         void SetCurrentLambda(float userLambda) { Check(mage_ba_set_lambda(m_handle, userLambda)); }
         float GetCurrentLambda() const { float l = 0; Check(mage_ba_get_lambda(m_handle, &l)); return l; }
@@ -87,7 +100,6 @@ namespace mage
 
     private:
         static void Check(int rc) { if (rc != MAGE_OK) throw std::runtime_error(std::string("mage_b200: ") + mage_last_error()); }
-        static void RequireNoTethers(size_t count) { if (count != 0) throw std::logic_error("mage_b200: tether constraints are not accelerated yet"); }
 
         mage_ba_t m_handle{ nullptr };
         size_t m_observations{ 0 };

@@ -90,6 +90,11 @@ def lib():
         L.mage_ba_set_points_bulk.argtypes = [vp, ci, vp]
         L.mage_ba_set_observations_bulk.argtypes = [vp, ci, vp, vp, vp, vp]
         L.mage_ba_set_lambda.argtypes = [vp, cf]
+        for name in ("mage_ba_alloc_fixed_distance_constraints", "mage_ba_alloc_relative_rotation_constraints", "mage_ba_alloc_relative_transform_constraints"):
+            getattr(L, name).argtypes = [vp, ci]
+        L.mage_ba_set_fixed_distance_constraint.argtypes = [vp, ci, ci, ci, cf, cf]
+        L.mage_ba_set_relative_rotation_constraint.argtypes = [vp, ci, ci, ci, vp, cf]
+        L.mage_ba_set_relative_transform_constraint.argtypes = [vp, ci, ci, ci, vp, vp, cf]
         L.mage_ba_get_lambda.argtypes = [vp, C.POINTER(cf)]
         L.mage_ba_step.argtypes = [vp, vp, ci, cf, vp, ci, C.POINTER(ci), C.POINTER(cf)]
         L.mage_ba_get_pose.argtypes = [vp, ci, vp, vp]

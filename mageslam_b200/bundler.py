@@ -65,6 +65,27 @@ class BundlerLib:
         check(lib().mage_ba_set_observation(self._h, int(idx), ptr(_f32(position, 2)), int(cameraIndex), int(mapPointIndex),
                                             float(informationMatrixScalar)))
 
+    # tether constraints between two cameras (reference BundlerLib.h:41-48); deltaRotation = (x, y, z, w)
+    def AllocateFixedDistanceConstraints(self, count):
+        check(lib().mage_ba_alloc_fixed_distance_constraints(self._h, int(count)))
+
+    def SetFixedDistanceConstraint(self, idx, cameraIndex1, cameraIndex2, distance=1.0, weight=1.0):
+        check(lib().mage_ba_set_fixed_distance_constraint(self._h, int(idx), int(cameraIndex1), int(cameraIndex2), float(distance), float(weight)))
+
+    def AllocateRelativeRotationConstraints(self, count):
+        check(lib().mage_ba_alloc_relative_rotation_constraints(self._h, int(count)))
+
+    def SetRelativeRotationConstraint(self, idx, cameraIndex1, cameraIndex2, deltaRotation, weight=1.0):
+        check(lib().mage_ba_set_relative_rotation_constraint(self._h, int(idx), int(cameraIndex1), int(cameraIndex2), ptr(_f32(deltaRotation, 4)),
+                                                             float(weight)))
+
+    def AllocateRelativeTransformConstraints(self, count):
+        check(lib().mage_ba_alloc_relative_transform_constraints(self._h, int(count)))
+
+    def SetRelativeTransformConstraint(self, idx, cameraIndex1, cameraIndex2, deltaPosition, deltaRotation, weight):
+        check(lib().mage_ba_set_relative_transform_constraint(self._h, int(idx), int(cameraIndex1), int(cameraIndex2), ptr(_f32(deltaPosition, 3)),
+                                                              ptr(_f32(deltaRotation, 4)), float(weight)))
+
     def SetCurrentLambda(self, userLambda):
         check(lib().mage_ba_set_lambda(self._h, float(userLambda)))
 
@@ -106,6 +127,16 @@ class BundlerLib:
         check(lib().mage_ba_set_points_bulk(self._h, P, ptr(_f32(prob["points"]))))
         check(lib().mage_ba_set_observations_bulk(self._h, E, ptr(_f32(prob["obs_uv"])), ptr(np.ascontiguousarray(prob["obs_cam"], np.int32)),
                                                   ptr(np.ascontiguousarray(prob["obs_pt"], np.int32)), ptr(_f32(prob["obs_info"]))))
+        dist, rot, xf = prob.get("tether_distance", []), prob.get("tether_rotation", []), prob.get("tether_transform", [])
+        if len(dist) or len(rot) or len(xf):               # synth.ba_add_tethers, same call order as the reference's setters
+            self.AllocateFixedDistanceConstraints(len(dist)); self.AllocateRelativeRotationConstraints(len(rot))
+            self.AllocateRelativeTransformConstraints(len(xf))
+            for i, (c1, c2, d, w) in enumerate(dist):
+                self.SetFixedDistanceConstraint(i, c1, c2, d, w)
+            for i, (c1, c2, q, w) in enumerate(rot):
+                self.SetRelativeRotationConstraint(i, c1, c2, q, w)
+            for i, (c1, c2, t, q, w) in enumerate(xf):
+                self.SetRelativeTransformConstraint(i, c1, c2, t, q, w)
         return self
 
     def poses(self):

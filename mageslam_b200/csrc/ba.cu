@@ -52,6 +52,11 @@ struct BaDev {
     // large reduced systems (global BA): S stays in global memory and is factorised by the whole grid
     int big;
     double* Wk;                               // [n][kLdltNB] panel workspace (L_ik * D_k)
+    // tether edges between two cameras (ref BundlerLib.cpp:24-90, :311-350), single-CTA kernel only
+    int nT;
+    const int4* t_def;                        // [nT] (type, cam1, cam2, error dimension)
+    const double* t_meas;                     // [nT][8]: type 0 distance | type 1 q(4) | type 2 C.q(4), C.t(3); [7] = weight
+    double *t_err, *t_J;                      // [nT][6], [nT][2][36] (dim x 6 row-major per vertex)
 };
 
 // ------------------------------------------------------------------------------------------------ small math
@@ -186,6 +191,7 @@ __device__ void phase_errors(const BaDev& p, int tid, int nt)
         p.err[2 * e + 1] = p.e_uv[2 * e + 1] - (xt[1] / xt[2] * f + p.cam_cy[c]);
     }
 }
+__device__ double tether_chi2_sum(const BaDev& p);
 // ref sparse_optimizer.cpp:102-117 activeRobustChi2
 __device__ double phase_chi2(const BaDev& p, double delta, double* sh)
 {
@@ -195,6 +201,7 @@ __device__ double phase_chi2(const BaDev& p, double delta, double* sh)
         huber(p.e_info[e] * (e0 * e0 + e1 * e1), delta, r0, r1);
         acc += r0;
     }
+    if (p.nT) acc += tether_chi2_sum(p);
     return block_sum(acc, sh);
 }
 
@@ -631,6 +638,216 @@ __device__ void phase_classify(const BaDev& p, double maxErrSq, double* sh, doub
     flagged = (int)block_sum(nfl, sh);
 }
 
+// ------------------------------------------------------------------------------------------------ tether edges
+// EdgeScaleConstraint / EdgeRotationConstraint (ref BundlerLib.cpp:24-90; BaseMultiEdge, no analytic Jacobian: g2o differentiates
+// them numerically, ref core/base_multi_edge.hpp:68-118) and g2o's EdgeSE3Expmap (ref types_six_dof_expmap.h:108-127,
+// .cpp:278-293). Few edges per problem (one or two per keyframe pair), so the phases below are thread-per-item loops.
+__device__ __forceinline__ void q_mul(const double* a, const double* b, double* r)
+{
+    r[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    r[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    r[1] = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    r[2] = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+}
+// ref se3quat.h:120-125 inverse, :99-105 operator* (normalises the rotation)
+__device__ void pose_inv(const double* q, const double* t, double* qi, double* ti)
+{
+    qi[0] = -q[0]; qi[1] = -q[1]; qi[2] = -q[2]; qi[3] = q[3];
+    const double nt[3] = {t[0] * -1., t[1] * -1., t[2] * -1.};
+    q_rot(qi, nt, ti);
+}
+__device__ void pose_mul(const double* qa, const double* ta, const double* qb, const double* tb, double* q, double* t)
+{
+    double rt[3];
+    q_rot(qa, tb, rt);
+    t[0] = ta[0] + rt[0]; t[1] = ta[1] + rt[1]; t[2] = ta[2] + rt[2];
+    q_mul(qa, qb, q);
+    q_normalize_rotation(q);
+}
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) C[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+// ref se3quat.h:171-210 SE3Quat::log -> (omega, upsilon)
+__device__ void pose_log(const double* q, const double* t, double* res)
+{
+    double R[9];
+    q_to_R(q, R);
+    const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+    const double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+    double om[3], c2;
+    if (fabs(d) > 0.99999) { om[0] = 0.5 * dR[0]; om[1] = 0.5 * dR[1]; om[2] = 0.5 * dR[2]; c2 = 1. / 12.; }
+    else {
+        const double theta = acos(d);
+        const double k = theta / (2 * sqrt(1 - d * d));
+        om[0] = k * dR[0]; om[1] = k * dR[1]; om[2] = k * dR[2];
+        c2 = (1 - theta / (2 * tan(theta / 2))) / (theta * theta);
+    }
+    const double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+    double O2[9];
+    mat3_mul(O, O, O2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        res[i] = om[i];
+        double acc = 0;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            const double v = ((i == j) ? 1.0 : 0.0) - 0.5 * O[i * 3 + j] + c2 * O2[i * 3 + j];
+            acc = (j == 0) ? v * t[0] : acc + v * t[j];
+        }
+        res[3 + i] = acc;
+    }
+}
+// ref se3quat.h:217-226 adj(): [R 0; skew(t) R, R] (row-major 6x6), scaled by sgn
+__device__ void pose_adj(const double* q, const double* t, double sgn, double* A)
+{
+    double R[9], SR[9];
+    q_to_R(q, R);
+    const double Sk[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+    mat3_mul(Sk, R, SR);
+#pragma unroll
+    for (int i = 0; i < 36; i++) A[i] = 0.0 * sgn;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { A[r * 6 + c] = sgn * R[r * 3 + c]; A[(3 + r) * 6 + 3 + c] = sgn * R[r * 3 + c]; A[(3 + r) * 6 + c] = sgn * SR[r * 3 + c]; }
+}
+// computeError of the three edge types at explicit poses of their two cameras
+__device__ void tether_error(int type, const double* m, const double* q1, const double* t1, const double* q2, const double* t2, double* err)
+{
+    const double w = m[7];
+    if (type == 0) {
+        const double dx = t2[0] - t1[0], dy = t2[1] - t1[1], dz = t2[2] - t1[2];
+        err[0] = (m[0] - sqrt(dx * dx + dy * dy + dz * dz)) * w;
+    } else if (type == 1) {
+        // (v1^-1 * v2).rotation().angularDistance(measurement): d = rel * conj(meas); 2 atan2(|d.vec|, |d.w|)
+        const double c1[4] = {-q1[0], -q1[1], -q1[2], q1[3]};
+        double rel[4], d[4];
+        q_mul(c1, q2, rel);
+        q_normalize_rotation(rel);
+        const double mc[4] = {-m[0], -m[1], -m[2], m[3]};
+        q_mul(rel, mc, d);
+        err[0] = 2 * atan2(sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), fabs(d[3])) * w;
+    } else {
+        // log(v2^-1 * C * v1)
+        double qi[4], ti[3], qa[4], ta[3], qe[4], te[3];
+        pose_inv(q2, t2, qi, ti);
+        pose_mul(qi, ti, m, m + 4, qa, ta);
+        pose_mul(qa, ta, q1, t1, qe, te);
+        pose_log(qe, te, err);
+    }
+}
+__device__ __noinline__ void phase_tether_errors(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < p.nT; i += nt) {
+        const int4 d = p.t_def[i];
+        tether_error(d.x, p.t_meas + 8 * (size_t)i, p.cam_q + 4 * d.y, p.cam_t + 3 * d.y, p.cam_q + 4 * d.z, p.cam_t + 3 * d.z, p.t_err + 6 * (size_t)i);
+    }
+}
+// chi2 = e^T Omega e (no robust kernel): Omega = I for the two scalar edges (the weight multiplies the error), w I for type 2
+__device__ __noinline__ double tether_chi2_sum(const BaDev& p)      // this thread's share of the tether edges
+{
+    double acc = 0;
+    for (int i = threadIdx.x; i < p.nT; i += blockDim.x) {
+        const int4 d = p.t_def[i];
+        const double om = d.x == 2 ? p.t_meas[8 * (size_t)i + 7] : 1.0;
+        double ss = 0;
+        for (int k = 0; k < d.w; k++) { const double e = p.t_err[6 * (size_t)i + k]; ss += e * (om * e); }
+        acc += ss;
+    }
+    return acc;
+}
+// linearizeOplus: one thread per (edge, vertex, tangent direction). Scalar edges: central differences with delta = 1e-9 through
+// oplus on the vertex (push / oplus / computeError / pop twice); type 2: the analytic adjoints (thread (v, d) = (0, 0) only).
+__device__ __noinline__ void phase_tether_linearize(const BaDev& p, int tid, int nt)
+{
+    for (int it = tid; it < p.nT * 12; it += nt) {
+        const int i = it / 12, v = (it % 12) / 6, dd = it % 6;
+        const int4 d = p.t_def[i];
+        const double* m = p.t_meas + 8 * (size_t)i;
+        double* J = p.t_J + 72 * (size_t)i;
+        const double *q1 = p.cam_q + 4 * d.y, *t1 = p.cam_t + 3 * d.y, *q2 = p.cam_q + 4 * d.z, *t2 = p.cam_t + 3 * d.z;
+        if (d.x == 2) {
+            if (v != 0 || dd != 0) continue;
+            // Xi = (Tj^-1 * Tij).adj(),  Xj = -(Ti^-1 * Tij^-1).adj()
+            double qi[4], ti[3], qa[4], ta[3], qc[4], tc[3];
+            pose_inv(q2, t2, qi, ti);
+            pose_mul(qi, ti, m, m + 4, qa, ta);
+            pose_adj(qa, ta, 1.0, J);
+            pose_inv(m, m + 4, qc, tc);
+            pose_inv(q1, t1, qi, ti);
+            pose_mul(qi, ti, qc, tc, qa, ta);
+            pose_adj(qa, ta, -1.0, J + 36);
+            continue;
+        }
+        const int cam = v == 0 ? d.y : d.z;
+        if (p.cam_h[cam] < 0) continue;                         // fixed vertex: no Jacobian (ref base_multi_edge.hpp:81-83)
+        const double delta = 1e-9, scalar = 1 / (2 * delta);
+        double ep[1], em[1];
+#pragma unroll
+        for (int sgn = 0; sgn < 2; sgn++) {
+            double u[6] = {0, 0, 0, 0, 0, 0};
+            u[dd] = sgn == 0 ? delta : -delta;
+            double q[4] = {p.cam_q[4 * cam], p.cam_q[4 * cam + 1], p.cam_q[4 * cam + 2], p.cam_q[4 * cam + 3]};
+            double t[3] = {p.cam_t[3 * cam], p.cam_t[3 * cam + 1], p.cam_t[3 * cam + 2]};
+            pose_oplus(q, t, u);
+            tether_error(d.x, m, v == 0 ? q : q1, v == 0 ? t : t1, v == 0 ? q2 : q, v == 0 ? t2 : t, sgn == 0 ? ep : em);
+        }
+        J[36 * v + dd] = scalar * (ep[0] - em[0]);              // 1 x 6 row
+    }
+}
+// constructQuadraticForm, diagonal part (ref base_multi_edge.hpp:155-176, base_binary_edge.hpp:75-103): one thread per free
+// camera walks the edges in order: H_ii += A^T Omega A, b_i += A^T (-Omega e)
+__device__ __noinline__ void phase_tether_accumulate(const BaDev& p, int tid, int nt)
+{
+    for (int kf = tid; kf < p.Kf; kf += nt) {
+        const int cam = p.c_cam[kf];
+        for (int i = 0; i < p.nT; i++) {
+            const int4 d = p.t_def[i];
+            if (d.y != cam && d.z != cam) continue;
+            const int v = d.y == cam ? 0 : 1;
+            const double om = d.x == 2 ? p.t_meas[8 * (size_t)i + 7] : 1.0;
+            const double* A = p.t_J + 72 * (size_t)i + 36 * v;
+            const double* e = p.t_err + 6 * (size_t)i;
+            for (int r = 0; r < 6; r++) {
+                double bb = 0;
+                for (int k = 0; k < d.w; k++) bb += A[k * 6 + r] * (-(om * e[k]));
+                p.bp[6 * kf + r] += bb;
+                for (int c = 0; c < 6; c++) {
+                    double hh = 0;
+                    for (int k = 0; k < d.w; k++) hh += (A[k * 6 + r] * om) * A[k * 6 + c];
+                    p.Hpp[36 * (size_t)kf + r * 6 + c] += hh;
+                }
+            }
+        }
+    }
+}
+// off-diagonal part: H_ij += A^T Omega B goes straight into the assembled reduced system (warp 0, edges in order)
+__device__ __noinline__ void phase_tether_offdiag(const BaDev& p, int warp, int lane)
+{
+    if (warp != 0) return;
+    for (int i = 0; i < p.nT; i++) {
+        const int4 d = p.t_def[i];
+        const int h1 = p.cam_h[d.y], h2 = p.cam_h[d.z];
+        if (h1 >= 0 && h2 >= 0) {
+            const double om = d.x == 2 ? p.t_meas[8 * (size_t)i + 7] : 1.0;
+            const double* A = p.t_J + 72 * (size_t)i;
+            const double* B = A + 36;
+            for (int el = lane; el < 36; el += 32) {
+                const int r = el / 6, c = el % 6;
+                double hh = 0;
+                for (int k = 0; k < d.w; k++) hh += (A[k * 6 + r] * om) * B[k * 6 + c];
+                p.S[(size_t)(6 * h1 + r) * p.n + 6 * h2 + c] += hh;
+                p.S[(size_t)(6 * h2 + c) * p.n + 6 * h1 + r] += hh;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the persistent LM kernel
 // One CTA per problem runs StepBundleAdjustment's whole loop: for each Huber width one g2o LM iteration
 // (ref optimization_algorithm_levenberg.cpp:57-149, up to 10 lambda trials), then the outlier classification.
@@ -694,14 +911,17 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
         if (s_stop) break;
         const double delta = (double)huberW[it];
         phase_errors(p, tid, nt);
+        if (p.nT) phase_tether_errors(p, tid, nt);
         __syncthreads();
         double currentChi = phase_chi2(p, delta, sh);
         PH(0);
         phase_build_points_lm(p, delta, tid, nt);
         phase_build_cams(p, delta, warp, nw, lane);
+        if (p.nT) phase_tether_linearize(p, tid, nt);
         __syncthreads();
         phase_finish_cams(p, tid, nt);
         __syncthreads();
+        if (p.nT) { phase_tether_accumulate(p, tid, nt); __syncthreads(); }
         PH(1);
         if (iteration == 0) {
             const double md = phase_max_diag(p, sh);
@@ -720,6 +940,7 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
             phase_schur_blocks(p, lambda, warp, nw, lane);
             __syncthreads();
             phase_finish_bs(p, tid, nt);
+            if (p.nT) phase_tether_offdiag(p, warp, lane);
             __syncthreads();
             PH(3);
             const bool ok2 = phase_ldlt_solve(p, sh);
@@ -731,6 +952,7 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
             __syncthreads();
             PH(6);
             phase_errors(p, tid, nt);
+            if (p.nT) phase_tether_errors(p, tid, nt);
             __syncthreads();
             double tempChi = phase_chi2(p, delta, sh);
             if (!ok2) tempChi = DBL_MAX;
@@ -1325,6 +1547,8 @@ template <class T> void R_to_q_host(const T* m, T* q)          // Eigen quaterni
 }
 
 struct HostObs { double u, v, info; int cam, pt; bool set, removed; long seq; };
+// tether edge: type 0 fixed distance, 1 relative rotation, 2 relative transform; m = measurement (+ weight in m[7])
+struct HostTether { int type = -1, c1 = -1, c2 = -1; double m[8] = {0, 0, 0, 0, 0, 0, 0, 0}; bool set = false; long seq = -1; };
 
 } // namespace
 
@@ -1335,6 +1559,7 @@ struct mage_ba_s {
     std::vector<double> cam_q, cam_t, cam_f, cam_cx, cam_cy, pt_X;
     std::vector<char> cam_fixed, cam_set, pt_set;
     std::vector<HostObs> obs;
+    std::vector<HostTether> teth[3];    // the three constraint pools of BundlerLib.h:41-48
     long next_seq = 0;
     bool dirty = true, useless = false, state_uploaded = false, host_state_valid = true;
     double user_lambda_init = 0, lambda = -1;
@@ -1411,6 +1636,14 @@ static int ba_build_structure(mage_ba_t h)
     const int Ea = (int)h->active.size();
     std::vector<char> camA(h->K, 0), ptA(h->P, 0);
     for (int e : h->active) { camA[h->obs[e].cam] = 1; ptA[h->obs[e].pt] = 1; }
+    // tether edges: active unless both cameras are fixed (allVerticesFixed); they make their cameras active vertices
+    std::vector<const HostTether*> tact;
+    for (auto& pool : h->teth) for (const HostTether& t : pool) {
+        if (!t.set || (h->cam_fixed[t.c1] && h->cam_fixed[t.c2])) continue;
+        tact.push_back(&t); camA[t.c1] = 1; camA[t.c2] = 1;
+    }
+    std::sort(tact.begin(), tact.end(), [](const HostTether* a, const HostTether* b) { return a->seq < b->seq; });
+    const int nT = (int)tact.size();
     std::vector<int> cam_h(h->K, -1), pt_l(h->P, -1), c_cam, l_pt;
     for (int k = 0; k < h->K; k++) if (camA[k] && !h->cam_fixed[k]) { cam_h[k] = (int)c_cam.size(); c_cam.push_back(k); }
     if (!h->points_fixed)       // point vertex ids count down (ref BundlerLib.cpp:210-218): Hessian order = descending index
@@ -1424,7 +1657,13 @@ static int ba_build_structure(mage_ba_t h)
     h->dirty = false;
     h->iteration_reset = 1;
     h->stats[3]++;
-    if (h->useless) { h->dev.Ea = 0; return MAGE_OK; }
+    if (h->useless) { h->dev.Ea = 0; h->dev.nT = 0; return MAGE_OK; }
+    std::vector<int4> t_def(nT);
+    std::vector<double> t_meas(8 * (size_t)nT);
+    for (int i = 0; i < nT; i++) {
+        t_def[i] = make_int4(tact[i]->type, tact[i]->c1, tact[i]->c2, tact[i]->type == 2 ? 6 : 1);
+        for (int k = 0; k < 8; k++) t_meas[8 * (size_t)i + k] = tact[i]->m[k];
+    }
 
     std::vector<int> e_cam(Ea), e_pt(Ea), e_l(Ea);
     std::vector<double> e_uv(2 * (size_t)Ea), e_info(Ea);
@@ -1483,6 +1722,7 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
     size_t o_Wk = rD(big ? (size_t)n * kLdltNB : 1);
+    size_t o_tdef = W.reserve(sizeof(int4) * std::max(nT, 1)), o_tmeas = rD(8 * (size_t)nT), o_terr = rD(6 * (size_t)nT), o_tJ = rD(72 * (size_t)nT);
     MAGE_CUDA_TRY(W.commit());
     MAGE_CUDA_TRY(cudaMemsetAsync(W.base, 0, W.size, h->stream));
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
@@ -1498,6 +1738,7 @@ static int ba_build_structure(mage_ba_t h)
     MAGE_CUDA_TRY(up(o_cedges, c_edges.data(), sizeof(int) * c_edges.size()));
     MAGE_CUDA_TRY(up(o_bij, blk_ij.data(), sizeof(int) * blk_ij.size())); MAGE_CUDA_TRY(up(o_bptr, blk_ptr.data(), sizeof(int) * blk_ptr.size()));
     MAGE_CUDA_TRY(up(o_pairs, pairs.data(), sizeof(int2) * pairs.size()));
+    MAGE_CUDA_TRY(up(o_tdef, t_def.data(), sizeof(int4) * nT)); MAGE_CUDA_TRY(up(o_tmeas, t_meas.data(), sizeof(double) * 8 * nT));
     BaDev& d = h->dev;
     d.K = h->K; d.P = h->P; d.Ea = Ea; d.Kf = Kf; d.Pl = Pl; d.n = n; d.nblk = nblk; d.cam_parts = cam_parts;
     d.cam_h = W.at<int>(o_camh); d.e_cam = W.at<int>(o_ecam); d.e_pt = W.at<int>(o_ept); d.e_l = W.at<int>(o_el);
@@ -1513,6 +1754,7 @@ static int ba_build_structure(mage_ba_t h)
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
     d.big = big; d.Wk = W.at<double>(o_Wk);
+    d.nT = nT; d.t_def = W.at<int4>(o_tdef); d.t_meas = W.at<double>(o_tmeas); d.t_err = W.at<double>(o_terr); d.t_J = W.at<double>(o_tJ);
     MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
     // pageable staging vectors go out of scope on return: make sure the copies have been consumed
     MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1647,6 +1889,65 @@ extern "C" int mage_ba_set_observations_bulk(mage_ba_t h, int n, const float* uv
     for (int e = 0; e < n; e++) { int rc = mage_ba_set_observation(h, e, uv + 2 * (size_t)e, cam[e], pt[e], info[e]); if (rc) return rc; }
     return MAGE_OK;
 }
+// ---- tether edges between two cameras (ref BundlerLib.h:41-48, BundlerLib.cpp:243-259 pools, :311-350 setters) ----------
+static int ba_alloc_tethers(mage_ba_t h, int pool, int count, const char* who)
+{
+    MAGE_REQUIRE(h && count >= 0, MAGE_ERR_INVALID, "%s: bad argument", who);
+    h->teth[pool].assign(count, HostTether());
+    return MAGE_OK;
+}
+extern "C" int mage_ba_alloc_fixed_distance_constraints(mage_ba_t h, int count) { return ba_alloc_tethers(h, 0, count, "mage_ba_alloc_fixed_distance_constraints"); }
+extern "C" int mage_ba_alloc_relative_rotation_constraints(mage_ba_t h, int count) { return ba_alloc_tethers(h, 1, count, "mage_ba_alloc_relative_rotation_constraints"); }
+extern "C" int mage_ba_alloc_relative_transform_constraints(mage_ba_t h, int count) { return ba_alloc_tethers(h, 2, count, "mage_ba_alloc_relative_transform_constraints"); }
+
+static int ba_tether_slot(mage_ba_t h, int pool, int idx, int cam1, int cam2, HostTether** out, const char* who)
+{
+    MAGE_REQUIRE(h && idx >= 0 && idx < (int)h->teth[pool].size() && cam1 >= 0 && cam1 < h->K && cam2 >= 0 && cam2 < h->K && cam1 != cam2,
+                 MAGE_ERR_INVALID, "%s: bad argument (idx %d cam1 %d cam2 %d)", who, idx, cam1, cam2);
+    HostTether& t = h->teth[pool][idx];
+    t = HostTether();
+    t.type = pool; t.c1 = cam1; t.c2 = cam2; t.set = true; t.seq = h->next_seq++;
+    h->dirty = true;
+    *out = &t;
+    return MAGE_OK;
+}
+// error = (distance - |t2 - t1|) * weight on the view-transform translations (ref :24-55, :311-322)
+extern "C" int mage_ba_set_fixed_distance_constraint(mage_ba_t h, int idx, int cam1, int cam2, float distance, float weight)
+{
+    HostTether* t;
+    int rc = ba_tether_slot(h, 0, idx, cam1, cam2, &t, "mage_ba_set_fixed_distance_constraint");
+    if (rc) return rc;
+    t->m[0] = distance; t->m[7] = weight;
+    return MAGE_OK;
+}
+// error = angularDistance((T1^-1 T2).rotation(), deltaRotation) * weight; the quaternion is used as given (ref :57-90, :324-336)
+extern "C" int mage_ba_set_relative_rotation_constraint(mage_ba_t h, int idx, int cam1, int cam2, const float* q_xyzw, float weight)
+{
+    MAGE_REQUIRE(q_xyzw, MAGE_ERR_INVALID, "mage_ba_set_relative_rotation_constraint: null quaternion");
+    HostTether* t;
+    int rc = ba_tether_slot(h, 1, idx, cam1, cam2, &t, "mage_ba_set_relative_rotation_constraint");
+    if (rc) return rc;
+    for (int i = 0; i < 4; i++) t->m[i] = q_xyzw[i];
+    t->m[7] = weight;
+    return MAGE_OK;
+}
+// g2o EdgeSE3Expmap: error = log(T2^-1 C T1), C = SE3Quat(deltaRotation, deltaPosition) (normalised), information = weight I (ref :338-350)
+extern "C" int mage_ba_set_relative_transform_constraint(mage_ba_t h, int idx, int cam1, int cam2, const float* delta_position,
+                                                         const float* q_xyzw, float weight)
+{
+    MAGE_REQUIRE(q_xyzw && delta_position, MAGE_ERR_INVALID, "mage_ba_set_relative_transform_constraint: null argument");
+    HostTether* t;
+    int rc = ba_tether_slot(h, 2, idx, cam1, cam2, &t, "mage_ba_set_relative_transform_constraint");
+    if (rc) return rc;
+    double q[4] = {q_xyzw[0], q_xyzw[1], q_xyzw[2], q_xyzw[3]};
+    if (q[3] < 0) for (int i = 0; i < 4; i++) q[i] = -q[i];
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) t->m[i] = q[i] / n;
+    for (int i = 0; i < 3; i++) t->m[4 + i] = delta_position[i];
+    t->m[7] = weight;
+    return MAGE_OK;
+}
+
 // ref BundlerLib.cpp:123-130 + :352-355: resets the iteration counter to 0 and sets the user lambda
 extern "C" int mage_ba_set_lambda(mage_ba_t h, float l)
 {
@@ -1733,7 +2034,9 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
     if (rc) return rc;
     if (!h->useless) {
         const size_t coop_smem = (h->dev.big ? kBigScratchBytes : ba_smem_need_S(h->dev.n)) + ba_smem_need_cams(h->dev.K);
-        const bool use_coop = h->coop_blocks > 1 && h->dev.K <= kBaMaxSmemCams && coop_smem <= 128 * 1024 && (h->dev.Ea >= 1024 || h->dev.big);
+        // tether edges are handled by the single-CTA kernel only (windows with tethers are stereo / IMU local BA, never the global size)
+        MAGE_REQUIRE(!(h->dev.nT > 0 && h->dev.big), MAGE_ERR_UNSUPPORTED, "tether edges are not supported on problems with %d pose unknowns", h->dev.n);
+        const bool use_coop = h->dev.nT == 0 && h->coop_blocks > 1 && h->dev.K <= kBaMaxSmemCams && coop_smem <= 128 * 1024 && (h->dev.Ea >= 1024 || h->dev.big);
         MAGE_REQUIRE(use_coop || !h->dev.big, MAGE_ERR_UNSUPPORTED, "reduced camera system of %d unknowns needs the cooperative kernel (not available)", h->dev.n);
         const int coop_grid = h->dev.big ? h->coop_blocks_max : h->coop_blocks;
         ProfScope ps(PROF_BA_STEP, h->stream);

@@ -10,7 +10,7 @@ from mageslam_b200 import synth
 from mageslam_b200.bundler import BundlerLib, BundlerParameters, StepMany
 from tests.ba_checks import TOL, best_checker, run_side_by_side
 from tests.oracle_ba import BaOracle, rel_frobenius
-from tools.gen_ba_golden import CASES
+from tools.gen_ba_golden import CASES, build_problem
 
 pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "ba_golden.npz"))
@@ -42,7 +42,7 @@ def test_local_ba_tier_config_matches_reference(variant):
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_matches_reference_golden_vectors(name):
     kw, pf, hub, mx, calls = CASES[name]
-    prob = synth.ba_problem(**kw)
+    prob = build_problem(kw)
     gpu = BundlerLib(BundlerParameters(pf)).load(prob)
     for c in range(calls):
         mean = gpu.StepBundleAdjustment(hub, mx)
@@ -51,8 +51,65 @@ def test_matches_reference_golden_vectors(name):
         assert rel_frobenius(rot, GOLD["%s/%d/rot" % (name, c)]) < TOL
         assert rel_frobenius(gpu.points(), GOLD["%s/%d/pts" % (name, c)]) < TOL
         gmean, glam = GOLD["%s/%d/scalars" % (name, c)]
-        assert abs(mean - gmean) <= 1e-4 * abs(gmean) and abs(gpu.GetCurrentLambda() - glam) <= 1e-3 * abs(glam)
+        assert abs(gpu.GetCurrentLambda() - glam) <= 1e-3 * abs(glam)
+        if "tethers" not in kw:       # with tether edges the reference's returned mean is undefined behaviour
+            assert abs(mean - gmean) <= 1e-4 * abs(gmean)
         assert np.array_equal(gpu.last_outliers.astype(np.int64), GOLD["%s/%d/outliers" % (name, c)])
+
+
+@pytest.mark.parametrize("kind", ["distance", "rotation", "transform", "all", "all_outliers"])
+def test_tether_edges_match_reference(kind):
+    """Fixed-distance / relative-rotation (numeric g2o Jacobians) and relative-transform (EdgeSE3Expmap) constraints between
+    cameras (ref BundlerLib.cpp:24-90, :311-350) at the tier's local-BA size, against the compiled reference when present."""
+    n = dict(distance=(6, 0, 0), rotation=(0, 6, 0), transform=(0, 0, 6), all=(5, 5, 5), all_outliers=(4, 4, 4))[kind]
+    base = synth.ba_problem(seed=31, outlier_frac=0.05 if kind == "all_outliers" else 0.0)
+    prob = synth.ba_add_tethers(base, seed=6, n_distance=n[0], n_rotation=n[1], n_transform=n[2], noise=1e-2)
+    gpu = BundlerLib(BundlerParameters(False)).load(prob)
+    chk = best_checker().load(prob)
+    free = BundlerLib(BundlerParameters(False)).load(base)
+    mx = 7.25 if kind == "all_outliers" else 1e9
+    rep = run_side_by_side(gpu, chk, [1.8, 1.8], mx, 3, tag="tether_" + kind, check_mean=False)
+    assert max(max(r) for r in rep) < 1e-6
+    # the constraints really pull: the tethered solution is far (>> tolerance) from the untethered one
+    for _ in range(3):
+        free.StepBundleAdjustment([1.8, 1.8], mx)
+    assert rel_frobenius(free.poses()[0], gpu.poses()[0]) > 1e-4
+    # ... and the port oracle agrees on the mean error over observation edges (tether edges never enter it)
+    port = BaOracle("port").load(prob)
+    g2 = BundlerLib(BundlerParameters(False)).load(prob)
+    for _ in range(2):
+        m_port, _o = port.StepBundleAdjustment([1.8, 1.8], mx)
+        m_gpu = g2.StepBundleAdjustment([1.8, 1.8], mx)
+        assert abs(m_gpu - m_port) <= 1e-4 * abs(m_port)
+
+
+def test_tether_edge_cases():
+    from mageslam_b200._lib import MageError
+    base = synth.ba_problem(K=6, P=200, obs_per_point=3, seed=33)
+    # a camera that is reachable only through a tether edge (no observations) still becomes an active vertex
+    prob = dict(base)
+    keep = base["obs_cam"] != 5
+    for k in ("obs_uv", "obs_cam", "obs_pt", "obs_info"):
+        prob[k] = base[k][keep]
+    prob = synth.ba_add_tethers(prob, seed=2, n_distance=0, n_rotation=0, n_transform=0)
+    Rm, t = base["true_cam_R"], base["true_cam_t"]
+    Rc = Rm[5] @ Rm[4].T
+    from mageslam_b200.synth import _quat_xyzw
+    prob["tether_transform"] = [(4, 5, (t[5] - Rc @ t[4]).astype(np.float32), _quat_xyzw(Rc).astype(np.float32), 1e5)]
+    prob["tether_distance"] = [(0, 1, 1.0, 10.0)]          # both cameras fixed: inactive edge
+    gpu = BundlerLib(BundlerParameters(False)).load(prob)
+    chk = best_checker().load(prob)
+    rep = run_side_by_side(gpu, chk, [1.8], 1e9, 4, tag="tether_only_camera", check_mean=False)
+    assert max(max(r) for r in rep) < 1e-6
+    # StepMany takes problems with tether edges too (same single-CTA kernel)
+    a = BundlerLib(BundlerParameters(False)).load(prob); b = BundlerLib(BundlerParameters(False)).load(prob)
+    StepMany([a], [1.8], 1e9); b.StepBundleAdjustment([1.8], 1e9)
+    assert rel_frobenius(a.state_f64()[0], b.state_f64()[0]) == 0
+    # argument validation
+    with pytest.raises(MageError):
+        gpu.SetFixedDistanceConstraint(0, 2, 2, 1.0, 1.0)          # both ends the same camera
+    with pytest.raises(MageError):
+        gpu.SetRelativeRotationConstraint(7, 1, 2, [0, 0, 0, 1], 1.0)   # slot outside the pool
 
 
 def test_pose_only_ba_like_track_local_map():

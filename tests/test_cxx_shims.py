@@ -34,6 +34,9 @@ def test_bundlerlib_shim_is_source_compatible_with_reference_call_sites():
              ' b.AllocateCameras(1); b.AllocateMapPoints(1); b.AllocateObservations(1);\n'
              ' b.SetCameraPose(0, Eigen::Map<const Eigen::Vector3f>(p), Eigen::Map<const Eigen::Matrix3f>(R), Eigen::Map<const Eigen::Vector4f>(k), false);\n'
              ' b.SetMapPoint(0, Eigen::Map<const Eigen::Vector3f>(p)); b.SetObservation(0, Eigen::Map<const Eigen::Vector2f>(uv), 0, 0, 1.0f);\n'
+             ' b.AllocateFixedDistanceConstraints(1); b.SetFixedDistanceConstraint(0, 0, 1); b.AllocateRelativeRotationConstraints(1);\n'
+             ' b.SetRelativeRotationConstraint(0, 0, 1, Eigen::Quaternionf::Identity(), 2.f); b.AllocateRelativeTransformConstraints(1);\n'
+             ' b.SetRelativeTransformConstraint(0, 0, 1, Eigen::Map<const Eigen::Vector3f>(p), Eigen::Quaternionf::Identity(), 3.f);\n'
              ' std::vector<unsigned int> out; float hub[3]={2,2,2}; float e = b.StepBundleAdjustment(hub, 25.f, out);\n'
              ' b.GetPose(0, Eigen::Map<Eigen::Vector3f>(p), Eigen::Map<Eigen::Matrix3f>(R)); b.GetPoint(0, Eigen::Map<Eigen::Vector3f>(p)); b.SetCurrentLambda(1.f);\n'
              ' return e + b.GetCurrentLambda(); }\n',
