@@ -57,6 +57,17 @@ struct BaDev {
     const int4* t_def;                        // [nT] (type, cam1, cam2, error dimension)
     const double* t_meas;                     // [nT][8]: type 0 distance | type 1 q(4) | type 2 C.q(4), C.t(3); [7] = weight
     double *t_err, *t_J;                      // [nT][6], [nT][2][36] (dim x 6 row-major per vertex)
+    // one-CTA-per-problem kernel: rotation matrices of the current camera state (row-major 3x3 per camera)
+    double* cam_R;                            // [K][9]
+    // local-window fast path (fast != 0): landmarks in batches of <= kFastBE edges whose pose-landmark blocks live in shared
+    // memory only; thread pair i owns the (block, part) item i and accumulates its share of the Schur products in registers
+    int fast, nb, nitems;
+    const int* batch_ptr;                     // [nb + 1] landmark boundaries
+    const int4* item_def;                     // [nitems] (block, part, parts of the block, 0)
+    const int2* blk_items;                    // [nblk] (first item, parts)
+    const int* cam_diag;                      // [Kf] index of the diagonal block of a free camera
+    const int* bb_ptr;                        // [nb * nblk + 1] pair ranges per (batch, block)
+    const ushort2* bpairs;                    // (edge of i1, edge of i2) relative to the batch's first edge
 };
 
 // ------------------------------------------------------------------------------------------------ small math
@@ -848,6 +859,618 @@ __device__ __noinline__ void phase_tether_offdiag(const BaDev& p, int warp, int 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ one-CTA fast path
+// Phases of k_ba_step (one CTA per problem, many problems per launch). Same algorithm as above, arranged so that a thread's
+// dependent chain is short: the projection of an edge is evaluated once per state (a = x/z, b = y/z, 1/z kept in a compact
+// per-edge record, one reciprocal instead of g2o's dozen divisions), every Jacobian is rebuilt from that record and the camera's
+// rotation matrix in shared memory, landmark phases run one thread per landmark with the landmark block in registers, and the
+// Schur products give every lane half of a 6x6 block so that the accumulators stay in registers without spilling.
+constexpr int kRec = 4;                     // doubles per edge record: a, b, 1/z, (pad) -- 32-byte aligned
+constexpr int kWDs = 20;                    // doubles per WD record in this path: rows 0..2 | pad | rows 3..5 | pad (two 16-byte aligned halves)
+
+__device__ void f_cam_R(const BaDev& p, int tid, int nt)
+{
+    for (int c = tid; c < p.K; c += nt) q_to_R(p.cam_q + 4 * c, p.cam_R + 9 * c);
+}
+// computeError of every active edge at the current state (ref types_six_dof_expmap.h:140-147) + the edge record
+__device__ void f_project(const BaDev& p, int tid, int nt)
+{
+#pragma unroll 2
+    for (int e = tid; e < p.Ea; e += nt) {
+        const int c = p.e_cam[e];
+        const double* __restrict__ R = p.cam_R + 9 * c;
+        const double* __restrict__ X = p.pt_X + 3 * (size_t)p.e_pt[e];
+        const double X0 = X[0], X1 = X[1], X2 = X[2];
+        const double x = R[0] * X0 + R[1] * X1 + R[2] * X2 + p.cam_t[3 * c];
+        const double y = R[3] * X0 + R[4] * X1 + R[5] * X2 + p.cam_t[3 * c + 1];
+        const double z = R[6] * X0 + R[7] * X1 + R[8] * X2 + p.cam_t[3 * c + 2];
+        const double iz = 1.0 / z, a = x * iz, b = y * iz, f = p.cam_f[c];
+        const double2 uv = *reinterpret_cast<const double2*>(p.e_uv + 2 * (size_t)e);
+        *reinterpret_cast<double2*>(p.err + 2 * (size_t)e) = make_double2(uv.x - (a * f + p.cam_cx[c]), uv.y - (b * f + p.cam_cy[c]));
+        double2* rec = reinterpret_cast<double2*>(p.Hc + kRec * (size_t)e);
+        rec[0] = make_double2(a, b);
+        rec[1] = make_double2(iz, 0.0);
+    }
+}
+// Jacobians of ref types_six_dof_expmap.cpp:295-331 from the edge record: Ji = -(f/z) [[1 0 -a], [0 1 -b]] R  (2x3),
+// Jj = f [[ab, -(1+a^2), b, -1/z, 0, a/z], [1+b^2, -ab, -a, 0, -1/z, b/z]]  (2x6, rotation first)
+__device__ __forceinline__ void f_point_jac(const double* __restrict__ R, double a, double b, double iz, double f, double* J0, double* J1)
+{
+    const double g = -(iz * f);
+#pragma unroll
+    for (int c = 0; c < 3; c++) { J0[c] = g * (R[c] - a * R[6 + c]); J1[c] = g * (R[3 + c] - b * R[6 + c]); }
+}
+__device__ __forceinline__ void f_pose_jac(double a, double b, double iz, double f, double* P0, double* P1)
+{
+    const double ab = a * b * f, izf = iz * f;
+    P0[0] = ab; P0[1] = -(f + a * a * f); P0[2] = b * f; P0[3] = -izf; P0[4] = 0.0; P0[5] = a * izf;
+    P1[0] = f + b * b * f; P1[1] = -ab; P1[2] = -(a * f); P1[3] = 0.0; P1[4] = -izf; P1[5] = b * izf;
+}
+// landmark blocks H_ll, b_l and pose-landmark blocks W (ref block_solver.hpp:463-521, base_binary_edge.hpp:62-134)
+__device__ void f_build_points(const BaDev& p, double delta, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double H00 = 0, H01 = 0, H02 = 0, H11 = 0, H12 = 0, H22 = 0, b0 = 0, b1 = 0, b2 = 0;
+        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
+#pragma unroll 2
+        for (int e = k0; e < k1; e++) {                  // edges are stored grouped by landmark
+            const int c = p.e_cam[e];
+            const double2* rec = reinterpret_cast<const double2*>(p.Hc + kRec * (size_t)e);
+            const double2 ab = rec[0];
+            const double iz = rec[1].x, f = p.cam_f[c];
+            const double2 er = *reinterpret_cast<const double2*>(p.err + 2 * (size_t)e);
+            const double info = p.e_info[e];
+            double r0, r1;
+            huber(info * (er.x * er.x + er.y * er.y), delta, r0, r1);
+            const double w = r1 * info, o0 = -info * er.x * r1, o1 = -info * er.y * r1;
+            double J0[3], J1[3];
+            f_point_jac(p.cam_R + 9 * c, ab.x, ab.y, iz, f, J0, J1);
+            const double w0[3] = {w * J0[0], w * J0[1], w * J0[2]}, w1[3] = {w * J1[0], w * J1[1], w * J1[2]};
+            H00 += w0[0] * J0[0] + w1[0] * J1[0]; H01 += w0[0] * J0[1] + w1[0] * J1[1]; H02 += w0[0] * J0[2] + w1[0] * J1[2];
+            H11 += w0[1] * J0[1] + w1[1] * J1[1]; H12 += w0[1] * J0[2] + w1[1] * J1[2]; H22 += w0[2] * J0[2] + w1[2] * J1[2];
+            b0 += J0[0] * o0 + J1[0] * o1; b1 += J0[1] * o0 + J1[1] * o1; b2 += J0[2] * o0 + J1[2] * o1;
+            if (p.cam_h[c] >= 0) {
+                double P0[6], P1[6];
+                f_pose_jac(ab.x, ab.y, iz, f, P0, P1);
+                double Wv[18];
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++) Wv[r * 3 + cc] = P0[r] * w0[cc] + P1[r] * w1[cc];
+                double2* W2 = reinterpret_cast<double2*>(p.W + 18 * (size_t)e);
+#pragma unroll
+                for (int i = 0; i < 9; i++) W2[i] = make_double2(Wv[2 * i], Wv[2 * i + 1]);
+            }
+        }
+        double* Hl = p.Hll + 9 * (size_t)li;
+        Hl[0] = H00; Hl[1] = H01; Hl[2] = H02; Hl[3] = H01; Hl[4] = H11; Hl[5] = H12; Hl[6] = H02; Hl[7] = H12; Hl[8] = H22;
+        p.bl[3 * li] = b0; p.bl[3 * li + 1] = b1; p.bl[3 * li + 2] = b2;
+    }
+}
+// pose blocks H_pp (upper 21) and b_p: one warp per (camera, part) slice, lanes stride the slice (same partials as phase_build_cams)
+__device__ void f_build_cams(const BaDev& p, double delta, int warp, int nwarps, int lane)
+{
+    const int items = p.Kf * p.cam_parts;
+    for (int it = warp; it < items; it += nwarps) {
+        const int kf = it / p.cam_parts, part = it % p.cam_parts;
+        const int beg = p.c_ptr[kf], end = p.c_ptr[kf + 1], len = end - beg;
+        const int per = (len + p.cam_parts - 1) / p.cam_parts;
+        const int s0 = beg + part * per, s1 = min(s0 + per, end);
+        const double f = p.cam_f[p.c_cam[kf]];
+        double A[21], b[6];
+#pragma unroll
+        for (int i = 0; i < 21; i++) A[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) b[i] = 0;
+        for (int k = s0 + lane; k < s1; k += 32) {
+            const int e = p.c_edges[k];
+            const double2* rec = reinterpret_cast<const double2*>(p.Hc + kRec * (size_t)e);
+            const double2 ab = rec[0];
+            const double iz = rec[1].x;
+            const double2 er = *reinterpret_cast<const double2*>(p.err + 2 * (size_t)e);
+            const double info = p.e_info[e];
+            double r0, r1;
+            huber(info * (er.x * er.x + er.y * er.y), delta, r0, r1);
+            const double w = r1 * info, o0 = -info * er.x * r1, o1 = -info * er.y * r1;
+            double P0[6], P1[6];
+            f_pose_jac(ab.x, ab.y, iz, f, P0, P1);
+            int idx = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                b[r] += P0[r] * o0 + P1[r] * o1;
+                const double a0 = w * P0[r], a1 = w * P1[r];
+#pragma unroll
+                for (int c = r; c < 6; c++) A[idx++] += a0 * P0[c] + a1 * P1[c];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 21; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) A[i] += __shfl_down_sync(0xffffffffu, A[i], o);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b[i] += __shfl_down_sync(0xffffffffu, b[i], o);
+        if (lane == 0) {
+            double* dst = p.part + (size_t)it * 27;
+#pragma unroll
+            for (int i = 0; i < 21; i++) dst[i] = A[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++) dst[21 + i] = b[i];
+        }
+    }
+}
+// Schur step 1 (ref block_solver.hpp:337-352), one thread per landmark: D^-1 = (H_ll + lambda I)^-1 once, db = D^-1 b_l, then
+// WD = W D^-1 for each of its edges with a free camera (stored as two 16-byte aligned halves of 3 rows)
+__device__ void f_schur_points(const BaDev& p, double lambda, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        const double* __restrict__ Hl = p.Hll + 9 * (size_t)li;
+        const double A0 = Hl[0] + lambda, A1 = Hl[1], A2 = Hl[2], A3 = Hl[3], A4 = Hl[4] + lambda, A5 = Hl[5], A6 = Hl[6], A7 = Hl[7], A8 = Hl[8] + lambda;
+        const double c00 = A4 * A8 - A5 * A7, c01 = A5 * A6 - A3 * A8, c02 = A3 * A7 - A4 * A6;
+        const double id = 1.0 / (A0 * c00 + A1 * c01 + A2 * c02);
+        double D[9];
+        D[0] = c00 * id; D[1] = (A2 * A7 - A1 * A8) * id; D[2] = (A1 * A5 - A2 * A4) * id;
+        D[3] = c01 * id; D[4] = (A0 * A8 - A2 * A6) * id; D[5] = (A2 * A3 - A0 * A5) * id;
+        D[6] = c02 * id; D[7] = (A1 * A6 - A0 * A7) * id; D[8] = (A0 * A4 - A1 * A3) * id;
+#pragma unroll
+        for (int i = 0; i < 9; i++) p.Dinv[9 * (size_t)li + i] = D[i];
+        const double b0 = p.bl[3 * li], b1 = p.bl[3 * li + 1], b2 = p.bl[3 * li + 2];
+        p.db[3 * li] = D[0] * b0 + D[1] * b1 + D[2] * b2;
+        p.db[3 * li + 1] = D[3] * b0 + D[4] * b1 + D[5] * b2;
+        p.db[3 * li + 2] = D[6] * b0 + D[7] * b1 + D[8] * b2;
+        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
+#pragma unroll 2
+        for (int e = k0; e < k1; e++) {
+            if (p.cam_h[p.e_cam[e]] < 0) continue;
+            const double2* W2 = reinterpret_cast<const double2*>(p.W + 18 * (size_t)e);
+            double w[18];
+#pragma unroll
+            for (int i = 0; i < 9; i++) { const double2 v = W2[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+            double o[kWDs];
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) o[(r / 3) * 10 + (r % 3) * 3 + c] = w[r * 3] * D[c] + w[r * 3 + 1] * D[3 + c] + w[r * 3 + 2] * D[6 + c];
+            o[9] = 0.0; o[19] = 0.0;
+            double2* O2 = reinterpret_cast<double2*>(p.WD + kWDs * (size_t)e);
+#pragma unroll
+            for (int i = 0; i < kWDs / 2; i++) O2[i] = make_double2(o[2 * i], o[2 * i + 1]);
+        }
+    }
+    for (int i = tid; i < p.n * p.n; i += nt) p.S[i] = 0.0;
+}
+// Schur step 2 (ref block_solver.hpp:354-390): one warp per upper block, a lane pair per (edge, edge) product -- the even lane
+// accumulates rows 0..2 of the 6x6 block, the odd lane rows 3..5 (18 accumulators each) -- then a parity-preserving shuffle tree
+__device__ void f_schur_blocks(const BaDev& p, double lambda, int warp, int nwarps, int lane)
+{
+    const int half = lane & 1;
+    for (int bi = warp; bi < p.nblk; bi += nwarps) {
+        const int i1 = p.blk_ij[2 * bi], i2 = p.blk_ij[2 * bi + 1];
+        double acc[18];
+#pragma unroll
+        for (int i = 0; i < 18; i++) acc[i] = 0;
+        const int end = p.blk_ptr[bi + 1];
+        for (int k = p.blk_ptr[bi] + (lane >> 1); k < end; k += 16) {
+            const int2 pr = p.pairs[k];
+            const double2* __restrict__ A2 = reinterpret_cast<const double2*>(p.WD + kWDs * (size_t)pr.x + 10 * half);
+            const double2* __restrict__ B2 = reinterpret_cast<const double2*>(p.W + 18 * (size_t)pr.y);
+            double a[10], b[18];
+#pragma unroll
+            for (int i = 0; i < 5; i++) { const double2 v = A2[i]; a[2 * i] = v.x; a[2 * i + 1] = v.y; }
+#pragma unroll
+            for (int i = 0; i < 9; i++) { const double2 v = B2[i]; b[2 * i] = v.x; b[2 * i + 1] = v.y; }
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[r * 6 + c] += a[r * 3] * b[c * 3] + a[r * 3 + 1] * b[c * 3 + 1] + a[r * 3 + 2] * b[c * 3 + 2];
+        }
+#pragma unroll
+        for (int i = 0; i < 18; i++)
+#pragma unroll
+            for (int o = 16; o > 1; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
+        if (lane < 2) {
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++)
+#pragma unroll
+                for (int c = 0; c < 6; c++) {
+                    const int r = 3 * half + rr;
+                    double v = -acc[rr * 6 + c];
+                    if (i1 == i2) v += p.Hpp[36 * (size_t)i1 + r * 6 + c] + ((r == c) ? lambda : 0.0);
+                    p.S[(size_t)(6 * i1 + r) * p.n + 6 * i2 + c] = v;
+                    if (i1 != i2) p.S[(size_t)(6 * i2 + c) * p.n + 6 * i1 + r] = v;
+                }
+        }
+    }
+    const int items = p.Kf * p.cam_parts;
+    for (int it = warp; it < items; it += nwarps) {
+        const int kf = it / p.cam_parts, part = it % p.cam_parts;
+        const int beg = p.c_ptr[kf], end = p.c_ptr[kf + 1], len = end - beg;
+        const int per = (len + p.cam_parts - 1) / p.cam_parts;
+        const int s0 = beg + part * per, s1 = min(s0 + per, end);
+        double c6[6] = {0, 0, 0, 0, 0, 0};
+        for (int k = s0 + lane; k < s1; k += 32) {
+            const int e = p.c_edges[k];
+            const int li = p.e_l[e];
+            if (li < 0) continue;
+            const double2* W2 = reinterpret_cast<const double2*>(p.W + 18 * (size_t)e);
+            double w[18];
+#pragma unroll
+            for (int i = 0; i < 9; i++) { const double2 v = W2[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+            const double d0 = p.db[3 * li], d1 = p.db[3 * li + 1], d2 = p.db[3 * li + 2];
+#pragma unroll
+            for (int r = 0; r < 6; r++) c6[r] += w[r * 3] * d0 + w[r * 3 + 1] * d1 + w[r * 3 + 2] * d2;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c6[i] += __shfl_down_sync(0xffffffffu, c6[i], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 6; i++) p.part[(size_t)it * 27 + i] = c6[i];
+        }
+    }
+}
+// ref block_solver.hpp:418-444: x_l = D^-1 (b_l - W^T x_p), one thread per landmark
+__device__ void f_backsub(const BaDev& p, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double c0 = p.bl[3 * li], c1 = p.bl[3 * li + 1], c2 = p.bl[3 * li + 2];
+        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
+#pragma unroll 2
+        for (int e = k0; e < k1; e++) {
+            const int hj = p.cam_h[p.e_cam[e]];
+            if (hj < 0) continue;
+            const double2* W2 = reinterpret_cast<const double2*>(p.W + 18 * (size_t)e);
+            double w[18];
+#pragma unroll
+            for (int i = 0; i < 9; i++) { const double2 v = W2[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+            const double* xp = p.x + 6 * hj;
+#pragma unroll
+            for (int r = 0; r < 6; r++) { const double xr = xp[r]; c0 -= w[r * 3] * xr; c1 -= w[r * 3 + 1] * xr; c2 -= w[r * 3 + 2] * xr; }
+        }
+        const double* D = p.Dinv + 9 * (size_t)li;
+        p.x[p.n + 3 * li] = D[0] * c0 + D[1] * c1 + D[2] * c2;
+        p.x[p.n + 3 * li + 1] = D[3] * c0 + D[4] * c1 + D[5] * c2;
+        p.x[p.n + 3 * li + 2] = D[6] * c0 + D[7] * c1 + D[8] * c2;
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ local-window fast path
+// For windows with <= kFastMaxKf free cameras the 6x3 pose-landmark blocks W and W D^-1 are never written to global memory:
+// a trial walks the landmarks in batches of <= kFastBE edges, rebuilds the batch's blocks from the 32-byte edge records into
+// shared memory, and thread pair i -- owner of one (reduced-system block, part) item for the whole trial -- adds the batch's
+// products to 18 register accumulators per thread. One fixed-order reduction over the parts at the end: bit-reproducible, no
+// atomics, and the per-problem traffic drops from ~13 MB to ~3 MB per LM iteration (what bounds many problems in flight).
+constexpr int kFastBE = 512;                // edges per batch
+constexpr int kFastBL = 256;                // landmarks per batch (bound only; the edge limit closes batches first)
+constexpr int kFastItems = 128;             // (block, part) items; thread t and t + 128 own the left / right 3 columns of item t's 6x6 block
+constexpr int kFastMaxKf = 10;
+constexpr int kFastRec = 18;                // doubles per staged edge: a b | 1/z jdb0 | jdb1 - | w J D^-1 (2x3) | w J (2x3)
+constexpr int kFastRed = 21;                // doubles per thread in the final reduction: 18 products + 3 coefficients
+constexpr size_t kFastRegionBytes = 74 * 1024;
+static_assert(sizeof(double) * kFastBE * kFastRec <= kFastRegionBytes, "batch buffer must fit the region");
+static_assert(sizeof(double) * ((6 * kFastMaxKf) * (6 * kFastMaxKf + 1) + 2 * kFastItems * kFastRed) <= kFastRegionBytes, "S + reduction slots must fit the region");
+
+// computeError at the current state + the edge records; returns this thread's share of the robust chi2 (edge order = g_chi2's)
+__device__ double g_project(const BaDev& p, double* __restrict__ rec, double* __restrict__ err, double delta, int tid, int nt)
+{
+    double acc = 0;
+#pragma unroll 2
+    for (int e = tid; e < p.Ea; e += nt) {
+        const int c = p.e_cam[e];
+        const double* __restrict__ R = p.cam_R + 9 * c;
+        const double* __restrict__ X = p.pt_X + 3 * (size_t)p.e_pt[e];
+        const double X0 = X[0], X1 = X[1], X2 = X[2];
+        const double x = R[0] * X0 + R[1] * X1 + R[2] * X2 + p.cam_t[3 * c];
+        const double y = R[3] * X0 + R[4] * X1 + R[5] * X2 + p.cam_t[3 * c + 1];
+        const double z = R[6] * X0 + R[7] * X1 + R[8] * X2 + p.cam_t[3 * c + 2];
+        const double iz = 1.0 / z, a = x * iz, b = y * iz, f = p.cam_f[c];
+        const double2 uv = *reinterpret_cast<const double2*>(p.e_uv + 2 * (size_t)e);
+        const double e0 = uv.x - (a * f + p.cam_cx[c]), e1 = uv.y - (b * f + p.cam_cy[c]);
+        *reinterpret_cast<double2*>(err + 2 * (size_t)e) = make_double2(e0, e1);
+        double2* r2 = reinterpret_cast<double2*>(rec + kRec * (size_t)e);
+        r2[0] = make_double2(a, b);
+        r2[1] = make_double2(iz, 0.0);
+        double r0, r1;
+        huber(p.e_info[e] * (e0 * e0 + e1 * e1), delta, r0, r1);
+        acc += r0;
+    }
+    return acc;
+}
+__device__ double g_chi2(const BaDev& p, const double* __restrict__ err, double delta, double* sh)
+{
+    double acc = 0;
+    for (int e = threadIdx.x; e < p.Ea; e += blockDim.x) {
+        const double2 er = *reinterpret_cast<const double2*>(err + 2 * (size_t)e);
+        double r0, r1;
+        huber(p.e_info[e] * (er.x * er.x + er.y * er.y), delta, r0, r1);
+        acc += r0;
+    }
+    if (p.nT) acc += tether_chi2_sum(p);
+    return block_sum(acc, sh);
+}
+// landmark blocks; the robust weight w of every edge goes into its record for the later phases
+__device__ void g_build_points(const BaDev& p, double* __restrict__ rec, const double* __restrict__ err, double delta, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double H00 = 0, H01 = 0, H02 = 0, H11 = 0, H12 = 0, H22 = 0, b0 = 0, b1 = 0, b2 = 0;
+        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
+#pragma unroll 2
+        for (int e = k0; e < k1; e++) {
+            const int c = p.e_cam[e];
+            double2* r2 = reinterpret_cast<double2*>(rec + kRec * (size_t)e);
+            const double2 ab = r2[0];
+            const double iz = r2[1].x, f = p.cam_f[c];
+            const double2 er = *reinterpret_cast<const double2*>(err + 2 * (size_t)e);
+            const double info = p.e_info[e];
+            double r0, r1;
+            huber(info * (er.x * er.x + er.y * er.y), delta, r0, r1);
+            const double w = r1 * info, o0 = -(w * er.x), o1 = -(w * er.y);
+            r2[1] = make_double2(iz, w);
+            double J0[3], J1[3];
+            f_point_jac(p.cam_R + 9 * c, ab.x, ab.y, iz, f, J0, J1);
+            const double w0[3] = {w * J0[0], w * J0[1], w * J0[2]}, w1[3] = {w * J1[0], w * J1[1], w * J1[2]};
+            H00 += w0[0] * J0[0] + w1[0] * J1[0]; H01 += w0[0] * J0[1] + w1[0] * J1[1]; H02 += w0[0] * J0[2] + w1[0] * J1[2];
+            H11 += w0[1] * J0[1] + w1[1] * J1[1]; H12 += w0[1] * J0[2] + w1[1] * J1[2]; H22 += w0[2] * J0[2] + w1[2] * J1[2];
+            b0 += J0[0] * o0 + J1[0] * o1; b1 += J0[1] * o0 + J1[1] * o1; b2 += J0[2] * o0 + J1[2] * o1;
+        }
+        double* Hl = p.Hll + 9 * (size_t)li;
+        Hl[0] = H00; Hl[1] = H01; Hl[2] = H02; Hl[3] = H01; Hl[4] = H11; Hl[5] = H12; Hl[6] = H02; Hl[7] = H12; Hl[8] = H22;
+        p.bl[3 * li] = b0; p.bl[3 * li + 1] = b1; p.bl[3 * li + 2] = b2;
+    }
+}
+__device__ void g_build_cams(const BaDev& p, const double* __restrict__ rec, const double* __restrict__ err, int parts, int warp, int nwarps, int lane)
+{
+    const int items = p.Kf * parts;
+    for (int it = warp; it < items; it += nwarps) {
+        const int kf = it / parts, part = it % parts;
+        const int beg = p.c_ptr[kf], end = p.c_ptr[kf + 1], len = end - beg;
+        const int per = (len + parts - 1) / parts;
+        const int s0 = beg + part * per, s1 = min(s0 + per, end);
+        const double f = p.cam_f[p.c_cam[kf]];
+        double A[21], b[6];
+#pragma unroll
+        for (int i = 0; i < 21; i++) A[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) b[i] = 0;
+#pragma unroll 2
+        for (int k = s0 + lane; k < s1; k += 32) {
+            const int e = p.c_edges[k];
+            const double2* r2 = reinterpret_cast<const double2*>(rec + kRec * (size_t)e);
+            const double2 ab = r2[0], zw = r2[1];
+            const double2 er = *reinterpret_cast<const double2*>(err + 2 * (size_t)e);
+            const double w = zw.y, o0 = -(w * er.x), o1 = -(w * er.y);
+            double P0[6], P1[6];
+            f_pose_jac(ab.x, ab.y, zw.x, f, P0, P1);
+            int idx = 0;
+#pragma unroll
+            for (int r = 0; r < 6; r++) {
+                b[r] += P0[r] * o0 + P1[r] * o1;
+                const double a0 = w * P0[r], a1 = w * P1[r];
+#pragma unroll
+                for (int c = r; c < 6; c++) A[idx++] += a0 * P0[c] + a1 * P1[c];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 21; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) A[i] += __shfl_down_sync(0xffffffffu, A[i], o);
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) b[i] += __shfl_down_sync(0xffffffffu, b[i], o);
+        if (lane == 0) {
+            double* dst = p.part + (size_t)it * 27;
+#pragma unroll
+            for (int i = 0; i < 21; i++) dst[i] = A[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++) dst[21 + i] = b[i];
+        }
+    }
+}
+__device__ void g_finish_cams(const BaDev& p, int parts, int tid, int nt)
+{
+    for (int i = tid; i < p.Kf * 27; i += nt) {
+        const int kf = i / 27, j = i % 27;
+        double s = 0;
+        for (int part = 0; part < parts; part++) s += p.part[((size_t)kf * parts + part) * 27 + j];
+        if (j >= 21) p.bp[6 * kf + (j - 21)] = s;
+        else {
+            int r = 0, rem = j;
+            while (rem >= 6 - r) { rem -= 6 - r; r++; }
+            const int c = r + rem;
+            p.Hpp[36 * (size_t)kf + r * 6 + c] = s;
+            p.Hpp[36 * (size_t)kf + c * 6 + r] = s;
+        }
+    }
+}
+// push + update in one pass (ref base_vertex.h:92-94, sparse_optimizer.cpp:433-446): the old state goes to the backup buffers
+__device__ void g_backup_update(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < p.Kf; i += nt) {
+        const int c = p.c_cam[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) p.cam_bak[7 * i + j] = p.cam_q[4 * c + j];
+#pragma unroll
+        for (int j = 0; j < 3; j++) p.cam_bak[7 * i + 4 + j] = p.cam_t[3 * c + j];
+        pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i);
+    }
+    for (int i = tid; i < p.Pl * 3; i += nt) {
+        double* X = p.pt_X + 3 * (size_t)p.l_pt[i / 3] + i % 3;
+        const double old = *X;
+        p.pt_bak[i] = old;
+        *X = old + p.x[p.n + i];
+    }
+}
+// W = w Jj^T Ji of one edge from its record (6x3 row-major)
+__device__ __forceinline__ void g_edge_W(const BaDev& p, const double* __restrict__ rec, int e, int c, double* W)
+{
+    const double2* r2 = reinterpret_cast<const double2*>(rec + kRec * (size_t)e);
+    const double2 ab = r2[0], zw = r2[1];
+    const double f = p.cam_f[c];
+    double J0[3], J1[3], P0[6], P1[6];
+    f_point_jac(p.cam_R + 9 * c, ab.x, ab.y, zw.x, f, J0, J1);
+    f_pose_jac(ab.x, ab.y, zw.x, f, P0, P1);
+    const double w0[3] = {zw.y * J0[0], zw.y * J0[1], zw.y * J0[2]}, w1[3] = {zw.y * J1[0], zw.y * J1[1], zw.y * J1[2]};
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int cc = 0; cc < 3; cc++) W[r * 3 + cc] = P0[r] * w0[cc] + P1[r] * w1[cc];
+}
+// Schur complement of one trial (ref block_solver.hpp:337-390) + assembly of the reduced system and its right-hand side
+// into shared memory. region = the CTA's kFastRegionBytes scratch (batch buffer, then S | bs | reduction slots).
+// W = w Pj^T J is rank 2 (P = 2x6 pose Jacobian, J = 2x3 point Jacobian), so  (W_i D^-1) W_j^T = P_i^T [ (w_i J_i D^-1)(w_j J_j)^T ] P_j:
+// an edge is staged as (a, b, 1/z) -- P is rebuilt from those -- plus the two 2x3 factors, 144 bytes instead of two 6x3 blocks.
+__device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double lambda, double* region)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int item = tid & (kFastItems - 1), half = tid >> 7;          // warp-uniform half: columns 3*half .. 3*half+2 (and rows, for the coefficients)
+    int blk = -1, part = 0, nparts = 1;
+    bool diag = false;
+    double f1 = 0, f2 = 0;
+    if (item < p.nitems) {
+        const int4 d = p.item_def[item];
+        blk = d.x; part = d.y; nparts = d.z;
+        const int i1 = p.blk_ij[2 * blk], i2 = p.blk_ij[2 * blk + 1];
+        diag = i1 == i2;
+        f1 = p.cam_f[p.c_cam[i1]]; f2 = p.cam_f[p.c_cam[i2]];
+    }
+    double acc[18], cacc[3] = {0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 18; i++) acc[i] = 0;
+    for (int b = 0; b < p.nb; b++) {
+        const int lm0 = p.batch_ptr[b], lm1 = p.batch_ptr[b + 1];
+        const int e0 = p.l_ptr[lm0], ne = p.l_ptr[lm1] - e0;
+        int q0 = 0, qn = 0;
+        if (blk >= 0) { q0 = p.bb_ptr[b * p.nblk + blk]; qn = p.bb_ptr[b * p.nblk + blk + 1] - q0; }
+        __syncthreads();                                     // the previous batch has been consumed
+        for (int t = tid; t < ne; t += nt) {
+            const int e = e0 + t, c = p.e_cam[e], li = p.e_l[e];
+            const double* __restrict__ Hl = p.Hll + 9 * (size_t)li;
+            const double A0 = Hl[0] + lambda, A1 = Hl[1], A2 = Hl[2], A4 = Hl[4] + lambda, A5 = Hl[5], A8 = Hl[8] + lambda;      // symmetric
+            const double c00 = A4 * A8 - A5 * A5, c01 = A5 * A2 - A1 * A8, c02 = A1 * A5 - A4 * A2;
+            const double id = 1.0 / (A0 * c00 + A1 * c01 + A2 * c02);
+            const double D0 = c00 * id, D1 = c01 * id, D2 = c02 * id, D4 = (A0 * A8 - A2 * A2) * id, D5 = (A2 * A1 - A0 * A5) * id, D8 = (A0 * A4 - A1 * A1) * id;
+            const double b0 = p.bl[3 * li], b1 = p.bl[3 * li + 1], b2 = p.bl[3 * li + 2];
+            const double db0 = D0 * b0 + D1 * b1 + D2 * b2, db1 = D1 * b0 + D4 * b1 + D5 * b2, db2 = D2 * b0 + D5 * b1 + D8 * b2;
+            if (e == p.l_ptr[li]) {
+                double* Dg = p.Dinv + 9 * (size_t)li;
+                Dg[0] = D0; Dg[1] = D1; Dg[2] = D2; Dg[3] = D1; Dg[4] = D4; Dg[5] = D5; Dg[6] = D2; Dg[7] = D5; Dg[8] = D8;
+                p.db[3 * li] = db0; p.db[3 * li + 1] = db1; p.db[3 * li + 2] = db2;
+            }
+            if (p.cam_h[c] >= 0) {
+                const double2* r2 = reinterpret_cast<const double2*>(rec + kRec * (size_t)e);
+                const double2 ab = r2[0], zw = r2[1];
+                double J0[3], J1[3];
+                f_point_jac(p.cam_R + 9 * c, ab.x, ab.y, zw.x, p.cam_f[c], J0, J1);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { J0[k] *= zw.y; J1[k] *= zw.y; }                      // w J
+                double2* o = reinterpret_cast<double2*>(region + kFastRec * t);
+                o[0] = ab;
+                o[1] = make_double2(zw.x, J0[0] * db0 + J0[1] * db1 + J0[2] * db2);
+                o[2] = make_double2(J1[0] * db0 + J1[1] * db1 + J1[2] * db2, 0.0);
+                const double g00 = J0[0] * D0 + J0[1] * D1 + J0[2] * D2, g01 = J0[0] * D1 + J0[1] * D4 + J0[2] * D5, g02 = J0[0] * D2 + J0[1] * D5 + J0[2] * D8;
+                const double g10 = J1[0] * D0 + J1[1] * D1 + J1[2] * D2, g11 = J1[0] * D1 + J1[1] * D4 + J1[2] * D5, g12 = J1[0] * D2 + J1[1] * D5 + J1[2] * D8;
+                o[3] = make_double2(g00, g01); o[4] = make_double2(g02, g10); o[5] = make_double2(g11, g12);
+                o[6] = make_double2(J0[0], J0[1]); o[7] = make_double2(J0[2], J1[0]); o[8] = make_double2(J1[1], J1[2]);
+            }
+        }
+        __syncthreads();
+        if (blk >= 0) {
+            const int k1 = q0 + ((part + 1) * qn) / nparts;
+            for (int k = q0 + (part * qn) / nparts; k < k1; k++) {
+                const ushort2 pr = p.bpairs[k];
+                const double2* __restrict__ A2 = reinterpret_cast<const double2*>(region + kFastRec * pr.x);
+                const double2* __restrict__ B2 = reinterpret_cast<const double2*>(region + kFastRec * pr.y);
+                const double2 ia = A2[0], iz = A2[1], g0 = A2[3], g1 = A2[4], g2 = A2[5];
+                const double2 ja = B2[0], jz = B2[1], h0 = B2[6], h1 = B2[7], h2 = B2[8];
+                // M = (w_i J_i D^-1)(w_j J_j)^T
+                const double M00 = g0.x * h0.x + g0.y * h0.y + g1.x * h1.x, M01 = g0.x * h1.y + g0.y * h2.x + g1.x * h2.y;
+                const double M10 = g1.y * h0.x + g2.x * h0.y + g2.y * h1.x, M11 = g1.y * h1.y + g2.x * h2.x + g2.y * h2.y;
+                // T = M P_j[:, 3*half ..]
+                double T0[3], T1[3];
+                if (half == 0) {
+                    const double q00 = ja.x * ja.y * f2, q01 = -(f2 + ja.x * ja.x * f2), q02 = ja.y * f2;
+                    const double q10 = f2 + ja.y * ja.y * f2, q12 = -(ja.x * f2);
+                    T0[0] = M00 * q00 + M01 * q10; T0[1] = M00 * q01 - M01 * q00; T0[2] = M00 * q02 + M01 * q12;
+                    T1[0] = M10 * q00 + M11 * q10; T1[1] = M10 * q01 - M11 * q00; T1[2] = M10 * q02 + M11 * q12;
+                } else {
+                    const double zf = jz.x * f2;
+                    T0[0] = -(zf * M00); T0[1] = -(zf * M01); T0[2] = zf * (ja.x * M00 + ja.y * M01);
+                    T1[0] = -(zf * M10); T1[1] = -(zf * M11); T1[2] = zf * (ja.x * M10 + ja.y * M11);
+                }
+                double P0[6], P1[6];
+                f_pose_jac(ia.x, ia.y, iz.x, f1, P0, P1);
+#pragma unroll
+                for (int r = 0; r < 6; r++)
+#pragma unroll
+                    for (int c = 0; c < 3; c++) acc[r * 3 + c] += P0[r] * T0[c] + P1[r] * T1[c];
+                if (diag) {
+                    const double j1 = A2[2].x;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) cacc[r] += (half ? P0[3 + r] : P0[r]) * iz.y + (half ? P1[3 + r] : P1[r]) * j1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n = p.n;
+    double* S = region;
+    double* bs = S + (size_t)n * n;
+    double* red = bs + n;
+    {
+        double* dst = red + (size_t)(item * 2 + half) * kFastRed;
+#pragma unroll
+        for (int i = 0; i < 18; i++) dst[i] = acc[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) dst[18 + i] = cacc[i];
+    }
+    for (int i = tid; i < n * n; i += nt) S[i] = 0.0;
+    __syncthreads();
+    for (int o = tid; o < p.nblk * 36; o += nt) {
+        const int bi = o / 36, r = (o % 36) / 6, c = o % 6;
+        const int2 it = p.blk_items[bi];
+        double s = 0;
+        for (int q = 0; q < it.y; q++) s += red[((it.x + q) * 2 + c / 3) * kFastRed + r * 3 + (c % 3)];
+        const int i1 = p.blk_ij[2 * bi], i2 = p.blk_ij[2 * bi + 1];
+        double v = -s;
+        if (i1 == i2) v += p.Hpp[36 * (size_t)i1 + r * 6 + c] + ((r == c) ? lambda : 0.0);
+        S[(size_t)(6 * i1 + r) * n + 6 * i2 + c] = v;
+        if (i1 != i2) S[(size_t)(6 * i2 + c) * n + 6 * i1 + r] = v;
+    }
+    for (int i = tid; i < n; i += nt) {
+        const int kf = i / 6, r = i % 6;
+        const int2 it = p.blk_items[p.cam_diag[kf]];
+        double s = 0;
+        for (int q = 0; q < it.y; q++) s += red[((it.x + q) * 2 + r / 3) * kFastRed + 18 + (r % 3)];
+        bs[i] = p.bp[i] - s;
+    }
+}
+__device__ void g_backsub(const BaDev& p, const double* __restrict__ rec, int tid, int nt)
+{
+    for (int li = tid; li < p.Pl; li += nt) {
+        double c0 = p.bl[3 * li], c1 = p.bl[3 * li + 1], c2 = p.bl[3 * li + 2];
+        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
+#pragma unroll 2
+        for (int e = k0; e < k1; e++) {
+            const int c = p.e_cam[e], hj = p.cam_h[c];
+            if (hj < 0) continue;
+            double W[18];
+            g_edge_W(p, rec, e, c, W);
+            const double* xp = p.x + 6 * hj;
+#pragma unroll
+            for (int r = 0; r < 6; r++) { const double xr = xp[r]; c0 -= W[r * 3] * xr; c1 -= W[r * 3 + 1] * xr; c2 -= W[r * 3 + 2] * xr; }
+        }
+        const double* D = p.Dinv + 9 * (size_t)li;
+        p.x[p.n + 3 * li] = D[0] * c0 + D[1] * c1 + D[2] * c2;
+        p.x[p.n + 3 * li + 1] = D[3] * c0 + D[4] * c1 + D[5] * c2;
+        p.x[p.n + 3 * li + 2] = D[6] * c0 + D[7] * c1 + D[8] * c2;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the persistent LM kernel
 // One CTA per problem runs StepBundleAdjustment's whole loop: for each Huber width one g2o LM iteration
 // (ref optimization_algorithm_levenberg.cpp:57-149, up to 10 lambda trials), then the outlier classification.
@@ -865,6 +1488,7 @@ constexpr size_t kBigScratchBytes = sizeof(double) * (2 * kLdltTile * (kLdltNB +
 
 __host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) * ((size_t)n * n + n); }
 __host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
+__host__ __device__ inline size_t ba_smem_need_cams_R(int K) { return sizeof(double) * 19 * (size_t)K + sizeof(int) * (size_t)K; }     // + rotation matrices
 
 __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq,
                                                             unsigned dynBytes)
@@ -880,16 +1504,21 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
         s_p = probs[blockIdx.x];
         g_cam_q = nullptr; g_cam_t = nullptr;
         size_t off = 0;
-        if (s_p.n > 0 && ba_smem_need_S(s_p.n) <= dynBytes) {
+        if (s_p.fast && kFastRegionBytes + ba_smem_need_cams_R(s_p.K) > dynBytes) s_p.fast = 0;      // cannot happen (host sizes the launch)
+        if (s_p.fast) {
+            s_p.S = reinterpret_cast<double*>(dyn); s_p.bs = s_p.S + (size_t)s_p.n * s_p.n;
+            off = kFastRegionBytes;
+        } else if (s_p.n > 0 && ba_smem_need_S(s_p.n) <= dynBytes) {
             s_p.S = reinterpret_cast<double*>(dyn); s_p.bs = s_p.S + (size_t)s_p.n * s_p.n;
             off = ba_smem_need_S(s_p.n);
         }
-        if (s_p.K <= kBaMaxSmemCams && off + ba_smem_need_cams(s_p.K) <= dynBytes) {
+        if (s_p.K <= kBaMaxSmemCams && off + ba_smem_need_cams_R(s_p.K) <= dynBytes) {
             double* c = reinterpret_cast<double*>(dyn + off);
             g_cam_q = s_p.cam_q; g_cam_t = s_p.cam_t;
             const double *gf = s_p.cam_f, *gx = s_p.cam_cx, *gy = s_p.cam_cy; const int* gh = s_p.cam_h;
             double* sq = c; double* st = c + 4 * s_p.K; double* sf = c + 7 * s_p.K; double* sx = c + 8 * s_p.K; double* sy = c + 9 * s_p.K;
-            int* shh = reinterpret_cast<int*>(c + 10 * s_p.K);
+            s_p.cam_R = c + 10 * s_p.K;
+            int* shh = reinterpret_cast<int*>(c + 19 * s_p.K);
             for (int k = 0; k < s_p.K; k++) {
                 for (int j = 0; j < 4; j++) sq[4 * k + j] = g_cam_q[4 * k + j];
                 for (int j = 0; j < 3; j++) st[3 * k + j] = g_cam_t[3 * k + j];
@@ -907,16 +1536,127 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
     long long trials = 0, iters = 0;
 
     long long t_last = gtimer();
+    f_cam_R(p, tid, nt);
+    __syncthreads();
+    if (p.fast) {
+        // local-window fast path: edge records + errors are double-buffered (current state | trial state) so that a rejected
+        // trial costs no re-projection and the outlier pass still sees the last COMPUTED errors, like g2o
+        double* recCur = p.Hc; double* recTry = p.Hc + kRec * (size_t)p.Ea;
+        double* errCur = p.err; double* errTry = p.Hc + 2 * kRec * (size_t)p.Ea;
+        const double* errLast = errCur;
+        double* region = reinterpret_cast<double*>(dyn);
+        bool haveState = false;
+        double chiDelta = -1.0, currentChi = 0;         // currentChi is valid for the Huber width chiDelta at the current state
+        const int camParts = max(1, nw / max(p.Kf, 1));
+        for (int it = 0; it < nIters; it++) {
+            if (s_stop) break;
+            const double delta = (double)huberW[it];
+            if (!haveState) {
+                double part = g_project(p, recCur, errCur, delta, tid, nt);
+                if (p.nT) { phase_tether_errors(p, tid, nt); __syncthreads(); part += tether_chi2_sum(p); }
+                currentChi = block_sum(part, sh);
+                chiDelta = delta;
+                haveState = true; errLast = errCur;
+            } else if (delta != chiDelta) {
+                currentChi = g_chi2(p, errCur, delta, sh);
+                chiDelta = delta;
+            }
+            PH(0);
+            g_build_points(p, recCur, errCur, delta, tid, nt);
+            if (p.nT) phase_tether_linearize(p, tid, nt);
+            __syncthreads();
+            g_build_cams(p, recCur, errCur, camParts, warp, nw, lane);
+            __syncthreads();
+            g_finish_cams(p, camParts, tid, nt);
+            __syncthreads();
+            if (p.nT) { phase_tether_accumulate(p, tid, nt); __syncthreads(); }
+            PH(1);
+            if (iteration == 0) {
+                const double md = phase_max_diag(p, sh);
+                if (tid == 0) { s_lambda = ctl->user_lambda_init > 0 ? ctl->user_lambda_init : 1e-5 * md; s_ni = 2; }
+                __syncthreads();
+            }
+            double rho = 0;
+            int qmax = 0;
+            bool lambdaFinite = true;
+            do {
+                const double lambda = s_lambda;
+                g_schur(p, recCur, lambda, region);
+                __syncthreads();
+                if (p.nT) { phase_tether_offdiag(p, warp, lane); __syncthreads(); }
+                PH(3);
+                const bool ok2 = phase_ldlt_solve(p, sh);
+                __syncthreads();
+                PH(4);
+                if (ok2) g_backsub(p, recCur, tid, nt);
+                __syncthreads();
+                g_backup_update(p, tid, nt);
+                __syncthreads();
+                f_cam_R(p, tid, nt);
+                __syncthreads();
+                PH(6);
+                double part = g_project(p, recTry, errTry, delta, tid, nt);
+                if (p.nT) { phase_tether_errors(p, tid, nt); __syncthreads(); part += tether_chi2_sum(p); }
+                errLast = errTry;
+                double tempChi = block_sum(part, sh);
+                if (!ok2) tempChi = DBL_MAX;
+                const double scale = phase_scale(p, lambda, sh) + 1e-3;
+                PH(7);
+                if (tid == 0) {
+                    double r = (currentChi - tempChi) / scale;
+                    s_rho = r;
+                    if (r > 0 && isfinite(tempChi)) {
+                        double alpha = 1. - pow((2 * r - 1), 3.0);
+                        alpha = fmin(alpha, 2. / 3.);
+                        s_lambda = lambda * fmax(1. / 3., alpha);
+                        s_ni = 2;
+                        s_accept = 1;
+                    } else {
+                        s_lambda = lambda * s_ni;
+                        s_ni = s_ni * 2;
+                        s_accept = 0;
+                    }
+                }
+                __syncthreads();
+                rho = s_rho;
+                if (s_accept) {
+                    currentChi = tempChi;
+                    double* t1 = recCur; recCur = recTry; recTry = t1;
+                    double* t2 = errCur; errCur = errTry; errTry = t2;
+                } else {
+                    phase_restore(p, tid, nt);
+                    __syncthreads();
+                    f_cam_R(p, tid, nt);
+                    if (p.nT) haveState = false;          // the tether errors are single-buffered: recompute at the restored state
+                    __syncthreads();
+                    if (!isfinite(s_lambda)) { lambdaFinite = false; trials++; break; }
+                }
+                qmax++;
+                trials++;
+            } while (rho < 0 && qmax < 10);
+            iteration++;
+            iters++;
+            if (qmax == 10 || rho == 0 || !lambdaFinite) { if (tid == 0) s_stop = 1; }     // Terminate => Step() == false => break
+            __syncthreads();
+        }
+        if (errLast != p.err) {
+            for (int i = tid; i < 2 * p.Ea; i += nt) p.err[i] = errLast[i];
+            __syncthreads();
+        }
+    } else {
+    bool errValid = false;              // p.err / the edge records describe the current state (true after an accepted trial)
     for (int it = 0; it < nIters; it++) {
         if (s_stop) break;
         const double delta = (double)huberW[it];
-        phase_errors(p, tid, nt);
-        if (p.nT) phase_tether_errors(p, tid, nt);
-        __syncthreads();
+        if (!errValid) {
+            f_project(p, tid, nt);
+            if (p.nT) phase_tether_errors(p, tid, nt);
+            __syncthreads();
+        }
         double currentChi = phase_chi2(p, delta, sh);
         PH(0);
-        phase_build_points_lm(p, delta, tid, nt);
-        phase_build_cams(p, delta, warp, nw, lane);
+        f_build_points(p, delta, tid, nt);
+        f_build_cams(p, delta, warp, nw, lane);
         if (p.nT) phase_tether_linearize(p, tid, nt);
         __syncthreads();
         phase_finish_cams(p, tid, nt);
@@ -934,10 +1674,10 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
         do {
             const double lambda = s_lambda;
             phase_backup(p, tid, nt);
-            phase_schur_points(p, lambda, tid, nt);
+            f_schur_points(p, lambda, tid, nt);
             __syncthreads();
             PH(2);
-            phase_schur_blocks(p, lambda, warp, nw, lane);
+            f_schur_blocks(p, lambda, warp, nw, lane);
             __syncthreads();
             phase_finish_bs(p, tid, nt);
             if (p.nT) phase_tether_offdiag(p, warp, lane);
@@ -946,12 +1686,14 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
             const bool ok2 = phase_ldlt_solve(p, sh);
             __syncthreads();
             PH(4);
-            if (ok2) phase_backsub(p, tid, nt);
+            if (ok2) f_backsub(p, tid, nt);
             __syncthreads();
             phase_update(p, tid, nt);
             __syncthreads();
+            f_cam_R(p, tid, nt);
+            __syncthreads();
             PH(6);
-            phase_errors(p, tid, nt);
+            f_project(p, tid, nt);
             if (p.nT) phase_tether_errors(p, tid, nt);
             __syncthreads();
             double tempChi = phase_chi2(p, delta, sh);
@@ -975,9 +1717,14 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
             }
             __syncthreads();
             rho = s_rho;
-            if (s_accept) currentChi = tempChi;
+            if (s_accept) { currentChi = tempChi; errValid = true; }
             else {
+                // the records keep describing the REJECTED state (the outlier pass reads the last computed errors, like g2o);
+                // the Jacobians of further trials come from W, which was built before the trial
+                errValid = false;
                 phase_restore(p, tid, nt);
+                __syncthreads();
+                f_cam_R(p, tid, nt);
                 __syncthreads();
                 if (!isfinite(s_lambda)) { lambdaFinite = false; trials++; break; }
             }
@@ -988,6 +1735,7 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
         iters++;
         if (qmax == 10 || rho == 0 || !lambdaFinite) { if (tid == 0) s_stop = 1; }     // Terminate => Step() == false => break
         __syncthreads();
+    }
     }
     double errSum; int inl, nfl;
     phase_classify(p, (double)maxErrSq, sh, errSum, inl, nfl);
@@ -1583,12 +2331,13 @@ struct mage_ba_s {
 };
 
 // dynamic shared memory for one problem: reduced system + camera state when they fit in 200 KB, else whatever subset fits
-static size_t ba_dyn_smem(int n, int K)
+static size_t ba_dyn_smem(int n, int K, int fast)
 {
     const size_t limit = 200 * 1024;
     size_t need = 0;
-    if (n > 0 && ba_smem_need_S(n) <= limit) need = ba_smem_need_S(n);
-    if (K <= kBaMaxSmemCams && need + ba_smem_need_cams(K) <= limit) need += ba_smem_need_cams(K);
+    if (fast) need = kFastRegionBytes;
+    else if (n > 0 && ba_smem_need_S(n) <= limit) need = ba_smem_need_S(n);
+    if (K <= kBaMaxSmemCams && need + ba_smem_need_cams_R(K) <= limit) need += ba_smem_need_cams_R(K);
     return need;
 }
 
@@ -1703,6 +2452,52 @@ static int ba_build_structure(mage_ba_t h)
         blk_ptr.push_back((int)pairs.size());
     }
     const int nblk = (int)blk_ij.size() / 2;
+    // local-window fast path (see g_schur): batches of landmarks, (block, part) items, pair lists per (batch, block)
+    int fast = 0, nb = 0, nitems = 0;
+    std::vector<int> batch_ptr, cam_diag(std::max(Kf, 1), 0), bb_ptr;
+    std::vector<int4> item_def;
+    std::vector<int2> blk_items(std::max(nblk, 1));
+    std::vector<ushort2> bpairs;
+    if (!h->points_fixed && Kf >= 1 && Kf <= kFastMaxKf && Pl >= 1 && nblk <= kFastItems && !getenv("MAGE_BA_NO_FAST")) {
+        fast = 1;
+        batch_ptr.push_back(0);
+        for (int li = 0, e_in = 0, l_in = 0; li < Pl; li++) {
+            const int ne = l_ptr[li + 1] - l_ptr[li];
+            if (ne > kFastBE) { fast = 0; break; }
+            if (e_in + ne > kFastBE || l_in == kFastBL) { batch_ptr.push_back(li); e_in = 0; l_in = 0; }
+            e_in += ne; l_in++;
+        }
+        batch_ptr.push_back(Pl);
+    }
+    if (fast) {
+        nb = (int)batch_ptr.size() - 1;
+        // parts per block: start with one each, then hand the spare thread pairs to the block with the longest share
+        std::vector<int> parts(nblk, 1), cnt(nblk);
+        for (int b = 0; b < nblk; b++) cnt[b] = blk_ptr[b + 1] - blk_ptr[b];
+        for (int spare = kFastItems - nblk; spare > 0; spare--) {
+            int best = 0;
+            for (int b = 1; b < nblk; b++) if ((long)cnt[b] * parts[best] > (long)cnt[best] * parts[b]) best = b;
+            parts[best]++;
+        }
+        for (int b = 0; b < nblk; b++) {
+            blk_items[b] = make_int2((int)item_def.size(), parts[b]);
+            for (int q = 0; q < parts[b]; q++) item_def.push_back(make_int4(b, q, parts[b], 0));
+            if (blk_ij[2 * b] == blk_ij[2 * b + 1]) cam_diag[blk_ij[2 * b]] = b;
+        }
+        nitems = (int)item_def.size();
+        // pairs regrouped by (batch, block); inside a group the landmark order of the block's pair list is kept
+        std::vector<int> lm_batch(Pl);
+        for (int b = 0; b < nb; b++) for (int li = batch_ptr[b]; li < batch_ptr[b + 1]; li++) lm_batch[li] = b;
+        std::vector<std::vector<ushort2>> groups((size_t)nb * nblk);
+        for (int b = 0; b < nblk; b++)
+            for (int k = blk_ptr[b]; k < blk_ptr[b + 1]; k++) {
+                const int2 pr = pairs[k];
+                const int bt = lm_batch[e_l[pr.x]], e0 = l_ptr[batch_ptr[bt]];
+                groups[(size_t)bt * nblk + b].push_back(make_ushort2((unsigned short)(pr.x - e0), (unsigned short)(pr.y - e0)));
+            }
+        bb_ptr.push_back(0);
+        for (auto& gq : groups) { bpairs.insert(bpairs.end(), gq.begin(), gq.end()); bb_ptr.push_back((int)bpairs.size()); }
+    }
     const int cam_parts = std::max(1, std::min(16, 256 / std::max(Kf, 1)));     // (camera, part) reduction items
     const int schur_parts = kSchurParts;
 
@@ -1714,11 +2509,13 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_lpt = rI(Pl), o_lptr = rI(Pl + 1), o_ledges = rI(l_edges.size());
     size_t o_ccam = rI(Kf), o_cptr = rI(Kf + 1), o_cedges = rI(c_edges.size());
     size_t o_bij = rI(blk_ij.size()), o_bptr = rI(blk_ptr.size()), o_pairs = W.reserve(sizeof(int2) * std::max<size_t>(pairs.size(), 1));
-    size_t o_err = rD(2 * (size_t)Ea), o_W = rD(18 * (size_t)Ea), o_WD = rD(18 * (size_t)Ea), o_Hll = rD(9 * (size_t)Pl), o_bl = rD(3 * (size_t)Pl);
+    size_t o_err = rD(2 * (size_t)Ea), o_W = rD(18 * (size_t)Ea), o_WD = rD(20 * (size_t)Ea), o_Hll = rD(9 * (size_t)Pl), o_bl = rD(3 * (size_t)Pl);
     size_t o_Dinv = rD(9 * (size_t)Pl), o_db = rD(3 * (size_t)Pl), o_Hpp = rD(36 * (size_t)Kf), o_bp = rD(n), o_S = rD((size_t)n * n), o_bs = rD(n);
     size_t o_x = rD(n + 3 * (size_t)Pl), o_cbak = rD(7 * (size_t)Kf), o_pbak = rD(3 * (size_t)Pl), o_part = rD((size_t)Kf * cam_parts * 27);
     size_t o_flags = W.reserve(std::max(Ea, 1));
-    size_t o_Hc = rD(12 * (size_t)Ea);
+    size_t o_Hc = rD(12 * (size_t)Ea), o_camR = rD(9 * (size_t)h->K);
+    size_t o_bptr2 = rI(batch_ptr.size()), o_idef = W.reserve(sizeof(int4) * std::max<size_t>(item_def.size(), 1)), o_bitems = W.reserve(sizeof(int2) * blk_items.size());
+    size_t o_cdiag = rI(cam_diag.size()), o_bbptr = rI(bb_ptr.size()), o_bpairs = W.reserve(sizeof(ushort2) * std::max<size_t>(bpairs.size(), 1));
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
     size_t o_Wk = rD(big ? (size_t)n * kLdltNB : 1);
@@ -1739,6 +2536,11 @@ static int ba_build_structure(mage_ba_t h)
     MAGE_CUDA_TRY(up(o_bij, blk_ij.data(), sizeof(int) * blk_ij.size())); MAGE_CUDA_TRY(up(o_bptr, blk_ptr.data(), sizeof(int) * blk_ptr.size()));
     MAGE_CUDA_TRY(up(o_pairs, pairs.data(), sizeof(int2) * pairs.size()));
     MAGE_CUDA_TRY(up(o_tdef, t_def.data(), sizeof(int4) * nT)); MAGE_CUDA_TRY(up(o_tmeas, t_meas.data(), sizeof(double) * 8 * nT));
+    if (fast) {
+        MAGE_CUDA_TRY(up(o_bptr2, batch_ptr.data(), sizeof(int) * batch_ptr.size())); MAGE_CUDA_TRY(up(o_idef, item_def.data(), sizeof(int4) * item_def.size()));
+        MAGE_CUDA_TRY(up(o_bitems, blk_items.data(), sizeof(int2) * blk_items.size())); MAGE_CUDA_TRY(up(o_cdiag, cam_diag.data(), sizeof(int) * cam_diag.size()));
+        MAGE_CUDA_TRY(up(o_bbptr, bb_ptr.data(), sizeof(int) * bb_ptr.size())); MAGE_CUDA_TRY(up(o_bpairs, bpairs.data(), sizeof(ushort2) * bpairs.size()));
+    }
     BaDev& d = h->dev;
     d.K = h->K; d.P = h->P; d.Ea = Ea; d.Kf = Kf; d.Pl = Pl; d.n = n; d.nblk = nblk; d.cam_parts = cam_parts;
     d.cam_h = W.at<int>(o_camh); d.e_cam = W.at<int>(o_ecam); d.e_pt = W.at<int>(o_ept); d.e_l = W.at<int>(o_el);
@@ -1750,7 +2552,10 @@ static int ba_build_structure(mage_ba_t h)
     d.Dinv = W.at<double>(o_Dinv); d.db = W.at<double>(o_db); d.Hpp = W.at<double>(o_Hpp); d.bp = W.at<double>(o_bp); d.S = W.at<double>(o_S);
     d.bs = W.at<double>(o_bs); d.x = W.at<double>(o_x); d.cam_bak = W.at<double>(o_cbak); d.pt_bak = W.at<double>(o_pbak); d.part = W.at<double>(o_part);
     d.flags = W.at<unsigned char>(o_flags);
-    d.Hc = W.at<double>(o_Hc);
+    d.Hc = W.at<double>(o_Hc); d.cam_R = W.at<double>(o_camR);
+    d.fast = fast; d.nb = nb; d.nitems = nitems;
+    d.batch_ptr = W.at<int>(o_bptr2); d.item_def = W.at<int4>(o_idef); d.blk_items = W.at<int2>(o_bitems);
+    d.cam_diag = W.at<int>(o_cdiag); d.bb_ptr = W.at<int>(o_bbptr); d.bpairs = W.at<ushort2>(o_bpairs);
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
     d.big = big; d.Wk = W.at<double>(o_Wk);
@@ -2045,7 +2850,7 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
             void* args[] = {(void*)&d_dev, (void*)&d_hub, (void*)&n_iters, (void*)&max_err_sq, (void*)&dynb};
             MAGE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ba_step_coop, dim3(coop_grid), dim3(kCoopThreads), args, coop_smem, h->stream));
         } else {
-            k_ba_step<<<1, kBaThreads, ba_dyn_smem(h->dev.n, h->dev.K), h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, (unsigned)ba_dyn_smem(h->dev.n, h->dev.K));
+            k_ba_step<<<1, kBaThreads, ba_dyn_smem(h->dev.n, h->dev.K, h->dev.fast), h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, (unsigned)ba_dyn_smem(h->dev.n, h->dev.K, h->dev.fast));
         }
         MAGE_CUDA_TRY(cudaGetLastError());
         h->stats[2]++;
@@ -2077,7 +2882,7 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
         if (n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(lead->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, lead->stream));
     }
     size_t dyn = 0;
-    for (auto& d : table) dyn = std::max(dyn, ba_dyn_smem(d.n, d.K));
+    for (auto& d : table) dyn = std::max(dyn, ba_dyn_smem(d.n, d.K, d.fast));
     if (!table.empty()) {
         if ((int)table.size() > lead->table_cap) {
             if (lead->d_table) cudaFree(lead->d_table);
