@@ -531,8 +531,8 @@ __device__ bool phase_ldlt_solve(const BaDev& p, double* sh)
         if (d < 0) { if (tid == 0) s_neg = 1; }
         const bool valid = fabs(d) > 0;
         const double inv_d = valid ? 1.0 / d : 0.0;
-        // trailing update with the unscaled column: S_ij -= a_ik * a_jk / d  (lower triangle, k < j <= i)
-        __syncthreads();
+        // trailing update with the unscaled column: S_ij -= a_ik * a_jk / d  (lower triangle, k < j <= i). No barrier is needed
+        // here: the scaling of column k-1 that other threads may still be doing touches neither column k nor the trailing block.
         if (valid) {
             for (int i = k + 1 + ty; i < n; i += nty) {
                 const double aik = S[(size_t)i * n + k] * inv_d;
@@ -544,15 +544,40 @@ __device__ bool phase_ldlt_solve(const BaDev& p, double* sh)
     }
     __syncthreads();
     if (s_neg) return false;
-    // solve L y = b (forward), D, L^T x = y (backward); y lives in sh-independent global bs (overwritten)
+    // solve L y = b (forward), D, L^T x = y (backward)
     double* y = p.bs;
+    const double tol = 1.0 / DBL_MAX;
+    if (n <= 64) {
+        // one warp, the right-hand side in registers (lane i owns rows i and i + 32), pivots broadcast by shuffle: no CTA barriers.
+        // Every y_i still receives its updates in the order k = 0, 1, ... of the loops below.
+        if (tid < 32) {
+            const int i0 = tid, i1 = tid + 32;
+            double y0 = i0 < n ? y[i0] : 0.0, y1 = i1 < n ? y[i1] : 0.0;
+            for (int k = 0; k < n; k++) {
+                const double yk = __shfl_sync(0xffffffffu, k < 32 ? y0 : y1, k & 31);
+                if (i0 > k && i0 < n) y0 -= S[(size_t)i0 * n + k] * yk;
+                if (i1 > k && i1 < n) y1 -= S[(size_t)i1 * n + k] * yk;
+            }
+            if (i0 < n) { const double d = S[(size_t)i0 * n + i0]; y0 = (fabs(d) > tol) ? y0 / d : 0.0; }
+            if (i1 < n) { const double d = S[(size_t)i1 * n + i1]; y1 = (fabs(d) > tol) ? y1 / d : 0.0; }
+            for (int k = n - 1; k >= 0; k--) {
+                const double xk = __shfl_sync(0xffffffffu, k < 32 ? y0 : y1, k & 31);
+                if (i0 < k) y0 -= S[(size_t)k * n + i0] * xk;
+                if (i1 < k) y1 -= S[(size_t)k * n + i1] * xk;
+            }
+            if (i0 < n) p.x[i0] = y0;
+            if (i1 < n) p.x[i1] = y1;
+        }
+        __syncthreads();
+        (void)sh;
+        return true;
+    }
     for (int k = 0; k < n; k++) {
         __syncthreads();
         const double yk = y[k];
         for (int i = k + 1 + tid; i < n; i += nt) y[i] -= S[(size_t)i * n + k] * yk;
     }
     __syncthreads();
-    const double tol = 1.0 / DBL_MAX;
     for (int i = tid; i < n; i += nt) { const double d = S[(size_t)i * n + i]; y[i] = (fabs(d) > tol) ? y[i] / d : 0.0; }
     for (int k = n - 1; k >= 0; k--) {
         __syncthreads();
@@ -1158,7 +1183,7 @@ static_assert(sizeof(double) * ((6 * kFastMaxKf) * (6 * kFastMaxKf + 1) + 2 * kF
 __device__ double g_project(const BaDev& p, double* __restrict__ rec, double* __restrict__ err, double delta, int tid, int nt)
 {
     double acc = 0;
-#pragma unroll 2
+#pragma unroll 4
     for (int e = tid; e < p.Ea; e += nt) {
         const int c = p.e_cam[e];
         const double* __restrict__ R = p.cam_R + 9 * c;
@@ -1288,8 +1313,10 @@ __device__ void g_finish_cams(const BaDev& p, int parts, int tid, int nt)
     }
 }
 // push + update in one pass (ref base_vertex.h:92-94, sparse_optimizer.cpp:433-446): the old state goes to the backup buffers
-__device__ void g_backup_update(const BaDev& p, int tid, int nt)
+__device__ double g_backup_update(const BaDev& p, double lambda, int tid, int nt)     // returns this thread's share of computeScale (ref levenberg.cpp:167-174)
 {
+    double acc = 0;
+    for (int j = tid; j < p.n; j += nt) { const double xj = p.x[j]; acc += xj * (lambda * xj + p.bp[j]); }
     for (int i = tid; i < p.Kf; i += nt) {
         const int c = p.c_cam[i];
 #pragma unroll
@@ -1300,10 +1327,12 @@ __device__ void g_backup_update(const BaDev& p, int tid, int nt)
     }
     for (int i = tid; i < p.Pl * 3; i += nt) {
         double* X = p.pt_X + 3 * (size_t)p.l_pt[i / 3] + i % 3;
-        const double old = *X;
+        const double old = *X, xj = p.x[p.n + i];
         p.pt_bak[i] = old;
-        *X = old + p.x[p.n + i];
+        *X = old + xj;
+        acc += xj * (lambda * xj + p.bl[i]);
     }
+    return acc;
 }
 // W = w Jj^T Ji of one edge from its record (6x3 row-major)
 __device__ __forceinline__ void g_edge_W(const BaDev& p, const double* __restrict__ rec, int e, int c, double* W)
@@ -1356,7 +1385,7 @@ __device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double l
             const double D0 = c00 * id, D1 = c01 * id, D2 = c02 * id, D4 = (A0 * A8 - A2 * A2) * id, D5 = (A2 * A1 - A0 * A5) * id, D8 = (A0 * A4 - A1 * A1) * id;
             const double b0 = p.bl[3 * li], b1 = p.bl[3 * li + 1], b2 = p.bl[3 * li + 2];
             const double db0 = D0 * b0 + D1 * b1 + D2 * b2, db1 = D1 * b0 + D4 * b1 + D5 * b2, db2 = D2 * b0 + D5 * b1 + D8 * b2;
-            if (e == p.l_ptr[li]) {
+            if (e == 0 || p.e_l[e - 1] != li) {
                 double* Dg = p.Dinv + 9 * (size_t)li;
                 Dg[0] = D0; Dg[1] = D1; Dg[2] = D2; Dg[3] = D1; Dg[4] = D4; Dg[5] = D5; Dg[6] = D2; Dg[7] = D5; Dg[8] = D8;
                 p.db[3 * li] = db0; p.db[3 * li + 1] = db1; p.db[3 * li + 2] = db2;
@@ -1408,10 +1437,14 @@ __device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double l
                 for (int r = 0; r < 6; r++)
 #pragma unroll
                     for (int c = 0; c < 3; c++) acc[r * 3 + c] += P0[r] * T0[c] + P1[r] * T1[c];
-                if (diag) {
+                if (diag & (half == 0)) {
                     const double j1 = A2[2].x;
 #pragma unroll
-                    for (int r = 0; r < 3; r++) cacc[r] += (half ? P0[3 + r] : P0[r]) * iz.y + (half ? P1[3 + r] : P1[r]) * j1;
+                    for (int r = 0; r < 3; r++) cacc[r] += P0[r] * iz.y + P1[r] * j1;
+                } else if (diag) {
+                    const double j1 = A2[2].x;
+#pragma unroll
+                    for (int r = 0; r < 3; r++) cacc[r] += P0[3 + r] * iz.y + P1[3 + r] * j1;
                 }
             }
         }
@@ -1590,7 +1623,7 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
                 PH(4);
                 if (ok2) g_backsub(p, recCur, tid, nt);
                 __syncthreads();
-                g_backup_update(p, tid, nt);
+                const double scalePart = g_backup_update(p, lambda, tid, nt);
                 __syncthreads();
                 f_cam_R(p, tid, nt);
                 __syncthreads();
@@ -1600,7 +1633,7 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
                 errLast = errTry;
                 double tempChi = block_sum(part, sh);
                 if (!ok2) tempChi = DBL_MAX;
-                const double scale = phase_scale(p, lambda, sh) + 1e-3;
+                const double scale = block_sum(scalePart, sh) + 1e-3;
                 PH(7);
                 if (tid == 0) {
                     double r = (currentChi - tempChi) / scale;
@@ -2793,8 +2826,8 @@ static int ba_prepare(mage_ba_t h, const float* huber, int n_iters, bool upload_
 // read-back of one call: the control block first; the per-edge outlier flags only when the kernel flagged something
 static int ba_fetch_flags(mage_ba_t h, cudaStream_t s)
 {
-    h->h_flags.assign(std::max(h->dev.Ea, 1), 0);
     if (h->h_ctl.n_flagged > 0) {
+        h->h_flags.assign(std::max(h->dev.Ea, 1), 0);
         MAGE_CUDA_TRY(cudaMemcpyAsync(h->h_flags.data(), h->dev.flags, h->dev.Ea, cudaMemcpyDeviceToHost, s));
         MAGE_CUDA_TRY(cudaStreamSynchronize(s));
     }
@@ -2816,8 +2849,9 @@ static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, f
     h->stats[0] = c.lm_iters; h->stats[1] = c.lm_trials;
     h->host_state_valid = false;
     std::vector<std::pair<long, int>> flagged;                          // (insertion sequence, observation) of every removed edge
-    for (int a = 0; a < h->dev.Ea; a++)
-        if (flags[a]) flagged.push_back({h->obs[h->active[a]].seq, h->active[a]});
+    if (c.n_flagged > 0)                                                // nothing to scan (and no flag read-back) when the kernel flagged no edge
+        for (int a = 0; a < h->dev.Ea; a++)
+            if (flags[a]) flagged.push_back({h->obs[h->active[a]].seq, h->active[a]});
     std::sort(flagged.begin(), flagged.end());                          // the reference walks activeEdges() in insertion order (:387)
     int m = 0;
     for (auto& fl : flagged) {
