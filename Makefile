@@ -3,7 +3,7 @@ NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v --fmad=true
 SRC := mageslam_b200/csrc
-OBJS := $(SRC)/capi.o $(SRC)/orb.o $(SRC)/match.o $(SRC)/ba.o $(SRC)/frontend.o $(SRC)/radius.o $(SRC)/project.o
+OBJS := $(SRC)/capi.o $(SRC)/orb.o $(SRC)/match.o $(SRC)/ba.o $(SRC)/frontend.o $(SRC)/radius.o $(SRC)/project.o $(SRC)/undistort.o
 LIB := mageslam_b200/libmage_b200.so
 
 all: $(LIB)

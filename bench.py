@@ -414,24 +414,41 @@ def bench_ba(args, world, rank, dist):
         b.StepBundleAdjustment(hub, 1e9)
         torch.cuda.synchronize(); single.append(time.perf_counter() - t0)
         st = b.stats()
-    # batched: one CTA per problem, one launch for all
-    bs = [BundlerLib().load(probs[i % len(probs)]) for i in range(nprob)]
-    StepMany(bs, [1.8], 1e9)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    t0 = time.perf_counter()
-    StepMany(bs, hub, 1e9)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    iters = sum(b.stats()["lm_iterations"] for b in bs) - nprob      # minus the untimed first iteration of each
+    # batched: one CTA per problem, one launch for all; three fresh sets of windows, median call
+    dts, its, trials = [], [], []
+    for rep in range(3):
+        bs = [BundlerLib().load(probs[i % len(probs)]) for i in range(nprob)]
+        StepMany(bs, [1.8], 1e9)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        StepMany(bs, hub, 1e9)
+        torch.cuda.synchronize()
+        dts.append(time.perf_counter() - t0)
+        st = [b.stats() for b in bs]
+        its.append(sum(s["lm_iterations"] for s in st) - nprob)      # minus the untimed first iteration of each
+        trials.append(sum(s["lambda_trials"] for s in st) - nprob)
+        del bs
+    k = sorted(range(3), key=lambda i: dts[i])[1]
+    dt, iters, ntrials = dts[k], its[k], trials[k]
     t = torch.tensor([dt], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    hbm, peak_src = peaks()
+    # one lambda trial of this window = 9.5 MFLOP (FP64) and 0.6 MB of algorithmic traffic
+    trial_rate = ntrials / float(t.item())
+    fp64_peak = 35.0        # TFLOP/s, FP64 FMA pipe measured on this pool's B200 with tools/fp64_peak.cu (profiles/README.md)
     out = {"metric": "local_ba_lm_iters_per_sec", "unit": "LM iterations/s", "value": world * iters / float(t.item()),
            "config": {"workload": "local BA 10 KF / 2000 pts / 8000 obs, Huber 1.8, 10 LM iterations per call", "problems_per_gpu": nprob,
-                      "mode": "batched: one CTA per problem, one persistent launch per call"},
+                      "mode": "batched: one CTA per problem, one persistent launch per call", "timer": "host clock around the synchronous C-ABI call, median of 3 fresh sets"},
            "single_problem": {"value": 10.0 / statistics.median(single), "unit": "LM iterations/s", "ms_per_call": 1e3 * statistics.median(single)},
+           "roofline": {"kernel": "k_ba_step", "bound": "hbm", "achieved": trial_rate * 0.6e6 / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": trial_rate * 0.6e6 / 1e9 / hbm, "traffic": 3.52e6, "traffic_unit": "bytes per lambda trial and problem (ncu, profiles/)",
+                        "peak_source": peak_src, "algorithmic_bytes_per_trial": 0.6e6,
+                        "fp64": {"achieved": trial_rate * 9.5e6 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": trial_rate * 9.5e6 / 1e12 / fp64_peak,
+                                 "flop_per_trial": 9.5e6},
+                        "note": "latency-bound on dependent global loads at 16 warps/SM (ncu: IPC 0.8, FP64 pipe 22 % busy, DRAM 30 %)"},
            "dtype": "f64"}
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_ba_baseline(parallel=False)
@@ -441,7 +458,7 @@ def bench_ba(args, world, rank, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="frames per step")

@@ -210,6 +210,27 @@ int  mage_project_map_points(const mage_projection_params* params, const mage_ma
 int  mage_project_map_points_device(const mage_projection_params* params, const mage_map_point* d_points, int n,
                                     mage_keypoint* d_out_kps, float* d_out_depth, uint8_t* d_out_flags, void* cuda_stream);
 
+/* --------------------------------------------------------------------------------------- Keypoint undistortion */
+
+/* A CameraCalibration as UndistortKeypoints reads it (ref Device/CameraCalibration.h:44-71): GetCameraMatrix() (cv::Matx33f,
+ * row-major) and GetCVDistortionCoeffs() in OpenCV order k1 k2 p1 p2 k3 [k4 k5 k6] -- 5 values for Poly3k, 8 for Rational6k,
+ * 0 for DistortionType::None. */
+typedef struct {
+    float camera_matrix[9];
+    float dist_coeffs[8];
+    int32_t n_dist_coeffs;
+} mage_camera_calibration;
+
+/* OrbFeatureDetector::UndistortKeypoints (ref Image/OrbFeatureDetector.cpp:30-62): every keypoint's pt is replaced by
+ * cv::undistortPoints(pt, distorted.K, distorted.coeffs, noArray(), undistorted.K) -- five fixed-point iterations in double,
+ * then the projective map by the undistorted camera matrix; bit-identical to OpenCV's result. The other KeyPoint fields are
+ * untouched. Host buffer, synchronous. The _device variant works in place on the detector's device output: n_frames slots of
+ * per_frame keypoints each, of which the first d_counts[f] are valid (d_counts NULL = all); it only enqueues on cuda_stream. */
+int  mage_undistort_keypoints(mage_keypoint* keypoints, int n, const mage_camera_calibration* distorted,
+                              const mage_camera_calibration* undistorted, void* cuda_stream);
+int  mage_undistort_keypoints_device(mage_keypoint* d_keypoints, const int* d_counts, int n_frames, int per_frame,
+                                     const mage_camera_calibration* distorted, const mage_camera_calibration* undistorted, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------- Front-end for a video stream */
 
 /* ORB extract of a batch of frames + Match of every frame (query) against its predecessor (train): the reference's

@@ -38,6 +38,11 @@ class OrbParams(C.Structure):
                 ("num_cells_x", C.c_int32), ("num_cells_y", C.c_int32)]
 
 
+class CameraCalibrationC(C.Structure):
+    """mage_camera_calibration: GetCameraMatrix() (row-major 3x3) + GetCVDistortionCoeffs() (reference Device/CameraCalibration.h:44-71)."""
+    _fields_ = [("camera_matrix", C.c_float * 9), ("dist_coeffs", C.c_float * 8), ("n_dist_coeffs", C.c_int32)]
+
+
 _lib = None
 
 
@@ -76,6 +81,8 @@ def lib():
     L.mage_radius_match.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, cf, ci, ci, vp, C.POINTER(ci), vp]
     L.mage_project_map_points.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.mage_project_map_points_device.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    L.mage_undistort_keypoints.argtypes = [vp, ci, vp, vp, vp]
+    L.mage_undistort_keypoints_device.argtypes = [vp, vp, ci, ci, vp, vp, vp]
     if hasattr(L, "mage_ba_create"):
         L.mage_ba_create.argtypes = [ci, C.POINTER(vp)]
         L.mage_ba_destroy.argtypes = [vp]

@@ -48,6 +48,8 @@ struct OrbGeom {
     float feature_factor, feature_strength, min_rf, max_rf;
     int umax[18];
     int gk[16];
+    float gkf[8];           // first half of the float Gaussian kernel (edge .. centre), used when blur_float != 0
+    int blur_float;         // the level ROIs are proper submatrices of the reference's packed buffer: cv::GaussianBlur's float path
     LevelGeom lv[kMaxLevels];
 };
 
@@ -776,6 +778,158 @@ __global__ void __launch_bounds__(256) k_blur7_edges(const __grid_constant__ Orb
     blur_ptr(g, b, f, l)[(size_t)y * L.pitch + x] = (uint8_t)(acc >> 16);
 }
 
+
+// ------------------------------------------------------------------------------------------------ K5b: blur, float path
+// cv::GaussianBlur of a SUBMATRIX source -- the reference blurs level ROIs of its packed pyramid buffer in place (ref :853-865),
+// which OpenCV does not route to the fixed-point path above but through sepFilter2D with CV_32F kernels:
+//   row    s = K[0]*x[0]; s = fma(K[k], x[k], s), k = 1 .. ksize-1          (uchar -> float, left to right)
+//   column s = Kc*r[c];   s = fma(K[c+k], r[c+k] + r[c-k], s), k = 1 .. ksize/2, then cvRound + saturate (float -> uchar)
+// evaluated with fused multiply-adds exactly like the stock OpenCV 4.13 build the parity tests compare with.
+// Every operation is an explicitly rounded intrinsic, so the result is bit-identical.
+__device__ __forceinline__ float u8f(uint32_t w, int byte)         // byte -> float without the quarter-rate I2F: 2^23 + x as bits, minus 2^23
+{
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650u | (uint32_t)byte)), 8388608.f);
+}
+__device__ __forceinline__ uint32_t f2u8(float s)
+{
+    return (uint32_t)min(max(__float2int_rn(s), 0), 255);
+}
+
+__global__ void __launch_bounds__(256) k_blurf(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    __shared__ uint8_t in[kBlurIH * kBlurIW];
+    __shared__ float mid[kBlurIH * kBlurOW];
+    const int f = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_base) l++;
+    const LevelGeom& L = g.lv[l];
+    const int t = blockIdx.x - L.blur_tile_base;
+    const int x0 = (t % L.blur_tiles_x) * kBlurOW, y0 = (t / L.blur_tiles_x) * kBlurOH;
+    const int r = g.ksize / 2, ks = g.ksize;
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+    const int iw = kBlurOW + 2 * r, ih = kBlurOH + 2 * r;
+    for (int i = threadIdx.x; i < ih * iw; i += blockDim.x) {
+        int ry = i / iw, rx = i - ry * iw;
+        int y = reflect101(min(y0 + ry - r, L.h + r), L.h), x = reflect101(min(x0 + rx - r, L.w + r), L.w);
+        in[ry * kBlurIW + rx] = img[(size_t)y * pitch + x];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ih * kBlurOW; i += blockDim.x) {
+        int ry = i / kBlurOW, ox = i - ry * kBlurOW;
+        float s = __fmul_rn(g.gkf[0], (float)in[ry * kBlurIW + ox]);
+        for (int k = 1; k < ks; k++) s = __fmaf_rn(g.gkf[k <= r ? k : 2 * r - k], (float)in[ry * kBlurIW + ox + k], s);
+        mid[ry * kBlurOW + ox] = s;
+    }
+    __syncthreads();
+    uint8_t* out = blur_ptr(g, b, f, l);
+    for (int i = threadIdx.x; i < kBlurOH * (kBlurOW / 4); i += blockDim.x) {
+        int oy = i / (kBlurOW / 4), ox = (i - oy * (kBlurOW / 4)) * 4;
+        int y = y0 + oy, x = x0 + ox;
+        if (y >= L.h || x >= L.w) continue;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float s = __fmul_rn(g.gkf[r], mid[(oy + r) * kBlurOW + ox + j]);
+            for (int k = 1; k <= r; k++) s = __fmaf_rn(g.gkf[r - k], __fadd_rn(mid[(oy + r + k) * kBlurOW + ox + j], mid[(oy + r - k) * kBlurOW + ox + j]), s);
+            packed |= f2u8(s) << (8 * j);
+        }
+        *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
+    }
+}
+
+// 7x7 float path, same work split as k_blur7: a thread owns 4 columns x kBlur7Rows rows, the row pass of its 22 source rows stays
+// in registers (88 floats), no shared memory. Interior columns only; k_blur7f_edges does the REFLECT_101 columns.
+__global__ void __launch_bounds__(256) k_blur7f(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    const int f = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].blur_tile_base) l++;
+    const LevelGeom& L = g.lv[l];
+    const int t = blockIdx.x - L.blur_tile_base;
+    const int x = (t % L.blur_tiles_x) * 128 + (threadIdx.x & 31) * 4;
+    const int y0 = (t / L.blur_tiles_x) * (8 * kBlur7Rows) + (threadIdx.x >> 5) * kBlur7Rows;
+    if (x < 4 || x + 8 > L.w || y0 >= L.h) return;
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+    const float k0 = g.gkf[0], k1 = g.gkf[1], k2 = g.gkf[2], k3 = g.gkf[3];
+    float T[kBlur7Rows + 6][4];
+#pragma unroll
+    for (int i = 0; i < kBlur7Rows + 6; i++) {
+        int sy = min(y0 + i - 3, L.h + 2);
+        sy = sy < 0 ? -sy : sy;
+        sy = sy >= L.h ? 2 * L.h - 2 - sy : sy;
+        const uint8_t* row = img + (size_t)sy * pitch;
+        const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row + x - 4), w1 = *reinterpret_cast<const uint32_t*>(row + x),
+                       w2 = *reinterpret_cast<const uint32_t*>(row + x + 4);
+        float v[10];                                           // pixels x-3 .. x+6
+        v[0] = u8f(w0, 1); v[1] = u8f(w0, 2); v[2] = u8f(w0, 3);
+        v[3] = u8f(w1, 0); v[4] = u8f(w1, 1); v[5] = u8f(w1, 2); v[6] = u8f(w1, 3);
+        v[7] = u8f(w2, 0); v[8] = u8f(w2, 1); v[9] = u8f(w2, 2);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float s = __fmul_rn(k0, v[j]);
+            s = __fmaf_rn(k1, v[j + 1], s); s = __fmaf_rn(k2, v[j + 2], s); s = __fmaf_rn(k3, v[j + 3], s);
+            s = __fmaf_rn(k2, v[j + 4], s); s = __fmaf_rn(k1, v[j + 5], s); s = __fmaf_rn(k0, v[j + 6], s);
+            T[i][j] = s;
+        }
+    }
+    uint8_t* out = blur_ptr(g, b, f, l);
+#pragma unroll
+    for (int r = 0; r < kBlur7Rows; r++) {
+        const int y = y0 + r;
+        if (y < L.h) {
+            uint32_t packed = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                float s = __fmul_rn(k3, T[r + 3][j]);
+                s = __fmaf_rn(k2, __fadd_rn(T[r + 4][j], T[r + 2][j]), s);
+                s = __fmaf_rn(k1, __fadd_rn(T[r + 5][j], T[r + 1][j]), s);
+                s = __fmaf_rn(k0, __fadd_rn(T[r + 6][j], T[r][j]), s);
+                packed |= f2u8(s) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_blur7f_edges(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    const int f = blockIdx.z, l = blockIdx.y;
+    if (l >= g.nlevels) return;
+    const LevelGeom& L = g.lv[l];
+    const int last = ((L.w - 8) / 4) * 4;
+    const int xr = (L.w >= 12) ? last + 4 : 0;
+    const int nleft = (L.w >= 12) ? 4 : 0, nright = L.w - xr, ncols = nleft + nright;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncols * L.h) return;
+    const int y = i / ncols, c = i - y * ncols;
+    const int x = (c < nleft) ? c : xr + (c - nleft);
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+    int xs[7];
+#pragma unroll
+    for (int k = 0; k < 7; k++) xs[k] = reflect101(x + k - 3, L.w);
+    const float kk[4] = {g.gkf[0], g.gkf[1], g.gkf[2], g.gkf[3]};
+    float R[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+        int sy = y + j - 3;
+        sy = sy < 0 ? -sy : sy;
+        sy = sy >= L.h ? 2 * L.h - 2 - sy : sy;
+        const uint8_t* row = img + (size_t)sy * pitch;
+        float s = __fmul_rn(kk[0], (float)row[xs[0]]);
+#pragma unroll
+        for (int k = 1; k < 7; k++) s = __fmaf_rn(kk[k <= 3 ? k : 6 - k], (float)row[xs[k]], s);
+        R[j] = s;
+    }
+    float s = __fmul_rn(kk[3], R[3]);
+    s = __fmaf_rn(kk[2], __fadd_rn(R[4], R[2]), s);
+    s = __fmaf_rn(kk[1], __fadd_rn(R[5], R[1]), s);
+    s = __fmaf_rn(kk[0], __fadd_rn(R[6], R[0]), s);
+    blur_ptr(g, b, f, l)[(size_t)y * L.pitch + x] = (uint8_t)f2u8(s);
+}
+
 // ------------------------------------------------------------------------------------------------ K4+K7: orientation + rBRIEF
 // ref OpenCVModified.cpp:399-437 (ICAngles), :756-760 (rescale), :502-549 (ComputeOrbDescriptorsPrerotated),
 // cv::fastAtan2 restated in SURVEY appendix A.1 (float32, no FMA contraction).
@@ -955,6 +1109,23 @@ const int* gauss_kernel_q8(int ksize)
     }
 }
 
+// getGaussianKernel(ksize, 2, CV_32F) of OpenCV 4.13, first half (edge .. centre): the kernels of cv::GaussianBlur's float path
+const float* gauss_kernel_f32(int ksize)
+{
+    static const float k3[] = {0x1.46d3eap-2f, 0x1.72582cp-2f};
+    static const float k5[] = {0x1.3841bep-3f, 0x1.c654bap-3f, 0x1.016988p-2f};
+    static const float k7[] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95c0p-3f};
+    static const float k9[] = {0x1.c4b2eep-6f, 0x1.0f7df8p-4f, 0x1.fb36c8p-4f, 0x1.70fefap-3f, 0x1.a22092p-3f};
+    static const float k11[] = {0x1.20c256p-7f, 0x1.bcb86ap-6f, 0x1.0ab50ap-4f, 0x1.f2464cp-4f, 0x1.6a7e1ep-3f, 0x1.9ac20ap-3f};
+    static const float k13[] = {0x1.22be4ep-9f, 0x1.1f7a64p-7f, 0x1.babf56p-6f, 0x1.098622p-4f, 0x1.f01066p-4f, 0x1.68e26cp-3f, 0x1.98ef8ap-3f};
+    static const float k15[] = {0x1.c99b3ap-12f, 0x1.227d56p-9f, 0x1.1f3a28p-7f, 0x1.ba5c6ap-6f, 0x1.094acep-4f, 0x1.efa190p-4f, 0x1.6891cap-3f, 0x1.98942ap-3f};
+    switch (ksize) {
+    case 3: return k3; case 5: return k5; case 7: return k7; case 9: return k9;
+    case 11: return k11; case 13: return k13; case 15: return k15;
+    default: return nullptr;
+    }
+}
+
 // cv::resize INTER_LINEAR coefficient tables for one axis
 void resize_axis(int ssize, int dsize, int* ofs, short2* coef)
 {
@@ -1005,7 +1176,13 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     g.ksize = p->gaussian_kernel_size > 1 ? (int)p->gaussian_kernel_size : 1;
     g.strong_response = p->strong_response; g.num_cells_x = p->num_cells_x; g.num_cells_y = p->num_cells_y;
     g.feature_factor = p->feature_factor; g.feature_strength = p->feature_strength; g.min_rf = p->min_robust_factor; g.max_rf = p->max_robust_factor;
-    if (g.ksize > 1) { const int* k = gauss_kernel_q8(g.ksize); for (int i = 0; i < g.ksize; i++) g.gk[i] = k[i]; }
+    if (g.ksize > 1) {
+        const int* k = gauss_kernel_q8(g.ksize); for (int i = 0; i < g.ksize; i++) g.gk[i] = k[i];
+        const float* kf = gauss_kernel_f32(g.ksize); for (int i = 0; i <= g.ksize / 2; i++) g.gkf[i] = kf[i];
+        // ref :792,:812,:860: the blur source is imagePyramid(layerInfo[level]) -- a proper submatrix of the (cols+15)&-16 wide packed
+        // buffer unless there is a single level that fills it; cv::GaussianBlur only takes its fixed-point path for non-submatrix sources
+        g.blur_float = (g.nlevels > 1 || (width & 15) != 0) ? 1 : 0;
+    }
     {   // ref :673-689 umax
         int hp = g.half_patch, v, v0, vmax = cvFloorF(hp * std::sqrt(2.f) / 2 + 1), vmin = cvCeilF(hp * std::sqrt(2.f) / 2);
         for (v = 0; v <= vmax; ++v) g.umax[v] = (int)lrint(std::sqrt((double)hp * hp - v * v));
@@ -1157,10 +1334,19 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
     if (fork) { MAGE_CUDA_TRY(cudaEventRecord(h->ev_pyr, s)); MAGE_CUDA_TRY(cudaStreamWaitEvent(sb, h->ev_pyr, 0)); }
     if (g.ksize == 7) {
         ProfScope ps(PROF_BLUR, sb);
-        k_blur7<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
-        k_blur7_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
+        if (g.blur_float) {
+            k_blur7f<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+            k_blur7f_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
+        } else {
+            k_blur7<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+            k_blur7_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
+        }
     }
-    else if (g.ksize > 1) { ProfScope ps(PROF_BLUR, sb); k_blur<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs); }
+    else if (g.ksize > 1) {
+        ProfScope ps(PROF_BLUR, sb);
+        if (g.blur_float) k_blurf<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+        else k_blur<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+    }
     if (fork) MAGE_CUDA_TRY(cudaEventRecord(h->ev_blur, sb));
     { ProfScope ps(PROF_FAST, s); k_fast<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs); }
     { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }

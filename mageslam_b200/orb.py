@@ -133,10 +133,45 @@ class OrbDetector:
         return out[:cnt.value]
 
 
+class CameraCalibration:
+    """The part of mage::CameraCalibration the detector reads (reference Device/CameraCalibration.h:44-71): the 3x3 camera
+    matrix and the OpenCV-ordered distortion coefficients k1 k2 p1 p2 k3 [k4 k5 k6] (none = DistortionType::None)."""
+
+    def __init__(self, fx, fy, cx, cy, dist_coeffs=()):
+        self.camera_matrix = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+        self.dist_coeffs = np.asarray(dist_coeffs, np.float32).ravel()
+        assert len(self.dist_coeffs) in (0, 4, 5, 8)
+
+    def __eq__(self, other):          # reference CameraCalibration::operator== (.cpp:95-108)
+        return (isinstance(other, CameraCalibration) and np.array_equal(self.camera_matrix, other.camera_matrix)
+                and np.array_equal(self.dist_coeffs, other.dist_coeffs))
+
+    def __ne__(self, other):
+        return not self == other
+
+    def c_struct(self):
+        from ._lib import CameraCalibrationC
+        c = CameraCalibrationC()
+        for i, v in enumerate(self.camera_matrix.ravel()):
+            c.camera_matrix[i] = float(v)
+        for i, v in enumerate(self.dist_coeffs):
+            c.dist_coeffs[i] = float(v)
+        c.n_dist_coeffs = len(self.dist_coeffs)
+        return c
+
+
+def UndistortKeypoints(inoutKeypoints, distortedCalibration, undistortedCalibration):
+    """Mirror of OrbFeatureDetector::UndistortKeypoints (reference Image/OrbFeatureDetector.cpp:30-62): in place on a
+    KEYPOINT_DTYPE array."""
+    assert inoutKeypoints.dtype == KEYPOINT_DTYPE and inoutKeypoints.flags["C_CONTIGUOUS"]
+    d, u = distortedCalibration.c_struct(), undistortedCalibration.c_struct()
+    check(lib().mage_undistort_keypoints(ptr(inoutKeypoints), len(inoutKeypoints), C.byref(d), C.byref(u), None))
+    return inoutKeypoints
+
+
 class OrbFeatureDetector:
     """Mirror of mage::OrbFeatureDetector (reference Image/OrbFeatureDetector.cpp:64-100). Process() runs
-    DetectAndCompute; keypoint undistortion (cv::undistortPoints, :30-62) only applies to distorted calibrations and is
-    out of scope: a distorted calibration raises."""
+    DetectAndCompute and, when the distorted and undistorted calibrations differ, UndistortKeypoints (:97-99)."""
 
     def __init__(self, settings: FeatureExtractorSettings, max_batch=1):
         s = settings
@@ -146,6 +181,7 @@ class OrbFeatureDetector:
                                       s.MaxRobustnessFactor, s.NumCellsX, s.NumCellsY, max_batch=max_batch)
 
     def Process(self, image, distortedCalibration=None, undistortedCalibration=None):
+        kps, desc = self.m_detector.DetectAndCompute(image, capacity=self.settings.NumFeatures)
         if distortedCalibration is not None and distortedCalibration != undistortedCalibration:
-            raise NotImplementedError("UndistortKeypoints is outside the accelerated path (SURVEY.md 8a, row A16)")
-        return self.m_detector.DetectAndCompute(image, capacity=self.settings.NumFeatures)
+            kps = UndistortKeypoints(np.ascontiguousarray(kps), distortedCalibration, undistortedCalibration)
+        return kps, desc

@@ -143,6 +143,64 @@ int gaussianBlur(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, in
     return 0;
 }
 
+// cv::GaussianBlur on a SUBMATRIX source -- what the reference's in-place blur of a level ROI of the packed pyramid buffer is
+// (ref :853-865; every level is a proper submatrix unless nlevels == 1 and cols % 16 == 0). OpenCV only takes the bit-exact
+// fixed-point path above for non-submatrix 8-bit sources; a submatrix goes createGaussianKernels(CV_32F) -> sepFilter2D:
+//   row pass    RowFilter<uchar, float, RowNoVec>:            s = kx[0]*x[0];  s += kx[k]*x[k], k = 1 .. ksize-1   (left to right)
+//   column pass SymmColumnFilter<Cast<float, uchar>, NoVec>:  s = ky[c]*r[c] + 0;  s += ky[c+k]*(r[c+k] + r[c-k]), k = 1 .. ksize/2
+//   saturate_cast<uchar>(float) = clamp(cvRound(s)).
+// Float kernels = getGaussianKernel(ksize, 2, CV_32F) of cv2 4.13 (first half; symmetric). `fused` evaluates every
+// multiply-add as one FMA -- what a -mfma build of OpenCV (the AVX2 dispatch unit of the cv2 wheel) makes of the same
+// source; the reference semantics (MSVC /fp:precise, SSE2 baseline) is the unfused one. The two differ in ~1e-5 of the pixels.
+const float* gaussKernelF32(int ksize)
+{
+    static const float k3[] = {0x1.46d3eap-2f, 0x1.72582cp-2f};
+    static const float k5[] = {0x1.3841bep-3f, 0x1.c654bap-3f, 0x1.016988p-2f};
+    static const float k7[] = {0x1.1f5f62p-4f, 0x1.0c70fcp-3f, 0x1.869472p-3f, 0x1.ba95c0p-3f};
+    static const float k9[] = {0x1.c4b2eep-6f, 0x1.0f7df8p-4f, 0x1.fb36c8p-4f, 0x1.70fefap-3f, 0x1.a22092p-3f};
+    static const float k11[] = {0x1.20c256p-7f, 0x1.bcb86ap-6f, 0x1.0ab50ap-4f, 0x1.f2464cp-4f, 0x1.6a7e1ep-3f, 0x1.9ac20ap-3f};
+    static const float k13[] = {0x1.22be4ep-9f, 0x1.1f7a64p-7f, 0x1.babf56p-6f, 0x1.098622p-4f, 0x1.f01066p-4f, 0x1.68e26cp-3f, 0x1.98ef8ap-3f};
+    static const float k15[] = {0x1.c99b3ap-12f, 0x1.227d56p-9f, 0x1.1f3a28p-7f, 0x1.ba5c6ap-6f, 0x1.094acep-4f, 0x1.efa190p-4f, 0x1.6891cap-3f, 0x1.98942ap-3f};
+    switch (ksize) {
+    case 3: return k3; case 5: return k5; case 7: return k7; case 9: return k9;
+    case 11: return k11; case 13: return k13; case 15: return k15;
+    default: return nullptr;
+    }
+}
+int gaussianBlurSubmatrix(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int ksize, bool fused)
+{
+    const float* kh = gaussKernelF32(ksize);
+    if (!kh) return -1;
+    const int r = ksize / 2;
+    auto K = [&](int i) { return kh[i <= r ? i : 2 * r - i]; };          // full symmetric kernel, index 0 .. ksize-1
+    std::vector<float> T((size_t)w * h);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* S = src + (size_t)y * sstride;
+        for (int x = 0; x < w; x++) {
+            float s = K(0) * (float)S[reflect101(x - r, w)];
+            for (int k = 1; k < ksize; k++) {
+                const float v = (float)S[reflect101(x + k - r, w)];
+                s = fused ? fmaf(K(k), v, s) : s + K(k) * v;
+            }
+            T[(size_t)y * w + x] = s;
+        }
+    }
+    for (int y = 0; y < h; y++) {
+        uint8_t* D = dst + (size_t)y * dstride;
+        for (int x = 0; x < w; x++) {
+            const float c = T[(size_t)y * w + x];
+            float s = fused ? fmaf(kh[r], c, 0.f) : kh[r] * c + 0.f;
+            for (int k = 1; k <= r; k++) {
+                const float v = T[(size_t)reflect101(y + k, h) * w + x] + T[(size_t)reflect101(y - k, h) * w + x];
+                s = fused ? fmaf(kh[r - k], v, s) : s + kh[r - k] * v;
+            }
+            int iv = cvRoundF(s);
+            D[x] = (uint8_t)(iv < 0 ? 0 : iv > 255 ? 255 : iv);
+        }
+    }
+    return 0;
+}
+
 // ---- FAST-9/16 ----------------------------------------------------------------------------------------------------
 // ref Image/OpenCVModified.cpp:890-921 (makeOffsets), ring order k = 0..15
 const int kRing[16][2] = {{0, 3}, {1, 3}, {2, 2}, {3, 1}, {3, 0}, {3, -1}, {2, -2}, {1, -3},
@@ -470,6 +528,10 @@ int orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_t*
 {
     return gaussianBlur(src, w, h, sstride, dst, dstride, ksize);
 }
+int orc_gaussian_blur_submatrix_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int ksize, int fused)
+{
+    return gaussianBlurSubmatrix(src, w, h, sstride, dst, dstride, ksize, fused != 0);
+}
 
 int orc_fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, orc_keypoint* out, int capacity)
 {
@@ -606,11 +668,15 @@ int orc_orb_detect_and_compute(const orc_orb_params* pp, const uint8_t* img, int
     for (auto& k : all) { float s = L.scale[k.octave]; k.x *= s; k.y *= s; }
 
     // ---- blur (ref :853-865). Per-level REFLECT_101; see DESIGN.md for when this equals the reference's ROI blur.
+    // The source is imagePyramid(layerInfo[level]): a proper submatrix of the (cols + 15) & -16 wide packed buffer (ref :792-812)
+    // unless a single level fills it, and cv::GaussianBlur routes submatrices through its generic float path.
     if (p.gaussian_kernel_size > 1) {
+        const bool submatrix = L.n > 1 || (w & 15) != 0;
         for (int l = 0; l < L.n; l++) {
             if (L.w[l] < 1 || L.h[l] < 1) continue;
             std::vector<uint8_t> tmp(pyr[l].size());
-            gaussianBlur(ptrs[l], L.w[l], L.h[l], L.w[l], tmp.data(), L.w[l], (int)p.gaussian_kernel_size);
+            if (submatrix) gaussianBlurSubmatrix(ptrs[l], L.w[l], L.h[l], L.w[l], tmp.data(), L.w[l], (int)p.gaussian_kernel_size, true);
+            else gaussianBlur(ptrs[l], L.w[l], L.h[l], L.w[l], tmp.data(), L.w[l], (int)p.gaussian_kernel_size);
             pyr[l].swap(tmp);
             ptrs[l] = pyr[l].data();
         }

@@ -54,6 +54,8 @@ int orc_orb_detect_and_compute(const orc_orb_params* p, const uint8_t* img, int 
 /* --- stage-level entry points, used by the cv2 cross-check tests and by the stage parity tests --- */
 void  orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);
 int   orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int ksize);
+/* cv::GaussianBlur of a SUBMATRIX source (generic separable float path); fused = every multiply-add as one FMA */
+int   orc_gaussian_blur_submatrix_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int ksize, int fused);
 float orc_fast_atan2(float y, float x);
 int   orc_cv_round_f(float v);
 /* FAST-9/16 + score + 3x3 NMS in raster order; returns number found (may exceed capacity; only capacity written) */

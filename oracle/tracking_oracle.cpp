@@ -88,4 +88,49 @@ float trk_octave_real(float distance, float dmin, float scale_factor)
     return log2f(distance / dmin) / log2f(scale_factor) - 0.5f;
 }
 
+
+
+/*
+ * Keypoint undistortion: mage::OrbFeatureDetector::UndistortKeypoints (Core/MAGESLAM/Source/Image/OrbFeatureDetector.cpp:30-62)
+ * = cv::undistortPoints(src, dst, distorted.GetCameraMatrix(), distorted.GetCVDistortionCoeffs(), noArray(), undistorted.GetCameraMatrix())
+ * on the keypoints' pt. OpenCV is not vendored: restated from its published algorithm (calib3d undistort, cvUndistortPointsInternal):
+ * everything in double, TermCriteria(MAX_ITER, 5, 0.01) => exactly five fixed-point iterations, the icdist < 0 escape, then the
+ * projective map with P = the new camera matrix. Pinned bit-for-bit against cv2 4.13 (tests/test_tracking_oracle.py).
+ * Coefficient order k1 k2 p1 p2 k3 [k4 k5 k6] (CameraCalibration.h:53); 5 (Poly3k) or 8 (Rational6k) are used by the reference.
+ */
+typedef struct { float camera_matrix[9]; float dist_coeffs[8]; int32_t n_dist_coeffs; } trk_calibration;
+
+void trk_undistort_keypoints(trk_keypoint* kps, int n, const trk_calibration* dist, const trk_calibration* undist)
+{
+    double k[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < dist->n_dist_coeffs && i < 8; i++) k[i] = (double)dist->dist_coeffs[i];
+    const double fx = dist->camera_matrix[0], fy = dist->camera_matrix[4], cx = dist->camera_matrix[2], cy = dist->camera_matrix[5];
+    const double ifx = 1. / fx, ify = 1. / fy;
+    double RR[9];
+    for (int i = 0; i < 9; i++) RR[i] = (double)undist->camera_matrix[i];
+    for (int i = 0; i < n; i++) {
+        double x = kps[i].x, y = kps[i].y;
+        const double u = x, v = y;
+        x = (x - cx) * ifx;
+        y = (y - cy) * ify;
+        if (dist->n_dist_coeffs > 0) {
+            const double x0 = x, y0 = y;
+            for (int j = 0; j < 5; j++) {
+                const double r2 = x * x + y * y;
+                const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+                if (icdist < 0) { x = (u - cx) * ifx; y = (v - cy) * ify; break; }
+                const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+                const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+                x = (x0 - deltaX) * icdist;
+                y = (y0 - deltaY) * icdist;
+            }
+        }
+        const double xx = RR[0] * x + RR[1] * y + RR[2];
+        const double yy = RR[3] * x + RR[4] * y + RR[5];
+        const double ww = 1. / (RR[6] * x + RR[7] * y + RR[8]);
+        kps[i].x = (float)(xx * ww);
+        kps[i].y = (float)(yy * ww);
+    }
+}
+
 } // extern "C"

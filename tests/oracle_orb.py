@@ -68,6 +68,21 @@ def blur(src, ksize=7):
     return dst
 
 
+def blur_submatrix(src, ksize=7, fused=True):
+    """cv::GaussianBlur of a SUBMATRIX source (the reference's in-place blur of a level ROI): the generic separable float path"""
+    src, sp = _u8(src)
+    dst = np.empty_like(src)
+    rc = lib().orc_gaussian_blur_submatrix_u8(sp, src.shape[1], src.shape[0], src.strides[0], dst.ctypes.data_as(C.c_void_p),
+                                              dst.strides[0], ksize, 1 if fused else 0)
+    assert rc == 0
+    return dst
+
+
+def level_blur(level, ksize, nlevels, width):
+    """the blur DetectAndCompute applies to a level: float path when the level ROI is a proper submatrix of the packed buffer"""
+    return blur_submatrix(level, ksize) if (nlevels > 1 or (width & 15) != 0) else blur(level, ksize)
+
+
 def fast_atan2(y, x):
     return lib().orc_fast_atan2(float(y), float(x))
 

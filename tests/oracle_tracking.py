@@ -25,6 +25,8 @@ def lib():
         L.trk_octave_real.restype = C.c_float
         L.trk_project_map_points.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.trk_project_map_points.restype = None
+        L.trk_undistort_keypoints.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.trk_undistort_keypoints.restype = None
         _LIB = L
     return _LIB
 
@@ -56,3 +58,45 @@ def project_map_points(params, pts):
 
 def octave_real(distance, dmin, scale):
     return lib().trk_octave_real(float(distance), float(dmin), float(scale))
+
+
+class Calibration(C.Structure):
+    """trk_calibration == mage_camera_calibration"""
+    _fields_ = [("camera_matrix", C.c_float * 9), ("dist_coeffs", C.c_float * 8), ("n_dist_coeffs", C.c_int32)]
+
+
+def calibration(K, dist=()):
+    c = Calibration()
+    for i, v in enumerate(np.asarray(K, np.float32).ravel()):
+        c.camera_matrix[i] = float(v)
+    for i, v in enumerate(np.asarray(dist, np.float32).ravel()):
+        c.dist_coeffs[i] = float(v)
+    c.n_dist_coeffs = len(dist)
+    return c
+
+
+def undistort_keypoints(kps, K_dist, dist, K_undist):
+    """oracle of OrbFeatureDetector::UndistortKeypoints; returns a modified copy"""
+    out = np.ascontiguousarray(kps, KP_DTYPE).copy()
+    d, u = calibration(K_dist, dist), calibration(K_undist)
+    lib().trk_undistort_keypoints(out.ctypes.data_as(C.c_void_p), len(out), C.byref(d), C.byref(u))
+    return out
+
+
+def undistort_cases(seed=0, n=1500):
+    """(name, keypoints, K_dist, dist, K_undist): Poly3k / Rational6k, mild and strong (icdist < 0 escape) distortion, identity P"""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for t, (name, nco, scale) in enumerate([("poly3k", 5, 1.0), ("rational6k", 8, 1.0), ("poly3k_strong", 5, 8.0), ("rational6k_strong", 8, 8.0),
+                                             ("radial_only", 4, 1.0), ("no_distortion", 0, 1.0)]):
+        fx, fy = rng.uniform(300, 700, 2).astype(np.float32)
+        cx, cy = np.float32(320 + rng.normal(0, 10)), np.float32(240 + rng.normal(0, 10))
+        Kd = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float32)
+        Ku = np.array([[fx * 0.95, 0, cx + 2], [0, fy * 0.97, cy - 1], [0, 0, 1]], np.float32)
+        D = (rng.normal(0, 1, nco) * np.array([0.2, 0.1, 0.003, 0.003, 0.05, 0.1, 0.05, 0.02][:nco]) * scale).astype(np.float32)
+        kps = np.zeros(n, KP_DTYPE)
+        kps["x"] = rng.uniform(0, 640, n).astype(np.float32); kps["y"] = rng.uniform(0, 480, n).astype(np.float32)
+        kps["size"] = 31; kps["angle"] = rng.uniform(0, 360, n).astype(np.float32); kps["response"] = rng.integers(10, 200, n)
+        kps["octave"] = rng.integers(0, 8, n); kps["class_id"] = -1
+        cases.append((name, kps, Kd, D, Ku))
+    return cases

@@ -67,6 +67,52 @@ def test_gaussian_blur_matches_cv2(ksize):
         assert np.array_equal(ref, orc.blur(src, ksize)), (ksize, shape)
 
 
+@pytest.mark.parametrize("ksize", [3, 5, 7, 9, 11, 13, 15])
+def test_submatrix_gaussian_blur_matches_cv2_generic_path(ksize):
+    """cv::GaussianBlur of a SUBMATRIX (the reference's in-place blur of a pyramid-level ROI, OpenCVModified.cpp:853-865) does not
+    take the fixed-point path: it is sepFilter2D with the CV_32F Gaussian kernel. Python cannot hand cv2 a submatrix, so the
+    same code path is reached through cv2.sepFilter2D; test_stock_orb_descriptors_use_the_submatrix_blur closes the loop."""
+    rng = np.random.default_rng(100 + ksize)
+    k = cv2.getGaussianKernel(ksize, 2, cv2.CV_32F)
+    worst = 0
+    for shape in [(480, 640), (400, 533), (134, 179), (37, 53), (16, 16)]:
+        src = rng.integers(0, 256, shape).astype(np.uint8)
+        ref = cv2.sepFilter2D(src, cv2.CV_8U, k, k, borderType=cv2.BORDER_REFLECT_101)
+        fused, unfused = orc.blur_submatrix(src, ksize, True), orc.blur_submatrix(src, ksize, False)
+        # this cv2 build contracts multiply-adds (AVX2 unit): the fused variant must be identical; a build without FMA gives the
+        # unfused one. Accept either as a whole, never a mixture.
+        assert np.array_equal(ref, fused) or np.array_equal(ref, unfused), (ksize, shape)
+        d = fused.astype(int) - unfused.astype(int)
+        assert np.abs(d).max(initial=0) <= 1
+        worst = max(worst, int((d != 0).sum()) / src.size)
+    assert worst < 2e-4            # the two evaluations differ only on rounding ties
+
+
+def test_stock_orb_descriptors_use_the_submatrix_blur():
+    """Stock cv::ORB blurs its level ROI with the same GaussianBlur(7x7, 2, 2, REFLECT_101) call on a submatrix as the reference.
+    With provided keypoints (angle 0, learned 31-pattern) its descriptors are reproduced exactly from the oracle's submatrix blur and
+    NOT from the fixed-point whole-image blur -- evidence that a submatrix source takes the float path."""
+    rng = np.random.default_rng(1)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (240, 320)).astype(np.uint8), (0, 0), 1.5)
+    orb = cv2.ORB_create(nfeatures=500, scaleFactor=1.2, nlevels=1, edgeThreshold=31, firstLevel=0, WTA_K=2, patchSize=31, fastThreshold=10)
+    kps = [cv2.KeyPoint(float(x), float(y), 31.0, 0.0, 1.0, 0, -1) for x, y in zip(rng.integers(40, 280, 300), rng.integers(40, 200, 300))]
+    kps, desc = orb.compute(img, kps)
+    pat = orc.brief_pattern(31)[0].astype(np.int32).reshape(-1, 2)          # row 0 of the pre-rotated table = the learned pattern
+
+    def describe(blurred):
+        out = np.zeros((len(kps), 32), np.uint8)
+        for n, kp in enumerate(kps):
+            cy, cx = int(kp.pt[1]), int(kp.pt[0])
+            a = blurred[cy + pat[0::2, 1], cx + pat[0::2, 0]].astype(np.int32)
+            b = blurred[cy + pat[1::2, 1], cx + pat[1::2, 0]].astype(np.int32)
+            out[n] = np.packbits((a < b).reshape(32, 8), axis=1, bitorder="little").ravel()
+        return out
+
+    assert np.array_equal(describe(orc.blur_submatrix(img, 7)), desc)
+    assert not np.array_equal(describe(orc.blur(img, 7)), desc)
+
+
+
 @pytest.mark.parametrize("thr,seed", [(10, 0), (20, 1), (4, 2), (40, 3)])
 def test_fast_matches_cv2(thr, seed):
     img = synth.noise_frame(seed, 320, 240) if seed % 2 == 0 else synth.video_frames(1, 320, 240, seed)[0]

@@ -46,8 +46,23 @@ def test_pyramid_and_blur_levels_bit_exact(frames):
         got = det.DebugLevel(0, l, blurred=False)
         assert np.array_equal(got, ref[l]), "pyramid level %d: %d px differ" % (l, int((got != ref[l]).sum()))
         gotb = det.DebugLevel(0, l, blurred=True)
-        refb = orc.blur(ref[l], 7)
+        refb = orc.level_blur(ref[l], 7, p.nlevels, img.shape[1])       # 8 levels: every ROI is a submatrix => cv::GaussianBlur's float path
         assert np.array_equal(gotb, refb), "blurred level %d: %d px differ" % (l, int((gotb != refb).sum()))
+
+
+@pytest.mark.parametrize("ksize,nlevels,width", [(7, 1, 320), (7, 1, 330), (5, 3, 320), (9, 2, 200), (3, 4, 333), (15, 2, 256)])
+def test_blur_paths_bit_exact(ksize, nlevels, width):
+    """fixed-point path only when a single level fills the packed buffer (width % 16 == 0); float path otherwise; every kernel size"""
+    p = orc.tier_params(nfeatures=300, nlevels=nlevels)
+    p.gaussian_kernel_size = ksize
+    det = make_detector(p)
+    img = synth.video_frames(1, width, 200, seed=ksize)[0]
+    det.DetectAndCompute(img)
+    ref = orc.build_pyramid(p, img)
+    for l in range(nlevels):
+        gotb = det.DebugLevel(0, l, blurred=True)
+        refb = orc.level_blur(ref[l], ksize, nlevels, width)
+        assert np.array_equal(gotb, refb), "ksize %d level %d: %d px differ" % (ksize, l, int((gotb != refb).sum()))
 
 
 @pytest.mark.parametrize("which,thr", [("noise", 10), ("video", 10), ("video", 4), ("noise", 35)])

@@ -106,3 +106,32 @@ def test_feeds_radius_match():
     want = orc.radius_match(kps.astype(orc.KP_DTYPE), qdesc, tk.astype(orc.KP_DTYPE), tdesc, 8.0, 50, 2, qmask=pred)
     assert len(got) == len(want) and len(got) > 50
     assert np.array_equal(got["query_idx"], want["query"]) and np.array_equal(got["train_idx"], want["train"])
+
+
+def test_undistort_keypoints_equals_oracle_bit_for_bit():
+    """A16 on the GPU (mage_undistort_keypoints through the python mirror of OrbFeatureDetector::UndistortKeypoints)."""
+    from mageslam_b200.orb import CameraCalibration, UndistortKeypoints
+    for name, kps, Kd, D, Ku in ot.undistort_cases(seed=5):
+        want = ot.undistort_keypoints(kps, Kd, D, Ku)
+        dist = CameraCalibration(Kd[0, 0], Kd[1, 1], Kd[0, 2], Kd[1, 2], D)
+        und = CameraCalibration(Ku[0, 0], Ku[1, 1], Ku[0, 2], Ku[1, 2])
+        got = UndistortKeypoints(np.ascontiguousarray(kps.astype(KEYPOINT_DTYPE)).copy(), dist, und)
+        assert got.tobytes() == want.astype(KEYPOINT_DTYPE).tobytes(), name
+    assert len(UndistortKeypoints(np.zeros(0, KEYPOINT_DTYPE), dist, und)) == 0        # empty span: no-op (ref :39-42)
+
+
+def test_process_with_distorted_calibration_undistorts_the_detected_keypoints():
+    from mageslam_b200 import synth
+    from mageslam_b200.orb import CameraCalibration, FeatureExtractorSettings, OrbFeatureDetector
+    s = FeatureExtractorSettings.tier(500, 4, 1.2, 10)
+    img = synth.video_frames(1, 320, 240, seed=2)[0]
+    det = OrbFeatureDetector(s)
+    dist = CameraCalibration(260, 262, 160, 120, [0.12, -0.06, 0.001, -0.002, 0.01])
+    und = CameraCalibration(250, 250, 160, 120)
+    k0, d0 = det.Process(img)
+    k1, d1 = det.Process(img, dist, und)
+    assert np.array_equal(d0, d1) and len(k0) == len(k1) > 100
+    want = ot.undistort_keypoints(k0, dist.camera_matrix, dist.dist_coeffs, und.camera_matrix)
+    assert np.ascontiguousarray(k1).tobytes() == want.astype(KEYPOINT_DTYPE).tobytes()
+    k2, _ = det.Process(img, und, und)                  # equal calibrations: keypoints untouched (ref :97)
+    assert np.ascontiguousarray(k2).tobytes() == np.ascontiguousarray(k0).tobytes()

@@ -96,3 +96,18 @@ def test_empty_and_degenerate_inputs():
     kps, depth, flags = ot.project_map_points(p, pts)
     assert depth[0] == 0 or abs(depth[0]) < 1e-6
     assert np.isfinite(kps["x"][0]) and np.isfinite(kps["y"][0])
+
+
+def test_undistort_keypoints_oracle_equals_cv2_bit_for_bit():
+    """A16: the restated cv::undistortPoints (five fixed-point iterations in double, icdist < 0 escape, projective map by the
+    new camera matrix) against stock OpenCV on the same inputs -- float outputs must be identical, only pt may change."""
+    cv2 = pytest.importorskip("cv2")
+    for name, kps, Kd, D, Ku in ot.undistort_cases():
+        got = ot.undistort_keypoints(kps, Kd, D, Ku)
+        src = np.stack([kps["x"], kps["y"]], 1).reshape(-1, 1, 2).copy()
+        ref = cv2.undistortPoints(src, Kd.astype(np.float64), D.astype(np.float64) if len(D) else None, None, Ku.astype(np.float64)).reshape(-1, 2)
+        mine = np.stack([got["x"], got["y"]], 1)
+        same = (mine.view(np.uint32) == ref.view(np.uint32)) | (np.isnan(mine) & np.isnan(ref))
+        assert same.all(), (name, int((~same).sum()))
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(got[f], kps[f])
