@@ -66,7 +66,7 @@ typedef struct mage_orb_params {
     uint32_t nfeatures;
     float    scale_factor;
     uint32_t nlevels;
-    uint32_t patch_size;             /* 31 or 15 (pre-rotated BRIEF tables) */
+    uint32_t patch_size;             /* 2..127: 31 / 15 use the pre-rotated BRIEF tables, any other size the cv::RNG pattern rotated at run time (ref :866-885) */
     uint32_t fast_threshold;
     int32_t  use_orientation;
     float    feature_factor;         /* featureFactorANMS */

@@ -46,7 +46,8 @@ struct OrbGeom {
     int fast_threshold, border, patch, half_patch, use_orientation, ksize;
     int strong_response, num_cells_x, num_cells_y;
     float feature_factor, feature_strength, min_rf, max_rf;
-    int umax[18];
+    int umax[66];           // half_patch + 2 entries (half_patch <= 63)
+    int generic_pattern;    // patch size without a pre-rotated table: runtime rotation of the cv::RNG pattern (ref :452-492)
     int gk[16];
     float gkf[8];           // first half of the float Gaussian kernel (edge .. centre), used when blur_float != 0
     int blur_float;         // the level ROIs are proper submatrices of the reference's packed buffer: cv::GaussianBlur's float path
@@ -67,7 +68,7 @@ struct OrbBuffers {
     unsigned long long* keys; size_t key_stride;
     uint32_t* sel;   int* sel_count;   size_t sel_stride;     // [f][sel_total], [f][kMaxLevels]
     int* status;                                                // [f]
-    const int8_t* pattern;                                      // 30 x 1024 pre-rotated BRIEF table
+    const int8_t* pattern;                                      // 30 x 1024 pre-rotated BRIEF table, or the 512 (x, y) points of the generic pattern
 };
 
 // ------------------------------------------------------------------------------------------------ device helpers
@@ -959,7 +960,7 @@ __device__ __forceinline__ void orient_moments(const uint8_t* center, int pitch,
 {
     const int hp = HP ? HP : hp_rt;
     const int u = lane - hp, au = u < 0 ? -u : u;
-    if (lane > 2 * hp) return;
+    if (HP && lane > 2 * hp) return;
     if (HP) {
         int val[2 * (HP ? HP : 1) + 1];
 #pragma unroll
@@ -972,9 +973,12 @@ __device__ __forceinline__ void orient_moments(const uint8_t* center, int pitch,
         for (int i = 0; i < 2 * HP + 1; i++) { rowsum += val[i]; m01 += (i - HP) * val[i]; }
         m10 += u * rowsum;
     } else {
-        for (int v = -hp; v <= hp; v++) {
-            const int av = v < 0 ? -v : v;
-            if (au <= umax[av]) { const int x = center[v * pitch + u]; m10 += u * x; m01 += v * x; }
+        for (int uu = lane; uu <= 2 * hp; uu += 32) {                // half patches above 15 need more than one column per lane
+            const int u2 = uu - hp, au2 = u2 < 0 ? -u2 : u2;
+            for (int v = -hp; v <= hp; v++) {
+                const int av = v < 0 ? -v : v;
+                if (au2 <= umax[av]) { const int x = center[v * pitch + u2]; m10 += u2 * x; m01 += v * x; }
+            }
         }
     }
 }
@@ -1032,6 +1036,28 @@ __global__ void __launch_bounds__(256) k_orient_describe(const __grid_constant__
     int pitch = L.pitch;
     if (!base) base = level_ptr(g, b, f, l, pitch);
     const uint8_t* ctr = base + (size_t)cyy * pitch + cxx;
+    if (g.generic_pattern) {
+        // ref :452-492 ComputeOrbDescriptors: a = (float)cos(angle), b = (float)sin(angle) in double precision on the float angle,
+        // x = px*a - py*b, y = px*b + py*a in float32 with separately rounded products, sampled at (cvRound(y), cvRound(x))
+        const float rad = __fmul_rn(angle, (float)(3.1415926535897932384626433832795 / 180.0f));
+        const float ca = (float)cos((double)rad), sa = (float)sin((double)rad);
+        const int4* gp = reinterpret_cast<const int4*>(b.pattern + lane * 32);
+        const int4 qa = __ldg(gp), qb = __ldg(gp + 1);
+        const int q8[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        int gval = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; bit++) {
+            const int w = q8[bit];
+            const float x0 = (float)(signed char)(w & 0xff), y0 = (float)(signed char)((w >> 8) & 0xff);
+            const float x1 = (float)(signed char)((w >> 16) & 0xff), y1 = (float)(signed char)((w >> 24) & 0xff);
+            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa))), iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa))), iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+            const int t0 = ctr[iy0 * pitch + ix0], t1 = ctr[iy1 * pitch + ix1];
+            gval |= (t0 < t1) << bit;
+        }
+        out_desc[((size_t)f * capacity + i) * 32 + lane] = (uint8_t)gval;
+        return;
+    }
     const int4* pp = reinterpret_cast<const int4*>(b.pattern + bin * 1024 + lane * 32);
     const int4 pa = __ldg(pp), pb = __ldg(pp + 1);
     const int w8[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
@@ -1151,8 +1177,7 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     MAGE_REQUIRE(width >= 16 && height >= 16 && max_batch >= 1, MAGE_ERR_INVALID, "mage_orb_create: bad size %dx%d batch %d", width, height, max_batch);
     MAGE_REQUIRE((size_t)width * height < (1u << 24), MAGE_ERR_UNSUPPORTED, "image larger than 2^24 pixels");
     MAGE_REQUIRE(p->patch_size >= 2, MAGE_ERR_INVALID, "patch_size must be >= 2 (CV_Assert in the reference)");
-    MAGE_REQUIRE(p->patch_size == 31 || p->patch_size == 15, MAGE_ERR_UNSUPPORTED,
-                 "patch_size %u: only the pre-rotated tables (31, 15) are built; the generic path needs cv::RNG", p->patch_size);
+    MAGE_REQUIRE(p->patch_size <= 127, MAGE_ERR_UNSUPPORTED, "patch_size %u: at most 127", p->patch_size);
     MAGE_REQUIRE(p->nlevels >= 1 && p->nlevels <= (unsigned)kMaxLevels, MAGE_ERR_UNSUPPORTED, "nlevels must be 1..%d", kMaxLevels);
     MAGE_REQUIRE(p->gaussian_kernel_size <= 1 || gauss_kernel_q8((int)p->gaussian_kernel_size), MAGE_ERR_UNSUPPORTED,
                  "gaussian_kernel_size %u unsupported (odd 3..15)", p->gaussian_kernel_size);
@@ -1172,6 +1197,7 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     g.nlevels = (int)p->nlevels; g.width = width; g.height = height;
     g.fast_threshold = (int)p->fast_threshold; g.patch = (int)p->patch_size; g.half_patch = g.patch / 2;
     g.use_orientation = p->use_orientation ? 1 : 0;
+    g.generic_pattern = (g.patch != 31 && g.patch != 15) ? 1 : 0;              // ref :866-885
     g.border = g.use_orientation ? cvCeilF(g.half_patch * std::sqrt(2.0f)) : g.half_patch;        // ref :712
     g.ksize = p->gaussian_kernel_size > 1 ? (int)p->gaussian_kernel_size : 1;
     g.strong_response = p->strong_response; g.num_cells_x = p->num_cells_x; g.num_cells_y = p->num_cells_y;
@@ -1262,6 +1288,14 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
         resize_axis(g.lv[l - 1].h, g.lv[l].h, &tofs[g.lv[l].tab_y], &tcoef[g.lv[l].tab_y]);
     }
     std::vector<int8_t> pat(30 * 1024);
+    if (g.generic_pattern) {
+        // ref :551-560 MakeRandomPattern: cv::RNG(0x34985739) -- multiply-with-carry, next() = (unsigned)(state = (unsigned)state *
+        // 4164903690 + (state >> 32)); uniform(a, b) = next() % (b - a) + a -- x then y for each of the 512 points
+        uint64_t state = 0x34985739u;
+        auto next = [&]() { state = (uint64_t)(uint32_t)state * 4164903690u + (uint32_t)(state >> 32); return (uint32_t)state; };
+        const int lo = -g.patch / 2, hi = g.patch / 2 + 1;
+        for (int i = 0; i < 1024; i++) pat[i] = (int8_t)(int)(next() % (uint32_t)(hi - lo) + lo);
+    } else
     {   // rows 1..29 = row 0 rotated by 12r degrees, float32, round-half-even
         const signed char* base = g.patch == 31 ? kBriefBase31 : kBriefBase15;
         for (int r = 0; r < 30; r++) {

@@ -493,6 +493,22 @@ void selectLevel(const orc_orb_params& p, std::vector<orc_keypoint>& kps, int nK
 
 // ---- pattern ------------------------------------------------------------------------------------------------------
 // rows 1..29 = row 0 rotated by 12r degrees in float32 with round-half-even.
+// ref :551-560 MakeRandomPattern: cv::RNG(0x34985739), x then y, each rng.uniform(-patchSize / 2, patchSize / 2 + 1).
+// cv::RNG is OpenCV's multiply-with-carry generator (core.hpp / operations.hpp, unchanged since 2.x):
+//   next(): state = (uint64)(unsigned)state * 4164903690U + (unsigned)(state >> 32); return (unsigned)state
+//   uniform(int a, int b) = a == b ? a : (int)(next() % (b - a) + a)
+// Pinned through stock cv::ORB, which builds the same pattern for patchSize != 31 (tests/test_oracle_vs_cv2.py).
+void makeRandomPattern(int patchSize, int* xy, int npoints)
+{
+    uint64_t state = 0x34985739u;
+    auto next = [&]() { state = (uint64_t)(uint32_t)state * 4164903690u + (uint32_t)(state >> 32); return (uint32_t)state; };
+    const int lo = -patchSize / 2, hi = patchSize / 2 + 1;
+    for (int i = 0; i < npoints; i++) {
+        xy[2 * i] = lo == hi ? lo : (int)(next() % (uint32_t)(hi - lo) + lo);
+        xy[2 * i + 1] = lo == hi ? lo : (int)(next() % (uint32_t)(hi - lo) + lo);
+    }
+}
+
 int briefPattern(int patch, int8_t* out)
 {
     const signed char* base = patch == 31 ? kBriefBase31 : patch == 15 ? kBriefBase15 : nullptr;
@@ -587,6 +603,30 @@ int orc_anms_radii(const orc_orb_params* p, const orc_keypoint* kps, int n_in, i
 }
 
 int orc_brief_pattern(int patch_size, int8_t* out) { return briefPattern(patch_size, out); }
+void orc_random_pattern(int patch_size, int* xy, int npoints) { makeRandomPattern(patch_size, xy, npoints); }
+/* ComputeOrbDescriptors (ref :452-492) on ONE already blurred level with scale 1: x, y = integer pixel centres, angle in degrees */
+void orc_generic_descriptors(const uint8_t* img, int stride, const float* xya, int n, int patch_size, uint8_t* desc)
+{
+    std::vector<int> pat(1024);
+    makeRandomPattern(patch_size, pat.data(), 512);
+    for (int j = 0; j < n; j++) {
+        float angle = xya[3 * j + 2];
+        angle *= (float)(3.1415926535897932384626433832795 / 180.0f);
+        const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+        const uint8_t* center = img + (size_t)cvRoundF(xya[3 * j + 1]) * stride + cvRoundF(xya[3 * j]);
+        const int* pp = pat.data();
+        auto value = [&](int idx) {
+            const float px = (float)pp[2 * idx], py = (float)pp[2 * idx + 1];
+            const float x = px * a - py * b, y = px * b + py * a;
+            return (int)center[cvRoundF(y) * stride + cvRoundF(x)];
+        };
+        for (int i = 0; i < 32; ++i, pp += 32) {
+            int val = 0;
+            for (int bit = 0; bit < 8; bit++) val |= (value(2 * bit) < value(2 * bit + 1)) << bit;
+            desc[32 * j + i] = (uint8_t)val;
+        }
+    }
+}
 
 int orc_umax(int half_patch, int* umax)
 {
@@ -603,7 +643,7 @@ int orc_orb_detect_and_compute(const orc_orb_params* pp, const uint8_t* img, int
     const orc_orb_params& p = *pp;
     *count = 0;
     if (p.patch_size < 2 || p.nlevels < 1) return -1;                       // CV_Assert(m_patchSize >= 2)
-    if (p.patch_size != 31 && p.patch_size != 15) return -2;                // generic path needs cv::RNG
+    if (p.patch_size > 255) return -2;                                      // pattern coordinates are kept in 8 bits on the device
     if (p.gaussian_kernel_size > 1 && !gaussKernelQ8((int)p.gaussian_kernel_size)) return -3;
 
     Levels L = levelLayout(p, w, h);
@@ -682,6 +722,35 @@ int orc_orb_detect_and_compute(const orc_orb_params* pp, const uint8_t* img, int
         }
     }
 
+    // ---- descriptors: generic pattern (ref :452-492) for patch sizes without a pre-rotated table (ref :878-885)
+    if (patchSize != 31 && patchSize != 15) {
+        std::vector<int> pat(1024);
+        makeRandomPattern(patchSize, pat.data(), 512);
+        for (size_t j = 0; j < all.size(); j++) {
+            const orc_keypoint& k = all[j];
+            const int lw = L.w[k.octave];
+            float scale = 1.f / L.scale[k.octave];
+            float angle = k.angle;
+            angle *= (float)(3.1415926535897932384626433832795 / 180.0f);          // (float)(CV_PI / HALF_CIRCLE_DEGREES<float>)
+            const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+            const uint8_t* center = ptrs[k.octave] + (size_t)cvRoundF(k.y * scale) * lw + cvRoundF(k.x * scale);
+            uint8_t* d = desc + j * 32;
+            const int* pp = pat.data();
+            auto value = [&](int idx) {
+                const float px = (float)pp[2 * idx], py = (float)pp[2 * idx + 1];
+                const float x = px * a - py * b, y = px * b + py * a;                 // float32, products rounded separately
+                return (int)center[cvRoundF(y) * lw + cvRoundF(x)];
+            };
+            for (int i = 0; i < 32; ++i, pp += 32) {
+                int val = 0;
+                for (int bit = 0; bit < 8; bit++) val |= (value(2 * bit) < value(2 * bit + 1)) << bit;
+                d[i] = (uint8_t)val;
+            }
+        }
+        std::copy(all.begin(), all.end(), kps);
+        *count = (int)all.size();
+        return 0;
+    }
     // ---- descriptors (ref :502-549)
     std::vector<int8_t> pattern(30 * 1024);
     briefPattern(patchSize, pattern.data());

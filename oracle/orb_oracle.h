@@ -57,6 +57,9 @@ int   orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int sstride, uint8_
 /* cv::GaussianBlur of a SUBMATRIX source (generic separable float path); fused = every multiply-add as one FMA */
 int   orc_gaussian_blur_submatrix_u8(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, int dstride, int ksize, int fused);
 float orc_fast_atan2(float y, float x);
+/* MakeRandomPattern (ref OpenCVModified.cpp:551-560): npoints (x, y) pairs from cv::RNG(0x34985739) */
+void  orc_random_pattern(int patch_size, int* xy, int npoints);
+void  orc_generic_descriptors(const uint8_t* img, int stride, const float* xya, int n, int patch_size, uint8_t* desc);
 int   orc_cv_round_f(float v);
 /* FAST-9/16 + score + 3x3 NMS in raster order; returns number found (may exceed capacity; only capacity written) */
 int   orc_fast9_nms(const uint8_t* img, int w, int h, int stride, int threshold, orc_keypoint* out, int capacity);

@@ -140,6 +140,21 @@ def brief_pattern(patch):
     return out.reshape(30, 256, 4)
 
 
+def random_pattern(patch):
+    out = np.zeros(1024, np.int32)
+    lib().orc_random_pattern(int(patch), out.ctypes.data_as(C.c_void_p), 512)
+    return out.reshape(512, 2)
+
+
+def generic_descriptors(img, xya, patch):
+    """ComputeOrbDescriptors (generic pattern) on one blurred level: xya = float32 [n, 3] (x, y, angle in degrees)"""
+    img, sp = _u8(img)
+    xya = np.ascontiguousarray(xya, np.float32)
+    desc = np.zeros((len(xya), 32), np.uint8)
+    lib().orc_generic_descriptors(sp, img.strides[0], xya.ctypes.data_as(C.c_void_p), len(xya), int(patch), desc.ctypes.data_as(C.c_void_p))
+    return desc
+
+
 def umax(half_patch):
     out = np.zeros(half_patch + 2, np.int32)
     lib().orc_umax(int(half_patch), out.ctypes.data_as(C.c_void_p))

@@ -162,3 +162,24 @@ def test_descriptor_distance_is_popcount():
         a = rng.integers(0, 256, 32, dtype=np.uint8); b = rng.integers(0, 256, 32, dtype=np.uint8)
         assert orc.descriptor_distance(a, b) == int(np.unpackbits(a ^ b).sum())
         assert orc.descriptor_distance(a, b) == int(cv2.norm(a, b, cv2.NORM_HAMMING))
+
+
+@pytest.mark.parametrize("patch", [19, 25, 36])
+def test_generic_pattern_and_rotation_match_stock_orb(patch):
+    """A15: MakeRandomPattern (cv::RNG restated) + the float32 rotation / cvRound of ComputeOrbDescriptors against stock cv::ORB, which
+    builds the same pattern for patchSize != 31 and samples it the same way. Ramp images (value = x, value = y) make the blur the
+    identity, so every descriptor bit is an ordering of two rotated, rounded pattern coordinates: 2 x 200 random angles x 256 tests."""
+    rng = np.random.default_rng(patch)
+    H, W = 160, 230
+    ramps = {"x": np.tile(np.arange(W, dtype=np.uint8), (H, 1)), "y": np.tile(np.arange(H, dtype=np.uint8)[:, None], (1, W))}
+    orb = cv2.ORB_create(nfeatures=500, scaleFactor=1.2, nlevels=1, edgeThreshold=patch, firstLevel=0, WTA_K=2, patchSize=patch, fastThreshold=10)
+    m = patch + 6
+    xya = np.stack([rng.integers(m, W - m, 200), rng.integers(m, H - m, 200), rng.uniform(0, 360, 200)], 1).astype(np.float32)
+    kps = [cv2.KeyPoint(float(x), float(y), float(patch), float(a), 1.0, 0, -1) for x, y, a in xya]
+    for name, img in ramps.items():
+        kk, desc = orb.compute(img, kps)
+        assert len(kk) == len(kps)
+        assert np.array_equal(orc.blur_submatrix(img, 7)[8:-8, 8:-8], img[8:-8, 8:-8])         # the blur is the identity on a ramp
+        assert np.array_equal(orc.generic_descriptors(img, xya, patch), desc), (patch, name)
+    pat = orc.random_pattern(patch)
+    assert pat.min() == -(patch // 2) and pat.max() == patch // 2

@@ -177,11 +177,24 @@ def test_device_resident_variant_equals_host_variant(frames):
 
 def test_unsupported_configurations_are_rejected():
     from mageslam_b200._lib import MageError
-    p = orc.tier_params(); p.patch_size = 21            # generic pattern path needs cv::RNG
+    p = orc.tier_params(); p.patch_size = 129           # pattern coordinates are kept in 8 bits
     with pytest.raises(MageError):
         make_detector(p).DetectAndCompute(np.zeros((480, 640), np.uint8))
     with pytest.raises(TypeError):                       # CV_Assert(type == CV_8UC1)
         make_detector(orc.tier_params()).DetectAndCompute(np.zeros((480, 640), np.float32))
+
+
+@pytest.mark.parametrize("patch,orient,nlevels", [(25, True, 4), (19, True, 3), (36, True, 2), (21, False, 3), (9, True, 1)])
+def test_generic_pattern_patch_sizes(patch, orient, nlevels):
+    """A15: patch sizes without a pre-rotated table -- cv::RNG pattern, runtime float32 rotation (ref :452-492, :551-560, :878-885)"""
+    p = orc.tier_params(nfeatures=600, nlevels=nlevels)
+    p.patch_size = patch; p.use_orientation = 1 if orient else 0
+    det = make_detector(p)
+    for img in synth.video_frames(2, 400, 300, seed=patch):
+        gk, gd = det.DetectAndCompute(img)
+        ok, od = orc.detect_and_compute(p, img, 1)
+        assert len(ok) > 100
+        assert_same_features(gk, gd, ok, od, "patch %d" % patch)
 
 
 def test_orb_feature_detector_process(frames):
