@@ -247,6 +247,14 @@ int  mage_frontend_capacity(mage_frontend_t f);              /* features per fra
 /* Host buffers (pinned for overlap), synchronous: kps/desc/matches are [n][capacity] arrays, counts/match_counts [n]. */
 int  mage_frontend_process(mage_frontend_t f, const uint8_t* images, int n, int stride, size_t frame_stride,
                            mage_keypoint* kps, uint8_t* desc, int* counts, mage_dmatch* matches, int* match_counts);
+/* Pipelined form of mage_frontend_process for a continuous stream: _submit enqueues upload -> compute -> download of one call and
+ * returns; _wait blocks until the OLDEST submitted call has delivered its results into the host buffers given to its _submit. Two
+ * calls may be in flight (frames are staged in two device buffers), so the upload of call j+1 and the download of call j-1 run under
+ * the compute of call j. The host buffers of a call must stay valid (and, for overlap, pinned) until its _wait returns.
+ * mage_frontend_process == _submit + _wait. */
+int  mage_frontend_submit(mage_frontend_t f, const uint8_t* images, int n, int stride, size_t frame_stride,
+                          mage_keypoint* kps, uint8_t* desc, int* counts, mage_dmatch* matches, int* match_counts);
+int  mage_frontend_wait(mage_frontend_t f);
 /* Device-resident frames, results stay in the handle's device buffers (mage_frontend_device_buffers). Asynchronous. */
 int  mage_frontend_process_device(mage_frontend_t f, const uint8_t* d_images, int n, int stride, size_t frame_stride,
                                   void* cuda_stream);

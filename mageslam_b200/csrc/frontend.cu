@@ -16,7 +16,9 @@ struct mage_frontend_s {
     mage_orb_t orb = nullptr;
     mage_matcher_t matcher = nullptr;
     int width = 0, height = 0, pitch = 0, batch = 0, chunk = 0, cap = 0, max_hamming = 30, min_diff = 1;
-    // device slots: slot 0 = last frame of the previous call, slots 1..batch = frames of this call
+    // device slots: slot 0 = last frame of the previous call, slots 1..batch = frames of an even call, batch+1..2*batch = of an odd call
+    // (two result sets, so the compute of call j+1 never waits for the download of call j)
+    int cur = 0;                                   // result set of the most recent call
     uint8_t* d_images = nullptr;
     mage_keypoint* d_kps = nullptr;
     uint8_t* d_desc = nullptr;
@@ -24,7 +26,11 @@ struct mage_frontend_s {
     mage_dmatch* d_matches = nullptr;
     int* d_match_counts = nullptr;
     cudaStream_t s_copy = nullptr, s_compute = nullptr, s_out = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_done;
+    // two calls can be in flight (mage_frontend_submit / _wait): call j stages its frames in image buffer j % 2; per chunk,
+    // ev_in = uploaded, ev_done = computed, ev_out = results delivered to the caller's host buffers
+    struct Flight { std::vector<cudaEvent_t> ev_in, ev_done, ev_out; int nch = 0; bool pending = false; };
+    Flight flight[2];
+    long long submitted = 0, waited = 0;
     cudaEvent_t ev_prev = nullptr;
     std::vector<int> a_idx, b_idx;
     bool has_prev = false;
@@ -45,32 +51,39 @@ extern "C" int mage_frontend_create(const mage_orb_params* p, int width, int hei
     mage_orb_level_info(f->orb, nullptr, nullptr, nullptr, nf);
     for (unsigned l = 0; l < p->nlevels; l++) sum += nf[l];
     f->cap = std::max((int)p->nfeatures, sum);
-    rc = mage_matcher_create(std::min(f->cap, 65535), batch, &f->matcher);
+    rc = mage_matcher_create(std::min(f->cap, 65535), 2 * batch, &f->matcher);
     if (rc != MAGE_OK) { mage_frontend_destroy(f); return rc; }
-    const size_t B1 = (size_t)batch + 1;
+    const size_t B1 = 2 * (size_t)batch + 1;
     f->pitch = (int)align_up((size_t)width, 16);          // staging rows: 16-byte aligned so every frame base is too
-    cudaError_t e = cudaMalloc(&f->d_images, (size_t)f->pitch * height * batch);
+    cudaError_t e = cudaMalloc(&f->d_images, (size_t)f->pitch * height * batch * 2);       // double-buffered staging
     if (e == cudaSuccess) e = cudaMalloc(&f->d_kps, sizeof(mage_keypoint) * f->cap * B1);
     if (e == cudaSuccess) e = cudaMalloc(&f->d_desc, (size_t)32 * f->cap * B1);
     if (e == cudaSuccess) e = cudaMalloc(&f->d_counts, sizeof(int) * B1);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_matches, sizeof(mage_dmatch) * f->cap * (size_t)batch);
-    if (e == cudaSuccess) e = cudaMalloc(&f->d_match_counts, sizeof(int) * batch);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_matches, sizeof(mage_dmatch) * f->cap * (size_t)batch * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&f->d_match_counts, sizeof(int) * batch * 2);
     if (e == cudaSuccess) e = cudaMemset(f->d_counts, 0, sizeof(int) * B1);
-    if (e == cudaSuccess) e = cudaMemset(f->d_match_counts, 0, sizeof(int) * batch);
+    if (e == cudaSuccess) e = cudaMemset(f->d_match_counts, 0, sizeof(int) * batch * 2);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking);
     const int nchunks = div_up(batch, chunk);
-    f->ev_in.resize(nchunks); f->ev_done.resize(nchunks);
-    for (int i = 0; i < nchunks && e == cudaSuccess; i++) {
-        e = cudaEventCreateWithFlags(&f->ev_in[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_done[i], cudaEventDisableTiming);
+    for (auto& fl : f->flight) {
+        fl.ev_in.assign(nchunks, nullptr); fl.ev_done.assign(nchunks, nullptr); fl.ev_out.assign(nchunks, nullptr);
+        for (int i = 0; i < nchunks && e == cudaSuccess; i++) {
+            e = cudaEventCreateWithFlags(&fl.ev_in[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fl.ev_done[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fl.ev_out[i], cudaEventDisableTiming);
+        }
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_prev, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("mage_frontend_create: %s", cudaGetErrorString(e)); mage_frontend_destroy(f); return MAGE_ERR_CUDA; }
-    f->a_idx.resize(batch); f->b_idx.resize(batch);
-    for (int i = 0; i < batch; i++) { f->a_idx[i] = i + 1; f->b_idx[i] = i; }       // frame i (query) vs frame i-1 (train)
-    rc = mage_matcher_set_jobs_device(f->matcher, f->d_desc, f->d_counts, (size_t)32 * f->cap, f->a_idx.data(), f->b_idx.data(), batch);
+    f->a_idx.resize(2 * batch); f->b_idx.resize(2 * batch);
+    for (int s = 0; s < 2; s++)
+        for (int i = 0; i < batch; i++) {                                               // frame i (query) vs frame i-1 (train); slot 0 precedes frame 0
+            f->a_idx[s * batch + i] = s * batch + i + 1;
+            f->b_idx[s * batch + i] = i == 0 ? 0 : s * batch + i;
+        }
+    rc = mage_matcher_set_jobs_device(f->matcher, f->d_desc, f->d_counts, (size_t)32 * f->cap, f->a_idx.data(), f->b_idx.data(), 2 * batch);
     if (rc != MAGE_OK) { mage_frontend_destroy(f); return rc; }
     *out = f;
     return MAGE_OK;
@@ -83,8 +96,11 @@ extern "C" void mage_frontend_destroy(mage_frontend_s* f)
     if (f->orb) mage_orb_destroy(f->orb);
     if (f->matcher) mage_matcher_destroy(f->matcher);
     cudaFree(f->d_images); cudaFree(f->d_kps); cudaFree(f->d_desc); cudaFree(f->d_counts); cudaFree(f->d_matches); cudaFree(f->d_match_counts);
-    for (auto e : f->ev_in) if (e) cudaEventDestroy(e);
-    for (auto e : f->ev_done) if (e) cudaEventDestroy(e);
+    for (auto& fl : f->flight) {
+        for (auto e : fl.ev_in) if (e) cudaEventDestroy(e);
+        for (auto e : fl.ev_done) if (e) cudaEventDestroy(e);
+        for (auto e : fl.ev_out) if (e) cudaEventDestroy(e);
+    }
     if (f->ev_prev) cudaEventDestroy(f->ev_prev);
     if (f->s_copy) cudaStreamDestroy(f->s_copy);
     if (f->s_compute) cudaStreamDestroy(f->s_compute);
@@ -99,27 +115,32 @@ extern "C" int mage_frontend_reset(mage_frontend_s* f)
     MAGE_CUDA_TRY(cudaDeviceSynchronize());
     MAGE_CUDA_TRY(cudaMemset(f->d_counts, 0, sizeof(int)));
     f->has_prev = false;
+    for (auto& fl : f->flight) fl.pending = false;
+    f->waited = f->submitted;
     return MAGE_OK;
 }
 
 // extract + match of frames [c0, c1) whose pixels are at d_img (frame stride fs, row stride st), on stream s
-static int frontend_compute(mage_frontend_s* f, const uint8_t* d_img, int st, size_t fs, int c0, int c1, cudaStream_t s)
+static int frontend_compute(mage_frontend_s* f, int set, const uint8_t* d_img, int st, size_t fs, int c0, int c1, cudaStream_t s)
 {
     const size_t cap = (size_t)f->cap;
-    int rc = mage_orb_extract_device(f->orb, d_img, c1 - c0, f->width, f->height, st, fs, f->d_kps + cap * (c0 + 1), f->d_desc + 32 * cap * (c0 + 1),
-                                     f->cap, f->d_counts + c0 + 1, s);
+    const int base = set * f->batch;               // first result slot (minus one) and first match job of this result set
+    int rc = mage_orb_extract_device(f->orb, d_img, c1 - c0, f->width, f->height, st, fs, f->d_kps + cap * (base + c0 + 1),
+                                     f->d_desc + 32 * cap * (base + c0 + 1), f->cap, f->d_counts + base + c0 + 1, s);
     if (rc != MAGE_OK) return rc;
-    return mage_match_run_jobs(f->matcher, c0, c1 - c0, f->max_hamming, f->min_diff, f->d_matches + cap * c0, f->cap, f->d_match_counts + c0, s);
+    return mage_match_run_jobs(f->matcher, base + c0, c1 - c0, f->max_hamming, f->min_diff, f->d_matches + cap * (base + c0), f->cap,
+                               f->d_match_counts + base + c0, s);
 }
 
 // keep the last frame of this call as "previous" for the next one
-static int frontend_roll(mage_frontend_s* f, int n, cudaStream_t s)
+static int frontend_roll(mage_frontend_s* f, int set, int n, cudaStream_t s)
 {
-    const size_t cap = (size_t)f->cap;
-    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_desc, f->d_desc + 32 * cap * n, 32 * cap, cudaMemcpyDeviceToDevice, s));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_kps, f->d_kps + cap * n, sizeof(mage_keypoint) * cap, cudaMemcpyDeviceToDevice, s));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_counts, f->d_counts + n, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    const size_t cap = (size_t)f->cap, last = (size_t)set * f->batch + n;
+    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_desc, f->d_desc + 32 * cap * last, 32 * cap, cudaMemcpyDeviceToDevice, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_kps, f->d_kps + cap * last, sizeof(mage_keypoint) * cap, cudaMemcpyDeviceToDevice, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_counts, f->d_counts + last, sizeof(int), cudaMemcpyDeviceToDevice, s));
     f->has_prev = true;
+    f->cur = set;
     return MAGE_OK;
 }
 
@@ -129,19 +150,85 @@ extern "C" int mage_frontend_process_device(mage_frontend_s* f, const uint8_t* d
     cudaStream_t s = (cudaStream_t)stream;       // NULL = the default stream, like any CUDA API
     for (int c0 = 0; c0 < n; c0 += f->chunk) {
         int c1 = std::min(n, c0 + f->chunk);
-        int rc = frontend_compute(f, d_images + (size_t)c0 * frame_stride, stride, frame_stride, c0, c1, s);
+        int rc = frontend_compute(f, 0, d_images + (size_t)c0 * frame_stride, stride, frame_stride, c0, c1, s);
         if (rc != MAGE_OK) return rc;
     }
-    return frontend_roll(f, n, s);
+    return frontend_roll(f, 0, n, s);
 }
 
 extern "C" int mage_frontend_device_buffers(mage_frontend_s* f, mage_keypoint** d_kps, uint8_t** d_desc, int** d_counts, mage_dmatch** d_matches,
                                             int** d_match_counts, int* capacity)
 {
     MAGE_REQUIRE(f, MAGE_ERR_INVALID, "null handle");
-    const size_t cap = (size_t)f->cap;
-    if (d_kps) *d_kps = f->d_kps + cap; if (d_desc) *d_desc = f->d_desc + 32 * cap; if (d_counts) *d_counts = f->d_counts + 1;
-    if (d_matches) *d_matches = f->d_matches; if (d_match_counts) *d_match_counts = f->d_match_counts; if (capacity) *capacity = f->cap;
+    const size_t cap = (size_t)f->cap, base = (size_t)f->cur * f->batch;            // the result set of the most recent call
+    if (d_kps) *d_kps = f->d_kps + cap * (base + 1); if (d_desc) *d_desc = f->d_desc + 32 * cap * (base + 1); if (d_counts) *d_counts = f->d_counts + base + 1;
+    if (d_matches) *d_matches = f->d_matches + cap * base; if (d_match_counts) *d_match_counts = f->d_match_counts + base; if (capacity) *capacity = f->cap;
+    return MAGE_OK;
+}
+
+// Asynchronous host variant: enqueue upload -> compute -> download of one call and return. Call j uses staging buffer j % 2, so
+// its upload overlaps the compute of call j-1 and the download of call j-1 overlaps its compute; the hazards are per chunk:
+//   upload(j, k)  waits for compute(j-2, k)  (same staging buffer)
+//   compute(j, k) waits for download(j-2, k) (same device result set; there are two)
+static int frontend_submit(mage_frontend_s* f, const uint8_t* images, int n, int stride, size_t frame_stride, mage_keypoint* kps,
+                           uint8_t* desc, int* counts, mage_dmatch* matches, int* match_counts)
+{
+    const size_t cap = (size_t)f->cap, W = (size_t)f->width, H = (size_t)f->height, PT = (size_t)f->pitch;
+    const int nch = div_up(n, f->chunk);
+    const int b = (int)(f->submitted & 1);
+    mage_frontend_s::Flight& me = f->flight[b];
+    uint8_t* stage = f->d_images + PT * H * (size_t)f->batch * b;
+    for (int k = 0; k < nch; k++) {
+        const int c0 = k * f->chunk, c1 = std::min(n, c0 + f->chunk);
+        if (me.pending && k < me.nch) MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_copy, me.ev_done[k], 0));            // call j-2 read this chunk's frames
+        if ((size_t)stride == PT && frame_stride == PT * H)
+            MAGE_CUDA_TRY(cudaMemcpyAsync(stage + PT * H * c0, images + frame_stride * c0, PT * H * (c1 - c0), cudaMemcpyHostToDevice, f->s_copy));
+        else
+            for (int i = c0; i < c1; i++)
+                MAGE_CUDA_TRY(cudaMemcpy2DAsync(stage + PT * H * i, PT, images + frame_stride * i, stride, W, H, cudaMemcpyHostToDevice, f->s_copy));
+        MAGE_CUDA_TRY(cudaEventRecord(me.ev_in[k], f->s_copy));
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, me.ev_in[k], 0));
+        if (me.pending) {                                                                                           // call j-2 delivered from this result set
+            const int ko = std::min(k, me.nch - 1);
+            MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, me.ev_out[ko], 0));
+            if (k == nch - 1) for (int q = ko + 1; q < me.nch; q++) MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, me.ev_out[q], 0));
+        }
+        int rc = frontend_compute(f, b, stage + PT * H * c0, f->pitch, PT * H, c0, c1, f->s_compute);
+        if (rc != MAGE_OK) return rc;
+        MAGE_CUDA_TRY(cudaEventRecord(me.ev_done[k], f->s_compute));
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_out, me.ev_done[k], 0));
+        const int m = c1 - c0;
+        const size_t r0 = (size_t)b * f->batch + c0;                      // first result slot (minus one) of the chunk
+        MAGE_CUDA_TRY(cudaMemcpyAsync(kps + cap * c0, f->d_kps + cap * (r0 + 1), sizeof(mage_keypoint) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(desc + 32 * cap * c0, f->d_desc + 32 * cap * (r0 + 1), 32 * cap * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(matches + cap * c0, f->d_matches + cap * r0, sizeof(mage_dmatch) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(counts + c0, f->d_counts + r0 + 1, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(match_counts + c0, f->d_match_counts + r0, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaEventRecord(me.ev_out[k], f->s_out));
+    }
+    me.nch = nch; me.pending = true;
+    f->submitted++;
+    return frontend_roll(f, b, n, f->s_compute);
+}
+
+extern "C" int mage_frontend_submit(mage_frontend_s* f, const uint8_t* images, int n, int stride, size_t frame_stride, mage_keypoint* kps,
+                                    uint8_t* desc, int* counts, mage_dmatch* matches, int* match_counts)
+{
+    MAGE_REQUIRE(f && images && kps && desc && counts && matches && match_counts && n >= 1 && n <= f->batch, MAGE_ERR_INVALID,
+                 "mage_frontend_submit: bad argument");
+    MAGE_REQUIRE(stride >= f->width, MAGE_ERR_INVALID, "stride smaller than width");
+    MAGE_REQUIRE(f->submitted - f->waited < 2, MAGE_ERR_INVALID, "two calls are already in flight: mage_frontend_wait first");
+    return frontend_submit(f, images, n, stride, frame_stride, kps, desc, counts, matches, match_counts);
+}
+
+extern "C" int mage_frontend_wait(mage_frontend_s* f)
+{
+    MAGE_REQUIRE(f, MAGE_ERR_INVALID, "null handle");
+    MAGE_REQUIRE(f->submitted > f->waited, MAGE_ERR_INVALID, "mage_frontend_wait: nothing in flight");
+    mage_frontend_s::Flight& fl = f->flight[(int)(f->waited & 1)];
+    MAGE_CUDA_TRY(cudaEventSynchronize(fl.ev_out[fl.nch - 1]));          // downloads of a call are enqueued in chunk order on one stream
+    f->waited++;
+    if (f->submitted == f->waited) MAGE_CUDA_TRY(cudaStreamSynchronize(f->s_compute));      // nothing left in flight: the roll copy too
     return MAGE_OK;
 }
 
@@ -151,34 +238,10 @@ extern "C" int mage_frontend_process(mage_frontend_s* f, const uint8_t* images, 
     MAGE_REQUIRE(f && images && kps && desc && counts && matches && match_counts && n >= 1 && n <= f->batch, MAGE_ERR_INVALID,
                  "mage_frontend_process: bad argument");
     MAGE_REQUIRE(stride >= f->width, MAGE_ERR_INVALID, "stride smaller than width");
-    const size_t cap = (size_t)f->cap, W = (size_t)f->width, H = (size_t)f->height, PT = (size_t)f->pitch;
-    const int nch = div_up(n, f->chunk);
-    // uploads of the next call must not overwrite frames still being read: the previous call ended with a full sync
-    for (int k = 0; k < nch; k++) {
-        const int c0 = k * f->chunk, c1 = std::min(n, c0 + f->chunk);
-        if ((size_t)stride == PT && frame_stride == PT * H)
-            MAGE_CUDA_TRY(cudaMemcpyAsync(f->d_images + PT * H * c0, images + frame_stride * c0, PT * H * (c1 - c0), cudaMemcpyHostToDevice, f->s_copy));
-        else
-            for (int i = c0; i < c1; i++)
-                MAGE_CUDA_TRY(cudaMemcpy2DAsync(f->d_images + PT * H * i, PT, images + frame_stride * i, stride, W, H, cudaMemcpyHostToDevice, f->s_copy));
-        MAGE_CUDA_TRY(cudaEventRecord(f->ev_in[k], f->s_copy));
-        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, f->ev_in[k], 0));
-        int rc = frontend_compute(f, f->d_images + PT * H * c0, f->pitch, PT * H, c0, c1, f->s_compute);
-        if (rc != MAGE_OK) return rc;
-        MAGE_CUDA_TRY(cudaEventRecord(f->ev_done[k], f->s_compute));
-        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_out, f->ev_done[k], 0));
-        const int m = c1 - c0;
-        MAGE_CUDA_TRY(cudaMemcpyAsync(kps + cap * c0, f->d_kps + cap * (c0 + 1), sizeof(mage_keypoint) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
-        MAGE_CUDA_TRY(cudaMemcpyAsync(desc + 32 * cap * c0, f->d_desc + 32 * cap * (c0 + 1), 32 * cap * m, cudaMemcpyDeviceToHost, f->s_out));
-        MAGE_CUDA_TRY(cudaMemcpyAsync(matches + cap * c0, f->d_matches + cap * c0, sizeof(mage_dmatch) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
-        MAGE_CUDA_TRY(cudaMemcpyAsync(counts + c0, f->d_counts + c0 + 1, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
-        MAGE_CUDA_TRY(cudaMemcpyAsync(match_counts + c0, f->d_match_counts + c0, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
-    }
-    int rc = frontend_roll(f, n, f->s_compute);
+    while (f->submitted > f->waited) { int rc = mage_frontend_wait(f); if (rc != MAGE_OK) return rc; }
+    int rc = frontend_submit(f, images, n, stride, frame_stride, kps, desc, counts, matches, match_counts);
     if (rc != MAGE_OK) return rc;
-    MAGE_CUDA_TRY(cudaStreamSynchronize(f->s_out));
-    MAGE_CUDA_TRY(cudaStreamSynchronize(f->s_compute));
-    return MAGE_OK;
+    return mage_frontend_wait(f);
 }
 
 extern "C" int mage_frontend_capacity(mage_frontend_s* f) { return f ? f->cap : 0; }

@@ -24,6 +24,8 @@ class FrontEnd:
         L.mage_frontend_reset.argtypes = [C.c_void_p]
         L.mage_frontend_capacity.argtypes = [C.c_void_p]
         L.mage_frontend_process.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t] + [C.c_void_p] * 5
+        L.mage_frontend_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t] + [C.c_void_p] * 5
+        L.mage_frontend_wait.argtypes = [C.c_void_p]
         L.mage_frontend_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
         L.mage_frontend_device_buffers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5 + [C.POINTER(C.c_int)]
         self.width, self.height, self.batch = int(width), int(height), int(batch)
@@ -72,6 +74,21 @@ class FrontEnd:
         kps = arr[0].reshape(self.batch, -1).view(KEYPOINT_DTYPE)
         matches = arr[3].reshape(self.batch, -1).view(DMATCH_DTYPE)
         return kps, arr[1], arr[2], matches, arr[4]
+
+    def Submit(self, images, outs):
+        """Asynchronous Process: enqueue one call (at most two in flight); its results are in `outs` after the matching Wait()."""
+        n = images.shape[0]
+        stride = images.stride(1) if hasattr(images, "stride") else images.strides[1]
+        fstride = images.stride(0) if hasattr(images, "stride") else images.strides[0]
+        check(lib().mage_frontend_submit(self._h, ptr(images), n, stride, fstride, *[ptr(o) for o in outs]))
+
+    def Wait(self):
+        """Blocks until the oldest submitted call has delivered its results."""
+        check(lib().mage_frontend_wait(self._h))
+
+    def views(self, outs):
+        arr = [o.numpy() if hasattr(o, "numpy") else o for o in outs]
+        return arr[0].reshape(self.batch, -1).view(KEYPOINT_DTYPE), arr[1], arr[2], arr[3].reshape(self.batch, -1).view(DMATCH_DTYPE), arr[4]
 
     def ProcessDevice(self, d_images, stream=None):
         """d_images: torch uint8 [n, h, w] on the device. Asynchronous; results via DeviceBuffers()."""

@@ -60,3 +60,35 @@ def test_reset_forgets_predecessor():
     fe.Reset()
     _, _, _, _, mc = fe.Process(vid[2:], outs)
     assert mc[0] == 0 and mc[1] > 0
+
+
+def test_pipelined_submit_wait_equals_synchronous_process():
+    """two calls in flight (upload of call j+1 and download of call j-1 under the compute of call j): same results as Process"""
+    import torch
+    s = FeatureExtractorSettings.tier(num_features=800, num_levels=5)
+    vid = torch.from_numpy(synth.video_frames(16, 640, 480, seed=6)).pin_memory()
+    sync = FrontEnd(s, 640, 480, batch=4, chunk=2)
+    so = sync.alloc_outputs()
+    want = []
+    for c in range(4):
+        want.append([np.copy(a) for a in sync.Process(vid[4 * c:4 * c + 4], so)])
+    pipe = FrontEnd(s, 640, 480, batch=4, chunk=2)
+    po = [pipe.alloc_outputs(), pipe.alloc_outputs()]
+    got = []
+    pipe.Submit(vid[0:4], po[0])
+    for c in range(1, 4):
+        pipe.Submit(vid[4 * c:4 * c + 4], po[c & 1])
+        pipe.Wait()
+        got.append([np.copy(a) for a in pipe.views(po[(c - 1) & 1])])
+    pipe.Wait()
+    got.append([np.copy(a) for a in pipe.views(po[1])])
+    with pytest.raises(Exception):
+        pipe.Wait()                                   # nothing in flight
+    for w, g in zip(want, got):
+        kps, desc, cnt, mt, mc = w
+        gk, gd, gc, gm, gmc = g
+        assert np.array_equal(cnt, gc) and np.array_equal(mc, gmc)
+        for i in range(4):
+            assert kps[i, :cnt[i]].tobytes() == gk[i, :cnt[i]].tobytes() and np.array_equal(desc[i, :cnt[i]], gd[i, :cnt[i]])
+            assert mt[i, :mc[i]].tobytes() == gm[i, :mc[i]].tobytes()
+    assert want[1][4][0] > 50                         # the first frame of a later call is matched against the previous call's last frame
