@@ -475,7 +475,7 @@ def bench_ba(args, world, rank, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 300; 20 for --impl reference, whose steps take ~0.5 s of CPU time)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="frames per step")
@@ -488,6 +488,8 @@ def main():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--ba-problems", type=int, default=296)
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.impl == "reference" else 300
     global W, H, METRIC, WORKLOAD
     if (args.width, args.height) != (W, H):
         WORKLOAD = WORKLOAD.replace("640x480", "%dx%d" % (args.width, args.height)); METRIC = "orb_extract_match_fps_%dx%d" % (args.width, args.height)

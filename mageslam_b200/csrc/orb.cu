@@ -13,6 +13,8 @@
 // sorted ANMS prefix) -- a conforming execution of the reference's std::nth_element calls.
 #include "common.cuh"
 
+#include <cuda.h>              // CUtensorMap + cuTensorMapEncodeTiled prototype (resolved at run time, libcuda is not linked)
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -270,49 +272,10 @@ __device__ __forceinline__ uint32_t fast_score_pair(const uint16_t* A, const uin
 constexpr int kFastScP = 64;                      // score row pitch in PAIR words (two u16 scores per word; 61 used + 3 zeroed)
 constexpr size_t kFastSmemBytes = 2 * (size_t)kFastPH * kFastP16 * sizeof(uint16_t) + (size_t)kFastSH * kFastScP * sizeof(uint32_t);
 
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+// scores -> strict 3x3 NMS -> border cull -> append, on a pixel tile already staged as u16 (A, As); shared by both FAST kernels
+__device__ __forceinline__ void fast_tile_compute(const OrbGeom& g, const OrbBuffers& b, const LevelGeom& L, int f, int l, int px0, int py0,
+                                                  uint16_t* A, uint16_t* As, uint32_t* sc, int& s_n, int& s_base)
 {
-    extern __shared__ __align__(16) uint8_t fast_smem[];
-    uint16_t* A = reinterpret_cast<uint16_t*>(fast_smem);
-    uint16_t* As = A + kFastPH * kFastP16;
-    uint32_t* sc = reinterpret_cast<uint32_t*>(As + kFastPH * kFastP16);       // [kFastSH][kFastScP], scores as u16 pairs
-    const int f = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].fast_tile_base) l++;
-    const LevelGeom& L = g.lv[l];
-    const int t = blockIdx.x - L.fast_tile_base;
-    const int tx = t % L.fast_tiles_x, ty = t / L.fast_tiles_x;
-    const int px0 = kFastOW * tx - 4, py0 = kFastOH * ty - 4;
-    int pitch;
-    const uint8_t* img = level_ptr(g, b, f, l, pitch);
-
-    // stage the pixel tile: 32-bit global loads (zero fill outside the image rows / pitch), all issued before the first use,
-    // then widened to u16 twice
-    constexpr int kStageIters = kFastPH * (kFastPW / 4) / 256;
-    static_assert(kStageIters * 256 == kFastPH * (kFastPW / 4), "pixel tile must be a whole number of 256-thread passes");
-    uint32_t pv[kStageIters];
-#pragma unroll
-    for (int it = 0; it < kStageIters; it++) {
-        const int i = it * 256 + threadIdx.x;
-        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
-        const int y = py0 + ry, x = px0 + rx;
-        pv[it] = 0;
-        if (y >= 0 && y < L.h && x >= 0 && x + 4 <= pitch) pv[it] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch + x));
-    }
-#pragma unroll
-    for (int it = 0; it < kStageIters; it++) {
-        const int i = it * 256 + threadIdx.x;
-        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
-        const uint32_t v = pv[it];
-        const uint32_t p01 = __byte_perm(v, 0, 0x4140), p23 = __byte_perm(v, 0, 0x4342), p12 = __byte_perm(v, 0, 0x4241);
-        uint16_t* a = A + ry * kFastP16 + rx;
-        uint16_t* as = As + ry * kFastP16 + rx;
-        *reinterpret_cast<uint32_t*>(a) = p01;
-        *reinterpret_cast<uint32_t*>(a + 2) = p23;
-        if (rx > 0) as[-1] = (uint16_t)(v & 0xff);               // As[x] = A[x + 1]
-        *reinterpret_cast<uint32_t*>(as) = p12;
-        as[2] = (uint16_t)(v >> 24);
-    }
     constexpr int kPairs = kFastSW / 2;                          // 61 pairs per score row
     for (int i = threadIdx.x; i < kFastSH * (kFastScP - kPairs); i += blockDim.x)      // the unused tail pairs read as 0
         sc[(i / (kFastScP - kPairs)) * kFastScP + kPairs + i % (kFastScP - kPairs)] = 0;
@@ -338,7 +301,6 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     // survivors are collected in shared memory (reusing the pixel tile) and appended with ONE global atomic per CTA:
     // a returning global atomic per warp iteration stalled the whole loop on L2 round trips (ncu: 41 % of samples)
     uint32_t* list = reinterpret_cast<uint32_t*>(A);            // <= 1920 survivors (strict NMS: one per 2x2 block)
-    __shared__ int s_n, s_base;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     // strict 3x3 non-maximum suppression, 4 pixels (two pair words) per thread iteration in packed u16x2 arithmetic: the
@@ -393,13 +355,149 @@ __global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g,
     }
     __syncthreads();
     const int n = s_n;
-    if (n == 0) return;
+    if (n == 0) return;        // uniform: s_n is shared
     if (threadIdx.x == 0) s_base = atomicAdd(b.cand_count + f * kMaxLevels + l, n);
     __syncthreads();
     uint32_t* cand = b.cand + (size_t)f * b.cand_stride + L.cand_off;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int slot = s_base + i;
         if (slot < (int)L.cand_cap) cand[slot] = list[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+{
+    extern __shared__ __align__(128) uint8_t fast_smem[];
+    uint16_t* A = reinterpret_cast<uint16_t*>(fast_smem);
+    uint16_t* As = A + kFastPH * kFastP16;
+    uint32_t* sc = reinterpret_cast<uint32_t*>(As + kFastPH * kFastP16);       // [kFastSH][kFastScP], scores as u16 pairs
+    const int f = blockIdx.y;
+    int l = 0;
+    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].fast_tile_base) l++;
+    const LevelGeom& L = g.lv[l];
+    const int t = blockIdx.x - L.fast_tile_base;
+    const int tx = t % L.fast_tiles_x, ty = t / L.fast_tiles_x;
+    const int px0 = kFastOW * tx - 4, py0 = kFastOH * ty - 4;
+    int pitch;
+    const uint8_t* img = level_ptr(g, b, f, l, pitch);
+
+    // stage the pixel tile: 32-bit global loads (zero fill outside the image rows / pitch), all issued before the first use,
+    // then widened to u16 twice
+    constexpr int kStageIters = kFastPH * (kFastPW / 4) / 256;
+    static_assert(kStageIters * 256 == kFastPH * (kFastPW / 4), "pixel tile must be a whole number of 256-thread passes");
+    uint32_t pv[kStageIters];
+#pragma unroll
+    for (int it = 0; it < kStageIters; it++) {
+        const int i = it * 256 + threadIdx.x;
+        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
+        const int y = py0 + ry, x = px0 + rx;
+        pv[it] = 0;
+        if (y >= 0 && y < L.h && x >= 0 && x + 4 <= pitch) pv[it] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch + x));
+    }
+#pragma unroll
+    for (int it = 0; it < kStageIters; it++) {
+        const int i = it * 256 + threadIdx.x;
+        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
+        const uint32_t v = pv[it];
+        const uint32_t p01 = __byte_perm(v, 0, 0x4140), p23 = __byte_perm(v, 0, 0x4342), p12 = __byte_perm(v, 0, 0x4241);
+        uint16_t* a = A + ry * kFastP16 + rx;
+        uint16_t* as = As + ry * kFastP16 + rx;
+        *reinterpret_cast<uint32_t*>(a) = p01;
+        *reinterpret_cast<uint32_t*>(a + 2) = p23;
+        if (rx > 0) as[-1] = (uint16_t)(v & 0xff);               // As[x] = A[x + 1]
+        *reinterpret_cast<uint32_t*>(as) = p12;
+        as[2] = (uint16_t)(v >> 24);
+    }
+    __shared__ int s_n, s_base;
+    fast_tile_compute(g, b, L, f, l, px0, py0, A, As, sc, s_n, s_base);
+}
+
+// TMA variant: a persistent CTA walks the (tile, frame) list; the pixel tile of the NEXT item is fetched by one
+// cp.async.bulk.tensor (3-D tensor map per level: x, y, frame; out-of-image bytes arrive as zeros, so there is no bounds logic)
+// into the other half of a double buffer while the current tile is scored -- the global-load latency and the staging barrier
+// bubbles of k_fast (ncu: 25 % of its stall samples) move under the min/max network. The innermost TMA coordinate must be a
+// multiple of 16 bytes (measured on B200: any other start raises an illegal-instruction fault, tools/tma_probe2.cu) while the tile
+// origin is 120 tx - 4, so the box is 16 bytes wider (144 x 72) and starts at the origin rounded down to 16.
+struct FastMaps { CUtensorMap m[kMaxLevels]; };
+constexpr int kFastRawW = kFastPW + 16;
+constexpr int kFastRawBytes = kFastPH * kFastRawW;
+constexpr size_t kFastTmaSmemBytes = 2 * (size_t)kFastRawBytes + kFastSmemBytes;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity)
+{
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(bar)),
+                 "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, void* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_fast_tma(const __grid_constant__ OrbGeom g, const OrbBuffers b, const __grid_constant__ FastMaps maps,
+                                                  int tiles_per_frame, int total)
+{
+    extern __shared__ __align__(128) uint8_t fast_smem[];
+    uint8_t* raw = fast_smem;                                                   // [2][kFastPH][kFastPW] bytes, written by the TMA engine
+    uint16_t* A = reinterpret_cast<uint16_t*>(fast_smem + 2 * kFastRawBytes);
+    uint16_t* As = A + kFastPH * kFastP16;
+    uint32_t* sc = reinterpret_cast<uint32_t*>(As + kFastPH * kFastP16);
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ int s_n, s_base;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto locate = [&](int item, int& f, int& l, int& px0, int& py0) {
+        f = item / tiles_per_frame;
+        const int tile = item - f * tiles_per_frame;
+        l = 0;
+        while (l + 1 < g.nlevels && tile >= g.lv[l + 1].fast_tile_base) l++;
+        const int t = tile - g.lv[l].fast_tile_base;
+        px0 = kFastOW * (t % g.lv[l].fast_tiles_x) - 4; py0 = kFastOH * (t / g.lv[l].fast_tiles_x) - 4;
+    };
+    auto fetch = [&](int item, int buf) {                                       // thread 0 only
+        int f, l, px0, py0;
+        locate(item, f, l, px0, py0);
+        mbar_expect_tx(&bar[buf], kFastRawBytes);
+        tma_load_3d(raw + buf * kFastRawBytes, &maps.m[l], px0 - ((px0 + 16) & 15), py0, f, &bar[buf]);
+    };
+    int item = blockIdx.x;
+    if (item < total && threadIdx.x == 0) fetch(item, 0);
+    for (int it = 0; item < total; item += gridDim.x, it++) {
+        const int buf = it & 1;
+        int f, l, px0, py0;
+        locate(item, f, l, px0, py0);
+        mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u);
+        // widen the landed bytes to u16 twice (A[y][x], As[y][x] = A[y][x+1]), as k_fast does from registers
+        const uint8_t* rw = raw + buf * kFastRawBytes + ((px0 + 16) & 15);          // first byte of the tile inside the wider box (4-byte aligned)
+        constexpr int kStageIters = kFastPH * (kFastPW / 4) / 256;
+#pragma unroll
+        for (int k = 0; k < kStageIters; k++) {
+            const int i = k * 256 + threadIdx.x;
+            const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(rw + ry * kFastRawW + rx);
+            const uint32_t p01 = __byte_perm(v, 0, 0x4140), p23 = __byte_perm(v, 0, 0x4342), p12 = __byte_perm(v, 0, 0x4241);
+            uint16_t* a = A + ry * kFastP16 + rx;
+            uint16_t* as = As + ry * kFastP16 + rx;
+            *reinterpret_cast<uint32_t*>(a) = p01;
+            *reinterpret_cast<uint32_t*>(a + 2) = p23;
+            if (rx > 0) as[-1] = (uint16_t)(v & 0xff);
+            *reinterpret_cast<uint32_t*>(as) = p12;
+            as[2] = (uint16_t)(v >> 24);
+        }
+        __syncthreads();                           // A / As complete; raw[buf] and (since the last iteration) raw[1 - buf] are free
+        const int next = item + gridDim.x;
+        if (next < total && threadIdx.x == 0) fetch(next, 1 - buf);
+        fast_tile_compute(g, b, g.lv[l], f, l, px0, py0, A, As, sc, s_n, s_base);
+        __syncthreads();                           // the tile buffers (A doubles as the survivor list) are reused by the next item
     }
 }
 
@@ -1109,6 +1207,12 @@ struct mage_orb_s {
     int stage_cap = 0;          // staging capacity per frame = max(nfeatures, sum of per-level budgets)
     cudaStream_t own_stream = nullptr;
     cudaStream_t aux_stream = nullptr;      // the blur runs here, concurrently with FAST + selection (it only feeds the descriptors)
+    // TMA path of FAST: one 3-D tensor map (x, y, frame) per level over the handle's pyramid slabs; level 0 is re-encoded per call
+    // when the pixels come from a caller's device buffer. Unavailable (=> k_fast) if the driver entry point cannot be resolved.
+    FastMaps maps;
+    bool tma_ok = false, maps_lvl0_foreign = false;
+    int sm_count = 0;
+    void* encode_fn = nullptr;
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
 };
 
@@ -1165,6 +1269,21 @@ void resize_axis(int ssize, int dsize, int* ofs, short2* coef)
         ofs[d] = s;
         coef[d] = make_short2((short)cvRoundF((1.f - fx) * 2048.f), (short)cvRoundF(fx * 2048.f));
     }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D byte tensor (x < w, y < h, frame < frames) with row stride `pitch` and frame stride `fstride`; box = one FAST pixel tile
+bool encode_level_map(void* fn, CUtensorMap* out, const void* base, int w, int h, int frames, size_t pitch, size_t fstride)
+{
+    if (!fn || ((uintptr_t)base & 15) || (pitch & 15) || (fstride & 15)) return false;
+    const cuuint64_t dim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
+    const cuuint64_t stride[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
+    const cuuint32_t box[3] = {(cuuint32_t)kFastRawW, (cuuint32_t)kFastPH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return reinterpret_cast<EncodeTiledFn>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int select_smem_bytes() { return kSelSmemItems * (8 + 4 + 4 + 1); }
@@ -1319,6 +1438,24 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("mage_orb_create: %s", cudaGetErrorString(e)); A.release(); delete h; return MAGE_ERR_CUDA; }
+    {   // TMA path of FAST: opt-in (MAGE_FAST_TMA=1). Measured on B200 it is correct but 16 % slower than the register-staged kernel
+        // (0.707 vs 0.610 ms per 128 frames: 3 instead of 4 CTAs per SM and an extra shared-to-shared pass on an ALU-bound kernel), DESIGN.md 5
+        const char* env = getenv("MAGE_FAST_TMA");
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        if (env && atoi(env) != 0 && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess && fn) {
+            h->encode_fn = fn;
+            bool ok = cudaFuncSetAttribute(k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastTmaSmemBytes) == cudaSuccess;
+            for (int l = 0; l < g.nlevels && ok; l++)
+                ok = encode_level_map(fn, &h->maps.m[l], b.pyr + g.lv[l].pyr_off, g.lv[l].w, g.lv[l].h, max_batch, (size_t)g.lv[l].pitch, pyr);
+            h->tma_ok = ok;
+        }
+        cudaGetLastError();
+    }
     *out = h;
     return MAGE_OK;
 }
@@ -1382,7 +1519,20 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
         else k_blur<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
     }
     if (fork) MAGE_CUDA_TRY(cudaEventRecord(h->ev_blur, sb));
-    { ProfScope ps(PROF_FAST, s); k_fast<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs); }
+    {
+        ProfScope ps(PROF_FAST, s);
+        bool tma = h->tma_ok;
+        if (tma && bufs.lvl0 != h->b.lvl0)          // level 0 lives in the caller's device buffer: its own map (falls back if it is not 16-byte regular)
+            tma = encode_level_map(h->encode_fn, &h->maps.m[0], bufs.lvl0, g.lv[0].w, g.lv[0].h, n, (size_t)bufs.lvl0_pitch, bufs.lvl0_frame_stride);
+        else if (tma && h->maps_lvl0_foreign)
+            tma = encode_level_map(h->encode_fn, &h->maps.m[0], h->b.pyr + g.lv[0].pyr_off, g.lv[0].w, g.lv[0].h, h->max_batch, (size_t)g.lv[0].pitch, h->b.slab);
+        h->maps_lvl0_foreign = bufs.lvl0 != h->b.lvl0;
+        if (tma) {
+            const int total = h->fast_tiles * n;
+            k_fast_tma<<<std::min(total, 3 * std::max(h->sm_count, 1)), 256, kFastTmaSmemBytes, s>>>(g, bufs, h->maps, h->fast_tiles, total);
+        } else
+            k_fast<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs);
+    }
     { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }
     if (fork) MAGE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_blur, 0));
     { ProfScope ps(PROF_ORIENT_DESCRIBE, s); k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity); }

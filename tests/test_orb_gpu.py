@@ -197,6 +197,31 @@ def test_generic_pattern_patch_sizes(patch, orient, nlevels):
         assert_same_features(gk, gd, ok, od, "patch %d" % patch)
 
 
+def test_tma_staged_fast_kernel_is_bit_exact(frames, monkeypatch):
+    """the opt-in TMA variant of FAST (cp.async.bulk.tensor tile fetch, persistent double-buffered CTAs) against the oracle, host and device input"""
+    import torch
+    monkeypatch.setenv("MAGE_FAST_TMA", "1")
+    p = orc.tier_params()
+    det = make_detector(p, max_batch=3)
+    vid = frames["video"][:3]
+    kps, desc, counts = det.DetectAndComputeBatch(np.ascontiguousarray(vid))
+    d_img = torch.from_numpy(np.ascontiguousarray(vid)).cuda()
+    d_kps = torch.zeros((3, 2000, 28), dtype=torch.uint8, device="cuda"); d_desc = torch.zeros((3, 2000, 32), dtype=torch.uint8, device="cuda")
+    d_cnt = torch.zeros(3, dtype=torch.int32, device="cuda")
+    det.ExtractDevice(d_img, d_kps, d_desc, d_cnt, 2000, stream=torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    for f in range(3):
+        ok, od = orc.detect_and_compute(p, vid[f], 1)
+        n = int(counts[f])
+        assert_same_features(kps[f, :n], desc[f, :n], ok, od, "tma host frame %d" % f)
+        assert d_kps[f, :n].cpu().numpy().tobytes() == kps[f, :n].tobytes() and np.array_equal(d_desc[f, :n].cpu().numpy(), desc[f, :n])
+    cands = det.DebugCandidates(0, 3)
+    monkeypatch.setenv("MAGE_FAST_TMA", "0")
+    det2 = make_detector(p, max_batch=3)
+    det2.DetectAndComputeBatch(np.ascontiguousarray(vid))
+    assert np.array_equal(cands, det2.DebugCandidates(0, 3))
+
+
 def test_orb_feature_detector_process(frames):
     s = FeatureExtractorSettings.tier()
     gk, gd = OrbFeatureDetector(s).Process(frames["video"][0])
