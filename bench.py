@@ -270,6 +270,7 @@ def run_ours(args):
     e0.record(stream)
     for i in range(args.steps):
         dev_step(args.warmup + i)
+    fe_dev.Join(stream)                   # the matches run on the handle's second stream: the closing event waits for them
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1) / args.steps

@@ -255,9 +255,12 @@ int  mage_frontend_process(mage_frontend_t f, const uint8_t* images, int n, int 
 int  mage_frontend_submit(mage_frontend_t f, const uint8_t* images, int n, int stride, size_t frame_stride,
                           mage_keypoint* kps, uint8_t* desc, int* counts, mage_dmatch* matches, int* match_counts);
 int  mage_frontend_wait(mage_frontend_t f);
-/* Device-resident frames, results stay in the handle's device buffers (mage_frontend_device_buffers). Asynchronous. */
+/* Device-resident frames, results stay in the handle's device buffers (mage_frontend_device_buffers). Asynchronous: the extraction
+ * is enqueued on cuda_stream, the matches on an internal stream so that they run under the extraction of the next call;
+ * mage_frontend_join makes a stream wait for everything enqueued so far (a device synchronisation does too). */
 int  mage_frontend_process_device(mage_frontend_t f, const uint8_t* d_images, int n, int stride, size_t frame_stride,
                                   void* cuda_stream);
+int  mage_frontend_join(mage_frontend_t f, void* cuda_stream);
 int  mage_frontend_device_buffers(mage_frontend_t f, mage_keypoint** d_kps, uint8_t** d_desc, int** d_counts,
                                   mage_dmatch** d_matches, int** d_match_counts, int* capacity);
 

@@ -25,10 +25,15 @@ struct mage_frontend_s {
     int* d_counts = nullptr;
     mage_dmatch* d_matches = nullptr;
     int* d_match_counts = nullptr;
-    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_out = nullptr;
+    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_match = nullptr, s_out = nullptr;
+    // the matcher runs on its own stream: Match(call j) only needs the descriptors of call j, so it executes under the extraction of
+    // the next chunk / call (different pipes: popcount vs packed min/max). ev_x = extracted, ev_m = matched (per chunk, per result set)
+    cudaEvent_t ev_dev_x[2] = {nullptr, nullptr}, ev_dev_m[2] = {nullptr, nullptr};       // device-resident path, per result set
+    bool dev_used[2] = {false, false};
+    long long dev_calls = 0;
     // two calls can be in flight (mage_frontend_submit / _wait): call j stages its frames in image buffer j % 2; per chunk,
     // ev_in = uploaded, ev_done = computed, ev_out = results delivered to the caller's host buffers
-    struct Flight { std::vector<cudaEvent_t> ev_in, ev_done, ev_out; int nch = 0; bool pending = false; };
+    struct Flight { std::vector<cudaEvent_t> ev_in, ev_done, ev_match, ev_out; cudaEvent_t ev_all_matched = nullptr; int nch = 0; bool pending = false; };
     Flight flight[2];
     long long submitted = 0, waited = 0;
     cudaEvent_t ev_prev = nullptr;
@@ -66,13 +71,20 @@ extern "C" int mage_frontend_create(const mage_orb_params* p, int width, int hei
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_copy, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_compute, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&f->s_match, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+        e = cudaEventCreateWithFlags(&f->ev_dev_x[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_dev_m[i], cudaEventDisableTiming);
+    }
     const int nchunks = div_up(batch, chunk);
     for (auto& fl : f->flight) {
-        fl.ev_in.assign(nchunks, nullptr); fl.ev_done.assign(nchunks, nullptr); fl.ev_out.assign(nchunks, nullptr);
+        fl.ev_in.assign(nchunks, nullptr); fl.ev_done.assign(nchunks, nullptr); fl.ev_match.assign(nchunks, nullptr); fl.ev_out.assign(nchunks, nullptr);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fl.ev_all_matched, cudaEventDisableTiming);
         for (int i = 0; i < nchunks && e == cudaSuccess; i++) {
             e = cudaEventCreateWithFlags(&fl.ev_in[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fl.ev_done[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fl.ev_out[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&fl.ev_match[i], cudaEventDisableTiming);
         }
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ev_prev, cudaEventDisableTiming);
@@ -100,7 +112,11 @@ extern "C" void mage_frontend_destroy(mage_frontend_s* f)
         for (auto e : fl.ev_in) if (e) cudaEventDestroy(e);
         for (auto e : fl.ev_done) if (e) cudaEventDestroy(e);
         for (auto e : fl.ev_out) if (e) cudaEventDestroy(e);
+        for (auto e : fl.ev_match) if (e) cudaEventDestroy(e);
+        if (fl.ev_all_matched) cudaEventDestroy(fl.ev_all_matched);
     }
+    for (int i = 0; i < 2; i++) { if (f->ev_dev_x[i]) cudaEventDestroy(f->ev_dev_x[i]); if (f->ev_dev_m[i]) cudaEventDestroy(f->ev_dev_m[i]); }
+    if (f->s_match) cudaStreamDestroy(f->s_match);
     if (f->ev_prev) cudaEventDestroy(f->ev_prev);
     if (f->s_copy) cudaStreamDestroy(f->s_copy);
     if (f->s_compute) cudaStreamDestroy(f->s_compute);
@@ -117,22 +133,29 @@ extern "C" int mage_frontend_reset(mage_frontend_s* f)
     f->has_prev = false;
     for (auto& fl : f->flight) fl.pending = false;
     f->waited = f->submitted;
+    f->dev_used[0] = f->dev_used[1] = false;
     return MAGE_OK;
 }
 
-// extract + match of frames [c0, c1) whose pixels are at d_img (frame stride fs, row stride st), on stream s
-static int frontend_compute(mage_frontend_s* f, int set, const uint8_t* d_img, int st, size_t fs, int c0, int c1, cudaStream_t s)
+// extract of frames [c0, c1) whose pixels are at d_img (frame stride fs, row stride st) into result set `set`, on stream s
+static int frontend_extract(mage_frontend_s* f, int set, const uint8_t* d_img, int st, size_t fs, int c0, int c1, cudaStream_t s)
 {
     const size_t cap = (size_t)f->cap;
     const int base = set * f->batch;               // first result slot (minus one) and first match job of this result set
-    int rc = mage_orb_extract_device(f->orb, d_img, c1 - c0, f->width, f->height, st, fs, f->d_kps + cap * (base + c0 + 1),
-                                     f->d_desc + 32 * cap * (base + c0 + 1), f->cap, f->d_counts + base + c0 + 1, s);
-    if (rc != MAGE_OK) return rc;
+    return mage_orb_extract_device(f->orb, d_img, c1 - c0, f->width, f->height, st, fs, f->d_kps + cap * (base + c0 + 1),
+                                   f->d_desc + 32 * cap * (base + c0 + 1), f->cap, f->d_counts + base + c0 + 1, s);
+}
+// Match(frame i, frame i-1) for the frames [c0, c1) of result set `set`, on stream s
+static int frontend_match(mage_frontend_s* f, int set, int c0, int c1, cudaStream_t s)
+{
+    const size_t cap = (size_t)f->cap;
+    const int base = set * f->batch;
     return mage_match_run_jobs(f->matcher, base + c0, c1 - c0, f->max_hamming, f->min_diff, f->d_matches + cap * (base + c0), f->cap,
                                f->d_match_counts + base + c0, s);
 }
 
-// keep the last frame of this call as "previous" for the next one
+// keep the last frame of this call as "previous" for the next one. Runs on the MATCH stream, after the call's matches (which read
+// the old slot 0) and before the next call's (which read the new one).
 static int frontend_roll(mage_frontend_s* f, int set, int n, cudaStream_t s)
 {
     const size_t cap = (size_t)f->cap, last = (size_t)set * f->batch + n;
@@ -144,16 +167,38 @@ static int frontend_roll(mage_frontend_s* f, int set, int n, cudaStream_t s)
     return MAGE_OK;
 }
 
+// Device-resident frames. The extraction is enqueued on the caller's stream, the matches on the handle's match stream (ordered by
+// events), alternating between the two result sets, so Match(call j) overlaps the extraction of call j+1. The results of a call are
+// complete once mage_frontend_join(f, stream) has been enqueued and `stream` has reached it (or after a device synchronisation).
 extern "C" int mage_frontend_process_device(mage_frontend_s* f, const uint8_t* d_images, int n, int stride, size_t frame_stride, void* stream)
 {
     MAGE_REQUIRE(f && d_images && n >= 1 && n <= f->batch, MAGE_ERR_INVALID, "mage_frontend_process_device: bad argument");
     cudaStream_t s = (cudaStream_t)stream;       // NULL = the default stream, like any CUDA API
+    const int set = (int)(f->dev_calls & 1);
+    if (f->dev_used[set]) MAGE_CUDA_TRY(cudaStreamWaitEvent(s, f->ev_dev_m[set], 0));      // the matches of two calls ago read this result set
     for (int c0 = 0; c0 < n; c0 += f->chunk) {
         int c1 = std::min(n, c0 + f->chunk);
-        int rc = frontend_compute(f, 0, d_images + (size_t)c0 * frame_stride, stride, frame_stride, c0, c1, s);
+        int rc = frontend_extract(f, set, d_images + (size_t)c0 * frame_stride, stride, frame_stride, c0, c1, s);
+        if (rc != MAGE_OK) return rc;
+        MAGE_CUDA_TRY(cudaEventRecord(f->ev_dev_x[set], s));
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_match, f->ev_dev_x[set], 0));
+        rc = frontend_match(f, set, c0, c1, f->s_match);
         if (rc != MAGE_OK) return rc;
     }
-    return frontend_roll(f, 0, n, s);
+    int rc = frontend_roll(f, set, n, f->s_match);
+    if (rc != MAGE_OK) return rc;
+    MAGE_CUDA_TRY(cudaEventRecord(f->ev_dev_m[set], f->s_match));
+    f->dev_used[set] = true;
+    f->dev_calls++;
+    return MAGE_OK;
+}
+
+// makes `stream` wait for everything mage_frontend_process_device has enqueued so far (the matches run on another stream)
+extern "C" int mage_frontend_join(mage_frontend_s* f, void* stream)
+{
+    MAGE_REQUIRE(f, MAGE_ERR_INVALID, "null handle");
+    for (int i = 0; i < 2; i++) if (f->dev_used[i]) MAGE_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, f->ev_dev_m[i], 0));
+    return MAGE_OK;
 }
 
 extern "C" int mage_frontend_device_buffers(mage_frontend_s* f, mage_keypoint** d_kps, uint8_t** d_desc, int** d_counts, mage_dmatch** d_matches,
@@ -193,22 +238,31 @@ static int frontend_submit(mage_frontend_s* f, const uint8_t* images, int n, int
             MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, me.ev_out[ko], 0));
             if (k == nch - 1) for (int q = ko + 1; q < me.nch; q++) MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, me.ev_out[q], 0));
         }
-        int rc = frontend_compute(f, b, stage + PT * H * c0, f->pitch, PT * H, c0, c1, f->s_compute);
+        if (k == 0 && me.pending) MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_compute, me.ev_all_matched, 0));           // matches of call j-2 read this set
+        int rc = frontend_extract(f, b, stage + PT * H * c0, f->pitch, PT * H, c0, c1, f->s_compute);
         if (rc != MAGE_OK) return rc;
         MAGE_CUDA_TRY(cudaEventRecord(me.ev_done[k], f->s_compute));
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_match, me.ev_done[k], 0));
+        rc = frontend_match(f, b, c0, c1, f->s_match);
+        if (rc != MAGE_OK) return rc;
+        MAGE_CUDA_TRY(cudaEventRecord(me.ev_match[k], f->s_match));
         MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_out, me.ev_done[k], 0));
         const int m = c1 - c0;
         const size_t r0 = (size_t)b * f->batch + c0;                      // first result slot (minus one) of the chunk
         MAGE_CUDA_TRY(cudaMemcpyAsync(kps + cap * c0, f->d_kps + cap * (r0 + 1), sizeof(mage_keypoint) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
         MAGE_CUDA_TRY(cudaMemcpyAsync(desc + 32 * cap * c0, f->d_desc + 32 * cap * (r0 + 1), 32 * cap * m, cudaMemcpyDeviceToHost, f->s_out));
-        MAGE_CUDA_TRY(cudaMemcpyAsync(matches + cap * c0, f->d_matches + cap * r0, sizeof(mage_dmatch) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
         MAGE_CUDA_TRY(cudaMemcpyAsync(counts + c0, f->d_counts + r0 + 1, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_out, me.ev_match[k], 0));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(matches + cap * c0, f->d_matches + cap * r0, sizeof(mage_dmatch) * cap * m, cudaMemcpyDeviceToHost, f->s_out));
         MAGE_CUDA_TRY(cudaMemcpyAsync(match_counts + c0, f->d_match_counts + r0, sizeof(int) * m, cudaMemcpyDeviceToHost, f->s_out));
         MAGE_CUDA_TRY(cudaEventRecord(me.ev_out[k], f->s_out));
     }
     me.nch = nch; me.pending = true;
     f->submitted++;
-    return frontend_roll(f, b, n, f->s_compute);
+    int rc = frontend_roll(f, b, n, f->s_match);
+    if (rc != MAGE_OK) return rc;
+    MAGE_CUDA_TRY(cudaEventRecord(me.ev_all_matched, f->s_match));
+    return MAGE_OK;
 }
 
 extern "C" int mage_frontend_submit(mage_frontend_s* f, const uint8_t* images, int n, int stride, size_t frame_stride, mage_keypoint* kps,
@@ -228,7 +282,7 @@ extern "C" int mage_frontend_wait(mage_frontend_s* f)
     mage_frontend_s::Flight& fl = f->flight[(int)(f->waited & 1)];
     MAGE_CUDA_TRY(cudaEventSynchronize(fl.ev_out[fl.nch - 1]));          // downloads of a call are enqueued in chunk order on one stream
     f->waited++;
-    if (f->submitted == f->waited) MAGE_CUDA_TRY(cudaStreamSynchronize(f->s_compute));      // nothing left in flight: the roll copy too
+    if (f->submitted == f->waited) MAGE_CUDA_TRY(cudaStreamSynchronize(f->s_match));        // nothing left in flight: the roll copy too
     return MAGE_OK;
 }
 

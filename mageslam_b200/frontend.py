@@ -27,6 +27,7 @@ class FrontEnd:
         L.mage_frontend_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t] + [C.c_void_p] * 5
         L.mage_frontend_wait.argtypes = [C.c_void_p]
         L.mage_frontend_process_device.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p]
+        L.mage_frontend_join.argtypes = [C.c_void_p, C.c_void_p]
         L.mage_frontend_device_buffers.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 5 + [C.POINTER(C.c_int)]
         self.width, self.height, self.batch = int(width), int(height), int(batch)
         self._p = _params(settings)
@@ -94,6 +95,10 @@ class FrontEnd:
         """d_images: torch uint8 [n, h, w] on the device. Asynchronous; results via DeviceBuffers()."""
         n = d_images.shape[0]
         check(lib().mage_frontend_process_device(self._h, ptr(d_images), n, d_images.stride(1), d_images.stride(0), stream_ptr(stream)))
+
+    def Join(self, stream=None):
+        """Makes `stream` wait for everything ProcessDevice has enqueued so far (the matches run on an internal stream)."""
+        check(lib().mage_frontend_join(self._h, stream_ptr(stream)))
 
     def DeviceBuffers(self):
         ps = [C.c_void_p() for _ in range(5)]
