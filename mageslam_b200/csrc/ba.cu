@@ -60,6 +60,7 @@ struct BaDev {
     double* ldlt_col;                         // 2 x (n + 1) doubles in shared memory for the register-blocked LDL^T (null: in-place version)
     // one-CTA-per-problem kernel: rotation matrices of the current camera state (row-major 3x3 per camera)
     double* cam_R;                            // [K][9]
+    double* cam_Rold;                         // [K][9] rotation matrices of the linearisation point while a trial state is being evaluated
     // local-window fast path (fast != 0): landmarks in batches of <= kFastBE edges whose pose-landmark blocks live in shared
     // memory only; thread pair i owns the (block, part) item i and accumulates its share of the Schur products in registers
     int fast, nb, nitems;
@@ -1407,13 +1408,13 @@ __device__ double g_backup_update(const BaDev& p, double lambda, int tid, int nt
     return acc;
 }
 // W = w Jj^T Ji of one edge from its record (6x3 row-major)
-__device__ __forceinline__ void g_edge_W(const BaDev& p, const double* __restrict__ rec, int e, int c, double* W)
+__device__ __forceinline__ void g_edge_W(const BaDev& p, const double* __restrict__ camR, const double* __restrict__ rec, int e, int c, double* W)
 {
     const double2* r2 = reinterpret_cast<const double2*>(rec + kRec * (size_t)e);
     const double2 ab = r2[0], zw = r2[1];
     const double f = p.cam_f[c];
     double J0[3], J1[3], P0[6], P1[6];
-    f_point_jac(p.cam_R + 9 * c, ab.x, ab.y, zw.x, f, J0, J1);
+    f_point_jac(camR + 9 * c, ab.x, ab.y, zw.x, f, J0, J1);
     f_pose_jac(ab.x, ab.y, zw.x, f, P0, P1);
     const double w0[3] = {zw.y * J0[0], zw.y * J0[1], zw.y * J0[2]}, w1[3] = {zw.y * J1[0], zw.y * J1[1], zw.y * J1[2]};
 #pragma unroll
@@ -1554,6 +1555,78 @@ __device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double l
         bs[i] = p.bp[i] - s;
     }
 }
+// One pass per trial after the reduced system has been solved and the cameras have been updated (their old rotations are in
+// cam_Rold): per landmark  x_l = D^-1 (b_l - W^T x_p)  (ref block_solver.hpp:418-444; W rebuilt from the records at the
+// linearisation point), push + oplus of the point (ref base_vertex.h:92-94, types_sba.h:149-153), then computeError of its edges at
+// the trial state into the trial records / errors. Returns this thread's shares of the robust chi2 and of computeScale's sum.
+__device__ void g_backsub_update_project(const BaDev& p, const double* __restrict__ recCur, double* __restrict__ recTry, double* __restrict__ errTry,
+                                         double lambda, double delta, bool solved, int tid, int nt, double& chiPart, double& scalePart)
+{
+    double chi = 0, sc = 0;
+    for (int j = tid; j < p.n; j += nt) { const double xj = p.x[j]; sc += xj * (lambda * xj + p.bp[j]); }
+    for (int li = tid; li < p.Pl; li += nt) {
+        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
+        const double bl0 = p.bl[3 * li], bl1 = p.bl[3 * li + 1], bl2 = p.bl[3 * li + 2];
+        double x0, x1, x2;
+        if (solved) {
+            double c0 = bl0, c1 = bl1, c2 = bl2;
+#pragma unroll 2
+            for (int e = k0; e < k1; e++) {
+                const int c = p.e_cam[e], hj = p.cam_h[c];
+                if (hj < 0) continue;
+                double W[18];
+                g_edge_W(p, p.cam_Rold, recCur, e, c, W);
+                const double* xp = p.x + 6 * hj;
+#pragma unroll
+                for (int r = 0; r < 6; r++) { const double xr = xp[r]; c0 -= W[r * 3] * xr; c1 -= W[r * 3 + 1] * xr; c2 -= W[r * 3 + 2] * xr; }
+            }
+            const double* D = p.Dinv + 9 * (size_t)li;
+            x0 = D[0] * c0 + D[1] * c1 + D[2] * c2; x1 = D[3] * c0 + D[4] * c1 + D[5] * c2; x2 = D[6] * c0 + D[7] * c1 + D[8] * c2;
+            p.x[p.n + 3 * li] = x0; p.x[p.n + 3 * li + 1] = x1; p.x[p.n + 3 * li + 2] = x2;
+        } else {                                   // failed factorisation: g2o updates with the stale increment (ref block_solver.hpp:396-400)
+            x0 = p.x[p.n + 3 * li]; x1 = p.x[p.n + 3 * li + 1]; x2 = p.x[p.n + 3 * li + 2];
+        }
+        double* X = p.pt_X + 3 * (size_t)p.l_pt[li];
+        const double o0 = X[0], o1 = X[1], o2 = X[2];
+        p.pt_bak[3 * li] = o0; p.pt_bak[3 * li + 1] = o1; p.pt_bak[3 * li + 2] = o2;
+        const double X0 = o0 + x0, X1 = o1 + x1, X2 = o2 + x2;
+        X[0] = X0; X[1] = X1; X[2] = X2;
+        sc += x0 * (lambda * x0 + bl0); sc += x1 * (lambda * x1 + bl1); sc += x2 * (lambda * x2 + bl2);
+#pragma unroll 2
+        for (int e = k0; e < k1; e++) {
+            const int c = p.e_cam[e];
+            const double* __restrict__ R = p.cam_R + 9 * c;
+            const double x = R[0] * X0 + R[1] * X1 + R[2] * X2 + p.cam_t[3 * c];
+            const double y = R[3] * X0 + R[4] * X1 + R[5] * X2 + p.cam_t[3 * c + 1];
+            const double z = R[6] * X0 + R[7] * X1 + R[8] * X2 + p.cam_t[3 * c + 2];
+            const double iz = 1.0 / z, a = x * iz, b = y * iz, f = p.cam_f[c];
+            const double2 uv = *reinterpret_cast<const double2*>(p.e_uv + 2 * (size_t)e);
+            const double e0 = uv.x - (a * f + p.cam_cx[c]), e1 = uv.y - (b * f + p.cam_cy[c]);
+            *reinterpret_cast<double2*>(errTry + 2 * (size_t)e) = make_double2(e0, e1);
+            double2* r2 = reinterpret_cast<double2*>(recTry + kRec * (size_t)e);
+            r2[0] = make_double2(a, b);
+            r2[1] = make_double2(iz, 0.0);
+            double r0, r1;
+            huber(p.e_info[e] * (e0 * e0 + e1 * e1), delta, r0, r1);
+            chi += r0;
+        }
+    }
+    chiPart = chi; scalePart = sc;
+}
+// push + oplus of the free cameras (ref base_vertex.h:92-94, types_six_dof_expmap.h:98-101); the rotation matrices of the
+// linearisation point are kept for the back-substitution
+__device__ void g_update_cams(const BaDev& p, int tid, int nt)
+{
+    for (int i = tid; i < 9 * p.K; i += nt) p.cam_Rold[i] = p.cam_R[i];
+    for (int i = tid; i < p.Kf; i += nt) {
+        const int c = p.c_cam[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) p.cam_bak[7 * i + j] = p.cam_q[4 * c + j];
+#pragma unroll
+        for (int j = 0; j < 3; j++) p.cam_bak[7 * i + 4 + j] = p.cam_t[3 * c + j];
+        pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i);
+    }
+}
 __device__ void g_backsub(const BaDev& p, const double* __restrict__ rec, int tid, int nt)
 {
     for (int li = tid; li < p.Pl; li += nt) {
@@ -1564,7 +1637,7 @@ __device__ void g_backsub(const BaDev& p, const double* __restrict__ rec, int ti
             const int c = p.e_cam[e], hj = p.cam_h[c];
             if (hj < 0) continue;
             double W[18];
-            g_edge_W(p, rec, e, c, W);
+            g_edge_W(p, p.cam_R, rec, e, c, W);
             const double* xp = p.x + 6 * hj;
 #pragma unroll
             for (int r = 0; r < 6; r++) { const double xr = xp[r]; c0 -= W[r * 3] * xr; c1 -= W[r * 3 + 1] * xr; c2 -= W[r * 3 + 2] * xr; }
@@ -1593,7 +1666,7 @@ constexpr size_t kBigScratchBytes = sizeof(double) * (2 * kLdltTile * (kLdltNB +
 
 __host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) * ((size_t)n * n + n); }
 __host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
-__host__ __device__ inline size_t ba_smem_need_cams_R(int K) { return sizeof(double) * 19 * (size_t)K + sizeof(int) * (size_t)K; }     // + rotation matrices
+__host__ __device__ inline size_t ba_smem_need_cams_R(int K) { return sizeof(double) * 28 * (size_t)K + sizeof(int) * (size_t)K; }     // + rotation matrices (current, linearisation point)
 
 __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq,
                                                             unsigned dynBytes)
@@ -1624,8 +1697,8 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
             g_cam_q = s_p.cam_q; g_cam_t = s_p.cam_t;
             const double *gf = s_p.cam_f, *gx = s_p.cam_cx, *gy = s_p.cam_cy; const int* gh = s_p.cam_h;
             double* sq = c; double* st = c + 4 * s_p.K; double* sf = c + 7 * s_p.K; double* sx = c + 8 * s_p.K; double* sy = c + 9 * s_p.K;
-            s_p.cam_R = c + 10 * s_p.K;
-            int* shh = reinterpret_cast<int*>(c + 19 * s_p.K);
+            s_p.cam_R = c + 10 * s_p.K; s_p.cam_Rold = c + 19 * s_p.K;
+            int* shh = reinterpret_cast<int*>(c + 28 * s_p.K);
             for (int k = 0; k < s_p.K; k++) {
                 for (int j = 0; j < 4; j++) sq[4 * k + j] = g_cam_q[4 * k + j];
                 for (int j = 0; j < 3; j++) st[3 * k + j] = g_cam_t[3 * k + j];
@@ -1695,14 +1768,13 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
                 const bool ok2 = phase_ldlt_solve(p, sh);
                 __syncthreads();
                 PH(4);
-                if (ok2) g_backsub(p, recCur, tid, nt);
-                __syncthreads();
-                const double scalePart = g_backup_update(p, lambda, tid, nt);
+                g_update_cams(p, tid, nt);
                 __syncthreads();
                 f_cam_R(p, tid, nt);
                 __syncthreads();
                 PH(6);
-                double part = g_project(p, recTry, errTry, delta, tid, nt);
+                double part, scalePart;
+                g_backsub_update_project(p, recCur, recTry, errTry, lambda, delta, ok2, tid, nt, part, scalePart);
                 if (p.nT) { phase_tether_errors(p, tid, nt); __syncthreads(); part += tether_chi2_sum(p); }
                 errLast = errTry;
                 double tempChi = block_sum(part, sh);
@@ -2622,7 +2694,7 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_Dinv = rD(9 * (size_t)Pl), o_db = rD(3 * (size_t)Pl), o_Hpp = rD(36 * (size_t)Kf), o_bp = rD(n), o_S = rD((size_t)n * n), o_bs = rD(n);
     size_t o_x = rD(n + 3 * (size_t)Pl), o_cbak = rD(7 * (size_t)Kf), o_pbak = rD(3 * (size_t)Pl), o_part = rD((size_t)Kf * cam_parts * 27);
     size_t o_flags = W.reserve(std::max(Ea, 1));
-    size_t o_Hc = rD(12 * (size_t)Ea), o_camR = rD(9 * (size_t)h->K);
+    size_t o_Hc = rD(12 * (size_t)Ea), o_camR = rD(18 * (size_t)h->K);
     size_t o_bptr2 = rI(batch_ptr.size()), o_idef = W.reserve(sizeof(int4) * std::max<size_t>(item_def.size(), 1)), o_bitems = W.reserve(sizeof(int2) * blk_items.size());
     size_t o_cdiag = rI(cam_diag.size()), o_bbptr = rI(bb_ptr.size()), o_bpairs = W.reserve(sizeof(ushort2) * std::max<size_t>(bpairs.size(), 1));
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
@@ -2661,7 +2733,7 @@ static int ba_build_structure(mage_ba_t h)
     d.Dinv = W.at<double>(o_Dinv); d.db = W.at<double>(o_db); d.Hpp = W.at<double>(o_Hpp); d.bp = W.at<double>(o_bp); d.S = W.at<double>(o_S);
     d.bs = W.at<double>(o_bs); d.x = W.at<double>(o_x); d.cam_bak = W.at<double>(o_cbak); d.pt_bak = W.at<double>(o_pbak); d.part = W.at<double>(o_part);
     d.flags = W.at<unsigned char>(o_flags);
-    d.Hc = W.at<double>(o_Hc); d.cam_R = W.at<double>(o_camR);
+    d.Hc = W.at<double>(o_Hc); d.cam_R = W.at<double>(o_camR); d.cam_Rold = d.cam_R + 9 * (size_t)h->K;
     d.fast = fast; d.nb = nb; d.nitems = nitems;
     d.batch_ptr = W.at<int>(o_bptr2); d.item_def = W.at<int4>(o_idef); d.blk_items = W.at<int2>(o_bitems);
     d.cam_diag = W.at<int>(o_cdiag); d.bb_ptr = W.at<int>(o_bbptr); d.bpairs = W.at<ushort2>(o_bpairs);

@@ -175,19 +175,20 @@ extern "C" int mage_frontend_process_device(mage_frontend_s* f, const uint8_t* d
     MAGE_REQUIRE(f && d_images && n >= 1 && n <= f->batch, MAGE_ERR_INVALID, "mage_frontend_process_device: bad argument");
     cudaStream_t s = (cudaStream_t)stream;       // NULL = the default stream, like any CUDA API
     const int set = (int)(f->dev_calls & 1);
+    cudaStream_t sm = prof_enabled() ? s : f->s_match;       // per-kernel timing (mage_profile_*) keeps everything on one stream
     if (f->dev_used[set]) MAGE_CUDA_TRY(cudaStreamWaitEvent(s, f->ev_dev_m[set], 0));      // the matches of two calls ago read this result set
     for (int c0 = 0; c0 < n; c0 += f->chunk) {
         int c1 = std::min(n, c0 + f->chunk);
         int rc = frontend_extract(f, set, d_images + (size_t)c0 * frame_stride, stride, frame_stride, c0, c1, s);
         if (rc != MAGE_OK) return rc;
         MAGE_CUDA_TRY(cudaEventRecord(f->ev_dev_x[set], s));
-        MAGE_CUDA_TRY(cudaStreamWaitEvent(f->s_match, f->ev_dev_x[set], 0));
-        rc = frontend_match(f, set, c0, c1, f->s_match);
+        MAGE_CUDA_TRY(cudaStreamWaitEvent(sm, f->ev_dev_x[set], 0));
+        rc = frontend_match(f, set, c0, c1, sm);
         if (rc != MAGE_OK) return rc;
     }
-    int rc = frontend_roll(f, set, n, f->s_match);
+    int rc = frontend_roll(f, set, n, sm);
     if (rc != MAGE_OK) return rc;
-    MAGE_CUDA_TRY(cudaEventRecord(f->ev_dev_m[set], f->s_match));
+    MAGE_CUDA_TRY(cudaEventRecord(f->ev_dev_m[set], sm));
     f->dev_used[set] = true;
     f->dev_calls++;
     return MAGE_OK;
