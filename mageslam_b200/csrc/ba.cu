@@ -1242,14 +1242,16 @@ __device__ void f_backsub(const BaDev& p, int tid, int nt)
 // shared memory, and thread pair i -- owner of one (reduced-system block, part) item for the whole trial -- adds the batch's
 // products to 18 register accumulators per thread. One fixed-order reduction over the parts at the end: bit-reproducible, no
 // atomics, and the per-problem traffic drops from ~13 MB to ~3 MB per LM iteration (what bounds many problems in flight).
+constexpr int kBaThreadsC = 256;             // = kBaThreads (declared below)
 constexpr int kFastBE = 512;                // edges per batch
-constexpr int kFastBL = 256;                // landmarks per batch (bound only; the edge limit closes batches first)
+constexpr int kFastBL = 128;                // landmarks per batch (their D^-1 and D^-1 b are staged in shared memory, 9 doubles each)
 constexpr int kFastItems = 128;             // (block, part) items; thread t and t + 128 own the left / right 3 columns of item t's 6x6 block
 constexpr int kFastMaxKf = 10;
 constexpr int kFastRec = 18;                // doubles per staged edge: a b | 1/z jdb0 | jdb1 - | w J D^-1 (2x3) | w J (2x3)
 constexpr int kFastRed = 21;                // doubles per thread in the final reduction: 18 products + 3 coefficients
-constexpr size_t kFastRegionBytes = 74 * 1024;
-static_assert(sizeof(double) * kFastBE * kFastRec <= kFastRegionBytes, "batch buffer must fit the region");
+constexpr int kFastLD = 9;                  // D^-1 (6 unique) + D^-1 b_l (3) per staged landmark
+constexpr size_t kFastRegionBytes = 82 * 1024;
+static_assert(sizeof(double) * (kFastBE * kFastRec + kFastBL * kFastLD) <= kFastRegionBytes, "batch buffers must fit the region");
 static_assert(sizeof(double) * ((6 * kFastMaxKf) * (6 * kFastMaxKf + 1) + 2 * kFastItems * kFastRed) <= kFastRegionBytes, "S + reduction slots must fit the region");
 
 // computeError at the current state + the edge records; returns this thread's share of the robust chi2 (edge order = g_chi2's)
@@ -1429,6 +1431,7 @@ __device__ __forceinline__ void g_edge_W(const BaDev& p, const double* __restric
 __device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double lambda, double* region)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
+    double* sD = region + (size_t)kFastBE * kFastRec;                  // [kFastBL][kFastLD] behind the staged edges
     const int item = tid & (kFastItems - 1), half = tid >> 7;          // warp-uniform half: columns 3*half .. 3*half+2 (and rows, for the coefficients)
     int blk = -1, part = 0, nparts = 1;
     bool diag = false;
@@ -1449,8 +1452,23 @@ __device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double l
         int q0 = 0, qn = 0;
         if (blk >= 0) { q0 = p.bb_ptr[b * p.nblk + blk]; qn = p.bb_ptr[b * p.nblk + blk + 1] - q0; }
         __syncthreads();                                     // the previous batch has been consumed
-        for (int t = tid; t < ne; t += nt) {
-            const int e = e0 + t, c = p.e_cam[e], li = p.e_l[e];
+        // the edges' own data first (two per thread, independent loads in flight under the landmark phase)
+        int ec[kFastBE / kBaThreadsC], el[kFastBE / kBaThreadsC];
+        double2 eab[kFastBE / kBaThreadsC], ezw[kFastBE / kBaThreadsC];
+#pragma unroll
+        for (int u = 0; u < kFastBE / kBaThreadsC; u++) {
+            const int t = tid + u * kBaThreadsC;
+            ec[u] = -1; el[u] = 0;
+            if (t < ne) {
+                const int e = e0 + t;
+                ec[u] = p.e_cam[e]; el[u] = p.e_l[e] - lm0;
+                const double2* r2 = reinterpret_cast<const double2*>(rec + kRec * (size_t)e);
+                eab[u] = r2[0]; ezw[u] = r2[1];
+            }
+        }
+        // one thread per landmark of the batch: D^-1 = (H_ll + lambda I)^-1 and D^-1 b_l, to shared memory (and to global for the back-substitution)
+        if (tid < lm1 - lm0) {
+            const int li = lm0 + tid;
             const double* __restrict__ Hl = p.Hll + 9 * (size_t)li;
             const double A0 = Hl[0] + lambda, A1 = Hl[1], A2 = Hl[2], A4 = Hl[4] + lambda, A5 = Hl[5], A8 = Hl[8] + lambda;      // symmetric
             const double c00 = A4 * A8 - A5 * A5, c01 = A5 * A2 - A1 * A8, c02 = A1 * A5 - A4 * A2;
@@ -1458,14 +1476,21 @@ __device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double l
             const double D0 = c00 * id, D1 = c01 * id, D2 = c02 * id, D4 = (A0 * A8 - A2 * A2) * id, D5 = (A2 * A1 - A0 * A5) * id, D8 = (A0 * A4 - A1 * A1) * id;
             const double b0 = p.bl[3 * li], b1 = p.bl[3 * li + 1], b2 = p.bl[3 * li + 2];
             const double db0 = D0 * b0 + D1 * b1 + D2 * b2, db1 = D1 * b0 + D4 * b1 + D5 * b2, db2 = D2 * b0 + D5 * b1 + D8 * b2;
-            if (e == 0 || p.e_l[e - 1] != li) {
-                double* Dg = p.Dinv + 9 * (size_t)li;
-                Dg[0] = D0; Dg[1] = D1; Dg[2] = D2; Dg[3] = D1; Dg[4] = D4; Dg[5] = D5; Dg[6] = D2; Dg[7] = D5; Dg[8] = D8;
-                p.db[3 * li] = db0; p.db[3 * li + 1] = db1; p.db[3 * li + 2] = db2;
-            }
-            if (p.cam_h[c] >= 0) {
-                const double2* r2 = reinterpret_cast<const double2*>(rec + kRec * (size_t)e);
-                const double2 ab = r2[0], zw = r2[1];
+            double* Dg = p.Dinv + 9 * (size_t)li;
+            Dg[0] = D0; Dg[1] = D1; Dg[2] = D2; Dg[3] = D1; Dg[4] = D4; Dg[5] = D5; Dg[6] = D2; Dg[7] = D5; Dg[8] = D8;
+            p.db[3 * li] = db0; p.db[3 * li + 1] = db1; p.db[3 * li + 2] = db2;
+            double* sd = sD + kFastLD * tid;
+            sd[0] = D0; sd[1] = D1; sd[2] = D2; sd[3] = D4; sd[4] = D5; sd[5] = D8; sd[6] = db0; sd[7] = db1; sd[8] = db2;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kFastBE / kBaThreadsC; u++) {
+            const int c = ec[u];
+            if (c >= 0 && p.cam_h[c] >= 0) {
+                const int t = tid + u * kBaThreadsC;
+                const double* sd = sD + kFastLD * el[u];
+                const double D0 = sd[0], D1 = sd[1], D2 = sd[2], D4 = sd[3], D5 = sd[4], D8 = sd[5], db0 = sd[6], db1 = sd[7], db2 = sd[8];
+                const double2 ab = eab[u], zw = ezw[u];
                 double J0[3], J1[3];
                 f_point_jac(p.cam_R + 9 * c, ab.x, ab.y, zw.x, p.cam_f[c], J0, J1);
 #pragma unroll
@@ -1480,13 +1505,15 @@ __device__ void g_schur(const BaDev& p, const double* __restrict__ rec, double l
                 o[6] = make_double2(J0[0], J0[1]); o[7] = make_double2(J0[2], J1[0]); o[8] = make_double2(J1[1], J1[2]);
             }
         }
+        ushort2 pr = make_ushort2(0, 0);                     // the first pair of this thread: fetched before the barrier, not after it
+        const int kbeg = q0 + (part * qn) / nparts, kend = q0 + ((part + 1) * qn) / nparts;
+        if (blk >= 0 && kbeg < kend) pr = p.bpairs[kbeg];
         __syncthreads();
         if (blk >= 0) {
-            const int k1 = q0 + ((part + 1) * qn) / nparts;
-            for (int k = q0 + (part * qn) / nparts; k < k1; k++) {
-                const ushort2 pr = p.bpairs[k];
+            for (int k = kbeg; k < kend; k++) {
                 const double2* __restrict__ A2 = reinterpret_cast<const double2*>(region + kFastRec * pr.x);
                 const double2* __restrict__ B2 = reinterpret_cast<const double2*>(region + kFastRec * pr.y);
+                if (k + 1 < kend) pr = p.bpairs[k + 1];          // next pair's indices under this pair's arithmetic
                 const double2 ia = A2[0], iz = A2[1], g0 = A2[3], g1 = A2[4], g2 = A2[5];
                 const double2 ja = B2[0], jz = B2[1], h0 = B2[6], h1 = B2[7], h2 = B2[8];
                 // M = (w_i J_i D^-1)(w_j J_j)^T
