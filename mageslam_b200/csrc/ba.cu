@@ -2603,8 +2603,43 @@ static int ba_build_structure(mage_ba_t h)
     const int nT = (int)tact.size();
     std::vector<int> cam_h(h->K, -1), pt_l(h->P, -1), c_cam, l_pt;
     for (int k = 0; k < h->K; k++) if (camA[k] && !h->cam_fixed[k]) { cam_h[k] = (int)c_cam.size(); c_cam.push_back(k); }
-    if (!h->points_fixed)       // point vertex ids count down (ref BundlerLib.cpp:210-218): Hessian order = descending index
-        for (int i = h->P - 1; i >= 0; i--) if (ptA[i]) { pt_l[i] = (int)l_pt.size(); l_pt.push_back(i); }
+    std::vector<int> bal_batch_ptr;                 // landmark boundaries of the balanced batches (fast path), empty otherwise
+    if (!h->points_fixed) {     // point vertex ids count down (ref BundlerLib.cpp:210-218): Hessian order = descending index
+        for (int i = h->P - 1; i >= 0; i--) if (ptA[i]) l_pt.push_back(i);
+        const int Kf0 = (int)c_cam.size();
+        if (Kf0 >= 1 && Kf0 <= kFastMaxKf && !l_pt.empty() && !getenv("MAGE_BA_NO_FAST") && !getenv("MAGE_BA_NO_BALANCE")) {
+            // Local-window fast path: the landmark order is free (it only fixes summation orders), so landmarks are dealt into the
+            // shared-memory batches such that every reduced-system block gets about the same number of (edge, edge) products in every
+            // batch -- the threads of a warp own different blocks and run the longest list of the warp, batch by batch.
+            std::vector<std::vector<int>> pc(h->P);
+            std::vector<int> pe(h->P, 0);
+            for (int e : h->active) { const HostObs& o = h->obs[e]; pe[o.pt]++; if (cam_h[o.cam] >= 0) pc[o.pt].push_back(cam_h[o.cam]); }
+            long tot_e = 0; int max_e = 0;
+            for (int pt : l_pt) { tot_e += pe[pt]; max_e = std::max(max_e, pe[pt]); }
+            if (max_e <= kFastBE) {
+                int nbat = (int)std::max<long>(1, std::max((tot_e + kFastBE - 1) / kFastBE, ((long)l_pt.size() + kFastBL - 1) / kFastBL));
+                std::vector<std::vector<int>> load(nbat, std::vector<int>(Kf0 * Kf0, 0)), members(nbat);
+                std::vector<int> edges(nbat, 0);
+                for (int pt : l_pt) {
+                    int best = -1; long best_cost = 0;
+                    for (int b = 0; b < (int)members.size(); b++) {
+                        if (edges[b] + pe[pt] > kFastBE || (int)members[b].size() >= kFastBL) continue;
+                        long cost = 0;
+                        for (int i : pc[pt]) for (int j : pc[pt]) if (i <= j) cost += load[b][i * Kf0 + j];
+                        cost = cost * 4096 + edges[b];
+                        if (best < 0 || cost < best_cost) { best = b; best_cost = cost; }
+                    }
+                    if (best < 0) { best = (int)members.size(); members.emplace_back(); load.emplace_back(Kf0 * Kf0, 0); edges.push_back(0); }
+                    members[best].push_back(pt); edges[best] += pe[pt];
+                    for (int i : pc[pt]) for (int j : pc[pt]) if (i <= j) load[best][i * Kf0 + j]++;
+                }
+                l_pt.clear();
+                bal_batch_ptr.push_back(0);
+                for (auto& m : members) { if (m.empty()) continue; l_pt.insert(l_pt.end(), m.begin(), m.end()); bal_batch_ptr.push_back((int)l_pt.size()); }
+            }
+        }
+        for (int i = 0; i < (int)l_pt.size(); i++) pt_l[l_pt[i]] = i;
+    }
     // device edge order: grouped by landmark (so a landmark's edges are contiguous and l_edges is the identity), insertion
     // order inside a group; the reference's activeEdges order (insertion) is restored on the host when outliers are reported
     if (!h->points_fixed)
@@ -2668,6 +2703,8 @@ static int ba_build_structure(mage_ba_t h)
     std::vector<ushort2> bpairs;
     if (!h->points_fixed && Kf >= 1 && Kf <= kFastMaxKf && Pl >= 1 && nblk <= kFastItems && !getenv("MAGE_BA_NO_FAST")) {
         fast = 1;
+        if (!bal_batch_ptr.empty()) batch_ptr = bal_batch_ptr;
+        else {
         batch_ptr.push_back(0);
         for (int li = 0, e_in = 0, l_in = 0; li < Pl; li++) {
             const int ne = l_ptr[li + 1] - l_ptr[li];
@@ -2676,6 +2713,7 @@ static int ba_build_structure(mage_ba_t h)
             e_in += ne; l_in++;
         }
         batch_ptr.push_back(Pl);
+        }
     }
     if (fast) {
         nb = (int)batch_ptr.size() - 1;
