@@ -462,11 +462,11 @@ def bench_ba(args, world, rank, dist):
                       "mode": "batched: one CTA per problem, one persistent launch per call", "timer": "host clock around the synchronous C-ABI call, median of 3 fresh sets"},
            "single_problem": {"value": 10.0 / statistics.median(single), "unit": "LM iterations/s", "ms_per_call": 1e3 * statistics.median(single)},
            "roofline": {"kernel": "k_ba_step", "bound": "hbm", "achieved": trial_rate * 0.6e6 / 1e9, "peak": hbm, "unit": "GB/s",
-                        "frac": trial_rate * 0.6e6 / 1e9 / hbm, "traffic": 3.52e6, "traffic_unit": "bytes per lambda trial and problem (ncu, profiles/)",
+                        "frac": trial_rate * 0.6e6 / 1e9 / hbm, "traffic": 3.47e6, "traffic_unit": "bytes per lambda trial and problem (ncu, profiles/)",
                         "peak_source": peak_src, "algorithmic_bytes_per_trial": 0.6e6,
                         "fp64": {"achieved": trial_rate * 9.5e6 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": trial_rate * 9.5e6 / 1e12 / fp64_peak,
                                  "flop_per_trial": 9.5e6},
-                        "note": "latency-bound on dependent global loads at 16 warps/SM (ncu: IPC 0.8, FP64 pipe 22 % busy, DRAM 30 %)"},
+                        "note": "bound by the L1/shared-memory data path and load latency at 16 warps/SM (ncu: L1TEX 66 %, IPC 0.9, FP64 pipe 23 % busy, DRAM 28 %)"},
            "dtype": "f64"}
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_ba_baseline(parallel=False)
