@@ -50,6 +50,14 @@ namespace mage_b200
         int m_width{ 0 }, m_height{ 0 };
     };
 
+    // OrbFeatureDetector::UndistortKeypoints(inoutKeypoints, distortedCalibration, undistortedCalibration, memory)
+    // (Image/OrbFeatureDetector.cpp:30-62): calibrations as mage_camera_calibration = GetCameraMatrix() + GetCVDistortionCoeffs()
+    inline void UndistortKeypoints(mage_keypoint* inoutKeypoints, int count, const mage_camera_calibration& distortedCalibration,
+                                   const mage_camera_calibration& undistortedCalibration)
+    {
+        Check(mage_undistort_keypoints(inoutKeypoints, count, &distortedCalibration, &undistortedCalibration, nullptr));
+    }
+
     // Match(imageA, imageB, imageAMask, imageBMask, ..., maxHammingDist, minHammingDifference, goodMatches) -> count
     inline unsigned int Match(mage_matcher_t matcher, const std::uint8_t* descA, int nA, const std::uint8_t* maskA, const std::uint8_t* descB, int nB,
                               const std::uint8_t* maskB, int maxHammingDist, int minHammingDifference, std::vector<mage_dmatch>& goodMatches)

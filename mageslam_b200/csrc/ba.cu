@@ -1387,28 +1387,6 @@ __device__ void g_finish_cams(const BaDev& p, int parts, int tid, int nt)
         }
     }
 }
-// push + update in one pass (ref base_vertex.h:92-94, sparse_optimizer.cpp:433-446): the old state goes to the backup buffers
-__device__ double g_backup_update(const BaDev& p, double lambda, int tid, int nt)     // returns this thread's share of computeScale (ref levenberg.cpp:167-174)
-{
-    double acc = 0;
-    for (int j = tid; j < p.n; j += nt) { const double xj = p.x[j]; acc += xj * (lambda * xj + p.bp[j]); }
-    for (int i = tid; i < p.Kf; i += nt) {
-        const int c = p.c_cam[i];
-#pragma unroll
-        for (int j = 0; j < 4; j++) p.cam_bak[7 * i + j] = p.cam_q[4 * c + j];
-#pragma unroll
-        for (int j = 0; j < 3; j++) p.cam_bak[7 * i + 4 + j] = p.cam_t[3 * c + j];
-        pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i);
-    }
-    for (int i = tid; i < p.Pl * 3; i += nt) {
-        double* X = p.pt_X + 3 * (size_t)p.l_pt[i / 3] + i % 3;
-        const double old = *X, xj = p.x[p.n + i];
-        p.pt_bak[i] = old;
-        *X = old + xj;
-        acc += xj * (lambda * xj + p.bl[i]);
-    }
-    return acc;
-}
 // W = w Jj^T Ji of one edge from its record (6x3 row-major)
 __device__ __forceinline__ void g_edge_W(const BaDev& p, const double* __restrict__ camR, const double* __restrict__ rec, int e, int c, double* W)
 {
@@ -1652,27 +1630,6 @@ __device__ void g_update_cams(const BaDev& p, int tid, int nt)
 #pragma unroll
         for (int j = 0; j < 3; j++) p.cam_bak[7 * i + 4 + j] = p.cam_t[3 * c + j];
         pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i);
-    }
-}
-__device__ void g_backsub(const BaDev& p, const double* __restrict__ rec, int tid, int nt)
-{
-    for (int li = tid; li < p.Pl; li += nt) {
-        double c0 = p.bl[3 * li], c1 = p.bl[3 * li + 1], c2 = p.bl[3 * li + 2];
-        const int k0 = p.l_ptr[li], k1 = p.l_ptr[li + 1];
-#pragma unroll 2
-        for (int e = k0; e < k1; e++) {
-            const int c = p.e_cam[e], hj = p.cam_h[c];
-            if (hj < 0) continue;
-            double W[18];
-            g_edge_W(p, p.cam_R, rec, e, c, W);
-            const double* xp = p.x + 6 * hj;
-#pragma unroll
-            for (int r = 0; r < 6; r++) { const double xr = xp[r]; c0 -= W[r * 3] * xr; c1 -= W[r * 3 + 1] * xr; c2 -= W[r * 3 + 2] * xr; }
-        }
-        const double* D = p.Dinv + 9 * (size_t)li;
-        p.x[p.n + 3 * li] = D[0] * c0 + D[1] * c1 + D[2] * c2;
-        p.x[p.n + 3 * li + 1] = D[3] * c0 + D[4] * c1 + D[5] * c2;
-        p.x[p.n + 3 * li + 2] = D[6] * c0 + D[7] * c1 + D[8] * c2;
     }
 }
 

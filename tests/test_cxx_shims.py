@@ -22,6 +22,7 @@ def _compile(src, incs):
 def test_orb_detector_shim_compiles():
     _compile('#include "mageslam_b200/OrbDetector.hpp"\n'
              'int f(){ mage_b200::OrbDetector d(7,2000,1.2f,8,31,10,true,1.5f,0.9f,20,1.1f,2.0f,32,32); std::vector<mage_dmatch> m; '
+             'mage_camera_calibration c{}; mage_keypoint k{}; mage_b200::UndistortKeypoints(&k, 1, c, c); '
              'return (int)sizeof(d) + (int)mage_b200::Match(nullptr,nullptr,0,nullptr,nullptr,0,nullptr,30,1,m); }\n',
              [os.path.join(ROOT, "include")])
 
