@@ -2080,6 +2080,7 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
     double* Ls = Ys + kLdltTile * (kLdltNB + 1);           // [kLdltTile][kLdltNB + 1]
     double* Dk = Ls + kLdltTile * (kLdltNB + 1);           // [kLdltNB][kLdltNB] diagonal block (L below the diagonal, D on it)
     __shared__ int s_bad;
+    __shared__ double s_col[2 * (kLdltNB + 1)];
     if (tid == 0) s_bad = 0;
     for (int k0 = 0; k0 < n; k0 += kLdltNB) {
         const int nb = min(kLdltNB, n - k0);
@@ -2087,21 +2088,8 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
         if (blockIdx.x == 0) {
             for (int i = tid; i < nb * nb; i += nt) Dk[i] = S[(size_t)(k0 + i / nb) * n + k0 + i % nb];
             __syncthreads();
-            for (int k = 0; k < nb; k++) {
-                const double d = Dk[k * nb + k];
-                if (d < 0 && tid == 0) s_bad = 1;
-                const bool valid = fabs(d) > 0;
-                const double inv_d = valid ? 1.0 / d : 0.0;
-                __syncthreads();
-                if (valid)
-                    for (int t = tid; t < (nb - k - 1) * (nb - k - 1); t += nt) {
-                        const int i = k + 1 + t / (nb - k - 1), j = k + 1 + t % (nb - k - 1);
-                        if (j <= i) Dk[i * nb + j] -= Dk[i * nb + k] * inv_d * Dk[j * nb + k];
-                    }
-                __syncthreads();
-                if (valid) for (int i = k + 1 + tid; i < nb; i += nt) Dk[i * nb + k] *= inv_d;
-                __syncthreads();
-            }
+            ldlt_factor_regs<2>(Dk, nb, &s_bad, s_col);         // 2 x 2 register blocks, one barrier per column (nb <= 32, 256 threads)
+            __syncthreads();
             for (int i = tid; i < nb * nb; i += nt) if (i % nb <= i / nb) S[(size_t)(k0 + i / nb) * n + k0 + i % nb] = Dk[i];
             if (tid == 0 && s_bad) *okflag = 0;
         }
@@ -2183,24 +2171,54 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
 // block 0: L y = b (row-oriented dot products), D, L^T x = y (row k of L is column k of L^T); x -> p.x[0..n)
 __device__ void tri_solve_big(const BaDev& p, double* sh)
 {
+    // Blocked substitution, 32 unknowns at a time: the 32 x 32 triangle on the diagonal is solved by one warp with the right-hand
+    // side in registers (pivots broadcast by shuffle), then every thread applies the solved block to its rows (forward) / columns
+    // (backward) -- two CTA barriers per 32 unknowns instead of one block-wide reduction per unknown.
     const int n = p.n, tid = threadIdx.x, nt = blockDim.x;
     const double* S = p.S;
     double* y = p.bs;
-    for (int i = 0; i < n; i++) {
-        double acc = 0;
-        const double* row = S + (size_t)i * n;
-        for (int k = tid; k < i; k += nt) acc += row[k] * y[k];
-        const double s = block_sum(acc, sh);
-        if (tid == 0) y[i] -= s;
+    __shared__ double yb[32];
+    (void)sh;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const int nb = min(32, n - k0);
+        if (tid < 32) {
+            double yv = tid < nb ? y[k0 + tid] : 0.0;
+            for (int c = 0; c < nb; c++) {
+                const double yc = __shfl_sync(0xffffffffu, yv, c);
+                if (tid > c && tid < nb) yv -= S[(size_t)(k0 + tid) * n + k0 + c] * yc;
+            }
+            if (tid < nb) { y[k0 + tid] = yv; yb[tid] = yv; }
+        }
+        __syncthreads();
+        for (int i = k0 + nb + tid; i < n; i += nt) {
+            const double* row = S + (size_t)i * n + k0;
+            double acc = 0;
+#pragma unroll 8
+            for (int j = 0; j < nb; j++) acc += row[j] * yb[j];
+            y[i] -= acc;
+        }
         __syncthreads();
     }
     const double tol = 1.0 / DBL_MAX;
     for (int i = tid; i < n; i += nt) { const double d = S[(size_t)i * n + i]; y[i] = (fabs(d) > tol) ? y[i] / d : 0.0; }
     __syncthreads();
-    for (int k = n - 1; k >= 0; k--) {
-        const double xk = y[k];
-        const double* row = S + (size_t)k * n;
-        for (int i = tid; i < k; i += nt) y[i] -= row[i] * xk;
+    for (int k0 = ((n - 1) / 32) * 32; k0 >= 0; k0 -= 32) {
+        const int nb = min(32, n - k0);
+        if (tid < 32) {
+            double yv = tid < nb ? y[k0 + tid] : 0.0;
+            for (int c = nb - 1; c >= 0; c--) {
+                const double xc = __shfl_sync(0xffffffffu, yv, c);
+                if (tid < c) yv -= S[(size_t)(k0 + c) * n + k0 + tid] * xc;
+            }
+            if (tid < nb) { y[k0 + tid] = yv; yb[tid] = yv; }
+        }
+        __syncthreads();
+        for (int i = tid; i < k0; i += nt) {
+            double acc = 0;
+#pragma unroll 8
+            for (int j = 0; j < nb; j++) acc += S[(size_t)(k0 + j) * n + i] * yb[j];
+            y[i] -= acc;
+        }
         __syncthreads();
     }
     for (int i = tid; i < n; i += nt) p.x[i] = y[i];

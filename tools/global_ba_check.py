@@ -18,3 +18,8 @@ for s in range(STEPS):
     print("step %d: gpu %.1f ms  cpu %.1f ms  mean %.6f / %.6f  lambda %.6g / %.6g  relF pos %.2e rot %.2e pts %.2e  stats %s" % (
         s, (t1 - t0) * 1e3, (t2 - t1) * 1e3, mg, mr, gpu.GetCurrentLambda(), chk.GetCurrentLambda(), rel_frobenius(pc, pr), rel_frobenius(rc, rr),
         rel_frobenius(gpu.points(), chk.points()), gpu.stats()))
+    import ctypes as _C, numpy as _np
+    from mageslam_b200 import _lib as _L
+    ph = _np.zeros(16, _np.int64)
+    _L.lib().mage_ba_debug_phase_ns(gpu._h, ph.ctypes.data_as(_C.c_void_p))
+    print('      cumulative phase us (errors+chi2, build, schur_pts, schur_prod, solve(after assemble), sync, backsub+update, errors+scale, assemble):', [round(float(x) / 1e3, 1) for x in ph[:9]])
