@@ -164,6 +164,24 @@ def test_step_many_equals_individual_steps_and_is_reproducible():
         assert rel_frobenius(cs, cm) < 1e-9 and rel_frobenius(ps, pm) < 1e-9
 
 
+def test_step_many_general_path_matches_reference():
+    """windows the local-window fast path does not take (more than 10 free cameras; fixed points) go through the one-CTA kernel's
+    general phases: same parity bar against the reference"""
+    hub = [1.8] * 3
+    for kw, pf in (({"K": 16, "P": 600, "obs_per_point": 5, "seed": 41}, False), ({"K": 14, "P": 500, "obs_per_point": 4, "seed": 42}, False),
+                   ({"K": 3, "P": 300, "obs_per_point": 3, "seed": 43}, True)):
+        prob = synth.ba_problem(**kw)
+        gpu = BundlerLib(BundlerParameters(pf)).load(prob)
+        chk = best_checker(pf).load(prob)
+        for call in range(3):
+            StepMany([gpu], hub, 1e9)
+            chk.StepBundleAdjustment(hub, 1e9)
+            pc, rc = gpu.poses(); pr, rr = chk.poses()
+            assert rel_frobenius(pc, pr) < TOL and rel_frobenius(rc, rr) < TOL, (kw, call)
+            if not pf:
+                assert rel_frobenius(gpu.points(), chk.points()) < TOL, (kw, call)
+
+
 def test_degenerate_inputs():
     prob = synth.ba_problem(K=4, P=40, obs_per_point=2, seed=1)
     gpu = BundlerLib().load(prob)
