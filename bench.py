@@ -356,7 +356,7 @@ def run_ours(args):
     if dom == "k_fast":
         roofline["note"] = ("integer-ALU bound, not HBM bound: ncu (profiles/README.md) has the ALU pipe at 78 % and the issue slots at 69 % of peak "
                             "with DRAM at 2 %; traffic = algorithmic bytes (no re-reads)")
-    launches_per_step = (NLEVELS - 1) + 1 + 1 + 1 + 1 + 2
+    launches_per_step = (NLEVELS - 1) + 2 + 1 + 1 + 1 + 2          # resize x7, blur (interior + edges), FAST, select, orient+describe, match (dir + emit)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
