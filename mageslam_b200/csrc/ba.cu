@@ -12,6 +12,8 @@
 
 #include <cooperative_groups.h>
 
+#include <chrono>
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -2529,6 +2531,7 @@ static int ba_upload_state(mage_ba_t h)
     // camera / point state and intrinsics live in one arena sized at first upload (pools are allocated once, ref :198-230)
     DeviceArena& A = h->state;
     if (!A.base) {
+        A.pooled = true;
         size_t oq = A.reserve(sizeof(double) * 4 * h->K), ot = A.reserve(sizeof(double) * 3 * h->K);
         size_t of = A.reserve(sizeof(double) * h->K), ox = A.reserve(sizeof(double) * h->K), oy = A.reserve(sizeof(double) * h->K);
         size_t op = A.reserve(sizeof(double) * 3 * h->P);
@@ -2555,6 +2558,10 @@ static int ba_upload_state(mage_ba_t h)
 // buildStructure, done on the host whenever the edge set changed (BundlerLib.cpp:156-166); uploads the index structure.
 static int ba_build_structure(mage_ba_t h)
 {
+    const bool timing = getenv("MAGE_BA_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto t_begin = tnow();
+    auto mark = [&](const char* what) { if (timing) { auto t = tnow(); fprintf(stderr, "[ba_build_structure] %-22s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t - t_begin).count()); t_begin = t; } };
     h->active.clear();
     std::vector<std::pair<long, int>> order;
     for (int e = 0; e < h->E; e++) {
@@ -2582,8 +2589,9 @@ static int ba_build_structure(mage_ba_t h)
     if (!h->points_fixed) {     // point vertex ids count down (ref BundlerLib.cpp:210-218): Hessian order = descending index
         for (int i = h->P - 1; i >= 0; i--) if (ptA[i]) l_pt.push_back(i);
         const int Kf0 = (int)c_cam.size();
-        if (Kf0 >= 1 && Kf0 <= kFastMaxKf && !l_pt.empty() && !getenv("MAGE_BA_NO_FAST") && !getenv("MAGE_BA_NO_BALANCE")) {
-            // Local-window fast path: the landmark order is free (it only fixes summation orders), so landmarks are dealt into the
+        if (Kf0 >= 1 && Kf0 <= kFastMaxKf && !l_pt.empty() && !getenv("MAGE_BA_NO_FAST") && getenv("MAGE_BA_BALANCE")) {
+            // Opt-in (MAGE_BA_BALANCE=1): measured +0.4 % on the batched kernel for ~0.7 ms of host time per structure build, which a
+            // one-shot local-BA window never earns back. The landmark order is free (it only fixes summation orders), so landmarks are dealt into the
             // shared-memory batches such that every reduced-system block gets about the same number of (edge, edge) products in every
             // batch -- the threads of a warp own different blocks and run the longest list of the warp, batch by batch.
             std::vector<std::vector<int>> pc(h->P);
@@ -2619,6 +2627,7 @@ static int ba_build_structure(mage_ba_t h)
     // order inside a group; the reference's activeEdges order (insertion) is restored on the host when outliers are reported
     if (!h->points_fixed)
         std::stable_sort(h->active.begin(), h->active.end(), [&](int a, int b) { return pt_l[h->obs[a].pt] < pt_l[h->obs[b].pt]; });
+    mark("order + balance");
     const int Kf = (int)c_cam.size(), Pl = (int)l_pt.size(), n = 6 * Kf;
     h->useless = (Kf + Pl) == 0;
     h->dirty = false;
@@ -2669,6 +2678,7 @@ static int ba_build_structure(mage_ba_t h)
         pairs.insert(pairs.end(), kv.second.begin(), kv.second.end());
         blk_ptr.push_back((int)pairs.size());
     }
+    mark("csr + pair lists");
     const int nblk = (int)blk_ij.size() / 2;
     // local-window fast path (see g_schur): batches of landmarks, (block, part) items, pair lists per (batch, block)
     int fast = 0, nb = 0, nitems = 0;
@@ -2722,8 +2732,9 @@ static int ba_build_structure(mage_ba_t h)
     const int cam_parts = std::max(1, std::min(16, 256 / std::max(Kf, 1)));     // (camera, part) reduction items
     const int schur_parts = kSchurParts;
 
+    mark("fast-path tables");
     DeviceArena& W = h->work;
-    W.release(); W = DeviceArena();
+    W.release(); W = DeviceArena(); W.pooled = true;        // the handle's calls are synchronous: nothing in flight uses the old arena
     auto rI = [&](size_t cnt) { return W.reserve(sizeof(int) * std::max<size_t>(cnt, 1)); };
     auto rD = [&](size_t cnt) { return W.reserve(sizeof(double) * std::max<size_t>(cnt, 1)); };
     size_t o_camh = rI(h->K), o_ecam = rI(Ea), o_ept = rI(Ea), o_el = rI(Ea), o_euv = rD(2 * (size_t)Ea), o_einfo = rD(Ea);
@@ -2742,6 +2753,7 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_Wk = rD(big ? (size_t)n * kLdltNB : 1);
     size_t o_tdef = W.reserve(sizeof(int4) * std::max(nT, 1)), o_tmeas = rD(8 * (size_t)nT), o_terr = rD(6 * (size_t)nT), o_tJ = rD(72 * (size_t)nT);
     MAGE_CUDA_TRY(W.commit());
+    mark("cudaMalloc");
     MAGE_CUDA_TRY(cudaMemsetAsync(W.base, 0, W.size, h->stream));
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
         return bytes ? cudaMemcpyAsync(W.base + off, src, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
@@ -2782,8 +2794,10 @@ static int ba_build_structure(mage_ba_t h)
     d.big = big; d.Wk = W.at<double>(o_Wk);
     d.nT = nT; d.t_def = W.at<int4>(o_tdef); d.t_meas = W.at<double>(o_tmeas); d.t_err = W.at<double>(o_terr); d.t_J = W.at<double>(o_tJ);
     MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
+    mark("enqueue uploads");
     // pageable staging vectors go out of scope on return: make sure the copies have been consumed
     MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    mark("sync");
     return MAGE_OK;
 }
 
@@ -2821,7 +2835,7 @@ extern "C" void mage_ba_destroy(mage_ba_t h)
     if (!h) return;
     cudaStreamSynchronize(h->stream);
     h->state.release(); h->work.release();
-    if (h->d_huber) cudaFree(h->d_huber);
+    if (h->d_huber) cudaFreeAsync(h->d_huber, h->stream);
     if (h->d_table) cudaFree(h->d_table);
     if (h->d_ctl_table) cudaFree(h->d_ctl_table);
     cudaStreamDestroy(h->stream);
@@ -2993,10 +3007,10 @@ static int ba_prepare(mage_ba_t h, const float* huber, int n_iters, bool upload_
     if (!h->state_uploaded) { int rc = ba_upload_state(h); if (rc) return rc; }
     if (h->dirty) { int rc = ba_build_structure(h); if (rc) return rc; }
     if (h->useless) return MAGE_OK;
-    if (upload_huber && n_iters > h->huber_cap) {
-        if (h->d_huber) cudaFree(h->d_huber);
+    if (upload_huber && n_iters > h->huber_cap) {                      // stream-ordered pool: no cudaMalloc latency per new window
+        if (h->d_huber) cudaFreeAsync(h->d_huber, h->stream);
         h->huber_cap = std::max(16, n_iters);
-        MAGE_CUDA_TRY(cudaMalloc(&h->d_huber, sizeof(float) * h->huber_cap));
+        MAGE_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&h->d_huber), sizeof(float) * h->huber_cap, h->stream));
     }
     if (upload_huber && n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, h->stream));
     if (h->iteration_reset) {
@@ -3097,9 +3111,9 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
     mage_ba_t lead = live.empty() ? hs[0] : hs[live[0]];
     if (!live.empty()) {
         if (n_iters > lead->huber_cap) {
-            if (lead->d_huber) cudaFree(lead->d_huber);
+            if (lead->d_huber) cudaFreeAsync(lead->d_huber, lead->stream);
             lead->huber_cap = std::max(16, n_iters);
-            MAGE_CUDA_TRY(cudaMalloc(&lead->d_huber, sizeof(float) * lead->huber_cap));
+            MAGE_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&lead->d_huber), sizeof(float) * lead->huber_cap, lead->stream));
         }
         if (n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(lead->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, lead->stream));
     }

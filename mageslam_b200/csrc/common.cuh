@@ -32,14 +32,38 @@ void set_error(const char* fmt, ...);
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
-// Simple bump allocator over one cudaMalloc'ed arena (all scratch of a handle lives in one allocation).
+// One device allocation carved into aligned sub-buffers. pooled = true takes it from the stream-ordered default memory pool
+// (cudaMallocAsync, release threshold raised so freed blocks stay cached): a few microseconds instead of the ~1-4 ms cudaFree +
+// cudaMalloc of a multi-megabyte block cost when a new problem is set up per call (a BundlerLib instance per local-BA window).
+// A pooled arena must only be released when the work using it has been synchronised (cudaFreeAsync does not wait like cudaFree).
 struct DeviceArena {
     uint8_t* base = nullptr;
     size_t size = 0, used = 0;
+    bool pooled = false;
     size_t reserve(size_t bytes, size_t align = 256) { used = align_up(used, align); size_t o = used; used += bytes; return o; }
-    cudaError_t commit() { size = used; return cudaMalloc(&base, size ? size : 256); }
+    cudaError_t commit()
+    {
+        size = used;
+        if (!pooled) return cudaMalloc(&base, size ? size : 256);
+        static bool pool_ready = false;
+        if (!pool_ready) {
+            int dev = 0; cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready = true;
+        }
+        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&base), size ? size : 256, static_cast<cudaStream_t>(0));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(0));       // usable from any stream afterwards
+        return e;
+    }
     template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
-    void release() { if (base) cudaFree(base); base = nullptr; }
+    void release()
+    {
+        if (base) { if (pooled) cudaFreeAsync(base, static_cast<cudaStream_t>(0)); else cudaFree(base); }
+        base = nullptr;
+    }
 };
 
 // Optional per-kernel timing (CUDA events on the launching stream), used by bench.py for the live roofline figure.
