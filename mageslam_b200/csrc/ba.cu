@@ -2625,8 +2625,13 @@ static int ba_build_structure(mage_ba_t h)
     }
     // device edge order: grouped by landmark (so a landmark's edges are contiguous and l_edges is the identity), insertion
     // order inside a group; the reference's activeEdges order (insertion) is restored on the host when outliers are reported
-    if (!h->points_fixed)
-        std::stable_sort(h->active.begin(), h->active.end(), [&](int a, int b) { return pt_l[h->obs[a].pt] < pt_l[h->obs[b].pt]; });
+    if (!h->points_fixed) {       // stable counting sort by landmark (every active edge's point is a landmark when points are free)
+        std::vector<int> start(l_pt.size() + 1, 0), sorted(h->active.size());
+        for (int e : h->active) start[pt_l[h->obs[e].pt] + 1]++;
+        for (size_t i = 0; i < l_pt.size(); i++) start[i + 1] += start[i];
+        for (int e : h->active) sorted[start[pt_l[h->obs[e].pt]]++] = e;
+        h->active.swap(sorted);
+    }
     mark("order + balance");
     const int Kf = (int)c_cam.size(), Pl = (int)l_pt.size(), n = 6 * Kf;
     h->useless = (Kf + Pl) == 0;
@@ -2658,25 +2663,45 @@ static int ba_build_structure(mage_ba_t h)
         if (e_l[a] >= 0) l_edges[lf[e_l[a]]++] = a;
         if (cam_h[e_cam[a]] >= 0) c_edges[cf[cam_h[e_cam[a]]]++] = a;
     }
-    // upper blocks of the reduced system and their (edge, edge) pair lists; every diagonal block exists
-    std::map<std::pair<int, int>, std::vector<int2>> blocks;
-    for (int i = 0; i < Kf; i++) blocks[{i, i}];
-    for (int li = 0; li < Pl; li++)
-        for (int k1 = l_ptr[li]; k1 < l_ptr[li + 1]; k1++) {
-            const int a1 = l_edges[k1], i1 = cam_h[e_cam[a1]];
-            if (i1 < 0) continue;
-            for (int k2 = l_ptr[li]; k2 < l_ptr[li + 1]; k2++) {
-                const int a2 = l_edges[k2], i2 = cam_h[e_cam[a2]];
-                if (i2 < 0 || i2 < i1) continue;
-                blocks[{i1, i2}].push_back(make_int2(a1, a2));
-            }
-        }
+    // upper blocks of the reduced system and their (edge, edge) pair lists; every diagonal block exists. Blocks in (i1, i2)
+    // lexicographic order, pairs of a block in landmark order -- two counting passes over a Kf x Kf table (a std::map keyed by the
+    // block when the table would be unreasonably large)
     std::vector<int> blk_ij, blk_ptr(1, 0);
     std::vector<int2> pairs;
-    for (auto& kv : blocks) {
-        blk_ij.push_back(kv.first.first); blk_ij.push_back(kv.first.second);
-        pairs.insert(pairs.end(), kv.second.begin(), kv.second.end());
-        blk_ptr.push_back((int)pairs.size());
+    auto for_each_pair = [&](auto&& fn) {
+        for (int li = 0; li < Pl; li++)
+            for (int k1 = l_ptr[li]; k1 < l_ptr[li + 1]; k1++) {
+                const int a1 = l_edges[k1], i1 = cam_h[e_cam[a1]];
+                if (i1 < 0) continue;
+                for (int k2 = l_ptr[li]; k2 < l_ptr[li + 1]; k2++) {
+                    const int a2 = l_edges[k2], i2 = cam_h[e_cam[a2]];
+                    if (i2 < 0 || i2 < i1) continue;
+                    fn(i1, i2, a1, a2);
+                }
+            }
+    };
+    if ((size_t)Kf * Kf <= (size_t)1 << 22) {
+        std::vector<int> cnt((size_t)Kf * Kf, 0), slot((size_t)Kf * Kf, -1);
+        for_each_pair([&](int i1, int i2, int, int) { cnt[(size_t)i1 * Kf + i2]++; });
+        for (int i1 = 0; i1 < Kf; i1++)
+            for (int i2 = i1; i2 < Kf; i2++) {
+                const size_t q = (size_t)i1 * Kf + i2;
+                if (cnt[q] == 0 && i1 != i2) continue;
+                slot[q] = blk_ptr.back();
+                blk_ij.push_back(i1); blk_ij.push_back(i2);
+                blk_ptr.push_back(blk_ptr.back() + cnt[q]);
+            }
+        pairs.resize((size_t)blk_ptr.back());
+        for_each_pair([&](int i1, int i2, int a1, int a2) { pairs[(size_t)slot[(size_t)i1 * Kf + i2]++] = make_int2(a1, a2); });
+    } else {
+        std::map<std::pair<int, int>, std::vector<int2>> blocks;
+        for (int i = 0; i < Kf; i++) blocks[{i, i}];
+        for_each_pair([&](int i1, int i2, int a1, int a2) { blocks[{i1, i2}].push_back(make_int2(a1, a2)); });
+        for (auto& kv : blocks) {
+            blk_ij.push_back(kv.first.first); blk_ij.push_back(kv.first.second);
+            pairs.insert(pairs.end(), kv.second.begin(), kv.second.end());
+            blk_ptr.push_back((int)pairs.size());
+        }
     }
     mark("csr + pair lists");
     const int nblk = (int)blk_ij.size() / 2;
