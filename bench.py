@@ -471,7 +471,10 @@ def bench_ba(args, world, rank, dist):
     out = {"metric": "local_ba_lm_iters_per_sec", "unit": "LM iterations/s", "value": world * iters / float(t.item()),
            "config": {"workload": "local BA 10 KF / 2000 pts / 8000 obs, Huber 1.8, 10 LM iterations per call", "problems_per_gpu": nprob,
                       "mode": "batched: one CTA per problem, one persistent launch per call", "timer": "host clock around the synchronous C-ABI call, median of 3 fresh sets"},
-XX: {"kernel": "k_ba_step", "bound": "hbm", "achieved": trial_rate * 0.6e6 / 1e9, "peak": hbm, "unit": "GB/s",
+           "single_problem": {"value": 10.0 / statistics.median(single), "unit": "LM iterations/s", "ms_per_call": 1e3 * statistics.median(single),
+                              "fresh_window_ms": 1e3 * statistics.median(fresh),
+                              "fresh_window_note": "new BundlerLib instance: bulk set-up + structure build + 10 LM iterations + read-back of the mean error, host clock"},
+           "roofline": {"kernel": "k_ba_step", "bound": "hbm", "achieved": trial_rate * 0.6e6 / 1e9, "peak": hbm, "unit": "GB/s",
                         "frac": trial_rate * 0.6e6 / 1e9 / hbm, "traffic": 3.47e6, "traffic_unit": "bytes per lambda trial and problem (ncu, profiles/)",
                         "peak_source": peak_src, "algorithmic_bytes_per_trial": 0.6e6,
                         "fp64": {"achieved": trial_rate * 9.5e6 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": trial_rate * 9.5e6 / 1e12 / fp64_peak,
