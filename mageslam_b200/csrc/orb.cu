@@ -1211,6 +1211,11 @@ struct mage_orb_s {
     // when the pixels come from a caller's device buffer. Unavailable (=> k_fast) if the driver entry point cannot be resolved.
     FastMaps maps;
     bool tma_ok = false, maps_lvl0_foreign = false;
+    // host path: the kernel chain of a call (memset + 12 launches + the blur fork/join) is captured once per (frames, capacity) and
+    // replayed as one CUDA graph -- per-frame calls are launch-latency bound
+    struct ChainGraph { int n, cap; cudaGraphExec_t exec; };
+    std::vector<ChainGraph> graphs;
+    bool graphs_off = false;
     int sm_count = 0;
     void* encode_fn = nullptr;
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
@@ -1467,6 +1472,7 @@ extern "C" void mage_orb_destroy(mage_orb_t h)
     if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
+    for (auto& gph : h->graphs) cudaGraphExecDestroy(gph.exec);
     h->arena.release();
     delete h;
 }
@@ -1575,7 +1581,27 @@ extern "C" int mage_orb_detect_and_compute_batch(mage_orb_t h, const uint8_t* im
     mage_keypoint* d_kps = h->arena.at<mage_keypoint>(h->off_stage_kps);
     uint8_t* d_desc = h->arena.at<uint8_t>(h->off_stage_desc);
     int* d_counts = h->arena.at<int>(h->off_stage_counts);
-    int rc = orb_launch(h, h->b, n, d_kps, d_desc, cap, d_counts, s);
+    int rc = MAGE_OK;
+    cudaGraphExec_t exec = nullptr;
+    if (!h->graphs_off && !prof_enabled()) {
+        for (auto& gph : h->graphs) if (gph.n == n && gph.cap == cap) exec = gph.exec;
+        if (!exec) {
+            static const bool env_off = getenv("MAGE_ORB_GRAPH") && atoi(getenv("MAGE_ORB_GRAPH")) == 0;
+            cudaGraph_t graph = nullptr;
+            if (env_off || cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) h->graphs_off = true;
+            else {
+                rc = orb_launch(h, h->b, n, d_kps, d_desc, cap, d_counts, s);
+                const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+                if (rc != MAGE_OK || ce != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { exec = nullptr; h->graphs_off = true; }
+                if (graph) cudaGraphDestroy(graph);
+                if (exec) h->graphs.push_back({n, cap, exec});
+                cudaGetLastError();
+                rc = MAGE_OK;
+            }
+        }
+    }
+    if (exec) { MAGE_CUDA_TRY(cudaGraphLaunch(exec, s)); h->last_n = n; }
+    else rc = orb_launch(h, h->b, n, d_kps, d_desc, cap, d_counts, s);
     if (rc != MAGE_OK) return rc;
     if (cap == capacity) {
         MAGE_CUDA_TRY(cudaMemcpyAsync(kps, d_kps, sizeof(mage_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, s));
