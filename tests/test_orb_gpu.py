@@ -242,3 +242,34 @@ def test_full_size_properties_1280x720():
     assert len({(float(k["x"]), float(k["y"]), int(k["octave"])) for k in gk}) == 2000   # no duplicates
     ok, od = orc.detect_and_compute(p, img, 1)
     assert_same_features(gk, gd, ok, od, "720p")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_configurations_bit_exact(seed, monkeypatch):
+    """seeded sweep over image sizes, pyramid shapes, thresholds, patch sizes (pre-rotated and generic), blur sizes, orientation on/off,
+    FAST kernels (register-staged / TMA): every configuration must reproduce the oracle's keypoints and descriptors exactly"""
+    rng = np.random.default_rng(1000 + seed)
+    w = int(rng.integers(120, 700)); h = int(rng.integers(100, 520))
+    nlevels = int(rng.integers(1, 7))
+    scale = float(np.float32(rng.choice([1.2, 1.25, 1.5, 2.0, 1.1])))
+    patch = int(rng.choice([31, 31, 15, 15, 9, 21, 25]))
+    p = orc.tier_params(nfeatures=int(rng.integers(50, 1200)), nlevels=nlevels, scale_factor=scale, fast_threshold=int(rng.integers(4, 40)))
+    p.patch_size = patch
+    p.use_orientation = int(rng.integers(0, 2))
+    p.gaussian_kernel_size = int(rng.choice([7, 7, 7, 5, 9, 3, 0]))
+    p.strong_response = max(int(p.fast_threshold) + 1 + int(rng.integers(0, 30)), int(p.strong_response))
+    p.num_cells_x = int(rng.choice([8, 16, 32])); p.num_cells_y = int(rng.choice([8, 16, 32]))
+    # every level must keep a usable interior (the reference asserts on degenerate pyramids)
+    border = int(np.ceil(patch // 2 * np.sqrt(2.0))) if p.use_orientation else patch // 2
+    smallest = min(w, h) / scale ** (nlevels - 1)
+    if smallest < 2 * border + 24:
+        pytest.skip("smallest level would be inside the border")
+    monkeypatch.setenv("MAGE_FAST_TMA", str(seed & 1))
+    kind = seed % 3
+    img = synth.noise_frame(seed, w, h) if kind == 0 else synth.video_frames(1, w, h, seed=seed)[0] if kind == 1 else \
+        np.clip(synth.video_frames(1, w, h, seed=seed)[0].astype(np.int32) // 3 + rng.integers(0, 40, (h, w)), 0, 255).astype(np.uint8)
+    det = make_detector(p)
+    gk, gd = det.DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert_same_features(gk, gd, ok, od, "seed %d (%dx%d L%d s%.2f patch %d orient %d blur %d thr %d)" % (
+        seed, w, h, nlevels, scale, patch, p.use_orientation, p.gaussian_kernel_size, p.fast_threshold))
