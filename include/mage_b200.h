@@ -328,6 +328,9 @@ int  mage_ba_debug_phase_ns(mage_ba_t h, long long phase_ns[16]);
  * mage_ba_step on each. means/outlier outputs are per handle. */
 int  mage_ba_step_many(mage_ba_t* handles, int n_handles, const float* huber_width_per_iteration, int n_iterations,
                        float max_error_square, float* mean_sq_errors);
+/* The observation indices the last mage_ba_step / mage_ba_step_many call removed from this problem (the `outliers` vector of
+ * StepBundleAdjustment, ref BundlerLib.cpp:385-441); returns the total count in *n_outliers even when capacity is smaller. */
+int  mage_ba_last_outliers(mage_ba_t h, unsigned int* outliers, int capacity, int* n_outliers);
 
 #ifdef __cplusplus
 }

@@ -111,6 +111,7 @@ def lib():
         L.mage_ba_get_state_f64.argtypes = [vp, vp, vp]
         L.mage_ba_get_stats.argtypes = [vp, vp]
         L.mage_ba_step_many.argtypes = [vp, ci, vp, ci, cf, vp]
+        L.mage_ba_last_outliers.argtypes = [vp, vp, ci, C.POINTER(ci)]
     _lib = L
     return L
 

@@ -2511,6 +2511,7 @@ struct mage_ba_s {
     int64_t stats[4] = {0, 0, 0, 0};
     BaCtl h_ctl{};                      // host copies of the last call's control block / outlier flags
     std::vector<unsigned char> h_flags;
+    std::vector<unsigned> last_outliers;     // observation indices removed by the last step (also after mage_ba_step_many)
     int coop_blocks = 0;               // > 0: cooperative launch available, grid size to use
     int coop_blocks_max = 0;           // co-resident limit (large problems use the whole chip)
 };
@@ -3081,10 +3082,12 @@ static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, f
             if (flags[a]) flagged.push_back({h->obs[h->active[a]].seq, h->active[a]});
     std::sort(flagged.begin(), flagged.end());                          // the reference walks activeEdges() in insertion order (:387)
     int m = 0;
+    h->last_outliers.clear();
     for (auto& fl : flagged) {
         const int e = fl.second;
         h->obs[e].removed = true; h->dirty = true;                     // removeEdge => m_dirty (ref :112-116, :435-441)
         if (outliers && m < cap) outliers[m] = (unsigned)e;
+        h->last_outliers.push_back((unsigned)e);
         m++;
     }
     *n_out = m;
@@ -3117,6 +3120,15 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
         h->stats[2]++;
     }
     return ba_finish(h, outliers, cap, n_outliers, mean_sq_error);
+}
+
+// the observations the last StepBundleAdjustment / step_many call removed from this problem, in the reference's order
+extern "C" int mage_ba_last_outliers(mage_ba_t h, unsigned int* outliers, int capacity, int* n_outliers)
+{
+    MAGE_REQUIRE(h && n_outliers && (outliers || capacity == 0), MAGE_ERR_INVALID, "mage_ba_last_outliers: bad argument");
+    *n_outliers = (int)h->last_outliers.size();
+    for (int i = 0; i < *n_outliers && i < capacity; i++) outliers[i] = h->last_outliers[i];
+    return MAGE_OK;
 }
 
 extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n_iters, float max_err_sq, float* means)

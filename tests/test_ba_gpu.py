@@ -182,6 +182,32 @@ def test_step_many_general_path_matches_reference():
                 assert rel_frobenius(gpu.points(), chk.points()) < TOL, (kw, call)
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_randomised_windows_match_reference(seed):
+    """seeded sweep over window shapes (cameras, fixed cameras, points, observations per point, outliers + removal, confidence weights, Huber
+    schedules): the batched one-CTA kernel (fast path or general path) and the single-window kernel against the reference, call by call"""
+    rng = np.random.default_rng(500 + seed)
+    K = int(rng.integers(3, 14)); d = int(rng.integers(2, min(K, 7) + 1))
+    kw = dict(K=K, P=int(rng.integers(60, 1200)), obs_per_point=d, seed=600 + seed, n_fixed=int(rng.integers(1, 3)),
+              outlier_frac=float(rng.choice([0.0, 0.0, 0.05])), info_mode=str(rng.choice(["one", "confidence"])))
+    prob = synth.ba_problem(**kw)
+    hub = [float(x) for x in np.linspace(2.5, 1.0, int(rng.integers(1, 6)))]
+    mx = 7.25 if kw["outlier_frac"] > 0 else 1e9
+    solo, many, chk1, chk2 = BundlerLib().load(prob), BundlerLib().load(prob), best_checker().load(prob), best_checker().load(prob)
+    rep = run_side_by_side(solo, chk1, hub, mx, 3, tag="solo %s" % kw)
+    assert max(max(r) for r in rep) < TOL
+
+    class Many:          # StepMany behind the single-problem interface of run_side_by_side
+        last_outliers = np.zeros(0, np.int64)
+        def StepBundleAdjustment(self, h, m):
+            mean = float(StepMany([many], h, m)[0]); self.last_outliers = many.last_outliers; return mean
+        def poses(self): return many.poses()
+        def points(self): return many.points()
+        def GetCurrentLambda(self): return many.GetCurrentLambda()
+    rep = run_side_by_side(Many(), chk2, hub, mx, 3, tag="many %s" % kw)
+    assert max(max(r) for r in rep) < TOL
+
+
 def test_degenerate_inputs():
     prob = synth.ba_problem(K=4, P=40, obs_per_point=2, seed=1)
     gpu = BundlerLib().load(prob)
