@@ -92,3 +92,41 @@ def test_pipelined_submit_wait_equals_synchronous_process():
             assert kps[i, :cnt[i]].tobytes() == gk[i, :cnt[i]].tobytes() and np.array_equal(desc[i, :cnt[i]], gd[i, :cnt[i]])
             assert mt[i, :mc[i]].tobytes() == gm[i, :mc[i]].tobytes()
     assert want[1][4][0] > 50                         # the first frame of a later call is matched against the previous call's last frame
+
+
+def test_pipelined_calls_with_varying_frame_counts():
+    """calls of different sizes (fewer frames than the batch, different chunk counts per call) through submit / wait and process"""
+    import torch
+    s = FeatureExtractorSettings.tier(num_features=600, num_levels=4)
+    vid = synth.video_frames(14, 640, 480, seed=8)
+    det = OrbFeatureDetector(s)
+    singles = [det.Process(f) for f in vid]
+    h = torch.from_numpy(vid).pin_memory()
+    fe = FrontEnd(s, 640, 480, batch=5, chunk=2)
+    outs = [fe.alloc_outputs(), fe.alloc_outputs()]
+    sizes = [5, 3, 1, 5]                      # 14 frames
+    starts = np.cumsum([0] + sizes)
+    results = []
+    fe.Submit(h[starts[0]:starts[1]], outs[0])
+    for c in range(1, len(sizes)):
+        fe.Submit(h[starts[c]:starts[c + 1]], outs[c & 1])
+        fe.Wait()
+        results.append([np.copy(a) for a in fe.views(outs[(c - 1) & 1])])
+    fe.Wait()
+    results.append([np.copy(a) for a in fe.views(outs[(len(sizes) - 1) & 1])])
+    for c, (kps, desc, cnt, mt, mc) in enumerate(results):
+        for i in range(sizes[c]):
+            g = starts[c] + i
+            sk, sd = singles[g]
+            assert cnt[i] == len(sk) and kps[i, :cnt[i]].tobytes() == sk.tobytes() and np.array_equal(desc[i, :cnt[i]], sd), (c, i)
+            if g == 0:
+                assert mc[i] == 0
+            else:
+                ref = Match(sd, singles[g - 1][1], None, None, 30, 1)
+                assert tuples(mt[i, :mc[i]]) == tuples(ref), (c, i)
+    # the synchronous call after pipelined ones continues the same sequence
+    fe2 = FrontEnd(s, 640, 480, batch=5, chunk=2)
+    o = fe2.alloc_outputs()
+    fe2.Process(h[0:5], o)
+    kps, desc, cnt, mt, mc = fe2.Process(h[5:8], o)
+    assert tuples(mt[0, :mc[0]]) == tuples(Match(singles[5][1], singles[4][1], None, None, 30, 1))
