@@ -22,3 +22,25 @@ bs = [BundlerLib().load(synth.ba_problem(K=5, P=100, obs_per_point=3, seed=i)) f
 print(StepMany(bs, [1.8] * 2, 1e9))
 big = BundlerLib().load(synth.ba_problem(K=60, P=600, obs_per_point=6, seed=4, loop=True)); print(big.StepBundleAdjustment([1.8] * 2, 1e9))
 po = BundlerLib(BundlerParameters(True)).load(synth.ba_problem(K=1, P=100, obs_per_point=1, n_fixed=0, seed=5)); print(po.StepBundleAdjustment([2.0] * 3, 25.0))
+# paths added later in the round: TMA variant of FAST, generic BRIEF pattern, single-level fixed-point blur, undistortion, pipelined front-end,
+# general (materialised) one-CTA BA path, tether edges
+import os
+from mageslam_b200.orb import CameraCalibration, UndistortKeypoints
+os.environ["MAGE_FAST_TMA"] = "1"
+det = OrbFeatureDetector(FeatureExtractorSettings.tier(400, 3)); print(len(det.Process(vid[2])[0]))
+os.environ["MAGE_FAST_TMA"] = "0"
+sg = FeatureExtractorSettings.tier(300, 3); sg.PatchSize = 21
+kg, dg = OrbFeatureDetector(sg).Process(vid[0]); print(len(kg))
+s1 = FeatureExtractorSettings.tier(300, 1)
+print(len(OrbFeatureDetector(s1).Process(synth.video_frames(1, 320, 200, seed=2)[0])[0]))
+print(UndistortKeypoints(np.ascontiguousarray(kg), CameraCalibration(260, 262, 160, 120, [0.1, -0.05, 0.001, -0.002, 0.01]), CameraCalibration(250, 250, 160, 120))[:2]["x"])
+fp = FrontEnd(FeatureExtractorSettings.tier(300, 3), 333, 241, batch=3, chunk=2)
+o2 = [fp.alloc_outputs(pinned=True), fp.alloc_outputs(pinned=True)]
+hv = torch.from_numpy(vid).pin_memory()
+fp.Submit(hv, o2[0]); fp.Submit(hv[:2], o2[1]); fp.Wait(); fp.Wait(); print(fp.views(o2[1])[4][:2])
+gen = [BundlerLib().load(synth.ba_problem(K=13, P=150, obs_per_point=4, seed=7))]; print(StepMany(gen, [1.8] * 2, 1e9))
+from tools.gen_ba_golden import CASES, build_problem
+for name in sorted(CASES):
+    kw, pf, hub, mx, calls = CASES[name]
+    if "tethers" in kw:
+        tb = BundlerLib(BundlerParameters(pf)).load(build_problem(kw)); print(name, tb.StepBundleAdjustment(hub, mx)); break
