@@ -1648,7 +1648,8 @@ constexpr int kBaThreads = 256;
 constexpr int kBaMaxSmemCams = 1024;
 constexpr int kLdltNB = 32;                 // panel width of the grid-wide blocked LDL^T
 constexpr int kLdltTile = 64;               // trailing-update tile
-constexpr size_t kBigScratchBytes = sizeof(double) * (2 * kLdltTile * (kLdltNB + 1) + kLdltNB * kLdltNB + 64);
+constexpr int kLdltTP = kLdltTile + 2;         // row pitch of the transposed tiles: even (16-byte rows), not a multiple of 32 words
+constexpr size_t kBigScratchBytes = sizeof(double) * (2 * kLdltNB * kLdltTP + kLdltNB * kLdltNB + 64);
 
 __host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) * ((size_t)n * n + n); }
 __host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
@@ -2076,11 +2077,14 @@ __device__ void phase_assemble_big(const BaDev& p, double lambda, int gtid, int 
 __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scratch, int* okflag)
 {
     const int n = p.n, tid = threadIdx.x, nt = blockDim.x;
+    long long t_mark = gtimer();
+    // diagnostics: block 0 accumulates the time of (a) diagonal block, (b) panel rows, (c) trailing update, and of the three barriers
+    auto lap = [&](int slot) { if (blockIdx.x == 0 && tid == 0) { const long long t = gtimer(); p.ctl->phase_ns[slot] += t - t_mark; t_mark = t; } };
     const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt;
     double* S = p.S;
-    double* Ys = scratch;                                   // [kLdltTile][kLdltNB + 1]
-    double* Ls = Ys + kLdltTile * (kLdltNB + 1);           // [kLdltTile][kLdltNB + 1]
-    double* Dk = Ls + kLdltTile * (kLdltNB + 1);           // [kLdltNB][kLdltNB] diagonal block (L below the diagonal, D on it)
+    double* Ys = scratch;                                   // [kLdltNB][kLdltTP]: panel columns of the tile's rows, k-major (transposed)
+    double* Ls = Ys + kLdltNB * kLdltTP;                    // [kLdltNB][kLdltTP]: the same for the tile's columns
+    double* Dk = Ls + kLdltNB * kLdltTP;                    // [kLdltNB][kLdltNB] diagonal block (L below the diagonal, D on it)
     __shared__ int s_bad;
     __shared__ double s_col[2 * (kLdltNB + 1)];
     if (tid == 0) s_bad = 0;
@@ -2095,37 +2099,34 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
             for (int i = tid; i < nb * nb; i += nt) if (i % nb <= i / nb) S[(size_t)(k0 + i / nb) * n + k0 + i % nb] = Dk[i];
             if (tid == 0 && s_bad) *okflag = 0;
         }
+        lap(9);
         grid.sync();
+        lap(12);
         const int r0 = k0 + nb;                              // first row below the panel
         if (r0 >= n) break;
         // (b) every block keeps a copy of the factored diagonal block
         for (int i = tid; i < nb * nb; i += nt) Dk[i] = S[(size_t)(k0 + i / nb) * n + k0 + i % nb];
         __syncthreads();
-        for (int row = r0 + gtid; row < n; row += gnt) {
-            double y[kLdltNB];
-            double* a = S + (size_t)row * n + k0;
-#pragma unroll
-            for (int j = 0; j < kLdltNB; j++) y[j] = (j < nb) ? a[j] : 0.0;
-#pragma unroll
-            for (int j = 0; j < kLdltNB; j++) {
-                if (j < nb) {
-                    double v = y[j];
-#pragma unroll
-                    for (int m = 0; m < kLdltNB; m++) if (m < j) v -= y[m] * Dk[j * nb + m];
-                    y[j] = v;
+        {   // one warp per panel row: lane j owns Y_j = A(row, k0 + j); the solved entries are broadcast by shuffle
+            const int lane = tid & 31, gw = gtid >> 5, gnw = gnt >> 5;
+            for (int row = r0 + gw; row < n; row += gnw) {
+                double* a = S + (size_t)row * n + k0;
+                double yv = lane < nb ? a[lane] : 0.0;
+                for (int c = 0; c < nb; c++) {
+                    const double yc = __shfl_sync(0xffffffffu, yv, c);
+                    if (lane > c && lane < nb) yv -= yc * Dk[lane * nb + c];
                 }
-            }
-            double* w = p.Wk + (size_t)row * kLdltNB;
-#pragma unroll
-            for (int j = 0; j < kLdltNB; j++) {
-                if (j < nb) {
-                    const double d = Dk[j * nb + j];
-                    w[j] = y[j];
-                    a[j] = (fabs(d) > 0) ? y[j] / d : 0.0;
-                } else w[j] = 0.0;
+                double* w = p.Wk + (size_t)row * kLdltNB;
+                if (lane < nb) {
+                    const double d = Dk[lane * nb + lane];
+                    w[lane] = yv;
+                    a[lane] = (fabs(d) > 0) ? yv / d : 0.0;
+                } else w[lane] = 0.0;
             }
         }
+        lap(10);
         grid.sync();
+        lap(12);
         // (c)
         const int T = (n - r0 + kLdltTile - 1) / kLdltTile, ntiles = T * (T + 1) / 2;
         const int ty = tid >> 4, tx = tid & 15;              // 16 x 16 threads, 4 x 4 outputs each
@@ -2138,8 +2139,8 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
             __syncthreads();
             for (int i = tid; i < kLdltTile * kLdltNB; i += nt) {
                 const int rr = i / kLdltNB, m = i % kLdltNB;
-                Ys[rr * (kLdltNB + 1) + m] = (ri + rr < n) ? p.Wk[(size_t)(ri + rr) * kLdltNB + m] : 0.0;
-                Ls[rr * (kLdltNB + 1) + m] = (rj + rr < n && m < nb) ? S[(size_t)(rj + rr) * n + k0 + m] : 0.0;
+                Ys[m * kLdltTP + rr] = (ri + rr < n) ? p.Wk[(size_t)(ri + rr) * kLdltNB + m] : 0.0;
+                Ls[m * kLdltTP + rr] = (rj + rr < n && m < nb) ? S[(size_t)(rj + rr) * n + k0 + m] : 0.0;
             }
             __syncthreads();
             double acc[4][4];
@@ -2149,9 +2150,10 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
                 for (int b = 0; b < 4; b++) acc[a][b] = 0;
 #pragma unroll 4
             for (int m = 0; m < kLdltNB; m++) {
-                double ya[4], lb[4];
-#pragma unroll
-                for (int a = 0; a < 4; a++) { ya[a] = Ys[(ty * 4 + a) * (kLdltNB + 1) + m]; lb[a] = Ls[(tx * 4 + a) * (kLdltNB + 1) + m]; }
+                // k-major tiles: a thread's four row / column operands are 32 contiguous bytes (two 16-byte loads, conflict-free across tx)
+                const double2 y01 = *reinterpret_cast<const double2*>(Ys + m * kLdltTP + ty * 4), y23 = *reinterpret_cast<const double2*>(Ys + m * kLdltTP + ty * 4 + 2);
+                const double2 l01 = *reinterpret_cast<const double2*>(Ls + m * kLdltTP + tx * 4), l23 = *reinterpret_cast<const double2*>(Ls + m * kLdltTP + tx * 4 + 2);
+                const double ya[4] = {y01.x, y01.y, y23.x, y23.y}, lb[4] = {l01.x, l01.y, l23.x, l23.y};
 #pragma unroll
                 for (int a = 0; a < 4; a++)
 #pragma unroll
@@ -2165,7 +2167,9 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
                     if (i < n && j < n && j <= i) S[(size_t)i * n + j] -= acc[a][b];
                 }
         }
+        lap(11);
         grid.sync();
+        lap(12);
     }
     return true;
 }

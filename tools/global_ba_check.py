@@ -22,4 +22,4 @@ for s in range(STEPS):
     from mageslam_b200 import _lib as _L
     ph = _np.zeros(16, _np.int64)
     _L.lib().mage_ba_debug_phase_ns(gpu._h, ph.ctypes.data_as(_C.c_void_p))
-    print('      cumulative phase us (errors+chi2, build, schur_pts, schur_prod, solve(after assemble), sync, backsub+update, errors+scale, assemble):', [round(float(x) / 1e3, 1) for x in ph[:9]])
+    print('      cumulative phase us (errors+chi2, build, schur_pts, schur_prod, solve(after assemble), sync, backsub+update, errors+scale, assemble):', [round(float(x) / 1e3, 1) for x in ph[:9]], ' LDLT (diag, panel, update, barriers):', [round(float(x) / 1e3, 1) for x in ph[9:13]])
