@@ -2137,10 +2137,22 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
             const int tj = tile - ti * (ti + 1) / 2;
             const int ri = r0 + ti * kLdltTile, rj = r0 + tj * kLdltTile;
             __syncthreads();
-            for (int i = tid; i < kLdltTile * kLdltNB; i += nt) {
-                const int rr = i / kLdltNB, m = i % kLdltNB;
-                Ys[m * kLdltTP + rr] = (ri + rr < n) ? p.Wk[(size_t)(ri + rr) * kLdltNB + m] : 0.0;
-                Ls[m * kLdltTP + rr] = (rj + rr < n && m < nb) ? S[(size_t)(rj + rr) * n + k0 + m] : 0.0;
+            {   // all 16 global loads of the thread in flight before the first shared store (the compiler cannot reorder them across
+                // the stores itself: the pointers may alias as far as it knows)
+                constexpr int kPer = kLdltTile * kLdltNB / kCoopThreads;
+                double yv[kPer], lv[kPer];
+#pragma unroll
+                for (int u = 0; u < kPer; u++) {
+                    const int i = tid + u * kCoopThreads, rr = i / kLdltNB, m = i % kLdltNB;
+                    yv[u] = (ri + rr < n) ? p.Wk[(size_t)(ri + rr) * kLdltNB + m] : 0.0;
+                    lv[u] = (rj + rr < n && m < nb) ? S[(size_t)(rj + rr) * n + k0 + m] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < kPer; u++) {
+                    const int i = tid + u * kCoopThreads, rr = i / kLdltNB, m = i % kLdltNB;
+                    Ys[m * kLdltTP + rr] = yv[u];
+                    Ls[m * kLdltTP + rr] = lv[u];
+                }
             }
             __syncthreads();
             double acc[4][4];
@@ -2159,12 +2171,20 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
 #pragma unroll
                     for (int b = 0; b < 4; b++) acc[a][b] += ya[a] * lb[b];
             }
+            double sv[4][4];                                  // read-modify-write of the 4 x 4 outputs: all loads first, then all stores
 #pragma unroll
             for (int a = 0; a < 4; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) {
                     const int i = ri + ty * 4 + a, j = rj + tx * 4 + b;
-                    if (i < n && j < n && j <= i) S[(size_t)i * n + j] -= acc[a][b];
+                    sv[a][b] = (i < n && j < n && j <= i) ? S[(size_t)i * n + j] : 0.0;
+                }
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int i = ri + ty * 4 + a, j = rj + tx * 4 + b;
+                    if (i < n && j < n && j <= i) S[(size_t)i * n + j] = sv[a][b] - acc[a][b];
                 }
         }
         lap(11);
