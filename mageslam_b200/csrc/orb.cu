@@ -27,7 +27,7 @@ namespace mage {
 constexpr int kMaxLevels = 16;
 constexpr int kMaxCells = 2048;
 constexpr int kSelThreads = 512;
-constexpr int kSelSmemItems = 4096;      // keypoints per (frame, level) handled entirely in shared memory
+constexpr int kSelSmemItems = 2048;      // keypoints per (frame, level) handled entirely in shared memory (34 KB: four 512-thread CTAs per SM; a level keeping more uses the global scratch)
 
 struct LevelGeom {
     int w, h, pitch, nfeat;
@@ -523,7 +523,7 @@ __device__ void bitonic_sort_desc(unsigned long long* keys, int npow2)
     }
 }
 
-__global__ void __launch_bounds__(kSelThreads) k_select(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+__global__ void __launch_bounds__(kSelThreads, 4) k_select(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int hist[256];
@@ -1081,7 +1081,7 @@ __device__ __forceinline__ void orient_moments(const uint8_t* center, int pitch,
     }
 }
 
-__global__ void __launch_bounds__(256) k_orient_describe(const __grid_constant__ OrbGeom g, const OrbBuffers b,
+__global__ void __launch_bounds__(256, 5) k_orient_describe(const __grid_constant__ OrbGeom g, const OrbBuffers b,
                                                          mage_keypoint* __restrict__ out_kps, uint8_t* __restrict__ out_desc,
                                                          int* __restrict__ out_counts, int capacity)
 {
