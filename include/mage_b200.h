@@ -331,6 +331,7 @@ int  mage_ba_step_many(mage_ba_t* handles, int n_handles, const float* huber_wid
 /* The observation indices the last mage_ba_step / mage_ba_step_many call removed from this problem (the `outliers` vector of
  * StepBundleAdjustment, ref BundlerLib.cpp:385-441); returns the total count in *n_outliers even when capacity is smaller. */
 int  mage_ba_last_outliers(mage_ba_t h, unsigned int* outliers, int capacity, int* n_outliers);
+int  mage_ba_last_outlier_counts(mage_ba_t* handles, int n_handles, int* counts);     /* the counts of many problems in one call */
 
 #ifdef __cplusplus
 }

@@ -112,6 +112,7 @@ def lib():
         L.mage_ba_get_stats.argtypes = [vp, vp]
         L.mage_ba_step_many.argtypes = [vp, ci, vp, ci, cf, vp]
         L.mage_ba_last_outliers.argtypes = [vp, vp, ci, C.POINTER(ci)]
+        L.mage_ba_last_outlier_counts.argtypes = [vp, ci, vp]
     _lib = L
     return L
 

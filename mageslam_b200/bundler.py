@@ -166,11 +166,14 @@ def StepMany(bundlers, huberWidthPerIteration, maxErrorSquare):
     arr = (C.c_void_p * len(bundlers))(*[b._h for b in bundlers])
     means = np.zeros(len(bundlers), np.float32)
     check(lib().mage_ba_step_many(arr, len(bundlers), ptr(hub), len(hub), float(maxErrorSquare), ptr(means)))
-    for b in bundlers:                       # the `outliers` vector of each problem's StepBundleAdjustment
-        n = C.c_int(0)
-        check(lib().mage_ba_last_outliers(b._h, None, 0, C.byref(n)))
-        buf = np.zeros(max(n.value, 1), np.uint32)
-        if n.value:
-            check(lib().mage_ba_last_outliers(b._h, ptr(buf), n.value, C.byref(n)))
-        b.last_outliers = buf[:n.value].copy()
+    counts = np.zeros(len(bundlers), np.int32)      # the `outliers` vector of each problem's StepBundleAdjustment
+    check(lib().mage_ba_last_outlier_counts(arr, len(bundlers), ptr(counts)))
+    empty = np.zeros(0, np.uint32)
+    for b, cnt in zip(bundlers, counts):
+        if cnt == 0:
+            b.last_outliers = empty
+            continue
+        buf = np.zeros(int(cnt), np.uint32); n = C.c_int(0)
+        check(lib().mage_ba_last_outliers(b._h, ptr(buf), int(cnt), C.byref(n)))
+        b.last_outliers = buf
     return means

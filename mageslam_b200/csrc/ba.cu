@@ -3155,6 +3155,13 @@ extern "C" int mage_ba_last_outliers(mage_ba_t h, unsigned int* outliers, int ca
     return MAGE_OK;
 }
 
+extern "C" int mage_ba_last_outlier_counts(mage_ba_t* hs, int n, int* counts)
+{
+    MAGE_REQUIRE(hs && counts && n >= 0, MAGE_ERR_INVALID, "mage_ba_last_outlier_counts: bad argument");
+    for (int i = 0; i < n; i++) counts[i] = hs[i] ? (int)hs[i]->last_outliers.size() : 0;
+    return MAGE_OK;
+}
+
 extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n_iters, float max_err_sq, float* means)
 {
     MAGE_REQUIRE(hs && n >= 1 && means && (huber || n_iters == 0), MAGE_ERR_INVALID, "mage_ba_step_many: bad argument");
