@@ -55,8 +55,10 @@ struct DeviceArena {
             pool_ready = true;
         }
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&base), size ? size : 256, static_cast<cudaStream_t>(0));
-        if (e == cudaSuccess) e = cudaStreamSynchronize(static_cast<cudaStream_t>(0));       // usable from any stream afterwards
-        return e;
+        if (e == cudaSuccess) return cudaStreamSynchronize(static_cast<cudaStream_t>(0));    // usable from any stream afterwards
+        cudaGetLastError();                                    // no stream-ordered pool on this device / driver: plain allocation
+        pooled = false; base = nullptr;
+        return cudaMalloc(&base, size ? size : 256);
     }
     template <class T> T* at(size_t off) const { return reinterpret_cast<T*>(base + off); }
     void release()
