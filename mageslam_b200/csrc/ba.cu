@@ -2194,61 +2194,93 @@ __device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scra
     return true;
 }
 
-// block 0: L y = b (row-oriented dot products), D, L^T x = y (row k of L is column k of L^T); x -> p.x[0..n)
-__device__ void tri_solve_big(const BaDev& p, double* sh)
+
+// Grid-wide version of the substitution: 128 unknowns per step. Block 0 solves the 128 x 128 triangle on the diagonal (four 32-wide
+// warp solves with in-CTA updates between them), then -- after a grid barrier -- every warp of the grid applies the solved block to
+// its share of the remaining rows (forward: one warp per row, lanes stride the 128 columns, coalesced) or columns (backward: one
+// thread per column). One SM could not stream the 70 MB factor twice in less than ~3 ms; the grid does it in under one.
+constexpr int kTriNB = 128;
+__device__ void tri_solve_big_grid(cg::grid_group& grid, const BaDev& p)
 {
-    // Blocked substitution, 32 unknowns at a time: the 32 x 32 triangle on the diagonal is solved by one warp with the right-hand
-    // side in registers (pivots broadcast by shuffle), then every thread applies the solved block to its rows (forward) / columns
-    // (backward) -- two CTA barriers per 32 unknowns instead of one block-wide reduction per unknown.
-    const int n = p.n, tid = threadIdx.x, nt = blockDim.x;
-    const double* S = p.S;
+    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt, gw = gtid >> 5, gnw = gnt >> 5;
+    const double* __restrict__ S = p.S;
     double* y = p.bs;
     __shared__ double yb[32];
-    (void)sh;
-    for (int k0 = 0; k0 < n; k0 += 32) {
-        const int nb = min(32, n - k0);
-        if (tid < 32) {
-            double yv = tid < nb ? y[k0 + tid] : 0.0;
-            for (int c = 0; c < nb; c++) {
-                const double yc = __shfl_sync(0xffffffffu, yv, c);
-                if (tid > c && tid < nb) yv -= S[(size_t)(k0 + tid) * n + k0 + c] * yc;
+    for (int k0 = 0; k0 < n; k0 += kTriNB) {
+        const int nb = min(kTriNB, n - k0);
+        if (blockIdx.x == 0) {
+            for (int s0 = 0; s0 < nb; s0 += 32) {
+                const int sb = min(32, nb - s0), q0 = k0 + s0;
+                if (tid < 32) {
+                    double yv = tid < sb ? y[q0 + tid] : 0.0;
+                    for (int c = 0; c < sb; c++) {
+                        const double yc = __shfl_sync(0xffffffffu, yv, c);
+                        if (tid > c && tid < sb) yv -= S[(size_t)(q0 + tid) * n + q0 + c] * yc;
+                    }
+                    if (tid < sb) { y[q0 + tid] = yv; yb[tid] = yv; }
+                }
+                __syncthreads();
+                for (int i = q0 + sb + tid; i < k0 + nb; i += nt) {              // the rest of this 128-block
+                    const double* row = S + (size_t)i * n + q0;
+                    double acc = 0;
+                    for (int j = 0; j < sb; j++) acc += row[j] * yb[j];
+                    y[i] -= acc;
+                }
+                __syncthreads();
             }
-            if (tid < nb) { y[k0 + tid] = yv; yb[tid] = yv; }
         }
-        __syncthreads();
-        for (int i = k0 + nb + tid; i < n; i += nt) {
+        __threadfence();
+        grid.sync();
+        for (int i = k0 + nb + gw; i < n; i += gnw) {                            // one warp per remaining row
             const double* row = S + (size_t)i * n + k0;
             double acc = 0;
-#pragma unroll 8
-            for (int j = 0; j < nb; j++) acc += row[j] * yb[j];
-            y[i] -= acc;
+            for (int j = lane; j < nb; j += 32) acc += row[j] * y[k0 + j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+            if (lane == 0) y[i] -= acc;
         }
-        __syncthreads();
+        __threadfence();
+        grid.sync();
     }
     const double tol = 1.0 / DBL_MAX;
-    for (int i = tid; i < n; i += nt) { const double d = S[(size_t)i * n + i]; y[i] = (fabs(d) > tol) ? y[i] / d : 0.0; }
-    __syncthreads();
-    for (int k0 = ((n - 1) / 32) * 32; k0 >= 0; k0 -= 32) {
-        const int nb = min(32, n - k0);
-        if (tid < 32) {
-            double yv = tid < nb ? y[k0 + tid] : 0.0;
-            for (int c = nb - 1; c >= 0; c--) {
-                const double xc = __shfl_sync(0xffffffffu, yv, c);
-                if (tid < c) yv -= S[(size_t)(k0 + c) * n + k0 + tid] * xc;
+    for (int i = gtid; i < n; i += gnt) { const double d = S[(size_t)i * n + i]; y[i] = (fabs(d) > tol) ? y[i] / d : 0.0; }
+    __threadfence();
+    grid.sync();
+    for (int k0 = ((n - 1) / kTriNB) * kTriNB; k0 >= 0; k0 -= kTriNB) {
+        const int nb = min(kTriNB, n - k0);
+        if (blockIdx.x == 0) {
+            for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
+                const int sb = min(32, nb - s0), q0 = k0 + s0;
+                if (tid < 32) {
+                    double yv = tid < sb ? y[q0 + tid] : 0.0;
+                    for (int c = sb - 1; c >= 0; c--) {
+                        const double xc = __shfl_sync(0xffffffffu, yv, c);
+                        if (tid < c) yv -= S[(size_t)(q0 + c) * n + q0 + tid] * xc;
+                    }
+                    if (tid < sb) { y[q0 + tid] = yv; yb[tid] = yv; }
+                }
+                __syncthreads();
+                for (int i = k0 + tid; i < q0; i += nt) {                          // the earlier unknowns of this 128-block
+                    double acc = 0;
+                    for (int j = 0; j < sb; j++) acc += S[(size_t)(q0 + j) * n + i] * yb[j];
+                    y[i] -= acc;
+                }
+                __syncthreads();
             }
-            if (tid < nb) { y[k0 + tid] = yv; yb[tid] = yv; }
         }
-        __syncthreads();
-        for (int i = tid; i < k0; i += nt) {
+        __threadfence();
+        grid.sync();
+        for (int i = gtid; i < k0; i += gnt) {                                    // one thread per remaining column
             double acc = 0;
-#pragma unroll 8
-            for (int j = 0; j < nb; j++) acc += S[(size_t)(k0 + j) * n + i] * yb[j];
+#pragma unroll 4
+            for (int j = 0; j < nb; j++) acc += S[(size_t)(k0 + j) * n + i] * y[k0 + j];
             y[i] -= acc;
         }
-        __syncthreads();
+        __threadfence();
+        grid.sync();
     }
-    for (int i = tid; i < n; i += nt) p.x[i] = y[i];
-    __syncthreads();
+    for (int i = gtid; i < n; i += gnt) p.x[i] = y[i];
 }
 
 __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __restrict__ prob, const float* __restrict__ huberW, int nIters, float maxErrSq,
@@ -2372,7 +2404,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
                 grid.sync();
                 PH(8);
                 grid_ldlt_big(grid, p, reinterpret_cast<double*>(dyn), &ctl->last_ok);
-                if (blockIdx.x == 0 && *reinterpret_cast<volatile int*>(&ctl->last_ok)) tri_solve_big(p, sh);
+                if (*reinterpret_cast<volatile int*>(&ctl->last_ok)) tri_solve_big_grid(grid, p);      // uniform: written before the last grid barrier
             }
             PH(4);
             grid.sync();
