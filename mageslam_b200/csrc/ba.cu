@@ -3163,7 +3163,11 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
         MAGE_REQUIRE(!(h->dev.nT > 0 && h->dev.big), MAGE_ERR_UNSUPPORTED, "tether edges are not supported on problems with %d pose unknowns", h->dev.n);
         const bool use_coop = h->dev.nT == 0 && h->coop_blocks > 1 && h->dev.K <= kBaMaxSmemCams && coop_smem <= 128 * 1024 && (h->dev.Ea >= 1024 || h->dev.big);
         MAGE_REQUIRE(use_coop || !h->dev.big, MAGE_ERR_UNSUPPORTED, "reduced camera system of %d unknowns needs the cooperative kernel (not available)", h->dev.n);
-        const int coop_grid = h->dev.big ? h->coop_blocks_max : h->coop_blocks;
+        // small systems: enough CTAs that every (reduced-system block, part) item of the Schur products gets its own warp in ONE round
+        // (288 items on 32 CTAs = 256 warps ran a second, nearly empty round)
+        int coop_grid = h->dev.big ? h->coop_blocks_max : h->coop_blocks;
+        if (!h->dev.big && !getenv("MAGE_BA_COOP_BLOCKS"))
+            coop_grid = std::min(h->coop_blocks_max, std::max(coop_grid, div_up(h->dev.nblk * h->dev.schur_parts, kCoopThreads / 32)));
         ProfScope ps(PROF_BA_STEP, h->stream);
         if (use_coop) {
             const BaDev* d_dev = h->d_dev; const float* d_hub = h->d_huber; unsigned dynb = (unsigned)coop_smem;
