@@ -228,18 +228,20 @@ __device__ __forceinline__ void edge_jacobians(const BaDev& p, int e, double* Ji
     double xt[3];
     q_rot(q, p.pt_X + 3 * (size_t)p.e_pt[e], xt);
     const double x = xt[0] + p.cam_t[3 * c], y = xt[1] + p.cam_t[3 * c + 1], z = xt[2] + p.cam_t[3 * c + 2];
-    const double f = p.cam_f[c], z2 = z * z;
+    const double f = p.cam_f[c];
     double R[9];
     q_to_R(q, R);
-    const double t00 = f, t02 = -x / z * f, t11 = f, t12 = -y / z * f, miz = -1. / z;
+    // one reciprocal instead of the dozen divisions of the reference's expressions (same values to rounding)
+    const double iz = 1.0 / z, a = x * iz, b = y * iz, g = -(iz * f);
 #pragma unroll
     for (int cc = 0; cc < 3; cc++) {
-        Ji[cc] = (miz * t00) * R[cc] + (miz * t02) * R[6 + cc];
-        Ji[3 + cc] = (miz * t11) * R[3 + cc] + (miz * t12) * R[6 + cc];
+        Ji[cc] = g * (R[cc] - a * R[6 + cc]);
+        Ji[3 + cc] = g * (R[3 + cc] - b * R[6 + cc]);
     }
     if (wantPose) {
-        Jj[0] = x * y / z2 * f; Jj[1] = -(1 + (x * x / z2)) * f; Jj[2] = y / z * f; Jj[3] = -1. / z * f; Jj[4] = 0; Jj[5] = x / z2 * f;
-        Jj[6] = (1 + y * y / z2) * f; Jj[7] = -x * y / z2 * f; Jj[8] = -x / z * f; Jj[9] = 0; Jj[10] = -1. / z * f; Jj[11] = y / z2 * f;
+        const double ab = a * b * f, izf = iz * f;
+        Jj[0] = ab; Jj[1] = -(f + a * a * f); Jj[2] = b * f; Jj[3] = -izf; Jj[4] = 0; Jj[5] = a * izf;
+        Jj[6] = f + b * b * f; Jj[7] = -ab; Jj[8] = -(a * f); Jj[9] = 0; Jj[10] = -izf; Jj[11] = b * izf;
     }
 }
 
