@@ -228,6 +228,29 @@ def cpu_ba_baseline(parallel=False, reps=8):
             "sample": "%d processes x %d independent windows x 10 LM iterations" % (cores, per)}
 
 
+def bind_to_gpu_numa_node(gpu):
+    """One process per GPU: run this rank (and allocate its pinned host buffers) on the CPUs of the NUMA node the GPU hangs off, so
+    that eight ranks streaming frames do not all pull from one socket's memory. Best effort; returns the node or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(gpu), "--query-gpu=pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True,
+                             timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        bus = bus[-12:] if len(bus) > 12 else bus                      # sysfs uses a 4-digit domain: 0000:17:00.0
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or os.sched_getaffinity(0))
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -237,6 +260,7 @@ def run_ours(args):
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)          # before any pinned allocation: first touch puts the staging buffers next to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()      # raises if the CUDA extension is missing: there is no fallback path
@@ -363,7 +387,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "frames_per_step": B, "sequences": world, "parallelism": "replicas (one sequence per GPU)",
                        "l2": "inputs larger than L2: %d-frame ring = %.0f MB per GPU" % (ring_n, ring_n * W * H / 1e6),
                        "keypoints_per_frame": kp_mean, "matches_per_frame": match_mean, "e2e_chunk": args.chunk,
-                       "e2e_timer": "host clock around the whole loop of C-ABI calls, device idle at both ends",
+                       "e2e_timer": "host clock around the whole loop of C-ABI calls, device idle at both ends", "numa_node": numa,
                        "e2e_mode": "pipelined mage_frontend_submit / _wait, two calls in flight, pinned host buffers; e2e.sync = the plain synchronous mage_frontend_process"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "sync": e2e_sync_value},
