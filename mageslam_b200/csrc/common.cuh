@@ -32,6 +32,20 @@ void set_error(const char* fmt, ...);
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
+// Raise the default stream-ordered pool's release threshold once, so blocks freed with cudaFreeAsync stay cached across synchronisations
+// (the default threshold of 0 hands them back to the driver at the next sync and every cudaMallocAsync pays a fresh allocation).
+inline void pool_keep_cached()
+{
+    static bool pool_ready = false;
+    if (pool_ready) return;
+    int dev = 0; cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_ready = true;
+}
+
 // One device allocation carved into aligned sub-buffers. pooled = true takes it from the stream-ordered default memory pool
 // (cudaMallocAsync, release threshold raised so freed blocks stay cached): a few microseconds instead of the ~1-4 ms cudaFree +
 // cudaMalloc of a multi-megabyte block cost when a new problem is set up per call (a BundlerLib instance per local-BA window).
@@ -45,15 +59,7 @@ struct DeviceArena {
     {
         size = used;
         if (!pooled) return cudaMalloc(&base, size ? size : 256);
-        static bool pool_ready = false;
-        if (!pool_ready) {
-            int dev = 0; cudaMemPool_t pool;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                unsigned long long keep = ~0ull;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            pool_ready = true;
-        }
+        pool_keep_cached();
         cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&base), size ? size : 256, static_cast<cudaStream_t>(0));
         if (e == cudaSuccess) return cudaStreamSynchronize(static_cast<cudaStream_t>(0));    // usable from any stream afterwards
         cudaGetLastError();                                    // no stream-ordered pool on this device / driver: plain allocation

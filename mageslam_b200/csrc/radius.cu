@@ -200,7 +200,12 @@ struct mage_spatial_index_s {
     RadiusIndexDev dev{};
     std::vector<int> rank;
     // per-call scratch (grown on demand)
-    uint8_t* d_scratch = nullptr; size_t scratch_bytes = 0;
+    uint8_t* d_scratch = nullptr; size_t scratch_bytes = 0; bool scratch_pooled = false;
+    void free_scratch()
+    {
+        if (d_scratch) { if (scratch_pooled) cudaFreeAsync(d_scratch, stream); else cudaFree(d_scratch); }
+        d_scratch = nullptr;
+    }
     cudaStream_t stream = nullptr;
 };
 
@@ -213,17 +218,19 @@ extern "C" int mage_spatial_index_create(const mage_keypoint* keypoints, int n, 
     mage_spatial_index_s* ix = new mage_spatial_index_s();
     ix->n = n;
     packed_rtree_rank(keypoints, n, ix->rank);
-    std::vector<float> x(n), y(n); std::vector<int> oc(n);
-    for (int i = 0; i < n; i++) { x[i] = keypoints[i].x; y[i] = keypoints[i].y; oc[i] = keypoints[i].octave; }
+    // one pooled arena, one packed upload: the index is rebuilt for every analysed frame, so its set-up cost is per-frame latency
     DeviceArena& A = ix->arena;
+    A.pooled = true;
     const size_t cnt = (size_t)std::max(n, 1);
-    size_t ox = A.reserve(4 * cnt), oy = A.reserve(4 * cnt), oo = A.reserve(4 * cnt), orank = A.reserve(4 * cnt);
+    size_t ox = A.reserve(4 * cnt, 16), oy = A.reserve(4 * cnt, 16), oo = A.reserve(4 * cnt, 16), orank = A.reserve(4 * cnt, 16);
+    std::vector<uint8_t> host(A.used);
+    float* x = reinterpret_cast<float*>(host.data() + ox); float* y = reinterpret_cast<float*>(host.data() + oy);
+    int* oc = reinterpret_cast<int*>(host.data() + oo);
+    for (int i = 0; i < n; i++) { x[i] = keypoints[i].x; y[i] = keypoints[i].y; oc[i] = keypoints[i].octave; }
+    if (n) memcpy(host.data() + orank, ix->rank.data(), 4 * (size_t)n);
     cudaError_t e = A.commit();
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess && n) e = cudaMemcpy(A.base + ox, x.data(), 4 * (size_t)n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && n) e = cudaMemcpy(A.base + oy, y.data(), 4 * (size_t)n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && n) e = cudaMemcpy(A.base + oo, oc.data(), 4 * (size_t)n, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && n) e = cudaMemcpy(A.base + orank, ix->rank.data(), 4 * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n) e = cudaMemcpy(A.base, host.data(), host.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { set_error("mage_spatial_index_create: %s", cudaGetErrorString(e)); A.release(); delete ix; return MAGE_ERR_CUDA; }
     ix->dev.x = A.at<float>(ox); ix->dev.y = A.at<float>(oy); ix->dev.octave = A.at<int>(oo); ix->dev.rank = A.at<int>(orank); ix->dev.n = n;
     *out = ix;
@@ -233,7 +240,7 @@ extern "C" int mage_spatial_index_create(const mage_keypoint* keypoints, int n, 
 extern "C" void mage_spatial_index_destroy(mage_spatial_index_s* ix)
 {
     if (!ix) return;
-    if (ix->d_scratch) cudaFree(ix->d_scratch);
+    ix->free_scratch();                                      // every match call synchronises before it returns, nothing is in flight
     if (ix->stream) cudaStreamDestroy(ix->stream);
     ix->arena.release();
     delete ix;
@@ -263,9 +270,14 @@ extern "C" int mage_radius_match(mage_spatial_index_s* ix, const mage_keypoint* 
     const size_t o_qk = take(sizeof(mage_keypoint) * nQ), o_qp = take(8 * nQ), o_qm = take(nQ), o_qd = take(32 * nQ), o_tm = take(nT), o_td = take(32 * nT);
     const size_t o_al = take(4 * nQ), o_tb = take(4 * nT), o_ts = take(4 * nT), o_out = take(sizeof(mage_dmatch) * nQ), o_cnt = take(4);
     if (off > ix->scratch_bytes) {
-        if (ix->d_scratch) cudaFree(ix->d_scratch);
+        ix->free_scratch();
+        ix->scratch_bytes = 0;
+        // stream-ordered pool first (an index lives for one frame, so this allocation is per-frame latency), plain allocation otherwise
+        pool_keep_cached();
+        ix->scratch_pooled = cudaMallocAsync(reinterpret_cast<void**>(&ix->d_scratch), off, ix->stream) == cudaSuccess;
+        if (ix->scratch_pooled) MAGE_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+        else { cudaGetLastError(); MAGE_CUDA_TRY(cudaMalloc(&ix->d_scratch, off)); }
         ix->scratch_bytes = off;
-        MAGE_CUDA_TRY(cudaMalloc(&ix->d_scratch, off));
     }
     uint8_t* S = ix->d_scratch;
     MAGE_CUDA_TRY(cudaMemcpyAsync(S + o_qk, query_kps, sizeof(mage_keypoint) * nQ, cudaMemcpyHostToDevice, s));
