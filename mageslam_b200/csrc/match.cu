@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 namespace mage {
@@ -44,7 +45,7 @@ __device__ __forceinline__ int job_count(const MatchJob& j, int side)
 // slots with integer atomics: best/second of row a (A -> B) and best/second of column b (B -> A). "second" receives the
 // loser of every best update, which yields exactly the second smallest key whatever the arrival order, so the result is
 // deterministic. stats layout: [pair][4][stride] = fwd best, fwd second, bwd best, bwd second.
-__global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
+__global__ void __launch_bounds__(kWarps * 32) k_match_dir_popc(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
 {
     __shared__ uint32_t tw[8][kChunk];          // train words, transposed: conflict-free lane-strided reads
     __shared__ uint32_t tx[kChunk];             // t0 ^ t1 ^ t2 per train
@@ -134,6 +135,236 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_dir(const MatchJob* __res
             atomicMin(&bsecond[tidx], max(old, kb));
         }
     }
+}
+
+// ---- tcgen05 path (the default for maxHamming <= kUmmaMaxHamming) ------------------------------------------------------------
+// With the descriptor bits spread to signed bytes (+1 for a set bit, -1 for a clear one) the Hamming distance is a dot product,
+//     <a, b> = 256 - 2 H(a, b),
+// so the 2000 x 2000 distance matrix of a frame pair is an int8 GEMM with K = 256: 5th-generation tensor cores
+// (tcgen05.mma kind::i8, M = 128 queries x N = 256 trains x K = 32 per instruction, operands in shared memory in the canonical
+// K-major no-swizzle layout, s32 accumulators in tensor memory) take it off the POPC pipe that bounds k_match_dir_popc.
+// The accumulators come back with tcgen05.ld (thread = query row, 32 train columns at a time); a running maximum against
+// T = 256 - 2 maxHamming finds the columns inside the radius -- their exact distance is (256 - acc) / 2 -- and those
+// (about 1 per query) make the same four packed atomic updates as above, so the statistics and hence the matches are identical.
+// CTA = 128 queries (A tile expanded once, 32 KB) x a walk over the train tiles (B tile 64 KB, double-buffered): the bit -> byte
+// expansion of tile j + 1 and the read-out of tile j - 1 run while the tensor core works on tile j; the accumulators alternate
+// between the two halves of the 512 TMEM columns. Masked or absent descriptors expand to zero bytes: acc = 0 < T.
+constexpr int kUmmaM = 128, kUmmaN = 256;
+constexpr int kUmmaThreads = 512;                                  // 16 warps: the expansion and the read-out are latency bound with fewer
+constexpr int kUmmaMaxHamming = 64;                               // T must stay positive; wider radii take the popc kernel
+constexpr uint32_t kUmmaLBO = 128, kUmmaSBO = 256;                // K-chunk (16 B) stride, 8-row group stride inside one K = 32 step
+constexpr uint32_t kUmmaStepA = kUmmaM * 32, kUmmaStepB = kUmmaN * 32;      // bytes per K = 32 step
+constexpr uint32_t kUmmaBytesA = kUmmaM * 256, kUmmaBytesB = kUmmaN * 256;
+constexpr size_t kUmmaSmemBytes = kUmmaBytesA + 2 * (size_t)kUmmaBytesB + 1024;
+// instruction descriptor (kind::i8): D = s32, A and B signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kUmmaIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor: start address, leading (K chunk) and stride (row group) byte offsets in 16-byte units, version 1
+// (Blackwell), no swizzle
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kUmmaLBO >> 4) << 16) | ((uint64_t)(kUmmaSBO >> 4) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kUmmaIdesc), "r"(accumulate), "r"(0u) : "memory");
+}
+
+// bounded wait on an mbarrier phase: a descriptor mistake must end in a trap, not in a hung device
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
+{
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        uint32_t done;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// A pair inside the radius makes four packed updates, two of which need the value an atomic returns: ~2 L2 round trips. With one CTA
+// of 8 warps per SM nothing hides that latency, so the read-out only appends (query row, train, distance) to a shared-memory list and
+// the whole CTA drains the list at the end, one entry per thread, all round trips in flight together.
+constexpr int kUmmaListCap = 4096;
+__device__ __forceinline__ void match_update(unsigned qidx, unsigned tidx, unsigned d, unsigned* fbest, unsigned* fsecond, unsigned* bbest, unsigned* bsecond)
+{
+    const unsigned kf = (d << 16) | tidx, kb = (d << 16) | qidx;
+    unsigned old = atomicMin(&fbest[qidx], kf);
+    atomicMin(&fsecond[qidx], max(old, kf));
+    old = atomicMin(&bbest[tidx], kb);
+    atomicMin(&bsecond[tidx], max(old, kb));
+}
+__device__ __noinline__ void match_update_direct(unsigned qidx, unsigned tidx, unsigned d, unsigned* fbest, unsigned* fsecond, unsigned* bbest, unsigned* bsecond)
+{
+    match_update(qidx, tidx, d, fbest, fsecond, bbest, bsecond);
+}
+
+// half a descriptor (4 words; half h = words 4 h .. 4 h + 3) -> its 8 K chunks of signed bytes at `row` of an operand tile. Any fixed
+// assignment of descriptor bits to K positions gives the same dot product as long as both operands use it, so a group of four K
+// positions takes bits b, b + 8, b + 16, b + 24 of one word: (w >> b) & 0x01010101 is already the 0/1 byte form (one shift, one AND),
+// and 0xFFFFFFFF - 0xFE t turns 1 -> 0x01 (+1), 0 -> 0xFF (-1) in every byte with one IMAD. An absent row is all zero bytes.
+__device__ __forceinline__ void umma_expand_half(uint8_t* tile, uint32_t kstep_bytes, int row, int h, const uint4& v, bool present)
+{
+    uint8_t* dst = tile + (row >> 3) * kUmmaSBO + (row & 7) * 16 + (4 * h) * kstep_bytes;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 8; q++) {                                  // chunk q of this half = K positions 16 (8 h + q) .. + 15
+        uint4 c = make_uint4(0u, 0u, 0u, 0u);
+        if (present) {
+            const uint32_t x = w[q >> 1] >> (4 * (q & 1));
+            c.x = 0xFFFFFFFFu - (x & 0x01010101u) * 0xFEu;
+            c.y = 0xFFFFFFFFu - ((x >> 1) & 0x01010101u) * 0xFEu;
+            c.z = 0xFFFFFFFFu - ((x >> 2) & 0x01010101u) * 0xFEu;
+            c.w = 0xFFFFFFFFu - ((x >> 3) & 0x01010101u) * 0xFEu;
+        }
+        *reinterpret_cast<uint4*>(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO) = c;
+    }
+}
+
+__global__ void __launch_bounds__(kUmmaThreads, 1) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
+{
+    extern __shared__ uint8_t umma_smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t s_tmem;
+    __shared__ uint32_t hit_list[kUmmaListCap];                    // row | train << 7 | distance << 23
+    __shared__ int hit_count;
+    const int pair = blockIdx.y;
+    const MatchJob& job = jobs[pair];
+    const int nQ = job_count(job, 0), nT = job_count(job, 1);
+    const int q0 = blockIdx.x * kUmmaM;
+    const int ntiles = (nT + kUmmaN - 1) / kUmmaN;
+    if (q0 >= nQ || (int)blockIdx.z >= ntiles) return;
+    uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)umma_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = sA + kUmmaBytesA;                                // two buffers of kUmmaBytesB
+    const uint4* Q4 = reinterpret_cast<const uint4*>(job.desc[0]);
+    const uint4* T4 = reinterpret_cast<const uint4*>(job.desc[1]);
+    const uint8_t* mQ = job.mask[0];
+    const uint8_t* mT = job.mask[1];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned* fbest = stats + ((size_t)pair * 4 + 0) * stride;
+    unsigned* fsecond = stats + ((size_t)pair * 4 + 1) * stride;
+    unsigned* bbest = stats + ((size_t)pair * 4 + 2) * stride;
+    unsigned* bsecond = stats + ((size_t)pair * 4 + 3) * stride;
+    const int thr = 256 - 2 * max_hamming;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        hit_count = 0;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[1])), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+
+    if (tid < 2 * kUmmaM) {                                        // A tile: this CTA's queries, expanded once (thread = row, half)
+        const int row = tid & (kUmmaM - 1), h = tid / kUmmaM, qi = q0 + row;
+        const bool present = qi < nQ && (!mQ || mQ[qi]);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (present) v = __ldg(Q4 + (size_t)qi * 2 + h);
+        umma_expand_half(sA, kUmmaStepA, row, h, v, present);
+    }
+    // read-out of the tile issued `it_done` iterations ago: warp w owns TMEM lanes 32 (w % 4) .. + 31 (queries) and, by w / 4, one quarter
+    // of the 256 train columns
+    auto read_out = [&](int it_done, int tile) {
+        const int buf = it_done & 1;
+        mbar_wait_bounded(smem_addr(&mbar[buf]), (uint32_t)(it_done >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = 32 * (warp & 3) + lane;
+        const unsigned qidx = (unsigned)(q0 + row);
+#pragma unroll 1
+        for (int c = 0; c < 2; c++) {
+            const int col0 = (warp >> 2) * 64 + c * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * kUmmaN + col0), v);
+            int m = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
+#pragma unroll
+            for (int i = 3; i + 1 < 32; i += 2) m = __vimax3_s32(m, (int)v[i], (int)v[i + 1]);
+            m = max(m, (int)v[31]);
+            if (m >= thr) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    if ((int)v[i] < thr) continue;
+                    const unsigned tidx = (unsigned)(tile * kUmmaN + col0 + i), d = (256u - v[i]) >> 1;
+                    const int slot = atomicAdd(&hit_count, 1);
+                    if (slot < kUmmaListCap) hit_list[slot] = (unsigned)row | (tidx << 7) | (d << 23);
+                    else match_update_direct(qidx, tidx, d, fbest, fsecond, bbest, bsecond);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.z; tile < ntiles; tile += gridDim.z, it++) {
+        const int buf = it & 1;
+        {   // B tile: thread = (train row, half). The MMA that last read this buffer (iteration it - 2) was waited for in read_out(it - 2).
+            const int row = tid & (kUmmaN - 1), h = tid / kUmmaN, ti = tile * kUmmaN + row;
+            const bool present = ti < nT && (!mT || mT[ti]);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (present) v = __ldg(T4 + (size_t)ti * 2 + h);
+            umma_expand_half(sB + (size_t)buf * kUmmaBytesB, kUmmaStepB, row, h, v, present);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core's reads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a0 = smem_addr(sA), b0 = smem_addr(sB + (size_t)buf * kUmmaBytesB);
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++)
+                umma_i8(tmem + (uint32_t)(buf * kUmmaN), umma_desc(a0 + ks * kUmmaStepA), umma_desc(b0 + ks * kUmmaStepB), ks > 0 ? 1u : 0u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mbar[buf])) : "memory");
+        }
+        if (it > 0) read_out(it - 1, prev_tile);
+        prev_tile = tile;
+    }
+    if (it > 0) read_out(it - 1, prev_tile);
+    __syncthreads();
+    for (int i = tid, n = min(hit_count, kUmmaListCap); i < n; i += blockDim.x) {
+        const unsigned e = hit_list[i];
+        match_update((unsigned)q0 + (e & 127u), (e >> 7) & 0xFFFFu, e >> 23, fbest, fsecond, bbest, bsecond);
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// grid for either matcher kernel; the tcgen05 one splits the train tiles over blockIdx.z until there are enough CTAs to fill the GPU
+// (a single 2000 x 2000 pair is only 16 query blocks)
+static cudaError_t launch_match_dir(const MatchJob* d_jobs, unsigned* best, int max_desc, int max_q, int max_t, int n_pairs, int max_hamming, cudaStream_t s)
+{
+    static const bool force_popc = getenv("MAGE_MATCH_POPC") != nullptr;
+    if (force_popc || max_hamming < 0 || max_hamming > kUmmaMaxHamming) {
+        dim3 grid(div_up(max_q, kQPerBlock), n_pairs);
+        k_match_dir_popc<<<grid, kWarps * 32, 0, s>>>(d_jobs, best, max_desc, max_hamming);
+        return cudaSuccess;
+    }
+    static cudaError_t attr = cudaFuncSetAttribute(k_match_dir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemBytes);
+    if (attr != cudaSuccess) return attr;
+    const int gx = std::max(1, div_up(max_q, kUmmaM)), tiles = std::max(1, div_up(max_t, kUmmaN));
+    const int gz = std::min(tiles, std::max(1, div_up(2 * 148, gx * n_pairs)));
+    dim3 grid(gx, n_pairs, gz);
+    k_match_dir<<<grid, kUmmaThreads, kUmmaSmemBytes, s>>>(d_jobs, best, max_desc, max_hamming);
+    return cudaSuccess;
 }
 
 // min-difference test (ref :130-135 / :149-154) on the packed stats, then cross-check (ref :158) and ordered emission
@@ -298,13 +529,12 @@ extern "C" void mage_matcher_destroy(mage_matcher_t m)
     delete m;
 }
 
-static int match_launch(mage_matcher_t m, int n_pairs, int max_q, int max_hamming, int min_diff, mage_dmatch* d_out, int out_cap,
+static int match_launch(mage_matcher_t m, int n_pairs, int max_q, int max_t, int max_hamming, int min_diff, mage_dmatch* d_out, int out_cap,
                         int* d_counts, cudaStream_t s)
 {
     MAGE_CUDA_TRY(cudaMemcpyAsync(m->d_jobs, m->h_jobs, sizeof(MatchJob) * n_pairs, cudaMemcpyHostToDevice, s));
-    dim3 grid(div_up(max_q, kQPerBlock), n_pairs);
     MAGE_CUDA_TRY(cudaMemsetAsync(m->d_best, 0xFF, sizeof(unsigned) * 4 * (size_t)n_pairs * m->max_desc, s));
-    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, max_hamming); }
+    { ProfScope ps(PROF_MATCH_DIR, s); MAGE_CUDA_TRY(launch_match_dir(m->d_jobs, m->d_best, m->max_desc, max_q, max_t, n_pairs, max_hamming, s)); }
     { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, min_diff, d_out, out_cap, d_counts); }
     MAGE_CUDA_TRY(cudaGetLastError());
     return MAGE_OK;
@@ -332,7 +562,7 @@ extern "C" int mage_match_bf(mage_matcher_t m, const uint8_t* descA, int nA, con
     MatchJob& j = m->h_jobs[0];
     j.desc[0] = dA; j.desc[1] = dB; j.mask[0] = maskA ? dmA : nullptr; j.mask[1] = maskB ? dmB : nullptr;
     j.count_ptr[0] = j.count_ptr[1] = nullptr; j.count[0] = nA; j.count[1] = nB; j.cap = m->max_desc;
-    int rc = match_launch(m, 1, nA > nB ? nA : nB, max_hamming, min_diff, dOut, m->max_desc, dCnt, s);
+    int rc = match_launch(m, 1, nA, nB, max_hamming, min_diff, dOut, m->max_desc, dCnt, s);
     if (rc != MAGE_OK) return rc;
     MAGE_CUDA_TRY(cudaMemcpyAsync(m->h_count, dCnt, sizeof(int), cudaMemcpyDeviceToHost, s));
     MAGE_CUDA_TRY(cudaMemcpyAsync(m->h_out, dOut, sizeof(mage_dmatch) * (size_t)nA, cudaMemcpyDeviceToHost, s));
@@ -375,10 +605,9 @@ extern "C" int mage_match_run_jobs(mage_matcher_t m, int first_pair, int n_pairs
                  MAGE_ERR_INVALID, "mage_match_run_jobs: pair range outside the registered table");
     cudaStream_t s = (cudaStream_t)stream;
     const int cap = m->h_jobs[first_pair].cap;
-    dim3 grid(div_up(cap, kQPerBlock), n_pairs);
     unsigned* best = m->d_best + (size_t)first_pair * 4 * m->max_desc;
     MAGE_CUDA_TRY(cudaMemsetAsync(best, 0xFF, sizeof(unsigned) * 4 * (size_t)n_pairs * m->max_desc, s));
-    { ProfScope ps(PROF_MATCH_DIR, s); k_match_dir<<<grid, kWarps * 32, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, max_hamming); }
+    { ProfScope ps(PROF_MATCH_DIR, s); MAGE_CUDA_TRY(launch_match_dir(m->d_jobs + first_pair, best, m->max_desc, cap, cap, n_pairs, max_hamming, s)); }
     { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, min_diff, d_matches, capacity, d_match_counts); }
     MAGE_CUDA_TRY(cudaGetLastError());
     return MAGE_OK;
