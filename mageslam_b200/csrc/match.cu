@@ -150,12 +150,12 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_dir_popc(const MatchJob* 
 // expansion of tile j + 1 and the read-out of tile j - 1 run while the tensor core works on tile j; the accumulators alternate
 // between the two halves of the 512 TMEM columns. Masked or absent descriptors expand to zero bytes: acc = 0 < T.
 constexpr int kUmmaM = 128, kUmmaN = 256;
-constexpr int kUmmaThreads = 512;                                  // 16 warps: the expansion and the read-out are latency bound with fewer
+constexpr int kUmmaThreads = 512;                                  // 16 working warps (the expansion and the read-out are latency bound with fewer) + 1 issuing warp
 constexpr int kUmmaMaxHamming = 64;                               // T must stay positive; wider radii take the popc kernel
 constexpr uint32_t kUmmaLBO = 128, kUmmaSBO = 256;                // K-chunk (16 B) stride, 8-row group stride inside one K = 32 step
 constexpr uint32_t kUmmaStepA = kUmmaM * 32, kUmmaStepB = kUmmaN * 32;      // bytes per K = 32 step
 constexpr uint32_t kUmmaBytesA = kUmmaM * 256, kUmmaBytesB = kUmmaN * 256;
-constexpr size_t kUmmaSmemBytes = kUmmaBytesA + 2 * (size_t)kUmmaBytesB + 1024;
+constexpr size_t kUmmaSmemBytes = kUmmaBytesA + (size_t)kUmmaBytesB + 1024;
 // instruction descriptor (kind::i8): D = s32, A and B signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kUmmaIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
 
@@ -200,7 +200,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 // A pair inside the radius makes four packed updates, two of which need the value an atomic returns: ~2 L2 round trips. With one CTA
 // of 8 warps per SM nothing hides that latency, so the read-out only appends (query row, train, distance) to a shared-memory list and
 // the whole CTA drains the list at the end, one entry per thread, all round trips in flight together.
-constexpr int kUmmaListCap = 4096;
+constexpr int kUmmaListCap = 2048;
 __device__ __forceinline__ void match_update(unsigned qidx, unsigned tidx, unsigned d, unsigned* fbest, unsigned* fsecond, unsigned* bbest, unsigned* bsecond)
 {
     const unsigned kf = (d << 16) | tidx, kb = (d << 16) | qidx;
@@ -221,25 +221,28 @@ __device__ __noinline__ void match_update_direct(unsigned qidx, unsigned tidx, u
 __device__ __forceinline__ void umma_expand_half(uint8_t* tile, uint32_t kstep_bytes, int row, int h, const uint4& v, bool present)
 {
     uint8_t* dst = tile + (row >> 3) * kUmmaSBO + (row & 7) * 16 + (4 * h) * kstep_bytes;
+    if (!present) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) *reinterpret_cast<uint4*>(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO) = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 8; q++) {                                  // chunk q of this half = K positions 16 (8 h + q) .. + 15
-        uint4 c = make_uint4(0u, 0u, 0u, 0u);
-        if (present) {
-            const uint32_t x = w[q >> 1] >> (4 * (q & 1));
-            c.x = 0xFFFFFFFFu - (x & 0x01010101u) * 0xFEu;
-            c.y = 0xFFFFFFFFu - ((x >> 1) & 0x01010101u) * 0xFEu;
-            c.z = 0xFFFFFFFFu - ((x >> 2) & 0x01010101u) * 0xFEu;
-            c.w = 0xFFFFFFFFu - ((x >> 3) & 0x01010101u) * 0xFEu;
-        }
+        const uint32_t x = w[q >> 1] >> (4 * (q & 1));
+        uint4 c;
+        c.x = 0xFFFFFFFFu - (x & 0x01010101u) * 0xFEu;
+        c.y = 0xFFFFFFFFu - ((x >> 1) & 0x01010101u) * 0xFEu;
+        c.z = 0xFFFFFFFFu - ((x >> 2) & 0x01010101u) * 0xFEu;
+        c.w = 0xFFFFFFFFu - ((x >> 3) & 0x01010101u) * 0xFEu;
         *reinterpret_cast<uint4*>(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO) = c;
     }
 }
 
-__global__ void __launch_bounds__(kUmmaThreads, 1) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
+__global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
 {
     extern __shared__ uint8_t umma_smem_raw[];
-    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t hit_list[kUmmaListCap];                    // row | train << 7 | distance << 23
     __shared__ int hit_count;
@@ -263,13 +266,12 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_match_dir(const MatchJob* _
     const int thr = 256 - 2 * max_hamming;
 
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(&s_tmem)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
         hit_count = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[0])), "r"(1) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[1])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar)), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -287,8 +289,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_match_dir(const MatchJob* _
     // read-out of the tile issued `it_done` iterations ago: warp w owns TMEM lanes 32 (w % 4) .. + 31 (queries) and, by w / 4, one quarter
     // of the 256 train columns
     auto read_out = [&](int it_done, int tile) {
-        const int buf = it_done & 1;
-        mbar_wait_bounded(smem_addr(&mbar[buf]), (uint32_t)(it_done >> 1) & 1u);
+        mbar_wait_bounded(smem_addr(&mbar), (uint32_t)it_done & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = 32 * (warp & 3) + lane;
         const unsigned qidx = (unsigned)(q0 + row);
@@ -296,16 +297,20 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_match_dir(const MatchJob* _
         for (int c = 0; c < 2; c++) {
             const int col0 = (warp >> 2) * 64 + c * 32;
             uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * kUmmaN + col0), v);
-            int m = __vimax3_s32((int)v[0], (int)v[1], (int)v[2]);
+            tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
+            // maxima of the four groups of 8 columns; a group is scanned only when some lane of the warp has a hit in it
 #pragma unroll
-            for (int i = 3; i + 1 < 32; i += 2) m = __vimax3_s32(m, (int)v[i], (int)v[i + 1]);
-            m = max(m, (int)v[31]);
-            if (m >= thr) {
+            for (int gq = 0; gq < 4; gq++) {
+                const uint32_t* u = v + 8 * gq;
+                int m = __vimax3_s32((int)u[0], (int)u[1], (int)u[2]);
+                m = __vimax3_s32(m, (int)u[3], (int)u[4]);
+                m = __vimax3_s32(m, (int)u[5], (int)u[6]);
+                m = max(m, (int)u[7]);
+                if (m < thr) continue;
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    if ((int)v[i] < thr) continue;
-                    const unsigned tidx = (unsigned)(tile * kUmmaN + col0 + i), d = (256u - v[i]) >> 1;
+                for (int i = 0; i < 8; i++) {
+                    if ((int)u[i] < thr) continue;
+                    const unsigned tidx = (unsigned)(tile * kUmmaN + col0 + 8 * gq + i), d = (256u - u[i]) >> 1;
                     const int slot = atomicAdd(&hit_count, 1);
                     if (slot < kUmmaListCap) hit_list[slot] = (unsigned)row | (tidx << 7) | (d << 23);
                     else match_update_direct(qidx, tidx, d, fbest, fsecond, bbest, bsecond);
@@ -315,37 +320,47 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_match_dir(const MatchJob* _
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
-    int it = 0, prev_tile = -1;
+    // Warps 0-15 expand and read out; warp 16 only issues the MMAs. Two CTAs share an SM (single B buffer, 256 TMEM columns each): while
+    // the tensor core works on one CTA's tile the other CTA expands or reads out, and 34 resident warps hide the latencies of those
+    // phases, which 17 did not (measured: 0.27 ms per 128 pairs with one double-buffered CTA per SM).
+    const bool mma_warp = warp == kUmmaThreads / 32;
+    auto load_half = [&](int tile, bool& present) {
+        const int ti = tile * kUmmaN + (tid & (kUmmaN - 1));
+        present = ti < nT && (!mT || mT[ti]);
+        return present ? __ldg(T4 + (size_t)ti * 2 + ((tid / kUmmaN) & 1)) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    int it = 0;
+    bool present = false;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (!mma_warp) v = load_half(blockIdx.z, present);
     for (int tile = blockIdx.z; tile < ntiles; tile += gridDim.z, it++) {
-        const int buf = it & 1;
-        {   // B tile: thread = (train row, half). The MMA that last read this buffer (iteration it - 2) was waited for in read_out(it - 2).
-            const int row = tid & (kUmmaN - 1), h = tid / kUmmaN, ti = tile * kUmmaN + row;
-            const bool present = ti < nT && (!mT || mT[ti]);
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (present) v = __ldg(T4 + (size_t)ti * 2 + h);
-            umma_expand_half(sB + (size_t)buf * kUmmaBytesB, kUmmaStepB, row, h, v, present);
+        if (!mma_warp) {
+            // B tile: thread = (train row, half). Every thread waited for the MMA that last read the buffer in its read_out.
+            umma_expand_half(sB, kUmmaStepB, tid & (kUmmaN - 1), (tid / kUmmaN) & 1, v, present);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core's reads
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a0 = smem_addr(sA), b0 = smem_addr(sB + (size_t)buf * kUmmaBytesB);
+        __syncthreads();                                                      // B expanded, accumulators of the previous tile read out
+        if (mma_warp) {
+            if (lane == 0) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = smem_addr(sA), b0 = smem_addr(sB);
 #pragma unroll
-            for (int ks = 0; ks < 8; ks++)
-                umma_i8(tmem + (uint32_t)(buf * kUmmaN), umma_desc(a0 + ks * kUmmaStepA), umma_desc(b0 + ks * kUmmaStepB), ks > 0 ? 1u : 0u);
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mbar[buf])) : "memory");
+                for (int ks = 0; ks < 8; ks++) umma_i8(tmem, umma_desc(a0 + ks * kUmmaStepA), umma_desc(b0 + ks * kUmmaStepB), ks > 0 ? 1u : 0u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mbar)) : "memory");
+            }
+            __syncwarp();
+        } else {
+            if (tile + (int)gridDim.z < ntiles) v = load_half(tile + gridDim.z, present);      // in flight during the MMA and the read-out
+            read_out(it, tile);
         }
-        if (it > 0) read_out(it - 1, prev_tile);
-        prev_tile = tile;
     }
-    if (it > 0) read_out(it - 1, prev_tile);
     __syncthreads();
     for (int i = tid, n = min(hit_count, kUmmaListCap); i < n; i += blockDim.x) {
         const unsigned e = hit_list[i];
         match_update((unsigned)q0 + (e & 127u), (e >> 7) & 0xFFFFu, e >> 23, fbest, fsecond, bbest, bsecond);
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
 // grid for either matcher kernel; the tcgen05 one splits the train tiles over blockIdx.z until there are enough CTAs to fill the GPU
@@ -363,7 +378,7 @@ static cudaError_t launch_match_dir(const MatchJob* d_jobs, unsigned* best, int 
     const int gx = std::max(1, div_up(max_q, kUmmaM)), tiles = std::max(1, div_up(max_t, kUmmaN));
     const int gz = std::min(tiles, std::max(1, div_up(2 * 148, gx * n_pairs)));
     dim3 grid(gx, n_pairs, gz);
-    k_match_dir<<<grid, kUmmaThreads, kUmmaSmemBytes, s>>>(d_jobs, best, max_desc, max_hamming);
+    k_match_dir<<<grid, kUmmaThreads + 32, kUmmaSmemBytes, s>>>(d_jobs, best, max_desc, max_hamming);
     return cudaSuccess;
 }
 

@@ -25,7 +25,9 @@ def noisy_copy(rng, A, flips, dup_frac=0.05):
     return B
 
 
-@pytest.mark.parametrize("n,flips,maxd,mind", [(2000, 12, 30, 1), (777, 30, 40, 3), (33, 4, 30, 1), (1500, 60, 64, 2), (256, 8, 30, 0)])
+# maxd <= 64 runs the tcgen05 kernel (sizes straddle its 128-query / 256-train tiles), larger radii the xor/popc kernel
+@pytest.mark.parametrize("n,flips,maxd,mind", [(2000, 12, 30, 1), (777, 30, 40, 3), (33, 4, 30, 1), (1500, 60, 64, 2), (256, 8, 30, 0),
+                                               (129, 6, 30, 1), (300, 6, 0, 0), (600, 40, 100, 2), (1000, 90, 65, 1)])
 def test_match_equals_oracle(n, flips, maxd, mind):
     rng = np.random.default_rng(n)
     A = rng.integers(0, 256, (n, 32), dtype=np.uint8)
@@ -34,6 +36,19 @@ def test_match_equals_oracle(n, flips, maxd, mind):
     ref = orc.match(A, B, maxd, mind)
     assert as_tuples(got) == as_tuples(ref, "query", "train")
     assert len(ref) > 0
+
+
+@pytest.mark.parametrize("mind", [0, 1])
+def test_match_many_hits_per_query(mind):
+    """8 distinct descriptors repeated 128 times: 128 x 128 in-radius pairs per query block overflow the kernel's shared-memory hit list
+    (the overflow takes the direct atomic path); ties resolve to the lowest index and are rejected when minDiff >= 1."""
+    rng = np.random.default_rng(11)
+    base = rng.integers(0, 256, (8, 32), dtype=np.uint8)
+    A = np.repeat(base, 128, axis=0)
+    B = np.tile(base, (128, 1))
+    got = Match(A, B, None, None, 30, mind)
+    ref = orc.match(A, B, 30, mind)
+    assert as_tuples(got) == as_tuples(ref, "query", "train")
 
 
 def test_match_with_masks_and_empty_sides():
