@@ -146,16 +146,16 @@ __global__ void __launch_bounds__(kWarps * 32) k_match_dir_popc(const MatchJob* 
 // The accumulators come back with tcgen05.ld (thread = query row, 32 train columns at a time); a running maximum against
 // T = 256 - 2 maxHamming finds the columns inside the radius -- their exact distance is (256 - acc) / 2 -- and those
 // (about 1 per query) make the same four packed atomic updates as above, so the statistics and hence the matches are identical.
-// CTA = 128 queries (A tile expanded once, 32 KB) x a walk over the train tiles (B tile 64 KB, double-buffered): the bit -> byte
+// CTA = 128 queries (A tile expanded once, 32 KB) x a walk over the train tiles of 128 (B tile 32 KB, double-buffered): the bit -> byte
 // expansion of tile j + 1 and the read-out of tile j - 1 run while the tensor core works on tile j; the accumulators alternate
-// between the two halves of the 512 TMEM columns. Masked or absent descriptors expand to zero bytes: acc = 0 < T.
-constexpr int kUmmaM = 128, kUmmaN = 256;
+// between the two halves of the CTA's 256 TMEM columns. Masked or absent descriptors expand to zero bytes: acc = 0 < T.
+constexpr int kUmmaM = 128, kUmmaN = 128;
 constexpr int kUmmaThreads = 512;                                  // 16 working warps (the expansion and the read-out are latency bound with fewer) + 1 issuing warp
 constexpr int kUmmaMaxHamming = 64;                               // T must stay positive; wider radii take the popc kernel
 constexpr uint32_t kUmmaLBO = 128, kUmmaSBO = 256;                // K-chunk (16 B) stride, 8-row group stride inside one K = 32 step
 constexpr uint32_t kUmmaStepA = kUmmaM * 32, kUmmaStepB = kUmmaN * 32;      // bytes per K = 32 step
 constexpr uint32_t kUmmaBytesA = kUmmaM * 256, kUmmaBytesB = kUmmaN * 256;
-constexpr size_t kUmmaSmemBytes = kUmmaBytesA + (size_t)kUmmaBytesB + 1024;
+constexpr size_t kUmmaSmemBytes = kUmmaBytesA + 2 * (size_t)kUmmaBytesB + 1024;
 // instruction descriptor (kind::i8): D = s32, A and B signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kUmmaIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kUmmaN >> 3) << 17) | ((uint32_t)(kUmmaM >> 4) << 24);
 
@@ -214,21 +214,21 @@ __device__ __noinline__ void match_update_direct(unsigned qidx, unsigned tidx, u
     match_update(qidx, tidx, d, fbest, fsecond, bbest, bsecond);
 }
 
-// half a descriptor (4 words; half h = words 4 h .. 4 h + 3) -> its 8 K chunks of signed bytes at `row` of an operand tile. Any fixed
-// assignment of descriptor bits to K positions gives the same dot product as long as both operands use it, so a group of four K
-// positions takes bits b, b + 8, b + 16, b + 24 of one word: (w >> b) & 0x01010101 is already the 0/1 byte form (one shift, one AND),
-// and 0xFFFFFFFF - 0xFE t turns 1 -> 0x01 (+1), 0 -> 0xFF (-1) in every byte with one IMAD. An absent row is all zero bytes.
-__device__ __forceinline__ void umma_expand_half(uint8_t* tile, uint32_t kstep_bytes, int row, int h, const uint4& v, bool present)
+// NW consecutive descriptor words (starting at word first_chunk / 2) -> their 2 NW K chunks of signed bytes at `row` of an operand tile.
+// Any fixed assignment of descriptor bits to K positions gives the same dot product as long as both operands use it, so a group of
+// four K positions takes bits b, b + 8, b + 16, b + 24 of one word: (w >> b) & 0x01010101 is already the 0/1 byte form (one shift, one
+// AND), and 0xFFFFFFFF - 0xFE t turns 1 -> 0x01 (+1), 0 -> 0xFF (-1) in every byte with one IMAD. An absent row is all zero bytes.
+template <int NW>
+__device__ __forceinline__ void umma_expand(uint8_t* tile, uint32_t kstep_bytes, int row, int first_chunk, const uint32_t (&w)[NW], bool present)
 {
-    uint8_t* dst = tile + (row >> 3) * kUmmaSBO + (row & 7) * 16 + (4 * h) * kstep_bytes;
+    uint8_t* dst = tile + (row >> 3) * kUmmaSBO + (row & 7) * 16 + (first_chunk >> 1) * kstep_bytes;       // first_chunk is even
     if (!present) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) *reinterpret_cast<uint4*>(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO) = make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 2 * NW; q++) *reinterpret_cast<uint4*>(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO) = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int q = 0; q < 8; q++) {                                  // chunk q of this half = K positions 16 (8 h + q) .. + 15
+    for (int q = 0; q < 2 * NW; q++) {                             // chunk first_chunk + q = K positions 16 (first_chunk + q) .. + 15
         const uint32_t x = w[q >> 1] >> (4 * (q & 1));
         uint4 c;
         c.x = 0xFFFFFFFFu - (x & 0x01010101u) * 0xFEu;
@@ -242,7 +242,7 @@ __device__ __forceinline__ void umma_expand_half(uint8_t* tile, uint32_t kstep_b
 __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
 {
     extern __shared__ uint8_t umma_smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t mbar[2];
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t hit_list[kUmmaListCap];                    // row | train << 7 | distance << 23
     __shared__ int hit_count;
@@ -271,7 +271,8 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
     }
     if (tid == 0) {
         hit_count = 0;
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar)), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[0])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[1])), "r"(1) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -284,77 +285,84 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
         const bool present = qi < nQ && (!mQ || mQ[qi]);
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (present) v = __ldg(Q4 + (size_t)qi * 2 + h);
-        umma_expand_half(sA, kUmmaStepA, row, h, v, present);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        umma_expand<4>(sA, kUmmaStepA, row, 8 * h, w, present);
     }
-    // read-out of the tile issued `it_done` iterations ago: warp w owns TMEM lanes 32 (w % 4) .. + 31 (queries) and, by w / 4, one quarter
-    // of the 256 train columns
+    // read-out of the tile issued in iteration it_done: warp w owns TMEM lanes 32 (w % 4) .. + 31 (queries) and, by w / 4, 32 of the
+    // 128 train columns
     auto read_out = [&](int it_done, int tile) {
-        mbar_wait_bounded(smem_addr(&mbar), (uint32_t)it_done & 1u);
+        const int buf = it_done & 1;
+        mbar_wait_bounded(smem_addr(&mbar[buf]), (uint32_t)(it_done >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = 32 * (warp & 3) + lane;
         const unsigned qidx = (unsigned)(q0 + row);
-#pragma unroll 1
-        for (int c = 0; c < 2; c++) {
-            const int col0 = (warp >> 2) * 64 + c * 32;
-            uint32_t v[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)col0, v);
-            // maxima of the four groups of 8 columns; a group is scanned only when some lane of the warp has a hit in it
+        const int col0 = (warp >> 2) * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(buf * kUmmaN + col0), v);
+        // maxima of the four groups of 8 columns; a group is scanned only when some lane of the warp has a hit in it
 #pragma unroll
-            for (int gq = 0; gq < 4; gq++) {
-                const uint32_t* u = v + 8 * gq;
-                int m = __vimax3_s32((int)u[0], (int)u[1], (int)u[2]);
-                m = __vimax3_s32(m, (int)u[3], (int)u[4]);
-                m = __vimax3_s32(m, (int)u[5], (int)u[6]);
-                m = max(m, (int)u[7]);
-                if (m < thr) continue;
+        for (int gq = 0; gq < 4; gq++) {
+            const uint32_t* u = v + 8 * gq;
+            int m = __vimax3_s32((int)u[0], (int)u[1], (int)u[2]);
+            m = __vimax3_s32(m, (int)u[3], (int)u[4]);
+            m = __vimax3_s32(m, (int)u[5], (int)u[6]);
+            m = max(m, (int)u[7]);
+            if (m < thr) continue;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if ((int)u[i] < thr) continue;
-                    const unsigned tidx = (unsigned)(tile * kUmmaN + col0 + 8 * gq + i), d = (256u - u[i]) >> 1;
-                    const int slot = atomicAdd(&hit_count, 1);
-                    if (slot < kUmmaListCap) hit_list[slot] = (unsigned)row | (tidx << 7) | (d << 23);
-                    else match_update_direct(qidx, tidx, d, fbest, fsecond, bbest, bsecond);
-                }
+            for (int i = 0; i < 8; i++) {
+                if ((int)u[i] < thr) continue;
+                const unsigned tidx = (unsigned)(tile * kUmmaN + col0 + 8 * gq + i), d = (256u - u[i]) >> 1;
+                const int slot = atomicAdd(&hit_count, 1);
+                if (slot < kUmmaListCap) hit_list[slot] = (unsigned)row | (tidx << 7) | (d << 23);
+                else match_update_direct(qidx, tidx, d, fbest, fsecond, bbest, bsecond);
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
 
-    // Warps 0-15 expand and read out; warp 16 only issues the MMAs. Two CTAs share an SM (single B buffer, 256 TMEM columns each): while
-    // the tensor core works on one CTA's tile the other CTA expands or reads out, and 34 resident warps hide the latencies of those
-    // phases, which 17 did not (measured: 0.27 ms per 128 pairs with one double-buffered CTA per SM).
+    // Warps 0-15 expand and read out; warp 16 only issues the MMAs (the issue blocks while the tensor pipe's queue is full and must not
+    // hold up a warp that has other work). The B tile and the accumulators are double-buffered, so the tensor core works on tile j
+    // while tile j + 1 is expanded and tile j - 1 read out; one CTA barrier per tile hands the expanded buffer and the drained
+    // accumulator half to the issuing warp. Two such CTAs share an SM (97 KB of shared memory and 256 TMEM columns each) to hide the
+    // latencies of the expansion and the read-out.
     const bool mma_warp = warp == kUmmaThreads / 32;
-    auto load_half = [&](int tile, bool& present) {
-        const int ti = tile * kUmmaN + (tid & (kUmmaN - 1));
+    const int brow = tid & (kUmmaN - 1), bquarter = (tid / kUmmaN) & 3;           // B tile: thread = (train row, quarter descriptor)
+    auto load_quarter = [&](int tile, bool& present) {
+        const int ti = tile * kUmmaN + brow;
         present = ti < nT && (!mT || mT[ti]);
-        return present ? __ldg(T4 + (size_t)ti * 2 + ((tid / kUmmaN) & 1)) : make_uint4(0u, 0u, 0u, 0u);
+        return present ? __ldg(reinterpret_cast<const uint2*>(T4 + (size_t)ti * 2) + bquarter) : make_uint2(0u, 0u);
     };
-    int it = 0;
+    int it = 0, prev_tile = -1;
     bool present = false;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (!mma_warp) v = load_half(blockIdx.z, present);
+    uint2 v = make_uint2(0u, 0u);
+    if (!mma_warp) v = load_quarter(blockIdx.z, present);
     for (int tile = blockIdx.z; tile < ntiles; tile += gridDim.z, it++) {
+        const int buf = it & 1;
         if (!mma_warp) {
-            // B tile: thread = (train row, half). Every thread waited for the MMA that last read the buffer in its read_out.
-            umma_expand_half(sB, kUmmaStepB, tid & (kUmmaN - 1), (tid / kUmmaN) & 1, v, present);
+            // the MMA that last read this buffer (iteration it - 2) was waited for by every thread in read_out(it - 2)
+            const uint32_t w[2] = {v.x, v.y};
+            umma_expand<2>(sB + (size_t)buf * kUmmaBytesB, kUmmaStepB, brow, 4 * bquarter, w, present);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                                      // B expanded, accumulators of the previous tile read out
+        __syncthreads();                                                      // B expanded, accumulator half it & 1 read out
         if (mma_warp) {
             if (lane == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = smem_addr(sA), b0 = smem_addr(sB);
+                const uint32_t a0 = smem_addr(sA), b0 = smem_addr(sB + (size_t)buf * kUmmaBytesB);
 #pragma unroll
-                for (int ks = 0; ks < 8; ks++) umma_i8(tmem, umma_desc(a0 + ks * kUmmaStepA), umma_desc(b0 + ks * kUmmaStepB), ks > 0 ? 1u : 0u);
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mbar)) : "memory");
+                for (int ks = 0; ks < 8; ks++)
+                    umma_i8(tmem + (uint32_t)(buf * kUmmaN), umma_desc(a0 + ks * kUmmaStepA), umma_desc(b0 + ks * kUmmaStepB), ks > 0 ? 1u : 0u);
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&mbar[buf])) : "memory");
             }
             __syncwarp();
         } else {
-            if (tile + (int)gridDim.z < ntiles) v = load_half(tile + gridDim.z, present);      // in flight during the MMA and the read-out
-            read_out(it, tile);
+            if (tile + (int)gridDim.z < ntiles) v = load_quarter(tile + gridDim.z, present);     // in flight during the read-out
+            if (it > 0) read_out(it - 1, prev_tile);
         }
+        prev_tile = tile;
     }
+    if (!mma_warp && it > 0) read_out(it - 1, prev_tile);
     __syncthreads();
     for (int i = tid, n = min(hit_count, kUmmaListCap); i < n; i += blockDim.x) {
         const unsigned e = hit_list[i];

@@ -15,4 +15,5 @@ ncu --set full --clock-control none --import-source on -k regex:"k_ba_step" -s 1
 python tools/quick_bench_ba.py > gpurun_out/quick_bench_ba.log 2>&1
 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1
 python tools/global_ba_check.py > gpurun_out/global_ba_check.log 2>&1
+compute-sanitizer --tool memcheck python tools/sanitize_match.py > gpurun_out/sanitizer_match.log 2>&1
 tail -2 gpurun_out/pytest_gpu.log; tail -c 600 gpurun_out/bench_n1.json

@@ -17,6 +17,7 @@ def pipe_table(reps):
     cols = [("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"), ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU %"),
             ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA %"), ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU %"),
             ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU %"), ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 %"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
             ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1TEX %"), ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %")]
     lines, seen = [], set()
     for rep in reps:
