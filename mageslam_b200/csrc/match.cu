@@ -218,13 +218,18 @@ __device__ __noinline__ void match_update_direct(unsigned qidx, unsigned tidx, u
 // Any fixed assignment of descriptor bits to K positions gives the same dot product as long as both operands use it, so a group of
 // four K positions takes bits b, b + 8, b + 16, b + 24 of one word: (w >> b) & 0x01010101 is already the 0/1 byte form (one shift, one
 // AND), and 0xFFFFFFFF - 0xFE t turns 1 -> 0x01 (+1), 0 -> 0xFF (-1) in every byte with one IMAD. An absent row is all zero bytes.
-template <int NW>
-__device__ __forceinline__ void umma_expand(uint8_t* tile, uint32_t kstep_bytes, int row, int first_chunk, const uint32_t (&w)[NW], bool present)
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& c)       // 32-bit shared-window address: no generic-pointer arithmetic
 {
-    uint8_t* dst = tile + (row >> 3) * kUmmaSBO + (row & 7) * 16 + (first_chunk >> 1) * kstep_bytes;       // first_chunk is even
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
+}
+
+template <int NW>
+__device__ __forceinline__ void umma_expand(uint32_t tile, uint32_t kstep_bytes, int row, int first_chunk, const uint32_t (&w)[NW], bool present)
+{
+    const uint32_t dst = tile + (row >> 3) * kUmmaSBO + (row & 7) * 16 + (first_chunk >> 1) * kstep_bytes;       // first_chunk is even
     if (!present) {
 #pragma unroll
-        for (int q = 0; q < 2 * NW; q++) *reinterpret_cast<uint4*>(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO) = make_uint4(0u, 0u, 0u, 0u);
+        for (int q = 0; q < 2 * NW; q++) sts128(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO, make_uint4(0u, 0u, 0u, 0u));
         return;
     }
 #pragma unroll
@@ -235,7 +240,7 @@ __device__ __forceinline__ void umma_expand(uint8_t* tile, uint32_t kstep_bytes,
         c.y = 0xFFFFFFFFu - ((x >> 1) & 0x01010101u) * 0xFEu;
         c.z = 0xFFFFFFFFu - ((x >> 2) & 0x01010101u) * 0xFEu;
         c.w = 0xFFFFFFFFu - ((x >> 3) & 0x01010101u) * 0xFEu;
-        *reinterpret_cast<uint4*>(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO) = c;
+        sts128(dst + (q >> 1) * kstep_bytes + (q & 1) * kUmmaLBO, c);
     }
 }
 
@@ -252,8 +257,8 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
     const int q0 = blockIdx.x * kUmmaM;
     const int ntiles = (nT + kUmmaN - 1) / kUmmaN;
     if (q0 >= nQ || (int)blockIdx.z >= ntiles) return;
-    uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)umma_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sB = sA + kUmmaBytesA;                                // two buffers of kUmmaBytesB
+    const uint32_t sA = (smem_addr(umma_smem_raw) + 1023u) & ~1023u;         // shared-window addresses
+    const uint32_t sB = sA + kUmmaBytesA;                          // two buffers of kUmmaBytesB
     const uint4* Q4 = reinterpret_cast<const uint4*>(job.desc[0]);
     const uint4* T4 = reinterpret_cast<const uint4*>(job.desc[1]);
     const uint8_t* mQ = job.mask[0];
@@ -341,7 +346,7 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
         if (!mma_warp) {
             // the MMA that last read this buffer (iteration it - 2) was waited for by every thread in read_out(it - 2)
             const uint32_t w[2] = {v.x, v.y};
-            umma_expand<2>(sB + (size_t)buf * kUmmaBytesB, kUmmaStepB, brow, 4 * bquarter, w, present);
+            umma_expand<2>(sB + (uint32_t)buf * kUmmaBytesB, kUmmaStepB, brow, 4 * bquarter, w, present);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -349,7 +354,7 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
         if (mma_warp) {
             if (lane == 0) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = smem_addr(sA), b0 = smem_addr(sB + (size_t)buf * kUmmaBytesB);
+                const uint32_t a0 = sA, b0 = sB + (uint32_t)buf * kUmmaBytesB;
 #pragma unroll
                 for (int ks = 0; ks < 8; ks++)
                     umma_i8(tmem + (uint32_t)(buf * kUmmaN), umma_desc(a0 + ks * kUmmaStepA), umma_desc(b0 + ks * kUmmaStepB), ks > 0 ? 1u : 0u);
