@@ -386,8 +386,6 @@ static cudaError_t launch_match_dir(const MatchJob* d_jobs, unsigned* best, int 
         k_match_dir_popc<<<grid, kWarps * 32, 0, s>>>(d_jobs, best, max_desc, max_hamming);
         return cudaSuccess;
     }
-    static cudaError_t attr = cudaFuncSetAttribute(k_match_dir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemBytes);
-    if (attr != cudaSuccess) return attr;
     const int gx = std::max(1, div_up(max_q, kUmmaM)), tiles = std::max(1, div_up(max_t, kUmmaN));
     const int gz = std::min(tiles, std::max(1, div_up(2 * 148, gx * n_pairs)));
     dim3 grid(gx, n_pairs, gz);
@@ -539,6 +537,7 @@ extern "C" int mage_matcher_create(int max_descriptors, int max_pairs, mage_matc
     if (e == cudaSuccess) e = cudaMallocHost(&m->h_out, sizeof(mage_dmatch) * (size_t)max_descriptors);
     if (e == cudaSuccess) e = cudaMallocHost(&m->h_count, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_dir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemBytes);      // per device
     if (e != cudaSuccess) { set_error("mage_matcher_create: %s", cudaGetErrorString(e)); mage_matcher_destroy(m); return MAGE_ERR_CUDA; }
     *out = m;
     return MAGE_OK;
