@@ -247,7 +247,7 @@ __device__ __forceinline__ void umma_expand(uint32_t tile, uint32_t kstep_bytes,
 __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJob* __restrict__ jobs, unsigned* __restrict__ stats, int stride, int max_hamming)
 {
     extern __shared__ uint8_t umma_smem_raw[];
-    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ __align__(8) uint64_t mbar[2], full[2];           // MMA of a tile done / B buffer of a tile expanded (512 arrivals)
     __shared__ uint32_t s_tmem;
     __shared__ uint32_t hit_list[kUmmaListCap];                    // row | train << 7 | distance << 23
     __shared__ int hit_count;
@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
         hit_count = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[0])), "r"(1) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&mbar[1])), "r"(1) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&full[0])), "r"(kUmmaThreads) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(&full[1])), "r"(kUmmaThreads) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -327,8 +329,9 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
 
     // Warps 0-15 expand and read out; warp 16 only issues the MMAs (the issue blocks while the tensor pipe's queue is full and must not
     // hold up a warp that has other work). The B tile and the accumulators are double-buffered, so the tensor core works on tile j
-    // while tile j + 1 is expanded and tile j - 1 read out; one CTA barrier per tile hands the expanded buffer and the drained
-    // accumulator half to the issuing warp. Two such CTAs share an SM (97 KB of shared memory and 256 TMEM columns each) to hide the
+    // while tile j + 1 is expanded and tile j - 1 read out. No CTA-wide barrier in the loop: every working thread arrives on full[buf]
+    // once it has expanded its part of the buffer (and, by program order, read its part of the accumulator half out); the issuing
+    // thread waits for the 512 arrivals, the working threads wait for the MMA's commit only when they read that tile out. Two such CTAs share an SM (97 KB of shared memory and 256 TMEM columns each) to hide the
     // latencies of the expansion and the read-out.
     const bool mma_warp = warp == kUmmaThreads / 32;
     const int brow = tid & (kUmmaN - 1), bquarter = (tid / kUmmaN) & 3;           // B tile: thread = (train row, quarter descriptor)
@@ -349,10 +352,10 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
             umma_expand<2>(sB + (uint32_t)buf * kUmmaBytesB, kUmmaStepB, brow, 4 * bquarter, w, present);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> visible to the tensor core's reads
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                                      // B expanded, accumulator half it & 1 read out
         if (mma_warp) {
             if (lane == 0) {
+                // every working thread has expanded its part of B[buf] and read its part of accumulator half `buf` out (tile it - 2)
+                mbar_wait_bounded(smem_addr(&full[buf]), (uint32_t)(it >> 1) & 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = sA, b0 = sB + (uint32_t)buf * kUmmaBytesB;
 #pragma unroll
@@ -362,6 +365,8 @@ __global__ void __launch_bounds__(kUmmaThreads + 32, 2) k_match_dir(const MatchJ
             }
             __syncwarp();
         } else {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(&full[buf])) : "memory");
             if (tile + (int)gridDim.z < ntiles) v = load_quarter(tile + gridDim.z, present);     // in flight during the read-out
             if (it > 0) read_out(it - 1, prev_tile);
         }
