@@ -57,3 +57,19 @@ def test_product_does_not_import_the_oracle():
                 if re.search(r"oracle/|liborb_oracle|libba_oracle|libbundler_ref|tests\.oracle|from tests", txt):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_tensor_core_and_tma_kernels_are_in_the_library():
+    """The brute-force matcher must be the tcgen05 kernel (tensor-core MMA, TMEM load, commit) and the TMA variant of FAST must use the
+    tensor-map load: checked on the SASS of the built library (tools/sass_evidence.py), so a silent fall-back to CUDA-core code shows."""
+    import shutil
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not installed")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_evidence
+    cnt = sass_evidence.collect(os.path.join(ROOT, "mageslam_b200", "libmage_b200.so"))
+    match = [v for k, v in cnt.items() if "k_match_dirE" in k]
+    assert match and match[0]["UTCIMMA"] == 8 and match[0]["LDTM"] >= 1 and match[0]["UTCBAR"] >= 1 and match[0]["UTCATOMSWS"] >= 2
+    tma = [v for k, v in cnt.items() if "k_fast_tma" in k]
+    assert tma and tma[0]["UTMALDG"] >= 1
