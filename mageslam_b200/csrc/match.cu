@@ -4,8 +4,10 @@
 // min best/second-best difference, cross-check) and GetDescriptorDistance (ref :453-504). Closed form in SURVEY A.5:
 //   for each query q: C = {t : H(q,t) <= maxHamming}; d1 <= d2 the two smallest; best(q) = argmin iff C != {} and
 //   (|C| == 1 or d2 - d1 >= minDiff); emit (a, best(a), d1) in ascending a iff best_B(best_A(a)) == a.
-// Integer work: xor + popc over 8 x 32-bit words, operands (2 x 64 KB at 2000 descriptors) live in shared memory /
-// L2 -- ALU bound, not HBM bound. One launch computes both directions of every pair of a batch.
+// The operands (2 x 64 KB at 2000 descriptors) live in shared memory / L2 -- compute bound, not HBM bound. One launch computes both
+// directions of every pair of a batch. Two kernels produce the same packed best / second-best statistics: k_match_dir evaluates the
+// distance matrix on the tcgen05 tensor cores as an int8 dot product (default, maxHamming <= 64), k_match_dir_popc with xor + popc
+// over 8 x 32-bit words behind a 96-bit filter (wider radii, or MAGE_MATCH_POPC=1).
 //
 // The reference sizes its backward lookup by the number of non-empty rows but indexes it by query index (:123-137,
 // :158) -- an out-of-range access whenever some B descriptor has no candidate. The lookup is sized nB here (the intent).
