@@ -640,6 +640,12 @@ int orc_umax(int half_patch, int* umax)
 int orc_orb_detect_and_compute(const orc_orb_params* pp, const uint8_t* img, int w, int h, int stride,
                                int order_mode, orc_keypoint* kps, uint8_t* desc, int capacity, int* count)
 {
+    return orc_orb_detect_and_compute_ex(pp, img, w, h, stride, order_mode, ORC_BLUR_AUTO, kps, desc, capacity, count);
+}
+
+int orc_orb_detect_and_compute_ex(const orc_orb_params* pp, const uint8_t* img, int w, int h, int stride,
+                                  int order_mode, int blur_mode, orc_keypoint* kps, uint8_t* desc, int capacity, int* count)
+{
     const orc_orb_params& p = *pp;
     *count = 0;
     if (p.patch_size < 2 || p.nlevels < 1) return -1;                       // CV_Assert(m_patchSize >= 2)
@@ -712,10 +718,11 @@ int orc_orb_detect_and_compute(const orc_orb_params* pp, const uint8_t* img, int
     // unless a single level fills it, and cv::GaussianBlur routes submatrices through its generic float path.
     if (p.gaussian_kernel_size > 1) {
         const bool submatrix = L.n > 1 || (w & 15) != 0;
+        const bool floatPath = blur_mode == ORC_BLUR_FLOAT_FUSED || blur_mode == ORC_BLUR_FLOAT_UNFUSED || (blur_mode == ORC_BLUR_AUTO && submatrix);
         for (int l = 0; l < L.n; l++) {
             if (L.w[l] < 1 || L.h[l] < 1) continue;
             std::vector<uint8_t> tmp(pyr[l].size());
-            if (submatrix) gaussianBlurSubmatrix(ptrs[l], L.w[l], L.h[l], L.w[l], tmp.data(), L.w[l], (int)p.gaussian_kernel_size, true);
+            if (floatPath) gaussianBlurSubmatrix(ptrs[l], L.w[l], L.h[l], L.w[l], tmp.data(), L.w[l], (int)p.gaussian_kernel_size, blur_mode != ORC_BLUR_FLOAT_UNFUSED);
             else gaussianBlur(ptrs[l], L.w[l], L.h[l], L.w[l], tmp.data(), L.w[l], (int)p.gaussian_kernel_size);
             pyr[l].swap(tmp);
             ptrs[l] = pyr[l].data();

@@ -4,11 +4,14 @@
  * Nothing under mageslam_b200/ may include, link or call this. Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs use it, and only as the checker / the CPU arm.
  *
- * Parity status: the reference ships no tests or golden vectors for this path and its
- * OrbDetector cannot be compiled here (needs OpenCV C++ 3.4 headers, not vendored). The restatement is pinned
- * against stock OpenCV 4.13 primitives through tests/test_oracle_vs_cv2.py (resize, GaussianBlur, fastAtan2,
- * FAST-9/16+NMS, BFMatcher::radiusMatch) and against golden vectors generated from it (tests/golden/).
- * => "parity unpinned by the reference; pinned by cv2 cross-checks" (DESIGN.md section 3).
+ * Parity status: PINNED against the reference's own code. Core/MAGESLAM/Source/Image/OpenCVModified.cpp is compiled
+ * UNMODIFIED from /root/reference behind a small cv:: shim (oracle/cvshim/, oracle/Makefile target _ref/liborb_ref.so; both
+ * with and without its CV_SSE2 branches) and tests/test_orb_ref.py checks that order mode 0 of this restatement reproduces it
+ * bit for bit -- key points (order included), angles and descriptors -- over the tier configurations, the reference
+ * defaults, patch 15 / generic patch sizes, degenerate selections and randomised settings. The three OpenCV primitives that
+ * are NOT in the reference tree (cv::resize, cv::GaussianBlur, cv::fastAtan2) are restated here and pinned bit for bit
+ * against OpenCV 4.13 (tests/test_oracle_vs_cv2.py); the shim forwards to those restatements. The reference ships no tests
+ * or golden vectors of its own for this path.
  */
 #ifndef MAGE_ORB_ORACLE_H
 #define MAGE_ORB_ORACLE_H
@@ -50,6 +53,16 @@ enum { ORC_ORDER_LIBSTDCXX = 0, ORC_ORDER_CANONICAL = 1 };
  * Returns 0 on success, <0 on unsupported configuration. */
 int orc_orb_detect_and_compute(const orc_orb_params* p, const uint8_t* img, int w, int h, int stride,
                                int order_mode, orc_keypoint* kps, uint8_t* desc, int capacity, int* count);
+
+/* Same with the Gaussian-blur arithmetic chosen explicitly:
+ *   ORC_BLUR_AUTO          what OpenCV 4.13 does on the reference's call: fixed-point Q8.8 when the level view is the whole
+ *                          packed buffer (one level, cols % 16 == 0), the fused float path for a proper submatrix;
+ *   ORC_BLUR_FLOAT_FUSED   sepFilter2D float path with every multiply-add as one FMA (an AVX2/FMA build of OpenCV) everywhere;
+ *   ORC_BLUR_FLOAT_UNFUSED the same path with separately rounded products (an SSE2-baseline build, e.g. the reference's MSVC x64);
+ *   ORC_BLUR_FIXED         the Q8.8 bit-exact path everywhere. */
+enum { ORC_BLUR_AUTO = 0, ORC_BLUR_FLOAT_FUSED = 1, ORC_BLUR_FLOAT_UNFUSED = 2, ORC_BLUR_FIXED = 3 };
+int orc_orb_detect_and_compute_ex(const orc_orb_params* p, const uint8_t* img, int w, int h, int stride,
+                                  int order_mode, int blur_mode, orc_keypoint* kps, uint8_t* desc, int capacity, int* count);
 
 /* --- stage-level entry points, used by the cv2 cross-check tests and by the stage parity tests --- */
 void  orc_resize_linear_u8(const uint8_t* src, int sw, int sh, int sstride, uint8_t* dst, int dw, int dh, int dstride);

@@ -161,16 +161,52 @@ def umax(half_patch):
     return out
 
 
-def detect_and_compute(params, img, mode=1, capacity=None):
+BLUR_AUTO, BLUR_FLOAT_FUSED, BLUR_FLOAT_UNFUSED, BLUR_FIXED = 0, 1, 2, 3
+
+
+def detect_and_compute(params, img, mode=1, capacity=None, blur_mode=BLUR_AUTO):
     img, ip = _u8(img)
     cap = int(capacity if capacity is not None else params.nfeatures)
     kps = np.zeros(cap, KP_DTYPE)
     desc = np.zeros((cap, 32), np.uint8)
     cnt = C.c_int(0)
-    rc = lib().orc_orb_detect_and_compute(C.byref(params), ip, img.shape[1], img.shape[0], img.strides[0], int(mode),
-                                          kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap, C.byref(cnt))
+    rc = lib().orc_orb_detect_and_compute_ex(C.byref(params), ip, img.shape[1], img.shape[0], img.strides[0], int(mode), int(blur_mode),
+                                             kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap, C.byref(cnt))
     if rc != 0:
         raise ValueError("orb oracle: unsupported configuration (%d)" % rc)
+    return kps[:cnt.value].copy(), desc[:cnt.value].copy()
+
+
+_OREF = {}
+
+
+def orb_ref(sse=True):
+    """The REFERENCE's own OrbDetector (OpenCVModified.cpp compiled unmodified behind oracle/cvshim, oracle/_ref/liborb_ref.so;
+    sse=False: the build without its CV_SSE2 branches). None when it was not built (needs /root/reference at build time)."""
+    name = "liborb_ref.so" if sse else "liborb_ref_nosse.so"
+    if name not in _OREF:
+        path = os.path.join(ROOT, "oracle", "_ref", name)
+        _OREF[name] = None
+        if os.path.exists(path):
+            lib()                                   # liborb_oracle.so first: the shim's resize / blur / fastAtan2 live there
+            R = C.CDLL(path)
+            assert R.ref_orb_sse2() == (1 if sse else 0)
+            _OREF[name] = R
+    return _OREF[name]
+
+
+def detect_and_compute_ref(params, img, blur_mode=BLUR_AUTO, sse=True, capacity=None):
+    """DetectAndCompute of the compiled reference; raises ValueError where the reference throws (CV_Assert)."""
+    R = orb_ref(sse)
+    img, ip = _u8(img)
+    cap = int(capacity if capacity is not None else params.nfeatures)
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    cnt = C.c_int(0)
+    rc = R.ref_orb_detect_and_compute(C.byref(params), ip, img.shape[1], img.shape[0], img.strides[0], int(blur_mode),
+                                      kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap, C.byref(cnt))
+    if rc != 0:
+        raise ValueError("reference OrbDetector threw (%d)" % rc)
     return kps[:cnt.value].copy(), desc[:cnt.value].copy()
 
 
