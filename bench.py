@@ -44,6 +44,29 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def pipe_peaks():
+    """FP64 FMA and packed-integer issue peaks of this pool's B200, measured by tools/measure_pipe_peaks.py (tools/fp64_peak.cu,
+    tools/pipe_probe.cu) and committed as profiles/pipe_peaks.json."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pipe_peaks.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {"fp64_tflops": 35.0, "issue_warp_inst_per_clk_sm": 4.0, "source": "fallback constants (profiles/pipe_peaks.json missing)"}
+
+
+def profile_counters():
+    """Per-launch ncu counters (DRAM bytes, executed warp instructions) of the committed capture, profiles/r02_traffic.json (r01 as fallback)."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tj = json.load(f)
+            tj["file"] = "profiles/" + name
+            return tj
+        except Exception:
+            continue
+    return None
+
+
 def frame_ring(n_unique, ring, seed):
     """ring frames (> L2 in total) from n_unique warped views of the synthetic scene; the rest are flips / brightness shifts."""
     from mageslam_b200 import synth
@@ -72,7 +95,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -80,7 +103,7 @@ class ClockSampler:
     def stop(self):
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.03)
         self.p.terminate()
         try:
             out = self.p.communicate(timeout=5)[0]
@@ -126,14 +149,24 @@ def algorithmic_bytes_per_frame():
     }
 
 
+def cpu_orb_kind():
+    """"reference": DetectAndCompute is the reference's own OpenCVModified.cpp compiled unmodified (oracle/_ref/liborb_ref.so, its
+    cv::resize / GaussianBlur / fastAtan2 being the cv2-pinned restatements since OpenCV is not vendored); Match is the restated
+    FeatureMatcher.cpp:61-190 (it needs cv::BFMatcher). "port": the restated oracle for both, when _ref was not built."""
+    from tests import oracle_orb as orc
+    return "reference" if orc.orb_ref() is not None else "port"
+
+
 def cpu_orb_sample(frames, threads=1):
-    """Oracle (port of the reference ORB + Match) on `frames` consecutive frames; returns fps. Checker code, CPU only."""
+    """The reference ORB extract (compiled reference when present, else the oracle port) + Match on `frames` consecutive frames;
+    returns fps. Checker code, CPU only."""
     from tests import oracle_orb as orc
     p = orc.tier_params(NFEAT, NLEVELS, SCALE, 10)
+    use_ref = orc.orb_ref() is not None
     t0 = time.perf_counter()
     prev = None
     for f in frames:
-        k, d = orc.detect_and_compute(p, f, 1)
+        k, d = orc.detect_and_compute_ref(p, f) if use_ref else orc.detect_and_compute(p, f, 1)
         if prev is not None:
             orc.match(d, prev, 30, 1)
         prev = d
@@ -152,34 +185,45 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
+def static_config(batch, world, ring_n):
+    """The workload description both arms print (the driver compares the two `config` objects)."""
+    return {"workload": WORKLOAD, "frames_per_step": batch, "sequences": world, "parallelism": "replicas (one sequence per GPU)",
+            "l2": "inputs larger than L2: %d-frame ring = %.0f MB per GPU" % (ring_n, ring_n * W * H / 1e6)}
+
+
 def run_reference(args):
-    """CPU arm: the reference's ORB path cannot be compiled here (needs OpenCV 3.4 C++ headers), so this times the oracle port
-    of it, frame-parallel over all host cores (the reference itself is single-threaded per frame, MAGESlam.cpp:146)."""
+    """CPU arm: the reference's own ORB extraction (OpenCVModified.cpp compiled unmodified behind oracle/cvshim; the oracle port
+    when oracle/_ref is absent) + the restated Match, frame-parallel over all host cores (the reference itself is single-threaded
+    per frame, MAGESlam.cpp:146). One step = the same 128-frame batch as the GPU arm, split over the worker processes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_worker = 4
+    frames_per_step = args.batch
+    workers = min(cores, frames_per_step)
+    share = [frames_per_step // workers + (1 if w < frames_per_step % workers else 0) for w in range(workers)]
     global _REF_RING
-    _REF_RING = frame_ring(min(args.unique, 32), 64, seed=10)
+    _REF_RING = frame_ring(min(args.unique, 32), 128, seed=10)
+    kind = cpu_orb_kind()
     ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(workers) as pool:
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_cpu_worker, [((s * cores + w) * per_worker, per_worker) for w in range(cores)])
+            pool.map(_cpu_worker, [(s * frames_per_step + sum(share[:w]), share[w]) for w in range(workers)], chunksize=1)
             dt = time.perf_counter() - t0
             if s >= args.warmup:
                 times.append(dt)
-    frames_per_step = cores * per_worker
     ms = 1e3 * sum(times) / len(times)
     value = frames_per_step / (ms / 1e3)
-    sample = "%d frames per step (%d worker processes x %d consecutive frames each, extract + match vs previous)" % (frames_per_step, cores, per_worker)
+    sample = "%d frames per step (%d worker processes x %d-%d consecutive frames each, extract + match vs previous)" % (
+        frames_per_step, workers, min(share), max(share))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames_per_step},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": static_config(args.batch, args.gpus, args.ring),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample,
+                             "note": "extract = the reference's OpenCVModified.cpp compiled unmodified (cv::resize/GaussianBlur/fastAtan2 restated, OpenCV is not vendored); Match = restated FeatureMatcher.cpp:61-190" if kind == "reference" else "restated oracle (oracle/_ref absent)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     # secondary: the reference's own BundlerLib + g2o (compiled unmodified into oracle/_ref) on the local-BA window
     try:
@@ -298,7 +342,6 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
-    clocks = clk.stop()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -331,6 +374,7 @@ def run_ours(args):
     fe_pipe.Wait()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = clk.stop()      # sampled every 20 ms from the start of the device-resident timed region to the end of the end-to-end one
     t = torch.tensor([e2e_ms, e2e_sync_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -359,36 +403,49 @@ def run_ours(args):
     step_kernel_ms = sum(v[0] for k, v in kern.items() if k in alg)
     dom = max((k for k in kern if k in alg), key=lambda k: kern[k][0])
     peak, peak_src = peaks()
+    pp = pipe_peaks()
     dom_ms = kern[dom][0]
-    achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    try:        # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel at the same batch size, from the committed ncu capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tj = json.load(f)
-        if dom in tj["kernels"]:      # captured at tj["frames_per_launch"] frames per launch; DRAM traffic scales with the batch
+    hbm_achieved = alg[dom] * B / (dom_ms * 1e-3) / 1e9
+    tj = profile_counters()
+    traffic = inst = None
+    if tj is not None:        # per-launch ncu counters of the same kernel, captured at tj["frames_per_launch"] frames per launch; both scale with the batch
+        if dom in tj.get("kernels", {}):
             traffic = tj["kernels"][dom] / tj["frames_per_launch"] * B
-    except Exception:
-        traffic = None
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "launch_ms": dom_ms, "share_of_step": dom_ms / step_kernel_ms,
+        if dom in tj.get("inst_executed", {}):
+            inst = tj["inst_executed"][dom] / tj["frames_per_launch"] * B
+    # which roofline binds each kernel (ncu pipe table, profiles/README.md): the streaming kernels move their bytes once but are
+    # limited by instruction issue, the matcher by the tensor pipe + the ALU work around it
+    bound_of = {"k_fast": "alu", "k_blur": "alu", "k_resize": "alu", "k_orient_describe": "hbm", "k_select": "hbm", "k_match_dir": "tensor", "k_match_emit": "hbm"}
+    sm_clock_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+    roofline = {"kernel": dom, "bound": bound_of.get(dom, "hbm"), "traffic": traffic, "launch_ms": dom_ms, "share_of_step": dom_ms / step_kernel_ms,
                 "algorithmic_bytes_per_launch": alg[dom] * B,
-                "kernels": {k: {"ms": round(v[0], 5), "share": round(v[0] / step_kernel_ms, 4),
+                "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src},
+                "kernels": {k: {"ms": round(v[0], 5), "share": round(v[0] / step_kernel_ms, 4), "bound": bound_of.get(k, "hbm"),
                                 "GBps": round(alg[k] * B / (v[0] * 1e-3) / 1e9, 2)} for k, v in kern.items() if k in alg}}
-    if dom == "k_match_dir":
-        wordops = 2 * 2 * NFEAT * NFEAT * 8 * B          # xor+popc word operations per launch (both directions)
-        roofline["note"] = "integer-ALU bound (xor+popc), operands live in shared memory/L2; %.2f Tera word-ops/s" % (wordops / (dom_ms * 1e-3) / 1e12)
-    if dom == "k_fast":
-        roofline["note"] = ("integer-ALU bound, not HBM bound: ncu (profiles/README.md) has the ALU pipe at 78 % and the issue slots at 69 % of peak "
-                            "with DRAM at 2 %; traffic = algorithmic bytes (no re-reads)")
+    if roofline["bound"] == "alu" and inst is not None:
+        # issue-slot roofline: warp instructions the kernel executes per launch (ncu smsp__inst_executed.sum of the committed capture,
+        # scaled to this batch) / its live launch time, against the measured issue peak (warp instructions per clock and SM x 148 SMs x SM clock)
+        ach = inst / (dom_ms * 1e-3) / 1e12
+        pk = pp["issue_warp_inst_per_clk_sm"] * 148 * sm_clock_hz / 1e12
+        roofline.update({"achieved": ach, "peak": pk, "unit": "T warp-instructions/s", "frac": ach / pk, "peak_source": pp.get("source"),
+                         "warp_instructions_per_launch": inst, "counters": tj["file"],
+                         "note": "instruction-issue bound, not HBM bound: DRAM traffic equals the algorithmic bytes (no re-reads); see roofline.hbm for the bandwidth view"})
+    elif roofline["bound"] == "tensor" and dom == "k_match_dir":
+        ops = 2.0 * NFEAT * NFEAT * 256 * B                  # one 2000 x 2000 x 256 int8 GEMM per frame pair serves both match directions; 2 ops per MAC
+        ach = ops / (dom_ms * 1e-3) / 1e12
+        pk = pp.get("int8_tops", 4500.0)
+        roofline.update({"achieved": ach, "peak": pk, "unit": "Tera int8 op/s", "frac": ach / pk, "peak_source": "nominal dense int8 (2x the bf16 peak)"})
+    else:
+        roofline.update({"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak, "peak_source": peak_src})
+        roofline["bound"] = "hbm"
     launches_per_step = (NLEVELS - 1) + 2 + 1 + 1 + 1 + 2          # resize x7, blur (interior + edges), FAST, select, orient+describe, match (dir + emit)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": B, "sequences": world, "parallelism": "replicas (one sequence per GPU)",
-                       "l2": "inputs larger than L2: %d-frame ring = %.0f MB per GPU" % (ring_n, ring_n * W * H / 1e6),
-                       "keypoints_per_frame": kp_mean, "matches_per_frame": match_mean, "e2e_chunk": args.chunk,
-                       "e2e_timer": "host clock around the whole loop of C-ABI calls, device idle at both ends", "numa_node": numa,
-                       "e2e_mode": "pipelined mage_frontend_submit / _wait, two calls in flight, pinned host buffers; e2e.sync = the plain synchronous mage_frontend_process"},
+            "config": static_config(B, world, ring_n),
+            "info": {"keypoints_per_frame": kp_mean, "matches_per_frame": match_mean, "e2e_chunk": args.chunk,
+                     "e2e_timer": "host clock around the whole loop of C-ABI calls, device idle at both ends", "numa_node": numa,
+                     "e2e_mode": "pipelined mage_frontend_submit / _wait, two calls in flight, pinned host buffers; e2e.sync = the plain synchronous mage_frontend_process"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "sync": e2e_sync_value},
             "gpu_launches": launches_per_step * args.steps,
@@ -397,7 +454,7 @@ def run_ours(args):
     if rank == 0 and world == 1:
         sample_n = args.cpu_frames
         fps = cpu_orb_sample(list(ring[:sample_n]))
-        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": "port",
+        line["cpu_baseline"] = {"value": fps, "unit": UNIT, "cores": 1, "kind": cpu_orb_kind(),
                                 "sample": "%d consecutive frames of the same ring, extract + match vs previous, 1 thread (host has %d cores)" % (sample_n, os.cpu_count() or 1)}
     # ---- secondary metric: local BA
     try:
@@ -409,6 +466,18 @@ def run_ours(args):
             line["radius_match"] = bench_radius(kps, desc, cnt)
         except Exception as e:      # pragma: no cover
             line["radius_match"] = {"error": str(e)[:300]}
+        if args.global_ba_steps > 0:
+            try:
+                line["global_ba"] = bench_global_ba(args)
+            except Exception as e:      # pragma: no cover
+                line["global_ba"] = {"error": str(e)[:300]}
+    if args.config5_frames > 0:
+        del fe_dev, fe_host, fe_pipe, d_ring
+        try:
+            c5 = bench_config5(args, world, rank, dist if world > 1 else None)
+        except Exception as e:      # pragma: no cover
+            c5 = {"error": str(e)[:300]}
+        line["config5"] = c5
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -510,6 +579,117 @@ def bench_ba(args, world, rank, dist):
     return out
 
 
+def bench_global_ba(args):
+    """BASELINE config 4: global BA, 500 keyframes / 50 000 points / 400 000 observations (reduced camera system 2988 x 2988), one
+    LM step per StepBundleAdjustment call. GPU: cooperative kernel + grid-wide dense solve; CPU: the reference's own BundlerLib + g2o
+    (dense Eigen LDLT, ref linear_solver_dense.h:65-113) on one host core, one step."""
+    import torch
+    from mageslam_b200 import synth
+    from mageslam_b200.bundler import BundlerLib
+    from tests.oracle_ba import BaOracle, have_ref, rel_frobenius
+    K, P, D = 500, 50000, 8
+    prob = synth.ba_problem(K=K, P=P, obs_per_point=D, seed=2, loop=True)
+    gpu = BundlerLib().load(prob)
+    gpu.StepBundleAdjustment([1.8], 1e9)                  # structure build + first step (untimed, as for the CPU arm)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(args.global_ba_steps):
+        t0 = time.perf_counter()
+        gpu.StepBundleAdjustment([1.8], 1e9)
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    st = gpu.stats()
+    ms = 1e3 * statistics.median(ts)
+    trials_per_step = (st["lambda_trials"] - 1) / max(st["lm_iterations"] - 1, 1) if st["lm_iterations"] > 1 else 1.0
+    pp = pipe_peaks()
+    # SURVEY 8(d): per LM trial 0.19 GFLOP assembly + 0.46 GFLOP Schur + n^3/3 = 8.9 GFLOP dense factorisation (n = 2988), about 130 MB
+    n = 6 * (K - 2)
+    flop = 0.19e9 + 0.46e9 + n ** 3 / 3.0
+    hbm, hbm_src = peaks()
+    out = {"metric": "global_ba_ms_per_lm_step", "value": ms, "unit": "ms", "higher_is_better": False,
+           "config": {"workload": "global BA 500 KF / 50 000 pts / 400 000 obs (8 per point, loop trajectory, 2 fixed), Huber 1.8, one LM step per call",
+                      "reduced_system": n, "timer": "host clock around the synchronous C-ABI call, median of %d steps" % args.global_ba_steps},
+           "lm_iterations": st["lm_iterations"], "lambda_trials_per_step": trials_per_step, "mean_sq_error": float(gpu.StepBundleAdjustment([], 1e9)) if False else None,
+           "roofline": {"kernel": "k_ba_step_coop", "bound": "fp64", "achieved": flop * trials_per_step / (ms * 1e-3) / 1e12, "peak": pp["fp64_tflops"],
+                        "unit": "TFLOP/s", "frac": flop * trials_per_step / (ms * 1e-3) / 1e12 / pp["fp64_tflops"], "peak_source": pp.get("source"),
+                        "flop_per_trial": flop, "hbm": {"achieved": 130e6 * trials_per_step / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "peak_source": hbm_src}},
+           "dtype": "f64"}
+    out.pop("mean_sq_error")
+    try:
+        import ctypes as C
+        ph = np.zeros(16, np.int64)
+        _lib = __import__("mageslam_b200._lib", fromlist=["lib"])
+        _lib.lib().mage_ba_debug_phase_ns(gpu._h, ph.ctypes.data_as(C.c_void_p))
+        steps = max(st["lm_iterations"], 1)
+        out["phase_ms_per_step"] = {"dense_solve": float(ph[4]) / 1e6 / steps, "ldlt_diag": float(ph[9]) / 1e6 / steps, "ldlt_panel": float(ph[10]) / 1e6 / steps,
+                                    "ldlt_update": float(ph[11]) / 1e6 / steps, "ldlt_barriers": float(ph[12]) / 1e6 / steps}
+    except Exception:
+        pass
+    # CPU arm: one timed step of the compiled reference (about 1.4 s) after its own untimed first step, then parity of the two states
+    kind = "reference" if have_ref() else "port"
+    chk = BaOracle("ref" if have_ref() else "port").load(prob)
+    chk.StepBundleAdjustment([1.8], 1e9)
+    t0 = time.perf_counter()
+    chk.StepBundleAdjustment([1.8], 1e9)
+    t_cpu = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": 1e3 * t_cpu, "unit": "ms", "cores": 1, "kind": kind, "sample": "one LM step (the second call) of the same 500 KF problem"}
+    # parity at the same iteration count: a second GPU instance stepped twice like the CPU arm
+    g2 = BundlerLib().load(prob)
+    g2.StepBundleAdjustment([1.8], 1e9); g2.StepBundleAdjustment([1.8], 1e9)
+    pc, rc = g2.poses(); pr, rr = chk.poses()
+    out["parity_after_2_steps"] = {"relF_positions": rel_frobenius(pc, pr), "relF_rotations": rel_frobenius(rc, rr), "relF_points": rel_frobenius(g2.points(), chk.points()),
+                                   "lambda": [g2.GetCurrentLambda(), chk.GetCurrentLambda()], "tolerance": 1e-4}
+    return out
+
+
+def bench_config5(args, world, rank, dist):
+    """BASELINE config 5: one independent 1280x720 sequence per GPU -- ORB extract + match per frame through the host-buffer C ABI
+    (pipelined submit / wait) and one fresh local-BA window (config-3 shape, 10 LM iterations) every 20 frames. Replicas only."""
+    import torch
+    from mageslam_b200 import synth
+    from mageslam_b200.frontend import FrontEnd
+    from mageslam_b200.orb import FeatureExtractorSettings
+    from mageslam_b200.bundler import BundlerLib, StepMany
+    Wc, Hc, B, frames_n, every = 1280, 720, 32, args.config5_frames, 20
+    vid = synth.video_frames(16, Wc, Hc, seed=10 + rank)                         # sequence seeds 10..17 (SURVEY 8d config 5)
+    frames = torch.from_numpy(np.concatenate([vid, vid[::-1]] * (frames_n // 32), 0)).pin_memory()
+    fe = FrontEnd(FeatureExtractorSettings.tier(NFEAT, NLEVELS, SCALE, 10), Wc, Hc, B, chunk=B)
+    outs2 = [fe.alloc_outputs(pinned=True), fe.alloc_outputs(pinned=True)]
+    n_windows = frames_n // every
+    probs = [synth.ba_problem(seed=100 * rank + w) for w in range(4)]
+    fe.Process(frames[:B], outs2[0]); fe.Reset()
+    StepMany([BundlerLib().load(probs[0])], [1.8], 1e9)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    kp = m = 0
+    nb = frames_n // B
+    for k in range(nb):
+        fe.Submit(frames[k * B:(k + 1) * B], outs2[k & 1])
+        if k:
+            fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(k - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
+    fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(nb - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
+    torch.cuda.synchronize()
+    t_frames = time.perf_counter() - t0
+    windows = [BundlerLib().load(probs[w % 4]) for w in range(n_windows)]      # fresh windows: set-up + structure build are inside the timed region
+    means = StepMany(windows, [1.8] * 10, 1e9)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt, t_frames], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt, t_frames = float(t[0].item()), float(t[1].item())
+    iters = sum(b.stats()["lm_iterations"] for b in windows)
+    return {"metric": "config5_frames_per_sec_1280x720_with_local_ba", "value": world * frames_n / dt, "unit": "frames/s", "higher_is_better": True, "scaling": "weak",
+            "config": {"workload": "one 1280x720 synthetic sequence per GPU (2000 keypoints/frame), ORB extract + match per frame + a fresh local-BA window (10 KF / 2000 pts / 8000 obs, 10 LM iterations) every %d frames" % every,
+                       "frames_per_gpu": frames_n, "sequences": world, "timer": "host clock, host buffers in and out, max over ranks"},
+            "ba_lm_iters_per_s": world * iters / dt, "frontend_only_frames_per_s": world * frames_n / t_frames,
+            "ba_only_lm_iters_per_s": world * iters / max(dt - t_frames, 1e-9), "keypoints_per_frame": kp / frames_n, "matches_per_frame": m / frames_n,
+            "ba_mean_sq_error": float(np.mean(means)), "wall_s": dt,
+            "h2d_bytes_per_frame": Wc * Hc, "d2h_bytes_per_frame": fe.capacity * (28 + 32 + 12) + 8}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -525,6 +705,8 @@ def main():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--ba-problems", type=int, default=296)
+    ap.add_argument("--global-ba-steps", type=int, default=5, help="timed LM steps of the 500-keyframe global BA (0 = skip; N = 1 only)")
+    ap.add_argument("--config5-frames", type=int, default=256, help="frames per GPU of the 1280x720 ORB + local-BA run (0 = skip)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = 20 if args.impl == "reference" else 300

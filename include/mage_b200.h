@@ -85,6 +85,16 @@ typedef struct mage_orb_s* mage_orb_t;
 int  mage_orb_create(const mage_orb_params* params, int width, int height, int max_batch, mage_orb_t* out);
 void mage_orb_destroy(mage_orb_t h);
 
+/* The arithmetic of the reference's cv::GaussianBlur call (ref OpenCVModified.cpp:863) is a property of the OpenCV build behind it,
+ * not of the reference source. Default = MAGE_BLUR_AUTO. Call between extractions, not during one.
+ *   MAGE_BLUR_AUTO           OpenCV 4.13: Q8.8 fixed point when the level view is the whole packed buffer (one level, width % 16 == 0),
+ *                            else the separable float path with fused multiply-adds (AVX2/FMA build, the stock cv2 wheel);
+ *   MAGE_BLUR_FLOAT_FUSED    the float path with FMAs everywhere;
+ *   MAGE_BLUR_FLOAT_UNFUSED  the float path with separately rounded products (SSE2-baseline build, e.g. MSVC x64);
+ *   MAGE_BLUR_FIXED          the Q8.8 bit-exact path everywhere. */
+enum { MAGE_BLUR_AUTO = 0, MAGE_BLUR_FLOAT_FUSED = 1, MAGE_BLUR_FLOAT_UNFUSED = 2, MAGE_BLUR_FIXED = 3 };
+int  mage_orb_set_blur_mode(mage_orb_t h, int mode);
+
 /* Replaces OrbDetector::DetectAndCompute for ONE host image (CV_8UC1, row stride in bytes).
  * kps/desc are host buffers with room for `capacity` features (ImageData::maxFeatures); desc is 32 bytes each
  * (ref Image/ORBDescriptor.h). Synchronous on return. stream may be NULL. */

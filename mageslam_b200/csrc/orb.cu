@@ -52,7 +52,7 @@ struct OrbGeom {
     int generic_pattern;    // patch size without a pre-rotated table: runtime rotation of the cv::RNG pattern (ref :452-492)
     int gk[16];
     float gkf[8];           // first half of the float Gaussian kernel (edge .. centre), used when blur_float != 0
-    int blur_float;         // the level ROIs are proper submatrices of the reference's packed buffer: cv::GaussianBlur's float path
+    int blur_float;         // 0: Q8.8 fixed point; 1 / 2: cv::GaussianBlur's float path (level ROIs are proper submatrices of the reference's packed buffer), fused / unfused
     LevelGeom lv[kMaxLevels];
 };
 
@@ -616,6 +616,28 @@ __global__ void __launch_bounds__(kSelThreads, 4) k_select(const __grid_constant
     }
     __syncthreads();
     const int K = s_vals[0], stop = s_vals[1];
+    if (K < nKeep) {
+        // RetainBestFeatures kept fewer than n_l (feature_strength > 1 lifts the cut above the n_l-th score, or feature_factor < 1):
+        // AdaptiveNonMaximalSuppresion returns early (ref :181-184) and the K survivors stay in RetainBest's (canonical: raster) order
+        bind(n);
+        int np2 = 1; while (np2 < n) np2 <<= 1;
+        for (int i = tid; i < np2; i += nt) {
+            unsigned long long key = 0;
+            if (i < n) {
+                const uint32_t c = cand[i];
+                if ((int)(c >> 24) >= stop) { const uint32_t inv = 0xFFFFFFu - (c & 0xFFFFFFu); key = ((unsigned long long)inv << 32) | (c & 0xFF000000u) | inv; }
+            }
+            keys[i] = key;
+        }
+        __syncthreads();
+        bitonic_sort_desc(keys, np2);
+        for (int i = tid; i < K; i += nt) {
+            const uint32_t lo = (uint32_t)keys[i];
+            sel[i] = (lo & 0xFF000000u) | (0xFFFFFFu - (lo & 0xFFFFFFu));
+        }
+        if (tid == 0) *selCount = K;
+        return;
+    }
     bind(K);
     {
         int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
@@ -894,6 +916,14 @@ __device__ __forceinline__ uint32_t f2u8(float s)
     return (uint32_t)min(max(__float2int_rn(s), 0), 255);
 }
 
+// FUSED = true: one FMA per multiply-add (an AVX2/FMA build of OpenCV, what the cv2 4.13 wheel runs); false: product and sum rounded
+// separately (an SSE2-baseline build such as the reference's MSVC x64 one). Selected by mage_orb_set_blur_mode.
+template <bool FUSED> __device__ __forceinline__ float blur_mad(float k, float v, float s)
+{
+    return FUSED ? __fmaf_rn(k, v, s) : __fadd_rn(s, __fmul_rn(k, v));
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(256) k_blurf(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
     __shared__ uint8_t in[kBlurIH * kBlurIW];
@@ -917,7 +947,7 @@ __global__ void __launch_bounds__(256) k_blurf(const __grid_constant__ OrbGeom g
     for (int i = threadIdx.x; i < ih * kBlurOW; i += blockDim.x) {
         int ry = i / kBlurOW, ox = i - ry * kBlurOW;
         float s = __fmul_rn(g.gkf[0], (float)in[ry * kBlurIW + ox]);
-        for (int k = 1; k < ks; k++) s = __fmaf_rn(g.gkf[k <= r ? k : 2 * r - k], (float)in[ry * kBlurIW + ox + k], s);
+        for (int k = 1; k < ks; k++) s = blur_mad<FUSED>(g.gkf[k <= r ? k : 2 * r - k], (float)in[ry * kBlurIW + ox + k], s);
         mid[ry * kBlurOW + ox] = s;
     }
     __syncthreads();
@@ -930,7 +960,7 @@ __global__ void __launch_bounds__(256) k_blurf(const __grid_constant__ OrbGeom g
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float s = __fmul_rn(g.gkf[r], mid[(oy + r) * kBlurOW + ox + j]);
-            for (int k = 1; k <= r; k++) s = __fmaf_rn(g.gkf[r - k], __fadd_rn(mid[(oy + r + k) * kBlurOW + ox + j], mid[(oy + r - k) * kBlurOW + ox + j]), s);
+            for (int k = 1; k <= r; k++) s = blur_mad<FUSED>(g.gkf[r - k], __fadd_rn(mid[(oy + r + k) * kBlurOW + ox + j], mid[(oy + r - k) * kBlurOW + ox + j]), s);
             packed |= f2u8(s) << (8 * j);
         }
         *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
@@ -939,6 +969,7 @@ __global__ void __launch_bounds__(256) k_blurf(const __grid_constant__ OrbGeom g
 
 // 7x7 float path, same work split as k_blur7: a thread owns 4 columns x kBlur7Rows rows, the row pass of its 22 source rows stays
 // in registers (88 floats), no shared memory. Interior columns only; k_blur7f_edges does the REFLECT_101 columns.
+template <bool FUSED>
 __global__ void __launch_bounds__(256) k_blur7f(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
     const int f = blockIdx.y;
@@ -968,8 +999,8 @@ __global__ void __launch_bounds__(256) k_blur7f(const __grid_constant__ OrbGeom 
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             float s = __fmul_rn(k0, v[j]);
-            s = __fmaf_rn(k1, v[j + 1], s); s = __fmaf_rn(k2, v[j + 2], s); s = __fmaf_rn(k3, v[j + 3], s);
-            s = __fmaf_rn(k2, v[j + 4], s); s = __fmaf_rn(k1, v[j + 5], s); s = __fmaf_rn(k0, v[j + 6], s);
+            s = blur_mad<FUSED>(k1, v[j + 1], s); s = blur_mad<FUSED>(k2, v[j + 2], s); s = blur_mad<FUSED>(k3, v[j + 3], s);
+            s = blur_mad<FUSED>(k2, v[j + 4], s); s = blur_mad<FUSED>(k1, v[j + 5], s); s = blur_mad<FUSED>(k0, v[j + 6], s);
             T[i][j] = s;
         }
     }
@@ -982,9 +1013,9 @@ __global__ void __launch_bounds__(256) k_blur7f(const __grid_constant__ OrbGeom 
 #pragma unroll
             for (int j = 0; j < 4; j++) {
                 float s = __fmul_rn(k3, T[r + 3][j]);
-                s = __fmaf_rn(k2, __fadd_rn(T[r + 4][j], T[r + 2][j]), s);
-                s = __fmaf_rn(k1, __fadd_rn(T[r + 5][j], T[r + 1][j]), s);
-                s = __fmaf_rn(k0, __fadd_rn(T[r + 6][j], T[r][j]), s);
+                s = blur_mad<FUSED>(k2, __fadd_rn(T[r + 4][j], T[r + 2][j]), s);
+                s = blur_mad<FUSED>(k1, __fadd_rn(T[r + 5][j], T[r + 1][j]), s);
+                s = blur_mad<FUSED>(k0, __fadd_rn(T[r + 6][j], T[r][j]), s);
                 packed |= f2u8(s) << (8 * j);
             }
             *reinterpret_cast<uint32_t*>(out + (size_t)y * L.pitch + x) = packed;
@@ -992,6 +1023,7 @@ __global__ void __launch_bounds__(256) k_blur7f(const __grid_constant__ OrbGeom 
     }
 }
 
+template <bool FUSED>
 __global__ void __launch_bounds__(256) k_blur7f_edges(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
     const int f = blockIdx.z, l = blockIdx.y;
@@ -1019,13 +1051,13 @@ __global__ void __launch_bounds__(256) k_blur7f_edges(const __grid_constant__ Or
         const uint8_t* row = img + (size_t)sy * pitch;
         float s = __fmul_rn(kk[0], (float)row[xs[0]]);
 #pragma unroll
-        for (int k = 1; k < 7; k++) s = __fmaf_rn(kk[k <= 3 ? k : 6 - k], (float)row[xs[k]], s);
+        for (int k = 1; k < 7; k++) s = blur_mad<FUSED>(kk[k <= 3 ? k : 6 - k], (float)row[xs[k]], s);
         R[j] = s;
     }
     float s = __fmul_rn(kk[3], R[3]);
-    s = __fmaf_rn(kk[2], __fadd_rn(R[4], R[2]), s);
-    s = __fmaf_rn(kk[1], __fadd_rn(R[5], R[1]), s);
-    s = __fmaf_rn(kk[0], __fadd_rn(R[6], R[0]), s);
+    s = blur_mad<FUSED>(kk[2], __fadd_rn(R[4], R[2]), s);
+    s = blur_mad<FUSED>(kk[1], __fadd_rn(R[5], R[1]), s);
+    s = blur_mad<FUSED>(kk[0], __fadd_rn(R[6], R[0]), s);
     blur_ptr(g, b, f, l)[(size_t)y * L.pitch + x] = (uint8_t)f2u8(s);
 }
 
@@ -1477,6 +1509,22 @@ extern "C" void mage_orb_destroy(mage_orb_t h)
     delete h;
 }
 
+// Which arithmetic cv::GaussianBlur runs depends on the OpenCV build behind the reference; the default is what
+// OpenCV 4.13 does on the reference's call. Captured launch graphs hold the geometry by value, so they are dropped.
+extern "C" int mage_orb_set_blur_mode(mage_orb_t h, int mode)
+{
+    MAGE_REQUIRE(h, MAGE_ERR_INVALID, "null handle");
+    MAGE_REQUIRE(mode >= MAGE_BLUR_AUTO && mode <= MAGE_BLUR_FIXED, MAGE_ERR_INVALID, "blur mode %d: 0..3", mode);
+    OrbGeom& g = h->g;
+    if (g.ksize > 1) {
+        const bool submatrix = g.nlevels > 1 || (g.width & 15) != 0;
+        g.blur_float = mode == MAGE_BLUR_FLOAT_FUSED ? 1 : mode == MAGE_BLUR_FLOAT_UNFUSED ? 2 : mode == MAGE_BLUR_FIXED ? 0 : (submatrix ? 1 : 0);
+    }
+    for (auto& gph : h->graphs) cudaGraphExecDestroy(gph.exec);
+    h->graphs.clear();
+    return MAGE_OK;
+}
+
 extern "C" int mage_orb_level_info(mage_orb_t h, int* widths, int* heights, float* scales, int* nfeat)
 {
     MAGE_REQUIRE(h, MAGE_ERR_INVALID, "null handle");
@@ -1511,9 +1559,12 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
     if (fork) { MAGE_CUDA_TRY(cudaEventRecord(h->ev_pyr, s)); MAGE_CUDA_TRY(cudaStreamWaitEvent(sb, h->ev_pyr, 0)); }
     if (g.ksize == 7) {
         ProfScope ps(PROF_BLUR, sb);
-        if (g.blur_float) {
-            k_blur7f<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
-            k_blur7f_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
+        if (g.blur_float == 1) {
+            k_blur7f<true><<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+            k_blur7f_edges<true><<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
+        } else if (g.blur_float == 2) {
+            k_blur7f<false><<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+            k_blur7f_edges<false><<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
         } else {
             k_blur7<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
             k_blur7_edges<<<dim3(div_up(15 * g.lv[0].h, 256), g.nlevels, n), 256, 0, sb>>>(g, bufs);
@@ -1521,7 +1572,8 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
     }
     else if (g.ksize > 1) {
         ProfScope ps(PROF_BLUR, sb);
-        if (g.blur_float) k_blurf<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+        if (g.blur_float == 1) k_blurf<true><<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
+        else if (g.blur_float == 2) k_blurf<false><<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
         else k_blur<<<dim3(h->blur_tiles, n), 256, 0, sb>>>(g, bufs);
     }
     if (fork) MAGE_CUDA_TRY(cudaEventRecord(h->ev_blur, sb));

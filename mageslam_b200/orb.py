@@ -52,6 +52,7 @@ class OrbDetector:
         self.max_batch = int(max_batch)
         self._h = None
         self._wh = None
+        self._blur_mode = 0
 
     # -- handle management
     def _ensure(self, w, h):
@@ -61,6 +62,14 @@ class OrbDetector:
         hnd = C.c_void_p()
         check(lib().mage_orb_create(C.byref(self.params), w, h, self.max_batch, C.byref(hnd)))
         self._h, self._wh = hnd, (w, h)
+        if self._blur_mode:
+            check(lib().mage_orb_set_blur_mode(self._h, self._blur_mode))
+
+    def SetBlurMode(self, mode):
+        """mage_orb_set_blur_mode: 0 auto (OpenCV 4.13 behaviour), 1 float fused, 2 float unfused, 3 fixed point"""
+        self._blur_mode = int(mode)
+        if self._h is not None:
+            check(lib().mage_orb_set_blur_mode(self._h, self._blur_mode))
 
     def close(self):
         if self._h is not None:

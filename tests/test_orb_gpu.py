@@ -273,3 +273,90 @@ def test_randomised_configurations_bit_exact(seed, monkeypatch):
     ok, od = orc.detect_and_compute(p, img, 1)
     assert_same_features(gk, gd, ok, od, "seed %d (%dx%d L%d s%.2f patch %d orient %d blur %d thr %d)" % (
         seed, w, h, nlevels, scale, patch, p.use_orientation, p.gaussian_kernel_size, p.fast_threshold))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# Straight against the REFERENCE'S OWN CODE (OpenCVModified.cpp compiled unmodified, oracle/_ref/liborb_ref.so, tests/test_orb_ref.py).
+# The compiled reference orders a level by libstdc++'s std::nth_element, the CUDA path by the canonical conforming order, so the two
+# are compared as per-octave sets of (key point, descriptor) records: bit-identical records, same multiplicity.
+def _records(k, d):
+    rec = np.concatenate([np.ascontiguousarray(k).view(np.uint8).reshape(len(k), 28), d], axis=1)
+    return rec[np.lexsort(rec.T[::-1])]
+
+
+needs_ref = pytest.mark.skipif(orc.orb_ref() is None, reason="oracle/_ref/liborb_ref.so not built")
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg", ["tier_video", "tier_noise", "defaults", "patch15_orient", "generic21", "720p"])
+def test_gpu_equals_compiled_reference(frames, cfg):
+    if cfg == "tier_video":
+        p, img = orc.tier_params(), frames["video"][2]
+    elif cfg == "tier_noise":
+        p, img = orc.tier_params(), frames["noise"]
+    elif cfg == "defaults":
+        p, img = orc.default_params(), synth.video_frames(1, 320, 180, seed=5)[0]
+    elif cfg == "patch15_orient":
+        p = orc.tier_params(nfeatures=500, nlevels=1); p.patch_size = 15
+        img = synth.video_frames(1, 400, 300, seed=12)[0]
+    elif cfg == "generic21":
+        p = orc.tier_params(nfeatures=500, nlevels=3); p.patch_size = 21
+        img = synth.video_frames(1, 400, 300, seed=13)[0]
+    else:
+        p, img = orc.tier_params(), synth.video_frames(1, 1280, 720, seed=10)[0]
+    gk, gd = make_detector(p).DetectAndCompute(img)
+    rk, rd = orc.detect_and_compute_ref(p, img)
+    assert len(gk) == len(rk) > 100
+    gs = {bytes(r) for r in _records(gk, gd)}; rs = {bytes(r) for r in _records(rk, rd)}
+    assert len(gs) == len(gk) and len(rs) == len(rk)
+    only_g, only_r = gs - rs, rs - gs
+    # a (suppression radius, strength) tie straddling a level's cut may pick a different member of the tie (the
+    # compiled reference takes whatever libstdc++'s nth_element leaves, the CUDA path the lowest raster index): a few records per
+    # level at most, and the swapped records carry the same (octave, response) multiset
+    assert len(only_g) == len(only_r) <= 0.02 * len(gk), "%s: %d of %d records differ from the compiled reference" % (cfg, len(only_g), len(gk))
+    if only_g:
+        key = lambda x: sorted((bytes(r[16:24])) for r in (np.frombuffer(b, np.uint8) for b in x))      # response (16:20) + octave (20:24)
+        assert key(only_g) == key(only_r)
+
+
+@needs_ref
+@pytest.mark.parametrize("mode", [orc.BLUR_FLOAT_FUSED, orc.BLUR_FLOAT_UNFUSED, orc.BLUR_FIXED])
+def test_blur_mode_selection(mode):
+    """mage_orb_set_blur_mode: every arithmetic variant of the reference's GaussianBlur call, level pixels and features bit-exact"""
+    p = orc.tier_params(nfeatures=600, nlevels=4)
+    img = synth.video_frames(1, 416, 300, seed=17)[0]
+    det = make_detector(p)
+    det.SetBlurMode(mode)
+    gk, gd = det.DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1, blur_mode=mode)
+    assert_same_features(gk, gd, ok, od, "blur mode %d" % mode)
+    ref = orc.build_pyramid(p, img)
+    for l in range(p.nlevels):
+        want = orc.blur(ref[l], 7) if mode == orc.BLUR_FIXED else orc.blur_submatrix(ref[l], 7, fused=(mode == orc.BLUR_FLOAT_FUSED))
+        assert np.array_equal(det.DebugLevel(0, l, blurred=True), want), "level %d" % l
+    rk, rd = orc.detect_and_compute_ref(p, img, mode)
+    assert np.array_equal(_records(gk, gd), _records(rk, rd))
+    # and back to the default on the same handle (captured launch graphs are dropped)
+    det.SetBlurMode(orc.BLUR_AUTO)
+    gk, gd = det.DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert_same_features(gk, gd, ok, od, "blur mode auto again")
+    # other kernel sizes through the generic float kernel, unfused
+    p5 = orc.tier_params(nfeatures=300, nlevels=2); p5.gaussian_kernel_size = 5
+    d5 = make_detector(p5); d5.SetBlurMode(mode)
+    gk, gd = d5.DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p5, img, 1, blur_mode=mode)
+    assert_same_features(gk, gd, ok, od, "k5 blur mode %d" % mode)
+
+
+def test_retain_best_keeps_fewer_than_the_budget():
+    """feature_strength > 1 or feature_factor < 1: RetainBestFeatures leaves K < n_l key points and ANMS returns early
+    (ref OpenCVModified.cpp:181-184); the K survivors are emitted, nothing else (round-1 advisor finding)"""
+    img = synth.noise_frame(4, 320, 240)
+    for strength, factor in ((1.6, 1.5), (0.9, 0.5), (1.3, 0.8)):
+        p = orc.tier_params(nfeatures=800, nlevels=2)
+        p.feature_strength, p.feature_factor = strength, factor
+        gk, gd = make_detector(p).DetectAndCompute(img)
+        ok, od = orc.detect_and_compute(p, img, 1)
+        assert 0 < len(ok) < 800
+        assert_same_features(gk, gd, ok, od, "strength %.1f factor %.1f" % (strength, factor))
