@@ -39,7 +39,8 @@ struct LevelGeom {
     unsigned key_cap;
     unsigned sel_off;       // entry offset inside a frame's selected array
     unsigned tab_x, tab_y;  // offsets of the resize tables (destination = this level)
-    int fast_tiles_x, fast_tiles_y, fast_tile_base;
+    int fast_tiles_x, fast_tiles_y, fast_tile_base;       // FAST tile grid over the border-inset rectangle
+    int fast_x0, fast_y0;                                // staged-pixel origin of tile (0, 0); x is a multiple of 16
     int blur_tiles_x, blur_tiles_y, blur_tile_base;      // tile rows = kBlurOH (generic kernel) or 8*kBlur7Rows (7x7 fast path)
 };
 
@@ -178,80 +179,98 @@ __global__ void __launch_bounds__(256) k_resize4(const __grid_constant__ OrbGeom
 // ------------------------------------------------------------------------------------------------ K2: FAST + score + NMS
 // ref OpenCVModified.cpp:1224-1512 (FAST_t<16>), :926-1071 (cornerScore<16>), :619-639 (RunByImageBorder).
 // Closed form: score = max(max_k min(d[k..k+8]), -min_k max(d[k..k+8])) - 1, corner <=> score >= thr.
-constexpr int kFastPW = 128, kFastPH = 72;      // pixel tile
-constexpr int kFastOW = 120, kFastOH = 64;      // keypoint (output) tile
-constexpr int kFastSW = 122, kFastSH = 66;      // score tile
+//
+// Only key points inside the border survive (ref :712, :619-639), so only the border-inset rectangle, dilated by the one pixel
+// the 3x3 suppression looks at, is scored: the tile grid starts at the border instead of the image corner. The kernel is bound by
+// instruction issue, not by HBM; what it is built around:
+//   * a pixel PAIR per thread in packed 16-bit lanes; the pixel tile is staged twice as 16-bit elements (A[y][x] and
+//     As[y][x] = A[y][x+1]) so that every (pixel, right neighbour) pair is one aligned 32-bit shared-memory load;
+//   * the staged element is the HALF-PRECISION number 1024 + pixel (bits 0x6400 | pixel). Bit patterns of positive halves order
+//     like integers, so packed integer min/max (ALU pipe) and half2 arithmetic (FMA pipe) work on the same registers: part of the
+//     min/max network runs as  d = relu(a - b), max = b + d, min = a - d  (exact: every intermediate is an integer below 2048),
+//     which spreads the network over both pipes instead of saturating the ALU pipe alone;
+//   * work items are laid out flat over the scored rectangle of a tile, so partial tiles at the right / bottom do not idle lanes;
+//   * the 3x3 suppression walks down the score tile keeping the row-wise maxima of the two previous rows in registers.
+constexpr int kFastTW = 112, kFastTH = 64;                       // key-point (output) tile
+constexpr int kFastPW = 128, kFastPH = 72;                       // staged pixel tile: 4-pixel apron (3 ring + 1 suppression neighbour); origin and width are multiples of 16 bytes
+constexpr int kFastSW = kFastTW + 2, kFastSH = kFastTH + 2;      // score tile
+constexpr int kFastNP = kFastSW / 2;                             // score pairs per row (57)
+constexpr int kFastScP = 64;                                     // score row pitch in pair words (two u16 scores per word; the tail stays zero)
+constexpr int kFastP16 = kFastPW;                                // 16-bit elements per staged row
+constexpr int kFastAsOff = kFastPH * kFastP16;                   // As = A + kFastAsOff
+constexpr size_t kFastSmemBytes = 2 * (size_t)kFastPH * kFastP16 * sizeof(uint16_t) + (size_t)kFastSH * kFastScP * sizeof(uint32_t);
+static_assert(kFastSW % 2 == 0 && kFastNP <= kFastScP - 2 && kFastTW + 8 <= kFastPW && kFastTH + 8 == kFastPH, "FAST tile geometry");
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return min(min(a, b), c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
 
-__device__ __forceinline__ int fast_score16(const uint8_t* c)      // c = centre pixel inside the smem tile (pitch kFastPW)
+// half2 arithmetic on raw 32-bit registers (FMA pipe)
+__device__ __forceinline__ uint32_t h2_relu_diff(uint32_t a, uint32_t b)      // relu(a - b)
 {
-    constexpr int P = kFastPW;
-    const int v = c[0];
-    int d[16];
-    d[0] = v - c[3 * P];      d[1] = v - c[3 * P + 1];   d[2] = v - c[2 * P + 2];   d[3] = v - c[P + 3];
-    d[4] = v - c[3];          d[5] = v - c[-P + 3];      d[6] = v - c[-2 * P + 2];  d[7] = v - c[-3 * P + 1];
-    d[8] = v - c[-3 * P];     d[9] = v - c[-3 * P - 1];  d[10] = v - c[-2 * P - 2]; d[11] = v - c[-P - 3];
-    d[12] = v - c[-3];        d[13] = v - c[P - 3];      d[14] = v - c[2 * P - 2];  d[15] = v - c[3 * P - 1];
-    int lo3[16], hi3[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        lo3[k] = min3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-        hi3[k] = max3(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    }
-    int q0 = -1000, q1 = 1000;
-#pragma unroll
-    for (int k = 0; k < 16; k++) {
-        q0 = max(q0, min3(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]));
-        q1 = min(q1, max3(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]));
-    }
-    return max(q0, -q1) - 1;
+    uint32_t d;
+    asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(0xBC00BC00u), "r"(a));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b)            // a + b
+{
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0x3C003C00u), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t h2_sub(uint32_t a, uint32_t b)            // a - b
+{
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(b), "r"(0xBC00BC00u), "r"(a));
+    return d;
+}
+// minimum and maximum of the same two operands: two ALU-pipe instructions, or three FMA-pipe ones
+template <bool FMA> __device__ __forceinline__ void h2_minmax(uint32_t a, uint32_t b, uint32_t& mn, uint32_t& mx)
+{
+    if (FMA) { const uint32_t d = h2_relu_diff(a, b); mx = h2_add(b, d); mn = h2_sub(a, d); }
+    else { mn = __vmins2(a, b); mx = __vmaxs2(a, b); }
 }
 
-// Two horizontally adjacent pixels per thread in packed s16x2 form (VIADD.16x2 / VIMNMX3.S16x2 on sm_100a): e[k] = ring - centre
-// for both pixels, sliding minimum/maximum over 9 consecutive ring positions as two levels of 3-input min/max.
-// The pixel tile is staged as u16 twice -- A[y][x] and As[y][x] = A[y][x+1] -- so that every (pixel, right neighbour) pair
-// is one aligned 32-bit shared-memory load whatever the parity of its column.
-constexpr int kFastP16 = kFastPW;                 // u16 elements per staged row
-
+// `base` = address of staged element (first pixel of the pair) - 1, an even element index: pair (x + DX, x + DX + 1) is A[...] when
+// x + DX is even and As[x + DX - 1] when it is odd -- either way one aligned word at a compile-time offset from `base`
 template <int DX, int DY>
-__device__ __forceinline__ uint32_t ring_pair(const uint16_t* A, const uint16_t* As, int py, int px /* odd */)
+__device__ __forceinline__ uint32_t ring_pair(const uint16_t* base)
 {
-    // column of the first pixel of the pair: c = px + DX; c even -> A[c], c odd -> As[c - 1]
-    const int c = px + DX;
-    const uint16_t* base = ((DX & 1) != 0) ? A : As;           // px is odd: DX odd => c even
-    const int col = ((DX & 1) != 0) ? c : c - 1;
-    return *reinterpret_cast<const uint32_t*>(base + (py + DY) * kFastP16 + col);
+    constexpr int off = DY * kFastP16 + ((DX & 1) != 0 ? DX + 1 : DX + kFastAsOff);
+    return *reinterpret_cast<const uint32_t*>(base + off);
 }
 
-__device__ __forceinline__ uint32_t fast_score_pair(const uint16_t* A, const uint16_t* As, int py, int px, uint32_t negthr2)
+// NP / NX / NQ: how many of the 8 + 8 first-level (min, max) pairs and of the 8 second-level pairs run on the FMA pipe
+template <int NP, int NX, int NQ>
+__device__ __forceinline__ uint32_t fast_score_pair(const uint16_t* base, uint32_t thr_h2)
 {
     // min/max commute with the subtraction of the centre, so the whole network runs on the RAW ring values R[0..15] and the
     // centre v enters once at the end:  score + 1 = max(v - T, S - v),  S = max_k min(R[k..k+8]),  T = min_k max(R[k..k+8]).
     // Windows k = 2j and 2j+1 share R[2j+1..2j+8]; max(min(sh, a), min(sh, b)) = min(sh, max(a, b)), hence
     //   S = max_j min(R[2j+1..2j+8], max(R[2j], R[2j+9])),  T = min_j max(R[2j+1..2j+8], min(R[2j], R[2j+9]))
-    // -> 36 packed min/max per polarity (the ALU pipe issues these at half rate, so their count is what bounds the kernel).
+    // -> 36 packed min/max per polarity.
     uint32_t R[16];
-    R[0] = ring_pair<0, 3>(A, As, py, px);    R[1] = ring_pair<1, 3>(A, As, py, px);
-    R[2] = ring_pair<2, 2>(A, As, py, px);    R[3] = ring_pair<3, 1>(A, As, py, px);
-    R[4] = ring_pair<3, 0>(A, As, py, px);    R[5] = ring_pair<3, -1>(A, As, py, px);
-    R[6] = ring_pair<2, -2>(A, As, py, px);   R[7] = ring_pair<1, -3>(A, As, py, px);
-    R[8] = ring_pair<0, -3>(A, As, py, px);   R[9] = ring_pair<-1, -3>(A, As, py, px);
-    R[10] = ring_pair<-2, -2>(A, As, py, px); R[11] = ring_pair<-3, -1>(A, As, py, px);
-    R[12] = ring_pair<-3, 0>(A, As, py, px);  R[13] = ring_pair<-3, 1>(A, As, py, px);
-    R[14] = ring_pair<-2, 2>(A, As, py, px);  R[15] = ring_pair<-1, 3>(A, As, py, px);
+    R[0] = ring_pair<0, 3>(base);    R[1] = ring_pair<1, 3>(base);    R[2] = ring_pair<2, 2>(base);    R[3] = ring_pair<3, 1>(base);
+    R[4] = ring_pair<3, 0>(base);    R[5] = ring_pair<3, -1>(base);   R[6] = ring_pair<2, -2>(base);   R[7] = ring_pair<1, -3>(base);
+    R[8] = ring_pair<0, -3>(base);   R[9] = ring_pair<-1, -3>(base);  R[10] = ring_pair<-2, -2>(base); R[11] = ring_pair<-3, -1>(base);
+    R[12] = ring_pair<-3, 0>(base);  R[13] = ring_pair<-3, 1>(base);  R[14] = ring_pair<-2, 2>(base);  R[15] = ring_pair<-1, 3>(base);
     uint32_t pmin[8], pmax[8], xmin[8], xmax[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        pmin[j] = __vmins2(R[(2 * j + 1) & 15], R[(2 * j + 2) & 15]);
-        pmax[j] = __vmaxs2(R[(2 * j + 1) & 15], R[(2 * j + 2) & 15]);
-        xmin[j] = __vmins2(R[2 * j], R[(2 * j + 9) & 15]);
-        xmax[j] = __vmaxs2(R[2 * j], R[(2 * j + 9) & 15]);
+        if (j < NP) h2_minmax<true>(R[(2 * j + 1) & 15], R[(2 * j + 2) & 15], pmin[j], pmax[j]);
+        else h2_minmax<false>(R[(2 * j + 1) & 15], R[(2 * j + 2) & 15], pmin[j], pmax[j]);
+        if (j < NX) h2_minmax<true>(R[2 * j], R[(2 * j + 9) & 15], xmin[j], xmax[j]);
+        else h2_minmax<false>(R[2 * j], R[(2 * j + 9) & 15], xmin[j], xmax[j]);
     }
     uint32_t qmin[8], qmax[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { qmin[j] = __vmins2(pmin[j], pmin[(j + 1) & 7]); qmax[j] = __vmaxs2(pmax[j], pmax[(j + 1) & 7]); }
+    for (int j = 0; j < 8; j++) {
+        if (j < NQ) {
+            qmin[j] = h2_sub(pmin[j], h2_relu_diff(pmin[j], pmin[(j + 1) & 7]));
+            qmax[j] = h2_add(pmax[(j + 1) & 7], h2_relu_diff(pmax[j], pmax[(j + 1) & 7]));
+        } else {
+            qmin[j] = __vmins2(pmin[j], pmin[(j + 1) & 7]); qmax[j] = __vmaxs2(pmax[j], pmax[(j + 1) & 7]);
+        }
+    }
     uint32_t ymin[8], ymax[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -262,166 +281,253 @@ __device__ __forceinline__ uint32_t fast_score_pair(const uint16_t* A, const uin
     S = __vimax3_s16x2(S, ymin[3], ymin[4]); T = __vimin3_s16x2(T, ymax[3], ymax[4]);
     S = __vimax3_s16x2(S, ymin[5], ymin[6]); T = __vimin3_s16x2(T, ymax[5], ymax[6]);
     S = __vmaxs2(S, ymin[7]); T = __vmins2(T, ymax[7]);
-    const uint32_t vv = ring_pair<0, 0>(A, As, py, px);
-    const uint32_t m = __vmaxs2(__vsub2(vv, T), __vsub2(S, vv));            // score + 1 per half
-    // Returned BIASED: max(score - (thr - 1), 0), i.e. 0 for non-corners and an order-preserving positive value for corners
-    // (the NMS only compares; the emitter adds thr - 1 back)
-    return __vmaxs2(__vadd2(m, negthr2), 0u);
+    const uint32_t vv = ring_pair<0, 0>(base);
+    // Returned BIASED: max(score + 1 - thr, 0) = max(relu(v - thr - T), relu(S - (v + thr))) -- 0 for non-corners and an
+    // order-preserving positive value for corners (the suppression only compares; the emitter adds thr - 1 back). Both terms are
+    // non-negative halves, so the integer maximum is their maximum; + 1024 puts the integer into the low 10 mantissa bits.
+    const uint32_t a1 = h2_relu_diff(h2_sub(vv, thr_h2), T), b1 = h2_relu_diff(S, h2_add(vv, thr_h2));
+    return h2_add(__vmaxs2(a1, b1), 0x64006400u) & 0x03ff03ffu;
 }
 
-constexpr int kFastScP = 64;                      // score row pitch in PAIR words (two u16 scores per word; 61 used + 3 zeroed)
-constexpr size_t kFastSmemBytes = 2 * (size_t)kFastPH * kFastP16 * sizeof(uint16_t) + (size_t)kFastSH * kFastScP * sizeof(uint32_t);
-
-// scores -> strict 3x3 NMS -> border cull -> append, on a pixel tile already staged as u16 (A, As); shared by both FAST kernels
-__device__ __forceinline__ void fast_tile_compute(const OrbGeom& g, const OrbBuffers& b, const LevelGeom& L, int f, int l, int px0, int py0,
-                                                  uint16_t* A, uint16_t* As, uint32_t* sc, int& s_n, int& s_base)
+// High-speed test of a pair (ref :1415-1440 tests the same compass points one pixel at a time): every 9-arc of the 16-ring contains
+// at least one pixel of each opposite couple {k, k + 8}, so S <= max(R[k], R[k+8]) and T >= min(R[k], R[k+8]) for every k. With the
+// couples k = 0 and k = 4:  score >= thr  =>  min(max(R0, R8), max(R4, R12)) - v > thr  or  v - max(min(R0, R8), min(R4, R12)) > thr.
+// True when either pixel of the pair can still be a corner; never false for a corner.
+__device__ __forceinline__ bool fast_pretest_pair(const uint16_t* base, uint32_t thr_h2)
 {
-    constexpr int kPairs = kFastSW / 2;                          // 61 pairs per score row
-    for (int i = threadIdx.x; i < kFastSH * (kFastScP - kPairs); i += blockDim.x)      // the unused tail pairs read as 0
-        sc[(i / (kFastScP - kPairs)) * kFastScP + kPairs + i % (kFastScP - kPairs)] = 0;
+    const uint32_t r0 = ring_pair<0, 3>(base), r4 = ring_pair<3, 0>(base), r8 = ring_pair<0, -3>(base), r12 = ring_pair<-3, 0>(base);
+    const uint32_t vv = ring_pair<0, 0>(base);
+    const uint32_t lo = __vmins2(__vmaxs2(r0, r8), __vmaxs2(r4, r12)), hi = __vmaxs2(__vmins2(r0, r8), __vmins2(r4, r12));
+    const uint32_t t = h2_relu_diff(lo, h2_add(vv, thr_h2)) | h2_relu_diff(h2_sub(vv, thr_h2), hi);
+    return (t & 0x7fff7fffu) != 0;
+}
+constexpr int kFastDenseAt = 22;       // survivors of a 32-pair chunk from which the test costs more than it saves
+constexpr int kFastDenseRun = 15;      // chunks a warp stays in dense mode before it probes again
+
+// One entry per tile of the per-frame grid, built on the host by mage_orb_create (fast_tile_table) and read by every thread of the
+// CTA with two 16-byte loads: the tile's place, the part of it that is scored and the constants of the flat item walk -- about 200
+// instructions of per-thread set-up otherwise. Score column sx <-> image x = px0 + 3 + sx <-> staged column 3 + sx.
+struct alignas(16) FastTile {
+    short l, px0, py0;                          // level, staged-pixel origin (px0 a multiple of 16)
+    short xlo, xhi;                             // key-point columns of this tile inside the border: [xlo, xhi)
+    signed char oy_lo, oy_hi;                   // first / last output row inside the border
+    unsigned char sp_lo, npx, sy_lo, nrows;     // scored rectangle: first score pair, pairs per row, first score row, rows -- the
+                                                // border-inset rectangle dilated by one pixel, clipped to 3 <= x <= w - 4 (FAST's domain)
+    unsigned char dsy, dsp;                     // 256 / npx, 256 % npx
+    unsigned char g_lo, g_hi;                   // first / last 16-pixel group of a staged row the rectangle touches
+    unsigned int inv_npx;                       // ceil(2^32 / npx): t / npx == umulhi(t, inv_npx) for t < 256
+    unsigned int pad[2];
+};
+static_assert(sizeof(FastTile) == 32, "FastTile is read as two uint4");
+__device__ __forceinline__ FastTile fast_tile_load(const FastTile* table, int tile)
+{
+    union { FastTile t; uint4 q[2]; } u;
+    u.q[0] = __ldg(reinterpret_cast<const uint4*>(table + tile)); u.q[1] = __ldg(reinterpret_cast<const uint4*>(table + tile) + 1);
+    return u.t;
+}
+
+// 16 pixels -> 16 staged elements of A (element k = 0x6400 | pixel k) and of As (element k = 0x6400 | pixel k + 1)
+__device__ __forceinline__ void fast_widen16(const uint4 v, uint32_t nxt, uint16_t* a)
+{
+    constexpr uint32_t H = 0x64646464u;
+    uint4 o;
+    o.x = __byte_perm(v.x, H, 0x4140); o.y = __byte_perm(v.x, H, 0x4342); o.z = __byte_perm(v.y, H, 0x4140); o.w = __byte_perm(v.y, H, 0x4342);
+    *reinterpret_cast<uint4*>(a) = o;
+    o.x = __byte_perm(v.z, H, 0x4140); o.y = __byte_perm(v.z, H, 0x4342); o.z = __byte_perm(v.w, H, 0x4140); o.w = __byte_perm(v.w, H, 0x4342);
+    *reinterpret_cast<uint4*>(a + 8) = o;
+    const uint32_t s0 = __funnelshift_r(v.x, v.y, 8), s1 = __funnelshift_r(v.y, v.z, 8), s2 = __funnelshift_r(v.z, v.w, 8), s3 = __funnelshift_r(v.w, nxt, 8);
+    o.x = __byte_perm(s0, H, 0x4140); o.y = __byte_perm(s0, H, 0x4342); o.z = __byte_perm(s1, H, 0x4140); o.w = __byte_perm(s1, H, 0x4342);
+    *reinterpret_cast<uint4*>(a + kFastAsOff) = o;
+    o.x = __byte_perm(s2, H, 0x4140); o.y = __byte_perm(s2, H, 0x4342); o.z = __byte_perm(s3, H, 0x4140); o.w = __byte_perm(s3, H, 0x4342);
+    *reinterpret_cast<uint4*>(a + kFastAsOff + 8) = o;
+}
+
+__device__ __forceinline__ void fast_zero_scores(uint32_t* sc)
+{
+    for (int i = threadIdx.x; i < kFastSH * kFastScP / 4; i += 256) reinterpret_cast<uint4*>(sc)[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// scores -> strict 3x3 NMS -> border cull -> append, on a pixel tile already staged (A, As) and a zeroed score tile; shared by
+// both FAST kernels. Begins with the barrier that publishes the staged tile.
+template <int NP, int NX, int NQ>
+__device__ __forceinline__ void fast_tile_compute(const OrbGeom& g, const OrbBuffers& b, const LevelGeom& L, int f, const FastTile& T,
+                                                  uint16_t* A, uint32_t* sc, uint16_t* queue, int& s_n, int& s_base)
+{
+    const int tid = threadIdx.x, thr = g.fast_threshold, bd = g.border, l = T.l, px0 = T.px0, py0 = T.py0;
+    struct { int sp_lo, npx, sy_lo, nrows; } rg = {T.sp_lo, T.npx, T.sy_lo, T.nrows};
+    if (tid == 0) s_n = 0;
     __syncthreads();
-    // scores: thread = (pair column, row phase); the column bounds become one hoisted mask and the row bounds loop limits
-    const int thr = g.fast_threshold;
     {
-        const uint32_t thr2 = (uint32_t)thr | ((uint32_t)thr << 16), negthr2 = __vadd2(~thr2, 0x00010001u);
-        const int sp = threadIdx.x & (kFastScP - 1), r0 = threadIdx.x / kFastScP;          // 64 pair columns x 4 row phases
-        const int x = px0 + 3 + 2 * sp;
-        const uint32_t cmask = ((x >= 3 && x <= L.w - 4) ? 0x0000ffffu : 0u) | ((x + 1 >= 3 && x + 1 <= L.w - 4) ? 0xffff0000u : 0u);
-        const int sy_lo = max(0, -py0), sy_hi = min(kFastSH - 1, L.h - 7 - py0);           // rows with 3 <= y <= h - 4
-        if (sp < kPairs) {
-            for (int sy = r0; sy < kFastSH; sy += 256 / kFastScP) {
-                uint32_t out = 0;
-                if (cmask != 0 && sy >= sy_lo && sy <= sy_hi) out = fast_score_pair(A, As, sy + 3, 2 * sp + 3, negthr2) & cmask;
-                sc[sy * kFastScP + sp] = out;
+        // scores: items = the pairs of the scored rectangle in raster order, a chunk of 32 per warp and step. A warp is either in
+        // DENSE mode (every pair goes through the network) or in SPARSE mode: every pair takes the high-speed test first and the
+        // survivors are queued per warp until 32 of them fill a full-width pass through the network -- on camera images a few
+        // per cent of the pairs survive, on a corner-dense chart most do and the test would only add work. A chunk whose
+        // survivors exceed kFastDenseAt switches the warp to dense mode for the next kFastDenseRun chunks, then it probes again.
+        // Pairs that fail the test keep the zero the score tile was cleared to; the outputs do not depend on the mode.
+        const int nit = rg.npx * rg.nrows, lane = tid & 31;
+        const int nchunks = (nit + 255) >> 8;
+        if (nchunks > 0) {
+            const uint32_t thr_h2 = h2_sub(0x64006400u | (uint32_t)thr | ((uint32_t)thr << 16), 0x64006400u);      // (thr, thr) as halves
+            const uint32_t lt = (1u << lane) - 1u;
+            uint16_t* q = queue + (tid >> 5) * 64;
+            int sy = (int)__umulhi((unsigned)tid, T.inv_npx), sp = tid - sy * rg.npx;
+            const int dsy = T.dsy, dsp = T.dsp;
+            const bool edge = bd < 5;                              // the rectangle then touches columns FAST is not defined on
+            int qn = 0, dense_left = 0;
+            for (int k = 0; k <= nchunks; k++) {                   // the last turn only drains the queue
+                bool go = false;
+                int e = 0;                                         // score-tile word of the pair: row << 6 | pair column
+                if (k < nchunks) {
+                    const bool valid = k * 256 + tid < nit;
+                    e = ((rg.sy_lo + sy) << 6) | (rg.sp_lo + sp);
+                    sp += dsp; sy += dsy;
+                    if (sp >= rg.npx) { sp -= rg.npx; sy++; }
+                    if (dense_left > 0) { dense_left--; go = valid; }
+                    else {
+                        const bool pass = valid && fast_pretest_pair(A + ((e >> 6) + 3) * kFastP16 + 2 * (e & 63) + 2, thr_h2);
+                        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+                        const int np = __popc(m);
+                        if (np >= kFastDenseAt) { dense_left = kFastDenseRun; go = valid; }
+                        else if (np > 0) {
+                            if (pass) q[qn + __popc(m & lt)] = (uint16_t)e;
+                            qn += np;
+                            __syncwarp();
+                            if (qn >= 32) { qn -= 32; e = q[qn + lane]; go = true; }
+                        }
+                    }
+                } else if (lane < qn) { e = q[lane]; go = true; }
+                if (go) {
+                    const int spx = e & 63;
+                    uint32_t out = fast_score_pair<NP, NX, NQ>(A + ((e >> 6) + 3) * kFastP16 + 2 * spx + 2, thr_h2);
+                    if (edge) {
+                        const int x = px0 + 3 + 2 * spx;
+                        out &= ((x >= 3 && x <= L.w - 4) ? 0x0000ffffu : 0u) | ((x + 1 >= 3 && x + 1 <= L.w - 4) ? 0xffff0000u : 0u);
+                    }
+                    sc[e] = out;
+                }
+                __syncwarp();                                      // queue reads of this turn precede the writes of the next
             }
         }
     }
     __syncthreads();
-    const int bd = g.border;
-    // survivors are collected in shared memory (reusing the pixel tile) and appended with ONE global atomic per CTA:
-    // a returning global atomic per warp iteration stalled the whole loop on L2 round trips (ncu: 41 % of samples)
-    uint32_t* list = reinterpret_cast<uint32_t*>(A);            // <= 1920 survivors (strict NMS: one per 2x2 block)
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    // strict 3x3 non-maximum suppression, 4 pixels (two pair words) per thread iteration in packed u16x2 arithmetic: the
-    // neighbourhood maximum of a pair is VIMNMX3 over funnel-shifted row words. Thread = (quad column, row phase): the border
-    // cull in x is one hoisted lane mask, in y the loop limits; quads without a corner leave after one 64-bit load. A warp is
-    // one row of quads and runs a uniform trip count, so survivors are appended with one shared atomic per warp iteration.
-    constexpr int kQuads = (kPairs + 1) / 2;                     // 31 quads per row (the last one half inside the zeroed tail)
-    static_assert(kQuads <= 32 && kFastOH % 8 == 0, "one warp per quad row, 8 row phases");
-    const int lane = threadIdx.x & 31, q = lane;
-    const int xq = px0 + 3 + 4 * q;                              // image column of quad pixel 0 (score column sx = 4q)
-    const int xlo = max(bd, px0 + 4), xhi = min(L.w - bd, px0 + 4 + kFastOW);     // keypoint columns of this tile inside the border
+    // Strict 3x3 non-maximum suppression. Lane = 4 score columns (two pair words), warp = 8 output rows: the warp walks down 10
+    // score rows; per row it forms LR = max(left, right) and H = max(LR, centre) in packed u16x2 arithmetic (the horizontal
+    // neighbours of a pair are funnel shifts over the words of the adjacent lanes) and keeps them for two rows, so a pixel's
+    // eight neighbours are max3(H above, H below, LR). Survivors are collected in shared memory (reusing the pixel tile) and
+    // appended with ONE global atomic per CTA.
+    uint32_t* list = reinterpret_cast<uint32_t*>(A);            // <= 1792 survivors (strict NMS: one per 2x2 block)
+    const int lane = tid & 31, oy0 = 8 * (tid >> 5);
+    const int xq = px0 + 3 + 4 * lane;                           // image column of the lane's first score column
+    const int xlo = T.xlo, xhi = T.xhi;                          // key-point columns of this tile inside the border
     uint2 xmask;
     xmask.x = ((xq >= xlo && xq < xhi) ? 0x0000ffffu : 0u) | ((xq + 1 >= xlo && xq + 1 < xhi) ? 0xffff0000u : 0u);
     xmask.y = ((xq + 2 >= xlo && xq + 2 < xhi) ? 0x0000ffffu : 0u) | ((xq + 3 >= xlo && xq + 3 < xhi) ? 0xffff0000u : 0u);
-    if (q >= kQuads) xmask.x = xmask.y = 0;
-    const int oy_lo = max(0, bd - (py0 + 4)), oy_hi = min(kFastOH - 1, L.h - bd - 1 - (py0 + 4));
-    for (int oy = threadIdx.x >> 5; oy < kFastOH; oy += 8) {
-        if (oy < oy_lo || oy > oy_hi) continue;                  // warp-uniform
-        const uint32_t* row = sc + (oy + 1) * kFastScP + 2 * (q < kQuads ? q : 0);
-        const uint2 c = *reinterpret_cast<const uint2*>(row);
-        uint32_t keep = 0;                                       // bit 0 / 16 / 1 / 17 = pixel 0 / 1 / 2 / 3 of the quad survives
-        if (((c.x & xmask.x) | (c.y & xmask.y)) != 0) {
-            const uint2 u = *reinterpret_cast<const uint2*>(row - kFastScP), d = *reinterpret_cast<const uint2*>(row + kFastScP);
-            const uint32_t cp = row[-1], cn = row[2], up = row[-kFastScP - 1], un = row[-kFastScP + 2];
-            const uint32_t dp = row[kFastScP - 1], dn = row[kFastScP + 2];
-            const uint32_t c01 = __funnelshift_r(c.x, c.y, 16), u01 = __funnelshift_r(u.x, u.y, 16), d01 = __funnelshift_r(d.x, d.y, 16);
-            // pair 0 (pixels 0,1): left = (prev.hi, x.lo), right = (x.hi, y.lo); pair 1 (pixels 2,3): left = (x.hi, y.lo), right = (y.hi, next.lo)
-            uint32_t n0 = __vimax3_u16x2(__funnelshift_r(up, u.x, 16), u.x, u01);
-            n0 = __vimax3_u16x2(n0, __funnelshift_r(cp, c.x, 16), c01);
-            n0 = __vimax3_u16x2(n0, __vimax3_u16x2(__funnelshift_r(dp, d.x, 16), d.x, d01), n0);
-            uint32_t n1 = __vimax3_u16x2(u01, u.y, __funnelshift_r(u.y, un, 16));
-            n1 = __vimax3_u16x2(n1, c01, __funnelshift_r(c.y, cn, 16));
-            n1 = __vimax3_u16x2(n1, __vimax3_u16x2(d01, d.y, __funnelshift_r(d.y, dn, 16)), n1);
-            // v > n  <=>  max(v, n) != n; the differences are < 256 per half, so "+ 0xff >> 8" turns each half into its nonzero flag
-            const uint32_t g0 = __vmaxu2(c.x & xmask.x, n0) ^ n0, g1 = __vmaxu2(c.y & xmask.y, n1) ^ n1;
-            keep = (((g0 + 0x00ff00ffu) >> 8) & 0x00010001u) | (((g1 + 0x00ff00ffu) >> 7) & 0x00020002u);
-        }
-        if (__any_sync(0xffffffffu, keep != 0)) {
-            const int mine = __popc(keep);
-            int incl = mine;                                      // inclusive warp prefix sum of the survivor counts
+    const int oy_lo = T.oy_lo, oy_hi = T.oy_hi;
+    if (oy0 <= oy_hi && oy0 + 7 >= oy_lo) {                      // warp-uniform
+        const uint32_t* col = sc + 2 * lane;
+        const uint32_t lt = (1u << lane) - 1u, bias = (uint32_t)(thr - 1);
+        uint2 cP = make_uint2(0u, 0u), hP = cP, hPP = cP, lrP = cP;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
-            int base = 0;
-            if (lane == 31) base = atomicAdd(&s_n, incl);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
-            const uint32_t pos = (uint32_t)((py0 + 4 + oy) * L.w + xq), bias = (uint32_t)(thr - 1);
-            if (keep & 0x00000001u) list[base++] = (((c.x & 0xffffu) + bias) << 24) | pos;
-            if (keep & 0x00010000u) list[base++] = (((c.x >> 16) + bias) << 24) | (pos + 1);
-            if (keep & 0x00000002u) list[base++] = (((c.y & 0xffffu) + bias) << 24) | (pos + 2);
-            if (keep & 0x00020000u) list[base++] = (((c.y >> 16) + bias) << 24) | (pos + 3);
+        for (int k = 0; k < 10; k++) {
+            const int r = oy0 + k;                               // score row
+            const uint2 c = *reinterpret_cast<const uint2*>(col + r * kFastScP);
+            const uint32_t cp = __shfl_up_sync(0xffffffffu, c.y, 1), cn = __shfl_down_sync(0xffffffffu, c.x, 1);
+            // lane 0 / 31 get their own word back: they only feed columns outside the key-point range (masked below)
+            const uint32_t l0 = __funnelshift_r(cp, c.x, 16), m01 = __funnelshift_r(c.x, c.y, 16), r1 = __funnelshift_r(c.y, cn, 16);
+            uint2 lr, hh;
+            lr.x = __vmaxu2(l0, m01); lr.y = __vmaxu2(m01, r1);
+            hh.x = __vmaxu2(lr.x, c.x); hh.y = __vmaxu2(lr.y, c.y);
+            const int oy = r - 2;                                // output row of the PREVIOUS score row
+            if (k >= 2 && oy >= oy_lo && oy <= oy_hi) {          // warp-uniform
+                const uint32_t n0 = __vimax3_u16x2(hPP.x, hh.x, lrP.x), n1 = __vimax3_u16x2(hPP.y, hh.y, lrP.y);
+                // v > n  <=>  max(v, n) != n; the differences are < 256 per half, so "+ 0xff >> 8" turns each half into its nonzero flag
+                const uint32_t g0 = __vmaxu2(cP.x & xmask.x, n0) ^ n0, g1 = __vmaxu2(cP.y & xmask.y, n1) ^ n1;
+                // bit 0 / 16 / 1 / 17 = pixel 0 / 1 / 2 / 3 of the quad survives (at most two of them: they are not adjacent)
+                const uint32_t keep = (((g0 + 0x00ff00ffu) >> 8) & 0x00010001u) | (((g1 + 0x00ff00ffu) >> 7) & 0x00020002u);
+                const uint32_t b1 = __ballot_sync(0xffffffffu, keep != 0);
+                if (b1 != 0) {
+                    const uint32_t b2 = __ballot_sync(0xffffffffu, (keep & (keep - 1u)) != 0);
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_n, __popc(b1) + __popc(b2));
+                    base = __shfl_sync(0xffffffffu, base, 0) + __popc(b1 & lt) + __popc(b2 & lt);
+                    const uint32_t pos = (uint32_t)((py0 + 4 + oy) * L.w + xq);
+                    if (keep & 0x00000001u) list[base++] = (((cP.x & 0xffffu) + bias) << 24) | pos;
+                    if (keep & 0x00010000u) list[base++] = (((cP.x >> 16) + bias) << 24) | (pos + 1);
+                    if (keep & 0x00000002u) list[base++] = (((cP.y & 0xffffu) + bias) << 24) | (pos + 2);
+                    if (keep & 0x00020000u) list[base++] = (((cP.y >> 16) + bias) << 24) | (pos + 3);
+                }
+            }
+            hPP = hP; hP = hh; lrP = lr; cP = c;
         }
     }
     __syncthreads();
     const int n = s_n;
     if (n == 0) return;        // uniform: s_n is shared
-    if (threadIdx.x == 0) s_base = atomicAdd(b.cand_count + f * kMaxLevels + l, n);
+    if (tid == 0) s_base = atomicAdd(b.cand_count + f * kMaxLevels + l, n);
     __syncthreads();
     uint32_t* cand = b.cand + (size_t)f * b.cand_stride + L.cand_off;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += 256) {
         const int slot = s_base + i;
         if (slot < (int)L.cand_cap) cand[slot] = list[i];
     }
 }
 
-__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+template <int NP, int NX, int NQ>
+__global__ void __launch_bounds__(256) k_fast(const __grid_constant__ OrbGeom g, const OrbBuffers b, const FastTile* __restrict__ tiles)
 {
     extern __shared__ __align__(128) uint8_t fast_smem[];
     uint16_t* A = reinterpret_cast<uint16_t*>(fast_smem);
-    uint16_t* As = A + kFastPH * kFastP16;
-    uint32_t* sc = reinterpret_cast<uint32_t*>(As + kFastPH * kFastP16);       // [kFastSH][kFastScP], scores as u16 pairs
+    uint32_t* sc = reinterpret_cast<uint32_t*>(A + 2 * kFastAsOff);            // [kFastSH][kFastScP], scores as u16 pairs
+    __shared__ int s_n, s_base;
+    __shared__ uint16_t queue[8 * 64];                                          // sparse-mode survivors, 64 per warp
     const int f = blockIdx.y;
-    int l = 0;
-    while (l + 1 < g.nlevels && (int)blockIdx.x >= g.lv[l + 1].fast_tile_base) l++;
+    const FastTile T = fast_tile_load(tiles, blockIdx.x);
+    const int l = T.l, px0 = T.px0, py0 = T.py0;
     const LevelGeom& L = g.lv[l];
-    const int t = blockIdx.x - L.fast_tile_base;
-    const int tx = t % L.fast_tiles_x, ty = t / L.fast_tiles_x;
-    const int px0 = kFastOW * tx - 4, py0 = kFastOH * ty - 4;
     int pitch;
     const uint8_t* img = level_ptr(g, b, f, l, pitch);
 
-    // stage the pixel tile: 32-bit global loads (zero fill outside the image rows / pitch), all issued before the first use,
-    // then widened to u16 twice
-    constexpr int kStageIters = kFastPH * (kFastPW / 4) / 256;
-    static_assert(kStageIters * 256 == kFastPH * (kFastPW / 4), "pixel tile must be a whole number of 256-thread passes");
-    uint32_t pv[kStageIters];
+    // stage the pixels the scored rectangle touches: 16-byte global loads (a thread = 16 pixels of one row), all issued before the
+    // first use, then widened to 16-bit elements twice. Rows are inside the image by construction; a 16-pixel group left of the
+    // image or running past the row pitch is loaded word by word with zero fill.
+    const int g_lo = T.g_lo, g_hi = T.g_hi, sy_lo = T.sy_lo;
+    const int n_rows = T.nrows > 0 && T.npx > 0 ? T.nrows + 6 : 0;
+    const bool wide = ((reinterpret_cast<uintptr_t>(img) | (uintptr_t)pitch) & 15) == 0;
+    constexpr int kStageIters = (kFastPH * 8 + 255) / 256;
+    uint4 pv[kStageIters];
 #pragma unroll
     for (int it = 0; it < kStageIters; it++) {
-        const int i = it * 256 + threadIdx.x;
-        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
-        const int y = py0 + ry, x = px0 + rx;
-        pv[it] = 0;
-        if (y >= 0 && y < L.h && x >= 0 && x + 4 <= pitch) pv[it] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)y * pitch + x));
+        const int i = it * 256 + threadIdx.x, ry = i >> 3, grp = i & 7;
+        pv[it] = make_uint4(0u, 0u, 0u, 0u);
+        if (ry < n_rows && grp >= g_lo && grp <= g_hi) {
+            const int x = px0 + 16 * grp;
+            const uint8_t* p = img + (size_t)(py0 + sy_lo + ry) * pitch + x;
+            if (wide && x >= 0 && x + 16 <= pitch) pv[it] = __ldg(reinterpret_cast<const uint4*>(p));
+            else {
+                if (x >= 0 && x + 4 <= pitch) pv[it].x = __ldg(reinterpret_cast<const uint32_t*>(p));
+                if (x + 4 >= 0 && x + 8 <= pitch) pv[it].y = __ldg(reinterpret_cast<const uint32_t*>(p + 4));
+                if (x + 8 >= 0 && x + 12 <= pitch) pv[it].z = __ldg(reinterpret_cast<const uint32_t*>(p + 8));
+                if (x + 12 >= 0 && x + 16 <= pitch) pv[it].w = __ldg(reinterpret_cast<const uint32_t*>(p + 12));
+            }
+        }
     }
+    fast_zero_scores(sc);
 #pragma unroll
     for (int it = 0; it < kStageIters; it++) {
-        const int i = it * 256 + threadIdx.x;
-        const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
-        const uint32_t v = pv[it];
-        const uint32_t p01 = __byte_perm(v, 0, 0x4140), p23 = __byte_perm(v, 0, 0x4342), p12 = __byte_perm(v, 0, 0x4241);
-        uint16_t* a = A + ry * kFastP16 + rx;
-        uint16_t* as = As + ry * kFastP16 + rx;
-        *reinterpret_cast<uint32_t*>(a) = p01;
-        *reinterpret_cast<uint32_t*>(a + 2) = p23;
-        if (rx > 0) as[-1] = (uint16_t)(v & 0xff);               // As[x] = A[x + 1]
-        *reinterpret_cast<uint32_t*>(as) = p12;
-        as[2] = (uint16_t)(v >> 24);
+        const int i = it * 256 + threadIdx.x, ry = i >> 3, grp = i & 7;
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, pv[it].x, 1);        // first pixel of the next group of the row (group 7: not needed)
+        if (ry < n_rows && grp >= g_lo && grp <= g_hi) fast_widen16(pv[it], nxt, A + (sy_lo + ry) * kFastP16 + 16 * grp);
     }
-    __shared__ int s_n, s_base;
-    fast_tile_compute(g, b, L, f, l, px0, py0, A, As, sc, s_n, s_base);
+    fast_tile_compute<NP, NX, NQ>(g, b, L, f, T, A, sc, queue, s_n, s_base);
 }
 
-// TMA variant: a persistent CTA walks the (tile, frame) list; the pixel tile of the NEXT item is fetched by one
-// cp.async.bulk.tensor (3-D tensor map per level: x, y, frame; out-of-image bytes arrive as zeros, so there is no bounds logic)
-// into the other half of a double buffer while the current tile is scored -- the global-load latency and the staging barrier
-// bubbles of k_fast (ncu: 25 % of its stall samples) move under the min/max network. The innermost TMA coordinate must be a
-// multiple of 16 bytes (measured on B200: any other start raises an illegal-instruction fault, tools/tma_probe2.cu) while the tile
-// origin is 120 tx - 4, so the box is 16 bytes wider (144 x 72) and starts at the origin rounded down to 16.
+// TMA variant: the pixel tile is fetched by ONE cp.async.bulk.tensor per CTA (3-D tensor map per level: x, y, frame; out-of-image
+// bytes arrive as zeros, so there is no address or bounds logic in the kernel) into the shared memory that later holds the score
+// tile, and is widened from there. The tile origin is a multiple of 16 bytes in x, as the TMA engine requires of the innermost
+// coordinate (measured on B200: any other start raises an illegal-instruction fault, tools/tma_probe2.cu).
 struct FastMaps { CUtensorMap m[kMaxLevels]; };
-constexpr int kFastRawW = kFastPW + 16;
-constexpr int kFastRawBytes = kFastPH * kFastRawW;
-constexpr size_t kFastTmaSmemBytes = 2 * (size_t)kFastRawBytes + kFastSmemBytes;
+constexpr int kFastRawBytes = kFastPH * kFastPW;
+static_assert(kFastRawBytes <= kFastSH * kFastScP * 4, "the raw tile is landed in the score tile's shared memory");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(void* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -440,65 +546,44 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
                  "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
 }
 
+template <int NP, int NX, int NQ>
 __global__ void __launch_bounds__(256) k_fast_tma(const __grid_constant__ OrbGeom g, const OrbBuffers b, const __grid_constant__ FastMaps maps,
-                                                  int tiles_per_frame, int total)
+                                                  const FastTile* __restrict__ tiles)
 {
     extern __shared__ __align__(128) uint8_t fast_smem[];
-    uint8_t* raw = fast_smem;                                                   // [2][kFastPH][kFastPW] bytes, written by the TMA engine
-    uint16_t* A = reinterpret_cast<uint16_t*>(fast_smem + 2 * kFastRawBytes);
-    uint16_t* As = A + kFastPH * kFastP16;
-    uint32_t* sc = reinterpret_cast<uint32_t*>(As + kFastPH * kFastP16);
-    __shared__ __align__(8) unsigned long long bar[2];
+    uint16_t* A = reinterpret_cast<uint16_t*>(fast_smem);
+    uint32_t* sc = reinterpret_cast<uint32_t*>(A + 2 * kFastAsOff);
+    uint8_t* raw = reinterpret_cast<uint8_t*>(sc);                              // [kFastPH][kFastPW] bytes, written by the TMA engine
+    __shared__ __align__(8) unsigned long long bar;
     __shared__ int s_n, s_base;
+    __shared__ uint16_t queue[8 * 64];
+    const int f = blockIdx.y;
+    const FastTile T = fast_tile_load(tiles, blockIdx.x);
+    const int l = T.l, px0 = T.px0, py0 = T.py0;
+    const LevelGeom& L = g.lv[l];
     if (threadIdx.x == 0) {
-        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&bar, kFastRawBytes);
+        tma_load_3d(raw, &maps.m[l], px0, py0, f, &bar);
     }
-    __syncthreads();
-    auto locate = [&](int item, int& f, int& l, int& px0, int& py0) {
-        f = item / tiles_per_frame;
-        const int tile = item - f * tiles_per_frame;
-        l = 0;
-        while (l + 1 < g.nlevels && tile >= g.lv[l + 1].fast_tile_base) l++;
-        const int t = tile - g.lv[l].fast_tile_base;
-        px0 = kFastOW * (t % g.lv[l].fast_tiles_x) - 4; py0 = kFastOH * (t / g.lv[l].fast_tiles_x) - 4;
-    };
-    auto fetch = [&](int item, int buf) {                                       // thread 0 only
-        int f, l, px0, py0;
-        locate(item, f, l, px0, py0);
-        mbar_expect_tx(&bar[buf], kFastRawBytes);
-        tma_load_3d(raw + buf * kFastRawBytes, &maps.m[l], px0 - ((px0 + 16) & 15), py0, f, &bar[buf]);
-    };
-    int item = blockIdx.x;
-    if (item < total && threadIdx.x == 0) fetch(item, 0);
-    for (int it = 0; item < total; item += gridDim.x, it++) {
-        const int buf = it & 1;
-        int f, l, px0, py0;
-        locate(item, f, l, px0, py0);
-        mbar_wait(&bar[buf], (uint32_t)(it >> 1) & 1u);
-        // widen the landed bytes to u16 twice (A[y][x], As[y][x] = A[y][x+1]), as k_fast does from registers
-        const uint8_t* rw = raw + buf * kFastRawBytes + ((px0 + 16) & 15);          // first byte of the tile inside the wider box (4-byte aligned)
-        constexpr int kStageIters = kFastPH * (kFastPW / 4) / 256;
+    const int g_lo = T.g_lo, g_hi = T.g_hi, sy_lo = T.sy_lo;
+    const int n_rows = T.nrows > 0 && T.npx > 0 ? T.nrows + 6 : 0;
+    __syncthreads();                                   // the barrier is initialised before anyone polls it
+    mbar_wait(&bar, 0u);
+    constexpr int kStageIters = (kFastPH * 8 + 255) / 256;
 #pragma unroll
-        for (int k = 0; k < kStageIters; k++) {
-            const int i = k * 256 + threadIdx.x;
-            const int ry = i / (kFastPW / 4), rx = (i % (kFastPW / 4)) * 4;
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(rw + ry * kFastRawW + rx);
-            const uint32_t p01 = __byte_perm(v, 0, 0x4140), p23 = __byte_perm(v, 0, 0x4342), p12 = __byte_perm(v, 0, 0x4241);
-            uint16_t* a = A + ry * kFastP16 + rx;
-            uint16_t* as = As + ry * kFastP16 + rx;
-            *reinterpret_cast<uint32_t*>(a) = p01;
-            *reinterpret_cast<uint32_t*>(a + 2) = p23;
-            if (rx > 0) as[-1] = (uint16_t)(v & 0xff);
-            *reinterpret_cast<uint32_t*>(as) = p12;
-            as[2] = (uint16_t)(v >> 24);
-        }
-        __syncthreads();                           // A / As complete; raw[buf] and (since the last iteration) raw[1 - buf] are free
-        const int next = item + gridDim.x;
-        if (next < total && threadIdx.x == 0) fetch(next, 1 - buf);
-        fast_tile_compute(g, b, g.lv[l], f, l, px0, py0, A, As, sc, s_n, s_base);
-        __syncthreads();                           // the tile buffers (A doubles as the survivor list) are reused by the next item
+    for (int it = 0; it < kStageIters; it++) {
+        const int i = it * 256 + threadIdx.x, ry = i >> 3, grp = i & 7;
+        const bool on = ry < n_rows && grp >= g_lo && grp <= g_hi;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (on) v = *reinterpret_cast<const uint4*>(raw + (sy_lo + ry) * kFastPW + 16 * grp);
+        const uint32_t nxt = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (on) fast_widen16(v, nxt, A + (sy_lo + ry) * kFastP16 + 16 * grp);
     }
+    __syncthreads();                                   // the raw bytes are consumed: their memory becomes the score tile
+    fast_zero_scores(sc);
+    fast_tile_compute<NP, NX, NQ>(g, b, L, f, T, A, sc, queue, s_n, s_base);
 }
 
 // ------------------------------------------------------------------------------------------------ K3: selection
@@ -1249,11 +1334,20 @@ struct mage_orb_s {
     std::vector<ChainGraph> graphs;
     bool graphs_off = false;
     int sm_count = 0;
+    int fast_variant = 0;
+    const FastTile* d_fast_tiles = nullptr;      // per-frame tile table of k_fast (in the arena)
     void* encode_fn = nullptr;
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
 };
 
 namespace {
+
+typedef void (*FastKernel)(const OrbGeom, const OrbBuffers, const FastTile*);
+typedef void (*FastTmaKernel)(const OrbGeom, const OrbBuffers, const FastMaps, const FastTile*);
+struct FastVariant { FastKernel k; FastTmaKernel kt; };
+#define MAGE_FV(np, nx, nq) {k_fast<np, nx, nq>, k_fast_tma<np, nx, nq>}
+const FastVariant kFastVariants[] = {MAGE_FV(8, 8, 0), MAGE_FV(0, 0, 0), MAGE_FV(4, 4, 0), MAGE_FV(6, 6, 0), MAGE_FV(8, 8, 4), MAGE_FV(8, 8, 8), MAGE_FV(8, 4, 0), MAGE_FV(4, 8, 0)};
+#undef MAGE_FV
 
 inline int cvRoundF(float v) { return (int)lrintf(v); }
 inline int cvFloorF(float v) { int i = (int)v; return i - (i > v); }
@@ -1317,13 +1411,49 @@ bool encode_level_map(void* fn, CUtensorMap* out, const void* base, int w, int h
     if (!fn || ((uintptr_t)base & 15) || (pitch & 15) || (fstride & 15)) return false;
     const cuuint64_t dim[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)frames};
     const cuuint64_t stride[2] = {(cuuint64_t)pitch, (cuuint64_t)fstride};
-    const cuuint32_t box[3] = {(cuuint32_t)kFastRawW, (cuuint32_t)kFastPH, 1u};
+    const cuuint32_t box[3] = {(cuuint32_t)kFastPW, (cuuint32_t)kFastPH, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     return reinterpret_cast<EncodeTiledFn>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dim, stride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int select_smem_bytes() { return kSelSmemItems * (8 + 4 + 4 + 1); }
+
+// The tile table of k_fast: for every tile of every level (in launch order) its origin, the part of it that is scored -- the
+// border-inset rectangle dilated by one pixel and clipped to FAST's domain 3 <= x <= w - 4, in pair granularity -- and the key-point
+// rows / columns it may emit (ref :619-639 RunByImageBorder).
+std::vector<FastTile> fast_tile_table(const OrbGeom& g)
+{
+    std::vector<FastTile> out;
+    const int bd = g.border;
+    for (int l = 0; l < g.nlevels; l++) {
+        const LevelGeom& L = g.lv[l];
+        for (int ty = 0; ty < L.fast_tiles_y; ty++)
+            for (int tx = 0; tx < L.fast_tiles_x; tx++) {
+                FastTile t;
+                memset(&t, 0, sizeof(t));
+                const int px0 = L.fast_x0 + kFastTW * tx, py0 = L.fast_y0 + kFastTH * ty;
+                const int vx_lo = std::max(3, bd - 1), vx_hi = std::min(L.w - 4, L.w - bd), vy_lo = std::max(3, bd - 1), vy_hi = std::min(L.h - 4, L.h - bd);
+                const int sx_lo = std::max(0, vx_lo - (px0 + 3)), sx_hi = std::min(kFastSW - 1, vx_hi - (px0 + 3));
+                const int sy_lo = std::max(0, vy_lo - (py0 + 3)), sy_hi = std::min(kFastSH - 1, vy_hi - (py0 + 3));
+                int sp_lo = sx_lo >> 1, npx = sx_hi >= sx_lo ? (sx_hi >> 1) - sp_lo + 1 : 0, nrows = std::max(sy_hi - sy_lo + 1, 0);
+                if (npx <= 0 || nrows <= 0) { npx = 0; nrows = 0; sp_lo = 0; }
+                t.l = (short)l; t.px0 = (short)px0; t.py0 = (short)py0;
+                t.xlo = (short)std::max(bd, px0 + 4); t.xhi = (short)std::min(L.w - bd, px0 + 4 + kFastTW);
+                t.oy_lo = (signed char)std::max(0, bd - (py0 + 4)); t.oy_hi = (signed char)std::min(kFastTH - 1, L.h - bd - 1 - (py0 + 4));
+                t.sp_lo = (unsigned char)sp_lo; t.npx = (unsigned char)npx; t.sy_lo = (unsigned char)(nrows ? sy_lo : 0); t.nrows = (unsigned char)nrows;
+                if (npx > 0) {
+                    t.dsy = (unsigned char)(256 / npx); t.dsp = (unsigned char)(256 % npx);
+                    t.g_lo = (unsigned char)((2 * sp_lo) >> 4); t.g_hi = (unsigned char)((2 * (sp_lo + npx - 1) + 7) >> 4);
+                    t.inv_npx = (unsigned int)((0x100000000ull + (unsigned)npx - 1) / (unsigned)npx);
+                    for (unsigned q = 0; q < 256; q++)                                   // the reciprocal is exact over the range it is used on
+                        if ((unsigned)(((unsigned long long)q * t.inv_npx) >> 32) != q / (unsigned)npx) { t.inv_npx = 0; break; }
+                }
+                out.push_back(t);
+            }
+    }
+    return out;
+}
 
 } // namespace
 
@@ -1399,7 +1529,13 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
         L.key_cap = kc; L.key_off = (unsigned)key; key += kc;
         L.sel_off = (unsigned)sel; sel += align_up((size_t)std::max(L.nfeat, 1), 32);
         L.tab_x = (unsigned)tab; tab += L.w; L.tab_y = (unsigned)tab; tab += L.h;
-        L.fast_tiles_x = div_up(L.w, kFastOW); L.fast_tiles_y = div_up(L.h, kFastOH); L.fast_tile_base = ftiles;
+        // key points live in [border, w - border) x [border, h - border) (ref :619-639, :706-711); the first tile's 4-pixel apron
+        // starts at border - 4 rounded down to a multiple of 16 bytes (vector loads / the TMA engine's innermost coordinate)
+        L.fast_x0 = (int)(((g.border - 4 + 1024) & ~15) - 1024); L.fast_y0 = g.border - 4;
+        const bool has_kp = L.w > 2 * g.border && L.h > 2 * g.border;
+        L.fast_tiles_x = has_kp ? div_up(L.w - g.border - (L.fast_x0 + 4), kFastTW) : 0;
+        L.fast_tiles_y = has_kp ? div_up(L.h - 2 * g.border, kFastTH) : 0;
+        L.fast_tile_base = ftiles;
         ftiles += L.fast_tiles_x * L.fast_tiles_y;
         L.blur_tiles_x = div_up(L.w, kBlurOW); L.blur_tiles_y = div_up(L.h, g.ksize == 7 ? 8 * kBlur7Rows : kBlurOH); L.blur_tile_base = btiles;
         btiles += L.blur_tiles_x * L.blur_tiles_y;
@@ -1416,6 +1552,7 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     size_t o_sel = A.reserve(sel * 4 * B);
     size_t o_cnt = A.reserve(sizeof(int) * kMaxLevels * B * 2 + sizeof(int) * B);     // cand_count, sel_count, status
     size_t o_pat = A.reserve(30 * 1024);
+    size_t o_ftiles = A.reserve(sizeof(FastTile) * (size_t)std::max(ftiles, 1));
     int sum_nl = 0;
     for (int l = 0; l < g.nlevels; l++) sum_nl += g.lv[l].nfeat;
     const int cap = std::max((int)p->nfeatures, sum_nl);
@@ -1436,6 +1573,7 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     b.sel = A.at<uint32_t>(o_sel); b.sel_stride = sel;
     b.cand_count = A.at<int>(o_cnt); b.sel_count = b.cand_count + kMaxLevels * B; b.status = b.sel_count + kMaxLevels * B;
     b.pattern = A.at<int8_t>(o_pat);
+    h->d_fast_tiles = A.at<FastTile>(o_ftiles);
 
     // tables
     std::vector<int> tofs(tab); std::vector<short2> tcoef(tab);
@@ -1468,8 +1606,17 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     cudaError_t e = cudaMemcpy((void*)b.tab_ofs, tofs.data(), tab * sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((void*)b.tab_coef, tcoef.data(), tab * sizeof(short2), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy((void*)b.pattern, pat.data(), pat.size(), cudaMemcpyHostToDevice);
+    {
+        const std::vector<FastTile> ft = fast_tile_table(g);
+        if (e == cudaSuccess && !ft.empty()) e = cudaMemcpy((void*)h->d_fast_tiles, ft.data(), ft.size() * sizeof(FastTile), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes());
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes);
+    {   // which share of the min/max network runs on the FMA pipe: tuning switch, every variant is bit-identical
+        const char* env = getenv("MAGE_FAST_VARIANT");
+        const int v = env ? atoi(env) : 0;
+        h->fast_variant = v >= 0 && v < (int)(sizeof(kFastVariants) / sizeof(kFastVariants[0])) ? v : 0;
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)kFastVariants[h->fast_variant].k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming);
@@ -1486,7 +1633,7 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
         if (env && atoi(env) != 0 && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess && fn) {
             h->encode_fn = fn;
-            bool ok = cudaFuncSetAttribute(k_fast_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastTmaSmemBytes) == cudaSuccess;
+            bool ok = cudaFuncSetAttribute((const void*)kFastVariants[h->fast_variant].kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes) == cudaSuccess;
             for (int l = 0; l < g.nlevels && ok; l++)
                 ok = encode_level_map(fn, &h->maps.m[l], b.pyr + g.lv[l].pyr_off, g.lv[l].w, g.lv[l].h, max_batch, (size_t)g.lv[l].pitch, pyr);
             h->tma_ok = ok;
@@ -1585,11 +1732,10 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
         else if (tma && h->maps_lvl0_foreign)
             tma = encode_level_map(h->encode_fn, &h->maps.m[0], h->b.pyr + g.lv[0].pyr_off, g.lv[0].w, g.lv[0].h, h->max_batch, (size_t)g.lv[0].pitch, h->b.slab);
         h->maps_lvl0_foreign = bufs.lvl0 != h->b.lvl0;
-        if (tma) {
-            const int total = h->fast_tiles * n;
-            k_fast_tma<<<std::min(total, 3 * std::max(h->sm_count, 1)), 256, kFastTmaSmemBytes, s>>>(g, bufs, h->maps, h->fast_tiles, total);
-        } else
-            k_fast<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs);
+        if (h->fast_tiles > 0) {         // no tile: every level is narrower than twice the border, nothing can be a key point
+            if (tma) kFastVariants[h->fast_variant].kt<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs, h->maps, h->d_fast_tiles);
+            else kFastVariants[h->fast_variant].k<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs, h->d_fast_tiles);
+        }
     }
     { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }
     if (fork) MAGE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_blur, 0));

@@ -284,3 +284,40 @@ def local_map_scene(n=4000, seed=0, width=640, height=480, scale=1.2, levels=8):
     pts["dmin"] = dmin.astype(np.float32); pts["dmax"] = dmax.astype(np.float32)
     return dict(view=view, K=K, position=C.astype(np.float32), forward=forward, points=pts, width=width, height=height,
                 scale=scale, levels=levels)
+
+
+def natural_frames(n, w=640, h=480, seed=0, noise_sigma=1.5):
+    """n frames with the statistics of an indoor camera image rather than of a corner-dense test chart: the structured scene's
+    shapes on a smooth gradient (piecewise-constant regions, so corners sit on object outlines), a 1/f ("pink") texture of a few
+    grey levels and independent sensor noise of `noise_sigma` grey levels per frame, seen through the same homography trajectory
+    as video_frames. About 2 % of the pixels pass FAST at threshold 10 (video_frames: about a quarter) and the tier configuration still finds its 2000 key points."""
+    rng = np.random.default_rng(seed + 7000)
+    sw, sh = 2 * w, 2 * h
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    img = 70.0 + 70.0 * xx / sw + 40.0 * yy / sh
+    for _ in range(200):
+        val = float(rng.integers(15, 241))
+        if rng.random() < 0.65:
+            x0 = int(rng.integers(0, sw - 30)); y0 = int(rng.integers(0, sh - 30))
+            img[y0:y0 + int(rng.integers(25, 260)), x0:x0 + int(rng.integers(25, 260))] = val
+        else:
+            cx = int(rng.integers(0, sw)); cy = int(rng.integers(0, sh)); rad = int(rng.integers(12, 110))
+            y0, y1 = max(0, cy - rad), min(sh, cy + rad + 1); x0, x1 = max(0, cx - rad), min(sw, cx + rad + 1)
+            sub = img[y0:y1, x0:x1]
+            sub[(yy[y0:y1, x0:x1] - cy) ** 2 + (xx[y0:y1, x0:x1] - cx) ** 2 <= rad * rad] = val
+    fy = np.fft.fftfreq(sh)[:, None]; fx = np.fft.rfftfreq(sw)[None, :]
+    amp = 1.0 / np.maximum(np.hypot(fx, fy), 1.0 / max(sw, sh))
+    tex = np.fft.irfft2(amp * np.exp(2j * np.pi * rng.random(amp.shape)), s=(sh, sw))
+    img += 12.0 * (tex - tex.mean()) / (tex.std() + 1e-9)
+    img = _sep_filter(img, _gauss_kernel(0.8))                       # lens blur: edges are a couple of pixels wide
+    scene = np.clip(np.round(img), 0, 255).astype(np.uint8)
+    ph = rng.random(6) * 2 * np.pi
+    out = np.empty((n, h, w), np.uint8)
+    for t in range(n):
+        a = 0.08 * np.sin(0.021 * t + ph[0]); s = 1.0 + 0.15 * np.sin(0.013 * t + ph[1])
+        tx = 0.5 * w + 0.35 * w * np.sin(0.017 * t + ph[2]); ty = 0.5 * h + 0.35 * h * np.sin(0.011 * t + ph[3])
+        p0 = 1e-5 * np.sin(0.009 * t + ph[4]); p1 = 1e-5 * np.sin(0.007 * t + ph[5])
+        c, sn = np.cos(a) * s, np.sin(a) * s
+        f = _warp(scene, np.array([[c, -sn, tx], [sn, c, ty], [p0, p1, 1.0]]), w, h).astype(np.float64)
+        out[t] = np.clip(np.round(f + noise_sigma * rng.standard_normal((h, w))), 0, 255).astype(np.uint8)
+    return out

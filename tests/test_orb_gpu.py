@@ -360,3 +360,79 @@ def test_retain_best_keeps_fewer_than_the_budget():
         ok, od = orc.detect_and_compute(p, img, 1)
         assert 0 < len(ok) < 800
         assert_same_features(gk, gd, ok, od, "strength %.1f factor %.1f" % (strength, factor))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# k_fast internals (round 2): border-inset tile grid, sparse / dense scoring modes, the half-precision share of the min/max network.
+@pytest.mark.parametrize("thr", [10, 25])
+def test_fast_sparse_mode_on_camera_like_frames(thr):
+    """a frame with camera statistics (about 2 % corners): most pairs fail the high-speed test, so the warps run in sparse mode
+    (queued survivors); candidates per level and the final features equal the oracle"""
+    img = synth.natural_frames(2, 640, 480, seed=3)[1]
+    p = orc.tier_params(fast_threshold=thr)
+    det = make_detector(p)
+    gk, gd = det.DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert len(ok) > 200
+    assert_same_features(gk, gd, ok, od, "natural thr %d" % thr)
+    ref_levels = orc.build_pyramid(p, img)
+    for l in range(p.nlevels):
+        h, w = ref_levels[l].shape
+        k = orc.fast9(ref_levels[l], thr)
+        k = k[(k["x"] >= 22) & (k["x"] < w - 22) & (k["y"] >= 22) & (k["y"] < h - 22)]
+        ref = (k["response"].astype(np.uint32) << 24) | (k["y"].astype(np.uint32) * w + k["x"].astype(np.uint32))
+        assert np.array_equal(det.DebugCandidates(0, l), ref), "level %d candidates differ" % l
+
+
+def test_fast_mixed_density_frame():
+    """left half corner-dense chart, right half flat with a few shapes: warps switch between the two modes inside a tile row"""
+    a = synth.video_frames(1, 640, 480, seed=4)[0]
+    b = synth.natural_frames(1, 640, 480, seed=5)[0]
+    img = np.where(np.arange(640)[None, :] < 300, a, b).astype(np.uint8)
+    img[200:280, :] = 128                                   # a flat band: no pair passes the test
+    p = orc.tier_params()
+    gk, gd = make_detector(p).DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert_same_features(gk, gd, ok, od, "mixed density")
+
+
+@pytest.mark.parametrize("patch,orient", [(2, False), (4, False), (6, True), (8, False), (9, False)])
+def test_fast_small_borders(patch, orient):
+    """borders of 1 .. 4 pixels: the scored rectangle reaches the columns / rows FAST is not defined on (x < 3, x > w - 4) and the
+    first tile starts left of the image"""
+    img = synth.video_frames(1, 200, 150, seed=21)[0]
+    p = orc.tier_params(nfeatures=400, nlevels=2)
+    p.patch_size, p.use_orientation = patch, orient
+    gk, gd = make_detector(p).DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert len(ok) > 50
+    assert_same_features(gk, gd, ok, od, "patch %d" % patch)
+
+
+def test_fast_levels_narrower_than_the_border():
+    """upper pyramid levels not wider than twice the border hold no key point (ref :706-707) and get no tile"""
+    img = synth.video_frames(1, 96, 80, seed=22)[0]
+    p = orc.tier_params(nfeatures=300, nlevels=6, scale_factor=1.3)
+    gk, gd = make_detector(p).DetectAndCompute(img)
+    ok, od = orc.detect_and_compute(p, img, 1)
+    assert len(ok) > 0
+    assert_same_features(gk, gd, ok, od, "narrow levels")
+
+
+@pytest.mark.parametrize("tma", [0, 1])
+def test_fast_every_network_split_is_identical(frames, monkeypatch, tma):
+    """MAGE_FAST_VARIANT moves part of the min/max network from packed-integer (ALU pipe) to half2 (FMA pipe) instructions: same bits"""
+    monkeypatch.setenv("MAGE_FAST_TMA", str(tma))
+    p = orc.tier_params()
+    imgs = np.ascontiguousarray(np.stack([frames["video"][1], synth.natural_frames(1, 640, 480, seed=9)[0]]))
+    want = None
+    for v in range(8):
+        monkeypatch.setenv("MAGE_FAST_VARIANT", str(v))
+        det = make_detector(p, max_batch=2)
+        kps, desc, counts = det.DetectAndComputeBatch(imgs)
+        got = (kps.tobytes(), desc.tobytes(), counts.tobytes(), [det.DebugCandidates(f, l).tobytes() for f in range(2) for l in range(p.nlevels)])
+        if want is None:
+            want = got
+            ok, od = orc.detect_and_compute(p, imgs[1], 1)
+            assert_same_features(kps[1, :int(counts[1])], desc[1, :int(counts[1])], ok, od, "variant 0")
+        assert got == want, "variant %d differs" % v
