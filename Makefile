@@ -8,7 +8,7 @@ LIB := mageslam_b200/libmage_b200.so
 
 all: $(LIB)
 
-$(SRC)/%.o: $(SRC)/%.cu $(SRC)/common.cuh include/mage_b200.h
+$(SRC)/%.o: $(SRC)/%.cu $(SRC)/common.cuh $(SRC)/dense_ldlt.cuh include/mage_b200.h
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
 
 $(LIB): $(OBJS)

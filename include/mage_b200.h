@@ -334,6 +334,12 @@ int  mage_ba_get_state_f64(mage_ba_t h, double* cam_qxyzw_t /*K*7*/, double* poi
 int  mage_ba_get_stats(mage_ba_t h, int64_t stats[4]);
 /* diagnostics: accumulated nanoseconds per phase of the cooperative kernel as seen by block 0 */
 int  mage_ba_debug_phase_ns(mage_ba_t h, long long phase_ns[16]);
+/* The dense solver of the reduced camera system on its own (test entry; replaces Eigen::LDLT of ref
+ * Dependencies/g2o/g2o/solvers/dense/linear_solver_dense.h:65-113): A is n x n row-major symmetric positive definite (lower triangle
+ * read), b the right-hand side; x receives the solution, factor (nullable, n x n) L below the diagonal and D on it, *positive 0 when a
+ * pivot was not positive, phase_ns (nullable) the time of the diagonal blocks / panel rows / tensor-core update / grid barriers /
+ * backward substitution as CTA 0 sees them, then finer splits (dense_ldlt.cuh). */
+int  mage_dense_debug_solve(int n, const double* A, const double* b, double* x, double* factor, int* positive, long long phase_ns[16]);
 /* Many independent problems stepped concurrently (one CTA group per problem): same result per handle as calling
  * mage_ba_step on each. means/outlier outputs are per handle. */
 int  mage_ba_step_many(mage_ba_t* handles, int n_handles, const float* huber_width_per_iteration, int n_iterations,

@@ -65,6 +65,7 @@ def lib():
     L.mage_orb_detect_and_compute_batch.argtypes = [vp, vp, ci, ci, ci, ci, sz, vp, vp, ci, vp, vp]
     L.mage_orb_extract_device.argtypes = [vp, vp, ci, ci, ci, ci, sz, vp, vp, ci, vp, vp]
     L.mage_orb_level_info.argtypes = [vp, vp, vp, vp, vp]
+    L.mage_dense_debug_solve.argtypes = [ci, vp, vp, vp, vp, vp, vp]
     L.mage_orb_set_blur_mode.argtypes = [vp, ci]
     L.mage_orb_debug_get_level.argtypes = [vp, ci, ci, ci, vp]
     L.mage_orb_debug_get_candidates.argtypes = [vp, ci, ci, vp, ci, C.POINTER(ci)]

@@ -9,6 +9,7 @@
 // Many independent problems are stepped by one launch (grid = problems). All reductions use a fixed order
 // (no floating-point atomics), so a run is bit-reproducible.
 #include "common.cuh"
+#include "dense_ldlt.cuh"
 
 #include <cooperative_groups.h>
 
@@ -28,7 +29,7 @@ struct BaCtl {
     int iteration, inlier_count, stop_flag, last_ok;
     int n_flagged, pad_;
     long long lm_iters, lm_trials;
-    long long phase_ns[16];     // cooperative kernel: time per phase seen by block 0 (diagnostics)
+    long long phase_ns[32];     // cooperative kernel: time per phase seen by block 0 (diagnostics; 9.. = the dense solver's)
 };
 
 struct BaDev {
@@ -53,7 +54,9 @@ struct BaDev {
     int schur_parts;
     // large reduced systems (global BA): S stays in global memory and is factorised by the whole grid
     int big;
-    double* Wk;                               // [n][kLdltNB] panel workspace (L_ik * D_k)
+    int8_t* Zq;                               // int8 slice planes of the current panel (dense_ldlt.cuh)
+    double* Ldiag;                            // factored diagonal blocks of the reduced system (dense_ldlt.cuh)
+    int* Ez;                                  // row exponents of the slices
     // tether edges between two cameras (ref BundlerLib.cpp:24-90, :311-350), single-CTA kernel only
     int nT;
     const int4* t_def;                        // [nT] (type, cam1, cam2, error dimension)
@@ -1648,10 +1651,7 @@ constexpr int kBaThreads = 256;
 // Hessian index) live in dynamic shared memory whenever they fit -- the dense LDL^T and every per-edge camera lookup then run
 // at shared-memory latency instead of L2 latency. Global memory stays the source of truth across launches.
 constexpr int kBaMaxSmemCams = 1024;
-constexpr int kLdltNB = 32;                 // panel width of the grid-wide blocked LDL^T
-constexpr int kLdltTile = 64;               // trailing-update tile
-constexpr int kLdltTP = kLdltTile + 2;         // row pitch of the transposed tiles: even (16-byte rows), not a multiple of 32 words
-constexpr size_t kBigScratchBytes = sizeof(double) * (2 * kLdltNB * kLdltTP + kLdltNB * kLdltNB + 64);
+constexpr size_t kCoopSmemMax = 220 * 1024;        // dynamic shared memory of the cooperative kernel (one CTA per SM)
 
 __host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) * ((size_t)n * n + n); }
 __host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
@@ -2071,220 +2071,6 @@ __device__ void phase_assemble_big(const BaDev& p, double lambda, int gtid, int 
     }
 }
 
-// Grid-wide right-looking blocked LDL^T without pivoting (the damped reduced system is SPD; a negative pivot => "not positive",
-// ref linear_solver_dense.h:104-112). In place: strict lower part <- L, diagonal <- D. Three grid barriers per panel:
-//   (a) block 0 factors the nb x nb diagonal block in shared memory,
-//   (b) every thread solves one row of the panel:  Y = A_ik L_kk^-T,  L_ik = Y D_k^-1   (Y kept in Wk for the update),
-//   (c) 64 x 64 tiles of the trailing matrix:  A_ij -= Y_i L_j^T  (lower tiles only), one tile per CTA pass.
-__device__ bool grid_ldlt_big(cg::grid_group& grid, const BaDev& p, double* scratch, int* okflag)
-{
-    const int n = p.n, tid = threadIdx.x, nt = blockDim.x;
-    long long t_mark = gtimer();
-    // diagnostics: block 0 accumulates the time of (a) diagonal block, (b) panel rows, (c) trailing update, and of the three barriers
-    auto lap = [&](int slot) { if (blockIdx.x == 0 && tid == 0) { const long long t = gtimer(); p.ctl->phase_ns[slot] += t - t_mark; t_mark = t; } };
-    const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt;
-    double* S = p.S;
-    double* Ys = scratch;                                   // [kLdltNB][kLdltTP]: panel columns of the tile's rows, k-major (transposed)
-    double* Ls = Ys + kLdltNB * kLdltTP;                    // [kLdltNB][kLdltTP]: the same for the tile's columns
-    double* Dk = Ls + kLdltNB * kLdltTP;                    // [kLdltNB][kLdltNB] diagonal block (L below the diagonal, D on it)
-    __shared__ int s_bad;
-    __shared__ double s_col[2 * (kLdltNB + 1)];
-    if (tid == 0) s_bad = 0;
-    for (int k0 = 0; k0 < n; k0 += kLdltNB) {
-        const int nb = min(kLdltNB, n - k0);
-        // (a)
-        if (blockIdx.x == 0) {
-            for (int i = tid; i < nb * nb; i += nt) Dk[i] = S[(size_t)(k0 + i / nb) * n + k0 + i % nb];
-            __syncthreads();
-            ldlt_factor_regs<2>(Dk, nb, &s_bad, s_col);         // 2 x 2 register blocks, one barrier per column (nb <= 32, 256 threads)
-            __syncthreads();
-            for (int i = tid; i < nb * nb; i += nt) if (i % nb <= i / nb) S[(size_t)(k0 + i / nb) * n + k0 + i % nb] = Dk[i];
-            if (tid == 0 && s_bad) *okflag = 0;
-        }
-        lap(9);
-        grid.sync();
-        lap(12);
-        const int r0 = k0 + nb;                              // first row below the panel
-        if (r0 >= n) break;
-        // (b) every block keeps a copy of the factored diagonal block
-        for (int i = tid; i < nb * nb; i += nt) Dk[i] = S[(size_t)(k0 + i / nb) * n + k0 + i % nb];
-        __syncthreads();
-        {   // one warp per panel row: lane j owns Y_j = A(row, k0 + j); the solved entries are broadcast by shuffle
-            const int lane = tid & 31, gw = gtid >> 5, gnw = gnt >> 5;
-            for (int row = r0 + gw; row < n; row += gnw) {
-                double* a = S + (size_t)row * n + k0;
-                double yv = lane < nb ? a[lane] : 0.0;
-                for (int c = 0; c < nb; c++) {
-                    const double yc = __shfl_sync(0xffffffffu, yv, c);
-                    if (lane > c && lane < nb) yv -= yc * Dk[lane * nb + c];
-                }
-                double* w = p.Wk + (size_t)row * kLdltNB;
-                if (lane < nb) {
-                    const double d = Dk[lane * nb + lane];
-                    w[lane] = yv;
-                    a[lane] = (fabs(d) > 0) ? yv / d : 0.0;
-                } else w[lane] = 0.0;
-            }
-        }
-        lap(10);
-        grid.sync();
-        lap(12);
-        // (c)
-        const int T = (n - r0 + kLdltTile - 1) / kLdltTile, ntiles = T * (T + 1) / 2;
-        const int ty = tid >> 4, tx = tid & 15;              // 16 x 16 threads, 4 x 4 outputs each
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            int ti = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
-            while ((ti + 1) * (ti + 2) / 2 <= tile) ti++;
-            while (ti * (ti + 1) / 2 > tile) ti--;
-            const int tj = tile - ti * (ti + 1) / 2;
-            const int ri = r0 + ti * kLdltTile, rj = r0 + tj * kLdltTile;
-            __syncthreads();
-            {   // all 16 global loads of the thread in flight before the first shared store (the compiler cannot reorder them across
-                // the stores itself: the pointers may alias as far as it knows)
-                constexpr int kPer = kLdltTile * kLdltNB / kCoopThreads;
-                double yv[kPer], lv[kPer];
-#pragma unroll
-                for (int u = 0; u < kPer; u++) {
-                    const int i = tid + u * kCoopThreads, rr = i / kLdltNB, m = i % kLdltNB;
-                    yv[u] = (ri + rr < n) ? p.Wk[(size_t)(ri + rr) * kLdltNB + m] : 0.0;
-                    lv[u] = (rj + rr < n && m < nb) ? S[(size_t)(rj + rr) * n + k0 + m] : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < kPer; u++) {
-                    const int i = tid + u * kCoopThreads, rr = i / kLdltNB, m = i % kLdltNB;
-                    Ys[m * kLdltTP + rr] = yv[u];
-                    Ls[m * kLdltTP + rr] = lv[u];
-                }
-            }
-            __syncthreads();
-            double acc[4][4];
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) acc[a][b] = 0;
-#pragma unroll 4
-            for (int m = 0; m < kLdltNB; m++) {
-                // k-major tiles: a thread's four row / column operands are 32 contiguous bytes (two 16-byte loads, conflict-free across tx)
-                const double2 y01 = *reinterpret_cast<const double2*>(Ys + m * kLdltTP + ty * 4), y23 = *reinterpret_cast<const double2*>(Ys + m * kLdltTP + ty * 4 + 2);
-                const double2 l01 = *reinterpret_cast<const double2*>(Ls + m * kLdltTP + tx * 4), l23 = *reinterpret_cast<const double2*>(Ls + m * kLdltTP + tx * 4 + 2);
-                const double ya[4] = {y01.x, y01.y, y23.x, y23.y}, lb[4] = {l01.x, l01.y, l23.x, l23.y};
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int b = 0; b < 4; b++) acc[a][b] += ya[a] * lb[b];
-            }
-            double sv[4][4];                                  // read-modify-write of the 4 x 4 outputs: all loads first, then all stores
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int i = ri + ty * 4 + a, j = rj + tx * 4 + b;
-                    sv[a][b] = (i < n && j < n && j <= i) ? S[(size_t)i * n + j] : 0.0;
-                }
-#pragma unroll
-            for (int a = 0; a < 4; a++)
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int i = ri + ty * 4 + a, j = rj + tx * 4 + b;
-                    if (i < n && j < n && j <= i) S[(size_t)i * n + j] = sv[a][b] - acc[a][b];
-                }
-        }
-        lap(11);
-        grid.sync();
-        lap(12);
-    }
-    return true;
-}
-
-
-// Grid-wide version of the substitution: 128 unknowns per step. Block 0 solves the 128 x 128 triangle on the diagonal (four 32-wide
-// warp solves with in-CTA updates between them), then -- after a grid barrier -- every warp of the grid applies the solved block to
-// its share of the remaining rows (forward: one warp per row, lanes stride the 128 columns, coalesced) or columns (backward: one
-// thread per column). One SM could not stream the 70 MB factor twice in less than ~3 ms; the grid does it in under one.
-constexpr int kTriNB = 128;
-__device__ void tri_solve_big_grid(cg::grid_group& grid, const BaDev& p)
-{
-    const int n = p.n, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-    const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt, gw = gtid >> 5, gnw = gnt >> 5;
-    const double* __restrict__ S = p.S;
-    double* y = p.bs;
-    __shared__ double yb[32];
-    for (int k0 = 0; k0 < n; k0 += kTriNB) {
-        const int nb = min(kTriNB, n - k0);
-        if (blockIdx.x == 0) {
-            for (int s0 = 0; s0 < nb; s0 += 32) {
-                const int sb = min(32, nb - s0), q0 = k0 + s0;
-                if (tid < 32) {
-                    double yv = tid < sb ? y[q0 + tid] : 0.0;
-                    for (int c = 0; c < sb; c++) {
-                        const double yc = __shfl_sync(0xffffffffu, yv, c);
-                        if (tid > c && tid < sb) yv -= S[(size_t)(q0 + tid) * n + q0 + c] * yc;
-                    }
-                    if (tid < sb) { y[q0 + tid] = yv; yb[tid] = yv; }
-                }
-                __syncthreads();
-                for (int i = q0 + sb + tid; i < k0 + nb; i += nt) {              // the rest of this 128-block
-                    const double* row = S + (size_t)i * n + q0;
-                    double acc = 0;
-                    for (int j = 0; j < sb; j++) acc += row[j] * yb[j];
-                    y[i] -= acc;
-                }
-                __syncthreads();
-            }
-        }
-        __threadfence();
-        grid.sync();
-        for (int i = k0 + nb + gw; i < n; i += gnw) {                            // one warp per remaining row
-            const double* row = S + (size_t)i * n + k0;
-            double acc = 0;
-            for (int j = lane; j < nb; j += 32) acc += row[j] * y[k0 + j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-            if (lane == 0) y[i] -= acc;
-        }
-        __threadfence();
-        grid.sync();
-    }
-    const double tol = 1.0 / DBL_MAX;
-    for (int i = gtid; i < n; i += gnt) { const double d = S[(size_t)i * n + i]; y[i] = (fabs(d) > tol) ? y[i] / d : 0.0; }
-    __threadfence();
-    grid.sync();
-    for (int k0 = ((n - 1) / kTriNB) * kTriNB; k0 >= 0; k0 -= kTriNB) {
-        const int nb = min(kTriNB, n - k0);
-        if (blockIdx.x == 0) {
-            for (int s0 = ((nb - 1) / 32) * 32; s0 >= 0; s0 -= 32) {
-                const int sb = min(32, nb - s0), q0 = k0 + s0;
-                if (tid < 32) {
-                    double yv = tid < sb ? y[q0 + tid] : 0.0;
-                    for (int c = sb - 1; c >= 0; c--) {
-                        const double xc = __shfl_sync(0xffffffffu, yv, c);
-                        if (tid < c) yv -= S[(size_t)(q0 + c) * n + q0 + tid] * xc;
-                    }
-                    if (tid < sb) { y[q0 + tid] = yv; yb[tid] = yv; }
-                }
-                __syncthreads();
-                for (int i = k0 + tid; i < q0; i += nt) {                          // the earlier unknowns of this 128-block
-                    double acc = 0;
-                    for (int j = 0; j < sb; j++) acc += S[(size_t)(q0 + j) * n + i] * yb[j];
-                    y[i] -= acc;
-                }
-                __syncthreads();
-            }
-        }
-        __threadfence();
-        grid.sync();
-        for (int i = gtid; i < k0; i += gnt) {                                    // one thread per remaining column
-            double acc = 0;
-#pragma unroll 4
-            for (int j = 0; j < nb; j++) acc += S[(size_t)(k0 + j) * n + i] * y[k0 + j];
-            y[i] -= acc;
-        }
-        __threadfence();
-        grid.sync();
-    }
-    for (int i = gtid; i < n; i += gnt) p.x[i] = y[i];
-}
-
 __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __restrict__ prob, const float* __restrict__ huberW, int nIters, float maxErrSq,
                                                                 unsigned dynBytes)
 {
@@ -2296,25 +2082,30 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
     __shared__ int s_accept, s_stop;
     __shared__ BaDev s_p;
     __shared__ double *g_cam_q, *g_cam_t;
+    __shared__ int s_cam_global;                                // the camera state stayed in global memory: one copy for the whole grid
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
     const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt, gwarp = gtid >> 5, gnw = gnt >> 5;
     __shared__ double s_ldlt_col[2 * 97];
     if (tid == 0) {
         s_p = prob[0];
         s_p.ldlt_col = s_ldlt_col;
-        size_t cam_off = kBigScratchBytes;                      // big mode: S / bs stay in global memory, the head of dyn is LDL^T scratch
+        size_t cam_off = dense::kSmemBytes;                     // big mode: S / bs stay in global memory, the head of dyn belongs to the dense solver
         if (!s_p.big) { s_p.S = reinterpret_cast<double*>(dyn); s_p.bs = s_p.S + (size_t)s_p.n * s_p.n; cam_off = ba_smem_need_S(s_p.n); }
-        double* c = reinterpret_cast<double*>(dyn + cam_off);
         g_cam_q = s_p.cam_q; g_cam_t = s_p.cam_t;
-        const double *gf = s_p.cam_f, *gx = s_p.cam_cx, *gy = s_p.cam_cy; const int* gh = s_p.cam_h;
-        double* sq = c; double* st = c + 4 * s_p.K; double* sf = c + 7 * s_p.K; double* sx = c + 8 * s_p.K; double* sy = c + 9 * s_p.K;
-        int* shh = reinterpret_cast<int*>(c + 10 * s_p.K);
-        for (int k = 0; k < s_p.K; k++) {
-            for (int j = 0; j < 4; j++) sq[4 * k + j] = g_cam_q[4 * k + j];
-            for (int j = 0; j < 3; j++) st[3 * k + j] = g_cam_t[3 * k + j];
-            sf[k] = gf[k]; sx[k] = gx[k]; sy[k] = gy[k]; shh[k] = gh[k];
+        s_cam_global = 1;
+        if (dynBytes >= cam_off + ba_smem_need_cams(s_p.K)) {
+            s_cam_global = 0;   // the camera state is staged in shared memory when it fits beside the solver
+            double* c = reinterpret_cast<double*>(dyn + cam_off);
+            const double *gf = s_p.cam_f, *gx = s_p.cam_cx, *gy = s_p.cam_cy; const int* gh = s_p.cam_h;
+            double* sq = c; double* st = c + 4 * s_p.K; double* sf = c + 7 * s_p.K; double* sx = c + 8 * s_p.K; double* sy = c + 9 * s_p.K;
+            int* shh = reinterpret_cast<int*>(c + 10 * s_p.K);
+            for (int k = 0; k < s_p.K; k++) {
+                for (int j = 0; j < 4; j++) sq[4 * k + j] = g_cam_q[4 * k + j];
+                for (int j = 0; j < 3; j++) st[3 * k + j] = g_cam_t[3 * k + j];
+                sf[k] = gf[k]; sx[k] = gx[k]; sy[k] = gy[k]; shh[k] = gh[k];
+            }
+            s_p.cam_q = sq; s_p.cam_t = st; s_p.cam_f = sf; s_p.cam_cx = sx; s_p.cam_cy = sy; s_p.cam_h = shh;
         }
-        s_p.cam_q = sq; s_p.cam_t = st; s_p.cam_f = sf; s_p.cam_cx = sx; s_p.cam_cy = sy; s_p.cam_h = shh;
     }
     __syncthreads();
     const BaDev& p = s_p;
@@ -2323,7 +2114,6 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
     __syncthreads();
     int iteration = ctl->iteration, seq = 0;
     long long trials = 0, iters = 0;
-    (void)dynBytes;
     long long t_last = gtimer();
 
     // errors of this thread's edges + robust chi2 partial
@@ -2405,8 +2195,13 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
                 if (blockIdx.x == 0) { phase_finish_bs(p, tid, nt); if (tid == 0) ctl->last_ok = 1; }
                 grid.sync();
                 PH(8);
-                grid_ldlt_big(grid, p, reinterpret_cast<double*>(dyn), &ctl->last_ok);
-                if (*reinterpret_cast<volatile int*>(&ctl->last_ok)) tri_solve_big_grid(grid, p);      // uniform: written before the last grid barrier
+                const dense::Scratch dsc = {p.Zq, p.Ez, p.Ldiag, p.bs, ctl->phase_ns + 9};
+                dense::ldlt_grid(grid, p.S, p.n, dsc, dyn, &ctl->last_ok);           // factorisation + forward substitution of bs
+                grid.sync();
+                if (*reinterpret_cast<volatile int*>(&ctl->last_ok)) {                                  // uniform: written before the grid barrier
+                    dense::solve_back_grid(grid, p.S, p.n, dsc, dyn);
+                    for (int i = gtid; i < p.n; i += gnt) p.x[i] = p.bs[i];
+                }
             }
             PH(4);
             grid.sync();
@@ -2417,7 +2212,8 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
             // update: a landmark's increment was written by the same thread that applies it; cameras are replicated
             for (int li = gtid; li < p.Pl; li += gnt)
                 for (int r = 0; r < 3; r++) p.pt_X[3 * (size_t)p.l_pt[li] + r] += p.x[p.n + 3 * li + r];
-            for (int i = tid; i < p.Kf; i += nt) { const int c = p.c_cam[i]; pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i); }
+            if (s_cam_global) { for (int i = gtid; i < p.Kf; i += gnt) { const int c = p.c_cam[i]; pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i); } }
+            else for (int i = tid; i < p.Kf; i += nt) { const int c = p.c_cam[i]; pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i); }
             grid.sync();
             PH(6);
             red[0] = errors_chi2(delta);
@@ -2491,8 +2287,10 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
         }
         grid_sum<2>(grid, red, p, seq, sh, sh_out);
         if (blockIdx.x == 0) {
-            for (int i = tid; i < 4 * p.K; i += nt) g_cam_q[i] = p.cam_q[i];
-            for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
+            if (!s_cam_global) {
+                for (int i = tid; i < 4 * p.K; i += nt) g_cam_q[i] = p.cam_q[i];
+                for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
+            }
             if (tid == 0) {
                 ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
                 ctl->err_sum = red[0]; ctl->inlier_count = (int)red[1]; ctl->stop_flag = s_stop; ctl->n_flagged = p.Ea - (int)red[1];
@@ -2834,7 +2632,8 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_cdiag = rI(cam_diag.size()), o_bbptr = rI(bb_ptr.size()), o_bpairs = W.reserve(sizeof(ushort2) * std::max<size_t>(bpairs.size(), 1));
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
-    size_t o_Wk = rD(big ? (size_t)n * kLdltNB : 1);
+    size_t o_Zq = W.reserve(big ? dense::scratch_zq_bytes(n) : 16, 1024), o_Ez = rI(big ? dense::scratch_ez_count(n) : 1);
+    size_t o_Ldiag = W.reserve(big ? dense::scratch_ldiag_bytes(n) : 16, 256);
     size_t o_tdef = W.reserve(sizeof(int4) * std::max(nT, 1)), o_tmeas = rD(8 * (size_t)nT), o_terr = rD(6 * (size_t)nT), o_tJ = rD(72 * (size_t)nT);
     MAGE_CUDA_TRY(W.commit());
     mark("cudaMalloc");
@@ -2875,7 +2674,7 @@ static int ba_build_structure(mage_ba_t h)
     d.cam_diag = W.at<int>(o_cdiag); d.bb_ptr = W.at<int>(o_bbptr); d.bpairs = W.at<ushort2>(o_bpairs);
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
-    d.big = big; d.Wk = W.at<double>(o_Wk);
+    d.big = big; d.Zq = W.at<int8_t>(o_Zq); d.Ez = W.at<int>(o_Ez); d.Ldiag = W.at<double>(o_Ldiag);
     d.nT = nT; d.t_def = W.at<int4>(o_tdef); d.t_meas = W.at<double>(o_tmeas); d.t_err = W.at<double>(o_terr); d.t_J = W.at<double>(o_tJ);
     MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
     mark("enqueue uploads");
@@ -2902,8 +2701,8 @@ extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const char* env = getenv("MAGE_BA_COOP_BLOCKS");
         int want = env ? atoi(env) : 32;
-        if (coop && want > 0 && cudaFuncSetAttribute(k_ba_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_step_coop, kCoopThreads, 128 * 1024) == cudaSuccess && per_sm > 0)
+        if (coop && want > 0 && cudaFuncSetAttribute(k_ba_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmemMax) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_step_coop, kCoopThreads, kCoopSmemMax) == cudaSuccess && per_sm > 0)
         {
             h->coop_blocks_max = std::min(kCoopMaxBlocks, sms * per_sm);
             h->coop_blocks = std::min(want, h->coop_blocks_max);
@@ -3160,10 +2959,14 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
     int rc = ba_prepare(h, huber, n_iters);
     if (rc) return rc;
     if (!h->useless) {
-        const size_t coop_smem = (h->dev.big ? kBigScratchBytes : ba_smem_need_S(h->dev.n)) + ba_smem_need_cams(h->dev.K);
+        // dynamic shared memory: the reduced system (small problems) or the dense solver's staging (large ones), then the camera state
+        // when it still fits -- otherwise the cameras stay in global memory
+        const size_t coop_head = h->dev.big ? dense::kSmemBytes : ba_smem_need_S(h->dev.n);
+        const bool cams_fit = h->dev.K <= kBaMaxSmemCams && coop_head + ba_smem_need_cams(h->dev.K) <= kCoopSmemMax;
+        const size_t coop_smem = coop_head + (cams_fit ? ba_smem_need_cams(h->dev.K) : 0);
         // tether edges are handled by the single-CTA kernel only (windows with tethers are stereo / IMU local BA, never the global size)
         MAGE_REQUIRE(!(h->dev.nT > 0 && h->dev.big), MAGE_ERR_UNSUPPORTED, "tether edges are not supported on problems with %d pose unknowns", h->dev.n);
-        const bool use_coop = h->dev.nT == 0 && h->coop_blocks > 1 && h->dev.K <= kBaMaxSmemCams && coop_smem <= 128 * 1024 && (h->dev.Ea >= 1024 || h->dev.big);
+        const bool use_coop = h->dev.nT == 0 && h->coop_blocks > 1 && (cams_fit || h->dev.big) && coop_smem <= kCoopSmemMax && (h->dev.Ea >= 1024 || h->dev.big);
         MAGE_REQUIRE(use_coop || !h->dev.big, MAGE_ERR_UNSUPPORTED, "reduced camera system of %d unknowns needs the cooperative kernel (not available)", h->dev.n);
         // small systems: enough CTAs that every (reduced-system block, part) item of the Schur products gets its own warp in ONE round
         // (288 items on 32 CTAs = 256 warps ran a second, nearly empty round)
@@ -3326,6 +3129,58 @@ extern "C" int mage_ba_debug_phase_ns(mage_ba_t h, long long out[16])
     BaCtl c;
     MAGE_CUDA_TRY(cudaMemcpy(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; i++) out[i] = c.phase_ns[i];
+    return MAGE_OK;
+}
+
+// ---- the dense solver on its own (test entry): factor a symmetric positive definite matrix and solve one right-hand side ------------
+__global__ void __launch_bounds__(kCoopThreads) k_dense_debug(double* S, int n, double* y, dense::Scratch sc, int* ok)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char dyn[];
+    dense::ldlt_grid(grid, S, n, sc, dyn, ok);
+    grid.sync();
+    dense::export_diag_blocks(S, n, sc);
+    if (*reinterpret_cast<volatile int*>(ok)) dense::solve_back_grid(grid, S, n, sc, dyn);
+}
+
+// A (n x n, row-major, symmetric; the lower triangle is read) and b on the host -> x, optionally the factor (L strictly below the
+// diagonal, D on it; the upper triangle is returned as it was passed in) and the phase timers of dense_ldlt.cuh.
+extern "C" int mage_dense_debug_solve(int n, const double* A, const double* b, double* x, double* factor, int* positive, long long phase_ns[16])
+{
+    MAGE_REQUIRE(n >= 1 && A && b && x && positive, MAGE_ERR_INVALID, "mage_dense_debug_solve: bad argument");
+    MAGE_REQUIRE(n % 2 == 0, MAGE_ERR_UNSUPPORTED, "n must be even (a reduced camera system has 6 unknowns per camera; rows are read as 16-byte pairs)");
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    MAGE_REQUIRE(coop, MAGE_ERR_UNSUPPORTED, "cooperative launch not available");
+    MAGE_CUDA_TRY(cudaFuncSetAttribute(k_dense_debug, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense::kSmemBytes));
+    MAGE_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense_debug, kCoopThreads, dense::kSmemBytes));
+    MAGE_REQUIRE(per_sm >= 1, MAGE_ERR_UNSUPPORTED, "the dense solver does not fit an SM");
+    DeviceArena W;
+    const size_t o_S = W.reserve(sizeof(double) * (size_t)n * n), o_y = W.reserve(sizeof(double) * n), o_zq = W.reserve(dense::scratch_zq_bytes(n), 1024);
+    const size_t o_ez = W.reserve(sizeof(int) * dense::scratch_ez_count(n)), o_ok = W.reserve(sizeof(int)), o_ns = W.reserve(sizeof(long long) * 16);
+    const size_t o_ld = W.reserve(dense::scratch_ldiag_bytes(n), 256);
+    MAGE_CUDA_TRY(W.commit());
+    cudaError_t e = cudaMemset(W.base, 0, W.size);
+    if (e == cudaSuccess) e = cudaMemcpy(W.base + o_S, A, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(W.base + o_y, b, sizeof(double) * n, cudaMemcpyHostToDevice);
+    const int one = 1;
+    if (e == cudaSuccess) e = cudaMemcpy(W.base + o_ok, &one, sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        double* dS = W.at<double>(o_S); double* dy = W.at<double>(o_y); int* dok = W.at<int>(o_ok);
+        dense::Scratch sc = {W.at<int8_t>(o_zq), W.at<int>(o_ez), W.at<double>(o_ld), dy, W.at<long long>(o_ns)};
+        int nn = n;
+        void* args[] = {(void*)&dS, (void*)&nn, (void*)&dy, (void*)&sc, (void*)&dok};
+        e = cudaLaunchCooperativeKernel((const void*)k_dense_debug, dim3(std::min(kCoopMaxBlocks, sms * per_sm)), dim3(kCoopThreads), args, dense::kSmemBytes, 0);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaMemcpy(x, W.base + o_y, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(positive, W.base + o_ok, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && factor) e = cudaMemcpy(factor, W.base + o_S, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && phase_ns) e = cudaMemcpy(phase_ns, W.base + o_ns, sizeof(long long) * 16, cudaMemcpyDeviceToHost);
+    W.release();
+    if (e != cudaSuccess) { set_error("mage_dense_debug_solve: %s", cudaGetErrorString(e)); return MAGE_ERR_CUDA; }
     return MAGE_OK;
 }
 
