@@ -1704,7 +1704,7 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
     int iteration = ctl->iteration;
     long long trials = 0, iters = 0;
 
-    long long t_last = gtimer();
+    long long t_last = (blockIdx.x == 0 && tid == 0) ? gtimer() : 0;     // %globaltimer reads serialise across the chip: one thread only
     f_cam_R(p, tid, nt);
     __syncthreads();
     if (p.fast) {
@@ -2114,7 +2114,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
     __syncthreads();
     int iteration = ctl->iteration, seq = 0;
     long long trials = 0, iters = 0;
-    long long t_last = gtimer();
+    long long t_last = (blockIdx.x == 0 && tid == 0) ? gtimer() : 0;
 
     // errors of this thread's edges + robust chi2 partial
     auto errors_chi2 = [&](double delta) {
@@ -3166,19 +3166,30 @@ extern "C" int mage_dense_debug_solve(int n, const double* A, const double* b, d
     if (e == cudaSuccess) e = cudaMemcpy(W.base + o_S, A, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(W.base + o_y, b, sizeof(double) * n, cudaMemcpyHostToDevice);
     const int one = 1;
+    long long kernel_ns = 0;
     if (e == cudaSuccess) e = cudaMemcpy(W.base + o_ok, &one, sizeof(int), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         double* dS = W.at<double>(o_S); double* dy = W.at<double>(o_y); int* dok = W.at<int>(o_ok);
-        dense::Scratch sc = {W.at<int8_t>(o_zq), W.at<int>(o_ez), W.at<double>(o_ld), dy, W.at<long long>(o_ns)};
+        // MAGE_DENSE_NO_TIMERS=1: no in-kernel phase timers (reading %globaltimer costs the timed thread about a microsecond each time)
+        dense::Scratch sc = {W.at<int8_t>(o_zq), W.at<int>(o_ez), W.at<double>(o_ld), dy, getenv("MAGE_DENSE_NO_TIMERS") ? nullptr : W.at<long long>(o_ns)};
         int nn = n;
         void* args[] = {(void*)&dS, (void*)&nn, (void*)&dy, (void*)&sc, (void*)&dok};
+        cudaEvent_t ev0, ev1;
+        cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, 0);
         e = cudaLaunchCooperativeKernel((const void*)k_dense_debug, dim3(std::min(kCoopMaxBlocks, sms * per_sm)), dim3(kCoopThreads), args, dense::kSmemBytes, 0);
+        cudaEventRecord(ev1, 0);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        float ms = 0;
+        if (e == cudaSuccess) cudaEventElapsedTime(&ms, ev0, ev1);
+        kernel_ns = (long long)(ms * 1e6);
+        cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     }
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaMemcpy(x, W.base + o_y, sizeof(double) * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(positive, W.base + o_ok, sizeof(int), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && factor) e = cudaMemcpy(factor, W.base + o_S, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && phase_ns) e = cudaMemcpy(phase_ns, W.base + o_ns, sizeof(long long) * 16, cudaMemcpyDeviceToHost);
+    if (phase_ns) phase_ns[15] = kernel_ns;                            // the whole kernel by CUDA events
     W.release();
     if (e != cudaSuccess) { set_error("mage_dense_debug_solve: %s", cudaGetErrorString(e)); return MAGE_ERR_CUDA; }
     return MAGE_OK;

@@ -38,7 +38,7 @@ constexpr int kThreads = 256;
 constexpr int LTP = NB + 2;                   // row pitch (doubles) of the transposed diagonal block in shared memory: 16-byte rows
 constexpr int kMinExp = 1023 - 400;           // rows whose largest |z| is below 2^-400 contribute nothing
 constexpr size_t kSmemUpdate = (size_t)SL * PLANE + (size_t)SL * BPLANE + TN * sizeof(double);
-constexpr size_t kSmemTrsm = sizeof(double) * ((size_t)NB * LTP + 2 * NB + 32 * 96);
+constexpr size_t kSmemTrsm = sizeof(double) * ((size_t)NB * LTP + 2 * NB + 32 * 96 + 128);
 constexpr size_t kSmemBytes = (kSmemUpdate > kSmemTrsm ? kSmemUpdate : kSmemTrsm) + 1024;     // + slack to align the base to 1 KB
 // instruction descriptor (kind::i8): D = s32, A and B signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -53,6 +53,9 @@ struct Scratch {
     long long* ns;    // optional [16] phase timers written by CTA 0: diag, panel, update, barriers, solve, ... (null: off)
 };
 
+// Rounds a pointer into the dynamic shared memory up to 1 KB by pointer arithmetic (a round trip through an integer would make
+// every access behind it a generic load / store instead of LDS / STS).
+__device__ __forceinline__ uint8_t* align_1k(uint8_t* p) { return p + ((1024u - ((uint32_t)__cvta_generic_to_shared(p) & 1023u)) & 1023u); }
 __device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
@@ -107,6 +110,34 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
                  : "r"(taddr) : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 16 columns of this warp's 32 accumulator rows; the registers are valid after tmem_ld16_wait (which takes them as in-out operands
+// so that no use can be scheduled above the wait)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]),
+                   "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :: "memory");
+}
+// 1 / d for a normal positive d (a pivot; anything else is reported as "not positive" by the caller): hardware seed, third-order
+// step and one Newton step -- the sequence __drcp_rn starts with, without its special-case tail (70 instructions per use)
+__device__ __forceinline__ double rcp_pos(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    e = fma(e, e, e);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    return fma(x, e, x);
+}
 __device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }      // -1022 <= e <= 1023
 
 // ---- (a) diagonal block, factored by EVERY CTA redundantly (same arithmetic, same result): the panel rows below need the factored
@@ -141,30 +172,54 @@ __device__ __forceinline__ void load_diag_block(const double* __restrict__ A, in
 
 __device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ invD, double* __restrict__ rsD, double* __restrict__ Yt, int nb, int* s_bad, long long* ns)
 {
+    double* colb = Yt + 32 * YP;                                // [2][64] column exchange of the sub-block factorisation, upper halves zero
+    if (threadIdx.x < 128) colb[threadIdx.x] = 0.0;
+    __syncthreads();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    long long tm = gtime();
-    auto lap = [&](int slot) { if (ns && blockIdx.x == 0 && tid == 0) { const long long t = gtime(); ns[slot] += t - tm; tm = t; } };
+    const bool timed = ns && blockIdx.x == 0 && tid == 0;       // reading %globaltimer is slow and serialises across the chip: one thread only
+    long long tm = timed ? gtime() : 0;
+    auto lap = [&](int slot) { if (timed) { const long long t = gtime(); ns[slot] += t - tm; tm = t; } };
     for (int j0 = 0; j0 < nb; j0 += 32) {
         if (warp == 0) {                                            // 1. the 32 x 32 block on the diagonal
+            // lane = row, the row's 32 entries in registers. Per column: the column goes through a double-buffered shared vector that
+            // every lane reads back as broadcasts (the pivot first: its reciprocal is the critical path), then one rank-1 update.
+            // The registers are a WINDOW that starts at the current column and moves on by four columns per pass of a rolled loop:
+            // fully unrolled, the 32 columns are 120 KB of straight-line code and the warp spent most of its time waiting for
+            // instructions (ncu: stall_no_inst 57 %). Entries shifted in behind column 31 are zeros and stay unused.
             double a[32];
 #pragma unroll
             for (int c = 0; c < 32; c++) a[c] = c <= lane ? Lt[(j0 + c) * LTP + j0 + lane] : 0.0;
             bool bad = false;
             double mine = 1.0;
+#pragma unroll 1
+            for (int kw = 0; kw < 32; kw += 4) {
 #pragma unroll
-            for (int k = 0; k < 32; k++) {
-                const double ck = a[k];
-                const double d = __shfl_sync(0xffffffffu, ck, k);
-                if (!(d > 0)) bad = true;
-                const double inv = fabs(d) > 0 ? __drcp_rn(d) : 0.0;            // correctly rounded, like 1.0 / d, in a third of the instructions
-                const double l = ck * inv;
+                for (int u = 0; u < 4; u++) {
+                    const int k = kw + u;
+                    const double ck = a[u];
+                    double* cb = colb + (u & 1) * 64;            // [2][64]: the upper halves stay zero (reads of a window past column 31)
+                    cb[lane] = ck;
+                    __syncwarp();
+                    const double d = cb[k];
+                    double cj[32];                                // A(k + t - u, k), t > u
+                    if ((u + 1) & 1) cj[u + 1] = cb[kw + u + 1];
 #pragma unroll
-                for (int j = k + 1; j < 32; j++) a[j] -= l * __shfl_sync(0xffffffffu, ck, j);       // A(i, j) -= L(i, k) A(j, k)
-                if (lane == k) mine = d;
-                a[k] = lane == k ? d : l;
+                    for (int t = (u + 2) & ~1; t < 32; t += 2) {
+                        const double2 c2 = *reinterpret_cast<const double2*>(cb + kw + t);
+                        cj[t] = c2.x; cj[t + 1] = c2.y;
+                    }
+                    if (!(d > 0)) bad = true;
+                    const double inv = fabs(d) > 0 ? rcp_pos(d) : 0.0;
+                    const double l = ck * inv;
+#pragma unroll
+                    for (int t = u + 1; t < 32; t++) a[t] -= l * cj[t];          // A(i, j) -= L(i, k) A(j, k)
+                    if (lane == k) mine = d;
+                    if (lane >= k) Lt[(j0 + k) * LTP + j0 + lane] = lane == k ? d : l;
+                }
+#pragma unroll
+                for (int t = 0; t < 28; t++) a[t] = a[t + 4];
+                a[28] = 0.0; a[29] = 0.0; a[30] = 0.0; a[31] = 0.0;
             }
-#pragma unroll
-            for (int c = 0; c < 32; c++) if (c <= lane) Lt[(j0 + c) * LTP + j0 + lane] = a[c];
             invD[j0 + lane] = fabs(mine) > 0 ? 1.0 / mine : 0.0;
             rsD[j0 + lane] = mine > 0 ? 1.0 / sqrt(mine) : 0.0;
             if (bad && lane == 0) *s_bad = 1;
@@ -175,19 +230,31 @@ __device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ i
         if (below <= 0) break;
         const int below4 = (below + 3) & ~3;                        // padded rows are zero and stay zero
         if (tid < below4) {                                         // 2. Y L_sub^T = A  ->  Y, L = Y D^-1
+            // thread = row; the same moving register window as above (rolled loop, four columns per pass)
             const int row = j0 + 32 + tid;
             double a[32];
 #pragma unroll
             for (int c = 0; c < 32; c++) a[c] = Lt[(j0 + c) * LTP + row];
+#pragma unroll 1
+            for (int kw = 0; kw < 32; kw += 4) {
 #pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const double yc = a[c];
-                const double* lc = Lt + (j0 + c) * LTP + j0;       // L_sub(j, c), the same address for every thread
+                for (int u = 0; u < 4; u++) {
+                    const int c = kw + u;
+                    const double yc = a[u];
+                    const double* lc = Lt + (j0 + c) * LTP + j0 + kw;   // L_sub(kw + t, c), the same address for every thread; t > u
+                    if ((u + 1) & 1) a[u + 1] -= yc * lc[u + 1];
 #pragma unroll
-                for (int j = c + 1; j < 32; j++) a[j] -= yc * lc[j];
+                    for (int t = (u + 2) & ~1; t < 32; t += 2) {                 // past row 31 of the sub-block: finite matrix data, results unused
+                        const double2 l2 = *reinterpret_cast<const double2*>(lc + t);
+                        a[t] -= yc * l2.x; a[t + 1] -= yc * l2.y;
+                    }
+                    Yt[c * YP + tid] = yc;
+                    Lt[(j0 + c) * LTP + row] = yc * invD[j0 + c];
+                }
+#pragma unroll
+                for (int t = 0; t < 28; t++) a[t] = a[t + 4];
+                a[28] = 0.0; a[29] = 0.0; a[30] = 0.0; a[31] = 0.0;
             }
-#pragma unroll
-            for (int c = 0; c < 32; c++) { Yt[c * YP + tid] = a[c]; Lt[(j0 + c) * LTP + row] = a[c] * invD[j0 + c]; }
         }
         __syncthreads();
         lap(6);
@@ -407,37 +474,68 @@ __device__ void update_tiles(double* __restrict__ S, int n, int ntot, int r0, co
             for (int c = 0; c < TN; c++) acc[c] = 0.0;
             const bool timed = sc.ns && blockIdx.x == 0 && tid == 128;
             long long tw = 0, tc = 0, t0 = timed ? gtime() : 0;
+            double* out = (row < n ? S + (size_t)row * n : sc.ytmp) + TN * jt;          // row n = the right-hand side
+            const int ncol = row < ntot ? min(TN, min(n, row + 1) - TN * jt) : 0;   // columns j <= row (and < n) of this tile
+            // the tile of S goes through registers in chunks of 16 columns; the first chunk is fetched before the accumulators are
+            // waited for, every further one while the chunk before it is combined and stored
+            double2 pre[2][8];
+            auto fetch = [&](int ch, double2 (&buf)[8]) {
 #pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int c = 16 * ch + 2 * q;
+                    if (c + 1 < ncol) buf[q] = *reinterpret_cast<const double2*>(out + c);
+                    else buf[q] = make_double2(c < ncol ? out[c] : 0.0, 0.0);
+                }
+            };
+            fetch(0, pre[0]);
+            const uint32_t tbase = tmem + ((uint32_t)(32 * (warp - 4)) << 16);
+            uint32_t v[2][16];
+            // 8 accumulators x 4 quarters of 16 columns; the load of the next quarter is in flight while one is combined. The loop
+            // over the accumulators stays rolled (small code: the unrolled epilogue did not fit the instruction cache).
+            // s32 -> f64 without the conversion instruction (a tenth of the DFMA rate): 2^52 + 2^31 + v as a bit pattern, minus the constant.
+            mbar_wait(saddr(&us.accfull[0]), par, &us.fail);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tmem_ld16_issue(tbase, v[0]);
+#pragma unroll 1
             for (int d = 0; d < SL; d++) {
-                mbar_wait(saddr(&us.accfull[d]), par, &us.fail);
-                if (timed) { const long long t = gtime(); tw += t - t0; t0 = t; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const double wd = pow2(-7 * d);
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(32 * (warp - 4)) << 16) + (uint32_t)(TN * d + 32 * half), v);
+                for (int q = 0; q < 4; q++) {
+                    tmem_ld16_wait(v[q & 1]);
+                    if (q < 3) tmem_ld16_issue(tbase + (uint32_t)(TN * d + 16 * (q + 1)), v[(q + 1) & 1]);
+                    else {                                        // accumulator d is in registers: the next tile may overwrite it
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(saddr(&us.tempty[d]));
+                        if (d + 1 < SL) {
+                            if (timed) t0 = gtime();
+                            mbar_wait(saddr(&us.accfull[d + 1]), par, &us.fail);
+                            if (timed) tw += gtime() - t0;
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            tmem_ld16_issue(tbase + (uint32_t)(TN * (d + 1)), v[0]);
+                        }
+                    }
 #pragma unroll
-                    for (int c = 0; c < 32; c++) acc[32 * half + c] = fma((double)(int)v[c], wd, acc[32 * half + c]);
+                    for (int c = 0; c < 16; c++) {
+                        const double x = __hiloint2double(0x43300000, (int)(v[q & 1][c] ^ 0x80000000u)) - 4503601774854144.0;
+                        acc[16 * q + c] = fma(x, wd, acc[16 * q + c]);
+                    }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                mbar_arrive(saddr(&us.tempty[d]));
-                if (timed) { const long long t = gtime(); tc += t - t0; t0 = t; }
             }
-            if (timed) { sc.ns[8] += tw; sc.ns[9] += tc; }
-            if (row < ntot) {
-                double* out = (row < n ? S + (size_t)row * n : sc.ytmp) + TN * jt;      // row n = the right-hand side
-                const int ncol = min(TN, min(n, row + 1) - TN * jt);            // columns j <= row (and < n) of this tile
+            if (timed) { sc.ns[8] += tw; t0 = gtime(); }
 #pragma unroll
-                for (int c = 0; c < TN; c += 2) {
-                    if (c + 1 < ncol) {
-                        double2 o = *reinterpret_cast<double2*>(out + c);
-                        o.x -= acc[c] * rowscale * colscale[c]; o.y -= acc[c + 1] * rowscale * colscale[c + 1];
-                        *reinterpret_cast<double2*>(out + c) = o;
-                    } else if (c < ncol) out[c] -= acc[c] * rowscale * colscale[c];
+            for (int ch = 0; ch < 4; ch++) {
+                if (ch < 3) fetch(ch + 1, pre[(ch + 1) & 1]);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int c = 16 * ch + 2 * q;
+                    double2 o = pre[ch & 1][q];
+                    o.x -= acc[c] * rowscale * colscale[c]; o.y -= acc[c + 1] * rowscale * colscale[c + 1];
+                    if (c + 1 < ncol) *reinterpret_cast<double2*>(out + c) = o;
+                    else if (c < ncol) out[c] = o.x;
                 }
             }
             if (timed) sc.ns[10] += gtime() - t0;
+            (void)tc;
         }
         last_it = it;
         done++;
@@ -457,11 +555,12 @@ __device__ void ldlt_grid(cg::grid_group& grid, double* __restrict__ S, int n, c
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int gwarp = (int)blockIdx.x * (nt >> 5) + warp, gnw = (int)gridDim.x * (nt >> 5);
     const int ntot = n + 1;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = align_1k(smem_raw);
     __shared__ UpdateShared us;
     __shared__ int s_bad;
-    long long t_mark = gtime();
-    auto lap = [&](int slot) { if (sc.ns && blockIdx.x == 0 && tid == 0) { const long long t = gtime(); sc.ns[slot] += t - t_mark; t_mark = t; } };
+    const bool timed0 = sc.ns && blockIdx.x == 0 && tid == 0;   // reading %globaltimer is slow and serialises across the chip: one thread only
+    long long t_mark = timed0 ? gtime() : 0;
+    auto lap = [&](int slot) { if (timed0) { const long long t = gtime(); sc.ns[slot] += t - t_mark; t_mark = t; } };
     const bool need_update = n > NB;
     if (need_update) {
         if (warp == 0) {
@@ -546,10 +645,11 @@ __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__
 {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
     double* y = sc.ytmp;
-    double* T = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);      // the diagonal block, Lt[c][r]
+    double* T = reinterpret_cast<double*>(align_1k(smem_raw));   // the diagonal block, Lt[c][r]
     double* xs = T + NB * LTP;                                   // [NB] unknowns of the block
     double* red = xs + NB;                                       // [8][32] partial sums
-    long long t_mark = gtime();
+    const bool timed0 = sc.ns && blockIdx.x == 0 && tid == 0;
+    const long long t_mark = timed0 ? gtime() : 0;
     for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
         const int nb = min(NB, n - k0);
         if (blockIdx.x == 0) {
@@ -617,7 +717,7 @@ __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__
         __threadfence();
         grid.sync();
     }
-    if (sc.ns && blockIdx.x == 0 && tid == 0) sc.ns[4] += gtime() - t_mark;
+    if (timed0) sc.ns[4] += gtime() - t_mark;
 }
 
 inline size_t scratch_zq_bytes(int n) { return (size_t)((n + 1 + TM - 1) / TM) * SL * PLANE; }
