@@ -32,17 +32,23 @@ def main():
     rows = list(csv.reader(io.StringIO(csvtxt)))
     hi = [i for i, r in enumerate(rows) if "# Samples" in r][0]
     hdr = rows[hi]; si = hdr.index("# Samples"); ie = hdr.index("Instructions Executed")
+    stall_cols = [(i, h[6:]) for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     data = [r for r in rows[hi + 1:] if len(r) > si and r[si].isdigit()]
     if len(data) % len(sl) == 0 and len(data) != len(sl):
         data = data[:len(sl)]                     # several captured launches are concatenated: use the first
     assert len(data) == len(sl), (len(data), len(sl))
     agg = collections.OrderedDict()
     for (addr, line, ins), r in zip(sl, data):
-        a = agg.setdefault(line, [0, 0]); a[0] += int(r[si]); a[1] += int(r[ie])
+        a = agg.setdefault(line, [0, 0, collections.Counter()]); a[0] += int(r[si]); a[1] += int(r[ie])
+        for i, h in stall_cols:
+            if r[i].isdigit(): a[2][h] += int(r[i])
     ts = sum(a[0] for a in agg.values()); ti = sum(a[1] for a in agg.values())
     print("total samples %d, warp instructions %d" % (ts, ti))
     src = {}
-    for line, (s, i) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+    allst = collections.Counter()
+    for a in agg.values(): allst.update(a[2])
+    print("stall reasons overall:", ", ".join("%s %.1f%%" % (h, 100 * v / max(1, sum(allst.values()))) for h, v in allst.most_common(8)))
+    for line, (s, i, st) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
         if line is None:
             print("%6.2f%% samples %6.2f%% instr  <no line info>" % (100 * s / ts, 100 * i / ti)); continue
         fn, no = line
@@ -54,7 +60,8 @@ def main():
             else:
                 src[fn] = []
         text = src[fn][no - 1].strip()[:110] if 0 < no <= len(src[fn]) else ""
-        print("%6.2f%% samples %6.2f%% instr  %s:%d  %s" % (100 * s / ts, 100 * i / ti, fn, no, text))
+        why = " ".join("%s:%d%%" % (h, 100 * v / max(1, sum(st.values()))) for h, v in st.most_common(2))
+        print("%6.2f%% samples %6.2f%% instr  %s:%d  [%s]  %s" % (100 * s / ts, 100 * i / ti, fn, no, why, text))
 
 if __name__ == "__main__":
     main()
