@@ -19,6 +19,7 @@
 // FP64 CUDA cores keep everything that is not a dense contraction: the diagonal blocks, the panel solves, the substitutions.
 #pragma once
 
+
 #include <cooperative_groups.h>
 
 #include <cfloat>
@@ -42,7 +43,7 @@ constexpr size_t kSmemTrsm = sizeof(double) * ((size_t)NB * LTP + 2 * NB + 32 * 
 constexpr size_t kSmemBytes = (kSmemUpdate > kSmemTrsm ? kSmemUpdate : kSmemTrsm) + 1024;     // + slack to align the base to 1 KB
 // instruction descriptor (kind::i8): D = s32, A and B signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-constexpr uint32_t kLBO = 128, kSBO = 256;    // K-chunk (16 B) stride, 8-row group stride inside one K = 32 step
+constexpr uint32_t kSBO = 1024;               // operand planes are K-major rows of 128 bytes under the 128-byte swizzle: stride of an 8-row group
 
 // global scratch of one problem (allocated with it, zero-initialised)
 struct Scratch {
@@ -61,12 +62,21 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t a)
 {
-    return (uint64_t)((a & 0x3FFFFu) >> 4) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46);
+    // start address, leading-dimension offset (unused under a swizzle: 1), stride offset, descriptor version 1, layout SWIZZLE_128B
+    return (uint64_t)((a & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(kSBO >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate)
 {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// the same with the descriptors given by their low words (start address, LBO); the high word is the constant of smem_desc
+__device__ __forceinline__ void mma_i8_lo(uint32_t tmem_d, uint32_t da_lo, uint32_t db_lo, uint32_t accumulate)
+{
+    constexpr uint32_t hi = (uint32_t)(((uint64_t)(kSBO >> 4) << 32 | (1ull << 46) | (2ull << 61)) >> 32);
+    asm volatile("{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %4, 0;\n mov.b64 da, {%1, %6};\n mov.b64 db, {%2, %6};\n"
+                 " tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, {%5, %5, %5, %5}, p;\n}"
+                 ::"r"(tmem_d), "r"(da_lo), "r"(db_lo), "r"(kIdesc), "r"(accumulate), "r"(0u), "r"(hi) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar)
 {
@@ -373,7 +383,9 @@ __device__ __forceinline__ void panel_rows_R(double* __restrict__ S, int n, int 
         double t[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) t[j] = z[j] * down * 64.0;
-        int8_t* dst = sc.Zq + (size_t)(row >> 7) * SL * PLANE + (lane >> 3) * 4096 + ((row & 127) >> 3) * 256 + ((lane >> 2) & 1) * 128 + (row & 7) * 16 + 4 * (lane & 3);
+        // plane = 128 rows x 128 bytes (K = the panel's 128 columns); 16-byte chunk c of row r sits at chunk c ^ (r & 7): the
+        // 128-byte swizzle the tensor core reads conflict-free (the unswizzled core-matrix layout ran the MMAs at 40 % of this rate)
+        int8_t* dst = sc.Zq + (size_t)(row >> 7) * SL * PLANE + (row & 127) * 128 + (((lane >> 2) ^ (row & 7)) << 4) + 4 * (lane & 3);
 #pragma unroll
         for (int s = 0; s < SL; s++) {
             uint32_t w = 0;
@@ -436,32 +448,41 @@ __device__ void update_tiles(double* __restrict__ S, int n, int ntot, int r0, co
                 if (done > 0) mbar_wait(saddr(&us.smemfree), prev, &us.fail);
                 const bool loadA = it != last_it;
                 const int8_t* gA = sc.Zq + (size_t)it * SL * PLANE;
-                const int8_t* gB = sc.Zq + (size_t)(jt >> 1) * SL * PLANE + (jt & 1) * 2048;
+                const int8_t* gB = sc.Zq + (size_t)(jt >> 1) * SL * PLANE + (jt & 1) * BPLANE;
 #pragma unroll 1
                 for (int s = 0; s < SL; s++) {
                     const uint32_t bar = saddr(&us.full[s]);
                     mbar_expect_tx(bar, (uint32_t)BPLANE + (loadA ? (uint32_t)PLANE : 0u));
                     if (loadA) bulk_load(sA + s * PLANE, gA + (size_t)s * PLANE, PLANE, bar);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++) bulk_load(sB + s * BPLANE + ks * 2048, gB + (size_t)s * PLANE + ks * 4096, 2048, bar);
+                    bulk_load(sB + s * BPLANE, gB + (size_t)s * PLANE, BPLANE, bar);
                 }
             }
         } else if (warp == 1) {
             if (lane == 0) {
+                const bool timedm = sc.ns && blockIdx.x == 0;
+                const uint32_t descA_lo = (uint32_t)smem_desc(sA), descB_lo = (uint32_t)smem_desc(sB);
+                long long m0 = timedm ? gtime() : 0, tf = 0, te = 0;
 #pragma unroll 1
                 for (int d = 0; d < SL; d++) {
                     mbar_wait(saddr(&us.full[d]), par, &us.fail);
+                    if (timedm) { const long long t = gtime(); tf += t - m0; m0 = t; }
                     if (done > 0) mbar_wait(saddr(&us.tempty[d]), prev, &us.fail);
+                    if (timedm) { const long long t = gtime(); te += t - m0; m0 = t; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    // one thread issues the 144 MMAs of a tile: the descriptors are a constant high word and a low word that moves
+                    // by a constant per slice / K step (built from scratch each time, the issue loop -- not the tensor core -- set the pace)
+#pragma unroll 1
                     for (int s = 0; s <= d; s++) {
-                        const int t = d - s;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ks++)
-                            mma_i8(tmem + (uint32_t)(TN * d), smem_desc(sA + s * PLANE + ks * 4096), smem_desc(sB + t * BPLANE + ks * 2048), (s > 0 || ks > 0) ? 1u : 0u);
+                        const uint32_t la = descA_lo + (uint32_t)s * (PLANE >> 4), lb = descB_lo + (uint32_t)(d - s) * (BPLANE >> 4);
+                        mma_i8_lo(tmem + (uint32_t)(TN * d), la, lb, s > 0 ? 1u : 0u);
+                        mma_i8_lo(tmem + (uint32_t)(TN * d), la + 2, lb + 2, 1u);
+                        mma_i8_lo(tmem + (uint32_t)(TN * d), la + 4, lb + 4, 1u);
+                        mma_i8_lo(tmem + (uint32_t)(TN * d), la + 6, lb + 6, 1u);
                     }
                     mma_commit(saddr(&us.accfull[d]));
                 }
                 mma_commit(saddr(&us.smemfree));
+                if (timedm) { sc.ns[11] += tf; sc.ns[12] += te; sc.ns[13] += 1; }
             }
         } else if (warp >= 4) {
             const int row = TM * it + 32 * (warp - 4) + lane;
@@ -469,73 +490,78 @@ __device__ void update_tiles(double* __restrict__ S, int n, int ntot, int r0, co
             if (tid - 128 < TN) { const int j = TN * jt + tid - 128; colscale[tid - 128] = j < n ? pow2(sc.Ez[j]) : 0.0; }
             const double rowscale = row < ntot ? pow2(sc.Ez[row] - 12) : 0.0;
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            double acc[TN];
-#pragma unroll
-            for (int c = 0; c < TN; c++) acc[c] = 0.0;
             const bool timed = sc.ns && blockIdx.x == 0 && tid == 128;
-            long long tw = 0, tc = 0, t0 = timed ? gtime() : 0;
+            long long tw = 0, ts = 0, t0 = 0;
             double* out = (row < n ? S + (size_t)row * n : sc.ytmp) + TN * jt;          // row n = the right-hand side
             const int ncol = row < ntot ? min(TN, min(n, row + 1) - TN * jt) : 0;   // columns j <= row (and < n) of this tile
-            // the tile of S goes through registers in chunks of 16 columns; the first chunk is fetched before the accumulators are
-            // waited for, every further one while the chunk before it is combined and stored
-            double2 pre[2][8];
-            auto fetch = [&](int ch, double2 (&buf)[8]) {
+            const uint32_t tbase = tmem + ((uint32_t)(32 * (warp - 4)) << 16);
+            // Two passes over the column halves of the tile. The 32 values of S a pass updates are fetched into registers when the
+            // pass before it ends (the first pass: before the accumulators are waited for), so their latency -- a warp reads 32
+            // different rows -- hides behind the combination of the eight accumulators; those are released to the next tile's MMAs
+            // as the second pass reads them.
+            double2 pre[16];
+            auto fetch = [&](int half) {
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int c = 16 * ch + 2 * q;
-                    if (c + 1 < ncol) buf[q] = *reinterpret_cast<const double2*>(out + c);
-                    else buf[q] = make_double2(c < ncol ? out[c] : 0.0, 0.0);
+                for (int q = 0; q < 16; q++) {
+                    const int c = 32 * half + 2 * q;
+                    if (c + 1 < ncol) pre[q] = *reinterpret_cast<const double2*>(out + c);
+                    else pre[q] = make_double2(c < ncol ? out[c] : 0.0, 0.0);
                 }
             };
-            fetch(0, pre[0]);
-            const uint32_t tbase = tmem + ((uint32_t)(32 * (warp - 4)) << 16);
-            uint32_t v[2][16];
-            // 8 accumulators x 4 quarters of 16 columns; the load of the next quarter is in flight while one is combined. The loop
-            // over the accumulators stays rolled (small code: the unrolled epilogue did not fit the instruction cache).
-            // s32 -> f64 without the conversion instruction (a tenth of the DFMA rate): 2^52 + 2^31 + v as a bit pattern, minus the constant.
-            mbar_wait(saddr(&us.accfull[0]), par, &us.fail);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tmem_ld16_issue(tbase, v[0]);
+            fetch(0);
 #pragma unroll 1
-            for (int d = 0; d < SL; d++) {
-                const double wd = pow2(-7 * d);
+            for (int half = 0; half < 2; half++) {
+                double acc[32];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    tmem_ld16_wait(v[q & 1]);
-                    if (q < 3) tmem_ld16_issue(tbase + (uint32_t)(TN * d + 16 * (q + 1)), v[(q + 1) & 1]);
-                    else {                                        // accumulator d is in registers: the next tile may overwrite it
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive(saddr(&us.tempty[d]));
-                        if (d + 1 < SL) {
-                            if (timed) t0 = gtime();
-                            mbar_wait(saddr(&us.accfull[d + 1]), par, &us.fail);
-                            if (timed) tw += gtime() - t0;
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            tmem_ld16_issue(tbase + (uint32_t)(TN * (d + 1)), v[0]);
+                for (int c = 0; c < 32; c++) acc[c] = 0.0;
+                uint32_t v[2][16];
+                if (timed) t0 = gtime();
+                mbar_wait(saddr(&us.accfull[0]), par, &us.fail);
+                if (timed) tw += gtime() - t0;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tmem_ld16_issue(tbase + (uint32_t)(32 * half), v[0]);
+                // 8 accumulators x 2 quarters of 16 columns; the load of the next quarter is in flight while one is combined.
+                // s32 -> f64 without the conversion instruction (a tenth of the DFMA rate): 2^52 + 2^31 + v as a bit pattern, minus the constant.
+#pragma unroll 1
+                for (int d = 0; d < SL; d++) {
+                    const double wd = pow2(-7 * d);
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        tmem_ld16_wait(v[q]);
+                        if (q == 0) tmem_ld16_issue(tbase + (uint32_t)(TN * d + 32 * half + 16), v[1]);
+                        else {
+                            if (half == 1) {                      // accumulator d is in registers: the next tile may overwrite it
+                                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                                mbar_arrive(saddr(&us.tempty[d]));
+                            }
+                            if (d + 1 < SL) {
+                                if (timed) t0 = gtime();
+                                mbar_wait(saddr(&us.accfull[d + 1]), par, &us.fail);      // second pass: passed long ago
+                                if (timed) tw += gtime() - t0;
+                                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                                tmem_ld16_issue(tbase + (uint32_t)(TN * (d + 1) + 32 * half), v[0]);
+                            }
+                        }
+#pragma unroll
+                        for (int c = 0; c < 16; c++) {
+                            const double x = __hiloint2double(0x43300000, (int)(v[q][c] ^ 0x80000000u)) - 4503601774854144.0;
+                            acc[16 * q + c] = fma(x, wd, acc[16 * q + c]);
                         }
                     }
-#pragma unroll
-                    for (int c = 0; c < 16; c++) {
-                        const double x = __hiloint2double(0x43300000, (int)(v[q & 1][c] ^ 0x80000000u)) - 4503601774854144.0;
-                        acc[16 * q + c] = fma(x, wd, acc[16 * q + c]);
-                    }
                 }
-            }
-            if (timed) { sc.ns[8] += tw; t0 = gtime(); }
+                if (timed) t0 = gtime();
 #pragma unroll
-            for (int ch = 0; ch < 4; ch++) {
-                if (ch < 3) fetch(ch + 1, pre[(ch + 1) & 1]);
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int c = 16 * ch + 2 * q;
-                    double2 o = pre[ch & 1][q];
-                    o.x -= acc[c] * rowscale * colscale[c]; o.y -= acc[c + 1] * rowscale * colscale[c + 1];
+                for (int q = 0; q < 16; q++) {
+                    const int c = 32 * half + 2 * q;
+                    double2 o = pre[q];
+                    o.x -= acc[2 * q] * rowscale * colscale[c]; o.y -= acc[2 * q + 1] * rowscale * colscale[c + 1];
                     if (c + 1 < ncol) *reinterpret_cast<double2*>(out + c) = o;
                     else if (c < ncol) out[c] = o.x;
                 }
+                if (half == 0) fetch(1);
+                if (timed) ts += gtime() - t0;
             }
-            if (timed) sc.ns[10] += gtime() - t0;
-            (void)tc;
+            if (timed) { sc.ns[8] += tw; sc.ns[10] += ts; }
         }
         last_it = it;
         done++;
@@ -636,11 +662,12 @@ __device__ void export_diag_blocks(double* __restrict__ S, int n, const Scratch&
     }
 }
 
-// Solves L^T x = y in place (y = sc.ytmp, as ldlt_grid leaves it), 128 unknowns per step from the last block up: CTA 0 solves the
-// triangle on the diagonal from shared memory -- per 32-wide sub-block one warp with one unknown per lane, the column of L in
-// registers, solved values broadcast by shuffle, then the sub-block's contribution to the earlier unknowns of the block -- and,
-// after a grid barrier, the grid subtracts the block's contribution from all earlier unknowns (32 columns x 8 row groups per CTA
-// pass, partial sums combined in a fixed order).
+// Solves L^T x = y in place (y = sc.ytmp, as ldlt_grid leaves it), 128 unknowns per step from the last block up, ONE grid barrier per
+// step: every CTA solves the triangle on the diagonal itself (same arithmetic, same result -- cheaper than a barrier and a round trip
+// through global memory) -- per 32-wide sub-block one warp with one unknown per lane, the column of L in registers, solved values
+// broadcast by shuffle, then the sub-block's contribution to the earlier unknowns of the block -- and then subtracts the block's
+// contribution from its share of all earlier unknowns (32 columns x 8 row groups per CTA pass, partial sums combined in a fixed
+// order). The next diagonal block travels into shared memory by cp.async meanwhile.
 __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__ S, int n, const Scratch& sc, uint8_t* smem_raw)
 {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
@@ -650,49 +677,55 @@ __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__
     double* red = xs + NB;                                       // [8][32] partial sums
     const bool timed0 = sc.ns && blockIdx.x == 0 && tid == 0;
     const long long t_mark = timed0 ? gtime() : 0;
-    for (int k0 = ((n - 1) / NB) * NB; k0 >= 0; k0 -= NB) {
+    auto fetch_block = [&](int k0) {                             // Ldiag[k0 / NB] -> T, asynchronously
+        const int nb = min(NB, n - k0), cnt = ((nb + 31) & ~31) * LTP / 2;
+        const double2* src = reinterpret_cast<const double2*>(sc.Ldiag + (size_t)(k0 / NB) * NB * LTP);
+        const uint32_t dst = saddr(T);
+        for (int i = tid; i < cnt; i += nt) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int klast = ((n - 1) / NB) * NB;
+    fetch_block(klast);
+    for (int k0 = klast; k0 >= 0; k0 -= NB) {
         const int nb = min(NB, n - k0);
-        if (blockIdx.x == 0) {
-            const double2* src = reinterpret_cast<const double2*>(sc.Ldiag + (size_t)(k0 / NB) * NB * LTP);
-            double2* dst = reinterpret_cast<double2*>(T);
-            const int cnt = ((nb + 31) & ~31) * LTP / 2;
-#pragma unroll 8
-            for (int i = tid; i < cnt; i += nt) dst[i] = src[i];
-            if (tid < NB) xs[tid] = tid < nb ? y[k0 + tid] : 0.0;
-            __syncthreads();
-            if (warp == 0) {
-                for (int j0 = (nb - 1) & ~31; j0 >= 0; j0 -= 32) {
-                    double col[32];                              // L(j0 + r, j0 + lane), r > lane
+        // the block solved in the previous step goes back into y only now: every CTA read its right-hand side from there at the
+        // top of that step, and all of them have passed a grid barrier since
+        if (blockIdx.x == 0 && k0 < klast && tid < min(NB, n - (k0 + NB))) y[k0 + NB + tid] = xs[tid];
+        __syncthreads();
+        if (tid < NB) xs[tid] = tid < nb ? y[k0 + tid] : 0.0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            for (int j0 = (nb - 1) & ~31; j0 >= 0; j0 -= 32) {
+                double col[32];                                  // L(j0 + r, j0 + lane), r > lane
+#pragma unroll
+                for (int r = 0; r < 32; r += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(T + (j0 + lane) * LTP + j0 + r);
+                    col[r] = v.x; col[r + 1] = v.y;
+                }
+                double a = xs[j0 + lane];
+#pragma unroll
+                for (int r = 31; r >= 1; r--) {
+                    const double xr = __shfl_sync(0xffffffffu, a, r);
+                    if (lane < r) a -= xr * col[r];
+                }
+                xs[j0 + lane] = a;
+                __syncwarp();
+                for (int c = lane; c < j0; c += 32) {            // earlier unknowns of this block
+                    double acc = 0;
 #pragma unroll
                     for (int r = 0; r < 32; r += 2) {
-                        const double2 v = *reinterpret_cast<const double2*>(T + (j0 + lane) * LTP + j0 + r);
-                        col[r] = v.x; col[r + 1] = v.y;
+                        const double2 v = *reinterpret_cast<const double2*>(T + c * LTP + j0 + r);
+                        acc = fma(v.x, xs[j0 + r], acc); acc = fma(v.y, xs[j0 + r + 1], acc);
                     }
-                    double a = xs[j0 + lane];
-#pragma unroll
-                    for (int r = 31; r >= 1; r--) {
-                        const double xr = __shfl_sync(0xffffffffu, a, r);
-                        if (lane < r) a -= xr * col[r];
-                    }
-                    xs[j0 + lane] = a;
-                    __syncwarp();
-                    for (int c = lane; c < j0; c += 32) {        // earlier unknowns of this block
-                        double acc = 0;
-#pragma unroll
-                        for (int r = 0; r < 32; r += 2) {
-                            const double2 v = *reinterpret_cast<const double2*>(T + c * LTP + j0 + r);
-                            acc = fma(v.x, xs[j0 + r], acc); acc = fma(v.y, xs[j0 + r + 1], acc);
-                        }
-                        xs[c] -= acc;
-                    }
-                    __syncwarp();
+                    xs[c] -= acc;
                 }
-                for (int c = lane; c < nb; c += 32) y[k0 + c] = xs[c];
+                __syncwarp();
             }
-            __threadfence();
         }
-        grid.sync();
-        if (k0 == 0) break;
+        __syncthreads();
+        if (k0 == 0) { if (blockIdx.x == 0 && tid < nb) y[tid] = xs[tid]; break; }      // nobody reads y[0 .. nb) any more
+        fetch_block(k0 - NB);
         {
             const int cl = tid & 31, rg = tid >> 5;              // 32 columns x 8 groups of 16 rows
             for (int g = (int)blockIdx.x; 32 * g < k0; g += (int)gridDim.x) {
@@ -701,7 +734,7 @@ __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__
 #pragma unroll
                 for (int jj = 0; jj < 16; jj++) {
                     const int j = 16 * rg + jj;
-                    if (j < nb) acc = fma(S[(size_t)(k0 + j) * n + i], y[k0 + j], acc);
+                    if (j < nb) acc = fma(S[(size_t)(k0 + j) * n + i], xs[j], acc);
                 }
                 red[32 * rg + cl] = acc;
                 __syncthreads();
@@ -717,6 +750,8 @@ __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__
         __threadfence();
         grid.sync();
     }
+    __threadfence();
+    grid.sync();                                                 // the first block's unknowns (written by CTA 0) are visible to every CTA
     if (timed0) sc.ns[4] += gtime() - t_mark;
 }
 

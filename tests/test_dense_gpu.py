@@ -36,7 +36,7 @@ def spd(n, seed, spread=0.0):
     return (A + A.T) / 2
 
 
-@pytest.mark.parametrize("n", [6, 90, 128, 130, 200, 256, 300, 514, 1000, 1666])
+@pytest.mark.parametrize("n", [6, 90, 128, 130, 200, 256, 300, 514, 1000, 1666, 2604, 2976])
 def test_solution_and_factor_match_fp64(n):
     A = spd(n, n, spread=2.0)
     rng = np.random.default_rng(n + 1)
@@ -64,7 +64,7 @@ def test_tier_size_reduced_system():
     assert ok == 1
     xr = np.linalg.solve(A, b)
     assert np.linalg.norm(x - xr) / np.linalg.norm(xr) < 1e-9
-    print("dense solve n=2988 phases (us): diag %.0f panel %.0f update %.0f barriers %.0f back-substitution %.0f; inside diag: sub-factor %.0f rows %.0f update %.0f; update epilogue warp: wait %.0f combine %.0f store %.0f" % tuple(v / 1e3 for v in ns[:11]))
+    print("dense solve n=2988 phases (us): diag %.0f panel %.0f update %.0f barriers %.0f back-substitution %.0f; inside diag: sub-factor %.0f rows %.0f update %.0f; update epilogue warp: wait %.0f (-) %.0f store %.0f; whole kernel %.0f" % tuple(v / 1e3 for v in list(ns[:11]) + [ns[15]]))
 
 
 def test_not_positive_definite_is_reported():
