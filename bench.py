@@ -297,6 +297,33 @@ def bind_to_gpu_numa_node(gpu):
     return None
 
 
+def copy_ceiling(h2d_bytes, d2h_bytes, chunks, steps, barrier):
+    """Bare copy ceiling of the end-to-end path: the same bytes per step as the pipelined front-end moves (frames host -> device,
+    results device -> host, pinned buffers, in `chunks` pieces each, the two directions on their own streams) with NO kernel between
+    them. Every rank runs it at the same time, so the N-rank figure is what the box's PCIe / host-memory fabric gives all GPUs at once.
+    Returns seconds per step (host clock, device idle at both ends)."""
+    import torch
+    hin = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory(); din = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    hout = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory(); dout = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    ci, co = h2d_bytes // chunks, d2h_bytes // chunks
+
+    def step():
+        for k in range(chunks):
+            with torch.cuda.stream(s_in):
+                din[k * ci:(k + 1) * ci].copy_(hin[k * ci:(k + 1) * ci], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hout[k * co:(k + 1) * co].copy_(dout[k * co:(k + 1) * co], non_blocking=True)
+    for _ in range(3):
+        step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / steps
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -434,6 +461,11 @@ def run_ours(args):
     cap = fe_host.capacity
     h2d = B * W * H
     d2h = B * (cap * (28 + 32 + 12) + 8)
+    # the copies alone, all ranks at once: what the end-to-end figure can reach on this box at this N
+    tc = torch.tensor([copy_ceiling(h2d, d2h, max(B // 32, 1), 50, barrier)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    copy_ceiling_value = world * B / float(tc.item())
 
     # ---- roofline of the dominant kernel from the per-kernel timing pass on the headline workload
     kern = kernel_times(dev_step, args.steps)
@@ -485,7 +517,9 @@ def run_ours(args):
                      "e2e_timer": "host clock around the whole loop of C-ABI calls, device idle at both ends", "numa_node": numa,
                      "e2e_mode": "pipelined mage_frontend_submit / _wait, two calls in flight, pinned host buffers; e2e.sync = the plain synchronous mage_frontend_process"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "sync": e2e_sync_value},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "sync": e2e_sync_value,
+                    "copy_ceiling": {"value": copy_ceiling_value, "unit": UNIT, "frac": e2e_value / copy_ceiling_value, "aggregate_GBps": (h2d + d2h) * copy_ceiling_value / B / 1e9,
+                                     "note": "the step's host<->device copies alone (same bytes, pinned buffers, both directions concurrently, no kernels), all ranks at once, max over ranks"}},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline}
 
@@ -600,7 +634,10 @@ def bench_ba(args, world, rank, dist):
     hbm, peak_src = peaks()
     # one lambda trial of this window = 9.5 MFLOP (FP64) and 0.6 MB of algorithmic traffic
     trial_rate = ntrials / float(t.item())
-    fp64_peak = 35.0        # TFLOP/s, FP64 FMA pipe measured on this pool's B200 with tools/fp64_peak.cu (profiles/README.md)
+    pp = pipe_peaks()
+    fp64_peak = pp["fp64_tflops"]        # FP64 FMA pipe measured on this pool's B200 (tools/fp64_peak.cu -> profiles/pipe_peaks.json)
+    tj = profile_counters()
+    ba_traffic = (tj or {}).get("ba", {}).get("k_ba_step_bytes_per_trial")       # ncu DRAM bytes of the batched kernel / (windows x trials)
     out = {"metric": "local_ba_lm_iters_per_sec", "unit": "LM iterations/s", "value": world * iters / float(t.item()),
            "config": {"workload": "local BA 10 KF / 2000 pts / 8000 obs, Huber 1.8, 10 LM iterations per call", "problems_per_gpu": nprob,
                       "mode": "batched: one CTA per problem, one persistent launch per call", "timer": "host clock around the synchronous C-ABI call, median of 5 fresh sets"},
@@ -608,10 +645,10 @@ def bench_ba(args, world, rank, dist):
                               "fresh_window_ms": 1e3 * statistics.median(fresh),
                               "fresh_window_note": "new BundlerLib instance: bulk set-up + structure build + 10 LM iterations + read-back of the mean error, host clock"},
            "roofline": {"kernel": "k_ba_step", "bound": "hbm", "achieved": trial_rate * 0.6e6 / 1e9, "peak": hbm, "unit": "GB/s",
-                        "frac": trial_rate * 0.6e6 / 1e9 / hbm, "traffic": 3.47e6, "traffic_unit": "bytes per lambda trial and problem (ncu, profiles/)",
+                        "frac": trial_rate * 0.6e6 / 1e9 / hbm, "traffic": ba_traffic, "traffic_unit": "bytes per lambda trial and problem (ncu capture of the batched kernel, %s)" % ((tj or {}).get("file", "-")),
                         "peak_source": peak_src, "algorithmic_bytes_per_trial": 0.6e6,
                         "fp64": {"achieved": trial_rate * 9.5e6 / 1e12, "peak": fp64_peak, "unit": "TFLOP/s", "frac": trial_rate * 9.5e6 / 1e12 / fp64_peak,
-                                 "flop_per_trial": 9.5e6},
+                                 "flop_per_trial": 9.5e6, "peak_source": pp.get("source")},
                         "note": "bound by the L1/shared-memory data path and load latency at 16 warps/SM (ncu: L1TEX 66 %, IPC 0.9, FP64 pipe 23 % busy, DRAM 28 %)"},
            "dtype": "f64"}
     if rank == 0 and world == 1:
@@ -661,8 +698,24 @@ def bench_global_ba(args):
         _lib = __import__("mageslam_b200._lib", fromlist=["lib"])
         _lib.lib().mage_ba_debug_phase_ns(gpu._h, ph.ctypes.data_as(C.c_void_p))
         steps = max(st["lm_iterations"], 1)
-        out["phase_ms_per_step"] = {"dense_solve": float(ph[4]) / 1e6 / steps, "ldlt_diag": float(ph[9]) / 1e6 / steps, "ldlt_panel": float(ph[10]) / 1e6 / steps,
-                                    "ldlt_update": float(ph[11]) / 1e6 / steps, "ldlt_barriers": float(ph[12]) / 1e6 / steps}
+        out["phase_ms_per_step"] = {"schur_products": float(ph[3]) / 1e6 / steps, "dense_solve": float(ph[4]) / 1e6 / steps,
+                                    "ldlt_diagonal_blocks": float(ph[9]) / 1e6 / steps, "ldlt_panel_rows": float(ph[10]) / 1e6 / steps,
+                                    "ldlt_tensor_update_issue": float(ph[11]) / 1e6 / steps, "ldlt_tensor_update_drain_and_barriers": float(ph[12]) / 1e6 / steps,
+                                    "back_substitution": float(ph[13]) / 1e6 / steps, "note": "as CTA 0 sees them (in-kernel %globaltimer)"}
+        # the trailing updates of the blocked LDL^T run on tcgen05 (kind::i8, exact 8 x 7-bit slices, 36 slice pairs x 4 K steps of
+        # 128 x 64 x 32 per 128 x 64 tile): int8 operations per factorisation over the time of the update phases
+        tiles = 0
+        for k0 in range(0, n, 128):
+            r0 = k0 + 128
+            if r0 >= n:
+                break
+            nt128, nt64 = (n + 1 + 127) // 128, (n + 63) // 64
+            tiles += sum(min(2 * it + 1, nt64 - 1) - r0 // 64 + 1 for it in range(r0 // 128, nt128))
+        ops = tiles * 36 * 4 * (128 * 64 * 32) * 2.0
+        upd_s = (float(ph[11]) + float(ph[12])) / 1e9 / steps / max(trials_per_step, 1e-9)
+        out["roofline"]["tensor"] = {"kernel_phase": "dense LDL^T trailing update (tcgen05.mma kind::i8, Ozaki slices)", "achieved": ops / upd_s / 1e12, "peak": pp.get("int8_tops", 4500.0),
+                                     "unit": "Top/s", "frac": ops / upd_s / 1e12 / pp.get("int8_tops", 4500.0), "int8_ops_per_factorisation": ops, "tiles": tiles,
+                                     "peak_source": "nominal dense int8 figure (no measured int8 peak on this pool)"}
     except Exception:
         pass
     # CPU arm: one timed step of the compiled reference (about 1.4 s) after its own untimed first step, then parity of the two states

@@ -2985,9 +2985,12 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
         const bool cams_fit = h->dev.K <= kBaMaxSmemCams && coop_head + ba_smem_need_cams(h->dev.K) <= kCoopSmemMax;
         const size_t coop_smem = coop_head + (cams_fit ? ba_smem_need_cams(h->dev.K) : 0);
         // tether edges are handled by the single-CTA kernel only (windows with tethers are stereo / IMU local BA, never the global size)
-        MAGE_REQUIRE(!(h->dev.nT > 0 && h->dev.big), MAGE_ERR_UNSUPPORTED, "tether edges are not supported on problems with %d pose unknowns", h->dev.n);
+        // (stereo / IMU windows; the one-CTA kernel keeps reduced systems of up to 158 unknowns in its shared memory -- beyond that a window with
+        // tethers is not a case the reference produces)
+        const bool one_cta_fits = ba_smem_need_S(h->dev.n) <= 200 * 1024;
+        MAGE_REQUIRE(!(h->dev.nT > 0 && !one_cta_fits), MAGE_ERR_UNSUPPORTED, "tether edges are not supported on problems with %d pose unknowns", h->dev.n);
         const bool use_coop = h->dev.nT == 0 && h->coop_blocks > 1 && (cams_fit || h->dev.big) && coop_smem <= kCoopSmemMax && (h->dev.Ea >= 1024 || h->dev.big);
-        MAGE_REQUIRE(use_coop || !h->dev.big, MAGE_ERR_UNSUPPORTED, "reduced camera system of %d unknowns needs the cooperative kernel (not available)", h->dev.n);
+        MAGE_REQUIRE(use_coop || !h->dev.big || one_cta_fits, MAGE_ERR_UNSUPPORTED, "reduced camera system of %d unknowns needs the cooperative kernel (not available)", h->dev.n);
         // small systems: enough CTAs that every (reduced-system block, part) item of the Schur products gets its own warp in ONE round
         // (288 items on 32 CTAs = 256 warps ran a second, nearly empty round)
         int coop_grid = h->dev.big ? h->coop_blocks_max : h->coop_blocks;

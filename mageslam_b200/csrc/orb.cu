@@ -1622,15 +1622,16 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pyr, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_blur, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error("mage_orb_create: %s", cudaGetErrorString(e)); A.release(); delete h; return MAGE_ERR_CUDA; }
-    {   // TMA path of FAST: opt-in (MAGE_FAST_TMA=1). Measured on B200 it is correct but 16 % slower than the register-staged kernel
-        // (0.707 vs 0.610 ms per 128 frames: 3 instead of 4 CTAs per SM and an extra shared-to-shared pass on an ALU-bound kernel), DESIGN.md 5
+    {   // TMA path of FAST: the default (MAGE_FAST_TMA=0 selects the register-staged kernel). One bulk tensor load per CTA brings the
+        // tile's box in (zero fill outside the image by the tensor map); on B200 the two kernels are within 1.5 % of each other
+        // (0.422 vs 0.416 ms per 128 frames on the chart scene, 0.293 vs 0.289 ms on camera-like frames): the kernel is ALU-bound
         const char* env = getenv("MAGE_FAST_TMA");
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaDriverEntryPointQueryResult qres;
         void* fn = nullptr;
-        if (env && atoi(env) != 0 && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        if ((!env || atoi(env) != 0) && cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
             qres == cudaDriverEntryPointSuccess && fn) {
             h->encode_fn = fn;
             bool ok = cudaFuncSetAttribute((const void*)kFastVariants[h->fast_variant].kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmemBytes) == cudaSuccess;
