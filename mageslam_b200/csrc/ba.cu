@@ -56,6 +56,7 @@ struct BaDev {
     int big;
     int8_t* Zq;                               // int8 slice planes of the current panel (dense_ldlt.cuh)
     double* Ldiag;                            // factored diagonal blocks of the reduced system (dense_ldlt.cuh)
+    int* dflag;                               // look-ahead counter of the dense solver (dense_ldlt.cuh)
     int* Ez;                                  // row exponents of the slices
     // tether edges between two cameras (ref BundlerLib.cpp:24-90, :311-350), single-CTA kernel only
     int nT;
@@ -2215,7 +2216,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
                 if (blockIdx.x == 0) { phase_finish_bs(p, tid, nt); if (tid == 0) ctl->last_ok = 1; }
                 grid.sync();
                 PH(8);
-                const dense::Scratch dsc = {p.Zq, p.Ez, p.Ldiag, p.bs, ctl->phase_ns + 9};
+                const dense::Scratch dsc = {p.Zq, p.Ez, p.Ldiag, p.dflag, p.bs, ctl->phase_ns + 9};
                 dense::ldlt_grid(grid, p.S, p.n, dsc, dyn, &ctl->last_ok);           // factorisation + forward substitution of bs
                 grid.sync();
                 if (*reinterpret_cast<volatile int*>(&ctl->last_ok)) {                                  // uniform: written before the grid barrier
@@ -2653,7 +2654,7 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
     size_t o_Zq = W.reserve(big ? dense::scratch_zq_bytes(n) : 16, 1024), o_Ez = rI(big ? dense::scratch_ez_count(n) : 1);
-    size_t o_Ldiag = W.reserve(big ? dense::scratch_ldiag_bytes(n) : 16, 256);
+    size_t o_Ldiag = W.reserve(big ? dense::scratch_ldiag_bytes(n) : 16, 256), o_dflag = rI(1);
     size_t o_tdef = W.reserve(sizeof(int4) * std::max(nT, 1)), o_tmeas = rD(8 * (size_t)nT), o_terr = rD(6 * (size_t)nT), o_tJ = rD(72 * (size_t)nT);
     MAGE_CUDA_TRY(W.commit());
     mark("cudaMalloc");
@@ -2694,7 +2695,7 @@ static int ba_build_structure(mage_ba_t h)
     d.cam_diag = W.at<int>(o_cdiag); d.bb_ptr = W.at<int>(o_bbptr); d.bpairs = W.at<ushort2>(o_bpairs);
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
-    d.big = big; d.Zq = W.at<int8_t>(o_Zq); d.Ez = W.at<int>(o_Ez); d.Ldiag = W.at<double>(o_Ldiag);
+    d.big = big; d.Zq = W.at<int8_t>(o_Zq); d.Ez = W.at<int>(o_Ez); d.Ldiag = W.at<double>(o_Ldiag); d.dflag = W.at<int>(o_dflag);
     d.nT = nT; d.t_def = W.at<int4>(o_tdef); d.t_meas = W.at<double>(o_tmeas); d.t_err = W.at<double>(o_terr); d.t_J = W.at<double>(o_tJ);
     MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
     mark("enqueue uploads");
@@ -3183,7 +3184,7 @@ extern "C" int mage_dense_debug_solve(int n, const double* A, const double* b, d
     DeviceArena W;
     const size_t o_S = W.reserve(sizeof(double) * (size_t)n * n), o_y = W.reserve(sizeof(double) * n), o_zq = W.reserve(dense::scratch_zq_bytes(n), 1024);
     const size_t o_ez = W.reserve(sizeof(int) * dense::scratch_ez_count(n)), o_ok = W.reserve(sizeof(int)), o_ns = W.reserve(sizeof(long long) * 16);
-    const size_t o_ld = W.reserve(dense::scratch_ldiag_bytes(n), 256);
+    const size_t o_ld = W.reserve(dense::scratch_ldiag_bytes(n), 256), o_fl = W.reserve(sizeof(int));
     MAGE_CUDA_TRY(W.commit());
     cudaError_t e = cudaMemset(W.base, 0, W.size);
     if (e == cudaSuccess) e = cudaMemcpy(W.base + o_S, A, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice);
@@ -3194,7 +3195,7 @@ extern "C" int mage_dense_debug_solve(int n, const double* A, const double* b, d
     if (e == cudaSuccess) {
         double* dS = W.at<double>(o_S); double* dy = W.at<double>(o_y); int* dok = W.at<int>(o_ok);
         // MAGE_DENSE_NO_TIMERS=1: no in-kernel phase timers (reading %globaltimer costs the timed thread about a microsecond each time)
-        dense::Scratch sc = {W.at<int8_t>(o_zq), W.at<int>(o_ez), W.at<double>(o_ld), dy, getenv("MAGE_DENSE_NO_TIMERS") ? nullptr : W.at<long long>(o_ns)};
+        dense::Scratch sc = {W.at<int8_t>(o_zq), W.at<int>(o_ez), W.at<double>(o_ld), W.at<int>(o_fl), dy, getenv("MAGE_DENSE_NO_TIMERS") ? nullptr : W.at<long long>(o_ns)};
         int nn = n;
         void* args[] = {(void*)&dS, (void*)&nn, (void*)&dy, (void*)&sc, (void*)&dok};
         cudaEvent_t ev0, ev1;

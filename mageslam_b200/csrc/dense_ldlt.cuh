@@ -40,6 +40,7 @@ constexpr int LTP = NB + 2;                   // row pitch (doubles) of the tran
 constexpr int kMinExp = 1023 - 400;           // rows whose largest |z| is below 2^-400 contribute nothing
 constexpr size_t kSmemUpdate = (size_t)SL * PLANE + (size_t)SL * BPLANE + TN * sizeof(double);
 constexpr size_t kSmemTrsm = sizeof(double) * ((size_t)NB * LTP + 2 * NB + 32 * 96 + 128);
+constexpr int kPack = NB * LTP + 2 * NB;      // doubles of one factored diagonal block as it is published: Lt, then 1 / D, then 1 / sqrt(D)
 constexpr size_t kSmemBytes = (kSmemUpdate > kSmemTrsm ? kSmemUpdate : kSmemTrsm) + 1024;     // + slack to align the base to 1 KB
 // instruction descriptor (kind::i8): D = s32, A and B signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -49,7 +50,8 @@ constexpr uint32_t kSBO = 1024;               // operand planes are K-major rows
 struct Scratch {
     int8_t* Zq;       // [row tiles of 128][SL][PLANE] over n + 1 rows; rows > n are never written and stay zero
     int* Ez;          // [row tiles * 128] exponent E of the row: z = z' 2^E, |z'| < 1
-    double* Ldiag;    // [panels][NB * LTP] the factored diagonal blocks, column-major
+    double* Ldiag;    // [panels][kPack] the factored diagonal blocks (column-major, pitch LTP) with 1 / D and 1 / sqrt(D) behind each
+    int* flag;        // counts the update tiles that cover the next diagonal blocks (zero at kernel start; see ldlt_grid)
     double* ytmp;     // [n] right-hand side in, solution out (16-byte aligned; may be the caller's vector)
     long long* ns;    // optional [16] phase timers written by CTA 0: diag, panel, update, barriers, solve, ... (null: off)
 };
@@ -172,7 +174,7 @@ __device__ __forceinline__ void load_diag_block(const double* __restrict__ A, in
 #pragma unroll
         for (int r = 0; r < 32; r++) {
             const int i = 32 * tr + r;
-            v[r] = (i < nb && c <= i) ? A[(size_t)i * ld + c] : (i == c ? 1.0 : 0.0);          // coalesced along the row
+            v[r] = (i < nb && c <= i) ? __ldcg(A + (size_t)i * ld + c) : (i == c ? 1.0 : 0.0);          // coalesced along the row
         }
         double* dst = Lt + c * LTP + 32 * tr;
 #pragma unroll
@@ -180,13 +182,13 @@ __device__ __forceinline__ void load_diag_block(const double* __restrict__ A, in
     }
 }
 
-__device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ invD, double* __restrict__ rsD, double* __restrict__ Yt, int nb, int* s_bad, long long* ns)
+__device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ invD, double* __restrict__ rsD, double* __restrict__ Yt, int nb, int* s_bad, long long* ns, bool timed_cta)
 {
     double* colb = Yt + 32 * YP;                                // [2][64] column exchange of the sub-block factorisation, upper halves zero
     if (threadIdx.x < 128) colb[threadIdx.x] = 0.0;
     __syncthreads();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool timed = ns && blockIdx.x == 0 && tid == 0;       // reading %globaltimer is slow and serialises across the chip: one thread only
+    const bool timed = ns && timed_cta && tid == 0;             // reading %globaltimer is slow and serialises across the chip: one thread only
     long long tm = timed ? gtime() : 0;
     auto lap = [&](int slot) { if (timed) { const long long t = gtime(); ns[slot] += t - tm; tm = t; } };
     for (int j0 = 0; j0 < nb; j0 += 32) {
@@ -201,16 +203,20 @@ __device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ i
             for (int c = 0; c < 32; c++) a[c] = c <= lane ? Lt[(j0 + c) * LTP + j0 + lane] : 0.0;
             bool bad = false;
             double mine = 1.0;
+            // software pipeline: column k + 1 is published (and its pivot's reciprocal started) right after the first update of
+            // column k has produced it, so the reciprocal's latency runs under the other 30 updates of column k
+            colb[lane] = a[0];
+            __syncwarp();
+            double d = colb[0];
+            double inv = fabs(d) > 0 ? rcp_pos(d) : 0.0;
 #pragma unroll 1
             for (int kw = 0; kw < 32; kw += 4) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const int k = kw + u;
                     const double ck = a[u];
-                    double* cb = colb + (u & 1) * 64;            // [2][64]: the upper halves stay zero (reads of a window past column 31)
-                    cb[lane] = ck;
-                    __syncwarp();
-                    const double d = cb[k];
+                    const double* cb = colb + (u & 1) * 64;      // [2][64]: the upper halves stay zero (reads of a window past column 31)
+                    double* cbn = colb + ((u + 1) & 1) * 64;
                     double cj[32];                                // A(k + t - u, k), t > u
                     if ((u + 1) & 1) cj[u + 1] = cb[kw + u + 1];
 #pragma unroll
@@ -219,12 +225,17 @@ __device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ i
                         cj[t] = c2.x; cj[t + 1] = c2.y;
                     }
                     if (!(d > 0)) bad = true;
-                    const double inv = fabs(d) > 0 ? rcp_pos(d) : 0.0;
                     const double l = ck * inv;
+                    a[u + 1] -= l * cj[u + 1];                     // A(i, k + 1) -= L(i, k) A(k + 1, k): the next column
+                    cbn[lane] = a[u + 1];
+                    __syncwarp();
+                    const double dn = cbn[k + 1];                  // (past column 31: the zero half)
+                    const double invn = fabs(dn) > 0 ? rcp_pos(dn) : 0.0;
 #pragma unroll
-                    for (int t = u + 1; t < 32; t++) a[t] -= l * cj[t];          // A(i, j) -= L(i, k) A(j, k)
+                    for (int t = u + 2; t < 32; t++) a[t] -= l * cj[t];          // A(i, j) -= L(i, k) A(j, k)
                     if (lane == k) mine = d;
                     if (lane >= k) Lt[(j0 + k) * LTP + j0 + lane] = lane == k ? d : l;
+                    d = dn; inv = invn;
                 }
 #pragma unroll
                 for (int t = 0; t < 28; t++) a[t] = a[t + 4];
@@ -391,8 +402,11 @@ __device__ __forceinline__ void panel_rows_R(double* __restrict__ S, int n, int 
             uint32_t w = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int q = __double2int_rn(t[j]);
-                t[j] = (t[j] - (double)q) * 128.0;
+                // round to nearest by adding 1.5 * 2^52: the integer is the sum's low word, its FP64 value the sum minus the constant
+                // (the F2I / I2F instructions run at a tenth of the FP64 add rate)
+                const double m = t[j] + 6755399441055744.0;
+                const int q = __double2loint(m);
+                t[j] = (t[j] - (m - 6755399441055744.0)) * 128.0;
                 w |= ((uint32_t)q & 0xffu) << (8 * j);
             }
             *reinterpret_cast<uint32_t*>(dst + (size_t)s * PLANE) = w;
@@ -425,23 +439,32 @@ __device__ __forceinline__ int tiles_of_row(int it, int jt0, int nt64) { return 
 // ---- (c) A_ij -= Z_i . Z_j over the trailing tiles (rows >= r0; 128 x 64 tiles of the lower triangle), contiguous chunks per CTA.
 // warp 0 lane 0 loads, warp 1 lane 0 issues the MMAs, warps 4-7 read the accumulators back and update A. `done` counts the tiles
 // this CTA has processed since the barriers were initialised (their phase parities).
-__device__ void update_tiles(double* __restrict__ S, int n, int ntot, int r0, const Scratch& sc, uint8_t* smem, UpdateShared& us, int& done)
+__device__ void update_tiles(double* __restrict__ S, int n, int ntot, int r0, const Scratch& sc, uint8_t* smem, UpdateShared& us, int& done, int worker, int nworkers)
 {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nt128 = (ntot + TM - 1) / TM, nt64 = (n + TN - 1) / TN, it0 = r0 / TM, jt0 = r0 / TN;
     int total = 0;
     for (int it = it0; it < nt128; it++) total += tiles_of_row(it, jt0, nt64);
-    const int chunk = (total + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int lo = min(total, (int)blockIdx.x * chunk), hi = min(total, lo + chunk);
-    if (lo >= hi) return;
-    int it = it0, off = lo;                                     // first tile of the chunk
-    while (off >= tiles_of_row(it, jt0, nt64)) { off -= tiles_of_row(it, jt0, nt64); it++; }
-    int jt = jt0 + off;
+    const int chunk = (total + nworkers - 1) / nworkers;
+    // contiguous chunks of the tile list (a row tile's operand planes are reused along the chunk), except that the first two tiles
+    // -- they cover the next diagonal block, which the factor CTA is waiting for -- open the chunks of two different workers:
+    // worker 0 takes tiles 0, 2 .. chunk, worker 1 takes 1, chunk + 1 .. 2 chunk - 1, worker w >= 2 takes [w chunk, (w + 1) chunk)
+    const bool split = chunk >= 2 && nworkers >= 2;
+    int first, lo, hi;                                          // the worker's tiles: `first` (if >= 0), then [lo, hi)
+    if (split && worker == 0) { first = 0; lo = 2; hi = min(total, chunk + 1); }
+    else if (split && worker == 1) { first = 1; lo = chunk + 1; hi = min(total, 2 * chunk); }
+    else { first = -1; lo = min(total, worker * chunk); hi = min(total, lo + chunk); }
+    const int mine = (first >= 0 ? 1 : 0) + max(hi - lo, 0);
+    if (mine == 0) return;
     const uint32_t sA = saddr(smem), sB = sA + SL * PLANE;
     double* colscale = reinterpret_cast<double*>(smem + (size_t)SL * PLANE + (size_t)SL * BPLANE);
     const uint32_t tmem = us.tmem;
     int last_it = -1;
-    for (int tile = lo; tile < hi; tile++) {
+    for (int i = 0; i < mine; i++) {
+        const int tile = first >= 0 ? (i == 0 ? first : lo + i - 1) : lo + i;
+        int it = it0, off = tile;                               // row tile / column tile of the linear tile index
+        while (off >= tiles_of_row(it, jt0, nt64)) { off -= tiles_of_row(it, jt0, nt64); it++; }
+        const int jt = jt0 + off;
         const uint32_t par = (uint32_t)done & 1u, prev = par ^ 1u;
         if (warp == 0) {
             if (lane == 0) {
@@ -562,10 +585,14 @@ __device__ void update_tiles(double* __restrict__ S, int n, int ntot, int r0, co
                 if (timed) ts += gtime() - t0;
             }
             if (timed) { sc.ns[8] += tw; sc.ns[10] += ts; }
+            if (it == it0 && jt <= jt0 + 1) {                      // a tile of the next diagonal block is in memory: tell the factor CTA
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid == 128) atomicAdd(sc.flag, 1);
+            }
         }
         last_it = it;
         done++;
-        if (++jt > min(2 * it + 1, nt64 - 1)) { it++; jt = jt0; }
     }
 }
 
@@ -610,16 +637,35 @@ __device__ void ldlt_grid(cg::grid_group& grid, double* __restrict__ S, int n, c
     double* rsD = invD + NB;
     double* Yt = rsD + NB;
     int done = 0;
+    // Look-ahead: the last CTA of the grid takes no update tiles. While the others run the trailing update of panel k it waits for
+    // the (at most two) tiles that cover the NEXT diagonal block -- the first ones in worker 0's chunk; their writers count them
+    // in sc.flag --, factors that block and publishes it; after the grid barrier everybody copies the factored block into shared
+    // memory instead of factoring it. Only the first diagonal block is factored by every CTA (nothing to overlap it with).
+    const bool lookahead = gridDim.x >= 8;
+    const bool factor_cta = lookahead && blockIdx.x == gridDim.x - 1;
+    const int nworkers = lookahead ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const int flag0 = lookahead && tid == 0 ? *reinterpret_cast<volatile int*>(sc.flag) : 0;      // the counter runs on across the calls of one launch
+    int expected = 0;
+    auto publish = [&](int kb) {                                 // Lt, 1 / D, 1 / sqrt(D) of the block just factored -> sc.Ldiag[kb]
+        double2* dst = reinterpret_cast<double2*>(sc.Ldiag + (size_t)kb * kPack);
+        const double2* src = reinterpret_cast<const double2*>(Lt);
+        for (int i = tid; i < kPack / 2; i += nt) dst[i] = src[i];
+        if (tid == 0 && s_bad) *okflag = 0;
+    };
     for (int k0 = 0; k0 < n; k0 += NB) {
         const int nb = min(NB, n - k0);
-        load_diag_block(S + (size_t)k0 * n + k0, n, nb, Lt);       // (a)
-        __syncthreads();
-        factor_diag_smem(Lt, invD, rsD, Yt, nb, &s_bad, sc.ns);
-        if (blockIdx.x == 0) {                                   // one CTA publishes the factored block (the substitution reads it back)
-            double2* dst = reinterpret_cast<double2*>(sc.Ldiag + (size_t)(k0 / NB) * NB * LTP);
-            const double2* src = reinterpret_cast<const double2*>(Lt);
-            for (int i = tid; i < NB * LTP / 2; i += nt) dst[i] = src[i];
-            if (tid == 0 && s_bad) *okflag = 0;
+        if (k0 == 0 || !lookahead) {                             // (a) every CTA factors the block (same arithmetic, same result)
+            load_diag_block(S + (size_t)k0 * n + k0, n, nb, Lt);
+            __syncthreads();
+            factor_diag_smem(Lt, invD, rsD, Yt, nb, &s_bad, sc.ns, blockIdx.x == 0);
+            if (blockIdx.x == 0) publish(k0 / NB);
+        } else {                                                 // (a') factored during the previous update phase
+            const double2* src = reinterpret_cast<const double2*>(sc.Ldiag + (size_t)(k0 / NB) * kPack);
+            const uint32_t dst = saddr(Lt);
+            for (int i = tid; i < kPack / 2; i += nt) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
         }
         lap(0);
         panel_rows(S, n, ntot, k0, nb, sc, Lt, invD, rsD, gwarp, gnw, lane);      // (b)
@@ -629,8 +675,27 @@ __device__ void ldlt_grid(cg::grid_group& grid, double* __restrict__ S, int n, c
         if (r0 >= n) break;
         grid.sync();
         lap(3);
-        asm volatile("fence.proxy.async;" ::: "memory");          // the planes other CTAs stored become visible to this CTA's bulk copies
-        update_tiles(S, n, ntot, r0, sc, smem, us, done);          // (c)
+        if (factor_cta) {
+            const int nbn = min(NB, n - r0), nt64 = (n + TN - 1) / TN, jt0 = r0 / TN;
+            expected += min(jt0 + 1, nt64 - 1) - jt0 + 1;         // tiles (row tile r0 / 128, column tiles jt0, jt0 + 1) of this update
+            const bool timedf = sc.ns && tid == 0;
+            long long f0 = timedf ? gtime() : 0;
+            if (tid == 0) {
+                int seen;
+                do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(sc.flag) : "memory"); } while (seen - flag0 < expected);
+            }
+            __syncthreads();
+            __threadfence();
+            if (timedf) { const long long t = gtime(); sc.ns[14] += t - f0; f0 = t; }
+            load_diag_block(S + (size_t)r0 * n + r0, n, nbn, Lt);
+            __syncthreads();
+            factor_diag_smem(Lt, invD, rsD, Yt, nbn, &s_bad, sc.ns, true);
+            publish(r0 / NB);
+            if (timedf) sc.ns[9] += gtime() - f0;
+        } else {
+            asm volatile("fence.proxy.async;" ::: "memory");      // the planes other CTAs stored become visible to this CTA's bulk copies
+            update_tiles(S, n, ntot, r0, sc, smem, us, done, (int)blockIdx.x, nworkers);          // (c)
+        }
         __threadfence();
         lap(2);
         grid.sync();
@@ -658,7 +723,7 @@ __device__ void export_diag_blocks(double* __restrict__ S, int n, const Scratch&
     const int nblk = (n + NB - 1) / NB;
     for (int i = gtid; i < nblk * NB * NB; i += gnt) {
         const int kb = i / (NB * NB), r = (i / NB) % NB, c = i % NB;
-        if (c <= r && kb * NB + r < n) S[(size_t)(kb * NB + r) * n + kb * NB + c] = sc.Ldiag[(size_t)kb * NB * LTP + c * LTP + r];
+        if (c <= r && kb * NB + r < n) S[(size_t)(kb * NB + r) * n + kb * NB + c] = sc.Ldiag[(size_t)kb * kPack + c * LTP + r];
     }
 }
 
@@ -679,7 +744,7 @@ __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__
     const long long t_mark = timed0 ? gtime() : 0;
     auto fetch_block = [&](int k0) {                             // Ldiag[k0 / NB] -> T, asynchronously
         const int nb = min(NB, n - k0), cnt = ((nb + 31) & ~31) * LTP / 2;
-        const double2* src = reinterpret_cast<const double2*>(sc.Ldiag + (size_t)(k0 / NB) * NB * LTP);
+        const double2* src = reinterpret_cast<const double2*>(sc.Ldiag + (size_t)(k0 / NB) * kPack);
         const uint32_t dst = saddr(T);
         for (int i = tid; i < cnt; i += nt) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + i) : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -757,7 +822,7 @@ __device__ void solve_back_grid(cg::grid_group& grid, const double* __restrict__
 
 inline size_t scratch_zq_bytes(int n) { return (size_t)((n + 1 + TM - 1) / TM) * SL * PLANE; }
 inline size_t scratch_ez_count(int n) { return (size_t)((n + 1 + TM - 1) / TM) * TM; }
-inline size_t scratch_ldiag_bytes(int n) { return (size_t)((n + NB - 1) / NB) * NB * LTP * sizeof(double); }
+inline size_t scratch_ldiag_bytes(int n) { return (size_t)((n + NB - 1) / NB) * kPack * sizeof(double); }
 
 } // namespace dense
 } // namespace mage
