@@ -2838,6 +2838,7 @@ static int ba_alloc_tethers(mage_ba_t h, int pool, int count, const char* who)
 {
     MAGE_REQUIRE(h && count >= 0, MAGE_ERR_INVALID, "%s: bad argument", who);
     h->teth[pool].assign(count, HostTether());
+    h->dirty = true;                     // edges set before a re-allocation are gone: the device structure is rebuilt at the next step
     return MAGE_OK;
 }
 extern "C" int mage_ba_alloc_fixed_distance_constraints(mage_ba_t h, int count) { return ba_alloc_tethers(h, 0, count, "mage_ba_alloc_fixed_distance_constraints"); }
@@ -3030,6 +3031,11 @@ extern "C" int mage_ba_last_outlier_counts(mage_ba_t* hs, int n, int* counts)
 extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n_iters, float max_err_sq, float* means)
 {
     MAGE_REQUIRE(hs && n >= 1 && means && (huber || n_iters == 0), MAGE_ERR_INVALID, "mage_ba_step_many: bad argument");
+    {   // a handle listed twice would be stepped by two CTAs at once
+        std::vector<mage_ba_t> seen(hs, hs + n);
+        std::sort(seen.begin(), seen.end());
+        MAGE_REQUIRE(std::adjacent_find(seen.begin(), seen.end()) == seen.end(), MAGE_ERR_INVALID, "mage_ba_step_many: the same handle is listed twice");
+    }
     // gather the per-problem descriptors into one table and step every problem with ONE launch (grid = problems)
     std::vector<BaDev> table;
     std::vector<int> live;

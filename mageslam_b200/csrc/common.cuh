@@ -1,5 +1,6 @@
 // Shared helpers for the sm_100a kernels and their C-ABI wrappers.
 #pragma once
+#include <mutex>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdint>
@@ -32,22 +33,42 @@ void set_error(const char* fmt, ...);
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
-// Raise the default stream-ordered pool's release threshold once, so blocks freed with cudaFreeAsync stay cached across synchronisations
-// (the default threshold of 0 hands them back to the driver at the next sync and every cudaMallocAsync pays a fresh allocation).
-inline void pool_keep_cached()
+// The library's OWN stream-ordered memory pool of the current device (created on first use, one per device, release threshold at the
+// maximum so blocks freed with cudaFreeAsync stay cached across synchronisations). The host application's default pool is left
+// alone: raising ITS threshold would change how the application's own cudaFreeAsync behaves. nullptr when the device / driver has no
+// stream-ordered allocator.
+inline cudaMemPool_t library_pool()
 {
-    static bool pool_ready = false;
-    if (pool_ready) return;
-    int dev = 0; cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    pool_ready = true;
+    constexpr int kMaxDev = 64;
+    static cudaMemPool_t pools[kMaxDev] = {};
+    static std::once_flag once[kMaxDev];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    std::call_once(once[dev], [dev]() {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        cudaMemPool_t pool = nullptr;
+        if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            pools[dev] = pool;
+        } else cudaGetLastError();
+    });
+    return pools[dev];
 }
 
-// One device allocation carved into aligned sub-buffers. pooled = true takes it from the stream-ordered default memory pool
-// (cudaMallocAsync, release threshold raised so freed blocks stay cached): a few microseconds instead of the ~1-4 ms cudaFree +
+// Stream-ordered allocation from the library's pool (the default pool, untouched, when the private one could not be created).
+inline cudaError_t pool_malloc_async(void** ptr, size_t bytes, cudaStream_t s)
+{
+    cudaMemPool_t pool = library_pool();
+    return pool ? cudaMallocFromPoolAsync(ptr, bytes, pool, s) : cudaMallocAsync(ptr, bytes, s);
+}
+
+// One device allocation carved into aligned sub-buffers. pooled = true takes it from the library's stream-ordered memory pool
+// (cudaMallocFromPoolAsync, release threshold raised so freed blocks stay cached): a few microseconds instead of the ~1-4 ms cudaFree +
 // cudaMalloc of a multi-megabyte block cost when a new problem is set up per call (a BundlerLib instance per local-BA window).
 // A pooled arena must only be released when the work using it has been synchronised (cudaFreeAsync does not wait like cudaFree).
 struct DeviceArena {
@@ -59,8 +80,8 @@ struct DeviceArena {
     {
         size = used;
         if (!pooled) return cudaMalloc(&base, size ? size : 256);
-        pool_keep_cached();
-        cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&base), size ? size : 256, static_cast<cudaStream_t>(0));
+        cudaMemPool_t pool = library_pool();
+        cudaError_t e = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void**>(&base), size ? size : 256, pool, static_cast<cudaStream_t>(0)) : cudaErrorNotSupported;
         if (e == cudaSuccess) return cudaStreamSynchronize(static_cast<cudaStream_t>(0));    // usable from any stream afterwards
         cudaGetLastError();                                    // no stream-ordered pool on this device / driver: plain allocation
         pooled = false; base = nullptr;

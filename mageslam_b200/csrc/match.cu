@@ -176,15 +176,23 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
                  ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(kUmmaIdesc), "r"(accumulate), "r"(0u) : "memory");
 }
 
-// bounded wait on an mbarrier phase: a descriptor mistake must end in a trap, not in a hung device
+// bounded wait on an mbarrier phase: a descriptor mistake must end in a trap, not in a hung device. The bound is TIME (ten seconds of
+// %globaltimer, looked at every 64 K polls), not a poll count: under time-slicing, a debugger or a profiler's replay a correct kernel
+// may poll for a long while, and a trap poisons the whole context.
 __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity)
 {
-    for (int spin = 0; spin < (1 << 24); spin++) {
+    long long t0 = 0;
+    for (unsigned spin = 0;; spin++) {
         uint32_t done;
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
         if (done) return;
+        if ((spin & 0xFFFFu) == 0xFFFFu) {
+            long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 10000000000ll) __trap();
+        }
     }
-    __trap();
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])

@@ -126,8 +126,7 @@ extern "C" int mage_project_map_points(const mage_projection_params* params, con
     const size_t o_pts = 0, o_kps = align_up(o_pts + sizeof(mage_map_point) * n, 256), o_dep = align_up(o_kps + sizeof(mage_keypoint) * n, 256);
     const size_t o_flg = align_up(o_dep + sizeof(float) * n, 256), total = o_flg + (size_t)n;
     uint8_t* d = nullptr;
-    pool_keep_cached();
-    MAGE_CUDA_TRY(cudaMallocAsync(&d, total, s));
+    MAGE_CUDA_TRY(pool_malloc_async(reinterpret_cast<void**>(&d), total, s));
     int rc = MAGE_OK;
     cudaError_t e = cudaMemcpyAsync(d + o_pts, points, sizeof(mage_map_point) * n, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {

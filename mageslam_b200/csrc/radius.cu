@@ -273,8 +273,7 @@ extern "C" int mage_radius_match(mage_spatial_index_s* ix, const mage_keypoint* 
         ix->free_scratch();
         ix->scratch_bytes = 0;
         // stream-ordered pool first (an index lives for one frame, so this allocation is per-frame latency), plain allocation otherwise
-        pool_keep_cached();
-        ix->scratch_pooled = cudaMallocAsync(reinterpret_cast<void**>(&ix->d_scratch), off, ix->stream) == cudaSuccess;
+        ix->scratch_pooled = pool_malloc_async(reinterpret_cast<void**>(&ix->d_scratch), off, ix->stream) == cudaSuccess;
         if (ix->scratch_pooled) MAGE_CUDA_TRY(cudaStreamSynchronize(ix->stream));
         else { cudaGetLastError(); MAGE_CUDA_TRY(cudaMalloc(&ix->d_scratch, off)); }
         ix->scratch_bytes = off;

@@ -99,8 +99,7 @@ extern "C" int mage_undistort_keypoints(mage_keypoint* keypoints, int n, const m
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: keypoint undistortion has no CPU fallback"); return MAGE_ERR_CUDA; }
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     mage_keypoint* d = nullptr;
-    pool_keep_cached();
-    MAGE_CUDA_TRY(cudaMallocAsync(&d, sizeof(mage_keypoint) * (size_t)n, s));
+    MAGE_CUDA_TRY(pool_malloc_async(reinterpret_cast<void**>(&d), sizeof(mage_keypoint) * (size_t)n, s));
     cudaError_t e = cudaMemcpyAsync(d, keypoints, sizeof(mage_keypoint) * (size_t)n, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) rc = mage_undistort_keypoints_device(d, nullptr, 1, n, distorted, undistorted, cuda_stream);
     if (e == cudaSuccess && rc == MAGE_OK) e = cudaMemcpyAsync(keypoints, d, sizeof(mage_keypoint) * (size_t)n, cudaMemcpyDeviceToHost, s);

@@ -164,6 +164,13 @@ def test_step_many_equals_individual_steps_and_is_reproducible():
         assert rel_frobenius(cs, cm) < 1e-9 and rel_frobenius(ps, pm) < 1e-9
 
 
+def test_step_many_rejects_a_handle_listed_twice():
+    from mageslam_b200._lib import MageError
+    b = BundlerLib().load(synth.ba_problem(K=5, P=200, obs_per_point=3, seed=4))
+    with pytest.raises(MageError):
+        StepMany([b, b], [1.8], 1e9)
+
+
 def test_step_many_general_path_matches_reference():
     """windows the local-window fast path does not take (more than 10 free cameras; fixed points) go through the one-CTA kernel's
     general phases: same parity bar against the reference"""
