@@ -85,6 +85,14 @@ def main():
                 a[m.group(1)] = a.pop(k)
         a["k_resize"] = resize
         a["k_blur"] = a.get("k_blur7f", 0) + a.get("k_blur7f_edges", 0)
+        inst = {}                                                         # executed warp instructions per launch (last column of the summary table)
+        for ln in open(t("orb_ncu_full.md")).read().splitlines():
+            m = re.match(r"\| `(?:void )?(k_[a-z0-9_]+?)(?:_tma)?(?:<[^`]*)?` \|.*\| ([\d.]+) inst \|$", ln)
+            if m and m.group(1) not in inst:
+                inst[m.group(1)] = float(m.group(2))
+        if "k_blur7f" in inst:
+            inst["k_blur"] = inst.get("k_blur7f", 0) + inst.get("k_blur7f_edges", 0)
+        traffic["inst_executed"] = inst
         traffic.update({"frames_per_launch": 32, "source": "ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum), tools/quick_bench.py 32 3 (%s_orb_ncu_full.md); "
                         "k_resize = sum of the 7 level launches, k_blur = k_blur7f + k_blur7f_edges" % TAG, "kernels": a})
     # ---- bundle adjustment
