@@ -755,7 +755,23 @@ def bench_config5(args, world, rank, dist):
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    # the reference runs mapping (local BA) on its own thread beside tracking: the fresh windows are set up and stepped on a second
+    # host thread (the C-ABI calls release the GIL) while this thread streams the frames through the front-end
+    import threading
+    ba_out = {}
+
+    def mapping_thread():
+        torch.cuda.set_device(dev_index)
+        tb = time.perf_counter()
+        ws = [BundlerLib().load(probs[w % 4]) for w in range(n_windows)]      # fresh windows: set-up + structure build are inside the timed region
+        ba_out["means"] = StepMany(ws, [1.8] * 10, 1e9)
+        ba_out["iters"] = sum(b.stats()["lm_iterations"] for b in ws)
+        ba_out["seconds"] = time.perf_counter() - tb
+
+    dev_index = torch.cuda.current_device()
     t0 = time.perf_counter()
+    th = threading.Thread(target=mapping_thread)
+    th.start()
     kp = m = 0
     nb = frames_n // B
     for k in range(nb):
@@ -763,22 +779,20 @@ def bench_config5(args, world, rank, dist):
         if k:
             fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(k - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
     fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(nb - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
-    torch.cuda.synchronize()
     t_frames = time.perf_counter() - t0
-    windows = [BundlerLib().load(probs[w % 4]) for w in range(n_windows)]      # fresh windows: set-up + structure build are inside the timed region
-    means = StepMany(windows, [1.8] * 10, 1e9)
+    th.join()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    means, iters, t_ba = ba_out["means"], ba_out["iters"], ba_out["seconds"]
     t = torch.tensor([dt, t_frames], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt, t_frames = float(t[0].item()), float(t[1].item())
-    iters = sum(b.stats()["lm_iterations"] for b in windows)
     return {"metric": "config5_frames_per_sec_1280x720_with_local_ba", "value": world * frames_n / dt, "unit": "frames/s", "higher_is_better": True, "scaling": "weak",
-            "config": {"workload": "one 1280x720 synthetic sequence per GPU (2000 keypoints/frame), ORB extract + match per frame + a fresh local-BA window (10 KF / 2000 pts / 8000 obs, 10 LM iterations) every %d frames" % every,
+            "config": {"workload": "one 1280x720 synthetic sequence per GPU (2000 keypoints/frame), ORB extract + match per frame + a fresh local-BA window (10 KF / 2000 pts / 8000 obs, 10 LM iterations) every %d frames, stepped on a second host thread like the reference's mapping thread" % every,
                        "frames_per_gpu": frames_n, "sequences": world, "timer": "host clock, host buffers in and out, max over ranks"},
             "ba_lm_iters_per_s": world * iters / dt, "frontend_only_frames_per_s": world * frames_n / t_frames,
-            "ba_only_lm_iters_per_s": world * iters / max(dt - t_frames, 1e-9), "keypoints_per_frame": kp / frames_n, "matches_per_frame": m / frames_n,
+            "ba_only_lm_iters_per_s": world * iters / max(t_ba, 1e-9), "ba_thread_ms": 1e3 * t_ba, "frontend_thread_ms": 1e3 * t_frames, "keypoints_per_frame": kp / frames_n, "matches_per_frame": m / frames_n,
             "ba_mean_sq_error": float(np.mean(means)), "wall_s": dt,
             "h2d_bytes_per_frame": Wc * Hc, "d2h_bytes_per_frame": fe.capacity * (28 + 32 + 12) + 8}
 

@@ -16,6 +16,9 @@
 #include <chrono>
 
 #include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
 #include <cfloat>
 #include <cmath>
 #include <limits>
@@ -3039,6 +3042,31 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
     // gather the per-problem descriptors into one table and step every problem with ONE launch (grid = problems)
     std::vector<BaDev> table;
     std::vector<int> live;
+    {   // fresh windows: the state upload and the structure build are host work per handle (0.8 ms for a local window) -- one host
+        // thread per handle, up to eight at a time (the handles share nothing; each worker binds to the caller's device)
+        std::vector<int> todo;
+        for (int i = 0; i < n; i++) if (hs[i] && (hs[i]->dirty || !hs[i]->state_uploaded)) todo.push_back(i);
+        const int nthreads = getenv("MAGE_BA_SERIAL_PREPARE") ? 1 : std::min<int>({(int)todo.size(), 8, (int)std::max(1u, std::thread::hardware_concurrency())});
+        if (nthreads > 1) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            std::atomic<int> next{0};
+            std::vector<int> rcs(todo.size(), MAGE_OK);
+            std::vector<std::string> msgs(todo.size());
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; t++)
+                pool.emplace_back([&]() {
+                    cudaSetDevice(dev);
+                    for (int k; (k = next.fetch_add(1)) < (int)todo.size();) {
+                        rcs[k] = ba_prepare(hs[todo[k]], huber, n_iters, false);
+                        if (rcs[k]) msgs[k] = mage_last_error();          // the message lives in the worker's thread-local buffer
+                    }
+                });
+            for (auto& th : pool) th.join();
+            for (size_t k = 0; k < todo.size(); k++)
+                if (rcs[k]) { set_error("%s", msgs[k].c_str()); return rcs[k]; }
+        }
+    }
     for (int i = 0; i < n; i++) {
         int rc = ba_prepare(hs[i], huber, n_iters, false);        // the Huber table is uploaded once, on the lead handle
         if (rc) return rc;
