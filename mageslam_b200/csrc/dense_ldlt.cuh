@@ -39,7 +39,7 @@ constexpr int kThreads = 256;
 constexpr int LTP = NB + 2;                   // row pitch (doubles) of the transposed diagonal block in shared memory: 16-byte rows
 constexpr int kMinExp = 1023 - 400;           // rows whose largest |z| is below 2^-400 contribute nothing
 constexpr size_t kSmemUpdate = (size_t)SL * PLANE + (size_t)SL * BPLANE + TN * sizeof(double);
-constexpr size_t kSmemTrsm = sizeof(double) * ((size_t)NB * LTP + 2 * NB + 32 * 96 + 128);
+constexpr size_t kSmemTrsm = sizeof(double) * ((size_t)NB * LTP + 2 * NB + 32 * 96 + 128 + 32 * 64);
 constexpr int kPack = NB * LTP + 2 * NB;      // doubles of one factored diagonal block as it is published: Lt, then 1 / D, then 1 / sqrt(D)
 constexpr size_t kSmemBytes = (kSmemUpdate > kSmemTrsm ? kSmemUpdate : kSmemTrsm) + 1024;     // + slack to align the base to 1 KB
 // instruction descriptor (kind::i8): D = s32, A and B signed 8 bit, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
@@ -185,7 +185,9 @@ __device__ __forceinline__ void load_diag_block(const double* __restrict__ A, in
 __device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ invD, double* __restrict__ rsD, double* __restrict__ Yt, int nb, int* s_bad, long long* ns, bool timed_cta)
 {
     double* colb = Yt + 32 * YP;                                // [2][64] column exchange of the sub-block factorisation, upper halves zero
+    double* Lsub = colb + 128;                                  // [32][64] the factored 32 x 32 sub-block, column-major, upper halves zero
     if (threadIdx.x < 128) colb[threadIdx.x] = 0.0;
+    for (int i = threadIdx.x; i < 32 * 64; i += kThreads) Lsub[i] = 0.0;
     __syncthreads();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool timed = ns && timed_cta && tid == 0;             // reading %globaltimer is slow and serialises across the chip: one thread only
@@ -235,6 +237,7 @@ __device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ i
                     for (int t = u + 2; t < 32; t++) a[t] -= l * cj[t];          // A(i, j) -= L(i, k) A(j, k)
                     if (lane == k) mine = d;
                     if (lane >= k) Lt[(j0 + k) * LTP + j0 + lane] = lane == k ? d : l;
+                    Lsub[k * 64 + lane] = lane > k ? l : 0.0;        // compact copy for the row solves below: column k, zeros behind row 31
                     d = dn; inv = invn;
                 }
 #pragma unroll
@@ -262,10 +265,10 @@ __device__ void factor_diag_smem(double* __restrict__ Lt, double* __restrict__ i
                 for (int u = 0; u < 4; u++) {
                     const int c = kw + u;
                     const double yc = a[u];
-                    const double* lc = Lt + (j0 + c) * LTP + j0 + kw;   // L_sub(kw + t, c), the same address for every thread; t > u
+                    const double* lc = Lsub + c * 64 + kw;              // L_sub(kw + t, c), the same address for every thread; t > u (zeros past row 31)
                     if ((u + 1) & 1) a[u + 1] -= yc * lc[u + 1];
 #pragma unroll
-                    for (int t = (u + 2) & ~1; t < 32; t += 2) {                 // past row 31 of the sub-block: finite matrix data, results unused
+                    for (int t = (u + 2) & ~1; t < 32; t += 2) {
                         const double2 l2 = *reinterpret_cast<const double2*>(lc + t);
                         a[t] -= yc * l2.x; a[t + 1] -= yc * l2.y;
                     }

@@ -44,3 +44,8 @@ for name in sorted(CASES):
     kw, pf, hub, mx, calls = CASES[name]
     if "tethers" in kw:
         tb = BundlerLib(BundlerParameters(pf)).load(build_problem(kw)); print(name, tb.StepBundleAdjustment(hub, mx)); break
+# round 2: the dense solver of the reduced camera system alone (tcgen05 update, look-ahead factorisation, backward substitution)
+from tests.test_dense_gpu import solve, spd
+for n in (90, 300):
+    A = spd(n, n, spread=1.0); bb = np.random.default_rng(n).standard_normal(n)
+    xx, _, okk, _ = solve(A, bb); print("dense", n, okk, float(np.linalg.norm(A @ xx - bb) / np.linalg.norm(bb)))
