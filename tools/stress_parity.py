@@ -12,9 +12,10 @@ from mageslam_b200.matcher import Match
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 150
+only = sys.argv[3] if len(sys.argv) > 3 else "all"          # all | global
 t0 = time.time()
 ran = skipped = 0
-for seed in range(first, first + count):
+for seed in range(first, first + (count if only == "all" else 0)):
     mp = MonkeyPatch()
     try:
         test_orb_gpu.test_randomised_configurations_bit_exact(seed, mp); ran += 1
@@ -24,16 +25,16 @@ for seed in range(first, first + count):
         mp.undo()
 print("ORB: %d random configurations bit-exact vs the oracle (%d degenerate pyramids skipped), %.0f s" % (ran, skipped, time.time() - t0))
 t0 = time.time()
-for seed in range(first, first + count):
+for seed in range(first, first + (count if only == "all" else 0)):
     rng = np.random.default_rng(seed)
     n = int(rng.integers(1, 2300)); flips = int(rng.integers(1, 100)); maxd = int(rng.choice([0, 10, 30, 40, 64, 65, 100])); mind = int(rng.integers(0, 4))
     A = rng.integers(0, 256, (n, 32), dtype=np.uint8)
     B = test_match_gpu.noisy_copy(rng, A, flips)[: max(1, n - int(rng.integers(0, n // 3 + 1)))]
     got, ref = Match(A, B, None, None, maxd, mind), orc.match(A, B, maxd, mind)
     assert test_match_gpu.as_tuples(got) == test_match_gpu.as_tuples(ref, "query", "train"), (seed, n, flips, maxd, mind)
-print("Match: %d random cases equal the oracle's pairs, %.0f s" % (count, time.time() - t0))
+print("Match: %d random cases equal the oracle's pairs, %.0f s" % (count if only == "all" else 0, time.time() - t0))
 t0 = time.time()
-nba = max(count // 5, 1)
+nba = max(count // 5, 1) if only == "all" else 0
 knife = 0
 for seed in range(first, first + nba):
     try:
@@ -70,6 +71,29 @@ for seed in range(first, first + nba):
 print("BA: %d random windows (solo + batched) within 1e-4 of the reference, call by call; lambda, outliers and mean equal in all but %d "
       "window(s) where LM had converged (mean error unchanged to 1e-5) and the sign of the gain ratio -- a difference of two sums that "
       "agree to ~1e-9 -- fell the other way: states still within 1e-4, lambda off by the accept / reject factor; %.0f s" % (nba, knife, time.time() - t0))
+t0 = time.time()
+ng = max(count // 25, 1) if only == "all" else count
+from mageslam_b200 import synth as _synth
+from mageslam_b200.bundler import BundlerLib as _BL
+from tests.ba_checks import TOL as _TOL, best_checker as _chk, run_side_by_side as _side
+worst_g = 0.0
+ran_g = 0
+for seed in range(first, first + ng):
+    rng = np.random.default_rng(9000 + seed)
+    K = int(rng.integers(16, 140)); d = int(rng.integers(3, 9))
+    kw = dict(K=K, P=int(rng.integers(40 * K // 4, 60 * K)), obs_per_point=d, seed=seed, loop=True, outlier_frac=float(rng.choice([0.0, 0.0, 0.03])))
+    try:
+        prob = _synth.ba_problem(**kw)
+    except RuntimeError:
+        continue                                  # the generator could not place the points of this shape
+    hub = [1.8] * int(rng.integers(1, 4))
+    mx = 7.25 if kw["outlier_frac"] > 0 else 1e9
+    rep = _side(_BL().load(prob), _chk().load(prob), hub, mx, int(rng.integers(1, 4)), tag="global %s" % kw)
+    worst_g = max(worst_g, max(max(r) for r in rep))
+    ran_g += 1
+    assert worst_g < _TOL
+print("global BA: %d random loop problems (16-140 key frames: reduced systems of 84-828 unknowns through the tcgen05 dense solver, 1-3 Huber widths per "
+      "call, outliers in a third) within %.1e of the reference, lambda / outliers / mean equal, %.0f s" % (ran_g, worst_g, time.time() - t0))
 t0 = time.time()
 worst = 0.0
 for seed in range(first, first + max(count // 5, 1)):
