@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <cfloat>
@@ -2396,6 +2397,34 @@ struct mage_ba_s {
     int coop_blocks_max = 0;           // co-resident limit (large problems use the whole chip)
 };
 
+// Pinned host staging buffers for the structure upload, pooled process-wide (cudaHostAlloc costs more than the build itself): a build
+// takes one, the batched call's worker threads take one each.
+struct PinnedStage { uint8_t* p = nullptr; size_t cap = 0; };
+static std::mutex g_stage_mu;
+static std::vector<PinnedStage> g_stage_free;
+static PinnedStage stage_acquire(size_t bytes)
+{
+    PinnedStage st;
+    {
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        for (size_t i = 0; i < g_stage_free.size(); i++)
+            if (g_stage_free[i].cap >= bytes) { st = g_stage_free[i]; g_stage_free.erase(g_stage_free.begin() + i); return st; }
+        if (!g_stage_free.empty()) { st = g_stage_free.back(); g_stage_free.pop_back(); }
+    }
+    if (st.p) { cudaFreeHost(st.p); st = PinnedStage(); }     // too small: grow
+    const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&st.p), cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); st.p = nullptr; return st; }
+    st.cap = cap;
+    return st;
+}
+static void stage_release(PinnedStage st)
+{
+    if (!st.p) return;
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (g_stage_free.size() < 16) g_stage_free.push_back(st);
+    else cudaFreeHost(st.p);
+}
+
 // dynamic shared memory for one problem: reduced system + camera state when they fit in 200 KB, else whatever subset fits
 static size_t ba_dyn_smem(int n, int K, int fast)
 {
@@ -2647,23 +2676,31 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_lpt = rI(Pl), o_lptr = rI(Pl + 1), o_ledges = rI(l_edges.size());
     size_t o_ccam = rI(Kf), o_cptr = rI(Kf + 1), o_cedges = rI(c_edges.size());
     size_t o_bij = rI(blk_ij.size()), o_bptr = rI(blk_ptr.size()), o_pairs = W.reserve(sizeof(int2) * std::max<size_t>(pairs.size(), 1));
+    size_t o_bptr2 = rI(batch_ptr.size()), o_idef = W.reserve(sizeof(int4) * std::max<size_t>(item_def.size(), 1)), o_bitems = W.reserve(sizeof(int2) * blk_items.size());
+    size_t o_cdiag = rI(cam_diag.size()), o_bbptr = rI(bb_ptr.size()), o_bpairs = W.reserve(sizeof(ushort2) * std::max<size_t>(bpairs.size(), 1));
+    size_t o_tdef = W.reserve(sizeof(int4) * std::max(nT, 1)), o_tmeas = rD(8 * (size_t)nT);
+    const size_t upload_end = W.reserve(0, 256);               // everything above is host-built and goes up in ONE copy; the work arrays follow
     size_t o_err = rD(2 * (size_t)Ea), o_W = rD(18 * (size_t)Ea), o_WD = rD(20 * (size_t)Ea), o_Hll = rD(9 * (size_t)Pl), o_bl = rD(3 * (size_t)Pl);
     size_t o_Dinv = rD(9 * (size_t)Pl), o_db = rD(3 * (size_t)Pl), o_Hpp = rD(36 * (size_t)Kf), o_bp = rD(n), o_S = rD((size_t)n * n), o_bs = rD(n);
     size_t o_x = rD(n + 3 * (size_t)Pl), o_cbak = rD(7 * (size_t)Kf), o_pbak = rD(3 * (size_t)Pl), o_part = rD((size_t)Kf * cam_parts * 27);
     size_t o_flags = W.reserve(std::max(Ea, 1));
     size_t o_Hc = rD(12 * (size_t)Ea), o_camR = rD(18 * (size_t)h->K);
-    size_t o_bptr2 = rI(batch_ptr.size()), o_idef = W.reserve(sizeof(int4) * std::max<size_t>(item_def.size(), 1)), o_bitems = W.reserve(sizeof(int2) * blk_items.size());
-    size_t o_cdiag = rI(cam_diag.size()), o_bbptr = rI(bb_ptr.size()), o_bpairs = W.reserve(sizeof(ushort2) * std::max<size_t>(bpairs.size(), 1));
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
     size_t o_Zq = W.reserve(big ? dense::scratch_zq_bytes(n) : 16, 1024), o_Ez = rI(big ? dense::scratch_ez_count(n) : 1);
     size_t o_Ldiag = W.reserve(big ? dense::scratch_ldiag_bytes(n) : 16, 256), o_dflag = rI(1);
-    size_t o_tdef = W.reserve(sizeof(int4) * std::max(nT, 1)), o_tmeas = rD(8 * (size_t)nT), o_terr = rD(6 * (size_t)nT), o_tJ = rD(72 * (size_t)nT);
+    size_t o_terr = rD(6 * (size_t)nT), o_tJ = rD(72 * (size_t)nT);
     MAGE_CUDA_TRY(W.commit());
     mark("cudaMalloc");
-    MAGE_CUDA_TRY(cudaMemsetAsync(W.base, 0, W.size, h->stream));
+    MAGE_CUDA_TRY(cudaMemsetAsync(W.base + upload_end, 0, W.size - upload_end, h->stream));
+    // the host-built tables are packed into one pinned staging buffer (same offsets as in the arena) and go up in one copy: twenty
+    // separate copies from pageable vectors cost 0.2 ms of driver calls per window
+    PinnedStage stage = stage_acquire(std::max<size_t>(upload_end, 256));
+    MAGE_REQUIRE(stage.p, MAGE_ERR_CUDA, "ba_build_structure: no pinned staging memory");
+    memset(stage.p, 0, upload_end);
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
-        return bytes ? cudaMemcpyAsync(W.base + off, src, bytes, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+        if (bytes) memcpy(stage.p + off, src, bytes);
+        return cudaSuccess;
     };
     MAGE_CUDA_TRY(up(o_camh, cam_h.data(), sizeof(int) * h->K));
     MAGE_CUDA_TRY(up(o_ecam, e_cam.data(), sizeof(int) * Ea)); MAGE_CUDA_TRY(up(o_ept, e_pt.data(), sizeof(int) * Ea));
@@ -2700,10 +2737,13 @@ static int ba_build_structure(mage_ba_t h)
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
     d.big = big; d.Zq = W.at<int8_t>(o_Zq); d.Ez = W.at<int>(o_Ez); d.Ldiag = W.at<double>(o_Ldiag); d.dflag = W.at<int>(o_dflag);
     d.nT = nT; d.t_def = W.at<int4>(o_tdef); d.t_meas = W.at<double>(o_tmeas); d.t_err = W.at<double>(o_terr); d.t_J = W.at<double>(o_tJ);
-    MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream));
+    cudaError_t eup = upload_end ? cudaMemcpyAsync(W.base, stage.p, upload_end, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
+    if (eup == cudaSuccess) eup = cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream);
     mark("enqueue uploads");
-    // pageable staging vectors go out of scope on return: make sure the copies have been consumed
-    MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    // the staging buffer goes back to the pool and `d` out of scope on return: make sure the copies have been consumed
+    if (eup == cudaSuccess) eup = cudaStreamSynchronize(h->stream);
+    stage_release(stage);
+    MAGE_CUDA_TRY(eup);
     mark("sync");
     return MAGE_OK;
 }
