@@ -2480,7 +2480,7 @@ static int ba_build_structure(mage_ba_t h)
         if (h->points_fixed && h->cam_fixed[o.cam]) continue;               // allVerticesFixed
         order.push_back({o.seq, e});
     }
-    std::sort(order.begin(), order.end());                                   // EdgeIDCompare = insertion order
+    if (!std::is_sorted(order.begin(), order.end())) std::sort(order.begin(), order.end());      // EdgeIDCompare = insertion order (callers usually set the observations in that order already)
     for (auto& pr : order) h->active.push_back(pr.second);
     const int Ea = (int)h->active.size();
     std::vector<char> camA(h->K, 0), ptA(h->P, 0);
@@ -2578,17 +2578,22 @@ static int ba_build_structure(mage_ba_t h)
     // block when the table would be unreasonably large)
     std::vector<int> blk_ij, blk_ptr(1, 0);
     std::vector<int2> pairs;
+    std::vector<int> le_h(l_edges.size());                      // reduced-system index of the camera behind each landmark-edge slot (-1: fixed)
+    for (size_t k = 0; k < l_edges.size(); k++) le_h[k] = cam_h[e_cam[l_edges[k]]];
     auto for_each_pair = [&](auto&& fn) {
-        for (int li = 0; li < Pl; li++)
-            for (int k1 = l_ptr[li]; k1 < l_ptr[li + 1]; k1++) {
-                const int a1 = l_edges[k1], i1 = cam_h[e_cam[a1]];
+        for (int li = 0; li < Pl; li++) {
+            const int kb = l_ptr[li], ke = l_ptr[li + 1];
+            for (int k1 = kb; k1 < ke; k1++) {
+                const int i1 = le_h[k1];
                 if (i1 < 0) continue;
-                for (int k2 = l_ptr[li]; k2 < l_ptr[li + 1]; k2++) {
-                    const int a2 = l_edges[k2], i2 = cam_h[e_cam[a2]];
-                    if (i2 < 0 || i2 < i1) continue;
-                    fn(i1, i2, a1, a2);
+                const int a1 = l_edges[k1];
+                for (int k2 = kb; k2 < ke; k2++) {
+                    const int i2 = le_h[k2];
+                    if (i2 < i1) continue;                              // (also skips fixed cameras: -1 < i1)
+                    fn(i1, i2, a1, l_edges[k2]);
                 }
             }
+        }
     };
     if ((size_t)Kf * Kf <= (size_t)1 << 22) {
         std::vector<int> cnt((size_t)Kf * Kf, 0), slot((size_t)Kf * Kf, -1);
@@ -2654,15 +2659,19 @@ static int ba_build_structure(mage_ba_t h)
         // pairs regrouped by (batch, block); inside a group the landmark order of the block's pair list is kept
         std::vector<int> lm_batch(Pl);
         for (int b = 0; b < nb; b++) for (int li = batch_ptr[b]; li < batch_ptr[b + 1]; li++) lm_batch[li] = b;
-        std::vector<std::vector<ushort2>> groups((size_t)nb * nblk);
+        // counting sort of the pairs by (batch, block): sizes, exclusive scan, fill (the order inside a group is the block's pair order)
+        bb_ptr.assign((size_t)nb * nblk + 1, 0);
+        for (int b = 0; b < nblk; b++)
+            for (int k = blk_ptr[b]; k < blk_ptr[b + 1]; k++) bb_ptr[(size_t)lm_batch[e_l[pairs[k].x]] * nblk + b + 1]++;
+        for (size_t q = 0; q < (size_t)nb * nblk; q++) bb_ptr[q + 1] += bb_ptr[q];
+        bpairs.resize(pairs.size());
+        std::vector<int> fill(bb_ptr.begin(), bb_ptr.end() - 1);
         for (int b = 0; b < nblk; b++)
             for (int k = blk_ptr[b]; k < blk_ptr[b + 1]; k++) {
                 const int2 pr = pairs[k];
                 const int bt = lm_batch[e_l[pr.x]], e0 = l_ptr[batch_ptr[bt]];
-                groups[(size_t)bt * nblk + b].push_back(make_ushort2((unsigned short)(pr.x - e0), (unsigned short)(pr.y - e0)));
+                bpairs[fill[(size_t)bt * nblk + b]++] = make_ushort2((unsigned short)(pr.x - e0), (unsigned short)(pr.y - e0));
             }
-        bb_ptr.push_back(0);
-        for (auto& gq : groups) { bpairs.insert(bpairs.end(), gq.begin(), gq.end()); bb_ptr.push_back((int)bpairs.size()); }
     }
     const int cam_parts = std::max(1, std::min(16, 256 / std::max(Kf, 1)));     // (camera, part) reduction items
     const int schur_parts = kSchurParts;
