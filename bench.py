@@ -701,7 +701,8 @@ def bench_global_ba(args):
         out["phase_ms_per_step"] = {"schur_products": float(ph[3]) / 1e6 / steps, "dense_solve": float(ph[4]) / 1e6 / steps,
                                     "ldlt_diagonal_blocks": float(ph[9]) / 1e6 / steps, "ldlt_panel_rows": float(ph[10]) / 1e6 / steps,
                                     "ldlt_tensor_update_issue": float(ph[11]) / 1e6 / steps, "ldlt_tensor_update_drain_and_barriers": float(ph[12]) / 1e6 / steps,
-                                    "back_substitution": float(ph[13]) / 1e6 / steps, "note": "as CTA 0 sees them (in-kernel %globaltimer)"}
+                                    "back_substitution": float(ph[13]) / 1e6 / steps,
+                                    "note": "as CTA 0 sees them (in-kernel %globaltimer); with the look-ahead factorisation every diagonal block after the first is factored by the last CTA during the update phase (about 37 us each, tools/dense_call.py prints it), so CTA 0's own diagonal time is the copy of the published block and its update time includes waiting for that CTA"}
         # the trailing updates of the blocked LDL^T run on tcgen05 (kind::i8, exact 8 x 7-bit slices, 36 slice pairs x 4 K steps of
         # 128 x 64 x 32 per 128 x 64 tile): int8 operations per factorisation over the time of the update phases
         tiles = 0
