@@ -1,22 +1,29 @@
-// Grid-wide dense LDL^T of the reduced camera system and the two triangular solves (global bundle adjustment).
+// Grid-wide dense LDL^T of the reduced camera system with the forward substitution folded in, and the backward substitution
+// (global bundle adjustment).
 //
 // Replaces g2o's LinearSolverDense::solve (ref Dependencies/g2o/g2o/solvers/dense/linear_solver_dense.h:65-113: Eigen::LDLT of the
 // n x n reduced system, n = 6 x free cameras, 2988 for the 500-key-frame tier problem) inside the cooperative LM kernel of ba.cu.
 // Right-looking blocked factorisation without pivoting (the damped system is SPD; a non-positive pivot => "not positive"), panels of
-// NB = 128 columns, three grid barriers per panel:
-//   (a) CTA 0 factors the 128 x 128 diagonal block in registers (16 x 16 threads x 8 x 8 blocks, one CTA barrier per column);
-//   (b) one warp per trailing row solves Y = A_ik L_kk^-T against the block held (transposed) in shared memory, stores
-//       L_ik = Y D^-1 and cuts Z = Y D^-1/2 -- the row of the Cholesky factor, so that the update below is -Z Z^T with ONE operand
-//       -- into SL = 8 signed 7-bit slices per value relative to the row's largest exponent (exact: z = 2^E sum_s q_s 2^(-6-7s) +
-//       a remainder below 2^(E-56)), written as int8 planes in the tensor core's canonical K-major shared-memory layout;
+// NB = 128 columns, two grid barriers per panel:
+//   (a) the 128 x 128 diagonal block is factored in shared memory (32-wide sub-blocks: one warp factors the 32 x 32 block with a row
+//       per lane, one thread per row below solves its 32 entries, all threads apply the rank-32 update). The first block by every
+//       CTA (same arithmetic, same result); every later one by the LAST CTA of the grid while the others run the trailing update of
+//       the panel before it (look-ahead: the two update tiles that cover the block open the chunks of two workers and are counted
+//       in a flag the factor CTA waits on), published to global memory and copied into shared memory by everybody;
+//   (b) a warp per (up to three) trailing rows solves Y = A_ik L_kk^-T against the block in shared memory, stores L_ik = Y D^-1
+//       and cuts Z = Y D^-1/2 -- the row of the Cholesky factor, so that the update below is -Z Z^T with ONE operand -- into
+//       SL = 8 signed 7-bit slices per value relative to the row's largest exponent (exact: z = 2^E sum_s q_s 2^(-6-7s) + a remainder
+//       below 2^(E-56)), written as int8 planes in the 128-byte-swizzled K-major layout the tensor core reads. Row n of the matrix
+//       is the right-hand side of the linear system: the last row of the bordered factor is D^-1 L^-1 b, the forward substitution;
 //   (c) the trailing update A_ij -= sum_m Z_im Z_jm runs on the 5th-generation tensor cores as exact integer arithmetic (the Ozaki
-//       scheme): for every slice pair (s, t) with s + t = d <= 7 one tcgen05.mma kind::i8 (M = 128 rows x N = 64 columns x K = 128)
-//       accumulates q_s(i) . q_t(j) in s32 in tensor memory, one accumulator per d (|sum| <= 8 * 128 * 64 * 64 = 2^22); the
-//       epilogue reads the eight accumulators back (tcgen05.ld), combines them in FP64 with the weights 2^(-12-7d), scales by
-//       2^(E_i + E_j) and subtracts from A in place. The products dropped (s + t >= 8) are below 2^-46 of the row maxima's product --
-//       the rounding error an FP64 dot product of 128 terms carries anyway. Operand planes come in by cp.async.bulk (the TMA engine's
-//       linear mode), slice by slice, so the first MMAs start while the later slices are still in flight.
-// FP64 CUDA cores keep everything that is not a dense contraction: the diagonal blocks, the panel solves, the substitutions.
+//       scheme): for every slice pair (s, t) with s + t = d <= 7 one chain of tcgen05.mma kind::i8 (M = 128 rows x N = 64 columns x
+//       K = 32, four per pair) accumulates q_s(i) . q_t(j) in s32 in tensor memory, one accumulator per d (|sum| <= 8 * 128 * 64 * 64
+//       = 2^22); the epilogue reads the eight accumulators back (tcgen05.ld), combines them in FP64 with the weights 2^(-12-7d),
+//       scales by 2^(E_i + E_j) and subtracts from A in place. The products dropped (s + t >= 8) are below 2^-46 of the row maxima's
+//       product -- the rounding error an FP64 dot product of 128 terms carries anyway. Operand planes come in by cp.async.bulk (the
+//       TMA engine's linear mode), slice by slice, so the first MMAs start while the later slices are still in flight.
+// The backward substitution takes one grid barrier per 128 unknowns (every CTA solves the diagonal triangle itself).
+// FP64 CUDA cores keep everything that is not a dense contraction: the diagonal blocks, the panel solves, the substitution.
 #pragma once
 
 
