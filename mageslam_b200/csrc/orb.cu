@@ -26,7 +26,7 @@ namespace mage {
 
 constexpr int kMaxLevels = 16;
 constexpr int kMaxCells = 2048;
-constexpr int kSelThreads = 512;
+constexpr int kSelThreads = 1024;        // launch bound; batches launch half of it (see the launch site)
 constexpr int kSelSmemItems = 2048;      // keypoints per (frame, level) handled entirely in shared memory (34 KB: four 512-thread CTAs per SM; a level keeping more uses the global scratch)
 
 struct LevelGeom {
@@ -608,7 +608,7 @@ __device__ void bitonic_sort_desc(unsigned long long* keys, int npow2)
     }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 4) k_select(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+__global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int hist[256];
@@ -1738,7 +1738,9 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
             else kFastVariants[h->fast_variant].k<<<dim3(h->fast_tiles, n), 256, kFastSmemBytes, s>>>(g, bufs, h->d_fast_tiles);
         }
     }
-    { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), kSelThreads, select_smem_bytes(), s>>>(g, bufs); }
+    // one CTA per (level, frame): a chain of dependent phases. With a few frames the call's latency is this kernel's (58 us for one 640 x 480
+    // frame with 512 threads, 46 us with 1024); with a batch four 512-thread CTAs per SM give the better throughput
+    { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), n <= 4 ? kSelThreads : kSelThreads / 2, select_smem_bytes(), s>>>(g, bufs); }
     if (fork) MAGE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_blur, 0));
     { ProfScope ps(PROF_ORIENT_DESCRIBE, s); k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity); }
     MAGE_CUDA_TRY(cudaGetLastError());
