@@ -3095,7 +3095,11 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
         // thread per handle, up to eight at a time (the handles share nothing; each worker binds to the caller's device)
         std::vector<int> todo;
         for (int i = 0; i < n; i++) if (hs[i] && (hs[i]->dirty || !hs[i]->state_uploaded)) todo.push_back(i);
-        const int nthreads = getenv("MAGE_BA_SERIAL_PREPARE") ? 1 : std::min<int>({(int)todo.size(), 8, (int)std::max(1u, std::thread::hardware_concurrency())});
+        // (a box usually runs one process per GPU: leave each its share of the host cores)
+        int ndev = 1;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); ndev = 1; }
+        const int share = std::max(2, (int)std::thread::hardware_concurrency() / ndev);
+        const int nthreads = getenv("MAGE_BA_SERIAL_PREPARE") ? 1 : std::min<int>({(int)todo.size(), 8, share});
         if (nthreads > 1) {
             int dev = 0;
             cudaGetDevice(&dev);
