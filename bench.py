@@ -752,7 +752,7 @@ def bench_config5(args, world, rank, dist):
     n_windows = frames_n // every
     probs = [synth.ba_problem(seed=100 * rank + w) for w in range(4)]
     fe.Process(frames[:B], outs2[0]); fe.Reset()
-    StepMany([BundlerLib().load(probs[0])], [1.8], 1e9)
+    StepMany([BundlerLib().load(probs[w % 4]) for w in range(n_windows)], [1.8], 1e9)      # warm-up at the steady-state shape (worker threads, staging buffers, pools)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/mage_b200.h"
@@ -33,10 +34,12 @@ void set_error(const char* fmt, ...);
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }
 
-// The library's OWN stream-ordered memory pool of the current device (created on first use, one per device, release threshold at the
-// maximum so blocks freed with cudaFreeAsync stay cached across synchronisations). The host application's default pool is left
-// alone: raising ITS threshold would change how the application's own cudaFreeAsync behaves. nullptr when the device / driver has no
-// stream-ordered allocator.
+// The stream-ordered memory pool the library allocates from on the current device (set up on first use, once per device, thread-safe).
+// Default: the device's default pool with its release threshold raised to the maximum, so blocks freed with cudaFreeAsync stay
+// cached across synchronisations (at the default threshold of 0 they go back to the driver at the next sync and every new window
+// pays a fresh allocation). That is a process-wide setting the host application shares; MAGE_POOL_PRIVATE=1 gives the library a
+// pool of its own instead -- measured slower and less steady on B200 (a fresh local-BA window 2.0 - 4.4 ms instead of 1.8 ms), which
+// is why it is the option and not the default. nullptr when the device / driver has no stream-ordered allocator.
 inline cudaMemPool_t library_pool()
 {
     constexpr int kMaxDev = 64;
@@ -45,6 +48,15 @@ inline cudaMemPool_t library_pool()
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
     std::call_once(once[dev], [dev]() {
+        if (!getenv("MAGE_POOL_PRIVATE")) {
+            cudaMemPool_t dp = nullptr;
+            if (cudaDeviceGetDefaultMemPool(&dp, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(dp, cudaMemPoolAttrReleaseThreshold, &keep);
+                pools[dev] = dp;
+            } else cudaGetLastError();
+            return;
+        }
         cudaMemPoolProps props = {};
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
@@ -83,6 +95,7 @@ struct DeviceArena {
         cudaMemPool_t pool = library_pool();
         cudaError_t e = pool ? cudaMallocFromPoolAsync(reinterpret_cast<void**>(&base), size ? size : 256, pool, static_cast<cudaStream_t>(0)) : cudaErrorNotSupported;
         if (e == cudaSuccess) return cudaStreamSynchronize(static_cast<cudaStream_t>(0));    // usable from any stream afterwards
+        if (getenv("MAGE_DEBUG_POOL")) fprintf(stderr, "[pool] stream-ordered allocation of %zu bytes failed (%s, pool %p): plain cudaMalloc\n", size, cudaGetErrorString(e), (void*)pool);
         cudaGetLastError();                                    // no stream-ordered pool on this device / driver: plain allocation
         pooled = false; base = nullptr;
         return cudaMalloc(&base, size ? size : 256);
