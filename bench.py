@@ -545,6 +545,12 @@ def run_ours(args):
                 line["global_ba"] = bench_global_ba(args)
             except Exception as e:      # pragma: no cover
                 line["global_ba"] = {"error": str(e)[:300]}
+    if world > 1 and args.global_ba_steps > 0:
+        try:
+            sg = bench_sharded_global_ba(args, world, rank, dist)
+        except Exception as e:      # pragma: no cover
+            sg = {"error": str(e)[:300]}
+        line["sharded_global_ba"] = sg
     if args.config5_frames > 0:
         del fe_dev, fe_host, fe_pipe, d_ring
         try:
@@ -733,6 +739,48 @@ def bench_global_ba(args):
     pc, rc = g2.poses(); pr, rr = chk.poses()
     out["parity_after_2_steps"] = {"relF_positions": rel_frobenius(pc, pr), "relF_rotations": rel_frobenius(rc, rr), "relF_points": rel_frobenius(g2.points(), chk.points()),
                                    "lambda": [g2.GetCurrentLambda(), chk.GetCurrentLambda()], "tolerance": 1e-4}
+    return out
+
+
+def bench_sharded_global_ba(args, world, rank, dist):
+    """The one path with a real exchange step (SURVEY 8(e) "next"): the config-4 problem with its landmarks dealt out over the ranks,
+    the reduced camera system all-reduced over NVLink once per lambda trial (mageslam_b200/sharded.py). Strong scaling: the problem is
+    fixed, every rank repeats the dense factorisation. Rank 0 also steps the whole problem on its own GPU and compares the states."""
+    import torch
+    from mageslam_b200 import synth
+    from mageslam_b200.bundler import BundlerLib
+    from mageslam_b200.sharded import ShardedGlobalBA
+    from tests.oracle_ba import rel_frobenius
+    K, P, D = 500, 50000, 8
+    prob = synth.ba_problem(K=K, P=P, obs_per_point=D, seed=2, loop=True)
+    sh = ShardedGlobalBA(prob, rank, world, dist)
+    sh.StepBundleAdjustment([1.8])
+    ts = []
+    for _ in range(args.global_ba_steps):
+        dist.barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sh.StepBundleAdjustment([1.8])
+        torch.cuda.synchronize()
+        ts.append(time.perf_counter() - t0)
+    t = torch.tensor(ts, dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = 1e3 * statistics.median(t.tolist())
+    n = sh.n
+    out = {"metric": "global_ba_ms_per_lm_step", "value": ms, "unit": "ms", "higher_is_better": False, "scaling": "strong", "n_gpus": world,
+           "config": {"workload": "global BA 500 KF / 50 000 pts / 400 000 obs, landmarks dealt out over %d ranks (landmark i on rank i %% %d), all cameras on every rank, Huber 1.8, one LM step per call" % (world, world),
+                      "reduced_system": n, "timer": "host clock around the call, max over ranks, median of %d steps" % args.global_ba_steps},
+           "exchange": {"collective": "NCCL all-reduce (sum) of the reduced camera system and its right-hand side, once per lambda trial",
+                        "bytes_per_trial": 8 * (n * n + n), "small_all_reduces_per_step": 4},
+           "lambda_trials": sh.trials, "dtype": "f64"}
+    if rank == 0:
+        one = BundlerLib().load(prob)
+        for _ in range(1 + args.global_ba_steps):
+            one.StepBundleAdjustment([1.8], 1e9)
+        p1, r1 = one.poses(); p2, r2 = sh.poses()
+        ids, pts = sh.points()
+        out["parity_vs_one_gpu"] = {"relF_positions": rel_frobenius(p2, p1), "relF_rotations": rel_frobenius(r2, r1), "relF_points": rel_frobenius(pts, one.points()[ids]),
+                                    "lambda": [sh.GetCurrentLambda(), one.GetCurrentLambda()], "tolerance": 1e-4}
+    dist.barrier()
     return out
 
 

@@ -334,6 +334,16 @@ int  mage_ba_get_state_f64(mage_ba_t h, double* cam_qxyzw_t /*K*7*/, double* poi
 int  mage_ba_get_stats(mage_ba_t h, int64_t stats[4]);
 /* diagnostics: accumulated nanoseconds per phase of the cooperative kernel as seen by block 0 */
 int  mage_ba_debug_phase_ns(mage_ba_t h, long long phase_ns[16]);
+/* Sharded global bundle adjustment (SURVEY 8(e) "next": observations partitioned by landmark over the ranks, the all-reduce of the reduced
+ * camera system is the one exchange step; ref block_solver.hpp:331-422 builds that system, linear_solver_dense.h:65-113 solves it). Every
+ * rank creates the problem with ALL cameras and its own points / observations; mage_ba_shard_prepare builds the structure and returns the
+ * device buffers to all-reduce (S: n x n, bs: n, xchg: 16 + 2 n doubles), mage_ba_shard_stage runs one stage of the LM iteration
+ * (1 linearise, 2 Schur complement of this rank's landmarks, 3 damp + solve + update + trial chi2, 4 restore, 5 error sums); the host
+ * loop around them is mageslam_b200/sharded.py. lead = 1 on exactly one rank (it adds the camera part of the gain-ratio denominator). */
+int  mage_ba_shard_prepare(mage_ba_t h, int* n, double** d_S, double** d_bs, double** d_xchg);
+int  mage_ba_shard_stage(mage_ba_t h, int stage, double huber_delta, double lambda, int lead);
+/* diagnostics: a work array of the built problem (0 x = the last increment, 1 Hpp, 2 bp, 3 bl, 4 Hll, 5 bs, 6 S of a large system) */
+int  mage_ba_debug_get_array(mage_ba_t h, int which, double* out, long long capacity, long long* count);
 /* The dense solver of the reduced camera system on its own (test entry; replaces Eigen::LDLT of ref
  * Dependencies/g2o/g2o/solvers/dense/linear_solver_dense.h:65-113): A is n x n row-major symmetric positive definite (lower triangle
  * read), b the right-hand side; x receives the solution, factor (nullable, n x n) L below the diagonal and D on it, *positive 0 when a

@@ -61,6 +61,7 @@ struct BaDev {
     int8_t* Zq;                               // int8 slice planes of the current panel (dense_ldlt.cuh)
     double* Ldiag;                            // factored diagonal blocks of the reduced system (dense_ldlt.cuh)
     int* dflag;                               // look-ahead counter of the dense solver (dense_ldlt.cuh)
+    double* xchg;                             // [16 + 2 n] scalars / diag(Hpp) / bp exchanged between the ranks of a sharded problem (big mode only)
     int* Ez;                                  // row exponents of the slices
     // tether edges between two cameras (ref BundlerLib.cpp:24-90, :311-350), single-CTA kernel only
     int nT;
@@ -2697,7 +2698,7 @@ static int ba_build_structure(mage_ba_t h)
     size_t o_spart = rD((size_t)nblk * schur_parts * 36), o_gred = rD(2 * (size_t)kCoopRedVals * kCoopMaxBlocks);
     const int big = ba_smem_need_S(n) > 56 * 1024 ? 1 : 0;             // reduced system too large for one CTA's shared memory
     size_t o_Zq = W.reserve(big ? dense::scratch_zq_bytes(n) : 16, 1024), o_Ez = rI(big ? dense::scratch_ez_count(n) : 1);
-    size_t o_Ldiag = W.reserve(big ? dense::scratch_ldiag_bytes(n) : 16, 256), o_dflag = rI(1);
+    size_t o_Ldiag = W.reserve(big ? dense::scratch_ldiag_bytes(n) : 16, 256), o_dflag = rI(1), o_xchg = rD(big ? 16 + 2 * (size_t)n : 1);
     size_t o_terr = rD(6 * (size_t)nT), o_tJ = rD(72 * (size_t)nT);
     MAGE_CUDA_TRY(W.commit());
     mark("cudaMalloc");
@@ -2744,7 +2745,7 @@ static int ba_build_structure(mage_ba_t h)
     d.cam_diag = W.at<int>(o_cdiag); d.bb_ptr = W.at<int>(o_bbptr); d.bpairs = W.at<ushort2>(o_bpairs);
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
-    d.big = big; d.Zq = W.at<int8_t>(o_Zq); d.Ez = W.at<int>(o_Ez); d.Ldiag = W.at<double>(o_Ldiag); d.dflag = W.at<int>(o_dflag);
+    d.big = big; d.Zq = W.at<int8_t>(o_Zq); d.Ez = W.at<int>(o_Ez); d.Ldiag = W.at<double>(o_Ldiag); d.dflag = W.at<int>(o_dflag); d.xchg = W.at<double>(o_xchg);
     d.nT = nT; d.t_def = W.at<int4>(o_tdef); d.t_meas = W.at<double>(o_tmeas); d.t_err = W.at<double>(o_terr); d.t_J = W.at<double>(o_tJ);
     cudaError_t eup = upload_end ? cudaMemcpyAsync(W.base, stage.p, upload_end, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
     if (eup == cudaSuccess) eup = cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream);
@@ -3240,6 +3241,174 @@ extern "C" int mage_ba_debug_phase_ns(mage_ba_t h, long long out[16])
     BaCtl c;
     MAGE_CUDA_TRY(cudaMemcpy(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; i++) out[i] = c.phase_ns[i];
+    return MAGE_OK;
+}
+
+// ---- sharded global bundle adjustment (SURVEY 8(e) / 8(f) "next": observations partitioned by landmark over the ranks, ONE exchange step
+// per lambda trial: the all-reduce of the reduced camera system). Every rank holds all cameras and its own landmarks; the LM loop of
+// k_ba_step_coop is cut at the points where the ranks must agree, the host (mageslam_b200/sharded.py) runs NCCL all-reduces on the
+// device buffers in between and takes the accept / reject decision like g2o does (ref optimization_algorithm_levenberg.cpp:57-174):
+//   LINEARIZE  errors, robust chi2 (partial), landmark blocks, this rank's part of Hpp and bp           -> xchg: chi2, max diag(Hll), diag(Hpp_r), bp_r
+//   SCHUR      backups, D^-1 (lambda), Schur products, S_r = Hpp_r - sum W D^-1 W^T (no damping yet), bs_r   -> S, bs (summed over the ranks)
+//   SOLVE      S += lambda I, dense solve (every rank the same), own landmarks' increments, update, chi2 of the trial, x^T (lambda x + b) (partial)
+//   RESTORE    rejected trial: state back from the backups;   FINISH  sum of squared errors and edge count for the returned mean
+enum { kShardLinearize = 1, kShardSchur = 2, kShardSolve = 3, kShardRestore = 4, kShardFinish = 5 };
+
+__device__ double shard_errors_chi2(const BaDev& p, double delta, int gtid, int gnt)
+{
+    double acc = 0;
+    for (int e = gtid; e < p.Ea; e += gnt) {
+        const int c = p.e_cam[e];
+        double xt[3];
+        q_rot(p.cam_q + 4 * c, p.pt_X + 3 * (size_t)p.e_pt[e], xt);
+        xt[0] += p.cam_t[3 * c]; xt[1] += p.cam_t[3 * c + 1]; xt[2] += p.cam_t[3 * c + 2];
+        const double f = p.cam_f[c];
+        const double e0 = p.e_uv[2 * e] - (xt[0] / xt[2] * f + p.cam_cx[c]), e1 = p.e_uv[2 * e + 1] - (xt[1] / xt[2] * f + p.cam_cy[c]);
+        p.err[2 * e] = e0; p.err[2 * e + 1] = e1;
+        double r0, r1;
+        huber(p.e_info[e] * (e0 * e0 + e1 * e1), delta, r0, r1);
+        acc += r0;
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(kCoopThreads) k_ba_shard_stage(const BaDev* __restrict__ prob, int stage, double delta, double lambda, int lead)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char dyn[];
+    __shared__ double sh[33];
+    __shared__ double sh_out[4];
+    __shared__ BaDev s_p;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const int gtid = blockIdx.x * nt + tid, gnt = gridDim.x * nt, gwarp = gtid >> 5, gnw = gnt >> 5;
+    if (tid == 0) s_p = prob[0];                               // the camera state stays in global memory: it lives across the stage launches
+    __syncthreads();
+    const BaDev& p = s_p;
+    BaCtl* ctl = p.ctl;
+    int seq = 0;
+    double red[2];
+    if (stage == kShardLinearize) {
+        red[0] = shard_errors_chi2(p, delta, gtid, gnt);
+        grid_sum<1>(grid, reinterpret_cast<double(&)[1]>(red[0]), p, seq, sh, sh_out);
+        if (gtid == 0) p.xchg[0] = red[0];
+        phase_build_points(p, delta, gtid, gnt);
+        phase_build_cams(p, delta, gwarp, gnw, lane);
+        grid.sync();
+        phase_sum_points(p, gtid, gnt);
+        phase_finish_cams(p, gtid, gnt);
+        grid.sync();
+        double m = 0;
+        for (int i = gtid; i < p.Pl * 3; i += gnt) m = fmax(m, fabs(p.Hll[9 * (size_t)(i / 3) + (i % 3) * 4]));
+        const double bm = block_max(m, sh);
+        double* slot = p.gred + (size_t)(seq & 1) * kCoopRedVals * kCoopMaxBlocks; seq++;
+        if (tid == 0) slot[blockIdx.x] = bm;
+        grid.sync();
+        if (gtid == 0) { double md = 0; for (unsigned bI = 0; bI < gridDim.x; bI++) md = fmax(md, slot[bI]); p.xchg[1] = md; }
+        for (int i = gtid; i < p.n; i += gnt) { p.xchg[16 + i] = p.Hpp[36 * (size_t)(i / 6) + (i % 6) * 7]; p.xchg[16 + p.n + i] = p.bp[i]; }
+    } else if (stage == kShardSchur) {
+        for (int i = tid; i < p.Kf; i += nt) {
+            const int c = p.c_cam[i];
+            for (int j = 0; j < 4; j++) p.cam_bak[7 * i + j] = p.cam_q[4 * c + j];      // every block writes the same values
+            for (int j = 0; j < 3; j++) p.cam_bak[7 * i + 4 + j] = p.cam_t[3 * c + j];
+        }
+        for (int i = gtid; i < p.Pl * 3; i += gnt) p.pt_bak[i] = p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3];
+        phase_schur_points(p, lambda, gtid, gnt);              // also zeroes p.S
+        grid.sync();
+        phase_schur_products_parts(p, gwarp, gnw, lane, (uint32_t)__cvta_generic_to_shared(dyn));
+        phase_coeff_parts(p, gwarp, gnw, lane);
+        grid.sync();
+        phase_assemble_big(p, 0.0, gtid, gnt);                 // this rank's Hpp_r - products; the damping goes on after the all-reduce
+        if (blockIdx.x == 0) phase_finish_bs(p, tid, nt);      // bs_r = bp_r - coeff_r
+    } else if (stage == kShardSolve) {
+        for (int i = gtid; i < p.n; i += gnt) p.S[(size_t)i * p.n + i] += lambda;
+        if (gtid == 0) ctl->last_ok = 1;
+        grid.sync();
+        const dense::Scratch dsc = {p.Zq, p.Ez, p.Ldiag, p.dflag, p.bs, nullptr};
+        dense::ldlt_grid(grid, p.S, p.n, dsc, dyn, &ctl->last_ok);
+        grid.sync();
+        const bool ok = *reinterpret_cast<volatile int*>(&ctl->last_ok) != 0;
+        if (ok) {
+            dense::solve_back_grid(grid, p.S, p.n, dsc, dyn);
+            for (int i = gtid; i < p.n; i += gnt) p.x[i] = p.bs[i];
+        }
+        grid.sync();
+        if (ok) phase_backsub(p, gtid, gnt);
+        __syncthreads();
+        for (int li = gtid; li < p.Pl; li += gnt)
+            for (int r = 0; r < 3; r++) p.pt_X[3 * (size_t)p.l_pt[li] + r] += p.x[p.n + 3 * li + r];
+        for (int i = gtid; i < p.Kf; i += gnt) { const int c = p.c_cam[i]; pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, p.x + 6 * i); }
+        grid.sync();
+        red[0] = shard_errors_chi2(p, delta, gtid, gnt);
+        red[1] = 0;
+        for (int j = gtid; j < 3 * p.Pl; j += gnt) { const double xj = p.x[p.n + j]; red[1] += xj * (lambda * xj + p.bl[j]); }
+        if (lead) for (int j = gtid; j < p.n; j += gnt) { const double xj = p.x[j]; red[1] += xj * (lambda * xj + p.xchg[16 + p.n + j]); }      // bp summed over the ranks
+        grid_sum<2>(grid, red, p, seq, sh, sh_out);
+        if (gtid == 0) { p.xchg[0] = ok ? red[0] : DBL_MAX; p.xchg[1] = red[1]; p.xchg[2] = ok ? 1.0 : 0.0; }
+    } else if (stage == kShardRestore) {
+        for (int i = gtid; i < p.Kf; i += gnt) {
+            const int c = p.c_cam[i];
+            for (int j = 0; j < 4; j++) p.cam_q[4 * c + j] = p.cam_bak[7 * i + j];
+            for (int j = 0; j < 3; j++) p.cam_t[3 * c + j] = p.cam_bak[7 * i + 4 + j];
+        }
+        for (int i = gtid; i < p.Pl * 3; i += gnt) p.pt_X[3 * (size_t)p.l_pt[i / 3] + i % 3] = p.pt_bak[i];
+    } else if (stage == kShardFinish) {
+        shard_errors_chi2(p, delta, gtid, gnt);                // the errors of the state as it stands (a step may end on a restored trial)
+        grid.sync();
+        red[0] = 0; red[1] = 0;
+        for (int e = gtid; e < p.Ea; e += gnt) { red[0] += p.err[2 * e] * p.err[2 * e] + p.err[2 * e + 1] * p.err[2 * e + 1]; red[1] += 1.0; }
+        grid_sum<2>(grid, red, p, seq, sh, sh_out);
+        if (gtid == 0) { p.xchg[0] = red[0]; p.xchg[1] = red[1]; }
+    }
+}
+
+// Prepares a shard (state upload, structure build) and hands out the device buffers the ranks exchange: the reduced system S (n x n),
+// its right-hand side bs (n) and the small exchange vector (16 + 2 n doubles, see k_ba_shard_stage).
+extern "C" int mage_ba_shard_prepare(mage_ba_t h, int* n, double** d_S, double** d_bs, double** d_xchg)
+{
+    MAGE_REQUIRE(h && n && d_S && d_bs && d_xchg, MAGE_ERR_INVALID, "mage_ba_shard_prepare: null argument");
+    int rc = ba_prepare(h, nullptr, 0);
+    if (rc) return rc;
+    MAGE_REQUIRE(!h->useless && h->dev.big && h->dev.nT == 0 && !h->points_fixed, MAGE_ERR_UNSUPPORTED,
+                 "sharding is for global problems (a reduced system too large for one CTA's shared memory, free points, no tether edges)");
+    MAGE_REQUIRE(h->coop_blocks_max > 1, MAGE_ERR_UNSUPPORTED, "cooperative launch not available");
+    static bool attr_set = false;
+    if (!attr_set) { MAGE_CUDA_TRY(cudaFuncSetAttribute(k_ba_shard_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dense::kSmemBytes)); attr_set = true; }
+    *n = h->dev.n; *d_S = h->dev.S; *d_bs = h->dev.bs; *d_xchg = h->dev.xchg;
+    return MAGE_OK;
+}
+
+extern "C" int mage_ba_shard_stage(mage_ba_t h, int stage, double delta, double lambda, int lead)
+{
+    MAGE_REQUIRE(h && stage >= kShardLinearize && stage <= kShardFinish && !h->dirty && h->dev.big, MAGE_ERR_INVALID, "mage_ba_shard_stage: bad argument (prepare first)");
+    const BaDev* d_dev = h->d_dev;
+    void* args[] = {(void*)&d_dev, (void*)&stage, (void*)&delta, (void*)&lambda, (void*)&lead};
+    MAGE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ba_shard_stage, dim3(h->coop_blocks_max), dim3(kCoopThreads), args, dense::kSmemBytes, h->stream));
+    MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    if (stage == kShardSolve || stage == kShardRestore) h->host_state_valid = false;      // the getters read the device state back
+    h->stats[2]++;
+    return MAGE_OK;
+}
+
+// diagnostics: a work array of the built problem by name index (0 x, 1 Hpp, 2 bp, 3 bl, 4 Hll, 5 bs, 6 S) copied to the host
+extern "C" int mage_ba_debug_get_array(mage_ba_t h, int which, double* out, long long capacity, long long* count)
+{
+    MAGE_REQUIRE(h && out && count && !h->dirty && !h->useless, MAGE_ERR_INVALID, "mage_ba_debug_get_array: bad argument");
+    const BaDev& d = h->dev;
+    const double* src = nullptr; long long n = 0;
+    switch (which) {
+        case 0: src = d.x; n = d.n + 3LL * d.Pl; break;
+        case 1: src = d.Hpp; n = 36LL * d.Kf; break;
+        case 2: src = d.bp; n = d.n; break;
+        case 3: src = d.bl; n = 3LL * d.Pl; break;
+        case 4: src = d.Hll; n = 9LL * d.Pl; break;
+        case 5: src = d.bs; n = d.n; break;
+        case 6: src = d.S; n = d.big ? (long long)d.n * d.n : 0; break;
+        default: break;
+    }
+    MAGE_REQUIRE(src && n > 0 && n <= capacity, MAGE_ERR_INVALID, "mage_ba_debug_get_array: unknown array or buffer too small (%lld needed)", n);
+    MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    MAGE_CUDA_TRY(cudaMemcpy(out, src, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost));
+    *count = n;
     return MAGE_OK;
 }
 
