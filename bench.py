@@ -755,6 +755,7 @@ def bench_sharded_global_ba(args, world, rank, dist):
     prob = synth.ba_problem(K=K, P=P, obs_per_point=D, seed=2, loop=True)
     sh = ShardedGlobalBA(prob, rank, world, dist)
     sh.StepBundleAdjustment([1.8])
+    sh.seconds.clear(); trials0 = sh.trials
     ts = []
     for _ in range(args.global_ba_steps):
         dist.barrier(); torch.cuda.synchronize()
@@ -770,8 +771,11 @@ def bench_sharded_global_ba(args, world, rank, dist):
            "config": {"workload": "global BA 500 KF / 50 000 pts / 400 000 obs, landmarks dealt out over %d ranks (landmark i on rank i %% %d), all cameras on every rank, Huber 1.8, one LM step per call" % (world, world),
                       "reduced_system": n, "timer": "host clock around the call, max over ranks, median of %d steps" % args.global_ba_steps},
            "exchange": {"collective": "NCCL all-reduce (sum) of the reduced camera system and its right-hand side, once per lambda trial",
-                        "bytes_per_trial": 8 * (n * n + n), "small_all_reduces_per_step": 4},
-           "lambda_trials": sh.trials, "dtype": "f64"}
+                        "bytes_per_trial": 8 * (n * n + n), "small_all_reduces_per_step": 3},
+           "lambda_trials_per_step": (sh.trials - trials0) / max(args.global_ba_steps, 1),
+           "phase_ms_per_step": {k: 1e3 * v / max(args.global_ba_steps, 1) for k, v in sorted(sh.seconds.items())},
+           "phase_note": "rank 0's host clock around each synchronous stage launch / all-reduce + synchronise",
+           "dtype": "f64"}
     if rank == 0:
         one = BundlerLib().load(prob)
         for _ in range(1 + args.global_ba_steps):

@@ -13,6 +13,7 @@ At the tier size one GPU solves the problem in 3.2 ms per step and two thirds of
 repeats: sharding buys memory capacity (the observations and landmark blocks are divided by the number of ranks), not time."""
 import ctypes as C
 import math
+import time
 
 import numpy as np
 
@@ -20,6 +21,7 @@ from ._lib import check, lib
 from .bundler import BundlerLib
 
 LINEARIZE, SCHUR, SOLVE, RESTORE, FINISH = 1, 2, 3, 4, 5
+STAGE_NAMES = {1: "linearize", 2: "schur", 3: "solve_update", 4: "restore", 5: "finish"}
 
 
 def shard_problem(prob, rank, world):
@@ -70,6 +72,10 @@ class _CudaShard:
         self.S = torch.as_tensor(_DeviceVector(pS.value, self.n * self.n), device="cuda")
         self.bs = torch.as_tensor(_DeviceVector(pb.value, self.n), device="cuda")
         self.xchg = torch.as_tensor(_DeviceVector(px.value, 16 + 2 * self.n), device="cuda")
+        # S and its right-hand side are neighbours in the library's work arena (a few bytes of alignment padding at most between them):
+        # one all-reduce over the span carries both
+        gap = pb.value - pS.value - 8 * self.n * self.n
+        self.system = torch.as_tensor(_DeviceVector(pS.value, self.n * self.n + gap // 8 + self.n), device="cuda") if 0 <= gap <= 4096 and gap % 8 == 0 else None
         self.sync = torch.cuda.synchronize
 
     def stage(self, stage, delta, lam, lead):
@@ -90,6 +96,7 @@ class ShardedGlobalBA:
             self.ba = backend.ba
         self.be = backend
         self.n, self.S, self.bs, self.xchg = backend.n, backend.S, backend.bs, backend.xchg
+        self.system = getattr(backend, "system", None)
         # every rank must see the same free cameras (a camera without an observation in some shard would be left out there)
         nn = torch.tensor([self.n, -self.n], dtype=torch.int64, device=self.xchg.device)
         if self.dist is not None:
@@ -99,21 +106,27 @@ class ShardedGlobalBA:
         self.lam, self.ni, self.iteration, self.user_lambda = -1.0, 2.0, 0, user_lambda
         self.trials = 0
         self.collectives = 0
+        self.seconds = {}                 # host-clock seconds per stage / kind of exchange, accumulated (each stage call is synchronous)
 
     def _stage(self, stage, delta=0.0, lam=0.0):
-        self.be.stage(stage, delta, lam, 1 if self.rank == 0 else 0)
+        t0 = time.perf_counter()
+        self.be.stage(stage, delta, lam, 1 if self.rank == 0 else 0)      # returns when the stage's kernel has finished
+        self.seconds[STAGE_NAMES[stage]] = self.seconds.get(STAGE_NAMES[stage], 0.0) + time.perf_counter() - t0
+
+    def _reduce(self, t, op):
+        t0 = time.perf_counter()
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=op)
+            self.collectives += 1
+        self.be.sync()
+        name = "all_reduce_system" if t.numel() >= self.n * self.n else "all_reduce_small"
+        self.seconds[name] = self.seconds.get(name, 0.0) + time.perf_counter() - t0
 
     def _sum(self, t):
-        if self.dist is not None:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-            self.collectives += 1
-        self.be.sync()
+        self._reduce(t, self.dist.ReduceOp.SUM if self.dist is not None else None)
 
     def _max(self, t):
-        if self.dist is not None:
-            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
-            self.collectives += 1
-        self.be.sync()
+        self._reduce(t, self.dist.ReduceOp.MAX if self.dist is not None else None)
 
     def StepBundleAdjustment(self, huber_widths):
         """LM iterations, one per Huber width (BundlerLib::StepBundleAdjustment without outlier removal). Returns the mean squared
@@ -122,17 +135,22 @@ class ShardedGlobalBA:
         for delta in np.asarray(huber_widths, np.float32):      # the reference's widths are floats (ref BundlerLib.h:58)
             delta = float(delta)
             self._stage(LINEARIZE, delta)
-            self._sum(self.xchg[0:1]); self._max(self.xchg[1:2]); self._sum(self.xchg[16:16 + 2 * n])
-            head = self.xchg[0:2].cpu().numpy()
-            current_chi = float(head[0])
+            if self.iteration == 0:                       # the largest landmark diagonal entry is only needed for the initial damping
+                self._max(self.xchg[1:2])
+                md_land = float(self.xchg[1])
+            self._sum(self.xchg)                          # chi2, diag(Hpp), bp in one vector (the slots in between are not read afterwards)
+            current_chi = float(self.xchg[0])
             if self.iteration == 0:                       # ref :69-90 computeLambdaInit: tau * max diagonal entry of the Hessian
-                md = max(float(head[1]), float(self.xchg[16:16 + n].abs().max()))
+                md = max(md_land, float(self.xchg[16:16 + n].abs().max()))
                 self.lam = self.user_lambda if self.user_lambda > 0 else 1e-5 * md
                 self.ni = 2.0
             rho, qmax, finite = 0.0, 0, True
             while True:
                 self._stage(SCHUR, delta, self.lam)
-                self._sum(self.S); self._sum(self.bs)
+                if self.system is not None:
+                    self._sum(self.system)
+                else:
+                    self._sum(self.S); self._sum(self.bs)
                 self._stage(SOLVE, delta, self.lam)
                 self._sum(self.xchg[0:3])
                 tri = self.xchg[0:3].cpu().numpy()

@@ -155,7 +155,7 @@ def test_two_rank_lm_loop_equals_one_rank_gloo():
     assert np.allclose(r0[5], be1.c, rtol=1e-8, atol=1e-10)
     lands = np.zeros(L); lands[r0[6]] = r0[7]; lands[r1[6]] = r1[7]
     assert np.allclose(lands, be1.l, rtol=1e-8, atol=1e-10)
-    # exchange steps: per LM iteration 3 small all-reduces after LINEARIZE, per lambda trial S + bs + the 3 trial scalars, one at the end of a
+    # exchange steps: the MAX for the initial damping once, per LM iteration one small all-reduce after LINEARIZE, per lambda trial S + bs + the 3 trial scalars, one at the end of a
     # call (the free-camera check at construction is not counted)
     steps = TOY_STEPS
-    assert r0[4] == 3 * steps + 3 * r0[3] + steps
+    assert r0[4] == 1 + steps + 3 * r0[3] + steps

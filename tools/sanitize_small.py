@@ -21,6 +21,8 @@ b = BundlerLib().load(prob); print(b.StepBundleAdjustment([1.8] * 3, 7.25), len(
 bs = [BundlerLib().load(synth.ba_problem(K=5, P=100, obs_per_point=3, seed=i)) for i in range(3)]
 print(StepMany(bs, [1.8] * 2, 1e9))
 big = BundlerLib().load(synth.ba_problem(K=60, P=600, obs_per_point=6, seed=4, loop=True)); print(big.StepBundleAdjustment([1.8] * 2, 1e9))
+from mageslam_b200.sharded import ShardedGlobalBA
+shd = ShardedGlobalBA(synth.ba_problem(K=60, P=600, obs_per_point=6, seed=4, loop=True)); print('sharded stages (one rank):', [shd.StepBundleAdjustment([1.8]) for _ in range(2)], shd.trials)
 po = BundlerLib(BundlerParameters(True)).load(synth.ba_problem(K=1, P=100, obs_per_point=1, n_fixed=0, seed=5)); print(po.StepBundleAdjustment([2.0] * 3, 25.0))
 # paths added later in the round: TMA variant of FAST, generic BRIEF pattern, single-level fixed-point blur, undistortion, pipelined front-end,
 # general (materialised) one-CTA BA path, tether edges
