@@ -33,8 +33,16 @@ struct BaCtl {
     int iteration, inlier_count, stop_flag, last_ok;
     int n_flagged, pad_;
     long long lm_iters, lm_trials;
+    // --- end of the head: the batched call gathers the blocks of its problems only up to here (kCtlHeadBytes)
+    // final camera state of problems of up to kCtlCams cameras (q xyzw, t per camera): it comes back with the control block, so reading the
+    // poses after a step costs no further copy (the tracking thread's pose-only BA reads one pose per call)
+    int cams_valid, pad2_;
+    double cams[7 * 16];
     long long phase_ns[32];     // cooperative kernel: time per phase seen by block 0 (diagnostics; 9.. = the dense solver's)
 };
+constexpr int kCtlCams = 16;
+constexpr size_t kCtlHeadBytes = offsetof(BaCtl, cams_valid);
+static_assert(kCtlHeadBytes % 8 == 0, "the head of BaCtl is copied as 8-byte words");
 
 struct BaDev {
     int K, P, Ea, Kf, Pl, n, nblk, cam_parts;
@@ -75,6 +83,7 @@ struct BaDev {
     // local-window fast path (fast != 0): landmarks in batches of <= kFastBE edges whose pose-landmark blocks live in shared
     // memory only; thread pair i owns the (block, part) item i and accumulates its share of the Schur products in registers
     int fast, nb, nitems;
+    int pose1;                                // pose-only problem of ONE free camera (points fixed, no tethers): fused two-pass LM in k_ba_step
     const int* batch_ptr;                     // [nb + 1] landmark boundaries
     const int4* item_def;                     // [nitems] (block, part, parts of the block, 0)
     const int2* blk_items;                    // [nblk] (first item, parts)
@@ -1663,8 +1672,133 @@ __host__ __device__ inline size_t ba_smem_need_S(int n) { return sizeof(double) 
 __host__ __device__ inline size_t ba_smem_need_cams(int K) { return sizeof(double) * 10 * (size_t)K + sizeof(int) * (size_t)K; }
 __host__ __device__ inline size_t ba_smem_need_cams_R(int K) { return sizeof(double) * 28 * (size_t)K + sizeof(int) * (size_t)K; }     // + rotation matrices (current, linearisation point)
 
-__global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq,
-                                                            unsigned dynBytes)
+// ---- pose-only problems of one free camera (ref Tracking/TrackLocalMap.cpp:421-501 OptimizeCameraPose: ArePointsFixed, the current frame's
+// pose against 50 - 400 fixed map points, 3 then 4 LM iterations, twice per frame on the tracking thread). The reduced system IS the
+// camera's 6 x 6 block, so an iteration is two sweeps over the edges -- linearise (errors, robust chi2, H and b in one pass, 28 sums per
+// thread, fixed-order reduction) and the trial state's chi2 -- around a 6 x 6 LDL^T by one thread; the general path's fifteen phases with a
+// barrier and a round trip to global memory each cost 19 us per iteration on 300 edges, this one about 3.
+__device__ __forceinline__ void h_project(const double* __restrict__ R, const double* __restrict__ t, const double* __restrict__ X, double& a, double& b, double& iz)
+{
+    const double X0 = X[0], X1 = X[1], X2 = X[2];
+    const double x = R[0] * X0 + R[1] * X1 + R[2] * X2 + t[0];
+    const double y = R[3] * X0 + R[4] * X1 + R[5] * X2 + t[1];
+    const double z = R[6] * X0 + R[7] * X1 + R[8] * X2 + t[2];
+    iz = 1.0 / z; a = x * iz; b = y * iz;
+}
+// errors of all edges at the current pose (stored: the outlier pass reads the last computed ones) and this thread's share of the robust chi2
+__device__ double h_errors_chi2(const BaDev& p, int c, double delta, int tid, int nt)
+{
+    const double* __restrict__ R = p.cam_R + 9 * c;
+    const double* __restrict__ t = p.cam_t + 3 * c;
+    const double f = p.cam_f[c], cx = p.cam_cx[c], cy = p.cam_cy[c];
+    double acc = 0;
+    for (int e = tid; e < p.Ea; e += nt) {
+        double a, b, iz;
+        h_project(R, t, p.pt_X + 3 * (size_t)p.e_pt[e], a, b, iz);
+        const double2 uv = *reinterpret_cast<const double2*>(p.e_uv + 2 * (size_t)e);
+        const double e0 = uv.x - (a * f + cx), e1 = uv.y - (b * f + cy);
+        *reinterpret_cast<double2*>(p.err + 2 * (size_t)e) = make_double2(e0, e1);
+        double r0, r1;
+        huber(p.e_info[e] * (e0 * e0 + e1 * e1), delta, r0, r1);
+        acc += r0;
+    }
+    return acc;
+}
+// linearisation at the current pose: errors, robust chi2, the upper triangle of H (21) and b (6) -> red[0..27] (shared), summed in a
+// fixed order (lanes by shuffle tree, warps in sequence); same per-edge arithmetic as f_project + f_build_cams
+__device__ void h_linearize(const BaDev& p, int c, double delta, double* __restrict__ part /* [warps][28] */, double* __restrict__ red /* [28] */)
+{
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const double* __restrict__ R = p.cam_R + 9 * c;
+    const double* __restrict__ t = p.cam_t + 3 * c;
+    const double f = p.cam_f[c], cx = p.cam_cx[c], cy = p.cam_cy[c];
+    double A[28];
+#pragma unroll
+    for (int i = 0; i < 28; i++) A[i] = 0;
+    for (int e = tid; e < p.Ea; e += nt) {
+        double a, b, iz;
+        h_project(R, t, p.pt_X + 3 * (size_t)p.e_pt[e], a, b, iz);
+        const double2 uv = *reinterpret_cast<const double2*>(p.e_uv + 2 * (size_t)e);
+        const double e0 = uv.x - (a * f + cx), e1 = uv.y - (b * f + cy);
+        *reinterpret_cast<double2*>(p.err + 2 * (size_t)e) = make_double2(e0, e1);
+        const double info = p.e_info[e];
+        double r0, r1;
+        huber(info * (e0 * e0 + e1 * e1), delta, r0, r1);
+        A[27] += r0;
+        const double w = r1 * info, o0 = -info * e0 * r1, o1 = -info * e1 * r1;
+        double P0[6], P1[6];
+        f_pose_jac(a, b, iz, f, P0, P1);
+        int idx = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            A[21 + r] += P0[r] * o0 + P1[r] * o1;
+            const double a0 = w * P0[r], a1 = w * P1[r];
+#pragma unroll
+            for (int cc = r; cc < 6; cc++) A[idx++] += a0 * P0[cc] + a1 * P1[cc];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 28; i++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) A[i] += __shfl_down_sync(0xffffffffu, A[i], o);
+        if (lane == 0) part[warp * 28 + i] = A[i];
+    }
+    __syncthreads();
+    if (tid < 28) { double s = 0; for (int w = 0; w < nw; w++) s += part[w * 28 + tid]; red[tid] = s; }
+    __syncthreads();
+}
+// (H + lambda I) x = b for the 6 x 6 block by one thread: LDL^T with the pivot rules of phase_ldlt_solve (a negative pivot fails like
+// Eigen's isPositive(), a zero pivot is skipped), x written only on success
+__device__ bool h_solve6(const double* __restrict__ red, double lambda, double* __restrict__ x)
+{
+    double S[6][6], y[6];
+    int idx = 0;
+#pragma unroll
+    for (int r = 0; r < 6; r++)
+#pragma unroll
+        for (int cc = r; cc < 6; cc++) { const double v = red[idx++]; S[r][cc] = v; S[cc][r] = v; }
+#pragma unroll
+    for (int r = 0; r < 6; r++) { S[r][r] += lambda; y[r] = red[21 + r]; }
+    bool neg = false;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const double d = S[k][k];
+        if (d < 0) neg = true;
+        const bool valid = fabs(d) > 0;
+        const double inv_d = valid ? 1.0 / d : 0.0;
+        if (valid) {
+#pragma unroll
+            for (int i = k + 1; i < 6; i++) {
+                const double aik = S[i][k] * inv_d;
+#pragma unroll
+                for (int j = k + 1; j <= i; j++) S[i][j] -= aik * S[j][k];
+            }
+#pragma unroll
+            for (int i = k + 1; i < 6; i++) S[i][k] *= inv_d;
+        }
+    }
+    if (neg) return false;
+    const double tol = 1.0 / DBL_MAX;
+#pragma unroll
+    for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int i = k + 1; i < 6; i++) y[i] -= S[i][k] * y[k];
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] = (fabs(S[i][i]) > tol) ? y[i] / S[i][i] : 0.0;
+#pragma unroll
+    for (int k = 5; k >= 0; k--)
+#pragma unroll
+        for (int i = 0; i < k; i++) y[i] -= S[k][i] * y[k];
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = y[i];
+    return true;
+}
+
+// POSE1 = true compiles the pose-only path of one free camera in (its own kernel: the registers of its 28 running sums must not weigh on
+// the batched local-window path, which lives at 128 registers for two CTAs per SM)
+template <bool POSE1>
+__global__ void __launch_bounds__(kBaThreads, POSE1 ? 1 : 2) k_ba_step_t(const BaDev* __restrict__ probs, const float* __restrict__ huberW, int nIters, float maxErrSq,
+                                                                          unsigned dynBytes)
 {
     extern __shared__ __align__(16) unsigned char dyn[];
     __shared__ double sh[33];
@@ -1817,6 +1951,77 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
             for (int i = tid; i < 2 * p.Ea; i += nt) p.err[i] = errLast[i];
             __syncthreads();
         }
+    } else if (POSE1 && p.pose1) {
+        __shared__ double s_hpart[(kBaThreads / 32) * 28], s_hred[28];
+        __shared__ int s_ok;
+        const int c = p.c_cam[0];
+        for (int it = 0; it < nIters; it++) {
+            if (s_stop) break;
+            const double delta = (double)huberW[it];
+            h_linearize(p, c, delta, s_hpart, s_hred);
+            double currentChi = s_hred[27];
+            PH(1);
+            double rho = 0;
+            int qmax = 0;
+            bool lambdaFinite = true;
+            do {
+                if (tid == 0) {
+                    if (iteration == 0 && qmax == 0) {       // ref computeLambdaInit: tau * max |diag(H)|
+                        double md = 0;
+                        int idx = 0;
+                        for (int r = 0; r < 6; r++) { md = fmax(md, fabs(s_hred[idx])); idx += 6 - r; }
+                        s_lambda = ctl->user_lambda_init > 0 ? ctl->user_lambda_init : 1e-5 * md; s_ni = 2;
+                    }
+                    double x6[6];
+                    const bool ok = h_solve6(s_hred, s_lambda, x6);
+                    if (ok) for (int i = 0; i < 6; i++) p.x[i] = x6[i];
+                    else for (int i = 0; i < 6; i++) x6[i] = p.x[i];          // a failed factorisation leaves the previous increment, like g2o
+                    for (int j = 0; j < 4; j++) p.cam_bak[j] = p.cam_q[4 * c + j];
+                    for (int j = 0; j < 3; j++) p.cam_bak[4 + j] = p.cam_t[3 * c + j];
+                    pose_oplus(p.cam_q + 4 * c, p.cam_t + 3 * c, x6);
+                    q_to_R(p.cam_q + 4 * c, p.cam_R + 9 * c);
+                    double sc = 0;
+                    for (int j = 0; j < 6; j++) sc += x6[j] * (s_lambda * x6[j] + s_hred[21 + j]);
+                    s_rho = sc;                                 // the scale until the decision below turns it into rho
+                    s_ok = ok ? 1 : 0;
+                }
+                __syncthreads();
+                PH(4);
+                const double lambda = s_lambda;
+                double tempChi = block_sum(h_errors_chi2(p, c, delta, tid, nt), sh);
+                if (!s_ok) tempChi = DBL_MAX;
+                PH(7);
+                if (tid == 0) {
+                    const double scale = s_rho + 1e-3;
+                    double r = (currentChi - tempChi) / scale;
+                    s_rho = r;
+                    if (r > 0 && isfinite(tempChi)) {
+                        double alpha = 1. - pow((2 * r - 1), 3.0);
+                        alpha = fmin(alpha, 2. / 3.);
+                        s_lambda = lambda * fmax(1. / 3., alpha);
+                        s_ni = 2;
+                        s_accept = 1;
+                    } else {
+                        s_lambda = lambda * s_ni;
+                        s_ni = s_ni * 2;
+                        s_accept = 0;
+                        for (int j = 0; j < 4; j++) p.cam_q[4 * c + j] = p.cam_bak[j];
+                        for (int j = 0; j < 3; j++) p.cam_t[3 * c + j] = p.cam_bak[4 + j];
+                        q_to_R(p.cam_q + 4 * c, p.cam_R + 9 * c);
+                    }
+                }
+                __syncthreads();
+                rho = s_rho;
+                if (s_accept) currentChi = tempChi;
+                else if (!isfinite(s_lambda)) { lambdaFinite = false; trials++; break; }
+                qmax++;
+                trials++;
+            } while (rho < 0 && qmax < 10);
+            iteration++;
+            iters++;
+            if (qmax == 10 || rho == 0 || !lambdaFinite) { if (tid == 0) s_stop = 1; }     // Terminate => Step() == false => break
+            __syncthreads();
+        }
     } else {
     bool errValid = false;              // p.err / the edge records describe the current state (true after an accepted trial)
     for (int it = 0; it < nIters; it++) {
@@ -1917,10 +2122,12 @@ __global__ void __launch_bounds__(kBaThreads, 2) k_ba_step(const BaDev* __restri
         for (int i = tid; i < 4 * p.K; i += nt) g_cam_q[i] = p.cam_q[i];
         for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
     }
+    if (p.K <= kCtlCams) for (int i = tid; i < 7 * p.K; i += nt) ctl->cams[i] = (i % 7 < 4) ? p.cam_q[4 * (i / 7) + i % 7] : p.cam_t[3 * (i / 7) + i % 7 - 4];
     if (tid == 0) {
         ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
         ctl->err_sum = errSum; ctl->inlier_count = inl; ctl->stop_flag = s_stop; ctl->n_flagged = nfl;
         ctl->lm_iters += iters; ctl->lm_trials += trials;
+        ctl->cams_valid = p.K <= kCtlCams ? 1 : 0;
     }
 }
 
@@ -2317,20 +2524,26 @@ __global__ void __launch_bounds__(kCoopThreads) k_ba_step_coop(const BaDev* __re
                 for (int i = tid; i < 4 * p.K; i += nt) g_cam_q[i] = p.cam_q[i];
                 for (int i = tid; i < 3 * p.K; i += nt) g_cam_t[i] = p.cam_t[i];
             }
+            if (p.K <= kCtlCams) for (int i = tid; i < 7 * p.K; i += nt) ctl->cams[i] = (i % 7 < 4) ? p.cam_q[4 * (i / 7) + i % 7] : p.cam_t[3 * (i / 7) + i % 7 - 4];
             if (tid == 0) {
                 ctl->lambda = s_lambda; ctl->ni = s_ni; ctl->iteration = iteration;
                 ctl->err_sum = red[0]; ctl->inlier_count = (int)red[1]; ctl->stop_flag = s_stop; ctl->n_flagged = p.Ea - (int)red[1];
                 ctl->lm_iters += iters; ctl->lm_trials += trials;
+                ctl->cams_valid = p.K <= kCtlCams ? 1 : 0;
             }
         }
     }
 }
 
 // copies every problem's control block into one contiguous table (one D2H copy for a whole batch)
+// (a warp per problem, the block copied as 8-byte words)
 __global__ void k_ba_gather_ctl(const BaDev* __restrict__ probs, int n, BaCtl* __restrict__ out)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = *probs[i].ctl;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const unsigned long long* src = reinterpret_cast<const unsigned long long*>(probs[i].ctl);
+    unsigned long long* dst = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(out) + kCtlHeadBytes * i);      // heads only, packed
+    for (int w = lane; w < (int)(kCtlHeadBytes / 8); w += 32) dst[w] = src[w];
 }
 
 } // namespace mage
@@ -2367,6 +2580,8 @@ struct HostTether { int type = -1, c1 = -1, c2 = -1; double m[8] = {0, 0, 0, 0, 
 
 } // namespace
 
+struct PinnedStage { uint8_t* p = nullptr; size_t cap = 0; };      // pooled pinned host staging buffer (below)
+
 struct mage_ba_s {
     bool points_fixed = false;
     int K = 0, P = 0, E = 0;
@@ -2377,6 +2592,10 @@ struct mage_ba_s {
     std::vector<HostTether> teth[3];    // the three constraint pools of BundlerLib.h:41-48
     long next_seq = 0;
     bool dirty = true, useless = false, state_uploaded = false, host_state_valid = true;
+    bool host_cams_valid = false;      // the camera part of the host mirror came back with the control block of the last step
+    bool defer_sync = false;           // mage_ba_step: uploads, kernel and read-back share h->stream, so nothing waits for the uploads on the host
+    std::vector<PinnedStage> pending;  // pinned staging buffers of copies still in flight on h->stream (returned to the pool after its next synchronisation)
+    float* stage_huber = nullptr;      // room for the Huber widths in the newest pending staging buffer
     double user_lambda_init = 0, lambda = -1;
     int iteration_reset = 1;           // SetCurrentLambda / InitializeOptimization reset m_iteration to 0
     std::vector<int> active;           // active observation ids in insertion order
@@ -2400,7 +2619,6 @@ struct mage_ba_s {
 
 // Pinned host staging buffers for the structure upload, pooled process-wide (cudaHostAlloc costs more than the build itself): a build
 // takes one, the batched call's worker threads take one each.
-struct PinnedStage { uint8_t* p = nullptr; size_t cap = 0; };
 static std::mutex g_stage_mu;
 static std::vector<PinnedStage> g_stage_free;
 static PinnedStage stage_acquire(size_t bytes)
@@ -2425,6 +2643,13 @@ static void stage_release(PinnedStage st)
     if (g_stage_free.size() < 16) g_stage_free.push_back(st);
     else cudaFreeHost(st.p);
 }
+// after h->stream has been synchronised: the copies that read the handle's pending staging buffers are done
+static void ba_release_pending(mage_ba_t h)
+{
+    for (auto& st : h->pending) stage_release(st);
+    h->pending.clear();
+    h->stage_huber = nullptr;
+}
 
 // dynamic shared memory for one problem: reduced system + camera state when they fit in 200 KB, else whatever subset fits
 static size_t ba_dyn_smem(int n, int K, int fast)
@@ -2439,28 +2664,34 @@ static size_t ba_dyn_smem(int n, int K, int fast)
 
 static int ba_upload_state(mage_ba_t h)
 {
-    // camera / point state and intrinsics live in one arena sized at first upload (pools are allocated once, ref :198-230)
+    // camera / point state, intrinsics and the control block live in one arena sized at first upload (pools are allocated once,
+    // ref :198-230) and go up in ONE copy from a pinned staging buffer laid out like the arena (seven copies from pageable vectors cost
+    // 40 us of driver calls per new instance -- a third of a pose-only call)
     DeviceArena& A = h->state;
-    if (!A.base) {
-        A.pooled = true;
-        size_t oq = A.reserve(sizeof(double) * 4 * h->K), ot = A.reserve(sizeof(double) * 3 * h->K);
-        size_t of = A.reserve(sizeof(double) * h->K), ox = A.reserve(sizeof(double) * h->K), oy = A.reserve(sizeof(double) * h->K);
-        size_t op = A.reserve(sizeof(double) * 3 * h->P);
-        size_t oc = A.reserve(sizeof(BaCtl)), od = A.reserve(sizeof(BaDev));
-        MAGE_CUDA_TRY(A.commit());
-        h->dev.cam_q = A.at<double>(oq); h->dev.cam_t = A.at<double>(ot);
-        h->dev.cam_f = A.at<double>(of); h->dev.cam_cx = A.at<double>(ox); h->dev.cam_cy = A.at<double>(oy);
-        h->dev.pt_X = A.at<double>(op);
-        h->d_ctl = A.at<BaCtl>(oc); h->d_dev = A.at<BaDev>(od);
-        BaCtl c{}; c.lambda = -1; c.ni = 2;
-        MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_ctl, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
-    }
-    MAGE_CUDA_TRY(cudaMemcpyAsync(h->dev.cam_q, h->cam_q.data(), sizeof(double) * 4 * h->K, cudaMemcpyHostToDevice, h->stream));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(h->dev.cam_t, h->cam_t.data(), sizeof(double) * 3 * h->K, cudaMemcpyHostToDevice, h->stream));
-    MAGE_CUDA_TRY(cudaMemcpyAsync((void*)h->dev.cam_f, h->cam_f.data(), sizeof(double) * h->K, cudaMemcpyHostToDevice, h->stream));
-    MAGE_CUDA_TRY(cudaMemcpyAsync((void*)h->dev.cam_cx, h->cam_cx.data(), sizeof(double) * h->K, cudaMemcpyHostToDevice, h->stream));
-    MAGE_CUDA_TRY(cudaMemcpyAsync((void*)h->dev.cam_cy, h->cam_cy.data(), sizeof(double) * h->K, cudaMemcpyHostToDevice, h->stream));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(h->dev.pt_X, h->pt_X.data(), sizeof(double) * 3 * h->P, cudaMemcpyHostToDevice, h->stream));
+    MAGE_REQUIRE(!A.base, MAGE_ERR_INVALID, "ba_upload_state: state already uploaded");
+    A.pooled = true;
+    const size_t oq = A.reserve(sizeof(double) * 4 * h->K), ot = A.reserve(sizeof(double) * 3 * h->K);
+    const size_t of = A.reserve(sizeof(double) * h->K), ox = A.reserve(sizeof(double) * h->K), oy = A.reserve(sizeof(double) * h->K);
+    const size_t op = A.reserve(sizeof(double) * 3 * h->P);
+    const size_t oc = A.reserve(sizeof(BaCtl)), up_end = A.reserve(0, 256), od = A.reserve(sizeof(BaDev));
+    MAGE_CUDA_TRY(A.commit());
+    h->dev.cam_q = A.at<double>(oq); h->dev.cam_t = A.at<double>(ot);
+    h->dev.cam_f = A.at<double>(of); h->dev.cam_cx = A.at<double>(ox); h->dev.cam_cy = A.at<double>(oy);
+    h->dev.pt_X = A.at<double>(op);
+    h->d_ctl = A.at<BaCtl>(oc); h->d_dev = A.at<BaDev>(od);
+    PinnedStage stage = stage_acquire(up_end);
+    MAGE_REQUIRE(stage.p, MAGE_ERR_CUDA, "ba_upload_state: no pinned staging memory");
+    memset(stage.p, 0, up_end);
+    memcpy(stage.p + oq, h->cam_q.data(), sizeof(double) * 4 * h->K); memcpy(stage.p + ot, h->cam_t.data(), sizeof(double) * 3 * h->K);
+    memcpy(stage.p + of, h->cam_f.data(), sizeof(double) * h->K); memcpy(stage.p + ox, h->cam_cx.data(), sizeof(double) * h->K);
+    memcpy(stage.p + oy, h->cam_cy.data(), sizeof(double) * h->K);
+    memcpy(stage.p + op, h->pt_X.data(), sizeof(double) * 3 * h->P);
+    BaCtl c{}; c.lambda = -1; c.ni = 2;
+    c.user_lambda_init = h->user_lambda_init;                 // iteration 0 and the user lambda of a new instance go up with the block itself
+    h->iteration_reset = 0;
+    memcpy(stage.p + oc, &c, sizeof(c));
+    h->pending.push_back(stage);
+    MAGE_CUDA_TRY(cudaMemcpyAsync(A.base, stage.p, up_end, cudaMemcpyHostToDevice, h->stream));
     h->state_uploaded = true;
     return MAGE_OK;
 }
@@ -2705,7 +2936,8 @@ static int ba_build_structure(mage_ba_t h)
     MAGE_CUDA_TRY(cudaMemsetAsync(W.base + upload_end, 0, W.size - upload_end, h->stream));
     // the host-built tables are packed into one pinned staging buffer (same offsets as in the arena) and go up in one copy: twenty
     // separate copies from pageable vectors cost 0.2 ms of driver calls per window
-    PinnedStage stage = stage_acquire(std::max<size_t>(upload_end, 256));
+    const size_t st_dev = align_up(std::max<size_t>(upload_end, 256), 256), st_huber = st_dev + align_up(sizeof(BaDev), 256);      // the problem descriptor and the Huber widths ride along
+    PinnedStage stage = stage_acquire(st_huber + 64 * sizeof(float));
     MAGE_REQUIRE(stage.p, MAGE_ERR_CUDA, "ba_build_structure: no pinned staging memory");
     memset(stage.p, 0, upload_end);
     auto up = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
@@ -2741,18 +2973,25 @@ static int ba_build_structure(mage_ba_t h)
     d.flags = W.at<unsigned char>(o_flags);
     d.Hc = W.at<double>(o_Hc); d.cam_R = W.at<double>(o_camR); d.cam_Rold = d.cam_R + 9 * (size_t)h->K;
     d.fast = fast; d.nb = nb; d.nitems = nitems;
+    d.pose1 = (h->points_fixed && Kf == 1 && Pl == 0 && nT == 0 && !getenv("MAGE_BA_NO_POSE1")) ? 1 : 0;
     d.batch_ptr = W.at<int>(o_bptr2); d.item_def = W.at<int4>(o_idef); d.blk_items = W.at<int2>(o_bitems);
     d.cam_diag = W.at<int>(o_cdiag); d.bb_ptr = W.at<int>(o_bbptr); d.bpairs = W.at<ushort2>(o_bpairs);
     d.ctl = h->d_ctl;
     d.spart = W.at<double>(o_spart); d.gred = W.at<double>(o_gred); d.schur_parts = schur_parts;
     d.big = big; d.Zq = W.at<int8_t>(o_Zq); d.Ez = W.at<int>(o_Ez); d.Ldiag = W.at<double>(o_Ldiag); d.dflag = W.at<int>(o_dflag); d.xchg = W.at<double>(o_xchg);
     d.nT = nT; d.t_def = W.at<int4>(o_tdef); d.t_meas = W.at<double>(o_tmeas); d.t_err = W.at<double>(o_terr); d.t_J = W.at<double>(o_tJ);
+    memcpy(stage.p + st_dev, &d, sizeof(BaDev));
     cudaError_t eup = upload_end ? cudaMemcpyAsync(W.base, stage.p, upload_end, cudaMemcpyHostToDevice, h->stream) : cudaSuccess;
-    if (eup == cudaSuccess) eup = cudaMemcpyAsync(h->d_dev, &d, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream);
+    if (eup == cudaSuccess) eup = cudaMemcpyAsync(h->d_dev, stage.p + st_dev, sizeof(BaDev), cudaMemcpyHostToDevice, h->stream);
     mark("enqueue uploads");
-    // the staging buffer goes back to the pool and `d` out of scope on return: make sure the copies have been consumed
-    if (eup == cudaSuccess) eup = cudaStreamSynchronize(h->stream);
-    stage_release(stage);
+    h->pending.push_back(stage);
+    h->stage_huber = reinterpret_cast<float*>(stage.p + st_huber);
+    // the staging buffers go back to the pool once the copies have been consumed: here, unless the caller keeps everything on h->stream
+    // and synchronises it itself at the end of the call (mage_ba_step)
+    if (!h->defer_sync) {
+        if (eup == cudaSuccess) eup = cudaStreamSynchronize(h->stream);
+        ba_release_pending(h);
+    }
     MAGE_CUDA_TRY(eup);
     mark("sync");
     return MAGE_OK;
@@ -2766,22 +3005,31 @@ extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
     mage_ba_s* h = new mage_ba_s();
     h->points_fixed = are_points_fixed != 0;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return MAGE_ERR_CUDA; }
-    if (cudaFuncSetAttribute(k_ba_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); cudaStreamDestroy(h->stream); delete h; return MAGE_ERR_CUDA; }
-    // cooperative (multi-CTA) variant for the single-problem latency path
-    {
-        int dev = 0, coop = 0, sms = 0, per_sm = 0;
-        cudaGetDevice(&dev);
+    // kernel attributes and the co-resident grid of the cooperative (multi-CTA) variant: set up once per device, not per instance (the
+    // tracking thread makes a new instance per pose-only call: the four driver queries cost 25 us each time)
+    struct DevSetup { std::once_flag once; bool ok = false; int coop_blocks_max = 0; };
+    static DevSetup g_setup[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DevSetup& ds = g_setup[dev & 63];
+    std::call_once(ds.once, [&] {
+        ds.ok = cudaFuncSetAttribute(k_ba_step_t<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess &&
+                cudaFuncSetAttribute(k_ba_step_t<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+        int coop = 0, sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const char* env = getenv("MAGE_BA_COOP_BLOCKS");
-        int want = env ? atoi(env) : 32;
-        if (coop && want > 0 && cudaFuncSetAttribute(k_ba_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmemMax) == cudaSuccess &&
+        if (coop && cudaFuncSetAttribute(k_ba_step_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCoopSmemMax) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ba_step_coop, kCoopThreads, kCoopSmemMax) == cudaSuccess && per_sm > 0)
         {
-            h->coop_blocks_max = std::min(kCoopMaxBlocks, sms * per_sm);
-            h->coop_blocks = std::min(want, h->coop_blocks_max);
+            ds.coop_blocks_max = std::min(kCoopMaxBlocks, sms * per_sm);
         }
         cudaGetLastError();
+    });
+    if (!ds.ok) { set_error("cudaFuncSetAttribute failed"); cudaStreamDestroy(h->stream); delete h; return MAGE_ERR_CUDA; }
+    {
+        const char* env = getenv("MAGE_BA_COOP_BLOCKS");          // read per instance: the tools sweep it inside one process
+        const int want = env ? atoi(env) : 32;
+        if (want > 0 && ds.coop_blocks_max > 0) { h->coop_blocks_max = ds.coop_blocks_max; h->coop_blocks = std::min(want, ds.coop_blocks_max); }
     }
     *out = h;
     return MAGE_OK;
@@ -2791,6 +3039,7 @@ extern "C" void mage_ba_destroy(mage_ba_t h)
 {
     if (!h) return;
     cudaStreamSynchronize(h->stream);
+    ba_release_pending(h);
     h->state.release(); h->work.release();
     if (h->d_huber) cudaFreeAsync(h->d_huber, h->stream);
     if (h->d_table) cudaFree(h->d_table);
@@ -2970,7 +3219,11 @@ static int ba_prepare(mage_ba_t h, const float* huber, int n_iters, bool upload_
         h->huber_cap = std::max(16, n_iters);
         MAGE_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&h->d_huber), sizeof(float) * h->huber_cap, h->stream));
     }
-    if (upload_huber && n_iters) MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_huber, huber, sizeof(float) * n_iters, cudaMemcpyHostToDevice, h->stream));
+    if (upload_huber && n_iters) {
+        const float* src = huber;
+        if (h->stage_huber && n_iters <= 64) { memcpy(h->stage_huber, huber, sizeof(float) * n_iters); src = h->stage_huber; }      // pinned: no staging by the driver
+        MAGE_CUDA_TRY(cudaMemcpyAsync(h->d_huber, src, sizeof(float) * n_iters, cudaMemcpyHostToDevice, h->stream));
+    }
     if (h->iteration_reset) {
         // m_iteration = 0 (and the user lambda) take effect at the next solve()
         struct { double user; } u{h->user_lambda_init};
@@ -2978,6 +3231,7 @@ static int ba_prepare(mage_ba_t h, const float* huber, int n_iters, bool upload_
         int zero = 0;
         MAGE_CUDA_TRY(cudaMemcpyAsync(&h->d_ctl->iteration, &zero, sizeof(int), cudaMemcpyHostToDevice, h->stream));
         MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+        ba_release_pending(h);
         h->iteration_reset = 0;
     }
     return MAGE_OK;
@@ -3001,6 +3255,7 @@ static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, f
         s = h->stream;
         MAGE_CUDA_TRY(cudaMemcpyAsync(&h->h_ctl, h->d_ctl, sizeof(BaCtl), cudaMemcpyDeviceToHost, s));
         MAGE_CUDA_TRY(cudaStreamSynchronize(s));
+        ba_release_pending(h);
     }
     { int rc = ba_fetch_flags(h, s); if (rc) return rc; }
     const BaCtl& c = h->h_ctl;
@@ -3008,6 +3263,14 @@ static int ba_finish(mage_ba_t h, unsigned int* outliers, int cap, int* n_out, f
     h->lambda = c.lambda;
     h->stats[0] = c.lm_iters; h->stats[1] = c.lm_trials;
     h->host_state_valid = false;
+    h->host_cams_valid = c.cams_valid != 0 && h->K <= kCtlCams;
+    if (h->host_cams_valid) {
+        for (int k = 0; k < h->K; k++) {
+            for (int j = 0; j < 4; j++) h->cam_q[4 * k + j] = c.cams[7 * k + j];
+            for (int j = 0; j < 3; j++) h->cam_t[3 * k + j] = c.cams[7 * k + 4 + j];
+        }
+        if (h->points_fixed) h->host_state_valid = true;      // the points never move: the host mirror is complete again
+    }
     std::vector<std::pair<long, int>> flagged;                          // (insertion sequence, observation) of every removed edge
     if (c.n_flagged > 0)                                                // nothing to scan (and no flag read-back) when the kernel flagged no edge
         for (int a = 0; a < h->dev.Ea; a++)
@@ -3031,8 +3294,11 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
                             int* n_outliers, float* mean_sq_error)
 {
     MAGE_REQUIRE(h && n_outliers && mean_sq_error && (huber || n_iters == 0) && n_iters >= 0, MAGE_ERR_INVALID, "mage_ba_step: bad argument");
+    h->defer_sync = true;
     int rc = ba_prepare(h, huber, n_iters);
+    h->defer_sync = false;
     if (rc) return rc;
+    if (h->useless && !h->pending.empty()) { MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream)); ba_release_pending(h); }
     if (!h->useless) {
         // dynamic shared memory: the reduced system (small problems) or the dense solver's staging (large ones), then the camera state
         // when it still fits -- otherwise the cameras stay in global memory
@@ -3057,7 +3323,9 @@ extern "C" int mage_ba_step(mage_ba_t h, const float* huber, int n_iters, float 
             void* args[] = {(void*)&d_dev, (void*)&d_hub, (void*)&n_iters, (void*)&max_err_sq, (void*)&dynb};
             MAGE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ba_step_coop, dim3(coop_grid), dim3(kCoopThreads), args, coop_smem, h->stream));
         } else {
-            k_ba_step<<<1, kBaThreads, ba_dyn_smem(h->dev.n, h->dev.K, h->dev.fast), h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, (unsigned)ba_dyn_smem(h->dev.n, h->dev.K, h->dev.fast));
+            const unsigned dyn1 = (unsigned)ba_dyn_smem(h->dev.n, h->dev.K, h->dev.fast);
+            if (h->dev.pose1) k_ba_step_t<true><<<1, kBaThreads, dyn1, h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, dyn1);
+            else k_ba_step_t<false><<<1, kBaThreads, dyn1, h->stream>>>(h->d_dev, h->d_huber, n_iters, max_err_sq, dyn1);
         }
         MAGE_CUDA_TRY(cudaGetLastError());
         h->stats[2]++;
@@ -3149,7 +3417,7 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
         BaDev* d_table = lead->d_table;
         cudaError_t e = cudaMemcpyAsync(d_table, table.data(), sizeof(BaDev) * table.size(), cudaMemcpyHostToDevice, lead->stream);
         if (e == cudaSuccess) {
-            { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step<<<(unsigned)table.size(), kBaThreads, dyn, lead->stream>>>(d_table, lead->d_huber, n_iters, max_err_sq, (unsigned)dyn); }
+            { ProfScope ps(PROF_BA_STEP, lead->stream); k_ba_step_t<false><<<(unsigned)table.size(), kBaThreads, dyn, lead->stream>>>(d_table, lead->d_huber, n_iters, max_err_sq, (unsigned)dyn); }
             e = cudaGetLastError();
         }
         MAGE_CUDA_TRY(e);
@@ -3163,10 +3431,18 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
             MAGE_CUDA_TRY(cudaMalloc(&lead->d_ctl_table, sizeof(BaCtl) * nl));
         }
         lead->h_ctl_table.resize(nl);
-        k_ba_gather_ctl<<<div_up(nl, 128), 128, 0, lead->stream>>>(lead->d_table, nl, lead->d_ctl_table);
-        MAGE_CUDA_TRY(cudaMemcpyAsync(lead->h_ctl_table.data(), lead->d_ctl_table, sizeof(BaCtl) * nl, cudaMemcpyDeviceToHost, lead->stream));
-        MAGE_CUDA_TRY(cudaStreamSynchronize(lead->stream));
-        for (int k = 0; k < nl; k++) hs[live[k]]->h_ctl = lead->h_ctl_table[k];
+        k_ba_gather_ctl<<<div_up(nl, 4), 128, 0, lead->stream>>>(lead->d_table, nl, lead->d_ctl_table);
+        PinnedStage st = stage_acquire(kCtlHeadBytes * nl);          // pinned: the read-back is one DMA, not a staged pageable copy
+        void* dst = st.p ? static_cast<void*>(st.p) : static_cast<void*>(lead->h_ctl_table.data());
+        cudaError_t e = cudaMemcpyAsync(dst, lead->d_ctl_table, kCtlHeadBytes * nl, cudaMemcpyDeviceToHost, lead->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(lead->stream);
+        if (e == cudaSuccess)
+            for (int k = 0; k < nl; k++) {       // the camera states stay on the device: the getters fetch them on demand
+                memcpy(&hs[live[k]]->h_ctl, static_cast<const uint8_t*>(dst) + kCtlHeadBytes * k, kCtlHeadBytes);
+                hs[live[k]]->h_ctl.cams_valid = 0;
+            }
+        stage_release(st);
+        MAGE_CUDA_TRY(e);
     }
     for (int i = 0; i < n; i++) {
         int nout = 0;
@@ -3179,10 +3455,13 @@ extern "C" int mage_ba_step_many(mage_ba_t* hs, int n, const float* huber, int n
 static int ba_sync_host_state(mage_ba_t h)
 {
     if (h->host_state_valid || !h->state_uploaded) return MAGE_OK;
-    MAGE_CUDA_TRY(cudaMemcpyAsync(h->cam_q.data(), h->dev.cam_q, sizeof(double) * 4 * h->K, cudaMemcpyDeviceToHost, h->stream));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(h->cam_t.data(), h->dev.cam_t, sizeof(double) * 3 * h->K, cudaMemcpyDeviceToHost, h->stream));
+    if (!h->host_cams_valid) {
+        MAGE_CUDA_TRY(cudaMemcpyAsync(h->cam_q.data(), h->dev.cam_q, sizeof(double) * 4 * h->K, cudaMemcpyDeviceToHost, h->stream));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(h->cam_t.data(), h->dev.cam_t, sizeof(double) * 3 * h->K, cudaMemcpyDeviceToHost, h->stream));
+    }
     MAGE_CUDA_TRY(cudaMemcpyAsync(h->pt_X.data(), h->dev.pt_X, sizeof(double) * 3 * h->P, cudaMemcpyDeviceToHost, h->stream));
     MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
+    ba_release_pending(h);
     h->host_state_valid = true;
     return MAGE_OK;
 }
@@ -3384,7 +3663,8 @@ extern "C" int mage_ba_shard_stage(mage_ba_t h, int stage, double delta, double 
     void* args[] = {(void*)&d_dev, (void*)&stage, (void*)&delta, (void*)&lambda, (void*)&lead};
     MAGE_CUDA_TRY(cudaLaunchCooperativeKernel((const void*)k_ba_shard_stage, dim3(h->coop_blocks_max), dim3(kCoopThreads), args, dense::kSmemBytes, h->stream));
     MAGE_CUDA_TRY(cudaStreamSynchronize(h->stream));
-    if (stage == kShardSolve || stage == kShardRestore) h->host_state_valid = false;      // the getters read the device state back
+    ba_release_pending(h);
+    if (stage == kShardSolve || stage == kShardRestore) { h->host_state_valid = false; h->host_cams_valid = false; }      // the getters read the device state back
     h->stats[2]++;
     return MAGE_OK;
 }
