@@ -540,6 +540,10 @@ def run_ours(args):
             line["radius_match"] = bench_radius(kps, desc, cnt)
         except Exception as e:      # pragma: no cover
             line["radius_match"] = {"error": str(e)[:300]}
+        try:
+            line["pose_only_ba"] = bench_pose_only()
+        except Exception as e:      # pragma: no cover
+            line["pose_only_ba"] = {"error": str(e)[:300]}
         if args.global_ba_steps > 0:
             try:
                 line["global_ba"] = bench_global_ba(args)
@@ -660,6 +664,36 @@ def bench_ba(args, world, rank, dist):
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_ba_baseline(parallel=False)
     return out
+
+
+def bench_pose_only(points=300, reps=200):
+    """The tracking thread's pose-only bundle adjustment (ref Tracking/TrackLocalMap.cpp:421-501 OptimizeCameraPose: a new BundlerLib with
+    ArePointsFixed per call, the frame's camera against its matched map points, 3 then 4 LM iterations with outlier removal in between,
+    then the pose is read back) -- latency of the whole call sequence through the C ABI, host clock; the compiled reference runs the same
+    sequence on one host core (its set-up goes through per-element Python calls and is therefore left out of its figure)."""
+    from mageslam_b200 import synth
+    from mageslam_b200.bundler import BundlerLib, BundlerParameters
+    from tests.oracle_ba import BaOracle, have_ref
+    probs = [synth.ba_problem(K=1, P=points, obs_per_point=1, n_fixed=0, pose_sigma=0.03, seed=5 + i) for i in range(8)]
+
+    def run(make, n):
+        tot, solve = [], []
+        for r in range(n):
+            t0 = time.perf_counter(); b = make().load(probs[r % 8])
+            t1 = time.perf_counter(); b.StepBundleAdjustment([2.0] * 3, 25.0); b.StepBundleAdjustment([2.0] * 4, 25.0); b.poses()
+            t2 = time.perf_counter()
+            tot.append(t2 - t0); solve.append(t2 - t1)
+        return 1e6 * statistics.median(tot[n // 4:]), 1e6 * statistics.median(solve[n // 4:])
+
+    g_tot, g_solve = run(lambda: BundlerLib(BundlerParameters(True)), reps)
+    kind = "reference" if have_ref() else "port"
+    _, c_solve = run(lambda: BaOracle("ref" if have_ref() else "port", True), 40)
+    return {"metric": "pose_only_ba_us_per_frame_call", "value": g_tot, "unit": "us", "higher_is_better": False,
+            "config": {"workload": "pose-only BA as TrackLocalMap::OptimizeCameraPose runs it: new instance, 1 camera x %d fixed points, 3 + 4 LM iterations (Huber 2.0, max error 25), pose read back" % points,
+                       "timer": "host clock around the C-ABI call sequence, median of %d calls" % (reps - reps // 4)},
+            "solve_only_us": g_solve, "kernel": "k_ba_step_t<true> (one CTA, two sweeps over the edges per iteration)",
+            "cpu_baseline": {"value": c_solve, "unit": "us", "cores": 1, "kind": kind, "sample": "the two StepBundleAdjustment calls + pose read-back of the same problems (set-up excluded), median of 30"},
+            "dtype": "f64"}
 
 
 def bench_global_ba(args):

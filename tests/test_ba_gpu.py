@@ -121,6 +121,40 @@ def test_pose_only_ba_like_track_local_map():
     run_side_by_side(gpu, chk, [2.0] * 4, 25.0, 1, tag="pose4")
 
 
+@pytest.mark.parametrize("P,pose_sigma,outlier_frac,max_err,seed", [(50, 0.02, 0.0, 25.0, 11), (120, 0.05, 0.1, 7.25, 12), (400, 0.03, 0.05, 25.0, 13), (260, 0.1, 0.0, 2.0, 14)])
+def test_pose_only_fused_kernel_cases(P, pose_sigma, outlier_frac, max_err, seed):
+    """the one-free-camera pose-only kernel (k_ba_step_t<true>) against the compiled reference: few and many points, gross outliers with a
+    tight and a loose error bound (removed observations re-arm the solver), changing Huber widths, a badly perturbed start"""
+    prob = synth.ba_problem(K=1, P=P, obs_per_point=1, n_fixed=0, pose_sigma=pose_sigma, outlier_frac=outlier_frac, seed=seed)
+    gpu = BundlerLib(BundlerParameters(True)).load(prob)
+    chk = best_checker(True).load(prob)
+    run_side_by_side(gpu, chk, [2.0] * 3, max_err, 1, tag="pose_a")
+    run_side_by_side(gpu, chk, [1.5, 1.0, 0.5, 0.5], max_err, 2, tag="pose_b")
+    assert gpu.stats()["kernel_launches"] == 3
+
+
+def test_pose_only_one_free_camera_among_fixed_ones():
+    """points fixed, three cameras of which one is free: the observations of the fixed cameras connect fixed vertices only and drop out
+    (ref sparse_optimizer.cpp:208-272 allVerticesFixed), the free camera takes the fused pose-only path; the getters return every camera"""
+    prob = synth.ba_problem(K=3, P=200, obs_per_point=3, n_fixed=2, pose_sigma=0.03, seed=21)
+    gpu = BundlerLib(BundlerParameters(True)).load(prob)
+    chk = best_checker(True).load(prob)
+    run_side_by_side(gpu, chk, [2.0] * 3, 25.0, 2, tag="pose_fixed_mix")
+
+
+def test_pose_only_general_path_agrees(monkeypatch):
+    """MAGE_BA_NO_POSE1=1 sends the same problem through the general one-CTA path: same poses to rounding"""
+    prob = synth.ba_problem(K=1, P=150, obs_per_point=1, n_fixed=0, pose_sigma=0.04, seed=31)
+    a = BundlerLib(BundlerParameters(True)).load(prob)
+    ma = [a.StepBundleAdjustment([2.0] * 3, 25.0), a.StepBundleAdjustment([2.0] * 4, 25.0)]
+    monkeypatch.setenv("MAGE_BA_NO_POSE1", "1")
+    b = BundlerLib(BundlerParameters(True)).load(prob)
+    mb = [b.StepBundleAdjustment([2.0] * 3, 25.0), b.StepBundleAdjustment([2.0] * 4, 25.0)]
+    assert np.allclose(ma, mb, rtol=1e-6) and a.last_outliers == b.last_outliers
+    assert rel_frobenius(a.poses()[0], b.poses()[0]) < 1e-6 and rel_frobenius(a.poses()[1], b.poses()[1]) < 1e-6
+    assert abs(a.GetCurrentLambda() - b.GetCurrentLambda()) <= 1e-5 * abs(b.GetCurrentLambda())
+
+
 def test_per_element_setters_equal_bulk_upload():
     prob = synth.ba_problem(K=5, P=80, obs_per_point=3, seed=9)
     a = BundlerLib().load(prob)
