@@ -334,6 +334,19 @@ int  mage_ba_get_state_f64(mage_ba_t h, double* cam_qxyzw_t /*K*7*/, double* poi
 int  mage_ba_get_stats(mage_ba_t h, int64_t stats[4]);
 /* diagnostics: accumulated nanoseconds per phase of the cooperative kernel as seen by block 0 */
 int  mage_ba_debug_phase_ns(mage_ba_t h, long long phase_ns[16]);
+/* TrackLocalMap::OptimizeCameraPose in one call (ref Tracking/TrackLocalMap.cpp:421-501; it runs twice per frame on the tracking thread):
+ * equivalent to a new BundlerLib with ArePointsFixed, AllocateCameras(1) + SetCameraPose(0, position, rotation, intrinsics, false),
+ * n map points with one observation each (SetMapPoint(i), SetObservation(i, projection_i, 0, i, information_i)), ONE
+ * StepBundleAdjustment(n_iters x huber_width, max_outlier_err_sq, outliers) and GetPose(0) -- same kernel and results as that sequence
+ * through mage_ba_*, without the instance, its structure build and its copies (one upload, one launch, one read-back).
+ * position / rotation (column-major 3x3) = the view transform, intrinsics = (cx, cy, fx, fy); outliers receives the indices of the
+ * observations the reference would remove (at most `capacity` are written, *n_outliers is the full count); mean_sq_error is nullable.
+ * n_iters <= 64. Thread-safe (contexts are pooled per process). */
+int  mage_optimize_camera_pose(const float position[3], const float rotation_colmajor[9], const float intrinsics[4], int n,
+                               const float* map_points /*n*3*/, const float* projections /*n*2*/, const float* information /*n*/,
+                               int n_iters, float huber_width, float max_outlier_err_sq, float out_position[3],
+                               float out_rotation_colmajor[9], unsigned int* outliers, int capacity, int* n_outliers,
+                               float* mean_sq_error);
 /* Sharded global bundle adjustment (SURVEY 8(e) "next": observations partitioned by landmark over the ranks, the all-reduce of the reduced
  * camera system is the one exchange step; ref block_solver.hpp:331-422 builds that system, linear_solver_dense.h:65-113 solves it). Every
  * rank creates the problem with ALL cameras and its own points / observations; mage_ba_shard_prepare builds the structure and returns the

@@ -82,6 +82,7 @@ def lib():
     L.mage_spatial_index_rank.argtypes = [vp, vp]
     L.mage_radius_match.argtypes = [vp, vp, ci, vp, vp, vp, vp, vp, cf, ci, ci, vp, C.POINTER(ci), vp]
     L.mage_project_map_points.argtypes = [vp, vp, ci, vp, vp, vp, vp]
+    L.mage_optimize_camera_pose.argtypes = [vp, vp, vp, ci, vp, vp, vp, ci, cf, cf, vp, vp, vp, ci, C.POINTER(ci), C.POINTER(cf)]
     L.mage_project_map_points_device.argtypes = [vp, vp, ci, vp, vp, vp, vp]
     L.mage_undistort_keypoints.argtypes = [vp, ci, vp, vp, vp]
     L.mage_undistort_keypoints_device.argtypes = [vp, vp, ci, ci, vp, vp, vp]

@@ -2997,17 +2997,11 @@ static int ba_build_structure(mage_ba_t h)
     return MAGE_OK;
 }
 
-extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
+// kernel attributes and the co-resident grid of the cooperative (multi-CTA) variant: set up once per device, not per instance (the
+// tracking thread makes a new instance per pose-only call: the four driver queries cost 25 us each time)
+struct DevSetup { std::once_flag once; bool ok = false; int coop_blocks_max = 0; };
+static const DevSetup& ba_device_setup()
 {
-    MAGE_REQUIRE(out, MAGE_ERR_INVALID, "mage_ba_create: null argument");
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: bundle adjustment has no CPU fallback"); return MAGE_ERR_CUDA; }
-    mage_ba_s* h = new mage_ba_s();
-    h->points_fixed = are_points_fixed != 0;
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return MAGE_ERR_CUDA; }
-    // kernel attributes and the co-resident grid of the cooperative (multi-CTA) variant: set up once per device, not per instance (the
-    // tracking thread makes a new instance per pose-only call: the four driver queries cost 25 us each time)
-    struct DevSetup { std::once_flag once; bool ok = false; int coop_blocks_max = 0; };
     static DevSetup g_setup[64];
     int dev = 0;
     cudaGetDevice(&dev);
@@ -3025,6 +3019,18 @@ extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
         }
         cudaGetLastError();
     });
+    return ds;
+}
+
+extern "C" int mage_ba_create(int are_points_fixed, mage_ba_t* out)
+{
+    MAGE_REQUIRE(out, MAGE_ERR_INVALID, "mage_ba_create: null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: bundle adjustment has no CPU fallback"); return MAGE_ERR_CUDA; }
+    mage_ba_s* h = new mage_ba_s();
+    h->points_fixed = are_points_fixed != 0;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete h; return MAGE_ERR_CUDA; }
+    const DevSetup& ds = ba_device_setup();
     if (!ds.ok) { set_error("cudaFuncSetAttribute failed"); cudaStreamDestroy(h->stream); delete h; return MAGE_ERR_CUDA; }
     {
         const char* env = getenv("MAGE_BA_COOP_BLOCKS");          // read per instance: the tools sweep it inside one process
@@ -3520,6 +3526,180 @@ extern "C" int mage_ba_debug_phase_ns(mage_ba_t h, long long out[16])
     BaCtl c;
     MAGE_CUDA_TRY(cudaMemcpy(&c, h->d_ctl, sizeof(c), cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; i++) out[i] = c.phase_ns[i];
+    return MAGE_OK;
+}
+
+// ---- TrackLocalMap::OptimizeCameraPose in one call (ref Tracking/TrackLocalMap.cpp:421-501). The reference builds
+// a BundlerLib with ArePointsFixed for every call -- one camera, the frame's matched map points, one observation each --, runs ONE
+// StepBundleAdjustment(numIterations x huberWidth, maxOutlierErrorSquared, outliers) and reads pose 0 back; it does so twice per frame on
+// the tracking thread. Through the handle interface that is an instance, two arenas, a structure build and five copies per call
+// (250 us for 30 us of kernel); here the whole problem is packed into ONE pinned buffer laid out like the device arena of a cached
+// context, goes up in one copy, runs the same kernel as the handle path (k_ba_step_t<true>: same arithmetic, same results) and comes
+// back -- control block, camera state and outlier flags -- in one copy.
+namespace {
+struct PoseCtx { cudaStream_t stream = nullptr; uint8_t* d = nullptr; uint8_t* h = nullptr; size_t cap = 0; int dev = -1; };
+std::mutex g_pose_mu;
+std::vector<PoseCtx> g_pose_free;
+
+struct PoseLayout {
+    size_t dev, ctl, flags, huber, cam, x, idx, e_cam, e_pt, pt, uv, info, upload_end, err, bak, R, total;
+    explicit PoseLayout(int n)
+    {
+        const size_t N = (size_t)std::max(n, 1);
+        size_t o = 0;
+        auto take = [&](size_t bytes, size_t align = 16) { o = align_up(o, align); const size_t at = o; o += bytes; return at; };
+        dev = take(sizeof(BaDev), 256);
+        ctl = take(sizeof(BaCtl), 256); flags = take(N, 8);            // read back together: [ctl, flags + n)
+        huber = take(64 * sizeof(float));
+        cam = take(10 * sizeof(double));                               // q(4) t(3) f cx cy
+        x = take(6 * sizeof(double));
+        idx = take(2 * sizeof(int));                                   // cam_h[0] = 0, c_cam[0] = 0
+        e_cam = take(N * sizeof(int)); e_pt = take(N * sizeof(int));
+        pt = take(3 * N * sizeof(double)); uv = take(2 * N * sizeof(double)); info = take(N * sizeof(double));
+        upload_end = take(0, 256);
+        err = take(2 * N * sizeof(double)); bak = take(7 * sizeof(double)); R = take(18 * sizeof(double));
+        total = take(0, 256);
+    }
+};
+
+void pose_ctx_release(PoseCtx c)
+{
+    std::lock_guard<std::mutex> lk(g_pose_mu);
+    if (g_pose_free.size() < 8) { g_pose_free.push_back(c); return; }
+    cudaFree(c.d); cudaFreeHost(c.h); cudaStreamDestroy(c.stream);
+}
+bool pose_ctx_acquire(size_t bytes, PoseCtx& c)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_pose_mu);
+        for (size_t i = 0; i < g_pose_free.size(); i++)
+            if (g_pose_free[i].dev == dev) { c = g_pose_free[i]; g_pose_free.erase(g_pose_free.begin() + i); break; }
+    }
+    if (!c.stream && cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess) return false;
+    c.dev = dev;
+    if (c.cap < bytes) {
+        if (c.d) cudaFree(c.d);
+        if (c.h) cudaFreeHost(c.h);
+        c.d = nullptr; c.h = nullptr; c.cap = 0;
+        const size_t cap = std::max<size_t>(bytes + bytes / 2, 256 * 1024);
+        if (cudaMalloc(&c.d, cap) != cudaSuccess || cudaHostAlloc(reinterpret_cast<void**>(&c.h), cap, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            if (c.d) cudaFree(c.d);
+            if (c.h) cudaFreeHost(c.h);
+            cudaStreamDestroy(c.stream);
+            c = PoseCtx();
+            return false;
+        }
+        c.cap = cap;
+    }
+    return true;
+}
+// q (x y z w, double) and t of a view transform from the float position / column-major rotation the reference hands over
+// (ref BundlerLib.cpp:261-276, same steps as mage_ba_set_camera)
+void pose_to_qt(const float* pos, const float* rot, double* q, double* t)
+{
+    float m[9], qf[4];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) m[r * 3 + c] = rot[c * 3 + r];
+    R_to_q_host<float>(m, qf);
+    const float nn = qf[0] * qf[0] + qf[1] * qf[1] + qf[2] * qf[2] + qf[3] * qf[3];
+    if (nn > 0.f) { const float nrm = std::sqrt(nn); for (int i = 0; i < 4; i++) qf[i] = qf[i] / nrm; }
+    double qd[4] = {qf[0], qf[1], qf[2], qf[3]};
+    if (qd[3] < 0) for (int i = 0; i < 4; i++) qd[i] = -qd[i];
+    const double n = std::sqrt(qd[0] * qd[0] + qd[1] * qd[1] + qd[2] * qd[2] + qd[3] * qd[3]);
+    for (int i = 0; i < 4; i++) q[i] = qd[i] / n;
+    for (int i = 0; i < 3; i++) t[i] = pos[i];
+}
+// ref BundlerLib.cpp:457-465 (same steps as mage_ba_get_pose)
+void qt_to_pose(const double* qin, const double* t, float* pos, float* rot)
+{
+    double q[4] = {qin[0], qin[1], qin[2], qin[3]};
+    const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) q[i] /= n;
+    const double tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+    const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3], txx = tx * q[0], txy = ty * q[0], txz = tz * q[0], tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    const double R[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+    for (int i = 0; i < 3; i++) pos[i] = (float)t[i];
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) rot[c * 3 + r] = (float)R[r * 3 + c];
+}
+} // namespace
+
+extern "C" int mage_optimize_camera_pose(const float* position, const float* rotation, const float* intrinsics, int n, const float* map_points,
+                                         const float* projections, const float* information, int n_iters, float huber_width,
+                                         float max_outlier_err_sq, float* out_position, float* out_rotation, unsigned int* outliers, int cap,
+                                         int* n_outliers, float* mean_sq_error)
+{
+    MAGE_REQUIRE(position && rotation && intrinsics && out_position && out_rotation && n_outliers && n >= 0 && n_iters >= 0 && n_iters <= 64 &&
+                 (n == 0 || (map_points && projections && information)) && (outliers || cap == 0),
+                 MAGE_ERR_INVALID, "mage_optimize_camera_pose: bad argument (n %d, n_iters %d of at most 64)", n, n_iters);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: bundle adjustment has no CPU fallback"); return MAGE_ERR_CUDA; }
+    *n_outliers = 0;
+    double q[4], t[3];
+    pose_to_qt(position, rotation, q, t);
+    if (n == 0) {                                               // no edge: the optimizer has nothing to do (the handle path returns NaN too)
+        qt_to_pose(q, t, out_position, out_rotation);
+        if (mean_sq_error) *mean_sq_error = std::numeric_limits<float>::quiet_NaN();
+        return MAGE_OK;
+    }
+    MAGE_REQUIRE(ba_device_setup().ok, MAGE_ERR_CUDA, "cudaFuncSetAttribute failed");
+    const PoseLayout L(n);
+    PoseCtx c;
+    MAGE_REQUIRE(pose_ctx_acquire(L.total, c), MAGE_ERR_CUDA, "mage_optimize_camera_pose: no memory for a problem of %d points", n);
+    uint8_t* hb = c.h;
+    memset(hb, 0, L.upload_end);
+    BaDev d{};
+    d.K = 1; d.P = n; d.Ea = n; d.Kf = 1; d.Pl = 0; d.n = 6; d.nblk = 0; d.cam_parts = 1; d.pose1 = 1;
+    double* dcam = reinterpret_cast<double*>(c.d + L.cam);
+    d.cam_q = dcam; d.cam_t = dcam + 4; d.cam_f = dcam + 7; d.cam_cx = dcam + 8; d.cam_cy = dcam + 9;
+    d.cam_h = reinterpret_cast<int*>(c.d + L.idx); d.c_cam = reinterpret_cast<int*>(c.d + L.idx) + 1;
+    d.pt_X = reinterpret_cast<double*>(c.d + L.pt);
+    d.e_cam = reinterpret_cast<int*>(c.d + L.e_cam); d.e_pt = reinterpret_cast<int*>(c.d + L.e_pt);
+    d.e_uv = reinterpret_cast<double*>(c.d + L.uv); d.e_info = reinterpret_cast<double*>(c.d + L.info);
+    d.err = reinterpret_cast<double*>(c.d + L.err); d.x = reinterpret_cast<double*>(c.d + L.x); d.cam_bak = reinterpret_cast<double*>(c.d + L.bak);
+    d.cam_R = reinterpret_cast<double*>(c.d + L.R); d.cam_Rold = d.cam_R + 9;
+    d.flags = c.d + L.flags; d.ctl = reinterpret_cast<BaCtl*>(c.d + L.ctl);
+    memcpy(hb + L.dev, &d, sizeof(BaDev));
+    BaCtl ctl{}; ctl.lambda = -1; ctl.ni = 2;                   // a new instance: iteration 0, no user lambda
+    memcpy(hb + L.ctl, &ctl, sizeof(BaCtl));
+    float* hub = reinterpret_cast<float*>(hb + L.huber);
+    for (int i = 0; i < n_iters; i++) hub[i] = huber_width;
+    double* hc = reinterpret_cast<double*>(hb + L.cam);
+    for (int i = 0; i < 4; i++) hc[i] = q[i];
+    for (int i = 0; i < 3; i++) hc[4 + i] = t[i];
+    hc[7] = intrinsics[2]; hc[8] = intrinsics[0]; hc[9] = intrinsics[1];
+    int* hept = reinterpret_cast<int*>(hb + L.e_pt);
+    double* hpt = reinterpret_cast<double*>(hb + L.pt); double* huv = reinterpret_cast<double*>(hb + L.uv); double* hin = reinterpret_cast<double*>(hb + L.info);
+    for (int i = 0; i < n; i++) {
+        hept[i] = i;
+        hpt[3 * (size_t)i] = map_points[3 * (size_t)i]; hpt[3 * (size_t)i + 1] = map_points[3 * (size_t)i + 1]; hpt[3 * (size_t)i + 2] = map_points[3 * (size_t)i + 2];
+        huv[2 * (size_t)i] = projections[2 * (size_t)i]; huv[2 * (size_t)i + 1] = projections[2 * (size_t)i + 1];
+        hin[i] = information[i];
+    }
+    const unsigned dyn = (unsigned)ba_dyn_smem(6, 1, 0);
+    cudaError_t e = cudaMemcpyAsync(c.d, hb, L.upload_end, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) {
+        ProfScope ps(PROF_BA_STEP, c.stream);
+        k_ba_step_t<true><<<1, kBaThreads, dyn, c.stream>>>(reinterpret_cast<const BaDev*>(c.d + L.dev), reinterpret_cast<const float*>(c.d + L.huber), n_iters,
+                                                           max_outlier_err_sq, dyn);
+        e = cudaGetLastError();
+    }
+    const size_t back = L.flags + (size_t)n - L.ctl;            // control block (with the camera state) + the outlier flags
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb + L.ctl, c.d + L.ctl, back, cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    if (e != cudaSuccess) { set_error("mage_optimize_camera_pose: %s", cudaGetErrorString(e)); pose_ctx_release(c); return MAGE_ERR_CUDA; }
+    const BaCtl* rc = reinterpret_cast<const BaCtl*>(hb + L.ctl);
+    qt_to_pose(rc->cams, rc->cams + 4, out_position, out_rotation);
+    int m = 0;
+    if (rc->n_flagged > 0) {
+        const uint8_t* fl = hb + L.flags;
+        for (int i = 0; i < n; i++)
+            if (fl[i]) { if (m < cap) outliers[m] = (unsigned)i; m++; }
+    }
+    *n_outliers = m;
+    if (mean_sq_error) *mean_sq_error = (float)(rc->err_sum / (double)rc->inlier_count);
+    pose_ctx_release(c);
     return MAGE_OK;
 }
 

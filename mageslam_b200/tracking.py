@@ -5,6 +5,8 @@
                        (Tracking/Reprojection.cpp:26-43), IsGoodCandidate (TrackLocalMap.cpp:519-554), ComputeOctave
                        (Map/MappingMath.h:13-16), for a whole local map per call.
   ProjectPoints     <- reference Tracking/Reprojection.cpp:16-24.
+  OptimizeCameraPose <- TrackLocalMap::OptimizeCameraPose (TrackLocalMap.cpp:421-501): the pose-only bundle adjustment of the
+                       tracking thread in one call (mage_optimize_camera_pose).
 The returned keypoints are the `mapPointKp` the reference hands to RadiusMatch (TrackLocalMap.cpp:371), so they go straight
 into matcher.RadiusMatch as queries (mask = predicted). All arithmetic runs in the CUDA library.
 """
@@ -76,3 +78,20 @@ def ProjectPoints(points3D, cameraPose, calibrationMatrix):
     p = make_params(cameraPose, calibrationMatrix, (0, 0, 0), (0, 0, 1), 0.0, 0.0, 1, 1, 2.0, 1)
     kps, depth, _ = ProjectMapPoints(p, pts)
     return np.stack([kps["x"], kps["y"]], axis=1), depth
+
+
+def OptimizeCameraPose(position, rotation, intrinsics, mapPoints, projections, information, numIterations, maxOutlierErrorSquared, huberWidth):
+    """TrackLocalMap::OptimizeCameraPose (reference TrackLocalMap.cpp:421-501). position[3] + rotation[9, column-major] = the frame's view
+    transform, intrinsics = (cx, cy, fx, fy), mapPoints[n,3] / projections[n,2] / information[n] as the reference hands them to
+    BundlerLib (information = MapPointRefinementConfidence). Returns (position f32[3], rotation f32[9], outlierIndices u32[], mean error)."""
+    pos = np.ascontiguousarray(position, np.float32).reshape(3); rot = np.ascontiguousarray(rotation, np.float32).reshape(9)
+    intr = np.ascontiguousarray(intrinsics, np.float32).reshape(4)
+    pts = np.ascontiguousarray(mapPoints, np.float32).reshape(-1, 3); uv = np.ascontiguousarray(projections, np.float32).reshape(-1, 2)
+    info = np.ascontiguousarray(information, np.float32).reshape(-1)
+    n = len(pts)
+    assert len(uv) == n and len(info) == n
+    opos = np.zeros(3, np.float32); orot = np.zeros(9, np.float32); out = np.zeros(max(n, 1), np.uint32)
+    cnt = C.c_int(0); mean = C.c_float(0)
+    check(lib().mage_optimize_camera_pose(ptr(pos), ptr(rot), ptr(intr), n, ptr(pts), ptr(uv), ptr(info), int(numIterations), C.c_float(huberWidth),
+                                          C.c_float(maxOutlierErrorSquared), ptr(opos), ptr(orot), ptr(out), len(out), C.byref(cnt), C.byref(mean)))
+    return opos, orot, out[:cnt.value].copy(), float(mean.value)

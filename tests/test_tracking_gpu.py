@@ -135,3 +135,57 @@ def test_process_with_distorted_calibration_undistorts_the_detected_keypoints():
     assert np.ascontiguousarray(k1).tobytes() == want.astype(KEYPOINT_DTYPE).tobytes()
     k2, _ = det.Process(img, und, und)                  # equal calibrations: keypoints untouched (ref :97)
     assert np.ascontiguousarray(k2).tobytes() == np.ascontiguousarray(k0).tobytes()
+
+
+# ---- TrackLocalMap::OptimizeCameraPose in one call (mage_optimize_camera_pose)
+def _pose_problem(P, seed, pose_sigma=0.03, outlier_frac=0.0):
+    from mageslam_b200 import synth
+    return synth.ba_problem(K=1, P=P, obs_per_point=1, n_fixed=0, pose_sigma=pose_sigma, outlier_frac=outlier_frac, seed=seed)
+
+
+@pytest.mark.parametrize("P,iters,max_err,outlier_frac,seed", [(300, 3, 25.0, 0.0, 5), (300, 4, 25.0, 0.05, 6), (60, 3, 7.25, 0.1, 7), (1, 4, 25.0, 0.0, 8), (900, 10, 2.0, 0.02, 9)])
+def test_optimize_camera_pose_equals_bundlerlib_sequence(P, iters, max_err, outlier_frac, seed):
+    """one call == the reference's sequence (ref TrackLocalMap.cpp:421-501: new BundlerLib(ArePointsFixed), one camera, one observation per
+    map point, ONE StepBundleAdjustment, GetPose(0)): against the compiled reference within 1e-4, against this library's own handle
+    path (same kernel) to the last float, outlier lists equal"""
+    from mageslam_b200.bundler import BundlerLib, BundlerParameters
+    from mageslam_b200.tracking import OptimizeCameraPose
+    from tests.ba_checks import TOL, best_checker
+    from tests.oracle_ba import rel_frobenius
+    prob = _pose_problem(P, seed, outlier_frac=outlier_frac)
+    hub = 2.0
+    pos, rot, outl, mean = OptimizeCameraPose(prob["cam_pos"][0], prob["cam_rot"][0], prob["intrinsics"][0], prob["points"], prob["obs_uv"], prob["obs_info"], iters, max_err, hub)
+    h = BundlerLib(BundlerParameters(True)).load(prob)
+    mh = h.StepBundleAdjustment([hub] * iters, max_err)
+    ph, rh = h.poses()
+    assert np.array_equal(pos, ph[0]) and np.array_equal(rot, rh[0].reshape(9)) and list(outl) == list(h.last_outliers)
+    assert (np.isnan(mean) and np.isnan(mh)) or mean == np.float32(mh)
+    chk = best_checker(True).load(prob)
+    mc, oc = chk.StepBundleAdjustment([hub] * iters, max_err)
+    pc, rc = chk.poses()
+    assert rel_frobenius(pos, pc[0]) < TOL and rel_frobenius(rot, rc[0].reshape(9)) < TOL and list(outl) == list(oc)
+
+
+def test_optimize_camera_pose_edge_cases():
+    from mageslam_b200.tracking import OptimizeCameraPose
+    prob = _pose_problem(40, 3)
+    # no map point: the pose comes back as given (through the same quaternion round trip as GetPose), no outliers, NaN mean
+    pos, rot, outl, mean = OptimizeCameraPose(prob["cam_pos"][0], prob["cam_rot"][0], prob["intrinsics"][0], np.zeros((0, 3)), np.zeros((0, 2)), np.zeros(0), 3, 25.0, 2.0)
+    assert np.allclose(pos, prob["cam_pos"][0]) and np.allclose(rot, prob["cam_rot"][0].reshape(9), atol=1e-6) and len(outl) == 0 and np.isnan(mean)
+    # zero iterations: nothing moves and no error is ever computed, so nothing is flagged (the handle path behaves the same)
+    pos, rot, outl, mean = OptimizeCameraPose(prob["cam_pos"][0], prob["cam_rot"][0], prob["intrinsics"][0], prob["points"], prob["obs_uv"], prob["obs_info"], 0, 1e-6, 2.0)
+    assert np.allclose(pos, prob["cam_pos"][0]) and len(outl) == 0
+    with pytest.raises(Exception):
+        OptimizeCameraPose(prob["cam_pos"][0], prob["cam_rot"][0], prob["intrinsics"][0], prob["points"], prob["obs_uv"], prob["obs_info"], 65, 25.0, 2.0)
+    # many calls from several threads (pooled contexts): same answer every time
+    import threading
+    ref = OptimizeCameraPose(prob["cam_pos"][0], prob["cam_rot"][0], prob["intrinsics"][0], prob["points"], prob["obs_uv"], prob["obs_info"], 4, 25.0, 2.0)
+    bad = []
+    def work():
+        for _ in range(50):
+            r = OptimizeCameraPose(prob["cam_pos"][0], prob["cam_rot"][0], prob["intrinsics"][0], prob["points"], prob["obs_uv"], prob["obs_info"], 4, 25.0, 2.0)
+            if not (np.array_equal(r[0], ref[0]) and np.array_equal(r[1], ref[1]) and list(r[2]) == list(ref[2])):
+                bad.append(1)
+    ts = [threading.Thread(target=work) for _ in range(4)]
+    [t.start() for t in ts]; [t.join() for t in ts]
+    assert not bad
