@@ -23,6 +23,9 @@ print(StepMany(bs, [1.8] * 2, 1e9))
 big = BundlerLib().load(synth.ba_problem(K=60, P=600, obs_per_point=6, seed=4, loop=True)); print(big.StepBundleAdjustment([1.8] * 2, 1e9))
 from mageslam_b200.sharded import ShardedGlobalBA
 shd = ShardedGlobalBA(synth.ba_problem(K=60, P=600, obs_per_point=6, seed=4, loop=True)); print('sharded stages (one rank):', [shd.StepBundleAdjustment([1.8]) for _ in range(2)], shd.trials)
+from mageslam_b200.tracking import OptimizeCameraPose
+_pp = synth.ba_problem(K=1, P=77, obs_per_point=1, n_fixed=0, pose_sigma=0.03, outlier_frac=0.1, seed=6)
+print('optimize_camera_pose:', [OptimizeCameraPose(_pp['cam_pos'][0], _pp['cam_rot'][0], _pp['intrinsics'][0], _pp['points'], _pp['obs_uv'], _pp['obs_info'], it, 7.25, 2.0)[2].tolist() for it in (3, 4)])
 po = BundlerLib(BundlerParameters(True)).load(synth.ba_problem(K=1, P=100, obs_per_point=1, n_fixed=0, seed=5)); print(po.StepBundleAdjustment([2.0] * 3, 25.0))
 # paths added later in the round: TMA variant of FAST, generic BRIEF pattern, single-level fixed-point blur, undistortion, pipelined front-end,
 # general (materialised) one-CTA BA path, tether edges
