@@ -591,24 +591,69 @@ __global__ void __launch_bounds__(256) k_fast_tma(const __grid_constant__ OrbGeo
 // One CTA per (level, frame). Keys are unique 64-bit words, sorted descending:
 //   ANMS   : r << 32 | score << 24 | (0xFFFFFF - raster)     (r desc, strength desc, raster asc)
 //   raster : (0xFFFFFF - raster) << 32 | score << 24 | (0xFFFFFF - raster)
+// Bitonic sort, descending, of npow2 (a power of two) keys by the whole CTA. A compare-exchange distance below 32 stays inside a warp
+// (element i sits in lane i % 32 because the block size is a multiple of 32): those stages run on registers through shuffles, with no
+// barrier; only the distances of 32 and more go through the array. For 1024 keys that is 21 barriers instead of 55 (the old all-in-memory
+// version spent 25 000 clocks here for a one-frame call: 460 per stage).
 __device__ void bitonic_sort_desc(unsigned long long* keys, int npow2)
 {
-    for (int k = 2; k <= npow2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
-                int ixj = i ^ j;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int per = (npow2 + nt - 1) / nt;
+    if (npow2 < 64 || (nt & 31)) {                   // tiny arrays (and odd block sizes): the plain all-in-memory network
+        for (int k = 2; k <= npow2; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < npow2; i += nt) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const unsigned long long a = keys[i], c = keys[ixj];
+                        const bool desc = (i & k) == 0;
+                        if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
+    // register stages j = jtop, jtop / 2, .. 1 of merge size k on the elements this thread holds (each element's partners at distances
+    // below 32 are in its own warp and belong to the same round m, so an element is loaded, exchanged and stored on its own)
+    auto reg_stages = [&](int k, int jtop) {
+        for (int m = 0; m < per; m++) {
+            const int i = tid + m * nt;
+            unsigned long long a = i < npow2 ? keys[i] : 0ull;
+            for (int kk = (k <= 32) ? 2 : k; kk <= k; kk <<= 1) {        // k <= 32: the whole prefix of the network at once
+                for (int j = min(kk >> 1, jtop); j > 0; j >>= 1) {
+                    const unsigned long long c = __shfl_xor_sync(0xffffffffu, a, j);
+                    const bool take_max = ((i & kk) == 0) == ((i & j) == 0);
+                    a = take_max ? (a > c ? a : c) : (a < c ? a : c);
+                }
+            }
+            if (i < npow2) keys[i] = a;
+        }
+        __syncthreads();
+    };
+    // merge sizes 2 .. 32 entirely in registers
+    reg_stages(min(32, npow2), min(16, npow2 >> 1));
+    for (int k = 64; k <= npow2; k <<= 1) {
+        for (int j = k >> 1; j >= 32; j >>= 1) {
+            for (int i = tid; i < npow2; i += nt) {
+                const int ixj = i ^ j;
                 if (ixj > i) {
-                    unsigned long long a = keys[i], c = keys[ixj];
-                    bool desc = (i & k) == 0;
+                    const unsigned long long a = keys[i], c = keys[ixj];
+                    const bool desc = (i & k) == 0;
                     if (desc ? (a < c) : (a > c)) { keys[i] = c; keys[ixj] = a; }
                 }
             }
             __syncthreads();
         }
+        reg_stages(k, 16);
     }
 }
 
-__global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant__ OrbGeom g, const OrbBuffers b)
+// LANES: eight lanes per key point in the ANMS ring search (the latency variant, for calls of a few frames); false: one thread per key
+// point (the throughput variant, for batches)
+template <bool LANES>
+__global__ void __launch_bounds__(kSelThreads, LANES ? 1 : 2) k_select(const __grid_constant__ OrbGeom g, const OrbBuffers b)
 {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ int hist[256];
@@ -626,6 +671,13 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant
     int* selCount = b.sel_count + f * kMaxLevels + l;
     const int nKeep = L.nfeat;
     const int tid = threadIdx.x, nt = blockDim.x;
+#ifdef MAGE_SELECT_TIMERS
+    long long tmr[12]; int tk = 0;
+#define SELT() do { __syncthreads(); if (tid == 0 && tk < 12) tmr[tk++] = clock64(); } while (0)
+#else
+#define SELT() do {} while (0)
+#endif
+    SELT();
 
     unsigned long long* keys;
     uint32_t *kept, *cxy;
@@ -664,10 +716,12 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant
     }
 
     // ---- RetainBestFeatures: histogram of scores, whole-bin cut
+    SELT();
     for (int i = tid; i < 256; i += nt) hist[i] = 0;
     __syncthreads();
     for (int i = tid; i < n; i += nt) atomicAdd(&hist[cand[i] >> 24], 1);
     __syncthreads();
+    SELT();
     // suffix sums cum[i] = sum_{j >= i} hist[j] by the first 256 threads (Hillis-Steele in shared memory), then the two
     // thresholds of RetainBestFeatures as max-reductions -- replaces two serial 256-bin walks by one thread
     __shared__ int cum[256];
@@ -723,6 +777,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant
         if (tid == 0) *selCount = K;
         return;
     }
+    SELT();
     bind(K);
     {
         int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
@@ -737,6 +792,7 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant
         }
         if (mnx != INT_MAX) { atomicMin(&s_vals[2], mnx); atomicMax(&s_vals[3], mxx); atomicMin(&s_vals[4], mny); atomicMax(&s_vals[5], mxy); }
     }
+    SELT();
     const int numX = g.num_cells_x, numY = g.num_cells_y, nCells = numX * numY;
     for (int i = tid; i < nCells; i += nt) { cellStart[i] = 0; cellFill[i] = 0; }
     __syncthreads();
@@ -752,36 +808,111 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant
         int dx = max((maxX - minX) / numX, 1), dy = max((maxY - minY) / numY, 1);
         s_vals[8] = min(dx, dy) * min(dx, dy);
     }
-    // cell histogram
+    // cell histogram; (cell, x | y << 16) of every kept key point is parked in the key array (free until the radii are written) so that the
+    // scatter pass below does not repeat the three integer divisions
     for (int j = tid; j < K; j += nt) {
         int pos = kept[j] & 0xFFFFFF, y = pos / L.w, x = pos - y * L.w;
         int cell = ((y - minY) * numY / (maxY + 1 - minY)) * numX + (x - minX) * numX / (maxX + 1 - minX);
         atomicAdd(&cellStart[cell], 1);
+        keys[j] = ((unsigned long long)(uint32_t)cell << 32) | (uint32_t)x | ((uint32_t)y << 16);
     }
     __syncthreads();
-    if (tid < 32) {          // exclusive scan over <= 2048 cells by one warp (64 cells per lane)
-        int per = (nCells + 31) / 32, beg = tid * per, end = min(beg + per, nCells), sum = 0;
+    {   // exclusive scan over the <= 2048 cells by the whole CTA: a few cells per thread, warp scan, scan of the warp totals
+        __shared__ int wsum[32];
+        const int per = (nCells + nt - 1) / nt, beg = tid * per, end = min(beg + per, nCells), lane = tid & 31, warp = tid >> 5;
+        int sum = 0;
         for (int i = beg; i < end; i++) sum += cellStart[i];
         int incl = sum;
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= o) incl += v; }
-        int run = incl - sum;
-        for (int i = beg; i < end; i++) { int c = cellStart[i]; cellStart[i] = run; run += c; }
-        if (tid == 31) cellStart[nCells] = incl;
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = lane < (nt >> 5) ? wsum[lane] : 0;
+            int wi = w;
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += v; }
+            wsum[lane] = wi - w;                              // exclusive warp offsets
+            if (lane == 31) cellStart[nCells] = wi;
+        }
+        __syncthreads();
+        int run = wsum[warp] + incl - sum;
+        for (int i = beg; i < end; i++) { const int c = cellStart[i]; cellStart[i] = run; run += c; }
     }
     __syncthreads();
     for (int j = tid; j < K; j += nt) {
-        uint32_t c = kept[j];
-        int pos = c & 0xFFFFFF, y = pos / L.w, x = pos - y * L.w;
-        int cell = ((y - minY) * numY / (maxY + 1 - minY)) * numX + (x - minX) * numX / (maxX + 1 - minX);
-        int slot = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
-        cxy[slot] = (uint32_t)x | ((uint32_t)y << 16);
-        csc[slot] = (uint8_t)(c >> 24);
+        const unsigned long long cz = keys[j];
+        const int cell = (int)(cz >> 32);
+        const int slot = cellStart[cell] + atomicAdd(&cellFill[cell], 1);
+        cxy[slot] = (uint32_t)cz;
+        csc[slot] = (uint8_t)(kept[j] >> 24);
     }
     __syncthreads();
+    SELT();
     // ---- ANMS radii: literal ring search of ref :268-326, one thread per keypoint
     const int R = s_vals[7], mcd2 = s_vals[8];
     const float rf = s_rf;
     int np2 = 1; while (np2 < K) np2 <<= 1;
+    // how far the ring search of this level can reach: rings d with (d - 1)^2 mcd2 < R
+    int dmax = 1;
+    while (dmax * dmax * mcd2 < R && dmax < numX + numY) dmax++;
+    if (LANES && dmax >= 5) {
+        // Eight lanes per key point (levels whose searches reach five rings or more: the small ones; below that the plain loop is faster): ring d of the cell grid (one cell for d = 0, else the 8 d cells of the square's border) is dealt out
+        // over the lanes, the minimum squared distance to a stronger key point is reduced over the group after every ring -- the reference
+        // tests its stopping rule once per ring too and only ever takes minima inside one, so the radius is the same whatever the order of
+        // the cells. On the small levels a key point walks up to 17 x 17 mostly empty cells: one thread per key point is a chain of
+        // 36 000 clocks there (in-kernel timers, -DMAGE_SELECT_TIMERS), the critical path of a one-frame call.
+        const int gl = tid & 7, ngrp = nt >> 3;
+        for (int base = 0; base < np2; base += ngrp) {
+            const int slot = base + (tid >> 3);
+            const bool live = slot < K;
+            int x = 0, y = 0, sc = 0, cx = 0, cy = 0;
+            if (live) {
+                const uint32_t me = cxy[slot];
+                x = me & 0xFFFF; y = me >> 16; sc = csc[slot];
+                cx = (x - minX) * numX / (maxX + 1 - minX); cy = (y - minY) * numY / (maxY + 1 - minY);
+            }
+            const float s = __fadd_rn(__fmul_rn((float)sc, rf), 0.002f);           // strength >= 0 always (FAST scores)
+            int minR2 = R;
+            bool go = live;
+            for (int d = 0; ; d++) {
+                go = go && max(0, d - 1) * max(0, d - 1) * mcd2 < minR2 && d <= numX + numY;      // beyond numX + numY there are no cells
+                if (!__any_sync(0xffffffffu, go)) break;
+                if (go) {
+                    // work items of ring d: the two full rows at cy -+ d, each ONE range of slots (the cells of a grid row are neighbours
+                    // in the sorted arrays), then the two end cells of every row in between
+                    const int items = d == 0 ? 1 : 4 * d;
+                    const int x0 = max(cx - d, 0), x1 = min(cx + d, numX - 1);
+                    for (int i = gl; i < items; i += 8) {
+                        int c0 = 0, c1 = 0;
+                        if (i < 2) {
+                            const int cYY = i ? cy + d : cy - d;
+                            if (cYY >= 0 && cYY < numY) { c0 = cellStart[cYY * numX + x0]; c1 = cellStart[cYY * numX + x1 + 1]; }
+                        } else {
+                            const int k = i - 2, cYY = cy - d + 1 + (k >> 1), cXX = (k & 1) ? cx + d : cx - d;
+                            if (cXX >= 0 && cXX < numX && cYY >= 0 && cYY < numY) { c0 = cellStart[cYY * numX + cXX]; c1 = cellStart[cYY * numX + cXX + 1]; }
+                        }
+                        for (int o = c0; o < c1; o++) {
+                            if ((float)csc[o] > s) {
+                                const uint32_t ot = cxy[o];
+                                const int ddx = x - (int)(ot & 0xFFFF), ddy = y - (int)(ot >> 16);
+                                minR2 = min(minR2, ddx * ddx + ddy * ddy);
+                            }
+                        }
+                    }
+                }
+                minR2 = min(minR2, __shfl_xor_sync(0xffffffffu, minR2, 1));
+                minR2 = min(minR2, __shfl_xor_sync(0xffffffffu, minR2, 2));
+                minR2 = min(minR2, __shfl_xor_sync(0xffffffffu, minR2, 4));
+            }
+            if (gl == 0 && slot < np2) {
+                unsigned long long key = 0;
+                if (live) {
+                    const uint32_t inv = 0xFFFFFFu - (uint32_t)(y * L.w + x);
+                    key = ((unsigned long long)(uint32_t)minR2 << 32) | ((uint32_t)sc << 24) | inv;
+                }
+                keys[slot] = key;
+            }
+        }
+    } else {
     for (int slot = tid; slot < np2; slot += nt) {
         unsigned long long key = 0;
         if (slot < K) {
@@ -792,24 +923,23 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant
             int minR2 = R;
             for (int d = 0; max(0, d - 1) * max(0, d - 1) * mcd2 < minR2; d++) {
                 if (d > numX + numY) break;                                     // no cells out there
-                for (int yy = -d; yy <= d; yy++) {
-                    int cYY = yy + cy;
-                    if (cYY < 0 || cYY >= numY) continue;
-                    int step = (yy == -d || yy == d) ? 1 : 2 * d;               // ring: full rows at +-d, else the two ends
-                    if (step == 0) step = 1;
-                    for (int xx = -d; xx <= d; xx += step) {
-                        int cXX = xx + cx;
-                        if (cXX < 0 || cXX >= numX) continue;
-                        int c0 = cellStart[cYY * numX + cXX], c1 = cellStart[cYY * numX + cXX + 1];
-                        for (int o = c0; o < c1; o++) {
-                            if ((float)csc[o] > s) {
-                                uint32_t ot = cxy[o];
-                                int ddx = x - (int)(ot & 0xFFFF), ddy = y - (int)(ot >> 16);
-                                int r = ddx * ddx + ddy * ddy;
-                                if (r < minR2) minR2 = r;
-                            }
+                // ring d: the full rows at cy -+ d are ONE range of slots each (the cells of a grid row are neighbours in the sorted
+                // arrays), the rows in between contribute their two end cells
+                auto scan = [&](int c0, int c1) {
+                    for (int o = c0; o < c1; o++) {
+                        if ((float)csc[o] > s) {
+                            const uint32_t ot = cxy[o];
+                            const int ddx = x - (int)(ot & 0xFFFF), ddy = y - (int)(ot >> 16);
+                            minR2 = min(minR2, ddx * ddx + ddy * ddy);
                         }
                     }
+                };
+                const int x0 = max(cx - d, 0), x1 = min(cx + d, numX - 1);
+                if (cy - d >= 0) scan(cellStart[(cy - d) * numX + x0], cellStart[(cy - d) * numX + x1 + 1]);
+                if (d > 0 && cy + d < numY) scan(cellStart[(cy + d) * numX + x0], cellStart[(cy + d) * numX + x1 + 1]);
+                for (int cYY = max(cy - d + 1, 0); cYY <= min(cy + d - 1, numY - 1); cYY++) {
+                    if (cx - d >= 0) scan(cellStart[cYY * numX + cx - d], cellStart[cYY * numX + cx - d + 1]);
+                    if (cx + d < numX) scan(cellStart[cYY * numX + cx + d], cellStart[cYY * numX + cx + d + 1]);
                 }
             }
             uint32_t inv = 0xFFFFFFu - (uint32_t)(y * L.w + x);
@@ -817,13 +947,21 @@ __global__ void __launch_bounds__(kSelThreads, 2) k_select(const __grid_constant
         }
         keys[slot] = key;
     }
+    }
     __syncthreads();
+    SELT();
     bitonic_sort_desc(keys, np2);
+    SELT();
     for (int i = tid; i < nKeep; i += nt) {
         uint32_t lo = (uint32_t)keys[i];
         sel[i] = (lo & 0xFF000000u) | (0xFFFFFFu - (lo & 0xFFFFFFu));
     }
     if (tid == 0) *selCount = nKeep;
+#ifdef MAGE_SELECT_TIMERS
+    SELT();
+    if (tid == 0 && f == 0) printf("[k_select] level %d n %d K %d nKeep %d clk: start %lld hist %lld cut %lld compact %lld cells %lld rings %lld sort %lld out %lld\n", l, n, K, nKeep,
+                                   tmr[1] - tmr[0], tmr[2] - tmr[1], tmr[3] - tmr[2], tmr[4] - tmr[3], tmr[5] - tmr[4], tmr[6] - tmr[5], tmr[7] - tmr[6], tmr[8] - tmr[7]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ K5: Gaussian blur
@@ -1610,7 +1748,8 @@ extern "C" int mage_orb_create(const mage_orb_params* p, int width, int height, 
         const std::vector<FastTile> ft = fast_tile_table(g);
         if (e == cudaSuccess && !ft.empty()) e = cudaMemcpy((void*)h->d_fast_tiles, ft.data(), ft.size() * sizeof(FastTile), cudaMemcpyHostToDevice);
     }
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes());
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, select_smem_bytes());
     {   // which share of the min/max network runs on the FMA pipe: tuning switch, every variant is bit-identical
         const char* env = getenv("MAGE_FAST_VARIANT");
         const int v = env ? atoi(env) : 0;
@@ -1740,7 +1879,13 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
     }
     // one CTA per (level, frame): a chain of dependent phases. With a few frames the call's latency is this kernel's (58 us for one 640 x 480
     // frame with 512 threads, 46 us with 1024); with a batch four 512-thread CTAs per SM give the better throughput
-    { ProfScope ps(PROF_SELECT, s); k_select<<<dim3(g.nlevels, n), n <= 4 ? kSelThreads : kSelThreads / 2, select_smem_bytes(), s>>>(g, bufs); }
+    {
+        static const int lanes_env = getenv("MAGE_SELECT_LANES") ? atoi(getenv("MAGE_SELECT_LANES")) : -1;      // -1: by batch size
+        const bool lanes = lanes_env >= 0 ? lanes_env != 0 : n <= 4;
+        ProfScope ps(PROF_SELECT, s);
+        if (lanes) k_select<true><<<dim3(g.nlevels, n), n <= 4 ? kSelThreads : kSelThreads / 2, select_smem_bytes(), s>>>(g, bufs);
+        else k_select<false><<<dim3(g.nlevels, n), n <= 4 ? kSelThreads : kSelThreads / 2, select_smem_bytes(), s>>>(g, bufs);
+    }
     if (fork) MAGE_CUDA_TRY(cudaStreamWaitEvent(s, h->ev_blur, 0));
     { ProfScope ps(PROF_ORIENT_DESCRIBE, s); k_orient_describe<<<dim3(div_up(capacity, 8), n), 256, 0, s>>>(g, bufs, d_kps, d_desc, d_counts, capacity); }
     MAGE_CUDA_TRY(cudaGetLastError());
