@@ -2580,8 +2580,6 @@ struct HostTether { int type = -1, c1 = -1, c2 = -1; double m[8] = {0, 0, 0, 0, 
 
 } // namespace
 
-struct PinnedStage { uint8_t* p = nullptr; size_t cap = 0; };      // pooled pinned host staging buffer (below)
-
 struct mage_ba_s {
     bool points_fixed = false;
     int K = 0, P = 0, E = 0;
@@ -2617,32 +2615,6 @@ struct mage_ba_s {
     int coop_blocks_max = 0;           // co-resident limit (large problems use the whole chip)
 };
 
-// Pinned host staging buffers for the structure upload, pooled process-wide (cudaHostAlloc costs more than the build itself): a build
-// takes one, the batched call's worker threads take one each.
-static std::mutex g_stage_mu;
-static std::vector<PinnedStage> g_stage_free;
-static PinnedStage stage_acquire(size_t bytes)
-{
-    PinnedStage st;
-    {
-        std::lock_guard<std::mutex> lk(g_stage_mu);
-        for (size_t i = 0; i < g_stage_free.size(); i++)
-            if (g_stage_free[i].cap >= bytes) { st = g_stage_free[i]; g_stage_free.erase(g_stage_free.begin() + i); return st; }
-        if (!g_stage_free.empty()) { st = g_stage_free.back(); g_stage_free.pop_back(); }
-    }
-    if (st.p) { cudaFreeHost(st.p); st = PinnedStage(); }     // too small: grow
-    const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
-    if (cudaHostAlloc(reinterpret_cast<void**>(&st.p), cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); st.p = nullptr; return st; }
-    st.cap = cap;
-    return st;
-}
-static void stage_release(PinnedStage st)
-{
-    if (!st.p) return;
-    std::lock_guard<std::mutex> lk(g_stage_mu);
-    if (g_stage_free.size() < 16) g_stage_free.push_back(st);
-    else cudaFreeHost(st.p);
-}
 // after h->stream has been synchronised: the copies that read the handle's pending staging buffers are done
 static void ba_release_pending(mage_ba_t h)
 {

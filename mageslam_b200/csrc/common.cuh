@@ -1,6 +1,8 @@
 // Shared helpers for the sm_100a kernels and their C-ABI wrappers.
 #pragma once
+#include <algorithm>
 #include <mutex>
+#include <vector>
 #include <cuda_runtime.h>
 #include <cstdarg>
 #include <cstdint>
@@ -107,6 +109,38 @@ struct DeviceArena {
         base = nullptr;
     }
 };
+
+// Pinned host staging buffers, pooled process-wide (cudaHostAlloc costs more than most of the calls that need one): the structure upload
+// of a bundle-adjustment problem takes one (the batched call's worker threads one each), the one-call host paths of the matchers pack their
+// inputs into one and land their results in it -- a copy between the device and a caller's pageable array is a staged, synchronous
+// transfer of the driver (about 8 us each), one DMA from / to pinned memory plus a memcpy is not.
+struct PinnedStage { uint8_t* p = nullptr; size_t cap = 0; };
+struct PinnedPool { std::mutex mu; std::vector<PinnedStage> free; };
+inline PinnedPool& pinned_pool() { static PinnedPool pool; return pool; }
+inline PinnedStage stage_acquire(size_t bytes)
+{
+    PinnedPool& P = pinned_pool();
+    PinnedStage st;
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        for (size_t i = 0; i < P.free.size(); i++)
+            if (P.free[i].cap >= bytes) { st = P.free[i]; P.free.erase(P.free.begin() + i); return st; }
+        if (!P.free.empty()) { st = P.free.back(); P.free.pop_back(); }
+    }
+    if (st.p) { cudaFreeHost(st.p); st = PinnedStage(); }     // too small: grow
+    const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    if (cudaHostAlloc(reinterpret_cast<void**>(&st.p), cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); st.p = nullptr; return st; }
+    st.cap = cap;
+    return st;
+}
+inline void stage_release(PinnedStage st)
+{
+    if (!st.p) return;
+    PinnedPool& P = pinned_pool();
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (P.free.size() < 16) P.free.push_back(st);
+    else cudaFreeHost(st.p);
+}
 
 // Optional per-kernel timing (CUDA events on the launching stream), used by bench.py for the live roofline figure.
 enum ProfSlot { PROF_RESIZE = 0, PROF_BLUR, PROF_FAST, PROF_SELECT, PROF_ORIENT_DESCRIBE, PROF_MATCH_DIR, PROF_MATCH_EMIT, PROF_BA_STEP, PROF_SLOTS };

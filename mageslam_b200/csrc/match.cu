@@ -528,7 +528,8 @@ struct mage_matcher_s {
     MatchJob* d_jobs = nullptr;
     unsigned* d_best = nullptr;     // [max_pairs][4][max_desc]: fwd best, fwd second, bwd best, bwd second
     uint8_t* d_stage = nullptr;     // single-pair host API staging: A, B, masks, matches, count
-    mage_dmatch* h_out = nullptr;   // pinned staging for results
+    mage_dmatch* h_out = nullptr;   // pinned staging for results (+ the count behind them)
+    uint8_t* h_in = nullptr;        // pinned staging of the single-pair host API's descriptors (A | B, laid out like d_stage)
     int* h_count = nullptr;
     cudaStream_t own_stream = nullptr;
     // memo of the last device-batched job table (a video stream re-submits the same slot pairs every batch)
@@ -549,7 +550,8 @@ extern "C" int mage_matcher_create(int max_descriptors, int max_pairs, mage_matc
     if (e == cudaSuccess) e = cudaMalloc(&m->d_jobs, sizeof(MatchJob) * max_pairs);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_best, sizeof(unsigned) * 4 * (size_t)max_pairs * max_descriptors);
     if (e == cudaSuccess) e = cudaMalloc(&m->d_stage, stage);
-    if (e == cudaSuccess) e = cudaMallocHost(&m->h_out, sizeof(mage_dmatch) * (size_t)max_descriptors);
+    if (e == cudaSuccess) e = cudaMallocHost(&m->h_out, sizeof(mage_dmatch) * (size_t)max_descriptors + sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost(&m->h_in, (size_t)max_descriptors * 64);
     if (e == cudaSuccess) e = cudaMallocHost(&m->h_count, sizeof(int));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_match_dir, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemBytes);      // per device
@@ -566,6 +568,7 @@ extern "C" void mage_matcher_destroy(mage_matcher_t m)
     if (m->d_best) cudaFree(m->d_best);
     if (m->d_stage) cudaFree(m->d_stage);
     if (m->h_out) cudaFreeHost(m->h_out);
+    if (m->h_in) cudaFreeHost(m->h_in);
     if (m->h_count) cudaFreeHost(m->h_count);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
@@ -596,8 +599,11 @@ extern "C" int mage_match_bf(mage_matcher_t m, const uint8_t* descA, int nA, con
     uint8_t* dA = m->d_stage; uint8_t* dB = dA + N * 32; uint8_t* dmA = dB + N * 32; uint8_t* dmB = dmA + N;
     mage_dmatch* dOut = reinterpret_cast<mage_dmatch*>(m->d_stage + align_up(N * 66, 256));
     int* dCnt = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(dOut) + sizeof(mage_dmatch) * N);
-    MAGE_CUDA_TRY(cudaMemcpyAsync(dA, descA, (size_t)nA * 32, cudaMemcpyHostToDevice, s));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(dB, descB, (size_t)nB * 32, cudaMemcpyHostToDevice, s));
+    // both descriptor sets through ONE copy from pinned staging laid out like the device buffer (two copies from the caller's pageable
+    // arrays are two staged transfers of the driver), the matches and their count back in one copy likewise
+    memcpy(m->h_in, descA, (size_t)nA * 32);
+    memcpy(m->h_in + N * 32, descB, (size_t)nB * 32);
+    MAGE_CUDA_TRY(cudaMemcpyAsync(dA, m->h_in, N * 32 + (size_t)nB * 32, cudaMemcpyHostToDevice, s));
     if (maskA) MAGE_CUDA_TRY(cudaMemcpyAsync(dmA, maskA, nA, cudaMemcpyHostToDevice, s));
     if (maskB) MAGE_CUDA_TRY(cudaMemcpyAsync(dmB, maskB, nB, cudaMemcpyHostToDevice, s));
     m->memo_desc = nullptr; m->memo_a.clear(); m->memo_b.clear();
@@ -606,10 +612,9 @@ extern "C" int mage_match_bf(mage_matcher_t m, const uint8_t* descA, int nA, con
     j.count_ptr[0] = j.count_ptr[1] = nullptr; j.count[0] = nA; j.count[1] = nB; j.cap = m->max_desc;
     int rc = match_launch(m, 1, nA, nB, max_hamming, min_diff, dOut, m->max_desc, dCnt, s);
     if (rc != MAGE_OK) return rc;
-    MAGE_CUDA_TRY(cudaMemcpyAsync(m->h_count, dCnt, sizeof(int), cudaMemcpyDeviceToHost, s));
-    MAGE_CUDA_TRY(cudaMemcpyAsync(m->h_out, dOut, sizeof(mage_dmatch) * (size_t)nA, cudaMemcpyDeviceToHost, s));
+    MAGE_CUDA_TRY(cudaMemcpyAsync(m->h_out, dOut, sizeof(mage_dmatch) * N + sizeof(int), cudaMemcpyDeviceToHost, s));      // [matches | count]
     MAGE_CUDA_TRY(cudaStreamSynchronize(s));
-    *count = *m->h_count;
+    *count = *reinterpret_cast<const int*>(reinterpret_cast<const uint8_t*>(m->h_out) + sizeof(mage_dmatch) * N);
     memcpy(out, m->h_out, sizeof(mage_dmatch) * (size_t)(*count));
     return MAGE_OK;
 }

@@ -1458,6 +1458,7 @@ struct mage_orb_s {
     size_t sel_total = 0, cand_total = 0, key_total = 0;
     int fast_tiles = 0, blur_tiles = 0;
     size_t off_stage_kps = 0, off_stage_desc = 0, off_stage_counts = 0, off_lvl0 = 0;
+    uint8_t* h_back = nullptr; size_t h_back_bytes = 0;      // pinned landing buffer of the host path's read-back (allocated at the first call)
     int last_n = 0;
     int stage_cap = 0;          // staging capacity per frame = max(nfeatures, sum of per-level budgets)
     cudaStream_t own_stream = nullptr;
@@ -1792,6 +1793,7 @@ extern "C" void mage_orb_destroy(mage_orb_t h)
     if (h->ev_pyr) cudaEventDestroy(h->ev_pyr);
     if (h->ev_blur) cudaEventDestroy(h->ev_blur);
     for (auto& gph : h->graphs) cudaGraphExecDestroy(gph.exec);
+    if (h->h_back) cudaFreeHost(h->h_back);
     h->arena.release();
     delete h;
 }
@@ -1949,6 +1951,34 @@ extern "C" int mage_orb_detect_and_compute_batch(mage_orb_t h, const uint8_t* im
     if (exec) { MAGE_CUDA_TRY(cudaGraphLaunch(exec, s)); h->last_n = n; }
     else rc = orb_launch(h, h->b, n, d_kps, d_desc, cap, d_counts, s);
     if (rc != MAGE_OK) return rc;
+    // read-back. The staged key points, descriptors and counts are neighbours in the arena: when the call fills most of that span (a
+    // one-frame detector always does) it comes back as ONE copy into a pinned landing buffer and is handed out from there -- four copies
+    // into the caller's pageable arrays are four staged, synchronous transfers (about 8 us each on a 200 us call)
+    const size_t span = h->off_stage_counts + sizeof(int) * (size_t)h->max_batch - h->off_stage_kps, span_al = align_up(span, 256);
+    if ((size_t)n * cap * (sizeof(mage_keypoint) + 32) * 2 >= span) {
+        if (h->h_back_bytes < span_al + sizeof(int) * (size_t)h->max_batch) {
+            if (h->h_back) cudaFreeHost(h->h_back);
+            h->h_back = nullptr; h->h_back_bytes = 0;
+            if (cudaHostAlloc(reinterpret_cast<void**>(&h->h_back), span_al + sizeof(int) * (size_t)h->max_batch, cudaHostAllocDefault) == cudaSuccess)
+                h->h_back_bytes = span_al + sizeof(int) * (size_t)h->max_batch;
+            else cudaGetLastError();
+        }
+    }
+    if (h->h_back_bytes && (size_t)n * cap * (sizeof(mage_keypoint) + 32) * 2 >= span) {
+        MAGE_CUDA_TRY(cudaMemcpyAsync(h->h_back, h->arena.base + h->off_stage_kps, span, cudaMemcpyDeviceToHost, s));
+        MAGE_CUDA_TRY(cudaMemcpyAsync(h->h_back + span_al, h->b.status, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+        MAGE_CUDA_TRY(cudaStreamSynchronize(s));
+        const uint8_t* bk = h->h_back;
+        const uint8_t* bd = h->h_back + (h->off_stage_desc - h->off_stage_kps);
+        for (int f = 0; f < n; f++) {
+            memcpy(kps + (size_t)capacity * f, bk + sizeof(mage_keypoint) * (size_t)cap * f, sizeof(mage_keypoint) * (size_t)cap);
+            memcpy(desc + (size_t)32 * capacity * f, bd + (size_t)32 * cap * f, (size_t)32 * cap);
+        }
+        memcpy(counts, h->h_back + (h->off_stage_counts - h->off_stage_kps), sizeof(int) * n);
+        const int* st = reinterpret_cast<const int*>(h->h_back + span_al);
+        for (int f = 0; f < n; f++) MAGE_REQUIRE(st[f] == 0, MAGE_ERR_OVERFLOW, "frame %d: candidate list overflow", f);
+        return MAGE_OK;
+    }
     if (cap == capacity) {
         MAGE_CUDA_TRY(cudaMemcpyAsync(kps, d_kps, sizeof(mage_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, s));
         MAGE_CUDA_TRY(cudaMemcpyAsync(desc, d_desc, (size_t)32 * cap * n, cudaMemcpyDeviceToHost, s));

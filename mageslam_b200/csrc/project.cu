@@ -128,17 +128,26 @@ extern "C" int mage_project_map_points(const mage_projection_params* params, con
     uint8_t* d = nullptr;
     MAGE_CUDA_TRY(pool_malloc_async(reinterpret_cast<void**>(&d), total, s));
     int rc = MAGE_OK;
-    cudaError_t e = cudaMemcpyAsync(d + o_pts, points, sizeof(mage_map_point) * n, cudaMemcpyHostToDevice, s);
+    // the map points go up from, and the three result arrays come back into, ONE pinned staging buffer laid out like the device scratch
+    // (a copy between the device and a caller's pageable array is a staged, synchronous transfer of the driver: four of them per call before)
+    PinnedStage st = stage_acquire(total);
+    if (!st.p) { cudaFreeAsync(d, s); MAGE_REQUIRE(false, MAGE_ERR_CUDA, "mage_project_map_points: no pinned staging memory"); }
+    memcpy(st.p + o_pts, points, sizeof(mage_map_point) * n);
+    cudaError_t e = cudaMemcpyAsync(d + o_pts, st.p + o_pts, sizeof(mage_map_point) * n, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
         rc = mage_project_map_points_device(params, reinterpret_cast<const mage_map_point*>(d + o_pts), n, reinterpret_cast<mage_keypoint*>(d + o_kps),
                                             reinterpret_cast<float*>(d + o_dep), d + o_flg, cuda_stream);
     }
-    if (e == cudaSuccess && rc == MAGE_OK) e = cudaMemcpyAsync(out_kps, d + o_kps, sizeof(mage_keypoint) * n, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && rc == MAGE_OK && out_depth) e = cudaMemcpyAsync(out_depth, d + o_dep, sizeof(float) * n, cudaMemcpyDeviceToHost, s);
-    if (e == cudaSuccess && rc == MAGE_OK) e = cudaMemcpyAsync(out_flags, d + o_flg, (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess && rc == MAGE_OK) e = cudaMemcpyAsync(st.p + o_kps, d + o_kps, total - o_kps, cudaMemcpyDeviceToHost, s);
     cudaFreeAsync(d, s);
     cudaError_t e2 = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess && rc == MAGE_OK) {
+        memcpy(out_kps, st.p + o_kps, sizeof(mage_keypoint) * n);
+        if (out_depth) memcpy(out_depth, st.p + o_dep, sizeof(float) * n);
+        memcpy(out_flags, st.p + o_flg, (size_t)n);
+    }
+    stage_release(st);
     if (rc != MAGE_OK) return rc;
     MAGE_CUDA_TRY(e);
     return MAGE_OK;
