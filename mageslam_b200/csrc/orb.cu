@@ -133,6 +133,9 @@ __global__ void __launch_bounds__(256) k_resize4(const __grid_constant__ OrbGeom
     const LevelGeom& S = g.lv[l - 1];
     const int f = blockIdx.z;
     const int dx0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    // programmatic dependent launch along the chain of levels: the next level's grid may become resident and set its coefficients up
+    // while this one is still running; it waits below, before it touches the level this grid writes
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (dx0 >= D.w) return;
     int spitch;
     const uint8_t* src = level_ptr(g, b, f, l - 1, spitch);
@@ -152,6 +155,7 @@ __global__ void __launch_bounds__(256) k_resize4(const __grid_constant__ OrbGeom
         o1[p] = (sb1 - base >= 4) ? base + 4 : base;             // the second word is only touched when a tap lies in it (never past the row)
     }
     const int dyb = blockIdx.y * (8 * kResizeRows) + threadIdx.y;
+    asm volatile("griddepcontrol.wait;" ::: "memory");          // the source level is complete and visible (no-op for a plain launch)
 #pragma unroll
     for (int k = 0; k < kResizeRows; k++) {
         const int dy = dyb + 8 * k;
@@ -1833,12 +1837,25 @@ static int orb_launch(mage_orb_t h, const OrbBuffers& bufs, int n, mage_keypoint
     MAGE_CUDA_TRY(cudaMemsetAsync(bufs.cand_count, 0, sizeof(int) * kMaxLevels * h->max_batch * 2 + sizeof(int) * h->max_batch, s));
     {
         ProfScope ps(PROF_RESIZE, s);       // the L-1 chained launches are timed as one group
+        bool prev_fast = false;
         for (int l = 1; l < g.nlevels; l++) {
             dim3 block(32, 8);
             // a pair of adjacent output pixels must find its four taps inside two aligned words: source step <= 3 pixels
             const bool fast = (double)g.lv[l - 1].w / g.lv[l].w <= 3.0 && g.lv[l - 1].w >= 8;
-            if (fast) k_resize4<<<dim3(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 8 * kResizeRows), n), block, 0, s>>>(g, bufs, l);
+            if (fast) {
+                // levels 2.. follow a k_resize4 launch: programmatic dependent launch overlaps their launch latency and set-up with the
+                // tail of the level before (seven dependent launches of a few microseconds each are a third of a one-frame call)
+                static const bool pdl_on = !(getenv("MAGE_ORB_PDL") && atoi(getenv("MAGE_ORB_PDL")) == 0);
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 8 * kResizeRows), n); cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+                cudaLaunchAttribute at{};
+                at.id = cudaLaunchAttributeProgrammaticStreamSerialization; at.val.programmaticStreamSerializationAllowed = 1;
+                const bool dep = pdl_on && prev_fast && l >= 2;
+                cfg.attrs = dep ? &at : nullptr; cfg.numAttrs = dep ? 1 : 0;
+                MAGE_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_resize4, g, bufs, l));
+            }
             else k_resize<<<dim3(div_up(g.lv[l].w, 128), div_up(g.lv[l].h, 8), n), block, 0, s>>>(g, bufs, l);
+            prev_fast = fast;
         }
     }
     // fork: the blurred pyramid is only read by the descriptor stage, so it is produced on a second stream while FAST and the
