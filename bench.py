@@ -885,20 +885,30 @@ def bench_config5(args, world, rank, dist):
         ba_out["seconds"] = time.perf_counter() - tb
 
     dev_index = torch.cuda.current_device()
-    t0 = time.perf_counter()
-    th = threading.Thread(target=mapping_thread)
-    th.start()
-    kp = m = 0
-    nb = frames_n // B
-    for k in range(nb):
-        fe.Submit(frames[k * B:(k + 1) * B], outs2[k & 1])
-        if k:
-            fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(k - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
-    fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(nb - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
-    t_frames = time.perf_counter() - t0
-    th.join()
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    # the pass is short (10 ms for 256 frames): it is run three times and the pass with the median wall time is reported, so that a
+    # one-off stall of the box (seen once: 69 ms) does not become the number
+    passes = []
+    for rep in range(3):
+        if dist is not None:
+            dist.barrier()
+        fe.Reset()
+        t0 = time.perf_counter()
+        th = threading.Thread(target=mapping_thread)
+        th.start()
+        kp = m = 0
+        nb = frames_n // B
+        for k in range(nb):
+            fe.Submit(frames[k * B:(k + 1) * B], outs2[k & 1])
+            if k:
+                fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(k - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
+        fe.Wait(); _, _, cnt, _, mc = fe.views(outs2[(nb - 1) & 1]); kp += int(cnt.sum()); m += int(mc.sum())
+        t_frames = time.perf_counter() - t0
+        th.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        passes.append((dt, t_frames, dict(ba_out), kp, m))
+    passes.sort(key=lambda q: q[0])
+    dt, t_frames, ba_out, kp, m = passes[1]
     means, iters, t_ba = ba_out["means"], ba_out["iters"], ba_out["seconds"]
     t = torch.tensor([dt, t_frames], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -906,7 +916,7 @@ def bench_config5(args, world, rank, dist):
     dt, t_frames = float(t[0].item()), float(t[1].item())
     return {"metric": "config5_frames_per_sec_1280x720_with_local_ba", "value": world * frames_n / dt, "unit": "frames/s", "higher_is_better": True, "scaling": "weak",
             "config": {"workload": "one 1280x720 synthetic sequence per GPU (2000 keypoints/frame), ORB extract + match per frame + a fresh local-BA window (10 KF / 2000 pts / 8000 obs, 10 LM iterations) every %d frames, stepped on a second host thread like the reference's mapping thread" % every,
-                       "frames_per_gpu": frames_n, "sequences": world, "timer": "host clock, host buffers in and out, max over ranks"},
+                       "frames_per_gpu": frames_n, "sequences": world, "timer": "host clock, host buffers in and out, max over ranks; the median of three passes"},
             "ba_lm_iters_per_s": world * iters / dt, "frontend_only_frames_per_s": world * frames_n / t_frames,
             "ba_only_lm_iters_per_s": world * iters / max(t_ba, 1e-9), "ba_thread_ms": 1e3 * t_ba, "frontend_thread_ms": 1e3 * t_frames, "keypoints_per_frame": kp / frames_n, "matches_per_frame": m / frames_n,
             "ba_mean_sq_error": float(np.mean(means)), "wall_s": dt,

@@ -123,12 +123,14 @@ inline PinnedStage stage_acquire(size_t bytes)
     PinnedStage st;
     {
         std::lock_guard<std::mutex> lk(P.mu);
-        for (size_t i = 0; i < P.free.size(); i++)
-            if (P.free[i].cap >= bytes) { st = P.free[i]; P.free.erase(P.free.begin() + i); return st; }
-        if (!P.free.empty()) { st = P.free.back(); P.free.pop_back(); }
+        size_t best = P.free.size();
+        for (size_t i = 0; i < P.free.size(); i++)                // best fit: a small request must not take the one large buffer
+            if (P.free[i].cap >= bytes && (best == P.free.size() || P.free[i].cap < P.free[best].cap)) best = i;
+        if (best < P.free.size()) { st = P.free[best]; P.free.erase(P.free.begin() + best); return st; }
     }
-    if (st.p) { cudaFreeHost(st.p); st = PinnedStage(); }     // too small: grow
-    const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 20);
+    // nothing large enough: a new buffer (buffers that are too small stay pooled -- cudaFreeHost synchronises the device, which a
+    // latency path must never do on somebody else's behalf)
+    const size_t cap = align_up(std::max<size_t>(bytes + bytes / 4, 1 << 20), 1 << 20);
     if (cudaHostAlloc(reinterpret_cast<void**>(&st.p), cap, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); st.p = nullptr; return st; }
     st.cap = cap;
     return st;
@@ -137,9 +139,17 @@ inline void stage_release(PinnedStage st)
 {
     if (!st.p) return;
     PinnedPool& P = pinned_pool();
-    std::lock_guard<std::mutex> lk(P.mu);
-    if (P.free.size() < 16) P.free.push_back(st);
-    else cudaFreeHost(st.p);
+    PinnedStage drop;
+    {
+        std::lock_guard<std::mutex> lk(P.mu);
+        P.free.push_back(st);
+        if (P.free.size() > 48) {                                 // far more than any call pattern keeps in flight: let the smallest one go
+            size_t k = 0;
+            for (size_t i = 1; i < P.free.size(); i++) if (P.free[i].cap < P.free[k].cap) k = i;
+            drop = P.free[k]; P.free.erase(P.free.begin() + k);
+        }
+    }
+    if (drop.p) cudaFreeHost(drop.p);
 }
 
 // Optional per-kernel timing (CUDA events on the launching stream), used by bench.py for the live roofline figure.

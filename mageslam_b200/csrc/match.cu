@@ -416,10 +416,11 @@ __device__ __forceinline__ unsigned resolve_best(unsigned best, unsigned second,
     return best;
 }
 
-__global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__ jobs, const unsigned* __restrict__ stats, int stride, int min_diff,
+constexpr int kEmitThreads = 1024;      // one CTA per pair walks the queries in rounds of two dependent global round trips each: 2 rounds for 2000, not 8
+__global__ void __launch_bounds__(kEmitThreads) k_match_emit(const MatchJob* __restrict__ jobs, const unsigned* __restrict__ stats, int stride, int min_diff,
                                                     mage_dmatch* __restrict__ out, int out_cap, int* __restrict__ out_count)
 {
-    __shared__ int warp_sum[8];
+    __shared__ int warp_sum[kEmitThreads / 32];
     __shared__ int base;
     const int pair = blockIdx.x;
     const MatchJob& job = jobs[pair];
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(256) k_match_emit(const MatchJob* __restrict__
         off += __popc(m & ((1u << lane) - 1));
         if (ok && off < out_cap) { mage_dmatch dm; dm.query_idx = a; dm.train_idx = (int)(key & 0xFFFF); dm.distance = (float)(key >> 16); o[off] = dm; }
         __syncthreads();
-        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 8; w++) tot += warp_sum[w]; base += tot; }
+        if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += warp_sum[w]; base += tot; }
         __syncthreads();
     }
     if (threadIdx.x == 0) out_count[pair] = min(base, out_cap);
@@ -580,7 +581,7 @@ static int match_launch(mage_matcher_t m, int n_pairs, int max_q, int max_t, int
     MAGE_CUDA_TRY(cudaMemcpyAsync(m->d_jobs, m->h_jobs, sizeof(MatchJob) * n_pairs, cudaMemcpyHostToDevice, s));
     MAGE_CUDA_TRY(cudaMemsetAsync(m->d_best, 0xFF, sizeof(unsigned) * 4 * (size_t)n_pairs * m->max_desc, s));
     { ProfScope ps(PROF_MATCH_DIR, s); MAGE_CUDA_TRY(launch_match_dir(m->d_jobs, m->d_best, m->max_desc, max_q, max_t, n_pairs, max_hamming, s)); }
-    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, min_diff, d_out, out_cap, d_counts); }
+    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, kEmitThreads, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, min_diff, d_out, out_cap, d_counts); }
     MAGE_CUDA_TRY(cudaGetLastError());
     return MAGE_OK;
 }
@@ -655,7 +656,7 @@ extern "C" int mage_match_run_jobs(mage_matcher_t m, int first_pair, int n_pairs
     unsigned* best = m->d_best + (size_t)first_pair * 4 * m->max_desc;
     MAGE_CUDA_TRY(cudaMemsetAsync(best, 0xFF, sizeof(unsigned) * 4 * (size_t)n_pairs * m->max_desc, s));
     { ProfScope ps(PROF_MATCH_DIR, s); MAGE_CUDA_TRY(launch_match_dir(m->d_jobs + first_pair, best, m->max_desc, cap, cap, n_pairs, max_hamming, s)); }
-    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, 256, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, min_diff, d_matches, capacity, d_match_counts); }
+    { ProfScope ps(PROF_MATCH_EMIT, s); k_match_emit<<<n_pairs, kEmitThreads, 0, s>>>(m->d_jobs + first_pair, best, m->max_desc, min_diff, d_matches, capacity, d_match_counts); }
     MAGE_CUDA_TRY(cudaGetLastError());
     return MAGE_OK;
 }
@@ -712,7 +713,7 @@ extern "C" int mage_indexed_match(mage_matcher_t m, const uint8_t* descA, int nA
     if (e == cudaSuccess) {
         const int nmax = nA > nB ? nA : nB;
         k_indexed_best<<<dim3(div_up(nmax, 8), 2), 256, 0, s>>>(m->d_jobs, d_off0, d_c0, d_off1, d_c1, m->d_best, m->max_desc, max_hamming);
-        k_match_emit<<<1, 256, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, min_diff, dOut, m->max_desc, dCnt);
+        k_match_emit<<<1, kEmitThreads, 0, s>>>(m->d_jobs, m->d_best, m->max_desc, min_diff, dOut, m->max_desc, dCnt);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(m->h_count, dCnt, sizeof(int), cudaMemcpyDeviceToHost, s);
