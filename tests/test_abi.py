@@ -73,3 +73,6 @@ def test_tensor_core_and_tma_kernels_are_in_the_library():
     assert match and match[0]["UTCIMMA"] == 8 and match[0]["LDTM"] >= 1 and match[0]["UTCBAR"] >= 1 and match[0]["UTCATOMSWS"] >= 2
     tma = [v for k, v in cnt.items() if "k_fast_tma" in k]
     assert tma and tma[0]["UTMALDG"] >= 1
+    # the resize chain runs under programmatic dependent launch: griddepcontrol.launch_dependents / .wait are in the level kernel
+    rs = [v for k, v in cnt.items() if "k_resize4" in k]
+    assert rs and rs[0]["PREEXIT"] >= 1 and rs[0]["ACQBULK"] >= 1

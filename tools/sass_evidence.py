@@ -4,7 +4,7 @@ the evidence B200_PROFILING.md asks for that a kernel really uses the tensor cor
 import collections, os, re, subprocess, sys
 
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mageslam_b200", "libmage_b200.so")
-PAT = re.compile(r"UTCIMMA|UTCHMMA|UTCQMMA|LDTM|STTM|UTCBAR|UTCATOMSWS|UTMALDG|UBLKCP|SYNCS|FENCE\.VIEW\.ASYNC")
+PAT = re.compile(r"UTCIMMA|UTCHMMA|UTCQMMA|LDTM|STTM|UTCBAR|UTCATOMSWS|UTMALDG|UBLKCP|SYNCS|FENCE\.VIEW\.ASYNC|PREEXIT|ACQBULK")
 
 
 def collect(path):
@@ -26,7 +26,8 @@ if __name__ == "__main__":
     cnt = collect(lib)
     print("# Blackwell-specific SASS per kernel (`cuobjdump -sass %s`)\n" % os.path.basename(lib))
     print("`UTCIMMA` = tcgen05.mma kind::i8, `LDTM` = tcgen05.ld, `UTCBAR` = tcgen05.commit, `UTCATOMSWS` = tcgen05.alloc / dealloc, "
-          "`UTMALDG` = cp.async.bulk.tensor (TMA), `SYNCS.*` = mbarrier operations, `FENCE.VIEW.ASYNC` = fence.proxy.async.\n")
+          "`UTMALDG` = cp.async.bulk.tensor (TMA), `SYNCS.*` = mbarrier operations, `FENCE.VIEW.ASYNC` = fence.proxy.async, "
+          "`PREEXIT` / `ACQBULK` = griddepcontrol.launch_dependents / .wait (programmatic dependent launch).\n")
     print("| kernel | mnemonics (static count) |\n|---|---|")
     for k, v in sorted(cnt.items()):
         name = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip().split("(")[0]
