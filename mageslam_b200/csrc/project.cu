@@ -125,13 +125,14 @@ extern "C" int mage_project_map_points(const mage_projection_params* params, con
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
     const size_t o_pts = 0, o_kps = align_up(o_pts + sizeof(mage_map_point) * n, 256), o_dep = align_up(o_kps + sizeof(mage_keypoint) * n, 256);
     const size_t o_flg = align_up(o_dep + sizeof(float) * n, 256), total = o_flg + (size_t)n;
-    uint8_t* d = nullptr;
-    MAGE_CUDA_TRY(pool_malloc_async(reinterpret_cast<void**>(&d), total, s));
+    DevStage dsg = dev_stage_acquire(total);                 // pooled device scratch: no allocation per call
+    MAGE_REQUIRE(dsg.p, MAGE_ERR_CUDA, "mage_project_map_points: no device memory for %zu bytes", total);
+    uint8_t* d = dsg.p;
     int rc = MAGE_OK;
     // the map points go up from, and the three result arrays come back into, ONE pinned staging buffer laid out like the device scratch
     // (a copy between the device and a caller's pageable array is a staged, synchronous transfer of the driver: four of them per call before)
     PinnedStage st = stage_acquire(total);
-    if (!st.p) { cudaFreeAsync(d, s); MAGE_REQUIRE(false, MAGE_ERR_CUDA, "mage_project_map_points: no pinned staging memory"); }
+    if (!st.p) { dev_stage_release(dsg); MAGE_REQUIRE(false, MAGE_ERR_CUDA, "mage_project_map_points: no pinned staging memory"); }
     memcpy(st.p + o_pts, points, sizeof(mage_map_point) * n);
     cudaError_t e = cudaMemcpyAsync(d + o_pts, st.p + o_pts, sizeof(mage_map_point) * n, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
@@ -139,8 +140,8 @@ extern "C" int mage_project_map_points(const mage_projection_params* params, con
                                             reinterpret_cast<float*>(d + o_dep), d + o_flg, cuda_stream);
     }
     if (e == cudaSuccess && rc == MAGE_OK) e = cudaMemcpyAsync(st.p + o_kps, d + o_kps, total - o_kps, cudaMemcpyDeviceToHost, s);
-    cudaFreeAsync(d, s);
     cudaError_t e2 = cudaStreamSynchronize(s);
+    dev_stage_release(dsg);
     if (e == cudaSuccess) e = e2;
     if (e == cudaSuccess && rc == MAGE_OK) {
         memcpy(out_kps, st.p + o_kps, sizeof(mage_keypoint) * n);

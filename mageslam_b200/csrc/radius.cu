@@ -196,17 +196,10 @@ void packed_rtree_rank(const mage_keypoint* kps, int n, std::vector<int>& rank)
 
 struct mage_spatial_index_s {
     int n = 0;
-    DeviceArena arena;
+    DevStage mem;                   // coordinates, octaves and ranks of the indexed key points (from the process-wide scratch pool: the index is
+                                    // rebuilt for every analysed frame, so its set-up cost is per-frame latency)
     RadiusIndexDev dev{};
     std::vector<int> rank;
-    // per-call scratch (grown on demand)
-    uint8_t* d_scratch = nullptr; size_t scratch_bytes = 0; bool scratch_pooled = false;
-    void free_scratch()
-    {
-        if (d_scratch) { if (scratch_pooled) cudaFreeAsync(d_scratch, stream); else cudaFree(d_scratch); }
-        d_scratch = nullptr;
-    }
-    cudaStream_t stream = nullptr;
 };
 
 extern "C" int mage_spatial_index_create(const mage_keypoint* keypoints, int n, mage_spatial_index_s** out)
@@ -218,21 +211,23 @@ extern "C" int mage_spatial_index_create(const mage_keypoint* keypoints, int n, 
     mage_spatial_index_s* ix = new mage_spatial_index_s();
     ix->n = n;
     packed_rtree_rank(keypoints, n, ix->rank);
-    // one pooled arena, one packed upload: the index is rebuilt for every analysed frame, so its set-up cost is per-frame latency
-    DeviceArena& A = ix->arena;
-    A.pooled = true;
+    // one pooled buffer, one packed upload
     const size_t cnt = (size_t)std::max(n, 1);
-    size_t ox = A.reserve(4 * cnt, 16), oy = A.reserve(4 * cnt, 16), oo = A.reserve(4 * cnt, 16), orank = A.reserve(4 * cnt, 16);
-    std::vector<uint8_t> host(A.used);
+    size_t used = 0;
+    auto take = [&](size_t bytes) { used = align_up(used, 16); const size_t o = used; used += bytes; return o; };
+    const size_t ox = take(4 * cnt), oy = take(4 * cnt), oo = take(4 * cnt), orank = take(4 * cnt);
+    std::vector<uint8_t> host(used);
     float* x = reinterpret_cast<float*>(host.data() + ox); float* y = reinterpret_cast<float*>(host.data() + oy);
     int* oc = reinterpret_cast<int*>(host.data() + oo);
     for (int i = 0; i < n; i++) { x[i] = keypoints[i].x; y[i] = keypoints[i].y; oc[i] = keypoints[i].octave; }
     if (n) memcpy(host.data() + orank, ix->rank.data(), 4 * (size_t)n);
-    cudaError_t e = A.commit();
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess && n) e = cudaMemcpy(A.base, host.data(), host.size(), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { set_error("mage_spatial_index_create: %s", cudaGetErrorString(e)); A.release(); delete ix; return MAGE_ERR_CUDA; }
-    ix->dev.x = A.at<float>(ox); ix->dev.y = A.at<float>(oy); ix->dev.octave = A.at<int>(oo); ix->dev.rank = A.at<int>(orank); ix->dev.n = n;
+    ix->mem = dev_stage_acquire(used);
+    cudaError_t e = ix->mem.p ? cudaSuccess : cudaErrorMemoryAllocation;
+    if (e == cudaSuccess && n) e = cudaMemcpy(ix->mem.p, host.data(), host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { set_error("mage_spatial_index_create: %s", cudaGetErrorString(e)); dev_stage_release(ix->mem); delete ix; return MAGE_ERR_CUDA; }
+    uint8_t* base = ix->mem.p;
+    ix->dev.x = reinterpret_cast<float*>(base + ox); ix->dev.y = reinterpret_cast<float*>(base + oy);
+    ix->dev.octave = reinterpret_cast<int*>(base + oo); ix->dev.rank = reinterpret_cast<int*>(base + orank); ix->dev.n = n;
     *out = ix;
     return MAGE_OK;
 }
@@ -240,9 +235,7 @@ extern "C" int mage_spatial_index_create(const mage_keypoint* keypoints, int n, 
 extern "C" void mage_spatial_index_destroy(mage_spatial_index_s* ix)
 {
     if (!ix) return;
-    ix->free_scratch();                                      // every match call synchronises before it returns, nothing is in flight
-    if (ix->stream) cudaStreamDestroy(ix->stream);
-    ix->arena.release();
+    dev_stage_release(ix->mem);                              // every match call synchronises before it returns, nothing is in flight
     delete ix;
 }
 
@@ -262,28 +255,22 @@ extern "C" int mage_radius_match(mage_spatial_index_s* ix, const mage_keypoint* 
     *count = 0;
     if (nq == 0 || ix->n == 0) return MAGE_OK;
     MAGE_REQUIRE(target_desc, MAGE_ERR_INVALID, "mage_radius_match: null target descriptors");
-    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : ix->stream;
+    cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : thread_stream();      // (a null result is the default stream: still correct)
     const size_t nT = (size_t)ix->n, nQ = (size_t)nq;
     // scratch layout: query kps | query pos | query mask | query desc | target mask | target desc | almost | tbest | tsecond | out | count
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
     const size_t o_qk = take(sizeof(mage_keypoint) * nQ), o_qp = take(8 * nQ), o_qm = take(nQ), o_qd = take(32 * nQ), o_tm = take(nT), o_td = take(32 * nT);
     const size_t o_al = take(4 * nQ), o_tb = take(4 * nT), o_ts = take(4 * nT), o_out = take(sizeof(mage_dmatch) * nQ), o_cnt = take(4);
-    if (off > ix->scratch_bytes) {
-        ix->free_scratch();
-        ix->scratch_bytes = 0;
-        // stream-ordered pool first (an index lives for one frame, so this allocation is per-frame latency), plain allocation otherwise
-        ix->scratch_pooled = pool_malloc_async(reinterpret_cast<void**>(&ix->d_scratch), off, ix->stream) == cudaSuccess;
-        if (ix->scratch_pooled) MAGE_CUDA_TRY(cudaStreamSynchronize(ix->stream));
-        else { cudaGetLastError(); MAGE_CUDA_TRY(cudaMalloc(&ix->d_scratch, off)); }
-        ix->scratch_bytes = off;
-    }
-    uint8_t* S = ix->d_scratch;
+    // the scratch comes from the process-wide pool (an index lives for one frame: a scratch of its own would be allocated every frame)
+    DevStage ds = dev_stage_acquire(off);
+    MAGE_REQUIRE(ds.p, MAGE_ERR_CUDA, "mage_radius_match: no device memory for %zu bytes of scratch", off);
+    uint8_t* S = ds.p;
     // the inputs are packed into one pinned staging buffer laid out like the scratch (query kps .. target desc are neighbours) and go up in
     // ONE copy, the two target tables are cleared by one memset, matches + count come back in one copy: up to six uploads and two
     // read-backs between the device and the caller's pageable arrays were 60 us of a 107 us call
     PinnedStage st = stage_acquire(off);
-    MAGE_REQUIRE(st.p, MAGE_ERR_CUDA, "mage_radius_match: no pinned staging memory");
+    if (!st.p) { dev_stage_release(ds); MAGE_REQUIRE(false, MAGE_ERR_CUDA, "mage_radius_match: no pinned staging memory"); }
     memcpy(st.p + o_qk, query_kps, sizeof(mage_keypoint) * nQ);
     if (query_pos_override) memcpy(st.p + o_qp, query_pos_override, 8 * nQ);
     if (query_mask) memcpy(st.p + o_qm, query_mask, nQ);
@@ -292,7 +279,7 @@ extern "C" int mage_radius_match(mage_spatial_index_s* ix, const mage_keypoint* 
     memcpy(st.p + o_td, target_desc, 32 * nT);
     cudaError_t e = cudaMemcpyAsync(S + o_qk, st.p + o_qk, o_td + 32 * nT - o_qk, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemsetAsync(S + o_tb, 0xFF, o_ts + 4 * nT - o_tb, s);
-    if (e != cudaSuccess) { stage_release(st); MAGE_CUDA_TRY(e); }
+    if (e != cudaSuccess) { cudaStreamSynchronize(s); stage_release(st); dev_stage_release(ds); MAGE_CUDA_TRY(e); }
     k_radius_best<<<div_up(nq, 8), 256, 0, s>>>(ix->dev, reinterpret_cast<const mage_keypoint*>(S + o_qk), nq,
                                                 query_pos_override ? reinterpret_cast<const float*>(S + o_qp) : nullptr,
                                                 query_mask ? S + o_qm : nullptr, reinterpret_cast<const uint32_t*>(S + o_qd),
@@ -308,7 +295,9 @@ extern "C" int mage_radius_match(mage_spatial_index_s* ix, const mage_keypoint* 
         *count = *reinterpret_cast<const int*>(st.p + o_cnt);
         memcpy(out, st.p + o_out, sizeof(mage_dmatch) * (size_t)std::max(0, std::min(*count, nq)));
     }
+    if (e != cudaSuccess) cudaStreamSynchronize(s);          // nothing of this call may still be running when the buffers go back
     stage_release(st);
+    dev_stage_release(ds);
     MAGE_CUDA_TRY(e);
     return MAGE_OK;
 }
