@@ -40,8 +40,11 @@ def test_no_cpu_fallback_without_a_device():
     from mageslam_b200.bundler import BundlerLib
     from mageslam_b200.matcher import Matcher
     from mageslam_b200.orb import FeatureExtractorSettings, OrbFeatureDetector
+    from mageslam_b200.tracking import OptimizeCameraPose
+    eye = np.eye(3, dtype=np.float32).reshape(9)
     for make in (lambda: OrbFeatureDetector(FeatureExtractorSettings.tier()).Process(np.zeros((480, 640), np.uint8)),
-                 lambda: Matcher(100, 1), lambda: BundlerLib()):
+                 lambda: Matcher(100, 1), lambda: BundlerLib(),
+                 lambda: OptimizeCameraPose(np.zeros(3), eye, [320, 240, 500, 500], np.ones((4, 3)), np.ones((4, 2)), np.ones(4), 3, 25.0, 2.0)):
         with pytest.raises(MageError) as ei:
             make()
         assert ei.value.code == MAGE_ERR_CUDA
