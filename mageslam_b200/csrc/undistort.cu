@@ -98,14 +98,23 @@ extern "C" int mage_undistort_keypoints(mage_keypoint* keypoints, int n, const m
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_error("no CUDA device: keypoint undistortion has no CPU fallback"); return MAGE_ERR_CUDA; }
     cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-    mage_keypoint* d = nullptr;
-    MAGE_CUDA_TRY(pool_malloc_async(reinterpret_cast<void**>(&d), sizeof(mage_keypoint) * (size_t)n, s));
-    cudaError_t e = cudaMemcpyAsync(d, keypoints, sizeof(mage_keypoint) * (size_t)n, cudaMemcpyHostToDevice, s);
+    // pooled device scratch and pinned staging (one DMA each way instead of two staged copies between the device and the caller's
+    // pageable array; no allocation per call): this runs once per analysed frame, right after DetectAndCompute
+    const size_t bytes = sizeof(mage_keypoint) * (size_t)n;
+    DevStage dsg = dev_stage_acquire(bytes);
+    MAGE_REQUIRE(dsg.p, MAGE_ERR_CUDA, "mage_undistort_keypoints: no device memory for %zu bytes", bytes);
+    PinnedStage st = stage_acquire(bytes);
+    if (!st.p) { dev_stage_release(dsg); MAGE_REQUIRE(false, MAGE_ERR_CUDA, "mage_undistort_keypoints: no pinned staging memory"); }
+    mage_keypoint* d = reinterpret_cast<mage_keypoint*>(dsg.p);
+    memcpy(st.p, keypoints, bytes);
+    cudaError_t e = cudaMemcpyAsync(d, st.p, bytes, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) rc = mage_undistort_keypoints_device(d, nullptr, 1, n, distorted, undistorted, cuda_stream);
-    if (e == cudaSuccess && rc == MAGE_OK) e = cudaMemcpyAsync(keypoints, d, sizeof(mage_keypoint) * (size_t)n, cudaMemcpyDeviceToHost, s);
-    cudaFreeAsync(d, s);
+    if (e == cudaSuccess && rc == MAGE_OK) e = cudaMemcpyAsync(st.p, d, bytes, cudaMemcpyDeviceToHost, s);
     cudaError_t e2 = cudaStreamSynchronize(s);
     if (e == cudaSuccess) e = e2;
+    if (e == cudaSuccess && rc == MAGE_OK) memcpy(keypoints, st.p, bytes);
+    stage_release(st);
+    dev_stage_release(dsg);
     if (rc != MAGE_OK) return rc;
     MAGE_CUDA_TRY(e);
     return MAGE_OK;
